@@ -1,0 +1,205 @@
+/* vfm_b200.h -- C ABI of the B200-native Variational Factorization Machine step.
+ *
+ * The reference (jilljenn/vae) has no FFI for this path: its boundary is the
+ * PyTorch model API used by the training loops of vfm-torch.py and
+ * vfm-tomasrch.py.  This library is what a binding for that path would call;
+ * each entry point names the reference lines it replaces.  The host-side
+ * mirror of the reference's `class CF` lives in vae_b200/ (Python, ctypes).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked host;
+ *     the library allocates nothing persistent and frees nothing;
+ *   - tables are row-major contiguous fp32, base pointers 16-byte aligned:
+ *       bias   [R,2]  = [mean, raw scale]            (vfm-torch.py:152, vfm-tomasrch.py:229)
+ *       entity [R,2d] = [mean(d) | raw scale(d)]     (vfm-torch.py:153, vfm-tomasrch.py:251)
+ *   - all work is enqueued on the given stream; no call synchronises, so a
+ *     whole step can be captured into a CUDA graph;
+ *   - return 0 on success, otherwise a cudaError_t or a VFMB_E* code;
+ *     vfmb_last_error() gives the message (thread-local).  Nothing throws.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with the CUDA error.
+ */
+#ifndef VFM_B200_H
+#define VFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFMB_MAX_FIELDS 8
+
+#define VFMB_EINVAL 10001 /* bad argument (message says which)              */
+#define VFMB_ESHAPE 10002 /* unsupported width / field count                */
+#define VFMB_ESPACE 10003 /* workspace too small                            */
+
+enum { VFMB_GAUSSIAN = 0, VFMB_BERNOULLI = 1 };           /* vfm-torch.py:267-270 */
+enum { VFMB_LINK_ABS = 0, VFMB_LINK_SOFTPLUS = 1 };       /* vfm-torch.py:125-126 */
+enum { VFMB_ADAM_TOUCHED = 0, VFMB_GRAD_ONLY = 1 };       /* backward epilogue     */
+
+typedef void* vfmb_stream; /* cudaStream_t */
+
+/* Problem description shared by every call. */
+typedef struct vfmb_config {
+    int32_t B;            /* samples in the batch                                  */
+    int32_t F;            /* fields (columns of x), 2..VFMB_MAX_FIELDS             */
+    int32_t d;            /* embedding size                                        */
+    int32_t R;            /* table rows                                            */
+    int32_t S;            /* variational samples (vfm-torch.py:19), currently 1    */
+    int32_t likelihood;   /* VFMB_GAUSSIAN | VFMB_BERNOULLI                        */
+    int32_t link;         /* VFMB_LINK_*                                           */
+    int32_t n_classes;    /* KL weighting classes (<= F)                           */
+    /* class(u) = #{i : class_bound[i] <= u}.  vfm-torch.py:316 is {N+1} with
+     * sizes {N,M} (the `<= N` selection); vfm-tomasrch.py:574-587 is the field
+     * offsets {G_0, G_0+G_1, ...} with sizes {G_g}.                              */
+    int32_t class_bound[VFMB_MAX_FIELDS];
+    float class_size[VFMB_MAX_FIELDS];
+    float n_train;        /* nb_train_samples (vfm-torch.py:91,359)                */
+    uint64_t seed;        /* Philox key                                            */
+} vfmb_config;
+
+/* Parameter tables and Adam state.  m/v may be NULL for forward-only use. */
+typedef struct vfmb_tables {
+    float* bias;      float* bias_m;   float* bias_v;    /* [R,2]  */
+    float* entity;    float* entity_m; float* entity_v;  /* [R,2d] */
+    const float* train_counts;                           /* [R] bincount(X_train) as fp32
+                                                            (vfm-torch.py:89, vfm-tomasrch.py:182) */
+    /* scalar parameter block + Adam state, layout per variant (see below) */
+    float* scalars;   float* scalars_m; float* scalars_v;
+    /* device step counter: int32[1], number of Adam steps already applied */
+    int32_t* adam_step;
+} vfmb_tables;
+
+/* sampled variant scalar block (vfm-torch.py:136-138): */
+enum { VFMB_S_ALPHA = 0, VFMB_S_GB_MEAN = 1, VFMB_S_GB_SCALE = 2, VFMB_S_COUNT = 4 };
+/* closed-form variant scalar block (vfm-tomasrch.py:194-248): five scalars,
+ * then per group g: bias prior mean, bias prior scale, then entity prior
+ * mean[d] and scale[d]; use vfmb_closed_scalar_count / offsets below. */
+enum { VFMB_C_ALPHA = 0, VFMB_C_GB_MEAN = 1, VFMB_C_GB_SCALE = 2, VFMB_C_GB_PRIOR_MEAN = 3,
+       VFMB_C_GB_PRIOR_SCALE = 4, VFMB_C_GROUP_BASE = 8 };
+/* offsets inside the closed-form scalar block */
+int32_t vfmb_closed_off_bias_prior_mean(int32_t G, int32_t d, int32_t g);
+int32_t vfmb_closed_off_bias_prior_scale(int32_t G, int32_t d, int32_t g);
+int32_t vfmb_closed_off_entity_prior_mean(int32_t G, int32_t d, int32_t g);
+int32_t vfmb_closed_off_entity_prior_scale(int32_t G, int32_t d, int32_t g);
+int32_t vfmb_closed_scalar_count(int32_t G, int32_t d);
+
+typedef struct vfmb_adam {
+    /* torch.optim.Adam hyper-parameters (vfm-torch.py:339, vfm-tomasrch.py:518; betas
+     * (0.9, 0.999), eps 1e-8 by default).  Doubles, because torch forms 1-beta1, 1-beta2
+     * and the bias corrections in double before rounding to fp32 -- (1 - 0.999f) is off
+     * by 1.3e-5 relative. */
+    double lr, beta1, beta2, eps;
+} vfmb_adam;
+
+/* The batch plan: replaces the torch.unique calls of vfm-torch.py:190-192 and
+ * vfm-tomasrch.py:537-545.  All arrays are caller-allocated device memory of
+ * the capacities given by vfmb_plan_capacity().  Integer results are
+ * bit-identical to torch.unique(sorted=True, return_inverse, return_counts). */
+typedef struct vfmb_plan {
+    int32_t* uniq;       /* [U_cap]   sorted unique row ids                        */
+    int32_t* inverse;    /* [B*F]     rank of x[n,f] in uniq                       */
+    int32_t* seg_off;    /* [U_cap+1] segment offsets; counts[u]=seg_off[u+1]-seg_off[u] */
+    int32_t* occ;        /* [B*F]     occurrence ids n*F+f grouped by rank, ascending inside */
+    int32_t* item_first; /* [U_cap+1] first work item of each unique row            */
+    int32_t* item_row;   /* [W_cap]   unique rank of each work item                 */
+    int32_t* heavy_done; /* [U_cap]   arrival counters for multi-item rows          */
+    float* z;            /* [VFMB_MAX_FIELDS] per-column normaliser Z_f             */
+    int32_t* meta;       /* [8] 0:U 1:W 2:error flag (id out of range) 3..: reserved */
+} vfmb_plan;
+
+typedef struct vfmb_plan_capacity_t {
+    int64_t u_cap, w_cap, workspace_bytes;
+    int32_t chunk;       /* occurrences per work item */
+} vfmb_plan_capacity_t;
+
+int vfmb_plan_capacity(int32_t B, int32_t F, int32_t R, vfmb_plan_capacity_t* out /*host*/);
+
+/* Build the plan for one batch.  x: int64 [B,F] global row ids (the reference's
+ * LongTensor batch, vfm-torch.py:88,351).  train_counts is only used for the
+ * per-column normalisers Z_f = sum_{u in uniq(x[:,f])} cnt_f(u)/cnt_train(u)
+ * (vfm-torch.py:305-306, vfm-tomasrch.py:578-581). */
+int vfmb_plan_build(const vfmb_config* cfg /*host*/, const int64_t* x, const float* train_counts,
+                    const vfmb_plan* plan /*host struct of device ptrs*/, void* workspace,
+                    size_t workspace_bytes, vfmb_stream stream);
+
+/* Scratch + outputs of one step.  Capacities: vs [U_cap*d], ws [U_cap],
+ * partials [vfmb_partials_floats()], pred/mean/resid [B], stats [VFMB_STATS]. */
+typedef struct vfmb_step_io {
+    const float* y;          /* [B] targets (NULL: forward without likelihood terms)  */
+    const float* eps_global; /* [S]     injected N(0,1) draws, or NULL -> Philox      */
+    const float* eps_bias;   /* [S,U]   indexed by unique rank (vfm-torch.py:239)     */
+    const float* eps_entity; /* [S,U,d] (vfm-torch.py:241)                            */
+    float* vs;               /* scratch: sampled factor rows  [U_cap,d]               */
+    float* ws;               /* scratch: sampled biases       [U_cap]                 */
+    float* msg;              /* scratch [B,d], only F>2 (may be NULL for F==2)        */
+    float* pred;             /* [B] unscaled_pred (vfm-torch.py:265)                  */
+    float* mean;             /* [B] likelihood mean: pred or sigmoid(pred) (:363)     */
+    float* resid;            /* [B] dloss/dpred                                       */
+    double* partials;        /* scratch for deterministic reductions                  */
+    int32_t* counters;       /* [8] zero-initialised once by the caller               */
+    float* stats;            /* [VFMB_STATS] see enum                                 */
+    float* grad_bias;        /* VFMB_GRAD_ONLY: dense [R,2]  (touched rows written)   */
+    float* grad_entity;      /* VFMB_GRAD_ONLY: dense [R,2d]                          */
+    float* grad_scalars;     /* VFMB_GRAD_ONLY: [scalar count]                        */
+} vfmb_step_io;
+
+enum { VFMB_ST_LOSS = 0,      /* n_train*mean(nll) + kl           (vfm-torch.py:359) */
+       VFMB_ST_NLL_MEAN = 1,  /* mean over batch of -log_prob                        */
+       VFMB_ST_KL = 2,        /* KL(global) + rescaled row KL     (vfm-torch.py:320-324) */
+       VFMB_ST_SUM_RESID = 3, VFMB_ST_SUM_SQERR = 4, VFMB_ST_KL_ROWS = 5,
+       VFMB_ST_W0 = 6, VFMB_ST_U = 7, VFMB_STATS = 16 };
+
+/* size (in doubles) of vfmb_step_io.partials for this problem */
+int64_t vfmb_partials_doubles(const vfmb_config* cfg /*host*/);
+
+/* Sampled ELBO, forward: gather of the unique rows, reparameterised draw,
+ * FM interaction, likelihood and KL -- vfm-torch.py:200-324 (+ :359 when y given). */
+int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                         const vfmb_step_io* io, vfmb_stream stream);
+
+/* Sampled ELBO, backward: deterministic segmented reduction over the sorted
+ * occurrence list, chain rule to (mean, raw scale) + KL gradient, then either
+ * Adam on the touched rows (mode VFMB_ADAM_TOUCHED) or dense gradient output
+ * (VFMB_GRAD_ONLY).  Replaces loss.backward(); optimizer.step() of
+ * vfm-torch.py:368-370.  io->resid must hold dloss/dpred (written by the
+ * forward when y was given, or supplied by the caller's autograd). */
+int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                          const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                          float kl_grad_scale, vfmb_stream stream);
+
+/* Dense Adam sweep over whole tables given dense gradients: the reference's
+ * torch.optim.Adam semantics (every row moves every step). */
+int vfmb_adam_dense(float* p, float* m, float* v, const float* g, int64_t n,
+                    const vfmb_adam* adam, const int32_t* adam_step /*device*/,
+                    vfmb_stream stream);
+int vfmb_adam_step_advance(int32_t* adam_step, vfmb_stream stream);
+
+/* Closed-form Gaussian variant (vfm-tomasrch.py:323-453 forward,
+ * :569-594 loss/backward/Adam).  Same plan, same scratch. */
+int vfmb_closed_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                        const vfmb_step_io* io, vfmb_stream stream);
+int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                         const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                         vfmb_stream stream);
+
+/* Posterior-mean prediction without a plan: global + sum of bias means +
+ * product over fields of factor means (vfm-torch.py:248-259 last_logits,
+ * vfm-tomasrch.py:342-348). */
+int vfmb_predict_mean(const vfmb_config* cfg, const float* bias, const float* entity,
+                      float global_bias, const int64_t* x, float* out, vfmb_stream stream);
+
+/* The N(0,1) draws the Philox path uses for `step` (for tests / reproducibility):
+ * eps_bias [U], eps_entity [U,d] for the given unique row ids. */
+int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, int32_t U, int32_t step,
+                        float* eps_global, float* eps_bias, float* eps_entity, vfmb_stream stream);
+
+const char* vfmb_last_error(void);
+int vfmb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFM_B200_H */

@@ -1,0 +1,333 @@
+"""Parity of the CUDA sampled-ELBO path (through the C ABI) with the oracle:
+golden vectors of the unmodified reference, the torch port and the fp64 maths.
+
+Tolerances (north_star): integer plan bit-exact; fp32 predictions / ELBO /
+updated parameters within 1e-5 relative with the same injected noise.  The
+reference's own fp32 gradient carries ~1e-5 of summation-order noise
+(sequential scatter-add over hot rows), so gradients are compared in max-norm."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import vfm_math, vfm_port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(meta, g, t=0, **kw):
+    from vae_b200.vfm_torch import CF
+    m = CF(meta["d"], output=meta["output"], n_users=meta["N"], n_items=meta["M"],
+           train_counts=torch.from_numpy(g["train_counts"]), n_var_samples=meta["S"],
+           link=meta["link"], n_train=meta["n_train"], max_batch=meta["batch"], lr=meta["lr"], **kw)
+    _restore(m, g, t)
+    return m
+
+
+def _restore(m, g, t):
+    sd = gu.state(g, "init" if t == 0 else f"step{t - 1}.after")
+    own = m.state_dict()
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)).reshape(own[k].shape) for k, v in sd.items()
+                       if k in own}, strict=False)
+    for buf in (m.bias_m, m.bias_v, m.entity_m, m.entity_v, m._scalars_m, m._scalars_v):
+        buf.zero_()
+    m.adam_step.fill_(t)
+    if t > 0:
+        a = lambda k: torch.from_numpy(g[f"step{t - 1}.adam.{k}"]).to(DEV)
+        m.bias_m.copy_(a("bias_params.weight.m")), m.bias_v.copy_(a("bias_params.weight.v"))
+        m.entity_m.copy_(a("entity_params.weight.m")), m.entity_v.copy_(a("entity_params.weight.v"))
+        from vae_b200 import _lib as L
+        for name, idx in (("alpha", L.S_ALPHA), ("global_bias_mean", L.S_GB_MEAN),
+                          ("global_bias_scale", L.S_GB_SCALE)):
+            if f"step{t - 1}.adam.{name}.m" in g:
+                m._scalars_m[idx] = float(g[f"step{t - 1}.adam.{name}.m"][0])
+                m._scalars_v[idx] = float(g[f"step{t - 1}.adam.{name}.v"][0])
+
+
+def _noise(g, t):
+    return [torch.from_numpy(g[f"step{t}.noise{i}"]).to(DEV) for i in range(3)]
+
+
+S1 = [n for n in gu.SAMPLED if n != "sampled_class_s2"]
+
+
+@pytest.mark.parametrize("name", S1)
+def test_plan_is_bit_exact(name):
+    meta, g = gu.load(name)
+    m = _model(meta, g)
+    for t in range(meta["steps"]):
+        x, _ = gu.batch_of(meta, g, t)
+        plan = m.plan(torch.from_numpy(x).to(DEV))
+        plan.check_ids()
+        uniq, inverse, counts = plan.as_unique()
+        assert np.array_equal(uniq.cpu().numpy(), g[f"step{t}.uniq"])
+        assert np.array_equal(inverse.cpu().numpy(), g[f"step{t}.inverse"])
+        assert np.array_equal(counts.cpu().numpy(), g[f"step{t}.counts"])
+        ref = vfm_math.build_plan(x)
+        U = len(ref["uniq"])
+        assert np.array_equal(plan.seg_off[:U + 1].cpu().numpy(), ref["seg_off"])
+        assert np.array_equal(plan.occ[:x.size].cpu().numpy(), ref["order"])     # touched-row segments
+
+
+@pytest.mark.parametrize("B,F,R,hot", [(1, 2, 10, 0), (7, 2, 5, 0), (1000, 2, 50, 1), (4096, 3, 100000, 0),
+                                       (5000, 8, 3000, 1), (65536, 2, 165237, 1)])
+def test_plan_random_shapes_vs_torch_unique(B, F, R, hot):
+    from vae_b200 import _lib as L
+    from vae_b200.engine import BatchPlan, make_config
+    gen = torch.Generator().manual_seed(B + F)
+    x = torch.randint(0, R, (B, F), generator=gen)
+    if hot:
+        x[torch.rand(B, generator=gen) < 0.3, F - 1] = R - 1          # a heavy row, and the max id
+    tc = torch.ones(R, device=DEV)
+    plan = BatchPlan(B, F, R, DEV)
+    cfg = make_config(B, F, 8, R, 1, "reg", "abs", [R // 2 + 1], [R // 2, R - R // 2], 100, 7)
+    plan.build(cfg, x.to(DEV), tc)
+    plan.check_ids()
+    u, i, c = torch.unique(x, return_inverse=True, return_counts=True)
+    pu, pi, pc = plan.as_unique()
+    assert torch.equal(pu.cpu(), u) and torch.equal(pi.cpu(), i) and torch.equal(pc.cpu(), c)
+    U = len(u)
+    order = torch.argsort(i.reshape(-1), stable=True)
+    assert torch.equal(plan.occ[: B * F].cpu().long(), order)
+    # work items: ceil(count/chunk) per row, contiguous
+    first = plan.item_first[: U + 1].cpu().long()
+    n_items = (c + plan.chunk - 1) // plan.chunk
+    assert torch.equal(first[1:] - first[:-1], n_items)
+    assert int(plan.meta[1].item()) == int(n_items.sum())
+    rows = plan.item_row[: int(n_items.sum())].cpu().long()
+    assert torch.equal(rows, torch.repeat_interleave(torch.arange(U), n_items))
+    # per-column normaliser Z_f = sum_n 1/cnt_train = B for unit counts
+    np.testing.assert_allclose(plan.z[:F].cpu().numpy(), np.full(F, float(B)), rtol=1e-6)
+
+
+def test_plan_flags_out_of_range_ids():
+    from vae_b200.engine import BatchPlan, make_config
+    x = torch.tensor([[0, 3], [1, 9]])
+    plan = BatchPlan(2, 2, 5, DEV)
+    cfg = make_config(2, 2, 4, 5, 1, "reg", "abs", [3], [2, 3], 2, 7)
+    plan.build(cfg, x.to(DEV), torch.ones(5, device=DEV))
+    with pytest.raises(IndexError):
+        plan.check_ids()
+
+
+@pytest.mark.parametrize("name", S1)
+def test_forward_matches_reference_golden(name):
+    meta, g = gu.load(name)
+    for t in range(meta["steps"]):
+        m = _model(meta, g, t)
+        x, y = gu.batch_of(meta, g, t)
+        out = m.fused_step(torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV), noise=_noise(g, t),
+                           update=False)
+        np.testing.assert_allclose(out["pred"].cpu().numpy(), g[f"step{t}.pred"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(out["loss"].item(), g[f"step{t}.loss"][0], rtol=1e-5)
+        np.testing.assert_allclose(out["kl"].item(), g[f"step{t}.kl"][0], rtol=1e-5)
+        np.testing.assert_allclose(out["nll_mean"].item(), g[f"step{t}.nll_mean"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", S1)
+def test_gradients_match_reference_and_fp64_maths(name):
+    meta, g = gu.load(name)
+    m = _model(meta, g, 0)
+    x, y = gu.batch_of(meta, g, 0)
+    noise = _noise(g, 0)
+    gr = m.gradients(torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV), noise=noise)
+    exact = vfm_math.sampled_step(gu.sampled_math_params(gu.state(g, "init")), x, y,
+                                  [n.cpu().numpy() for n in noise], g["train_counts"], meta["n_train"],
+                                  [meta["N"], meta["M"]], output=meta["output"], link=meta["link"])
+    pairs = [("entity_params.weight", "entity"), ("bias_params.weight", "bias"),
+             ("global_bias_mean",) * 2, ("global_bias_scale",) * 2]
+    if meta["output"] == "reg":
+        pairs.append(("alpha",) * 2)
+    for k, kk in pairs:
+        got = gr[k].cpu().numpy()
+        assert gu.rel_err(got, exact["grads"][kk]) < 3e-6, (k, "vs fp64 maths")
+        assert gu.rel_err(got, g[f"step0.grad.{k}"]) < 2e-5, (k, "vs reference fp32")
+    # untouched rows: exactly zero gradient, touched-row set bit-exact
+    touched = np.zeros(meta["N"] + meta["M"], dtype=bool)
+    touched[g["step0.uniq"]] = True
+    ge = gr["entity_params.weight"].cpu().numpy()
+    assert not ge[~touched].any()
+    assert (np.abs(ge[touched]).sum(axis=1) > 0).all()
+
+
+@pytest.mark.parametrize("name", S1)
+def test_fused_step_updates_match_reference(name):
+    """One fused step from the exact pre-step state of every golden step."""
+    meta, g = gu.load(name)
+    lr = meta["lr"]
+    for t in range(meta["steps"]):
+        m = _model(meta, g, t)
+        x, y = gu.batch_of(meta, g, t)
+        xd, yd, noise = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV), _noise(g, t)
+        before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        mv = (m.entity_m.clone(), m.entity_v.clone(), m.bias_m.clone(), m.bias_v.clone())
+        gr = m.gradients(xd, yd, noise=noise)
+        out = m.fused_step(xd, yd, noise=noise)
+        assert int(m.adam_step.item()) == t + 1
+        uniq = g[f"step{t}.uniq"]
+        after = gu.state(g, f"step{t}.after")
+        # (a) the fused Adam arithmetic == torch's recurrence applied to the kernel's own gradient
+        for key, mm, vv in (("entity_params.weight", mv[0], mv[1]), ("bias_params.weight", mv[2], mv[3])):
+            p1, m1, v1 = vfm_math.adam_update(before[key].cpu().numpy().astype(np.float64),
+                                              gr[key].cpu().numpy().astype(np.float64),
+                                              mm.cpu().numpy().astype(np.float64),
+                                              vv.cpu().numpy().astype(np.float64), t + 1, lr, rows=uniq)
+            got = m.state_dict()[key].cpu().numpy()
+            np.testing.assert_allclose(got, p1, rtol=2e-6, atol=2e-6 * max(1.0, lr))
+        # (b) touched rows against the reference's dense-Adam result (identical on touched rows);
+        # elements whose update is ill-conditioned in fp32 (|g| ~ Adam eps, or m ~ 0) are the
+        # reference's own summation-order noise: allow a 1e-4 fraction of outliers
+        for key in ("entity_params.weight", "bias_params.weight"):
+            got, want = m.state_dict()[key].cpu().numpy()[uniq], after[key][uniq]
+            bad = np.abs(got - want) > 1e-5 * np.abs(want) + 2e-5 * lr + 1e-6
+            assert bad.mean() <= 1e-4, (name, t, key, float(bad.mean()))
+        for key in ("global_bias_mean", "global_bias_scale") + (("alpha",) if meta["output"] == "reg" else ()):
+            np.testing.assert_allclose(m.state_dict()[key].cpu().numpy(), after[key], rtol=1e-5,
+                                       atol=2e-5 * lr + 1e-6)
+        if meta["output"] != "reg":                       # Bernoulli: alpha must not move
+            assert torch.equal(m.state_dict()["alpha"], before["alpha"])
+        # untouched rows are untouched by the lazy update
+        mask = np.ones(meta["N"] + meta["M"], dtype=bool)
+        mask[uniq] = False
+        assert torch.equal(m.state_dict()["entity_params.weight"][mask], before["entity_params.weight"][mask])
+        np.testing.assert_allclose(out["loss"].item(), g[f"step{t}.loss"][0], rtol=1e-5)
+
+
+def test_backward_is_bitwise_deterministic():
+    meta, g = gu.load("sampled_fraction")               # 20 item rows with ~430 occurrences each
+    x, y = gu.batch_of(meta, g, 0)
+    outs = []
+    for _ in range(3):
+        m = _model(meta, g, 0)
+        m.fused_step(torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV), noise=_noise(g, 0))
+        outs.append((m.entity_params.weight.clone(), m.bias_params.weight.clone(), m.entity_v.clone()))
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(o, outs[0]))
+
+
+def test_dropin_autograd_path_equals_reference_loop():
+    """The reference's own loop (vfm-torch.py:353-370) run against the drop-in module:
+    model(x) -> likelihood/kl -> loss.backward() -> torch.optim.Adam(dense).step()."""
+    meta, g = gu.load("sampled_reg_d5")
+    m = _model(meta, g, 0)
+    opt = torch.optim.Adam(m.parameters(), lr=meta["lr"])
+    for t in range(meta["steps"]):
+        if t > 0:                                         # replay from the exact reference state
+            _restore(m, g, t)
+            for k, p in m.named_parameters():
+                if f"step{t - 1}.adam.{k}.m" in g:
+                    opt.state[p] = {"step": torch.tensor(float(t)),
+                                    "exp_avg": torch.from_numpy(g[f"step{t - 1}.adam.{k}.m"]).to(DEV).reshape(p.shape),
+                                    "exp_avg_sq": torch.from_numpy(g[f"step{t - 1}.adam.{k}.v"]).to(DEV).reshape(p.shape)}
+        x, y = gu.batch_of(meta, g, t)
+        likelihood, last_logits, mean_logits, kl_term = m(torch.from_numpy(x).to(DEV), noise=_noise(g, t))
+        assert last_logits is None and mean_logits is None
+        loss = -likelihood.log_prob(torch.from_numpy(y).to(DEV).float()).mean() * meta["n_train"] + kl_term
+        np.testing.assert_allclose(loss.item(), g[f"step{t}.loss"][0], rtol=1e-5)
+        np.testing.assert_allclose(likelihood.mean.squeeze().detach().cpu().numpy(), g[f"step{t}.pred"],
+                                   rtol=1e-5, atol=2e-6)
+        opt.zero_grad()
+        loss.backward()
+        if t == 0:
+            for k in ("entity_params.weight", "bias_params.weight", "alpha", "global_bias_mean",
+                      "global_bias_scale"):
+                got = dict(m.named_parameters())[k].grad.cpu().numpy()
+                assert gu.rel_err(got, g[f"step0.grad.{k}"]) < 2e-5, k
+            assert m.prec_user_bias_prior.grad is None
+        opt.step()
+        after = gu.state(g, f"step{t}.after")
+        for k in ("entity_params.weight", "bias_params.weight", "alpha", "global_bias_mean", "global_bias_scale"):
+            got, want = m.state_dict()[k].cpu().numpy(), after[k]       # dense Adam: every row
+            bad = np.abs(got - want) > 1e-5 * np.abs(want) + 2e-5 * meta["lr"] + 1e-6
+            assert bad.mean() <= 1e-4, (t, k, float(bad.mean()))
+
+
+def test_philox_mode_matches_oracle_with_exported_noise():
+    meta, g = gu.load("sampled_reg_d64")
+    m = _model(meta, g, 0, seed=1234)
+    x, y = gu.batch_of(meta, g, 0)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    uniq = torch.from_numpy(g["step0.uniq"])
+    noise = m.philox_noise(uniq)
+    e = noise[2].reshape(-1).cpu().numpy()
+    assert abs(e.mean()) < 0.02 and abs(e.std() - 1.0) < 0.02 and np.abs(e).max() < 6.5
+    assert torch.equal(m.philox_noise(uniq)[2], noise[2])                 # counter-based: reproducible
+    assert not torch.equal(m.philox_noise(uniq, step=1)[2], noise[2])     # new step, new draws
+    out = m.fused_step(xd, yd)                                            # Philox inside the kernels
+    pred_philox, loss_philox = out["pred"].clone(), out["loss"].item()
+    w_after = m.entity_params.weight.clone()
+    m2 = _model(meta, g, 0, seed=1234)
+    out2 = m2.fused_step(xd, yd, noise=noise)                             # same draws, injected
+    assert torch.allclose(pred_philox, out2["pred"], rtol=1e-6, atol=1e-6)
+    assert abs(loss_philox - out2["loss"].item()) <= 1e-6 * abs(loss_philox)
+    assert torch.allclose(w_after, m2.entity_params.weight, rtol=1e-6, atol=1e-6)
+    exact = vfm_math.sampled_step(gu.sampled_math_params(gu.state(g, "init")), x, y,
+                                  [n.cpu().numpy() for n in noise], g["train_counts"], meta["n_train"],
+                                  [meta["N"], meta["M"]], output=meta["output"], link=meta["link"])
+    np.testing.assert_allclose(pred_philox.cpu().numpy(), exact["mean"].squeeze(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(loss_philox, exact["loss"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("F,d", [(3, 8), (8, 64), (4, 20)])
+def test_multi_field_pairwise_matches_fp64_maths(F, d):
+    """Config-4 shape: F>2 fields, pairwise interaction, per-group KL weights.  The reference has
+    no sampled implementation for F>2; the oracle is the fp64 maths (+ torch port)."""
+    from vae_b200.vfm_torch import CF
+    fs = [37, 23, 11, 9, 7, 5, 4, 3][:F]
+    R, B = sum(fs), 700
+    rng = np.random.default_rng(F)
+    offs = np.concatenate(([0], np.cumsum(fs)[:-1]))
+    x = np.stack([offs[f] + rng.integers(0, fs[f], B) for f in range(F)], 1).astype(np.int64)
+    y = (rng.random(B) < 0.5).astype(np.float32)
+    tc = np.bincount(x.reshape(-1), minlength=R)
+    tc[tc == 0] = 1
+    torch.manual_seed(3)
+    m = CF(d, output="class", n_users=fs[0], n_items=fs[1], train_counts=torch.from_numpy(tc),
+           field_sizes=fs, kl_weighting="group", n_train=B, max_batch=B, lr=0.05)
+    with torch.no_grad():
+        m.entity_params.weight.mul_(0.3)                 # keep 8-field sums in a sane range
+    sd = {k: v.cpu().numpy() for k, v in m.state_dict().items()}
+    U = len(np.unique(x))
+    gen = torch.Generator().manual_seed(5)
+    noise = [torch.randn(1, 1, generator=gen), torch.randn(1, U, generator=gen), torch.randn(1, U, d, generator=gen)]
+    exact = vfm_math.sampled_step(gu.sampled_math_params(sd), x, y, [n.numpy() for n in noise], tc, B, fs,
+                                  output="class", interaction="pairwise", kl_weighting="group")
+    port = vfm_port.SampledPort(fs[0], fs[1], d, torch.from_numpy(tc), output="class", field_sizes=fs,
+                                interaction="pairwise", kl_weighting="group")
+    gu.load_state(port, sd)
+    po = vfm_port.sampled_port_step(port, torch.optim.Adam(port.parameters(), lr=0.05), torch.from_numpy(x),
+                                    torch.from_numpy(y), B, noise)
+    np.testing.assert_allclose(po["loss"].item(), exact["loss"], rtol=1e-5)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    gr = m.gradients(xd, yd, noise=[n.to(DEV) for n in noise])
+    np.testing.assert_allclose(gr["loss"].item(), exact["loss"], rtol=1e-5)
+    np.testing.assert_allclose(gr["pred"].cpu().numpy(), exact["mean"].squeeze(), rtol=1e-5, atol=2e-6)
+    assert gu.rel_err(gr["entity_params.weight"].cpu().numpy(), exact["grads"]["entity"]) < 1e-5
+    assert gu.rel_err(gr["bias_params.weight"].cpu().numpy(), exact["grads"]["bias"]) < 1e-5
+    m.fused_step(xd, yd, noise=[n.to(DEV) for n in noise])
+    uniq = exact["plan"]["uniq"]
+    got, want = m.entity_params.weight.cpu().numpy()[uniq], port.entity_params.weight.detach().numpy()[uniq]
+    bad = np.abs(got - want) > 1e-5 * np.abs(want) + 2e-5 * 0.05 + 1e-6
+    assert bad.mean() <= 1e-4
+
+
+def test_mean_prediction_and_saved_weights():
+    meta, g = gu.load("sampled_reg_d64")
+    m = _model(meta, g, 0)
+    x, _ = gu.batch_of(meta, g, 0)
+    xd = torch.from_numpy(x).to(DEV)
+    d = meta["d"]
+    W, Bw = m.entity_params.weight.detach().cpu().numpy(), m.bias_params.weight.detach().cpu().numpy()
+    want = (m.global_bias_mean.item() + Bw[x, 0].sum(1) + W[x][:, :, :d].prod(1).sum(1))
+    np.testing.assert_allclose(m.predict_mean(xd).cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    m.save_weights()
+    _, last_logits, mean_logits, _ = m(xd)
+    np.testing.assert_allclose(last_logits.cpu().numpy(), want, rtol=1e-5, atol=1e-5)   # vfm-torch.py:248-259
+    np.testing.assert_allclose(mean_logits.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_no_cpu_fallback():
+    from vae_b200.vfm_torch import CF
+    with pytest.raises(RuntimeError):
+        CF(4, n_users=3, n_items=3, train_counts=torch.ones(6), device="cpu")

@@ -1,0 +1,31 @@
+// C-ABI glue: error reporting, version, closed-form scalar-block layout.
+#include <cstdarg>
+#include <cstdio>
+
+#include "internal.h"
+
+namespace vfmb {
+
+static thread_local char g_error[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+}  // namespace vfmb
+
+extern "C" const char* vfmb_last_error(void) { return vfmb::g_error; }
+extern "C" int vfmb_version(void) { return 100; }
+
+// closed-form scalar block: [0..8) globals, then bias prior mean[G], bias prior scale[G],
+// (padded to a multiple of 4) entity prior mean[G*d], entity prior scale[G*d]
+static int32_t entity_base(int32_t G) { return VFMB_C_GROUP_BASE + ((2 * G + 3) / 4) * 4; }
+extern "C" int32_t vfmb_closed_off_bias_prior_mean(int32_t G, int32_t d, int32_t g) { (void)d; (void)G; return VFMB_C_GROUP_BASE + g; }
+extern "C" int32_t vfmb_closed_off_bias_prior_scale(int32_t G, int32_t d, int32_t g) { (void)d; return VFMB_C_GROUP_BASE + G + g; }
+extern "C" int32_t vfmb_closed_off_entity_prior_mean(int32_t G, int32_t d, int32_t g) { return entity_base(G) + g * d; }
+extern "C" int32_t vfmb_closed_off_entity_prior_scale(int32_t G, int32_t d, int32_t g) { return entity_base(G) + G * d + g * d; }
+extern "C" int32_t vfmb_closed_scalar_count(int32_t G, int32_t d) { return entity_base(G) + 2 * G * d; }

@@ -1,0 +1,34 @@
+// Host-side internals shared by the translation units of libvfm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vfm_b200.h"
+
+namespace vfmb {
+
+constexpr int kChunk = 64;          // occurrences per backward work item
+constexpr int kNumSMs = 148;        // B200
+constexpr int kPlanGrid = 2 * kNumSMs;
+constexpr int kMaxGrid = 8 * kNumSMs;   // cap for grid-stride kernels with block partials
+constexpr int kPriorGrid = 2 * kNumSMs; // blocks that carry prior-gradient partials (closed form)
+
+int set_error(int code, const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess)                                                          \
+            return ::vfmb::set_error((int)_e, "%s failed: %s (%s:%d)", #expr,           \
+                                     cudaGetErrorString(_e), __FILE__, __LINE__);       \
+    } while (0)
+
+// lane layout for a given embedding size (see common.cuh)
+struct Layout {
+    int vec;   // 4 or 1
+    int lpr;   // lanes per row: 4, 8, 16, 32
+    int nv;    // vectors per lane: 1 or 2
+};
+bool pick_layout(int d, Layout* out);
+
+}  // namespace vfmb
