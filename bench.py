@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the VFM training step (BASELINE.json metric: fwd+bwd(+Adam) samples/s and
+achieved HBM GB/s vs the measured peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload ml20m|sideinfo|big100m|ml100k]
+
+A "step" is one pass of the hot path -- batch plan, forward, backward, Adam on the touched
+rows -- over one batch of a synthetic dataset of the named shape.  Batches
+are consecutive, never shuffled, as in the reference loaders (vfm-torch.py:121-122).
+
+One JSON line is printed by rank 0; see DESIGN.md ("Measurement") for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vae_b200 import synth                                   # noqa: E402
+
+METRIC = "vfm_train_step_samples_per_s"
+UNIT = "samples/s"
+
+
+# ------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(B, F, d, U):
+    """ids, target, prediction + per touched row parameters, Adam m and v read and
+    written once, plus its int64 train count."""
+    return B * (8 * F + 4 + 4) + U * ((2 * d + 2) * 4 * 6 + 8)
+
+
+def rows_kernel_bytes(B, F, d, U):
+    """Compulsory traffic of the dominant kernel (k_rows): p, m, v of every touched row in and out,
+    the sorted occurrence list and the residuals."""
+    return U * (2 * d + 2) * 4 * 6 + B * F * 4 + B * 4
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.reasons, self.max_mhz = period_s, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:                                     # pragma: no cover
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:                                 # pragma: no cover
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_model(w: synth.Workload, device, train_counts, lr):
+    from vae_b200.vfm_torch import CF
+    torch.manual_seed(synth.PARAM_SEED)
+    kl = "torch" if w.n_fields == 2 else "group"
+    return CF(w.d, output=w.output, n_users=w.field_sizes[0], n_items=w.field_sizes[1],
+              train_counts=torch.from_numpy(train_counts), field_sizes=w.field_sizes, kl_weighting=kl,
+              n_train=w.n_train, max_batch=w.batch, seed=synth.NOISE_SEED, lr=lr, device=device)
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    w = synth.make_workload(args.workload, n_rows=args.rows)
+    B, F, d = w.batch, w.n_fields, w.d
+    n_batches = w.n_train // B
+    assert n_batches >= 1
+    tc = w.train_counts()
+    lr = 1.0 / (1 + w.n_train // B)                           # vfm-torch.py:92
+    model = make_model(w, device, tc, lr)
+    # weak scaling over independent replicas is NOT the multi-GPU mode of this path; see
+    # vae_b200/dist.py.  For N>1 each rank takes every world-th batch of the global stream.
+    x_all = torch.from_numpy(w.x[: n_batches * B]).to(device)
+    y_all = torch.from_numpy(w.y[: n_batches * B]).to(device)
+
+    def batch(i):
+        j = (i * world + rank) % n_batches
+        return x_all[j * B:(j + 1) * B], y_all[j * B:(j + 1) * B]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = args.warmup, args.steps
+    for i in range(W):
+        model.fused_step(*batch(i))
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(W, W + K):
+        model.fused_step(*batch(i))
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    loss = float(model._buf.stats[0].item())
+
+    # dominant kernel (k_rows, inside vfmb_sampled_backward), timed per launch on the launch stream
+    kr = []
+    for i in range(W + K, W + K + min(K, 200)):
+        xb, yb = batch(i)
+        model._forward_kernels(xb, yb, None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model._backward_kernels(None, 0, 1.0)
+        e1.record()
+        kr.append((e0, e1))
+    torch.cuda.synchronize()
+    rows_ms = float(np.mean([a.elapsed_time(b) for a, b in kr]))
+
+    # measured U of the timed batches (outside the timed region)
+    us = [int(torch.unique(batch(i)[0]).numel()) for i in range(W, W + min(K, 64))]
+    U = float(np.mean(us))
+
+    # end to end through the public API with HOST inputs: pinned x/y -> device every step,
+    # loss/KL scalars back to pinned host memory every step
+    e2e = measure_e2e(model, w, rank, world, n_batches, W, min(K, 500), device, barrier)
+
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    value = K * B * world / (ms * 1e-3)
+    step_bytes = algorithmic_bytes(B, F, d, U)
+    rk_bytes = rows_kernel_bytes(B, F, d, U)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(args.workload, {}).get("k_rows_dram_bytes")
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w.name}: {'+'.join(map(str, w.field_sizes))} rows, d={d}, "
+                               f"{w.n_train} ratings, batch {B}, {w.variant} ELBO, {w.output}",
+                   "fields": F, "unique_rows_per_step": U, "adam": "touched rows (lazy)",
+                   "noise": "Philox4x32-10 in-kernel", "plan": "built every step (CUB radix sort + own kernels)",
+                   "l2": "params+Adam state 258 MB > 126 MB L2; consecutive distinct batches, no flush"
+                   if args.workload == "ml20m" else "consecutive distinct batches, no flush",
+                   "parallelism": f"dp{world}" if world > 1 else "single"},
+        "roofline": {"bound": "hbm", "kernel": "k_rows (segmented backward + Adam)",
+                     "achieved": rk_bytes / (rows_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": rk_bytes / (rows_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                     "peak_source": peak_src, "kernel_ms": rows_ms, "algorithmic_bytes": rk_bytes},
+        "roofline_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms / K * 1e-3) / 1e9,
+                          "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak, "unit": "GB/s"},
+        "e2e": e2e, "gpu_launches": 7 * K, "library_launches_per_step": "CUB radix sort + 2 scans",
+        "clocks": clocks, "final_loss": loss,
+    }
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_budget)
+    print(json.dumps(out), flush=True)
+
+
+def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier):
+    B, F = w.batch, w.n_fields
+    xh = torch.from_numpy(w.x[: n_batches * B]).pin_memory()
+    yh = torch.from_numpy(w.y[: n_batches * B]).pin_memory()
+    xd = [torch.empty((B, F), dtype=torch.int64, device=device) for _ in range(2)]
+    yd = [torch.empty(B, dtype=torch.float32, device=device) for _ in range(2)]
+    res = torch.empty((K + W, 16), dtype=torch.float32).pin_memory()
+
+    def step(i):
+        j = (i * world + rank) % n_batches
+        s = i & 1
+        xd[s].copy_(xh[j * B:(j + 1) * B], non_blocking=True)
+        yd[s].copy_(yh[j * B:(j + 1) * B], non_blocking=True)
+        out = model.fused_step(xd[s], yd[s])
+        res[i].copy_(out["stats"], non_blocking=True)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    assert np.isfinite(res[W:W + K, 0].numpy()).all(), "non-finite loss in the e2e run"
+    return {"value": K * B * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * F * 8 + B * 4,
+            "d2h_bytes_per_step": 16 * 4, "steps": K, "ms_per_step": ms / K}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_baseline(args, budget_s=20.0):
+    """The oracle port (torch CPU, same ATen ops as the reference: unique, embedding, distributions,
+    autograd, dense Adam) on this box's host cores, on a bounded number of full-size steps."""
+    from oracle import vfm_port
+    w = synth.make_workload(args.workload, n_rows=args.rows)
+    if w.rows > 20_000_000:                                   # dense grads + dense Adam cannot hold 100M rows
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": "skipped: dense reference cannot allocate this table"}
+    B = w.batch
+    tc = torch.from_numpy(w.train_counts())
+    torch.manual_seed(synth.PARAM_SEED)
+    kl = "torch" if w.n_fields == 2 else "group"
+    model = vfm_port.SampledPort(w.field_sizes[0], w.field_sizes[1], w.d, tc, output=w.output,
+                                 field_sizes=w.field_sizes, kl_weighting=kl,
+                                 interaction="prod" if w.n_fields == 2 else "pairwise")
+    opt = torch.optim.Adam(model.parameters(), lr=1.0 / (1 + w.n_train // B))
+    x, y = torch.from_numpy(w.x), torch.from_numpy(w.y)
+    n_batches = w.n_train // B
+    times = []
+    t_start = time.time()
+    i = 0
+    while True:
+        j = i % n_batches
+        t0 = time.perf_counter()
+        vfm_port.sampled_port_step(model, opt, x[j * B:(j + 1) * B], y[j * B:(j + 1) * B], w.n_train)
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            times.append(dt)
+        i += 1
+        if len(times) >= 5 and time.time() - t_start > budget_s:
+            break
+        if len(times) >= 200:
+            break
+    med = float(np.median(times))
+    return {"value": B / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "host_cpus": os.cpu_count(), "torch": torch.__version__,
+            "sample": f"{len(times)} full-size steps (batch {B}) after 2 warm-ups, median step {med * 1e3:.1f} ms"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  The reference is pure
+    Python/torch and is not present on the GPU box, so this times the oracle port
+    (oracle/vfm_port.py: same ATen op sequence), with all host threads torch will use."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    w = synth.make_workload(args.workload, n_rows=args.rows)
+    t0 = time.time()
+    cb = cpu_baseline(args, budget_s=max(20.0, min(150.0, 0.05 * args.steps)))
+    wall = time.time() - t0
+    v = cb["value"]
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": (w.batch / v * 1e3) if v else None, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{w.name}: {'+'.join(map(str, w.field_sizes))} rows, d={w.d}, "
+                                  f"{w.n_train} ratings, batch {w.batch}, {w.variant} ELBO, {w.output}",
+                      "fields": w.n_fields, "adam": "dense (torch.optim.Adam)", "wall_s": wall},
+           "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ml20m")
+    ap.add_argument("--rows", type=int, default=None, help="override the synthetic dataset size")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

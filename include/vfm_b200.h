@@ -103,16 +103,18 @@ typedef struct vfmb_plan {
     int32_t* inverse;    /* [B*F]     rank of x[n,f] in uniq                       */
     int32_t* seg_off;    /* [U_cap+1] segment offsets; counts[u]=seg_off[u+1]-seg_off[u] */
     int32_t* occ;        /* [B*F]     occurrence ids n*F+f grouped by rank, ascending inside */
-    int32_t* item_first; /* [U_cap+1] first work item of each unique row            */
-    int32_t* item_row;   /* [W_cap]   unique rank of each work item                 */
-    int32_t* heavy_done; /* [U_cap]   arrival counters for multi-item rows          */
+    int32_t* pos_of;     /* [B*F]     inverse permutation of occ: sorted position of (n,f)   */
+    int32_t* pos_rank;   /* [B*F]     unique rank of each sorted position                    */
+    int32_t* partner;    /* [B*F]     per sorted position: F==2 the rank of the sample's other
+                                      field; F>2 the sample index n                          */
+    int32_t* urec;       /* [U_cap,4] per unique row {row id, batch count, seg_off, 0}       */
     float* z;            /* [VFMB_MAX_FIELDS] per-column normaliser Z_f             */
-    int32_t* meta;       /* [8] 0:U 1:W 2:error flag (id out of range) 3..: reserved */
+    int32_t* meta;       /* [8] 0:U 2:error flag (id out of range); rest reserved   */
 } vfmb_plan;
 
 typedef struct vfmb_plan_capacity_t {
-    int64_t u_cap, w_cap, workspace_bytes;
-    int32_t chunk;       /* occurrences per work item */
+    int64_t u_cap, n_tiles, workspace_bytes;
+    int32_t tile;        /* sorted positions per backward tile */
 } vfmb_plan_capacity_t;
 
 int vfmb_plan_capacity(int32_t B, int32_t F, int32_t R, vfmb_plan_capacity_t* out /*host*/);
@@ -125,8 +127,9 @@ int vfmb_plan_build(const vfmb_config* cfg /*host*/, const int64_t* x, const flo
                     const vfmb_plan* plan /*host struct of device ptrs*/, void* workspace,
                     size_t workspace_bytes, vfmb_stream stream);
 
-/* Scratch + outputs of one step.  Capacities: vs [U_cap*d], ws [U_cap],
- * partials [vfmb_partials_floats()], pred/mean/resid [B], stats [VFMB_STATS]. */
+/* Scratch + outputs of one step.  Capacities: vs/es/grow [U_cap*d], ws/ebs/cq/gws [U_cap],
+ * msg [B*d] (F>2 only), pred/mean/resid [B], rsorted [B*F],
+ * partials [vfmb_partials_doubles()], stats [VFMB_STATS]. */
 typedef struct vfmb_step_io {
     const float* y;          /* [B] targets (NULL: forward without likelihood terms)  */
     const float* eps_global; /* [S]     injected N(0,1) draws, or NULL -> Philox      */
@@ -134,10 +137,16 @@ typedef struct vfmb_step_io {
     const float* eps_entity; /* [S,U,d] (vfm-torch.py:241)                            */
     float* vs;               /* scratch: sampled factor rows  [U_cap,d]               */
     float* ws;               /* scratch: sampled biases       [U_cap]                 */
+    float* es;               /* scratch: the step's factor noise [U_cap,d] (Philox)   */
+    float* ebs;              /* scratch: the step's bias noise   [U_cap]   (Philox)   */
+    float* cq;               /* scratch: KL weight c_u per unique row [U_cap]         */
+    float* grow;             /* scratch: dloss/dv per unique row [U_cap,d]            */
+    float* gws;              /* scratch: dloss/dw per unique row [U_cap]              */
     float* msg;              /* scratch [B,d], only F>2 (may be NULL for F==2)        */
     float* pred;             /* [B] unscaled_pred (vfm-torch.py:265)                  */
     float* mean;             /* [B] likelihood mean: pred or sigmoid(pred) (:363)     */
     float* resid;            /* [B] dloss/dpred                                       */
+    float* rsorted;          /* [B*F] dloss/dpred per sorted occurrence (scratch)     */
     double* partials;        /* scratch for deterministic reductions                  */
     int32_t* counters;       /* [8] zero-initialised once by the caller               */
     float* stats;            /* [VFMB_STATS] see enum                                 */

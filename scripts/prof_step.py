@@ -1,0 +1,28 @@
+"""A handful of fused training steps on a BASELINE workload -- the command profiled under ncu."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench                                                   # noqa: E402
+from vae_b200 import synth                                      # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="ml20m")
+ap.add_argument("--rows", type=int, default=2_000_000)
+ap.add_argument("--steps", type=int, default=6)
+ap.add_argument("--warmup", type=int, default=4)
+a = ap.parse_args()
+w = synth.make_workload(a.workload, n_rows=a.rows)
+model = bench.make_model(w, torch.device("cuda", 0), w.train_counts(), 1.0 / (1 + w.n_train // w.batch))
+B = w.batch
+x = torch.from_numpy(w.x).cuda()
+y = torch.from_numpy(w.y).cuda()
+nb = w.n_train // B
+for i in range(a.warmup + a.steps):
+    j = i % nb
+    out = model.fused_step(x[j * B:(j + 1) * B], y[j * B:(j + 1) * B])
+torch.cuda.synchronize()
+print("loss", out["loss"].item(), "U", int(model._plan.meta[0]), "W", int(model._plan.meta[1]))

@@ -90,13 +90,15 @@ def test_plan_random_shapes_vs_torch_unique(B, F, R, hot):
     U = len(u)
     order = torch.argsort(i.reshape(-1), stable=True)
     assert torch.equal(plan.occ[: B * F].cpu().long(), order)
-    # work items: ceil(count/chunk) per row, contiguous
-    first = plan.item_first[: U + 1].cpu().long()
-    n_items = (c + plan.chunk - 1) // plan.chunk
-    assert torch.equal(first[1:] - first[:-1], n_items)
-    assert int(plan.meta[1].item()) == int(n_items.sum())
-    rows = plan.item_row[: int(n_items.sum())].cpu().long()
-    assert torch.equal(rows, torch.repeat_interleave(torch.arange(U), n_items))
+    # flat records: pos_of inverts occ; partner = rank of the sample's other field (F=2) or n
+    occ = plan.occ[: B * F].cpu().long()
+    assert torch.equal(plan.pos_of[: B * F].cpu().long()[occ], torch.arange(B * F))
+    want_partner = i.reshape(-1)[occ ^ 1] if F == 2 else occ // F
+    assert torch.equal(plan.partner[: B * F].cpu().long(), want_partner)
+    urec = plan.urec[: 4 * U].cpu().long().reshape(U, 4)
+    seg = torch.cat((torch.zeros(1, dtype=torch.long), torch.cumsum(c, 0)))
+    assert torch.equal(urec[:, 0], u) and torch.equal(urec[:, 1], c) and torch.equal(urec[:, 2], seg[:-1])
+    assert torch.equal(plan.pos_rank[: B * F].cpu().long(), i.reshape(-1)[occ])
     # per-column normaliser Z_f = sum_n 1/cnt_train = B for unit counts
     np.testing.assert_allclose(plan.z[:F].cpu().numpy(), np.full(F, float(B)), rtol=1e-6)
 
@@ -307,7 +309,7 @@ def test_multi_field_pairwise_matches_fp64_maths(F, d):
     assert gu.rel_err(gr["bias_params.weight"].cpu().numpy(), exact["grads"]["bias"]) < 1e-5
     m.fused_step(xd, yd, noise=[n.to(DEV) for n in noise])
     uniq = exact["plan"]["uniq"]
-    got, want = m.entity_params.weight.cpu().numpy()[uniq], port.entity_params.weight.detach().numpy()[uniq]
+    got, want = m.entity_params.weight.detach().cpu().numpy()[uniq], port.entity_params.weight.detach().numpy()[uniq]
     bad = np.abs(got - want) > 1e-5 * np.abs(want) + 2e-5 * 0.05 + 1e-6
     assert bad.mean() <= 1e-4
 

@@ -16,8 +16,10 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libvfm_b200.so")
 SOURCES = ["api.cu", "plan.cu", "sampled.cu", "closed.cu"]
 HEADERS = ["common.cuh", "internal.h", os.path.join(_ROOT, "include", "vfm_b200.h")]
+# -prec-div/-prec-sqrt=false: MUFU-based division and square root (<= 2 ulp) instead of the IEEE
+# slow paths, which made the Adam epilogue instruction-bound; denormals and expf/logf stay precise
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-w"]
+              "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-shared", "-w"]
 
 MAX_FIELDS = 8
 GAUSSIAN, BERNOULLI = 0, 1
@@ -53,19 +55,20 @@ class Adam(C.Structure):
 
 class Plan(C.Structure):
     _fields_ = [("uniq", _i32p), ("inverse", _i32p), ("seg_off", _i32p), ("occ", _i32p),
-                ("item_first", _i32p), ("item_row", _i32p), ("heavy_done", _i32p),
+                ("pos_of", _i32p), ("pos_rank", _i32p), ("partner", _i32p), ("urec", _i32p),
                 ("z", _f32p), ("meta", _i32p)]
 
 
 class PlanCapacity(C.Structure):
-    _fields_ = [("u_cap", C.c_int64), ("w_cap", C.c_int64), ("workspace_bytes", C.c_int64),
-                ("chunk", C.c_int32)]
+    _fields_ = [("u_cap", C.c_int64), ("n_tiles", C.c_int64), ("workspace_bytes", C.c_int64),
+                ("tile", C.c_int32)]
 
 
 class StepIO(C.Structure):
     _fields_ = [("y", _f32p), ("eps_global", _f32p), ("eps_bias", _f32p), ("eps_entity", _f32p),
-                ("vs", _f32p), ("ws", _f32p), ("msg", _f32p), ("pred", _f32p), ("mean", _f32p),
-                ("resid", _f32p), ("partials", _f64p), ("counters", _i32p), ("stats", _f32p),
+                ("vs", _f32p), ("ws", _f32p), ("es", _f32p), ("ebs", _f32p), ("cq", _f32p),
+                ("grow", _f32p), ("gws", _f32p), ("msg", _f32p), ("pred", _f32p), ("mean", _f32p),
+                ("resid", _f32p), ("rsorted", _f32p), ("partials", _f64p), ("counters", _i32p), ("stats", _f32p),
                 ("grad_bias", _f32p), ("grad_entity", _f32p), ("grad_scalars", _f32p)]
 
 

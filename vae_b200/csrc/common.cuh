@@ -78,6 +78,21 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 
+// ---------------------------------------------------------------- cheap special functions
+// Single-MUFU approximations (<= 2 ulp; denormal inputs flush to zero).  The step kernels are
+// instruction-issue bound, and the IEEE division / square-root sequences dominated the Adam
+// epilogue; the results stay far inside the 1e-5 parity tolerance.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+// L2 prefetch of the 128-byte line holding p: no register is tied up while it is in flight
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 // ---------------------------------------------------------------- link functions
 // LINK 0: abs (vfm-torch.py:126, vfm-tomasrch.py:201), 1: softplus (vfm-torch.py:125)
 template <int LINK> __device__ __forceinline__ float link_fn(float raw) {
@@ -100,6 +115,12 @@ __device__ __forceinline__ float kl_std_normal(float m, float s) {
     float vr = s * s;
     return 0.5f * (vr + m * m - 1.f - logf(vr));
 }
+// same with the MUFU logarithm (abs. error 2^-21.4 for vr in [0.5, 2]); used per element in
+// k_stage where the precise logf sequence was a quarter of all instructions
+__device__ __forceinline__ float kl_std_normal_fast(float m, float s) {
+    float vr = s * s;
+    return 0.5f * (vr + m * m - 1.f - __logf(vr));
+}
 
 // ---------------------------------------------------------------- Philox4x32-10
 // Counter-based RNG (Salmon et al. 2011).  Keyed by (seed); the counter is
@@ -109,12 +130,10 @@ struct Philox {
     static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
     static constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
     __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#ifdef __CUDA_ARCH__
-        uint32_t hi0 = __umulhi(M0, c[0]), hi1 = __umulhi(M1, c[2]);
-#else
-        uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c[0]) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c[2]) >> 32);
-#endif
-        uint32_t lo0 = M0 * c[0], lo1 = M1 * c[2];
+        // one 32x32->64 multiply per lane pair (IMAD.WIDE.U32) gives both halves
+        uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
         uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
         c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
     }

@@ -7,10 +7,10 @@
 
 namespace vfmb {
 
-constexpr int kChunk = 64;          // occurrences per backward work item
+constexpr int kTile = 32;           // sorted positions per backward tile (k_gather)
 constexpr int kNumSMs = 148;        // B200
 constexpr int kPlanGrid = 2 * kNumSMs;
-constexpr int kMaxGrid = 8 * kNumSMs;   // cap for grid-stride kernels with block partials
+constexpr int kMaxGrid = 4 * kNumSMs;   // grid-stride kernels: one resident wave at 4 blocks/SM
 constexpr int kPriorGrid = 2 * kNumSMs; // blocks that carry prior-gradient partials (closed form)
 
 int set_error(int code, const char* fmt, ...);

@@ -60,11 +60,12 @@ k_plan_keys(const int64_t* __restrict__ x, const float* __restrict__ train_count
     __syncthreads();
     if (s_last) {
         __threadfence();
-        if (threadIdx.x < F) {
+        // warp f reduces column f: lane l adds blocks l, l+32, ... then a fixed shuffle tree
+        if (warp < F) {
             double s = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b)
-                s += __ldcg(partials + (size_t)b * kMaxFields + threadIdx.x);
-            z[threadIdx.x] = (float)s;
+            for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * kMaxFields + warp);
+            s = warp_sum(s);
+            if (lane == 0) z[warp] = (float)s;
         }
         if (threadIdx.x == 0) *counter = 0;
     }
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256)
 k_plan_scatter(const int32_t* __restrict__ keys_s, const int32_t* __restrict__ vals_s,
                const int32_t* __restrict__ rank_incl, int N, int32_t* __restrict__ uniq,
                int32_t* __restrict__ seg_off, int32_t* __restrict__ inverse, int32_t* __restrict__ occ,
-               int32_t* __restrict__ meta) {
+               int32_t* __restrict__ pos_of, int32_t* __restrict__ pos_rank, int32_t* __restrict__ meta) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         int r = rank_incl[i] - 1;
         int k = keys_s[i];
@@ -91,31 +92,28 @@ k_plan_scatter(const int32_t* __restrict__ keys_s, const int32_t* __restrict__ v
         if (head) { uniq[r] = k; seg_off[r] = i; }
         inverse[o] = r;
         occ[i] = o;
+        pos_of[o] = i;
+        pos_rank[i] = r;
         if (i == N - 1) { meta[0] = r + 1; seg_off[r + 1] = N; }
     }
 }
 
-struct ItemCount {
-    const int32_t* seg_off;
-    const int32_t* meta;
-    int chunk;
-    __host__ __device__ int32_t operator()(int u) const {
-        if (u >= meta[0]) return 0;
-        int c = seg_off[u + 1] - seg_off[u];
-        return (c + chunk - 1) / chunk;
-    }
-};
-
-// ---- P5: expand item_first into the item -> row list --------------------------------------
+// ---- P4: flat records the step kernels read with one load each -----------------------------
+//   partner[i]  per sorted position: F==2 the rank of the sample's other field, else sample n
+//   urec[u]     {row id, batch count, segment offset, 0}
 __global__ void __launch_bounds__(256)
-k_plan_items(const int32_t* __restrict__ item_first, int u_cap, int32_t* __restrict__ item_row,
-             int32_t* __restrict__ meta) {
-    int U = meta[0];
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
-        int a = item_first[u];
-        int b = (u + 1 < u_cap + 1) ? item_first[u + 1] : a;
-        for (int w = a; w < b; ++w) item_row[w] = u;
-        if (u == U - 1) meta[1] = b;
+k_plan_finish(const int32_t* __restrict__ uniq, const int32_t* __restrict__ seg_off,
+              const int32_t* __restrict__ occ, const int32_t* __restrict__ inverse, int N, int F,
+              int32_t* __restrict__ partner, int32_t* __restrict__ urec, const int32_t* __restrict__ meta) {
+    const int U = meta[0];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = tid; i < N; i += nth) {
+        int o = occ[i];
+        partner[i] = (F == 2) ? inverse[o ^ 1] : o / F;
+    }
+    for (int u = tid; u < U; u += nth) {
+        const int seg0 = seg_off[u];
+        reinterpret_cast<int4*>(urec)[u] = make_int4(uniq[u], seg_off[u + 1] - seg0, seg0, 0);
     }
 }
 
@@ -147,17 +145,13 @@ static PlanWs carve(void* base, int N, int u_cap) {
     w.rank = (int32_t*)take((size_t)N * 4);
     w.partials = (double*)take((size_t)kPlanGrid * kMaxFields * 8);
     w.counter = (int32_t*)take(256);
-    size_t sort_b = 0, scan_b = 0, scan2_b = 0;
+    size_t sort_b = 0, scan_b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (int32_t*)nullptr, (int32_t*)nullptr,
                                     (int32_t*)nullptr, (int32_t*)nullptr, N, 0, 31);
     cub::TransformInputIterator<int32_t, HeadFlag, cub::CountingInputIterator<int>> it(
         cub::CountingInputIterator<int>(0), HeadFlag{nullptr});
     cub::DeviceScan::InclusiveSum(nullptr, scan_b, it, (int32_t*)nullptr, N);
-    cub::TransformInputIterator<int32_t, ItemCount, cub::CountingInputIterator<int>> it2(
-        cub::CountingInputIterator<int>(0), ItemCount{nullptr, nullptr, kChunk});
-    cub::DeviceScan::ExclusiveSum(nullptr, scan2_b, it2, (int32_t*)nullptr, u_cap + 1);
     w.cub_bytes = sort_b > scan_b ? sort_b : scan_b;
-    if (scan2_b > w.cub_bytes) w.cub_bytes = scan2_b;
     w.cub = take(w.cub_bytes);
     w.total = off;
     return w;
@@ -173,8 +167,8 @@ extern "C" int vfmb_plan_capacity(int32_t B, int32_t F, int32_t R, vfmb_plan_cap
     int64_t N = (int64_t)B * F;
     if (N >= (1LL << 30)) return set_error(VFMB_ESHAPE, "vfmb_plan_capacity: B*F must be < 2^30");
     out->u_cap = N < R ? N : R;
-    out->w_cap = out->u_cap + N / kChunk + 1;
-    out->chunk = kChunk;
+    out->n_tiles = (N + kTile - 1) / kTile;
+    out->tile = kTile;
     PlanWs w = carve(nullptr, (int)N, (int)out->u_cap);
     out->workspace_bytes = (int64_t)w.total;
     return 0;
@@ -212,15 +206,10 @@ extern "C" int vfmb_plan_build(const vfmb_config* cfg, const int64_t* x, const f
     int grid2 = (N + 255) / 256;
     if (grid2 > 4 * kPlanGrid) grid2 = 4 * kPlanGrid;
     k_plan_scatter<<<grid2, 256, 0, stream>>>(w.keys_s, w.vals_s, w.rank, N, plan->uniq, plan->seg_off,
-                                              plan->inverse, plan->occ, plan->meta);
+                                              plan->inverse, plan->occ, plan->pos_of, plan->pos_rank, plan->meta);
     CUDA_TRY(cudaGetLastError());
-    cub::TransformInputIterator<int32_t, ItemCount, cub::CountingInputIterator<int>> counts(
-        cub::CountingInputIterator<int>(0), ItemCount{plan->seg_off, plan->meta, kChunk});
-    cb = w.cub_bytes;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(w.cub, cb, counts, plan->item_first, u_cap + 1, stream));
-    int grid3 = (u_cap + 255) / 256;
-    if (grid3 > 4 * kPlanGrid) grid3 = 4 * kPlanGrid;
-    k_plan_items<<<grid3, 256, 0, stream>>>(plan->item_first, u_cap, plan->item_row, plan->meta);
+    k_plan_finish<<<grid2, 256, 0, stream>>>(plan->uniq, plan->seg_off, plan->occ, plan->inverse, N, cfg->F,
+                                             plan->partner, plan->urec, plan->meta);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

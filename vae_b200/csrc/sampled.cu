@@ -95,73 +95,140 @@ __device__ __forceinline__ bool block_partials(const double (&acc)[K], double* _
     return s_last;
 }
 
+// Final reduction by the last block: thread t adds the partials of blocks t, t+256, ... in that
+// order, then the 256 per-thread sums are combined by a fixed shuffle/shared-memory tree.  The
+// association order depends only on gridDim, so the result is bitwise reproducible.
+// Must be called by every thread of the (256-thread) block; result valid in thread 0.
 template <int K>
-__device__ __forceinline__ double final_sum(const double* __restrict__ partials, int i) {
-    double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partials + (size_t)b * K + i);
-    return s;
+__device__ __forceinline__ void final_sums(const double* __restrict__ partials, double (&out)[K]) {
+    __shared__ double s_fin[K][8];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(partials + (size_t)b * K + i);
+        s = warp_sum(s);
+        if (lane == 0) s_fin[i][warp] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_fin[i][w];
+        out[i] = s;
+    }
+}
+
+// Work distribution of the step kernels ("hybrid"): a warp takes CH = 4*GPW consecutive units
+// (unique rows / samples / work items; GPW = 32/LPR rows fit in a warp).  Everything that is one
+// scalar per unit -- record decode, bias row, train count, bias noise (one Philox block),
+// likelihood, bias Adam -- is done lane-parallel by the first CH lanes with coalesced loads;
+// the warp then walks the CH units in 4 rounds, GPW rows per round with LPR lanes per row for the
+// wide (d-element) work, fetching each unit's scalars by shuffle.  Rows of the later rounds are
+// prefetched into L2 up front.  This keeps ~50 warps per SM busy while taking the per-row scalar
+// code out of the wide path, where it ran at 1/LPR lane efficiency.
+constexpr int kRounds = 4;
+
+template <typename T>
+__device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// hand a per-group value back to the lane that owns unit (it*GPW + g)
+template <int LPR, typename T>
+__device__ __forceinline__ void hand_back(T& mine, T val, int it, int lane) {
+    constexpr int GPW = kWarp / LPR;
+#pragma unroll
+    for (int g = 0; g < GPW; ++g) {
+        T v = __shfl_sync(0xffffffffu, val, g * LPR);
+        if (lane == it * GPW + g) mine = v;
+    }
+}
+
+__device__ __forceinline__ void prefetch_row(const float* p, int bytes) {
+    for (int off = 0; off < bytes; off += 128) prefetch_l2(reinterpret_cast<const char*>(p) + off);
 }
 
 // ------------------------------------------------------------------------------- k_stage
 template <int VEC, int LPR, int NV, int LINK>
 __global__ void __launch_bounds__(256)
 k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ entity,
-        const float* __restrict__ train_counts, const int32_t* __restrict__ uniq,
-        const int32_t* __restrict__ seg_off, const int32_t* __restrict__ meta,
-        const float* __restrict__ z, int32_t* __restrict__ heavy_done,
+        const float* __restrict__ train_counts, const int32_t* __restrict__ urec,
+        const int32_t* __restrict__ meta, const float* __restrict__ z,
         const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
         const int32_t* __restrict__ adam_step, float* __restrict__ vs, float* __restrict__ ws,
+        float* __restrict__ es, float* __restrict__ ebs, float* __restrict__ cq,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
-    constexpr int GPW = kWarp / LPR;                  // groups (rows) per warp
+    constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
     const int U = meta[0];
     const int d = c.d;
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
-    const int lane = threadIdx.x & 31, gl = lane % LPR;
-    const int group = (threadIdx.x >> 5) * GPW + lane / LPR;
-    const int groups_per_block = (blockDim.x >> 5) * GPW;
-    double acc[kMaxFields];
-#pragma unroll
-    for (int i = 0; i < kMaxFields; ++i) acc[i] = 0.0;
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
+    const unsigned gmask = group_mask<LPR>();
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    float facc = 0.f;                                   // sum_u c_u * KL_u over this thread's rows
 
-    for (int u = blockIdx.x * groups_per_block + group; u < U; u += gridDim.x * groups_per_block) {
-        const int rowid = uniq[u];
-        const float* erow = entity + (size_t)rowid * 2 * d;
-        float kl = 0.f;
+    for (int base = gwarp * CH; base < U; base += nwarps * CH) {
+        // ---- lane-parallel: one unique row per lane (first CH lanes)
+        const int ul = base + lane;
+        const bool valid = lane < CH && ul < U;
+        int rowid_l = 0;
+        float klb = 0.f, cqv = 0.f;
+        if (valid) {
+            const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
+            rowid_l = rec.x;
+            prefetch_row(entity + (size_t)rowid_l * 2 * d, 8 * d);
+            const float2 ab = *reinterpret_cast<const float2*>(bias + (size_t)rowid_l * 2);
+            const float tcnt = __ldg(train_counts + rowid_l);
+            const float eb = bias_eps(eps_bias, c, ul, rowid_l, step);
+            if (!eps_bias) ebs[ul] = eb;
+            const float tau = link_fn<LINK>(ab.y);
+            ws[ul] = fmaf(eb, tau, ab.x);
+            klb = kl_std_normal(ab.x, tau);
+            const int cls = class_of(c, rowid_l);
+            float csz = 0.f, zc = 1.f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            int k = (gl + i * LPR) * VEC;
-            if (k < d) {
-                Vec<VEC> mu = ld_vec<VEC>(erow + k), rho = ld_vec<VEC>(erow + d + k);
-                Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid, k, step), out;
+            for (int i = 0; i < kMaxFields; ++i) if (i == cls) { csz = c.class_size[i]; zc = __ldg(z + i); }
+            cqv = ((float)rec.y / tcnt) * (csz / zc);        // c_u of SURVEY 8-Maths
+            cq[ul] = cqv;
+        }
+        float klrow = 0.f;
+        // ---- wide work: GPW rows per round, LPR lanes per row
+#pragma unroll 1
+        for (int it = 0; it < kRounds; ++it) {
+            const int sel = it * GPW + gidx;
+            const int rowid = bcast(rowid_l, sel);
+            const int u = base + sel;
+            float kl = 0.f;
+            if (u < U) {
+                const float* erow = entity + (size_t)rowid * 2 * d;
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    float sig = link_fn<LINK>(rho.v[j]);
-                    out.v[j] = mu.v[j] + e.v[j] * sig;
-                    kl += kl_std_normal(mu.v[j], sig);
+                for (int i = 0; i < NV; ++i) {
+                    int k = (gl + i * LPR) * VEC;
+                    if (k < d) {
+                        Vec<VEC> mu = ld_vec<VEC>(erow + k), rho = ld_vec<VEC>(erow + d + k);
+                        Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid, k, step), out;
+                        if (!eps_entity) st_vec<VEC>(es + (size_t)u * d + k, e);
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) {
+                            float sig = link_fn<LINK>(rho.v[j]);
+                            out.v[j] = fmaf(e.v[j], sig, mu.v[j]);
+                            kl += kl_std_normal_fast(mu.v[j], sig);
+                        }
+                        st_vec<VEC>(vs + (size_t)u * d + k, out);
+                    }
                 }
-                st_vec<VEC>(vs + (size_t)u * d + k, out);
+                kl = group_sum<LPR>(kl, gmask);
             }
+            hand_back<LPR>(klrow, kl, it, lane);
         }
-        kl = group_sum<LPR>(kl, group_mask<LPR>());
-        if (gl == 0) {
-            float a = bias[(size_t)rowid * 2], b = bias[(size_t)rowid * 2 + 1];
-            float tau = link_fn<LINK>(b);
-            ws[u] = a + bias_eps(eps_bias, c, u, rowid, step) * tau;
-            kl += kl_std_normal(a, tau);
-            float q = (float)(seg_off[u + 1] - seg_off[u]) / __ldg(train_counts + rowid);
-            int cls = class_of(c, rowid);
-            double t = (double)(q * kl);
-#pragma unroll
-            for (int i = 0; i < kMaxFields; ++i) if (i == cls) acc[i] += t;
-            heavy_done[u] = 0;
-        }
+        if (valid) facc = fmaf(cqv, klrow + klb, facc);
     }
-    if (block_partials<kMaxFields>(acc, partials, counter)) {
+    double acc[1] = {(double)facc};
+    if (block_partials<1>(acc, partials, counter)) {
+        double tot[1];
+        final_sums<1>(partials, tot);
         if (threadIdx.x == 0) {
-            double kl_rows = 0.0;
-            for (int i = 0; i < c.n_classes; ++i)
-                kl_rows += (double)(c.class_size[i] / z[i]) * final_sum<kMaxFields>(partials, i);
-            stats[VFMB_ST_KL_ROWS] = (float)kl_rows;
+            stats[VFMB_ST_KL_ROWS] = (float)tot[0];
             stats[VFMB_ST_U] = (float)U;
             *counter = 0;
         }
@@ -172,101 +239,127 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
 template <int VEC, int LPR, int NV, int LINK, int LIK>
 __global__ void __launch_bounds__(256)
 k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__ inverse,
-        const float* __restrict__ vs, const float* __restrict__ ws, const float* __restrict__ y,
-        const float* __restrict__ eps_global, const int32_t* __restrict__ adam_step,
-        float* __restrict__ pred, float* __restrict__ mean, float* __restrict__ resid,
-        float* __restrict__ msg, double* __restrict__ partials, int32_t* __restrict__ counter,
-        float* __restrict__ stats) {
-    constexpr int GPW = kWarp / LPR;
+        const int32_t* __restrict__ pos_of, const float* __restrict__ vs, const float* __restrict__ ws,
+        const float* __restrict__ y, const float* __restrict__ eps_global,
+        const int32_t* __restrict__ adam_step, float* __restrict__ pred, float* __restrict__ mean,
+        float* __restrict__ resid, float* __restrict__ rsorted, float* __restrict__ msg,
+        double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
+    constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
     const int d = c.d, F = c.F, B = c.B;
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
-    const int lane = threadIdx.x & 31, gl = lane % LPR;
-    const int group = (threadIdx.x >> 5) * GPW + lane / LPR;
-    const int groups_per_block = (blockDim.x >> 5) * GPW;
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
+    const unsigned gmask = group_mask<LPR>();
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
     const float mu0 = scalars[VFMB_S_GB_MEAN];
     const float sig0 = link_fn<LINK>(scalars[VFMB_S_GB_SCALE]);
     const float w0 = mu0 + global_eps(eps_global, c, step) * sig0;
     const float alpha = link_fn<LINK>(scalars[VFMB_S_ALPHA]);
+    const float half_log_alpha = 0.5f * logf(alpha);
     const float scale = c.n_train / ((float)c.S * (float)B);
     double acc[3] = {0.0, 0.0, 0.0};     // nll, resid, squared error
 
-    for (int n = blockIdx.x * groups_per_block + group; n < B; n += gridDim.x * groups_per_block) {
-        float part = 0.f, bsum = 0.f;
-        Vec<VEC> ssum[NV];
-        if (F == 2) {
-            int r0 = __ldg(inverse + 2 * n), r1 = __ldg(inverse + 2 * n + 1);
-            bsum = __ldg(ws + r0) + __ldg(ws + r1);
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                int k = (gl + i * LPR) * VEC;
-                if (k < d) {
-                    Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r0 * d + k);
-                    Vec<VEC> b = ld_vec_nc<VEC>(vs + (size_t)r1 * d + k);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) part += a.v[j] * b.v[j];
-                }
-            }
-        } else {
-            Vec<VEC> sq[NV];
-#pragma unroll
-            for (int i = 0; i < NV; ++i)
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) { ssum[i].v[j] = 0.f; sq[i].v[j] = 0.f; }
-            for (int f = 0; f < F; ++f) {
-                int r = __ldg(inverse + (size_t)n * F + f);
-                bsum += __ldg(ws + r);
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-                        Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r * d + k);
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) { ssum[i].v[j] += a.v[j]; sq[i].v[j] += a.v[j] * a.v[j]; }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NV; ++i)
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) part += 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]);
-        }
-        const float inter = group_sum<LPR>(part, group_mask<LPR>());
-        const float p = w0 + bsum + inter;
-        float r = 0.f, mu_out = p;
-        if (LIK == VFMB_BERNOULLI) mu_out = 1.f / (1.f + expf(-p));
-        if (y) {
-            const float yn = __ldg(y + n);
-            float nll, err = yn - p;
-            if (LIK == VFMB_GAUSSIAN) {
-                nll = 0.5f * alpha * err * err - 0.5f * logf(alpha) + 0.9189385332046727f;
-                r = scale * alpha * (p - yn);
+    for (int base = gwarp * CH; base < B; base += nwarps * CH) {
+        // ---- lane-parallel: one sample per lane (ranks, bias sum, target)
+        const int nl = base + lane;
+        const bool valid = lane < CH && nl < B;
+        int2 rr = make_int2(0, 0);
+        float bsum = 0.f, yn = 0.f;
+        if (valid) {
+            if (F == 2) {
+                rr = __ldg(reinterpret_cast<const int2*>(inverse) + nl);
+                bsum = __ldg(ws + rr.x) + __ldg(ws + rr.y);
             } else {
-                nll = fmaxf(p, 0.f) - yn * p + log1pf(expf(-fabsf(p)));
-                r = scale * (mu_out - yn);
+                for (int f = 0; f < F; ++f) bsum += __ldg(ws + __ldg(inverse + (size_t)nl * F + f));
             }
-            if (gl == 0) { acc[0] += (double)nll; acc[1] += (double)r; acc[2] += (double)err * (double)err; }
-            if (F > 2 && msg) {
+            if (y) yn = __ldg(y + nl);
+        }
+        float inter_l = 0.f;
+        // ---- wide work: interaction of GPW samples per round
+#pragma unroll 1
+        for (int it = 0; it < kRounds; ++it) {
+            const int sel = it * GPW + gidx;
+            const int n = base + sel;
+            float part = 0.f;
+            if (F == 2) {
+                const int r0 = bcast(rr.x, sel), r1 = bcast(rr.y, sel);
+                if (n < B) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        int k = (gl + i * LPR) * VEC;
+                        if (k < d) {
+                            Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r0 * d + k);
+                            Vec<VEC> b = ld_vec_nc<VEC>(vs + (size_t)r1 * d + k);
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) part = fmaf(a.v[j], b.v[j], part);
+                        }
+                    }
+                }
+            } else if (n < B) {
+                Vec<VEC> ssum[NV], sq[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) { ssum[i].v[j] = 0.f; sq[i].v[j] = 0.f; }
+#pragma unroll 4
+                for (int f = 0; f < F; ++f) {
+                    const int r = __ldg(inverse + (size_t)n * F + f);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        int k = (gl + i * LPR) * VEC;
+                        if (k < d) {
+                            Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r * d + k);
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) { ssum[i].v[j] += a.v[j]; sq[i].v[j] = fmaf(a.v[j], a.v[j], sq[i].v[j]); }
+                        }
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     int k = (gl + i * LPR) * VEC;
                     if (k < d) {
-                        Vec<VEC> o;
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) o.v[j] = r * ssum[i].v[j];
-                        st_vec<VEC>(msg + (size_t)n * d + k, o);
+                        for (int j = 0; j < VEC; ++j) part += 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]);
+                        if (msg) st_vec<VEC>(msg + (size_t)n * d + k, ssum[i]);   // S_n = sum_f v_f (unscaled)
                     }
                 }
             }
+            part = group_sum<LPR>(part, gmask);
+            hand_back<LPR>(inter_l, part, it, lane);
         }
-        if (gl == 0) {
-            pred[n] = p;
-            mean[n] = mu_out;
-            if (y) resid[n] = r;
+        // ---- lane-parallel: likelihood, residual, outputs (coalesced)
+        if (valid) {
+            const float p = w0 + bsum + inter_l;
+            float r = 0.f, mu_out = p;
+            if (LIK == VFMB_BERNOULLI) mu_out = 1.f / (1.f + expf(-p));
+            pred[nl] = p;
+            mean[nl] = mu_out;
+            if (y) {
+                float nll, err = yn - p;
+                if (LIK == VFMB_GAUSSIAN) {
+                    nll = 0.5f * alpha * err * err - half_log_alpha + 0.9189385332046727f;
+                    r = scale * alpha * (p - yn);
+                } else {
+                    nll = fmaxf(p, 0.f) - yn * p + log1pf(expf(-fabsf(p)));
+                    r = scale * (mu_out - yn);
+                }
+                acc[0] += (double)nll; acc[1] += (double)r; acc[2] += (double)err * (double)err;
+                resid[nl] = r;
+                // residual in sorted-occurrence order: the backward reads it coalesced
+                if (F == 2) {
+                    const int2 pp = __ldg(reinterpret_cast<const int2*>(pos_of) + nl);
+                    rsorted[pp.x] = r; rsorted[pp.y] = r;
+                } else {
+                    for (int f = 0; f < F; ++f) rsorted[__ldg(pos_of + (size_t)nl * F + f)] = r;
+                }
+            }
         }
     }
     if (block_partials<3>(acc, partials, counter)) {
+        double tot[3];
+        final_sums<3>(partials, tot);
         if (threadIdx.x == 0) {
-            double nll = final_sum<3>(partials, 0), sr = final_sum<3>(partials, 1), sq = final_sum<3>(partials, 2);
+            double nll = tot[0], sr = tot[1], sq = tot[2];
             float kl0 = kl_std_normal(mu0, sig0);
             float kl = kl0 + stats[VFMB_ST_KL_ROWS];
             stats[VFMB_ST_NLL_MEAN] = (float)(nll / (double)B);
@@ -280,7 +373,218 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
     }
 }
 
-// ------------------------------------------------------------------------------- k_rows
+// residuals supplied by the caller (autograd path): scatter them into sorted-occurrence order
+__global__ void __launch_bounds__(256)
+k_scatter_resid(const float* __restrict__ resid, const int32_t* __restrict__ pos_of, int N, int F,
+                float* __restrict__ rsorted) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < N; o += gridDim.x * blockDim.x)
+        rsorted[pos_of[o]] = resid[o / F];
+}
+
+// ------------------------------------------------------------------------------- k_gather
+// Backward, phase A: deterministic segmented reduction over the SORTED occurrence list, tiled by
+// position so that every lane group does the same amount of work whatever the row popularity
+// (a Zipf head row with thousands of occurrences is just many tiles).  A group walks the kTile
+// positions of its tile in order, accumulating r_n * partner row; when the unique rank changes it
+// flushes.  Rows that lie inside the tile are final (-> grow/gws).  A row cut by a tile boundary
+// leaves a partial in the tile's head slot (row continues from the previous tile) or tail slot
+// (row starts here and continues); k_adam_rows adds a row's partials in tile order.  Fixed
+// summation order, no atomics => bitwise reproducible.
+// Everything read here is L2-resident scratch written by k_stage / k_score.
+template <int VEC, int LPR, int NV>
+__global__ void __launch_bounds__(256)
+k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
+         const float* __restrict__ vs, const float* __restrict__ msg, const float* __restrict__ rsorted,
+         float* __restrict__ gslot, float* __restrict__ grow, float* __restrict__ gws) {
+    constexpr int GPW = kWarp / LPR;
+    const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
+    const int lane = threadIdx.x & 31, gl = lane % LPR;
+    const unsigned gmask = group_mask<LPR>();
+    const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
+    const int ngroups = gridDim.x * (blockDim.x >> 5) * GPW;
+    const int n_tiles = (N + kTile - 1) / kTile;
+    const float* table = (F == 2) ? vs : msg;
+
+    for (int tile = group; tile < n_tiles; tile += ngroups) {
+        const int t0 = tile * kTile, t1 = min(N, t0 + kTile);
+        // does the first row continue from the previous tile / the last row into the next one?
+        const bool head_open = t0 > 0 && __ldg(pos_rank + t0 - 1) == __ldg(pos_rank + t0);
+        const bool tail_open = t1 < N && __ldg(pos_rank + t1) == __ldg(pos_rank + t1 - 1);
+        const int first_u = __ldg(pos_rank + t0), last_u = __ldg(pos_rank + t1 - 1);
+        int cur = first_u;
+        Vec<VEC> acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
+        float gw = 0.f;
+
+        auto flush = [&](int u) {
+            const bool open_h = head_open && u == first_u, open_t = tail_open && u == last_u;
+            float* dst; float* dstw;
+            if (open_h)      { dst = gslot + ((size_t)tile * 2) * dp;     dstw = dst + d; }
+            else if (open_t) { dst = gslot + ((size_t)tile * 2 + 1) * dp; dstw = dst + d; }
+            else             { dst = grow + (size_t)u * d;                dstw = gws + u; }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                int k = (gl + i * LPR) * VEC;
+                if (k < d) {
+                    if (F > 2 && !open_h && !open_t) {  // pairwise, complete row: sum r_n (S_n - v_u)
+                        Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) acc[i].v[j] = fmaf(-gw, own.v[j], acc[i].v[j]);
+                    }
+                    st_vec<VEC>(dst + k, acc[i]);
+                }
+            }
+            if (gl == 0) *dstw = gw;
+        };
+
+        for (int b0 = t0; b0 < t1; b0 += LPR) {
+            const int idx = b0 + gl;
+            const bool ok = idx < t1;
+            const float r = ok ? __ldg(rsorted + idx) : 0.f;
+            const int src = ok ? __ldg(partner + idx) : 0;
+            const int ur = ok ? __ldg(pos_rank + idx) : 0;
+            const int cnt = min(LPR, t1 - b0);
+            const int src0 = __shfl_sync(gmask, src, 0, LPR);
+            for (int j = 0; j < cnt; j += 4) {                 // 4 row gathers in flight
+                float rj[4]; int uj[4]; Vec<VEC> t[4][NV];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    rj[e] = __shfl_sync(gmask, r, (j + e) & (LPR - 1), LPR);
+                    uj[e] = __shfl_sync(gmask, ur, (j + e) & (LPR - 1), LPR);
+                    int sj = __shfl_sync(gmask, src, (j + e) & (LPR - 1), LPR);
+                    if (j + e >= cnt) sj = src0;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        int k = (gl + i * LPR) * VEC;
+                        if (k < d) t[e][i] = ld_vec_nc<VEC>(table + (size_t)sj * d + k);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (j + e < cnt) {                         // group-uniform
+                        if (uj[e] != cur) {
+                            flush(cur);
+                            cur = uj[e];
+#pragma unroll
+                            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) acc[i].v[q] = 0.f;
+                            gw = 0.f;
+                        }
+                        gw += rj[e];
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            int k = (gl + i * LPR) * VEC;
+                            if (k < d)
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) acc[i].v[q] = fmaf(rj[e], t[e][i].v[q], acc[i].v[q]);
+                        }
+                    }
+                }
+            }
+        }
+        flush(cur);
+    }
+}
+
+// ------------------------------------------------------------------------------- k_combine
+// Rows cut by tile boundaries: add the tile partials in tile order (tail slot of the first tile,
+// then the head slots of the following tiles).  A warp scans 32 rows, and the whole warp works on
+// each cut row: its GPW lane groups take contiguous ranges of the partials and the group sums are
+// added in group order -- a fixed association, so still bitwise reproducible.
+template <int VEC, int LPR, int NV>
+__global__ void __launch_bounds__(256)
+k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
+          const float* __restrict__ gslot, const float* __restrict__ vs,
+          float* __restrict__ grow, float* __restrict__ gws) {
+    constexpr int GPW = kWarp / LPR;
+    const int U = meta[0];
+    const int dp = d + 4;
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int base = gwarp * 32; base < U; base += nwarps * 32) {
+        const int ul = base + lane;
+        int tA_l = 0, tB_l = 0;
+        if (ul < U) {
+            const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
+            tA_l = rec.z / kTile;                          // first / last tile of the row's segment
+            tB_l = (rec.z + rec.y - 1) / kTile;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, tA_l != tB_l);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int u = base + src;
+            const int tA = __shfl_sync(0xffffffffu, tA_l, src), tB = __shfl_sync(0xffffffffu, tB_l, src);
+            const int P = tB - tA;                          // head slots tA+1 .. tB
+            const int per = (P + GPW - 1) / GPW;
+            const int lo = tA + 1 + gidx * per, hi = min(tB + 1, lo + per);
+            Vec<VEC> acc[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
+            float gw = 0.f;
+            for (int t = lo; t < hi; t += 4) {
+                Vec<VEC> part[4][NV]; float pw[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int tt = min(t + q, hi - 1);
+                    const float* sp = gslot + ((size_t)tt * 2) * dp;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        int k = (gl + i * LPR) * VEC;
+                        if (k < d) part[q][i] = ld_vec_nc<VEC>(sp + k);
+                    }
+                    pw[q] = __ldg(sp + d);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (t + q < hi) {
+#pragma unroll
+                        for (int i = 0; i < NV; ++i)
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) acc[i].v[j] += part[q][i].v[j];
+                        gw += pw[q];
+                    }
+            }
+            // total = tail(tA) + group 0 + group 1 + ...
+            const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
+            float gw_tot = __ldg(tp + d);
+#pragma unroll
+            for (int g = 0; g < GPW; ++g) gw_tot += __shfl_sync(0xffffffffu, gw, g * LPR);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                int k = (gl + i * LPR) * VEC;
+                Vec<VEC> tot;
+                if (k < d) tot = ld_vec_nc<VEC>(tp + k);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+#pragma unroll
+                    for (int g = 0; g < GPW; ++g) {
+                        float v = __shfl_sync(0xffffffffu, acc[i].v[j], g * LPR + gl);
+                        if (k < d) tot.v[j] += v;
+                    }
+                }
+                if (k < d && gidx == 0) {
+                    if (F > 2) {                           // pairwise: sum r_n (S_n - v_u)
+                        Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) tot.v[j] = fmaf(-gw_tot, own.v[j], tot.v[j]);
+                    }
+                    st_vec<VEC>(grow + (size_t)u * d + k, tot);
+                }
+            }
+            if (lane == 0) gws[u] = gw_tot;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- k_adam_rows
 // hyper-parameters as torch rounds them: every derived constant is formed in double first
 struct AdamDev {
     double lr, beta1, beta2;
@@ -294,185 +598,123 @@ static AdamDev make_adam(const vfmb_adam* a) {
     return h;
 }
 
-__device__ __forceinline__ void adam_coeffs(const AdamDev& h, int t, float* step_size, float* bc2_sqrt) {
+// step_size = lr / (1 - beta1^t), inv_bc2_sqrt = 1 / sqrt(1 - beta2^t)
+__device__ __forceinline__ void adam_coeffs(const AdamDev& h, int t, float* step_size, float* inv_bc2_sqrt) {
     double bc1 = 1.0 - pow(h.beta1, (double)t);
     double bc2 = 1.0 - pow(h.beta2, (double)t);
     *step_size = (float)(h.lr / bc1);
-    *bc2_sqrt = (float)sqrt(bc2);
+    *inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
 }
 
 // torch _single_tensor_adam: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
 // p.addcdiv_(m, sqrt(v)/bc2_sqrt + eps, -step_size)
 __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const AdamDev& h,
-                                          float step_size, float bc2_sqrt) {
-    m = m + (g - m) * h.omb1;
-    v = v * h.b2 + h.omb2 * g * g;
-    float denom = sqrtf(v) / bc2_sqrt + h.eps;
-    p = p - step_size * (m / denom);
+                                          float step_size, float inv_bc2_sqrt) {
+    m = fmaf(g - m, h.omb1, m);
+    v = fmaf(v, h.b2, h.omb2 * g * g);
+    float denom = fmaf(fast_sqrt(v), inv_bc2_sqrt, h.eps);
+    p = fmaf(-step_size, m * fast_rcp(denom), p);
 }
 
+// Backward, phase B: per unique row, chain rule from (g_v, g_w) to (mean, raw scale) plus the KL
+// gradient, then Adam on the row (or the dense-gradient store).  This is the HBM-bound kernel of
+// the step: parameters and both Adam moments of every touched row are read and written once.
 template <int VEC, int LPR, int NV, int LINK, int MODE>
 __global__ void __launch_bounds__(256)
-k_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
-       float* __restrict__ entity, float* __restrict__ entity_m, float* __restrict__ entity_v,
-       const float* __restrict__ train_counts, const int32_t* __restrict__ uniq,
-       const int32_t* __restrict__ inverse, const int32_t* __restrict__ seg_off,
-       const int32_t* __restrict__ occ, const int32_t* __restrict__ item_first,
-       const int32_t* __restrict__ item_row, int32_t* __restrict__ heavy_done,
-       const float* __restrict__ z, const int32_t* __restrict__ meta,
-       const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
-       const float* __restrict__ vs, const float* __restrict__ msg, const float* __restrict__ resid,
-       float* __restrict__ gpart, AdamDev h, const int32_t* __restrict__ adam_step, float kl_scale,
-       float* __restrict__ grad_bias, float* __restrict__ grad_entity) {
-    constexpr int GPW = kWarp / LPR;
-    const int W = meta[1];
-    const int d = c.d, F = c.F;
-    const int dp = d + 4;                               // partial-slot pitch (keeps 16 B alignment)
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
-    const int lane = threadIdx.x & 31, gl = lane % LPR;
-    const int gidx = lane / LPR;
-    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (gidx * LPR));
-    const int group = (threadIdx.x >> 5) * GPW + gidx;
-    const int groups_per_block = (blockDim.x >> 5) * GPW;
-    float step_size = 0.f, bc2_sqrt = 1.f;
-    if (MODE == VFMB_ADAM_TOUCHED) adam_coeffs(h, (int)step + 1, &step_size, &bc2_sqrt);
+k_adam_rows(int d, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
+            float* __restrict__ entity, float* __restrict__ entity_m, float* __restrict__ entity_v,
+            const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
+            const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
+            const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
+            AdamDev h, const int32_t* __restrict__ adam_step, float kl_scale,
+            float* __restrict__ grad_bias, float* __restrict__ grad_entity) {
+    constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
+    const int U = meta[0];
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    __shared__ float s_coef[2];
+    if (MODE == VFMB_ADAM_TOUCHED) {                      // fp64 pow once per block, not per thread
+        if (threadIdx.x == 0) adam_coeffs(h, adam_step[0] + 1, &s_coef[0], &s_coef[1]);
+        __syncthreads();
+    }
+    const float step_size = (MODE == VFMB_ADAM_TOUCHED) ? s_coef[0] : 0.f;
+    const float inv_bc2 = (MODE == VFMB_ADAM_TOUCHED) ? s_coef[1] : 1.f;
 
-    for (int w = blockIdx.x * groups_per_block + group; w < W; w += gridDim.x * groups_per_block) {
-        const int u = item_row[w];
-        const int first = item_first[u], nit = item_first[u + 1] - first, ci = w - first;
-        const int seg0 = seg_off[u], seg1 = seg_off[u + 1];
-        const int s0 = seg0 + ci * kChunk;
-        const int s1 = min(seg1, s0 + kChunk);
-        Vec<VEC> acc[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
-        float gw = 0.f;
-
-        for (int base = s0; base < s1; base += LPR) {
-            const int idx = base + gl;
-            const bool valid = idx < s1;
-            int o = valid ? __ldg(occ + idx) : 0;
-            int n = o / F, f = o - n * F;
-            float r = valid ? __ldg(resid + n) : 0.f;
-            int src = n;                                 // F>2: message row of the sample
-            if (F == 2) src = valid ? __ldg(inverse + 2 * n + (1 - f)) : 0;   // partner's rank
-            const int cnt = min(LPR, s1 - base);
-            const float* table = (F == 2) ? vs : msg;
-            for (int j = 0; j < cnt; ++j) {
-                float rj = __shfl_sync(gmask, r, j, LPR);
-                int sj = __shfl_sync(gmask, src, j, LPR);
-                gw += rj;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-                        Vec<VEC> t = ld_vec_nc<VEC>(table + (size_t)sj * d + k);
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e)
-                            acc[i].v[e] = (F == 2) ? fmaf(rj, t.v[e], acc[i].v[e]) : acc[i].v[e] + t.v[e];
-                    }
-                }
+    for (int base = gwarp * CH; base < U; base += nwarps * CH) {
+        // ---- lane-parallel: record, prefetch of the row's parameter / moment lines, bias update
+        const int ul = base + lane;
+        const bool valid = lane < CH && ul < U;
+        int rowid_l = 0;
+        float cfac_l = 0.f;
+        if (valid) {
+            rowid_l = __ldg(urec + 4 * (size_t)ul);
+            const size_t eoff = (size_t)rowid_l * 2 * d;
+            prefetch_row(entity + eoff, 8 * d);
+            if (MODE == VFMB_ADAM_TOUCHED) {
+                prefetch_row(entity_m + eoff, 8 * d);
+                prefetch_row(entity_v + eoff, 8 * d);
+            }
+            cfac_l = kl_scale * __ldg(cq + ul);
+            const size_t boff = (size_t)rowid_l * 2;
+            float2 ab = *reinterpret_cast<const float2*>(bias + boff);
+            const float gw = __ldg(gws + ul), eb = __ldg(eps_bias + ul);
+            const float tau = link_fn<LINK>(ab.y);
+            const float ga = fmaf(cfac_l, ab.x, gw);
+            const float gb = link_grad<LINK>(ab.y) * fmaf(gw, eb, cfac_l * (tau - fast_rcp(tau)));
+            if (MODE == VFMB_ADAM_TOUCHED) {
+                float2 bm = *reinterpret_cast<const float2*>(bias_m + boff);
+                float2 bv = *reinterpret_cast<const float2*>(bias_v + boff);
+                adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
+                adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
+                *reinterpret_cast<float2*>(bias + boff) = ab;
+                *reinterpret_cast<float2*>(bias_m + boff) = bm;
+                *reinterpret_cast<float2*>(bias_v + boff) = bv;
+            } else {
+                *reinterpret_cast<float2*>(grad_bias + boff) = make_float2(ga, gb);
             }
         }
-
-        if (nit > 1) {
-            // multi-chunk row: publish the partial, the last arriver combines all of them in
-            // chunk order (fixed order => bitwise reproducible)
-            const int slot = 2 * (s0 / kChunk) + (ci > 0 ? 1 : 0);
+        // ---- wide work: GPW rows per round
+#pragma unroll 1
+        for (int it = 0; it < kRounds; ++it) {
+            const int sel = it * GPW + gidx;
+            const int rowid = bcast(rowid_l, sel);
+            const float cfac = bcast(cfac_l, sel);
+            const int u = base + sel;
+            if (u >= U) continue;
+            const size_t eoff = (size_t)rowid * 2 * d;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 int k = (gl + i * LPR) * VEC;
-                if (k < d) st_vec<VEC>(gpart + (size_t)slot * dp + k, acc[i]);
-            }
-            if (gl == 0) gpart[(size_t)slot * dp + d] = gw;
-            __threadfence();
-            __syncwarp(gmask);
-            int old = 0;
-            if (gl == 0) old = atomicAdd(heavy_done + u, 1);
-            old = __shfl_sync(gmask, old, 0, LPR);
-            if (old != nit - 1) continue;
-            __threadfence();
-#pragma unroll
-            for (int i = 0; i < NV; ++i)
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
-            gw = 0.f;
-            for (int cc = 0; cc < nit; ++cc) {
-                const int sl = 2 * ((seg0 + cc * kChunk) / kChunk) + (cc > 0 ? 1 : 0);
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-                        const float* q = gpart + (size_t)sl * dp + k;
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[i].v[e] += __ldcg(q + e);
+                if (k < d) {
+                    Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
+                    Vec<VEC> m1, m2, v1, v2;
+                    if (MODE == VFMB_ADAM_TOUCHED) {
+                        m1 = ld_vec<VEC>(entity_m + eoff + k); m2 = ld_vec<VEC>(entity_m + eoff + d + k);
+                        v1 = ld_vec<VEC>(entity_v + eoff + k); v2 = ld_vec<VEC>(entity_v + eoff + d + k);
                     }
-                }
-                gw += __ldcg(gpart + (size_t)sl * dp + d);
-            }
-        }
-
-        // ---- epilogue: chain rule to (mu, rho), KL gradient, Adam / gradient store
-        const int rowid = uniq[u];
-        const float q = (float)(seg1 - seg0) / __ldg(train_counts + rowid);
-        const int cls = class_of(c, rowid);
-        float csz = 0.f, zc = 1.f;
-#pragma unroll
-        for (int i = 0; i < kMaxFields; ++i) if (i == cls) { csz = c.class_size[i]; zc = __ldg(z + i); }
-        const float cfac = kl_scale * q * (csz / zc);
-        const size_t eoff = (size_t)rowid * 2 * d;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            int k = (gl + i * LPR) * VEC;
-            if (k < d) {
-                Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
-                Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid, k, step);
-                Vec<VEC> gmu, grho;
-                if (F > 2) {
-                    Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) acc[i].v[j] -= gw * own.v[j];
-                }
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    float sig = link_fn<LINK>(rho.v[j]);
-                    gmu.v[j] = acc[i].v[j] + cfac * mu.v[j];
-                    grho.v[j] = link_grad<LINK>(rho.v[j]) * (acc[i].v[j] * e.v[j] + cfac * (sig - 1.f / sig));
-                }
-                if (MODE == VFMB_ADAM_TOUCHED) {
-                    Vec<VEC> m1 = ld_vec<VEC>(entity_m + eoff + k), m2 = ld_vec<VEC>(entity_m + eoff + d + k);
-                    Vec<VEC> v1 = ld_vec<VEC>(entity_v + eoff + k), v2 = ld_vec<VEC>(entity_v + eoff + d + k);
+                    const Vec<VEC> g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
+                    const Vec<VEC> e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
+                    Vec<VEC> gmu, grho;
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) {
-                        adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu.v[j], h, step_size, bc2_sqrt);
-                        adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, bc2_sqrt);
+                        float sig = link_fn<LINK>(rho.v[j]);
+                        gmu.v[j] = fmaf(cfac, mu.v[j], g.v[j]);
+                        grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(g.v[j], e.v[j], cfac * (sig - fast_rcp(sig)));
                     }
-                    st_vec<VEC>(entity + eoff + k, mu);        st_vec<VEC>(entity + eoff + d + k, rho);
-                    st_vec<VEC>(entity_m + eoff + k, m1);      st_vec<VEC>(entity_m + eoff + d + k, m2);
-                    st_vec<VEC>(entity_v + eoff + k, v1);      st_vec<VEC>(entity_v + eoff + d + k, v2);
-                } else {
-                    st_vec<VEC>(grad_entity + eoff + k, gmu);  st_vec<VEC>(grad_entity + eoff + d + k, grho);
+                    if (MODE == VFMB_ADAM_TOUCHED) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) {
+                            adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu.v[j], h, step_size, inv_bc2);
+                            adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, inv_bc2);
+                        }
+                        st_vec<VEC>(entity + eoff + k, mu);        st_vec<VEC>(entity + eoff + d + k, rho);
+                        st_vec<VEC>(entity_m + eoff + k, m1);      st_vec<VEC>(entity_m + eoff + d + k, m2);
+                        st_vec<VEC>(entity_v + eoff + k, v1);      st_vec<VEC>(entity_v + eoff + d + k, v2);
+                    } else {
+                        st_vec<VEC>(grad_entity + eoff + k, gmu);  st_vec<VEC>(grad_entity + eoff + d + k, grho);
+                    }
                 }
-            }
-        }
-        if (gl == 0) {
-            const size_t boff = (size_t)rowid * 2;
-            float a = bias[boff], b = bias[boff + 1];
-            float tau = link_fn<LINK>(b);
-            float eb = bias_eps(eps_bias, c, u, rowid, step);
-            float ga = gw + cfac * a;
-            float gb = link_grad<LINK>(b) * (gw * eb + cfac * (tau - 1.f / tau));
-            if (MODE == VFMB_ADAM_TOUCHED) {
-                float m1 = bias_m[boff], m2 = bias_m[boff + 1], v1 = bias_v[boff], v2 = bias_v[boff + 1];
-                adam_elem(a, m1, v1, ga, h, step_size, bc2_sqrt);
-                adam_elem(b, m2, v2, gb, h, step_size, bc2_sqrt);
-                bias[boff] = a; bias[boff + 1] = b;
-                bias_m[boff] = m1; bias_m[boff + 1] = m2;
-                bias_v[boff] = v1; bias_v[boff + 1] = v2;
-            } else {
-                grad_bias[boff] = ga; grad_bias[boff + 1] = gb;
             }
         }
     }
@@ -519,8 +761,10 @@ __global__ void k_final(DevCfg c, float* __restrict__ scalars, float* __restrict
 __global__ void __launch_bounds__(256)
 k_adam_dense(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
              const float* __restrict__ g, int64_t n, AdamDev h, const int32_t* __restrict__ adam_step) {
-    float ss, b2;
-    adam_coeffs(h, adam_step[0] + 1, &ss, &b2);
+    __shared__ float s_coef[2];
+    if (threadIdx.x == 0) adam_coeffs(h, adam_step[0] + 1, &s_coef[0], &s_coef[1]);
+    __syncthreads();
+    const float ss = s_coef[0], b2 = s_coef[1];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float pi = p[i], mi = m[i], vi = v[i];
         adam_elem(pi, mi, vi, g[i], h, ss, b2);
@@ -584,12 +828,6 @@ static int check_cfg(const vfmb_config* cfg, const char* who) {
     return 0;
 }
 
-static int grid_for(int64_t work_groups, int groups_per_block) {
-    int64_t g = (work_groups + groups_per_block - 1) / groups_per_block;
-    if (g < 1) g = 1;
-    if (g > kMaxGrid) g = kMaxGrid;
-    return (int)g;
-}
 
 }  // namespace vfmb
 
@@ -597,13 +835,22 @@ using namespace vfmb;
 
 extern "C" int64_t vfmb_partials_doubles(const vfmb_config* cfg) {
     if (!cfg) return 0;
-    // block partials of the reductions, then the heavy-row partial slots of k_rows (floats),
+    // block partials of the reductions, then the tile head/tail slots of k_gather (floats),
     // then (closed form) per-block prior-gradient partials
     int64_t n = (int64_t)cfg->B * cfg->F;
-    int64_t slots = 2 * (n / kChunk + 2);
-    int64_t gpart_doubles = (slots * (cfg->d + 4) + 1) / 2;
+    int64_t slots = 2 * ((n + kTile - 1) / kTile + 1);
+    int64_t gslot_doubles = (slots * (cfg->d + 4) + 1) / 2;
     int64_t prior = (int64_t)kPriorGrid * 2 * cfg->F * (1 + cfg->d);
-    return (int64_t)kMaxGrid * 16 + gpart_doubles + prior;
+    return (int64_t)kMaxGrid * 16 + gslot_doubles + prior;
+}
+
+// grid for a kernel whose warps each take `per_warp` units out of at most `units`
+static int grid_warps(int64_t units, int per_warp) {
+    int64_t warps = (units + per_warp - 1) / per_warp;
+    int64_t g = (warps + 7) / 8;
+    if (g < 1) g = 1;
+    if (g > kMaxGrid) g = kMaxGrid;
+    return (int)g;
 }
 
 extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
@@ -612,6 +859,7 @@ extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* t
     if (rc) return rc;
     if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: null argument");
     if (cfg->F > 2 && io->y && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: msg scratch required for F>2");
+    if (!io->eps_entity && !io->es) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: noise scratch (es/ebs) required");
     cudaStream_t stream = (cudaStream_t)stream_;
     Layout L;
     if (!pick_layout(cfg->d, &L)) return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
@@ -619,17 +867,18 @@ extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* t
     vfmb_plan_capacity_t cap;
     rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &cap);
     if (rc) return rc;
-    const int gpb = 8 * (32 / L.lpr);
-    const int grid_u = grid_for(cap.u_cap, gpb), grid_b = grid_for(cfg->B, gpb);
+    const int ch = kRounds * (32 / L.lpr);
+    const int grid_u = grid_warps(cap.u_cap, ch), grid_b = grid_warps(cfg->B, ch);
 #define LAUNCH_STAGE(LINK)                                                                             \
     k_stage<VEC, LPR, NV, LINK><<<grid_u, 256, 0, stream>>>(                                           \
-        dc, tab->bias, tab->entity, tab->train_counts, plan->uniq, plan->seg_off, plan->meta, plan->z, \
-        plan->heavy_done, io->eps_bias, io->eps_entity, tab->adam_step, io->vs, io->ws, io->partials,  \
-        io->counters + 0, io->stats)
+        dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
+        io->eps_bias, io->eps_entity, tab->adam_step, io->vs, io->ws, io->es,                          \
+        io->ebs, io->cq, io->partials, io->counters + 0, io->stats)
 #define LAUNCH_SCORE(LINK, LIK)                                                                        \
     k_score<VEC, LPR, NV, LINK, LIK><<<grid_b, 256, 0, stream>>>(                                      \
-        dc, tab->scalars, plan->inverse, io->vs, io->ws, io->y, io->eps_global, tab->adam_step,        \
-        io->pred, io->mean, io->resid, io->msg, io->partials, io->counters + 1, io->stats)
+        dc, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->y, io->eps_global,          \
+        tab->adam_step, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials,             \
+        io->counters + 1, io->stats)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
             LAUNCH_STAGE(0);
@@ -658,6 +907,7 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
         return set_error(VFMB_EINVAL, "vfmb_sampled_backward: gradient outputs required");
     if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: bad mode");
     if (cfg->F > 2 && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: msg scratch required for F>2");
+    if (!io->grow || !io->gws || !io->cq || !io->rsorted) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: scratch required");
     cudaStream_t stream = (cudaStream_t)stream_;
     Layout L;
     if (!pick_layout(cfg->d, &L)) return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
@@ -666,23 +916,39 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
     rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &cap);
     if (rc) return rc;
     AdamDev h = make_adam(adam);
-    const int gpb = 8 * (32 / L.lpr);
-    const int grid_w = grid_for(cap.w_cap, gpb);
-    float* gpart = (float*)(io->partials + (size_t)kMaxGrid * 16);   // heavy-row partial slots follow
-#define LAUNCH_ROWS(LINK, MODE)                                                                          \
-    k_rows<VEC, LPR, NV, LINK, MODE><<<grid_w, 256, 0, stream>>>(                                        \
-        dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,              \
-        tab->train_counts, plan->uniq, plan->inverse, plan->seg_off, plan->occ, plan->item_first,        \
-        plan->item_row, plan->heavy_done, plan->z, plan->meta, io->eps_bias, io->eps_entity, io->vs,     \
-        io->msg, io->resid, gpart, h, tab->adam_step, kl_grad_scale, io->grad_bias, io->grad_entity)
+    const int ch = kRounds * (32 / L.lpr);
+    const int grid_u = grid_warps(cap.u_cap, ch), grid_t = grid_warps(cap.n_tiles, 32 / L.lpr);
+    float* gslot = (float*)(io->partials + (size_t)kMaxGrid * 16);   // tile head/tail slots follow
+    // the noise the forward used: injected arrays, or what k_stage wrote to scratch (Philox)
+    const float* eps_e = io->eps_entity ? io->eps_entity : io->es;
+    const float* eps_b = io->eps_bias ? io->eps_bias : io->ebs;
+    if (mode == VFMB_GRAD_ONLY) {
+        // the residuals may come from the caller's autograd: (re)build their sorted-order copy
+        if (!io->resid) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: resid required");
+        const int N = cfg->B * cfg->F;
+        int g = (N + 255) / 256;
+        if (g > 4 * kNumSMs) g = 4 * kNumSMs;
+        k_scatter_resid<<<g, 256, 0, stream>>>(io->resid, plan->pos_of, N, cfg->F, io->rsorted);
+        CUDA_TRY(cudaGetLastError());
+    }
+#define LAUNCH_ADAM(LINK, MODE)                                                                          \
+    k_adam_rows<VEC, LPR, NV, LINK, MODE><<<grid_u, 256, 0, stream>>>(                                   \
+        cfg->d, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,          \
+        plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, h, tab->adam_step,              \
+        kl_grad_scale, io->grad_bias, io->grad_entity)
     VFMB_LAYOUT_SWITCH(L, {
+        k_gather<VEC, LPR, NV><<<grid_t, 256, 0, stream>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
+                                                           plan->pos_rank, io->vs, io->msg, io->rsorted,
+                                                           gslot, io->grow, io->gws);
+        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 0, stream>>>(
+            cfg->d, cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
         if (cfg->link == VFMB_LINK_ABS) {
-            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ROWS(0, VFMB_ADAM_TOUCHED); else LAUNCH_ROWS(0, VFMB_GRAD_ONLY);
+            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM(0, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM(0, VFMB_GRAD_ONLY);
         } else {
-            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ROWS(1, VFMB_ADAM_TOUCHED); else LAUNCH_ROWS(1, VFMB_GRAD_ONLY);
+            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM(1, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM(1, VFMB_GRAD_ONLY);
         }
     });
-#undef LAUNCH_ROWS
+#undef LAUNCH_ADAM
     CUDA_TRY(cudaGetLastError());
     if (mode == VFMB_GRAD_ONLY && !io->grad_scalars) return 0;
 #define LAUNCH_FINAL(LINK, LIK, MODE)                                                                    \

@@ -31,21 +31,22 @@ class BatchPlan:
         cap = L.PlanCapacity()
         L.check(L.lib().vfmb_plan_capacity(B, F, R, C.byref(cap)), "vfmb_plan_capacity")
         self.B_cap, self.F, self.R = B, F, R
-        self.u_cap, self.w_cap, self.chunk = int(cap.u_cap), int(cap.w_cap), int(cap.chunk)
+        self.u_cap, self.n_tiles, self.tile = int(cap.u_cap), int(cap.n_tiles), int(cap.tile)
         self.uniq = _i32(self.u_cap, device)
         self.inverse = _i32(B * F, device)
         self.seg_off = _i32(self.u_cap + 1, device)
         self.occ = _i32(B * F, device)
-        self.item_first = _i32(self.u_cap + 1, device)
-        self.item_row = _i32(self.w_cap, device)
-        self.heavy_done = torch.zeros(self.u_cap, dtype=torch.int32, device=device)
+        self.pos_of = _i32(B * F, device)
+        self.pos_rank = _i32(B * F, device)
+        self.partner = _i32(B * F, device)
+        self.urec = _i32(4 * self.u_cap, device)
         self.z = torch.zeros(L.MAX_FIELDS, dtype=torch.float32, device=device)
         self.meta = torch.zeros(8, dtype=torch.int32, device=device)
         self.workspace = torch.empty(int(cap.workspace_bytes), dtype=torch.uint8, device=device)
         self.B = 0
         self.struct = L.Plan(L.ptr(self.uniq), L.ptr(self.inverse), L.ptr(self.seg_off),
-                             L.ptr(self.occ), L.ptr(self.item_first), L.ptr(self.item_row),
-                             L.ptr(self.heavy_done), L.ptr(self.z), L.ptr(self.meta))
+                             L.ptr(self.occ), L.ptr(self.pos_of), L.ptr(self.pos_rank), L.ptr(self.partner),
+                             L.ptr(self.urec), L.ptr(self.z), L.ptr(self.meta))
 
     def build(self, cfg: L.Config, x: torch.Tensor, train_counts: torch.Tensor) -> "BatchPlan":
         assert x.dtype == torch.int64 and x.is_cuda and x.is_contiguous(), "x: contiguous CUDA int64 [B,F]"
@@ -81,11 +82,16 @@ class StepBuffers:
         B, d = plan.B_cap, cfg.d
         self.vs = _f32(plan.u_cap * d, device)
         self.ws = _f32(plan.u_cap, device)
-        self.aux = None
+        self.es = _f32(plan.u_cap * d, device)
+        self.ebs = _f32(plan.u_cap, device)
+        self.cq = _f32(plan.u_cap, device)
+        self.grow = _f32(plan.u_cap * d, device)
+        self.gws = _f32(plan.u_cap, device)
         self.msg = _f32(B * d, device) if need_msg else None
         self.pred = _f32(B, device)
         self.mean = _f32(B, device)
         self.resid = _f32(B, device)
+        self.rsorted = _f32(B * plan.F, device)
         n_part = int(L.lib().vfmb_partials_doubles(C.byref(cfg)))
         self.partials = torch.zeros(n_part, dtype=torch.float64, device=device)
         self.counters = torch.zeros(8, dtype=torch.int32, device=device)
@@ -101,8 +107,9 @@ class StepBuffers:
                 assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
         r = self.resid if resid is None else resid
         return L.StepIO(L.ptr(y), L.ptr(e0), L.ptr(eb), L.ptr(ee), L.ptr(self.vs), L.ptr(self.ws),
+                        L.ptr(self.es), L.ptr(self.ebs), L.ptr(self.cq), L.ptr(self.grow), L.ptr(self.gws),
                         L.ptr(self.msg), L.ptr(self.pred), L.ptr(self.mean), L.ptr(r),
-                        L.ptr(self.partials), L.ptr(self.counters), L.ptr(self.stats),
+                        L.ptr(self.rsorted), L.ptr(self.partials), L.ptr(self.counters), L.ptr(self.stats),
                         L.ptr(grad_bias), L.ptr(grad_entity), L.ptr(self.grad_scalars))
 
 
