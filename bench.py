@@ -143,16 +143,35 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     W, K = args.warmup, args.steps
-    for i in range(W):
-        model.fused_step(*batch(i))
+
+    def run_steps(lo, hi):
+        """Software-pipelined loop: the plan of batch i+1 is built on a side stream while the
+        kernels of batch i run (every batch still gets its own plan, built on the GPU)."""
+        if args.plan == "prefetch":
+            model.prefetch_plan(batch(lo)[0])
+        for i in range(lo, hi):
+            xb, yb = batch(i)
+            if args.plan == "prefetch" and i + 1 < hi:
+                model.prefetch_plan(batch(i + 1)[0])
+            if args.plan == "cached":
+                model.fused_step(xb, yb, plan=static_plans[(i * world + rank) % n_batches])
+            else:
+                model.fused_step(xb, yb)
+
+    static_plans = {}
+    if args.plan == "cached":                               # never-shuffled loader: plans recur every epoch
+        for i in range(W, W + K):
+            j = (i * world + rank) % n_batches
+            if j not in static_plans:
+                static_plans[j] = model.static_plan(batch(i)[0])
+    run_steps(0, W)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for i in range(W, W + K):
-        model.fused_step(*batch(i))
+    run_steps(W, W + K)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -203,7 +222,10 @@ def run_ours(args):
         "config": {"workload": f"{w.name}: {'+'.join(map(str, w.field_sizes))} rows, d={d}, "
                                f"{w.n_train} ratings, batch {B}, {w.variant} ELBO, {w.output}",
                    "fields": F, "unique_rows_per_step": U, "adam": "touched rows (lazy)",
-                   "noise": "Philox4x32-10 in-kernel", "plan": "built every step (CUB radix sort + own kernels)",
+                   "noise": "Philox4x32-10 in-kernel", "plan": {"inline": "built every step on the step's stream",
+                            "prefetch": "built every step, one batch ahead on a side stream",
+                            "cached": "precomputed per batch (never-shuffled loader)"}[args.plan]
+                           + " (CUB radix sort + own kernels)",
                    "l2": "params+Adam state 258 MB > 126 MB L2; consecutive distinct batches, no flush"
                    if args.workload == "ml20m" else "consecutive distinct batches, no flush",
                    "parallelism": f"dp{world}" if world > 1 else "single"},
@@ -225,25 +247,35 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier):
     B, F = w.batch, w.n_fields
     xh = torch.from_numpy(w.x[: n_batches * B]).pin_memory()
     yh = torch.from_numpy(w.y[: n_batches * B]).pin_memory()
-    xd = [torch.empty((B, F), dtype=torch.int64, device=device) for _ in range(2)]
-    yd = [torch.empty(B, dtype=torch.float32, device=device) for _ in range(2)]
+    xd = [torch.empty((B, F), dtype=torch.int64, device=device) for _ in range(3)]
+    yd = [torch.empty(B, dtype=torch.float32, device=device) for _ in range(3)]
     res = torch.empty((K + W, 16), dtype=torch.float32).pin_memory()
 
-    def step(i):
+    copied = [torch.cuda.Event() for _ in range(3)]
+
+    def stage(i):
+        """pinned host -> device copy of batch i's ids and targets, then its plan on the side stream"""
         j = (i * world + rank) % n_batches
-        s = i & 1
+        s = i % 3
         xd[s].copy_(xh[j * B:(j + 1) * B], non_blocking=True)
         yd[s].copy_(yh[j * B:(j + 1) * B], non_blocking=True)
-        out = model.fused_step(xd[s], yd[s])
-        res[i].copy_(out["stats"], non_blocking=True)
+        copied[s].record()
+        model.prefetch_plan(xd[s], after=copied[s])
 
-    for i in range(W):
-        step(i)
+    def run(lo, hi):
+        stage(lo)
+        for i in range(lo, hi):
+            if i + 1 < hi:
+                stage(i + 1)
+            s = i % 3
+            out = model.fused_step(xd[s], yd[s])
+            res[i].copy_(out["stats"], non_blocking=True)      # loss / KL / NLL back to the host
+
+    run(0, W)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(W, W + K):
-        step(i)
+    run(W, W + K)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -329,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ml20m")
     ap.add_argument("--rows", type=int, default=None, help="override the synthetic dataset size")
+    ap.add_argument("--plan", default="prefetch", choices=["inline", "prefetch", "cached"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()

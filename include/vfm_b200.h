@@ -179,6 +179,12 @@ int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* tab, const 
                           const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
                           float kl_grad_scale, vfmb_stream stream);
 
+/* Forward (with targets) + backward + Adam on the touched rows in one call: the whole training
+ * step of vfm-torch.py:351-370 after the plan.  Equivalent to vfmb_sampled_forward followed by
+ * vfmb_sampled_backward(mode VFMB_ADAM_TOUCHED, kl_grad_scale 1). */
+int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                      const vfmb_step_io* io, const vfmb_adam* adam, vfmb_stream stream);
+
 /* Dense Adam sweep over whole tables given dense gradients: the reference's
  * torch.optim.Adam semantics (every row moves every step). */
 int vfmb_adam_dense(float* p, float* m, float* v, const float* g, int64_t n,

@@ -333,3 +333,29 @@ def test_no_cpu_fallback():
     from vae_b200.vfm_torch import CF
     with pytest.raises(RuntimeError):
         CF(4, n_users=3, n_items=3, train_counts=torch.ones(6), device="cpu")
+
+
+def test_prefetched_and_static_plans_give_identical_steps():
+    """The plan depends only on the ids: building it ahead on a side stream, or once per
+    recurring batch, must give bit-identical training steps."""
+    meta, g = gu.load("sampled_reg_d64")
+    xs = [torch.from_numpy(gu.batch_of(meta, g, t)[0]).to(DEV) for t in range(3)]
+    ys = [torch.from_numpy(gu.batch_of(meta, g, t)[1]).to(DEV) for t in range(3)]
+    results = []
+    for mode in ("inline", "prefetch", "static"):
+        m = _model(meta, g, 0, seed=11)
+        plans = [m.static_plan(x) for x in xs] if mode == "static" else None
+        losses = []
+        if mode == "prefetch":
+            m.prefetch_plan(xs[0])
+        for t in range(6):
+            i = t % 3
+            if mode == "prefetch" and t + 1 < 6:
+                m.prefetch_plan(xs[(t + 1) % 3])
+            out = m.fused_step(xs[i], ys[i], plan=plans[i] if plans else None)
+            losses.append(out["loss"].item())
+        torch.cuda.synchronize()
+        results.append((losses, m.entity_params.weight.detach().clone(), m.bias_params.weight.detach().clone()))
+    for losses, ent, bias in results[1:]:
+        assert losses == results[0][0]
+        assert torch.equal(ent, results[0][1]) and torch.equal(bias, results[0][2])

@@ -14,6 +14,9 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <mutex>
+#include <unordered_map>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -145,13 +148,23 @@ static PlanWs carve(void* base, int N, int u_cap) {
     w.rank = (int32_t*)take((size_t)N * 4);
     w.partials = (double*)take((size_t)kPlanGrid * kMaxFields * 8);
     w.counter = (int32_t*)take(256);
-    size_t sort_b = 0, scan_b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (int32_t*)nullptr, (int32_t*)nullptr,
-                                    (int32_t*)nullptr, (int32_t*)nullptr, N, 0, 31);
-    cub::TransformInputIterator<int32_t, HeadFlag, cub::CountingInputIterator<int>> it(
-        cub::CountingInputIterator<int>(0), HeadFlag{nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, scan_b, it, (int32_t*)nullptr, N);
-    w.cub_bytes = sort_b > scan_b ? sort_b : scan_b;
+    // CUB temp-storage sizes: host-side queries, cached per N (they cost microseconds per call)
+    static std::mutex mu;
+    static std::unordered_map<int, size_t> cache;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it0 = cache.find(N);
+        if (it0 == cache.end()) {
+            size_t sort_b = 0, scan_b = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (int32_t*)nullptr, (int32_t*)nullptr,
+                                            (int32_t*)nullptr, (int32_t*)nullptr, N, 0, 31);
+            cub::TransformInputIterator<int32_t, HeadFlag, cub::CountingInputIterator<int>> it(
+                cub::CountingInputIterator<int>(0), HeadFlag{nullptr});
+            cub::DeviceScan::InclusiveSum(nullptr, scan_b, it, (int32_t*)nullptr, N);
+            it0 = cache.emplace(N, sort_b > scan_b ? sort_b : scan_b).first;
+        }
+        w.cub_bytes = it0->second;
+    }
     w.cub = take(w.cub_bytes);
     w.total = off;
     return w;

@@ -128,6 +128,7 @@ __device__ __forceinline__ void final_sums(const double* __restrict__ partials, 
 // prefetched into L2 up front.  This keeps ~50 warps per SM busy while taking the per-row scalar
 // code out of the wide path, where it ran at 1/LPR lane efficiency.
 constexpr int kRounds = 4;
+#define GPW_OF(LPR) (32 / (LPR))
 
 template <typename T>
 __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -492,21 +493,62 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
 
 // ------------------------------------------------------------------------------- k_combine
 // Rows cut by tile boundaries: add the tile partials in tile order (tail slot of the first tile,
-// then the head slots of the following tiles).  A warp scans 32 rows, and the whole warp works on
-// each cut row: its GPW lane groups take contiguous ranges of the partials and the group sums are
-// added in group order -- a fixed association, so still bitwise reproducible.
+// then the head slots of the following tiles).  A block scans 256 rows.  Rows with few partials
+// are handled per warp (GPW lane groups take contiguous ranges, group sums added in group order);
+// the rare hot rows (> kHotPartials tiles: a Zipf head row with thousands of occurrences) are
+// handled by the whole block, 8*GPW groups over contiguous ranges and a fixed-order shared-memory
+// reduction.  Every association is fixed by the plan, so the result is bitwise reproducible.
+constexpr int kHotPartials = 32;
+
+template <int VEC, int LPR, int NV, int UNR>
+__device__ __forceinline__ void sum_head_slots(const float* __restrict__ gslot, int dp, int d, int gl,
+                                               int lo, int hi, Vec<VEC> (&acc)[NV], float& gw) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
+    gw = 0.f;
+    for (int t = lo; t < hi; t += UNR) {
+        Vec<VEC> part[UNR][NV]; float pw[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+            const int tt = min(t + q, hi - 1);
+            const float* sp = gslot + ((size_t)tt * 2) * dp;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                int k = (gl + i * LPR) * VEC;
+                if (k < d) part[q][i] = ld_vec_nc<VEC>(sp + k);
+            }
+            pw[q] = __ldg(sp + d);
+        }
+#pragma unroll
+        for (int q = 0; q < UNR; ++q)
+            if (t + q < hi) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[i].v[j] += part[q][i].v[j];
+                gw += pw[q];
+            }
+    }
+}
+
 template <int VEC, int LPR, int NV>
 __global__ void __launch_bounds__(256)
 k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
           const float* __restrict__ gslot, const float* __restrict__ vs,
           float* __restrict__ grow, float* __restrict__ gws) {
-    constexpr int GPW = kWarp / LPR;
+    constexpr int GPW = kWarp / LPR, NG = 8 * GPW;
+    extern __shared__ float s_part[];                    // [NG][dp] block-level partial sums
+    __shared__ int s_hot[256];
+    __shared__ int s_nhot;
     const int U = meta[0];
     const int dp = d + 4;
-    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
-    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int base = gwarp * 32; base < U; base += nwarps * 32) {
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR, warp = threadIdx.x >> 5;
+    for (int bbase = blockIdx.x * 256; bbase < U; bbase += gridDim.x * 256) {
+        if (threadIdx.x == 0) s_nhot = 0;
+        __syncthreads();
+        const int base = bbase + warp * 32;
         const int ul = base + lane;
         int tA_l = 0, tB_l = 0;
         if (ul < U) {
@@ -514,44 +556,19 @@ k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restr
             tA_l = rec.z / kTile;                          // first / last tile of the row's segment
             tB_l = (rec.z + rec.y - 1) / kTile;
         }
-        unsigned todo = __ballot_sync(0xffffffffu, tA_l != tB_l);
+        const int P_l = tB_l - tA_l;
+        if (P_l > kHotPartials) s_hot[atomicAdd(&s_nhot, 1)] = ul;   // order only affects scheduling
+        unsigned todo = __ballot_sync(0xffffffffu, P_l > 0 && P_l <= kHotPartials);
+        // ---- per-warp: rows with few partials
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
             const int u = base + src;
             const int tA = __shfl_sync(0xffffffffu, tA_l, src), tB = __shfl_sync(0xffffffffu, tB_l, src);
-            const int P = tB - tA;                          // head slots tA+1 .. tB
-            const int per = (P + GPW - 1) / GPW;
+            const int per = (tB - tA + GPW - 1) / GPW;
             const int lo = tA + 1 + gidx * per, hi = min(tB + 1, lo + per);
-            Vec<VEC> acc[NV];
-#pragma unroll
-            for (int i = 0; i < NV; ++i)
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
-            float gw = 0.f;
-            for (int t = lo; t < hi; t += 4) {
-                Vec<VEC> part[4][NV]; float pw[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int tt = min(t + q, hi - 1);
-                    const float* sp = gslot + ((size_t)tt * 2) * dp;
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        int k = (gl + i * LPR) * VEC;
-                        if (k < d) part[q][i] = ld_vec_nc<VEC>(sp + k);
-                    }
-                    pw[q] = __ldg(sp + d);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (t + q < hi) {
-#pragma unroll
-                        for (int i = 0; i < NV; ++i)
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) acc[i].v[j] += part[q][i].v[j];
-                        gw += pw[q];
-                    }
-            }
+            Vec<VEC> acc[NV]; float gw;
+            sum_head_slots<VEC, LPR, NV, 4>(gslot, dp, d, gl, lo, hi, acc, gw);
             // total = tail(tA) + group 0 + group 1 + ...
             const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
             float gw_tot = __ldg(tp + d);
@@ -581,6 +598,50 @@ k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restr
             }
             if (lane == 0) gws[u] = gw_tot;
         }
+        __syncthreads();
+        // ---- whole block: hot rows
+        const int nhot = s_nhot;
+        for (int hi_ = 0; hi_ < nhot; ++hi_) {
+            const int u = s_hot[hi_];
+            const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
+            const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;
+            const int g = warp * GPW + gidx;                // group id 0 .. NG-1
+            const int per = (tB - tA + NG - 1) / NG;
+            const int lo = min(tB + 1, tA + 1 + g * per), hi = min(tB + 1, lo + per);
+            Vec<VEC> acc[NV]; float gw;
+            sum_head_slots<VEC, LPR, NV, 8>(gslot, dp, d, gl, lo, hi, acc, gw);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                int k = (gl + i * LPR) * VEC;
+                if (k < d) st_vec<VEC>(s_part + (size_t)g * dp + k, acc[i]);
+            }
+            if (gl == 0) s_part[(size_t)g * dp + d] = gw;
+            __syncthreads();
+            if (warp == 0 && gidx == 0) {                  // one lane group adds the NG sums in order
+                const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
+                float gw_tot = __ldg(tp + d);
+                for (int q = 0; q < NG; ++q) gw_tot += s_part[(size_t)q * dp + d];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    int k = (gl + i * LPR) * VEC;
+                    if (k < d) {
+                        Vec<VEC> tot = ld_vec_nc<VEC>(tp + k);
+                        for (int q = 0; q < NG; ++q)
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) tot.v[j] += s_part[(size_t)q * dp + k + j];
+                        if (F > 2) {
+                            Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) tot.v[j] = fmaf(-gw_tot, own.v[j], tot.v[j]);
+                        }
+                        st_vec<VEC>(grow + (size_t)u * d + k, tot);
+                    }
+                }
+                if (gl == 0) gws[u] = gw_tot;
+            }
+            __syncthreads();
+        }
+        __syncthreads();                                   // s_nhot / s_hot are reused by the next pass
     }
 }
 
@@ -940,7 +1001,7 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
         k_gather<VEC, LPR, NV><<<grid_t, 256, 0, stream>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
                                                            plan->pos_rank, io->vs, io->msg, io->rsorted,
                                                            gslot, io->grow, io->gws);
-        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 0, stream>>>(
+        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float), stream>>>(
             cfg->d, cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
         if (cfg->link == VFMB_LINK_ABS) {
             if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM(0, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM(0, VFMB_GRAD_ONLY);
@@ -969,6 +1030,14 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
 #undef LAUNCH_FINAL
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                 const vfmb_step_io* io, const vfmb_adam* adam, vfmb_stream stream) {
+    if (io && !io->y) return set_error(VFMB_EINVAL, "vfmb_sampled_step: targets required");
+    int rc = vfmb_sampled_forward(cfg, tab, plan, io, stream);
+    if (rc) return rc;
+    return vfmb_sampled_backward(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, stream);
 }
 
 extern "C" int vfmb_adam_dense(float* p, float* m, float* v, const float* g, int64_t n, const vfmb_adam* adam,

@@ -75,6 +75,75 @@ class BatchPlan:
         return uniq, inverse, counts
 
 
+class PlanPipeline:
+    """Batch plans for a training loop.
+
+    The plan of a batch depends only on its ids, never on the parameters, so it can be
+    built ahead of the step that consumes it: ``prefetch(x_next)`` enqueues the plan
+    kernels on a side stream, where they overlap the (HBM-bound) kernels of the current
+    step; ``acquire(x)`` returns that plan (making the current stream wait for it) or
+    builds one in line.  Plans of a never-shuffled loader (vfm-torch.py:121-122) can be
+    kept: ``build_static`` returns a plan object the caller may pass back every epoch."""
+
+    def __init__(self, B_cap: int, F: int, R: int, device, depth: int = 2):
+        self.B_cap, self.F, self.R, self.device = B_cap, F, R, device
+        self.ring = [BatchPlan(B_cap, F, R, device) for _ in range(depth)]
+        self.free_evt = [torch.cuda.Event() for _ in range(depth)]
+        self.ready_evt = [torch.cuda.Event() for _ in range(depth)]
+        self.slot_of = {}                                   # id(plan) -> ring slot
+        for i, p in enumerate(self.ring):
+            self.slot_of[id(p)] = i
+        self.next = 0
+        self.pending = {}                                   # (data_ptr, B) -> slot
+        self.stream = torch.cuda.Stream(device=device)
+        self.u_cap, self.n_tiles = self.ring[0].u_cap, self.ring[0].n_tiles
+
+    def _take_slot(self) -> int:
+        slot = self.next
+        self.next = (self.next + 1) % len(self.ring)
+        for k in [k for k, v in self.pending.items() if v == slot]:
+            del self.pending[k]                             # an unused prefetch is overwritten
+        return slot
+
+    def prefetch(self, cfg: L.Config, x: torch.Tensor, train_counts: torch.Tensor, after=None) -> None:
+        """``after``: optional event the ids become valid at (e.g. their host-to-device copy)."""
+        key = (x.data_ptr(), int(x.shape[0]))
+        if key in self.pending:
+            return
+        slot = self._take_slot()
+        self.stream.wait_event(self.free_evt[slot])          # last consumer of this buffer is done
+        if after is not None:
+            self.stream.wait_event(after)
+        with torch.cuda.stream(self.stream):
+            self.ring[slot].build(cfg, x, train_counts)
+            self.ready_evt[slot].record(self.stream)
+        self.pending[key] = slot
+
+    def acquire(self, cfg: L.Config, x: torch.Tensor, train_counts: torch.Tensor) -> BatchPlan:
+        key = (x.data_ptr(), int(x.shape[0]))
+        cur = torch.cuda.current_stream(self.device)
+        slot = self.pending.pop(key, None)
+        if slot is not None:
+            cur.wait_event(self.ready_evt[slot])
+            self.ring[slot].B = int(x.shape[0])
+            return self.ring[slot]
+        slot = self._take_slot()
+        cur.wait_event(self.free_evt[slot])
+        return self.ring[slot].build(cfg, x, train_counts)
+
+    def release(self, plan: BatchPlan) -> None:
+        """Call after the last kernel that reads ``plan`` was enqueued on the current stream."""
+        slot = self.slot_of.get(id(plan))
+        if slot is not None:
+            self.free_evt[slot].record(torch.cuda.current_stream(self.device))
+
+    def build_static(self, cfg: L.Config, x: torch.Tensor, train_counts: torch.Tensor) -> BatchPlan:
+        """A plan outside the ring (kept by the caller, e.g. one per batch of a fixed dataset)."""
+        plan = BatchPlan(int(x.shape[0]), self.F, self.R, self.device)
+        plan.u_cap_shared = self.u_cap
+        return plan.build(cfg, x, train_counts)
+
+
 class StepBuffers:
     """Scratch and outputs of one step for batches up to ``B`` samples."""
 
@@ -111,6 +180,30 @@ class StepBuffers:
                         L.ptr(self.msg), L.ptr(self.pred), L.ptr(self.mean), L.ptr(r),
                         L.ptr(self.rsorted), L.ptr(self.partials), L.ptr(self.counters), L.ptr(self.stats),
                         L.ptr(grad_bias), L.ptr(grad_entity), L.ptr(self.grad_scalars))
+
+
+class StepResult:
+    """Outputs of a fused step: lazy views of the (reused) device buffers, so that the hot loop
+    does not pay for tensor slicing it never looks at.  ``res["loss"]`` etc. work like a dict."""
+    __slots__ = ("_buf", "_B")
+    _STAT = {"loss": L.ST_LOSS, "kl": L.ST_KL, "nll_mean": L.ST_NLL_MEAN}
+
+    def __init__(self, buf: "StepBuffers", B: int):
+        self._buf, self._B = buf, B
+
+    def __getitem__(self, key: str):
+        if key in self._STAT:
+            return self._buf.stats[self._STAT[key]]
+        if key == "stats":
+            return self._buf.stats
+        if key == "pred":
+            return self._buf.mean[: self._B]
+        if key == "logits":
+            return self._buf.pred[: self._B]
+        raise KeyError(key)
+
+    def keys(self):
+        return ["loss", "kl", "nll_mean", "pred", "logits", "stats"]
 
 
 def make_config(B, F, d, R, S, likelihood, link, class_bounds, class_sizes, n_train, seed) -> L.Config:

@@ -29,7 +29,8 @@ import torch
 from torch import distributions, nn
 
 from . import _lib as L
-from .engine import BatchPlan, StepBuffers, current_stream, make_config, require_cuda
+from .engine import (BatchPlan, PlanPipeline, StepBuffers, StepResult, current_stream, make_config,
+                     require_cuda)
 
 _LINKS = {"abs": torch.abs, "softplus": nn.functional.softplus}
 
@@ -45,7 +46,7 @@ class _SampledFn(torch.autograd.Function):
     def forward(ctx, bias_w, entity_w, gb_mean, gb_scale, model, x, noise):
         out = model._forward_kernels(x, None, noise)
         ctx.model, ctx.noise = model, noise
-        ctx.e0 = out["e0"]
+        ctx.e0 = model._global_eps(out)
         ctx.save_for_backward(gb_scale)
         return out["pred"].reshape(1, -1).clone(), out["kl_rows"].reshape(1).clone()
 
@@ -128,9 +129,13 @@ class CF(nn.Module):
         # posterior-mean snapshots (vfm-torch.py:155-160, 179-185)
         self.saved_global_biases, self.saved_mean_biases, self.saved_mean_entities = [], [], []
         self.mean_saved_global_biases = self.mean_saved_mean_biases = self.mean_saved_mean_entities = None
-        self._plan: Optional[BatchPlan] = None
+        self._plan: Optional[BatchPlan] = None            # plan of the last step
+        self._pipe: Optional[PlanPipeline] = None
         self._buf: Optional[StepBuffers] = None
         self._cfg: Optional[L.Config] = None
+        self._cfg_cache = {}
+        self._tab_cache = None                            # (entity ptr, bias ptr, Tables)
+        self._fast_io = None
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -138,15 +143,19 @@ class CF(nn.Module):
         return self.entity_params.weight.device
 
     def _ensure(self, B: int):
-        if self._plan is None or B > self._plan.B_cap:
-            cap = max(B, self.max_batch if self._plan is None else B)
+        if self._pipe is None or B > self._pipe.B_cap:
+            cap = max(B, self.max_batch if self._pipe is None else B)
             cfg = self._config(cap)
-            self._plan = BatchPlan(cap, self.F, self.R, self.device)
-            self._buf = StepBuffers(cfg, self._plan, self.device, L.S_COUNT, need_msg=self.F > 2)
+            self._pipe = PlanPipeline(cap, self.F, self.R, self.device)
+            self._buf = StepBuffers(cfg, self._pipe.ring[0], self.device, L.S_COUNT, need_msg=self.F > 2)
 
     def _config(self, B: int) -> L.Config:
-        return make_config(B, self.F, self.d, self.R, self.S, self.output, self.link_name,
-                           self._class_bounds, self._class_sizes, self.n_train, self.seed)
+        cfg = self._cfg_cache.get(B)
+        if cfg is None:
+            cfg = make_config(B, self.F, self.d, self.R, self.S, self.output, self.link_name,
+                              self._class_bounds, self._class_sizes, self.n_train, self.seed)
+            self._cfg_cache[B] = cfg
+        return cfg
 
     def _sync_scalars(self):
         """The three scalar parameters live in one device block the kernels read;
@@ -165,6 +174,15 @@ class CF(nn.Module):
             self.global_bias_scale.data = self._scalars[L.S_GB_SCALE:L.S_GB_SCALE + 1]
 
     def _tables(self) -> L.Tables:
+        key = (self.entity_params.weight.data_ptr(), self.bias_params.weight.data_ptr(),
+               self._scalars.data_ptr())
+        if self._tab_cache is not None and self._tab_cache[0] == key:
+            return self._tab_cache[1]
+        tab = self._make_tables()
+        self._tab_cache = (key, tab)
+        return tab
+
+    def _make_tables(self) -> L.Tables:
         return L.Tables(L.ptr(self.bias_params.weight), L.ptr(self.bias_m), L.ptr(self.bias_v),
                         L.ptr(self.entity_params.weight), L.ptr(self.entity_m), L.ptr(self.entity_v),
                         L.ptr(self.train_counts), L.ptr(self._scalars), L.ptr(self._scalars_m),
@@ -177,15 +195,36 @@ class CF(nn.Module):
                      for t in noise)
 
     def plan(self, x: torch.Tensor) -> BatchPlan:
-        """Build the batch plan for ``x`` (int64 ``[B,F]``) on the current stream."""
+        """The batch plan for ``x`` (int64 ``[B,F]``): the prefetched one if ``prefetch_plan(x)``
+        was called, else built now on the current stream."""
         x = x.to(self.device, non_blocking=True).contiguous()
         self._ensure(int(x.shape[0]))
         self._cfg = self._config(int(x.shape[0]))
-        return self._plan.build(self._cfg, x, self.train_counts)
+        self._plan = self._pipe.acquire(self._cfg, x, self.train_counts)
+        return self._plan
 
-    def _forward_kernels(self, x, y, noise):
+    def prefetch_plan(self, x: torch.Tensor, after=None) -> None:
+        """Start building the plan of an upcoming batch on a side stream (it depends only on
+        the ids).  ``x`` must stay unchanged until the step that uses it; ``after`` is an
+        optional CUDA event marking when ``x`` is valid (e.g. its host-to-device copy)."""
+        assert x.is_cuda and x.is_contiguous() and x.dtype == torch.int64
+        self._ensure(int(x.shape[0]))
+        self._pipe.prefetch(self._config(int(x.shape[0])), x, self.train_counts, after)
+
+    def static_plan(self, x: torch.Tensor) -> BatchPlan:
+        """A reusable plan for a batch that recurs every epoch (the reference loaders never
+        shuffle, vfm-torch.py:121-122); pass it as ``fused_step(x, y, plan=...)``."""
+        x = x.to(self.device).contiguous()
+        self._ensure(int(x.shape[0]))
+        return self._pipe.build_static(self._config(int(x.shape[0])), x, self.train_counts)
+
+    def _forward_kernels(self, x, y, noise, plan: Optional[BatchPlan] = None):
         self._sync_scalars()
-        self.plan(x)
+        if plan is None:
+            self.plan(x)
+        else:
+            self._ensure(plan.B)
+            self._cfg, self._plan = self._config(plan.B), plan
         noise = self._prep_noise(noise)
         if y is not None:
             y = y.to(self.device, torch.float32, non_blocking=True).contiguous()
@@ -196,13 +235,15 @@ class CF(nn.Module):
                 "vfmb_sampled_forward")
         B = self._cfg.B
         st = self._buf.stats
-        if noise is not None:
-            e0 = noise[0].reshape(-1)[0]
-        else:
-            sig0 = _LINKS[self.link_name](self._scalars[L.S_GB_SCALE])
-            e0 = (st[L.ST_W0] - self._scalars[L.S_GB_MEAN]) / sig0
         return {"pred": self._buf.pred[:B], "mean": self._buf.mean[:B], "stats": st,
-                "kl_rows": st[L.ST_KL_ROWS], "e0": e0.detach()}
+                "kl_rows": st[L.ST_KL_ROWS], "noise": noise}
+
+    def _global_eps(self, out):
+        """The N(0,1) draw behind the sampled global bias of the last forward."""
+        if out["noise"] is not None:
+            return out["noise"][0].reshape(-1)[0].detach()
+        sig0 = _LINKS[self.link_name](self._scalars[L.S_GB_SCALE])
+        return ((out["stats"][L.ST_W0] - self._scalars[L.S_GB_MEAN]) / sig0).detach()
 
     def _backward_kernels(self, noise, mode, kl_scale, resid=None, grad_bias=None, grad_entity=None,
                           want_scalars=True):
@@ -214,6 +255,7 @@ class CF(nn.Module):
         L.check(L.lib().vfmb_sampled_backward(C.byref(self._cfg), C.byref(tab), C.byref(self._plan.struct),
                                               C.byref(io), C.byref(self.adam), mode, float(kl_scale),
                                               current_stream(self.device)), "vfmb_sampled_backward")
+        self._pipe.release(self._plan)
 
     # ------------------------------------------------------------------ reference API
     def forward(self, x: torch.Tensor, noise: Optional[Sequence[torch.Tensor]] = None):
@@ -286,16 +328,44 @@ class CF(nn.Module):
 
     @torch.no_grad()
     def fused_step(self, x: torch.Tensor, y: torch.Tensor,
-                   noise: Optional[Sequence[torch.Tensor]] = None, update: bool = True) -> dict:
+                   noise: Optional[Sequence[torch.Tensor]] = None, update: bool = True,
+                   plan: Optional[BatchPlan] = None) -> dict:
         """Plan + forward + backward + Adam on the touched rows (vfm-torch.py:351-370 in
         one go).  Returns device tensors (views of reused buffers -- clone to keep):
         ``loss [ ]``, ``kl [ ]``, ``pred [B]`` (likelihood mean), ``logits [B]``."""
-        out = self._forward_kernels(x, y, noise)
+        if (noise is None and update and x.is_cuda and y.is_cuda and y.dtype == torch.float32
+                and x.is_contiguous() and y.is_contiguous()):
+            return self._fused_step_fast(x, y, plan)
+        out = self._forward_kernels(x, y, noise, plan)
         if update:
             self._backward_kernels(noise, L.ADAM_TOUCHED, 1.0)
+        else:
+            self._pipe.release(self._plan)
         st = out["stats"]
         return {"loss": st[L.ST_LOSS], "kl": st[L.ST_KL], "nll_mean": st[L.ST_NLL_MEAN],
                 "pred": out["mean"], "logits": out["pred"], "stats": st}
+
+    def _fused_step_fast(self, x, y, plan):
+        """Hot loop: cached ctypes structures, one C call for forward + backward + Adam."""
+        self._sync_scalars()
+        B = int(x.shape[0])
+        if plan is None:
+            self._ensure(B)
+            self._cfg = self._config(B)
+            self._plan = self._pipe.acquire(self._cfg, x, self.train_counts)
+        else:
+            self._ensure(plan.B)
+            self._cfg, self._plan = self._config(plan.B), plan
+        io = self._fast_io
+        if io is None or io[0] is not self._buf:
+            io = (self._buf, self._buf.io())
+            self._fast_io = io
+        io[1].y = y.data_ptr()
+        L.check(L.lib().vfmb_sampled_step(C.byref(self._cfg), C.byref(self._tables()),
+                                          C.byref(self._plan.struct), C.byref(io[1]), C.byref(self.adam),
+                                          current_stream(self.device)), "vfmb_sampled_step")
+        self._pipe.release(self._plan)
+        return StepResult(self._buf, B)
 
     @torch.no_grad()
     def gradients(self, x, y, noise=None) -> dict:
