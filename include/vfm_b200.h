@@ -108,6 +108,8 @@ typedef struct vfmb_plan {
     int32_t* partner;    /* [B*F]     per sorted position: F==2 the rank of the sample's other
                                       field; F>2 the sample index n                          */
     int32_t* urec;       /* [U_cap,4] per unique row {row id, batch count, seg_off, 0}       */
+    int32_t* class_off;  /* [VFMB_MAX_FIELDS+1] first unique rank of each KL class (class_bound
+                                      of the config); class_off[n_classes] = U               */
     float* z;            /* [VFMB_MAX_FIELDS] per-column normaliser Z_f             */
     int32_t* meta;       /* [8] 0:U 2:error flag (id out of range); rest reserved   */
 } vfmb_plan;
@@ -128,7 +130,8 @@ int vfmb_plan_build(const vfmb_config* cfg /*host*/, const int64_t* x, const flo
                     size_t workspace_bytes, vfmb_stream stream);
 
 /* Scratch + outputs of one step.  Capacities: vs/es/grow [U_cap*d], ws/ebs/cq/gws [U_cap],
- * msg [B*d] (F>2 only), pred/mean/resid [B], rsorted [B*F],
+ * msg [B*d] (F>2 only), pred/mean/resid [B], rsorted [B*F]; the closed-form variant uses
+ * vs [U_cap*2d] (mean | raw scale^2), grow [U_cap*3d], msg [B*3d],
  * partials [vfmb_partials_doubles()], stats [VFMB_STATS]. */
 typedef struct vfmb_step_io {
     const float* y;          /* [B] targets (NULL: forward without likelihood terms)  */
@@ -150,6 +153,8 @@ typedef struct vfmb_step_io {
     double* partials;        /* scratch for deterministic reductions                  */
     int32_t* counters;       /* [8] zero-initialised once by the caller               */
     float* stats;            /* [VFMB_STATS] see enum                                 */
+    float* kl_bias_out;      /* optional [U]   per-row bias KL   (closed form, kls[1])  */
+    float* kl_entity_out;    /* optional [U,d] per-row factor KL (closed form, kls[2])  */
     float* grad_bias;        /* VFMB_GRAD_ONLY: dense [R,2]  (touched rows written)   */
     float* grad_entity;      /* VFMB_GRAD_ONLY: dense [R,2d]                          */
     float* grad_scalars;     /* VFMB_GRAD_ONLY: [scalar count]                        */

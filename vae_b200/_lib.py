@@ -56,7 +56,7 @@ class Adam(C.Structure):
 class Plan(C.Structure):
     _fields_ = [("uniq", _i32p), ("inverse", _i32p), ("seg_off", _i32p), ("occ", _i32p),
                 ("pos_of", _i32p), ("pos_rank", _i32p), ("partner", _i32p), ("urec", _i32p),
-                ("z", _f32p), ("meta", _i32p)]
+                ("class_off", _i32p), ("z", _f32p), ("meta", _i32p)]
 
 
 class PlanCapacity(C.Structure):
@@ -69,6 +69,7 @@ class StepIO(C.Structure):
                 ("vs", _f32p), ("ws", _f32p), ("es", _f32p), ("ebs", _f32p), ("cq", _f32p),
                 ("grow", _f32p), ("gws", _f32p), ("msg", _f32p), ("pred", _f32p), ("mean", _f32p),
                 ("resid", _f32p), ("rsorted", _f32p), ("partials", _f64p), ("counters", _i32p), ("stats", _f32p),
+                ("kl_bias_out", _f32p), ("kl_entity_out", _f32p),
                 ("grad_bias", _f32p), ("grad_entity", _f32p), ("grad_scalars", _f32p)]
 
 

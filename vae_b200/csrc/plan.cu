@@ -104,10 +104,19 @@ k_plan_scatter(const int32_t* __restrict__ keys_s, const int32_t* __restrict__ v
 // ---- P4: flat records the step kernels read with one load each -----------------------------
 //   partner[i]  per sorted position: F==2 the rank of the sample's other field, else sample n
 //   urec[u]     {row id, batch count, segment offset, 0}
+struct ClassBounds { int n; int bound[kMaxFields]; };
+__device__ __forceinline__ int plan_class_of(const ClassBounds& cb, int row) {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxFields - 1; ++i) k += (i < cb.n - 1 && row >= cb.bound[i]) ? 1 : 0;
+    return k;
+}
+
 __global__ void __launch_bounds__(256)
 k_plan_finish(const int32_t* __restrict__ uniq, const int32_t* __restrict__ seg_off,
               const int32_t* __restrict__ occ, const int32_t* __restrict__ inverse, int N, int F,
-              int32_t* __restrict__ partner, int32_t* __restrict__ urec, const int32_t* __restrict__ meta) {
+              ClassBounds cb, int32_t* __restrict__ partner, int32_t* __restrict__ urec,
+              int32_t* __restrict__ class_off, const int32_t* __restrict__ meta) {
     const int U = meta[0];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int i = tid; i < N; i += nth) {
@@ -116,7 +125,13 @@ k_plan_finish(const int32_t* __restrict__ uniq, const int32_t* __restrict__ seg_
     }
     for (int u = tid; u < U; u += nth) {
         const int seg0 = seg_off[u];
-        reinterpret_cast<int4*>(urec)[u] = make_int4(uniq[u], seg_off[u + 1] - seg0, seg0, 0);
+        const int rowid = uniq[u];
+        reinterpret_cast<int4*>(urec)[u] = make_int4(rowid, seg_off[u + 1] - seg0, seg0, 0);
+        // class_off[g] = first rank whose class is >= g (uniq is sorted, classes are id ranges)
+        const int cls = plan_class_of(cb, rowid);
+        const int prev = (u == 0) ? -1 : plan_class_of(cb, uniq[u - 1]);
+        for (int g = prev + 1; g <= cls; ++g) class_off[g] = u;
+        if (u == U - 1) for (int g = cls + 1; g <= kMaxFields; ++g) class_off[g] = U;
     }
 }
 
@@ -221,8 +236,11 @@ extern "C" int vfmb_plan_build(const vfmb_config* cfg, const int64_t* x, const f
     k_plan_scatter<<<grid2, 256, 0, stream>>>(w.keys_s, w.vals_s, w.rank, N, plan->uniq, plan->seg_off,
                                               plan->inverse, plan->occ, plan->pos_of, plan->pos_rank, plan->meta);
     CUDA_TRY(cudaGetLastError());
+    ClassBounds cbd{};
+    cbd.n = cfg->n_classes;
+    for (int i = 0; i < kMaxFields; ++i) cbd.bound[i] = cfg->class_bound[i];
     k_plan_finish<<<grid2, 256, 0, stream>>>(plan->uniq, plan->seg_off, plan->occ, plan->inverse, N, cfg->F,
-                                             plan->partner, plan->urec, plan->meta);
+                                             cbd, plan->partner, plan->urec, plan->class_off, plan->meta);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -40,13 +40,14 @@ class BatchPlan:
         self.pos_rank = _i32(B * F, device)
         self.partner = _i32(B * F, device)
         self.urec = _i32(4 * self.u_cap, device)
+        self.class_off = torch.zeros(L.MAX_FIELDS + 1, dtype=torch.int32, device=device)
         self.z = torch.zeros(L.MAX_FIELDS, dtype=torch.float32, device=device)
         self.meta = torch.zeros(8, dtype=torch.int32, device=device)
         self.workspace = torch.empty(int(cap.workspace_bytes), dtype=torch.uint8, device=device)
         self.B = 0
         self.struct = L.Plan(L.ptr(self.uniq), L.ptr(self.inverse), L.ptr(self.seg_off),
                              L.ptr(self.occ), L.ptr(self.pos_of), L.ptr(self.pos_rank), L.ptr(self.partner),
-                             L.ptr(self.urec), L.ptr(self.z), L.ptr(self.meta))
+                             L.ptr(self.urec), L.ptr(self.class_off), L.ptr(self.z), L.ptr(self.meta))
 
     def build(self, cfg: L.Config, x: torch.Tensor, train_counts: torch.Tensor) -> "BatchPlan":
         assert x.dtype == torch.int64 and x.is_cuda and x.is_contiguous(), "x: contiguous CUDA int64 [B,F]"
@@ -147,16 +148,18 @@ class PlanPipeline:
 class StepBuffers:
     """Scratch and outputs of one step for batches up to ``B`` samples."""
 
-    def __init__(self, cfg: L.Config, plan: BatchPlan, device, n_scalars: int, need_msg: bool):
+    def __init__(self, cfg: L.Config, plan: BatchPlan, device, n_scalars: int, need_msg: bool,
+                 closed: bool = False):
         B, d = plan.B_cap, cfg.d
-        self.vs = _f32(plan.u_cap * d, device)
+        wv, wg = (2, 3) if closed else (1, 1)              # closed form: vs=[mu|rho^2], grow=[A|B|C]
+        self.vs = _f32(plan.u_cap * d * wv, device)
         self.ws = _f32(plan.u_cap, device)
         self.es = _f32(plan.u_cap * d, device)
         self.ebs = _f32(plan.u_cap, device)
         self.cq = _f32(plan.u_cap, device)
-        self.grow = _f32(plan.u_cap * d, device)
+        self.grow = _f32(plan.u_cap * d * wg, device)
         self.gws = _f32(plan.u_cap, device)
-        self.msg = _f32(B * d, device) if need_msg else None
+        self.msg = _f32(B * d * wg, device) if need_msg else None
         self.pred = _f32(B, device)
         self.mean = _f32(B, device)
         self.resid = _f32(B, device)
@@ -168,7 +171,7 @@ class StepBuffers:
         self.grad_scalars = torch.zeros(n_scalars, dtype=torch.float32, device=device)
 
     def io(self, y=None, noise: Optional[Sequence[torch.Tensor]] = None, grad_bias=None,
-           grad_entity=None, resid=None) -> L.StepIO:
+           grad_entity=None, resid=None, kl_bias_out=None, kl_entity_out=None) -> L.StepIO:
         e0 = eb = ee = None
         if noise is not None:
             e0, eb, ee = noise
@@ -179,6 +182,7 @@ class StepBuffers:
                         L.ptr(self.es), L.ptr(self.ebs), L.ptr(self.cq), L.ptr(self.grow), L.ptr(self.gws),
                         L.ptr(self.msg), L.ptr(self.pred), L.ptr(self.mean), L.ptr(r),
                         L.ptr(self.rsorted), L.ptr(self.partials), L.ptr(self.counters), L.ptr(self.stats),
+                        L.ptr(kl_bias_out), L.ptr(kl_entity_out),
                         L.ptr(grad_bias), L.ptr(grad_entity), L.ptr(self.grad_scalars))
 
 
