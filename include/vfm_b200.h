@@ -197,6 +197,23 @@ int vfmb_adam_dense(float* p, float* m, float* v, const float* g, int64_t n,
                     vfmb_stream stream);
 int vfmb_adam_step_advance(int32_t* adam_step, vfmb_stream stream);
 
+/* ---- batch data-parallel mode (replicated small tables, dense gradient all-reduce) -------------
+ * The reference is single-process; under DP the step on the GLOBAL batch must equal the
+ * single-process step on that batch.  Per rank: forward/backward on the local slice
+ * with kl_grad_scale 0 and n_train scaled by B_local/B_global (VFMB_GRAD_ONLY, dense gradients),
+ * vfmb_dp_scatter_counts, one all-reduce(sum) over [grad_entity | grad_bias | counts | tail],
+ * then vfmb_dp_apply_sampled on every rank: KL gradient with the global batch counts and
+ * normalisers, Adam (dense = the reference's torch.optim.Adam over every row, or touched rows),
+ * scalar parameters, step counter.  tail = {z[0..7], sum nll, sum resid, sum sq. err}. */
+enum { VFMB_DP_TAIL = 16, VFMB_DP_T_NLL = 8, VFMB_DP_T_RESID = 9, VFMB_DP_T_SQERR = 10 };
+int vfmb_dp_scatter_counts(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
+                           float* counts /*[R], zeroed*/, float* tail /*[VFMB_DP_TAIL]*/,
+                           vfmb_stream stream);
+int vfmb_dp_apply_sampled(const vfmb_config* cfg_global, const vfmb_tables* tab, const float* grad_entity,
+                          const float* grad_bias, const float* counts, const float* tail,
+                          const float* eps_global, const vfmb_adam* adam, int32_t dense_adam,
+                          double* partials, int32_t* counters, float* stats, vfmb_stream stream);
+
 /* Closed-form Gaussian variant (vfm-tomasrch.py:323-453 forward,
  * :569-594 loss/backward/Adam).  Same plan, same scratch. */
 int vfmb_closed_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,

@@ -87,8 +87,13 @@ def kl_weights(plan, train_counts: np.ndarray, field_sizes: Sequence[int], weigh
 def sampled_step(params: Dict[str, np.ndarray], x: np.ndarray, y: np.ndarray,
                  noise: Sequence[np.ndarray], train_counts: np.ndarray, n_train: int,
                  field_sizes: Sequence[int], output: str = "reg", link: str = "abs",
-                 interaction: str = "prod", kl_weighting: str = "torch") -> Dict[str, np.ndarray]:
+                 interaction: str = "prod", kl_weighting: str = "torch", kl_scale: float = 1.0,
+                 kl_weight: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """Forward + analytic backward of the sampled ELBO.
+
+    ``kl_scale`` multiplies every KL contribution (0 = data term only, as each rank computes it
+    in data-parallel mode A); ``kl_weight`` overrides the per-unique-row KL weights c_u (e.g. the
+    global-batch weights restricted to this batch's rows).
 
     ``params``: ``alpha[1], global_bias_mean[1], global_bias_scale[1],
     bias[R,2], entity[R,2d]``.  ``noise`` = (eps0 ``[S,1]``, eps_bias ``[S,U]``,
@@ -131,8 +136,11 @@ def sampled_step(params: Dict[str, np.ndarray], x: np.ndarray, y: np.ndarray,
         dnll = 1.0 / (1.0 + np.exp(-pred)) - yy
         mean_out = 1.0 / (1.0 + np.exp(-pred))
     c, z = kl_weights(plan, train_counts, field_sizes, kl_weighting)
+    if kl_weight is not None:
+        c = np.asarray(kl_weight, dtype=f8)
+    c = kl_scale * c
     kl_rows = _kl(a, tau) + _kl(mu, sig).sum(axis=1)
-    kl0 = _kl(mu0, sig0)
+    kl0 = kl_scale * _kl(mu0, sig0)
     kl = kl0 + (c * kl_rows).sum()
     loss = n_train * nll.mean() + kl
 
@@ -140,8 +148,8 @@ def sampled_step(params: Dict[str, np.ndarray], x: np.ndarray, y: np.ndarray,
     r = n_train / (S * B) * dnll                                # [S,B] dloss/dpred
     rbar = r.mean(axis=0)                                       # dloss/dh[s',n] for every s'
     rsum = r.sum(axis=1)                                        # [S]
-    g_mu0 = rsum.sum() + mu0
-    g_rho0 = _dlink(rho0, link) * ((e0[:, 0] * rsum).sum() + sig0 - 1.0 / sig0)
+    g_mu0 = rsum.sum() + kl_scale * mu0
+    g_rho0 = _dlink(rho0, link) * ((e0[:, 0] * rsum).sum() + kl_scale * (sig0 - 1.0 / sig0))
     if output == "reg":
         g_alpha = _dlink(alpha, link) * n_train / (S * B) * (
             0.5 * (yy - pred) ** 2 - 0.5 / ap).sum()
@@ -170,8 +178,9 @@ def sampled_step(params: Dict[str, np.ndarray], x: np.ndarray, y: np.ndarray,
              "bias": g_bias, "entity": g_ent}
     if g_alpha is not None:
         grads["alpha"] = np.array([g_alpha])
-    return {"loss": loss, "kl": kl, "nll_mean": nll.mean(), "pred": pred, "mean": mean_out,
-            "resid": r, "kl_weight": c, "z": z, "plan": plan, "grads": grads}
+    return {"loss": loss, "kl": kl, "nll_mean": nll.mean(), "nll_sum": nll.sum(), "pred": pred,
+            "mean": mean_out, "resid": r, "kl_weight": c, "z": z, "plan": plan, "grads": grads,
+            "sq_err": ((yy - pred) ** 2).sum()}
 
 
 # ----------------------------------------------------------------------------- closed form

@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libvfm_b200.so")
-SOURCES = ["api.cu", "plan.cu", "sampled.cu", "closed.cu"]
-HEADERS = ["common.cuh", "internal.h", os.path.join(_ROOT, "include", "vfm_b200.h")]
+SOURCES = ["api.cu", "plan.cu", "sampled.cu", "closed.cu", "dp.cu"]
+HEADERS = ["common.cuh", "internal.h", "step_common.cuh", os.path.join(_ROOT, "include", "vfm_b200.h")]
 # -prec-div/-prec-sqrt=false: MUFU-based division and square root (<= 2 ulp) instead of the IEEE
 # slow paths, which made the Adam epilogue instruction-bound; denormals and expf/logf stay precise
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -91,6 +91,10 @@ SYMBOLS = {
     "vfmb_sampled_backward": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam),
                                         C.c_int32, C.c_float, C.c_void_p]),
     "vfmb_sampled_step": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam), C.c_void_p]),
+    "vfmb_dp_scatter_counts": (C.c_int, [_P(Config), _P(Plan), _P(StepIO), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vfmb_dp_apply_sampled": (C.c_int, [_P(Config), _P(Tables), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, _P(Adam), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "vfmb_adam_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   _P(Adam), C.c_void_p, C.c_void_p]),
     "vfmb_adam_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
