@@ -233,6 +233,12 @@ int vfmb_predict_mean(const vfmb_config* cfg, const float* bias, const float* en
 int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, int32_t U, int32_t step,
                         float* eps_global, float* eps_bias, float* eps_entity, vfmb_stream stream);
 
+/* Measurement hook: when both are non-NULL (cudaEvent_t), the following backward calls of this
+ * thread record them on the launch stream immediately before and after the step's dominant
+ * kernel (k_adam_rows / k_cadam); pass NULLs to switch it off.  Used by bench.py for the
+ * roofline of that kernel; no effect on results. */
+int vfmb_profile_events(void* start_event, void* stop_event);
+
 const char* vfmb_last_error(void);
 int vfmb_version(void);
 

@@ -16,7 +16,16 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+void profile_events(cudaEvent_t* start, cudaEvent_t* stop) { *start = g_prof_start; *stop = g_prof_stop; }
+
 }  // namespace vfmb
+
+extern "C" int vfmb_profile_events(void* start_event, void* stop_event) {
+    vfmb::g_prof_start = (cudaEvent_t)start_event;
+    vfmb::g_prof_stop = (cudaEvent_t)stop_event;
+    return 0;
+}
 
 extern "C" const char* vfmb_last_error(void) { return vfmb::g_error; }
 extern "C" int vfmb_version(void) { return 100; }

@@ -14,6 +14,8 @@ constexpr int kMaxGrid = 4 * kNumSMs;   // grid-stride kernels: one resident wav
 constexpr int kPriorGrid = 2 * kNumSMs; // blocks that carry prior-gradient partials (closed form)
 
 int set_error(int code, const char* fmt, ...);
+// optional events around the dominant kernel (see vfmb_profile_events)
+void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
 
 #define CUDA_TRY(expr)                                                                  \
     do {                                                                                \

@@ -682,11 +682,15 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
                                                            gslot, io->grow, io->gws);
         k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float), stream>>>(
             cfg->d, cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
+        cudaEvent_t ev0, ev1;
+        profile_events(&ev0, &ev1);
+        if (ev0 && ev1) cudaEventRecord(ev0, stream);
         if (cfg->link == VFMB_LINK_ABS) {
             if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM(0, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM(0, VFMB_GRAD_ONLY);
         } else {
             if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM(1, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM(1, VFMB_GRAD_ONLY);
         }
+        if (ev0 && ev1) cudaEventRecord(ev1, stream);
     });
 #undef LAUNCH_ADAM
     CUDA_TRY(cudaGetLastError());
