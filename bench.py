@@ -157,6 +157,14 @@ def run_ours(args):
             for i in range(lo, hi):
                 dp.step(*batch(i))
             return
+        if args.plan == "graph":                             # CUDA-graph replay of the same pipelined loop
+            loop.start(*batch(lo))
+            for i in range(lo, hi):
+                if i + 1 < hi:
+                    loop.step(*batch(i + 1))
+                else:
+                    loop.step()
+            return
         if args.plan == "prefetch":
             model.prefetch_plan(batch(lo)[0])
         for i in range(lo, hi):
@@ -168,6 +176,7 @@ def run_ours(args):
             else:
                 model.fused_step(xb, yb)
 
+    loop = model.graphed_loop(B) if (args.plan == "graph" and dp is None) else None
     static_plans = {}
     if args.plan == "cached":                               # never-shuffled loader: plans recur every epoch
         for i in range(W, W + K):
@@ -209,7 +218,7 @@ def run_ours(args):
 
     # end to end through the public API with HOST inputs: pinned x/y -> device every step,
     # loss/KL scalars back to pinned host memory every step
-    e2e = measure_e2e(model, w, rank, world, n_batches, W, min(K, 500), device, barrier, dp)
+    e2e = measure_e2e(model, w, rank, world, n_batches, W, min(K, 500), device, barrier, dp, loop)
 
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -239,6 +248,8 @@ def run_ours(args):
                    "fields": F, "unique_rows_per_step": U, "adam": "touched rows (lazy)",
                    "noise": "Philox4x32-10 in-kernel", "plan": {"inline": "built every step on the step's stream",
                             "prefetch": "built every step, one batch ahead on a side stream",
+                            "graph": "built every step, one batch ahead on a side stream; step + plan "
+                                     "replayed as one CUDA graph",
                             "cached": "precomputed per batch (never-shuffled loader)"}[args.plan]
                            + " (CUB radix sort + own kernels)",
                    "l2": "params+Adam state 258 MB > 126 MB L2; consecutive distinct batches, no flush"
@@ -267,7 +278,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None):
+def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None, loop=None):
     B, F = w.batch, w.n_fields
     xh = torch.from_numpy(w.x[: n_batches * B]).pin_memory()
     yh = torch.from_numpy(w.y[: n_batches * B]).pin_memory()
@@ -287,7 +298,20 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
         if dp is None:
             model.prefetch_plan(xd[s], after=copied[s])
 
+    def host_batch(i):
+        j = (i * world + rank) % n_batches
+        return xh[j * B:(j + 1) * B], yh[j * B:(j + 1) * B]
+
+    def run_graph(lo, hi):
+        """graphed loop fed straight from pinned host memory: the staging copies ARE the H2D copies"""
+        loop.start(*host_batch(lo))
+        for i in range(lo, hi):
+            out = loop.step(*host_batch(i + 1)) if i + 1 < hi else loop.step()
+            res[i].copy_(out["stats"], non_blocking=True)
+
     def run(lo, hi):
+        if loop is not None:
+            return run_graph(lo, hi)
         stage(lo)
         for i in range(lo, hi):
             if i + 1 < hi:
@@ -386,7 +410,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ml20m")
     ap.add_argument("--rows", type=int, default=None, help="override the synthetic dataset size")
-    ap.add_argument("--plan", default="prefetch", choices=["inline", "prefetch", "cached"])
+    ap.add_argument("--plan", default="graph", choices=["inline", "prefetch", "graph", "cached"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()

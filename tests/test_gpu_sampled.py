@@ -359,3 +359,25 @@ def test_prefetched_and_static_plans_give_identical_steps():
     for losses, ent, bias in results[1:]:
         assert losses == results[0][0]
         assert torch.equal(ent, results[0][1]) and torch.equal(bias, results[0][2])
+
+
+def test_graphed_loop_is_bitwise_identical_to_eager_steps():
+    """CUDA-graph replay of (step on batch i || plan of batch i+1) == eager fused_step sequence."""
+    meta, g = gu.load("sampled_reg_d64")
+    xs = [torch.from_numpy(gu.batch_of(meta, g, t)[0]).to(DEV) for t in range(3)]
+    ys = [torch.from_numpy(gu.batch_of(meta, g, t)[1]).to(DEV) for t in range(3)]
+    order = [0, 1, 2, 0, 1, 2, 0]
+    ref = _model(meta, g, 0, seed=5)
+    ref_losses = [ref.fused_step(xs[i], ys[i])["loss"].item() for i in order]
+    m = _model(meta, g, 0, seed=5)
+    loop = m.graphed_loop(meta["batch"])
+    loop.start(xs[order[0]], ys[order[0]])
+    losses = []
+    for k, i in enumerate(order):
+        nxt = order[k + 1] if k + 1 < len(order) else None
+        res = loop.step(xs[nxt], ys[nxt]) if nxt is not None else loop.step()
+        losses.append(res["loss"].item())
+    assert losses == ref_losses
+    assert torch.equal(m.entity_params.weight, ref.entity_params.weight)
+    assert torch.equal(m.bias_params.weight, ref.bias_params.weight)
+    assert torch.equal(m._scalars, ref._scalars) and int(m.adam_step) == len(order)

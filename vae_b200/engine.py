@@ -145,6 +145,81 @@ class PlanPipeline:
         return plan.build(cfg, x, train_counts)
 
 
+class GraphedLoop:
+    """CUDA-graph replay of the software-pipelined training loop (fixed batch size).
+
+    Launching the ~16 small kernels of a step from Python costs more host time than the GPU
+    needs to run them; the step is launch-bound.  All per-step state (Adam step counter, Philox
+    counter, reduction counters) lives on the device and the kernels take no per-step host
+    scalars, so a step can be captured once and replayed.  One graph per staging slot holds:
+
+        main stream   forward + backward + Adam on plan[s], targets ys[s]
+        side stream   plan of the NEXT batch from xs[1-s] into plan[1-s]   (forked / joined)
+
+    ``stage`` copies a batch into the staging buffers; ``step`` replays.  Usage::
+
+        loop = model.graphed_loop(B)
+        loop.start(x0, y0)
+        for x_next, y_next in batches[1:]:
+            res = loop.step(x_next, y_next)      # runs the step on the previously staged batch
+        res = loop.step()                         # last staged batch
+    """
+
+    def __init__(self, model, B: int, step_fn):
+        self.model, self.B, self.device = model, int(B), model.device
+        F = model.F if hasattr(model, "F") else model.G
+        self.xs = [torch.zeros((B, F), dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.ys = [torch.zeros(B, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.plans = [BatchPlan(B, F, model.R, self.device) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=self.device)
+        self.cfg = model._config(B)
+        self.graphs = []
+        self.cur = 0                                        # slot holding the batch to run next
+        self.staged = False
+        # warm-up on a side stream (lazy allocations, module loading), then capture
+        warm = torch.cuda.Stream(device=self.device)
+        warm.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(warm):
+            for s in range(2):
+                self.plans[s].build(self.cfg, self.xs[s], model.train_counts)
+        torch.cuda.current_stream(self.device).wait_stream(warm)
+        torch.cuda.synchronize(self.device)
+        for s in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cur = torch.cuda.current_stream(self.device)
+                self.side.wait_stream(cur)                   # fork
+                with torch.cuda.stream(self.side):
+                    self.plans[1 - s].build(self.cfg, self.xs[1 - s], model.train_counts)
+                step_fn(self.plans[s], self.ys[s])           # main branch
+                cur.wait_stream(self.side)                   # join
+            self.graphs.append(g)
+
+    def stage(self, slot: int, x: torch.Tensor, y: torch.Tensor) -> None:
+        self.xs[slot].copy_(x, non_blocking=True)
+        self.ys[slot].copy_(y, non_blocking=True)
+
+    def start(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Stage the first batch and build its plan (outside the graphs)."""
+        self.cur = 0
+        self.stage(0, x, y)
+        self.plans[0].build(self.cfg, self.xs[0], self.model.train_counts)
+        self.staged = True
+
+    def step(self, x_next: Optional[torch.Tensor] = None, y_next: Optional[torch.Tensor] = None):
+        """Run the step on the staged batch; stage ``x_next, y_next`` and build their plan
+        concurrently.  Returns a ``StepResult`` of the step that ran."""
+        assert self.staged, "call start() first"
+        s = self.cur
+        if x_next is not None:
+            self.stage(1 - s, x_next, y_next)
+        self.model._sync_scalars()
+        self.graphs[s].replay()
+        self.cur = 1 - s
+        self.staged = x_next is not None
+        return StepResult(self.model._buf, self.B)
+
+
 class StepBuffers:
     """Scratch and outputs of one step for batches up to ``B`` samples."""
 

@@ -29,8 +29,8 @@ import torch
 from torch import distributions, nn
 
 from . import _lib as L
-from .engine import (BatchPlan, PlanPipeline, StepBuffers, StepResult, current_stream, make_config,
-                     require_cuda)
+from .engine import (BatchPlan, GraphedLoop, PlanPipeline, StepBuffers, StepResult, current_stream,
+                     make_config, require_cuda)
 
 _LINKS = {"abs": torch.abs, "softplus": nn.functional.softplus}
 
@@ -344,6 +344,22 @@ class CF(nn.Module):
         st = out["stats"]
         return {"loss": st[L.ST_LOSS], "kl": st[L.ST_KL], "nll_mean": st[L.ST_NLL_MEAN],
                 "pred": out["mean"], "logits": out["pred"], "stats": st}
+
+    def graphed_loop(self, B: int) -> GraphedLoop:
+        """CUDA-graph replay of the training loop for batches of exactly ``B`` samples: the step
+        on the current batch and the plan of the next one are captured once and replayed, which
+        removes the host launch overhead (the step is otherwise launch-bound).  See GraphedLoop."""
+        self._ensure(B)
+        self._sync_scalars()
+
+        def step_fn(plan, y):
+            self._cfg, self._plan = self._config(B), plan
+            io = self._buf.io(y=y)
+            self._graph_io = getattr(self, "_graph_io", []) + [io]      # keep the structs alive
+            L.check(L.lib().vfmb_sampled_step(C.byref(self._cfg), C.byref(self._tables()), C.byref(plan.struct),
+                                              C.byref(io), C.byref(self.adam), current_stream(self.device)),
+                    "vfmb_sampled_step")
+        return GraphedLoop(self, B, step_fn)
 
     def _fused_step_fast(self, x, y, plan):
         """Hot loop: cached ctypes structures, one C call for forward + backward + Adam."""
