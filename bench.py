@@ -302,11 +302,18 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
         j = (i * world + rank) % n_batches
         return xh[j * B:(j + 1) * B], yh[j * B:(j + 1) * B]
 
+    hloop = model.graphed_loop(B, depth=3) if loop is not None else None
+
     def run_graph(lo, hi):
-        """graphed loop fed straight from pinned host memory: the staging copies ARE the H2D copies"""
-        loop.start(*host_batch(lo))
+        """graphed loop fed straight from pinned host memory: the staging copies ARE the H2D copies
+        (batch i+2 is copied on a copy stream while step i runs and the plan of i+1 is built)"""
+        hloop.start(*host_batch(lo))
+        if lo + 1 < hi:
+            hloop.stage(*host_batch(lo + 1))
         for i in range(lo, hi):
-            out = loop.step(*host_batch(i + 1)) if i + 1 < hi else loop.step()
+            if i + 2 < hi:
+                hloop.stage(*host_batch(i + 2))
+            out = hloop.step()
             res[i].copy_(out["stats"], non_blocking=True)
 
     def run(lo, hi):

@@ -381,3 +381,23 @@ def test_graphed_loop_is_bitwise_identical_to_eager_steps():
     assert torch.equal(m.entity_params.weight, ref.entity_params.weight)
     assert torch.equal(m.bias_params.weight, ref.bias_params.weight)
     assert torch.equal(m._scalars, ref._scalars) and int(m.adam_step) == len(order)
+
+
+def test_graphed_loop_depth3_from_pinned_host_matches_eager():
+    meta, g = gu.load("sampled_reg_d64")
+    xh = [torch.from_numpy(gu.batch_of(meta, g, t)[0]).pin_memory() for t in range(3)]
+    yh = [torch.from_numpy(gu.batch_of(meta, g, t)[1]).pin_memory() for t in range(3)]
+    order = [0, 1, 2, 2, 1, 0, 1, 2]
+    ref = _model(meta, g, 0, seed=9)
+    ref_losses = [ref.fused_step(xh[i].to(DEV), yh[i].to(DEV))["loss"].item() for i in order]
+    m = _model(meta, g, 0, seed=9)
+    loop = m.graphed_loop(meta["batch"], depth=3)
+    loop.start(xh[order[0]], yh[order[0]])
+    loop.stage(xh[order[1]], yh[order[1]])
+    losses = []
+    for k in range(len(order)):
+        if k + 2 < len(order):
+            loop.stage(xh[order[k + 2]], yh[order[k + 2]])
+        losses.append(loop.step()["loss"].item())
+    assert losses == ref_losses
+    assert torch.equal(m.entity_params.weight, ref.entity_params.weight)

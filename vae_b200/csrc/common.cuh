@@ -44,6 +44,28 @@ __device__ __forceinline__ Vec<VEC> ld_vec_nc(const float* p) {
     return r;
 }
 
+// streaming variants for data touched once per step (Adam moments): evict-first in L2 so that
+// the L2-resident scratch of the gather kernels is not displaced
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_vec_cs(const float* p) {
+    Vec<VEC> r;
+    if constexpr (VEC == 4) {
+        float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+        r.v[0] = __ldcs(p);
+    }
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_vec_cs(float* p, const Vec<VEC>& r) {
+    if constexpr (VEC == 4) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+    } else {
+        __stcs(p, r.v[0]);
+    }
+}
+
 template <int VEC>
 __device__ __forceinline__ void st_vec(float* p, const Vec<VEC>& r) {
     if constexpr (VEC == 4) {

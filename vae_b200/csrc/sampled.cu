@@ -88,7 +88,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
             cq[ul] = cqv;
         }
         float klrow = 0.f;
-        // ---- wide work: GPW rows per round, LPR lanes per row
+        // ---- wide work: GPW rows per round, LPR lanes per row (rows were prefetched into L2 above)
 #pragma unroll 1
         for (int it = 0; it < kRounds; ++it) {
             const int sel = it * GPW + gidx;
@@ -101,15 +101,27 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                 for (int i = 0; i < NV; ++i) {
                     int k = (gl + i * LPR) * VEC;
                     if (k < d) {
-                        Vec<VEC> mu = ld_vec<VEC>(erow + k), rho = ld_vec<VEC>(erow + d + k);
+                        const Vec<VEC> mu = ld_vec<VEC>(erow + k), rho = ld_vec<VEC>(erow + d + k);
                         Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid, k, step), out;
                         if (!eps_entity) st_vec<VEC>(es + (size_t)u * d + k, e);
+                        // sum_k KL(N(mu,sig)||N(0,1)) = 0.5 (sum sig^2 + mu^2 - 1) - 0.5 log prod sig^2:
+                        // one logarithm per lane instead of one per element
+                        float quad = 0.f, prodv = 1.f;
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) {
-                            float sig = link_fn<LINK>(rho.v[j]);
+                            const float sig = link_fn<LINK>(rho.v[j]);
                             out.v[j] = fmaf(e.v[j], sig, mu.v[j]);
-                            kl += kl_std_normal_fast(mu.v[j], sig);
+                            const float vr = sig * sig;
+                            quad += vr + mu.v[j] * mu.v[j] - 1.f;
+                            prodv *= vr;
                         }
+                        float lg = __logf(prodv);
+                        if (!(prodv > 1e-30f && prodv < 1e30f)) {       // tiny / huge scales: no product trick
+                            lg = 0.f;
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho.v[j]); lg += logf(sg * sg); }
+                        }
+                        kl += 0.5f * (quad - lg);
                         st_vec<VEC>(vs + (size_t)u * d + k, out);
                     }
                 }
@@ -172,56 +184,65 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         }
         float inter_l = 0.f;
         // ---- wide work: interaction of GPW samples per round
+        if (F == 2) {
 #pragma unroll 1
-        for (int it = 0; it < kRounds; ++it) {
-            const int sel = it * GPW + gidx;
-            const int n = base + sel;
-            float part = 0.f;
-            if (F == 2) {
+            for (int it = 0; it < kRounds; ++it) {
+                const int sel = it * GPW + gidx;
                 const int r0 = bcast(rr.x, sel), r1 = bcast(rr.y, sel);
-                if (n < B) {
+                float part = 0.f;
+                if (base + sel < B) {
 #pragma unroll
                     for (int i = 0; i < NV; ++i) {
                         int k = (gl + i * LPR) * VEC;
                         if (k < d) {
-                            Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r0 * d + k);
-                            Vec<VEC> b = ld_vec_nc<VEC>(vs + (size_t)r1 * d + k);
+                            const Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r0 * d + k);
+                            const Vec<VEC> b = ld_vec_nc<VEC>(vs + (size_t)r1 * d + k);
 #pragma unroll
                             for (int j = 0; j < VEC; ++j) part = fmaf(a.v[j], b.v[j], part);
                         }
                     }
                 }
-            } else if (n < B) {
-                Vec<VEC> ssum[NV], sq[NV];
+                part = group_sum<LPR>(part, gmask);
+                hand_back<LPR>(inter_l, part, it, lane);
+            }
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < kRounds; ++it) {
+                const int sel = it * GPW + gidx;
+                const int n = base + sel;
+                float part = 0.f;
+                if (n < B) {
+                    Vec<VEC> ssum[NV], sq[NV];
 #pragma unroll
-                for (int i = 0; i < NV; ++i)
+                    for (int i = 0; i < NV; ++i)
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) { ssum[i].v[j] = 0.f; sq[i].v[j] = 0.f; }
+                        for (int j = 0; j < VEC; ++j) { ssum[i].v[j] = 0.f; sq[i].v[j] = 0.f; }
 #pragma unroll 4
-                for (int f = 0; f < F; ++f) {
-                    const int r = __ldg(inverse + (size_t)n * F + f);
+                    for (int f = 0; f < F; ++f) {
+                        const int r = __ldg(inverse + (size_t)n * F + f);
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            int k = (gl + i * LPR) * VEC;
+                            if (k < d) {
+                                Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r * d + k);
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) { ssum[i].v[j] += a.v[j]; sq[i].v[j] = fmaf(a.v[j], a.v[j], sq[i].v[j]); }
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < NV; ++i) {
                         int k = (gl + i * LPR) * VEC;
                         if (k < d) {
-                            Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r * d + k);
 #pragma unroll
-                            for (int j = 0; j < VEC; ++j) { ssum[i].v[j] += a.v[j]; sq[i].v[j] = fmaf(a.v[j], a.v[j], sq[i].v[j]); }
+                            for (int j = 0; j < VEC; ++j) part += 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]);
+                            if (msg) st_vec<VEC>(msg + (size_t)n * d + k, ssum[i]);   // S_n = sum_f v_f (unscaled)
                         }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) part += 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]);
-                        if (msg) st_vec<VEC>(msg + (size_t)n * d + k, ssum[i]);   // S_n = sum_f v_f (unscaled)
-                    }
-                }
+                part = group_sum<LPR>(part, gmask);
+                hand_back<LPR>(inter_l, part, it, lane);
             }
-            part = group_sum<LPR>(part, gmask);
-            hand_back<LPR>(inter_l, part, it, lane);
         }
         // ---- lane-parallel: likelihood, residual, outputs (coalesced)
         if (valid) {
@@ -344,10 +365,11 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
             const int ur = ok ? __ldg(pos_rank + idx) : 0;
             const int cnt = min(LPR, t1 - b0);
             const int src0 = __shfl_sync(gmask, src, 0, LPR);
-            for (int j = 0; j < cnt; j += 4) {                 // 4 row gathers in flight
-                float rj[4]; int uj[4]; Vec<VEC> t[4][NV];
+            constexpr int UNR = (NV == 1) ? 8 : 4;
+            for (int j = 0; j < cnt; j += UNR) {               // UNR row gathers in flight
+                float rj[UNR]; int uj[UNR]; Vec<VEC> t[UNR][NV];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < UNR; ++e) {
                     rj[e] = __shfl_sync(gmask, r, (j + e) & (LPR - 1), LPR);
                     uj[e] = __shfl_sync(gmask, ur, (j + e) & (LPR - 1), LPR);
                     int sj = __shfl_sync(gmask, src, (j + e) & (LPR - 1), LPR);
@@ -359,7 +381,7 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < UNR; ++e) {
                     if (j + e < cnt) {                         // group-uniform
                         if (uj[e] != cur) {
                             flush(cur);
@@ -458,8 +480,8 @@ k_adam_rows(int d, float* __restrict__ bias, float* __restrict__ bias_m, float* 
                     Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
                     Vec<VEC> m1, m2, v1, v2;
                     if (MODE == VFMB_ADAM_TOUCHED) {
-                        m1 = ld_vec<VEC>(entity_m + eoff + k); m2 = ld_vec<VEC>(entity_m + eoff + d + k);
-                        v1 = ld_vec<VEC>(entity_v + eoff + k); v2 = ld_vec<VEC>(entity_v + eoff + d + k);
+                        m1 = ld_vec_cs<VEC>(entity_m + eoff + k); m2 = ld_vec_cs<VEC>(entity_m + eoff + d + k);
+                        v1 = ld_vec_cs<VEC>(entity_v + eoff + k); v2 = ld_vec_cs<VEC>(entity_v + eoff + d + k);
                     }
                     const Vec<VEC> g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
                     const Vec<VEC> e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
@@ -477,8 +499,8 @@ k_adam_rows(int d, float* __restrict__ bias, float* __restrict__ bias_m, float* 
                             adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, inv_bc2);
                         }
                         st_vec<VEC>(entity + eoff + k, mu);        st_vec<VEC>(entity + eoff + d + k, rho);
-                        st_vec<VEC>(entity_m + eoff + k, m1);      st_vec<VEC>(entity_m + eoff + d + k, m2);
-                        st_vec<VEC>(entity_v + eoff + k, v1);      st_vec<VEC>(entity_v + eoff + d + k, v2);
+                        st_vec_cs<VEC>(entity_m + eoff + k, m1);   st_vec_cs<VEC>(entity_m + eoff + d + k, m2);
+                        st_vec_cs<VEC>(entity_v + eoff + k, v1);   st_vec_cs<VEC>(entity_v + eoff + d + k, v2);
                     } else {
                         st_vec<VEC>(grad_entity + eoff + k, gmu);  st_vec<VEC>(grad_entity + eoff + d + k, grho);
                     }
@@ -610,12 +632,12 @@ extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* t
     const int ch = kRounds * (32 / L.lpr);
     const int grid_u = grid_warps(cap.u_cap, ch), grid_b = grid_warps(cfg->B, ch);
 #define LAUNCH_STAGE(LINK)                                                                             \
-    k_stage<VEC, LPR, NV, LINK><<<grid_u, 256, 0, stream>>>(                                           \
+    k_stage<VEC, LPR, NV, LINK><<<grid_resident(k_stage<VEC, LPR, NV, LINK>, cap.u_cap, ch), 256, 0, stream>>>(                                           \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
         io->eps_bias, io->eps_entity, tab->adam_step, io->vs, io->ws, io->es,                          \
         io->ebs, io->cq, io->partials, io->counters + 0, io->stats)
 #define LAUNCH_SCORE(LINK, LIK)                                                                        \
-    k_score<VEC, LPR, NV, LINK, LIK><<<grid_b, 256, 0, stream>>>(                                      \
+    k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, stream>>>(                                      \
         dc, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->y, io->eps_global,          \
         tab->adam_step, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials,             \
         io->counters + 1, io->stats)
@@ -672,12 +694,12 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
         CUDA_TRY(cudaGetLastError());
     }
 #define LAUNCH_ADAM(LINK, MODE)                                                                          \
-    k_adam_rows<VEC, LPR, NV, LINK, MODE><<<grid_u, 256, 0, stream>>>(                                   \
+    k_adam_rows<VEC, LPR, NV, LINK, MODE><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE>, cap.u_cap, ch), 256, 0, stream>>>(                                   \
         cfg->d, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,          \
         plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, h, tab->adam_step,              \
         kl_grad_scale, io->grad_bias, io->grad_entity)
     VFMB_LAYOUT_SWITCH(L, {
-        k_gather<VEC, LPR, NV><<<grid_t, 256, 0, stream>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
+        k_gather<VEC, LPR, NV><<<grid_resident(k_gather<VEC, LPR, NV>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
                                                            plan->pos_rank, io->vs, io->msg, io->rsorted,
                                                            gslot, io->grow, io->gws);
         k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float), stream>>>(

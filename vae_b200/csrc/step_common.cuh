@@ -339,6 +339,28 @@ static inline ScratchMap scratch_map(int B, int F, int d, int64_t u_cap) {
     return m;
 }
 
+// one resident wave for a grid-stride kernel: blocks/SM from the occupancy calculator (cached)
+template <typename K>
+static inline int resident_blocks(K kernel, int block, size_t smem) {
+    static int cached = 0;                                  // one instance per kernel type
+    if (cached == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        cached = per_sm * kNumSMs;
+    }
+    return cached;
+}
+template <typename K>
+static inline int grid_resident(K kernel, int64_t units, int per_warp, size_t smem = 0) {
+    int64_t warps = (units + per_warp - 1) / per_warp;
+    int64_t g = (warps + 7) / 8;
+    const int cap = resident_blocks(kernel, 256, smem);
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
 // grid for a kernel whose warps each take `per_warp` units out of at most `units`
 static inline int grid_warps(int64_t units, int per_warp) {
     int64_t warps = (units + per_warp - 1) / per_warp;

@@ -96,7 +96,7 @@ class PlanPipeline:
             self.slot_of[id(p)] = i
         self.next = 0
         self.pending = {}                                   # (data_ptr, B) -> slot
-        self.stream = torch.cuda.Stream(device=device)
+        self.stream = torch.cuda.Stream(device=device, priority=-1)   # tiny latency-bound kernels first
         self.u_cap, self.n_tiles = self.ring[0].u_cap, self.ring[0].n_tiles
 
     def _take_slot(self) -> int:
@@ -151,72 +151,102 @@ class GraphedLoop:
     Launching the ~16 small kernels of a step from Python costs more host time than the GPU
     needs to run them; the step is launch-bound.  All per-step state (Adam step counter, Philox
     counter, reduction counters) lives on the device and the kernels take no per-step host
-    scalars, so a step can be captured once and replayed.  One graph per staging slot holds:
+    scalars, so a step can be captured once and replayed.  One graph per staging slot s holds:
 
         main stream   forward + backward + Adam on plan[s], targets ys[s]
-        side stream   plan of the NEXT batch from xs[1-s] into plan[1-s]   (forked / joined)
+        side stream   plan of the NEXT batch from xs[s+1] into plan[s+1]   (forked / joined)
 
-    ``stage`` copies a batch into the staging buffers; ``step`` replays.  Usage::
+    Batches are consumed in the order they are staged.  ``depth`` = number of staging slots:
+    2 when the batches are already on the device (staging copies run on the main stream);
+    3 when they come from pinned host memory -- the host-to-device copy of batch i+2 then runs
+    on a copy stream while step i executes.  Usage (depth 2)::
 
         loop = model.graphed_loop(B)
         loop.start(x0, y0)
         for x_next, y_next in batches[1:]:
-            res = loop.step(x_next, y_next)      # runs the step on the previously staged batch
+            res = loop.step(x_next, y_next)      # runs the step on the oldest staged batch
         res = loop.step()                         # last staged batch
     """
 
-    def __init__(self, model, B: int, step_fn):
-        self.model, self.B, self.device = model, int(B), model.device
+    def __init__(self, model, B: int, step_fn, depth: int = 2):
+        assert depth in (2, 3)
+        self.model, self.B, self.device, self.depth = model, int(B), model.device, depth
         F = model.F if hasattr(model, "F") else model.G
-        self.xs = [torch.zeros((B, F), dtype=torch.int64, device=self.device) for _ in range(2)]
-        self.ys = [torch.zeros(B, dtype=torch.float32, device=self.device) for _ in range(2)]
-        self.plans = [BatchPlan(B, F, model.R, self.device) for _ in range(2)]
-        self.side = torch.cuda.Stream(device=self.device)
+        D = depth
+        self.xs = [torch.zeros((B, F), dtype=torch.int64, device=self.device) for _ in range(D)]
+        self.ys = [torch.zeros(B, dtype=torch.float32, device=self.device) for _ in range(D)]
+        self.plans = [BatchPlan(B, F, model.R, self.device) for _ in range(D)]
+        # high priority: the plan kernels are tiny and latency-bound; they should slip in as soon
+        # as blocks of the (machine-filling) step kernels retire
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self.copy = torch.cuda.Stream(device=self.device) if depth == 3 else None
+        self.copied = [torch.cuda.Event() for _ in range(D)]
+        self.done = [torch.cuda.Event() for _ in range(D)]
         self.cfg = model._config(B)
         self.graphs = []
-        self.cur = 0                                        # slot holding the batch to run next
-        self.staged = False
+        self.head = 0                                       # slot of the next batch to run
+        self.tail = 0                                       # slot the next staged batch goes to
+        self.n_staged = 0
         # warm-up on a side stream (lazy allocations, module loading), then capture
         warm = torch.cuda.Stream(device=self.device)
         warm.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(warm):
-            for s in range(2):
+            for s in range(D):
                 self.plans[s].build(self.cfg, self.xs[s], model.train_counts)
         torch.cuda.current_stream(self.device).wait_stream(warm)
         torch.cuda.synchronize(self.device)
-        for s in range(2):
+        for s in range(D):
+            nxt = (s + 1) % D
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 cur = torch.cuda.current_stream(self.device)
                 self.side.wait_stream(cur)                   # fork
                 with torch.cuda.stream(self.side):
-                    self.plans[1 - s].build(self.cfg, self.xs[1 - s], model.train_counts)
+                    self.plans[nxt].build(self.cfg, self.xs[nxt], model.train_counts)
                 step_fn(self.plans[s], self.ys[s])           # main branch
                 cur.wait_stream(self.side)                   # join
             self.graphs.append(g)
 
-    def stage(self, slot: int, x: torch.Tensor, y: torch.Tensor) -> None:
-        self.xs[slot].copy_(x, non_blocking=True)
-        self.ys[slot].copy_(y, non_blocking=True)
+    def stage(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Copy a batch (device or pinned host) into the next free staging slot."""
+        assert self.n_staged < self.depth, "all staging slots are in use; call step() first"
+        t = self.tail
+        if self.copy is None:
+            self.xs[t].copy_(x, non_blocking=True)
+            self.ys[t].copy_(y, non_blocking=True)
+        else:
+            self.copy.wait_event(self.done[t])               # the last step that read this slot
+            with torch.cuda.stream(self.copy):
+                self.xs[t].copy_(x, non_blocking=True)
+                self.ys[t].copy_(y, non_blocking=True)
+                self.copied[t].record(self.copy)
+        self.tail = (t + 1) % self.depth
+        self.n_staged += 1
 
     def start(self, x: torch.Tensor, y: torch.Tensor) -> None:
         """Stage the first batch and build its plan (outside the graphs)."""
-        self.cur = 0
-        self.stage(0, x, y)
+        self.head = self.tail = self.n_staged = 0
+        self.stage(x, y)
+        cur = torch.cuda.current_stream(self.device)
+        if self.copy is not None:
+            cur.wait_event(self.copied[0])
         self.plans[0].build(self.cfg, self.xs[0], self.model.train_counts)
-        self.staged = True
 
     def step(self, x_next: Optional[torch.Tensor] = None, y_next: Optional[torch.Tensor] = None):
-        """Run the step on the staged batch; stage ``x_next, y_next`` and build their plan
-        concurrently.  Returns a ``StepResult`` of the step that ran."""
-        assert self.staged, "call start() first"
-        s = self.cur
+        """Run the step on the oldest staged batch; the plan of the one staged after it is built
+        concurrently.  ``x_next, y_next`` (optional) are staged first.  Returns a ``StepResult``."""
         if x_next is not None:
-            self.stage(1 - s, x_next, y_next)
+            self.stage(x_next, y_next)
+        assert self.n_staged > 0, "nothing staged: call start() / stage() first"
+        s = self.head
+        cur = torch.cuda.current_stream(self.device)
+        if self.copy is not None:                            # the side branch reads slot s+1
+            cur.wait_event(self.copied[(s + 1) % self.depth])
         self.model._sync_scalars()
         self.graphs[s].replay()
-        self.cur = 1 - s
-        self.staged = x_next is not None
+        self.done[s].record(cur)
+        self.head = (s + 1) % self.depth
+        self.n_staged -= 1
         return StepResult(self.model._buf, self.B)
 
 
