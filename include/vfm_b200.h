@@ -57,7 +57,10 @@ typedef struct vfmb_config {
     int32_t class_bound[VFMB_MAX_FIELDS];
     float class_size[VFMB_MAX_FIELDS];
     float n_train;        /* nb_train_samples (vfm-torch.py:91,359)                */
+    int32_t row_stride;   /* row-sharded tables: global id of local row r is        */
     uint64_t seed;        /* Philox key                                            */
+    int32_t row_offset;   /*   r*row_stride + row_offset (0 / 0 mean 1 / 0); the    */
+    int32_t reserved;     /*   noise and the KL class are keyed by the GLOBAL id    */
 } vfmb_config;
 
 /* Parameter tables and Adam state.  m/v may be NULL for forward-only use. */
@@ -107,7 +110,7 @@ typedef struct vfmb_plan {
     int32_t* pos_rank;   /* [B*F]     unique rank of each sorted position                    */
     int32_t* partner;    /* [B*F]     per sorted position: F==2 the rank of the sample's other
                                       field; F>2 the sample index n                          */
-    int32_t* urec;       /* [U_cap,4] per unique row {row id, batch count, seg_off, 0}       */
+    int32_t* urec;       /* [U_cap,4] per unique row {row id, segment length, seg_off, batch count} */
     int32_t* class_off;  /* [VFMB_MAX_FIELDS+1] first unique rank of each KL class (class_bound
                                       of the config); class_off[n_classes] = U               */
     float* z;            /* [VFMB_MAX_FIELDS] per-column normaliser Z_f             */
@@ -183,6 +186,27 @@ int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* tab, const v
 int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                           const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
                           float kl_grad_scale, vfmb_stream stream);
+
+/* The phases of the sampled step as separate entry points (the row-sharded multi-GPU mode
+ * runs them on different ranks with all-to-all exchanges in between; F may be 1 here):
+ *   stage      k_stage       unique rows -> vs, ws, es, ebs, cq, KL sum       (needs plan->urec, z)
+ *   score      k_score       samples -> pred, mean, resid, rsorted, msg       (needs vs, ws)
+ *   gather     k_gather + k_combine -> grow, gws.  unit_coef != 0: rows of `table` are added
+ *              unscaled and gws sums io->rsorted -- the owner-side ordered sum of the
+ *              gradient rows received from the other ranks (table [B*F, d])
+ *   adam_rows  k_adam_rows   chain rule + KL gradient + Adam / dense gradients
+ *   dp_final   scalar parameters + loss from the all-reduced tail (see mode A)            */
+int vfmb_sampled_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                       const vfmb_step_io* io, vfmb_stream stream);
+int vfmb_sampled_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                       const vfmb_step_io* io, vfmb_stream stream);
+int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
+                        const float* table, int32_t unit_coef, vfmb_stream stream);
+int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                           const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                           float kl_grad_scale, vfmb_stream stream);
+int vfmb_dp_final(const vfmb_config* cfg_global, const vfmb_tables* tab, const float* tail,
+                  const float* eps_global, const vfmb_adam* adam, float* stats, vfmb_stream stream);
 
 /* Forward (with targets) + backward + Adam on the touched rows in one call: the whole training
  * step of vfm-torch.py:351-370 after the plan.  Equivalent to vfmb_sampled_forward followed by

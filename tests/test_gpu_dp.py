@@ -72,3 +72,74 @@ def test_touched_mode_equals_single_process_fused_step():
     assert torch.allclose(m.bias_params.weight, ref.bias_params.weight, rtol=1e-5, atol=2e-6)
     assert torch.allclose(m._scalars, ref._scalars, rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(out["loss"].item(), ref._buf.stats[0].item(), rtol=1e-5)
+
+
+def _run_sharded_emulated(ranks, xs, ys):
+    """Lock-step emulation of P ranks on one device: all-to-all = transpose of the send buffers."""
+    P = len(ranks)
+    req = [r.phase_request(x, y) for r, x, y in zip(ranks, xs, ys)]
+    z = sum(q[1] for q in req)
+    a2a = lambda bufs: [torch.stack([bufs[src][dst] for src in range(P)]).contiguous() for dst in range(P)]
+    recv = a2a([q[0] for q in req])
+    replies = [r.phase_owner_stage(rv, z) for r, rv in zip(ranks, recv)]
+    rows = a2a(replies)
+    loc = [r.phase_local(rw) for r, rw in zip(ranks, rows)]
+    tail = sum(t[1].clone() for t in loc)
+    grads = a2a([t[0] for t in loc])
+    return [r.phase_owner_update(g_, tail.clone()) for r, g_ in zip(ranks, grads)]
+
+
+@pytest.mark.parametrize("P", [2, 3, 4])
+@pytest.mark.parametrize("name", ["sampled_reg_d64", "sampled_fraction"])
+def test_row_sharded_mode_b_equals_single_process_step(name, P):
+    """Mode B (row-sharded tables, all-to-all of sampled rows and gradients), P ranks emulated on one
+    GPU, against the single-process fused step on the global batch with the same per-entity noise."""
+    from vae_b200.dist import ShardedSampled
+    meta, g = gu.load(name)
+    N, M, d = meta["N"], meta["M"], meta["d"]
+    R = N + M
+    x, y = gu.batch_of(meta, g, 0)
+    n = (len(x) // P) * P
+    x, y = x[:n], y[:n]
+    gen = torch.Generator().manual_seed(3)
+    e0 = torch.randn(1, generator=gen).to(DEV)
+    eb_t, ee_t = torch.randn(R, generator=gen).to(DEV), torch.randn(R, d, generator=gen).to(DEV)
+    init = gu.state(g, "init")
+    # single process on the global batch
+    ref = S._model(meta, g, 0)
+    ref._cfg_cache.clear()
+    uniq = torch.from_numpy(np.unique(x)).to(DEV)
+    for step in range(2):
+        out_ref = ref.fused_step(torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV),
+                                 noise=(e0.reshape(1, 1), eb_t[uniq][None], ee_t[uniq][None]))
+    loss_ref = out_ref["loss"].item()
+    # P ranks
+    ini = {"bias": torch.from_numpy(init["bias_params.weight"]), "entity": torch.from_numpy(init["entity_params.weight"]),
+           "alpha": init["alpha"][0], "global_bias_mean": init["global_bias_mean"][0],
+           "global_bias_scale": init["global_bias_scale"][0]}
+    ranks = [ShardedSampled(d, [N, M], torch.from_numpy(g["train_counts"]), meta["n_train"], n // P, P, p,
+                            output=meta["output"], link=meta["link"], lr=meta["lr"], init=ini,
+                            noise_tables=(e0, eb_t, ee_t), exchange=object()) for p in range(P)]
+    xs = [torch.from_numpy(x[p * (n // P):(p + 1) * (n // P)]).to(DEV) for p in range(P)]
+    ys = [torch.from_numpy(y[p * (n // P):(p + 1) * (n // P)]).to(DEV) for p in range(P)]
+    for step in range(2):
+        outs = _run_sharded_emulated(ranks, xs, ys)
+    for r in ranks:
+        r.check_overflow()
+        assert int(r.adam_step.item()) == 2
+    ent = torch.zeros(R, 2 * d, device=DEV)
+    bias = torch.zeros(R, 2, device=DEV)
+    for r in ranks:
+        gid, b, e = r.gather_tables()
+        ent[gid], bias[gid] = e, b
+    lr = meta["lr"]
+    for got, want in ((ent, ref.entity_params.weight.detach()), (bias, ref.bias_params.weight.detach())):
+        bad = (got - want).abs() > 1e-5 * want.abs() + 2e-5 * lr + 1e-6
+        assert bad.float().mean().item() <= 1e-4, float(bad.float().mean())
+    for o in outs:
+        np.testing.assert_allclose(o["loss"].item(), loss_ref, rtol=1e-5)
+    for r in ranks:
+        assert torch.allclose(r.scalars[:3], ref._scalars[:3], rtol=1e-5, atol=2e-6)
+    # predictions of each rank's slice
+    pred = torch.cat([o["pred"] for o in outs])
+    assert torch.allclose(pred, out_ref["pred"], rtol=1e-5, atol=2e-6)

@@ -98,6 +98,7 @@ def test_plan_random_shapes_vs_torch_unique(B, F, R, hot):
     urec = plan.urec[: 4 * U].cpu().long().reshape(U, 4)
     seg = torch.cat((torch.zeros(1, dtype=torch.long), torch.cumsum(c, 0)))
     assert torch.equal(urec[:, 0], u) and torch.equal(urec[:, 1], c) and torch.equal(urec[:, 2], seg[:-1])
+    assert torch.equal(urec[:, 3], c)
     assert torch.equal(plan.pos_rank[: B * F].cpu().long(), i.reshape(-1)[occ])
     # per-column normaliser Z_f = sum_n 1/cnt_train = B for unit counts
     np.testing.assert_allclose(plan.z[:F].cpu().numpy(), np.full(F, float(B)), rtol=1e-6)

@@ -38,7 +38,8 @@ class Config(C.Structure):
                 ("S", C.c_int32), ("likelihood", C.c_int32), ("link", C.c_int32),
                 ("n_classes", C.c_int32), ("class_bound", C.c_int32 * MAX_FIELDS),
                 ("class_size", C.c_float * MAX_FIELDS), ("n_train", C.c_float),
-                ("seed", C.c_uint64)]
+                ("row_stride", C.c_int32), ("seed", C.c_uint64), ("row_offset", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Tables(C.Structure):
@@ -91,6 +92,12 @@ SYMBOLS = {
     "vfmb_sampled_forward": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), C.c_void_p]),
     "vfmb_sampled_backward": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam),
                                         C.c_int32, C.c_float, C.c_void_p]),
+    "vfmb_sampled_stage": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), C.c_void_p]),
+    "vfmb_sampled_score": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), C.c_void_p]),
+    "vfmb_sampled_gather": (C.c_int, [_P(Config), _P(Plan), _P(StepIO), C.c_void_p, C.c_int32, C.c_void_p]),
+    "vfmb_sampled_adam_rows": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam), C.c_int32,
+                                         C.c_float, C.c_void_p]),
+    "vfmb_dp_final": (C.c_int, [_P(Config), _P(Tables), C.c_void_p, C.c_void_p, _P(Adam), C.c_void_p, C.c_void_p]),
     "vfmb_sampled_step": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam), C.c_void_p]),
     "vfmb_dp_scatter_counts": (C.c_int, [_P(Config), _P(Plan), _P(StepIO), C.c_void_p, C.c_void_p, C.c_void_p]),
     "vfmb_dp_apply_sampled": (C.c_int, [_P(Config), _P(Tables), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -94,7 +94,7 @@ k_cstage(ClosedCfg c, const float* __restrict__ bias, const float* __restrict__ 
             b2s[ul] = ab.y * ab.y;
             klb = kl_normal(ab.x, tau, pbm, pbs);
             if (klb_out) klb_out[ul] = klb;
-            cqv = ((float)rec.y / tcnt) * csz_over_z;
+            cqv = ((float)rec.w / tcnt) * csz_over_z;
             cq[ul] = cqv;
             s0 += cqv;
             s1 = fmaf(cqv, ab.x, s1);

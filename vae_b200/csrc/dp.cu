@@ -194,6 +194,16 @@ extern "C" int vfmb_dp_apply_sampled(const vfmb_config* cfg, const vfmb_tables* 
     VFMB_LAYOUT_SWITCH(L, { if (cfg->link == VFMB_LINK_ABS) LAUNCH_APPLY(0); else LAUNCH_APPLY(1); });
 #undef LAUNCH_APPLY
     CUDA_TRY(cudaGetLastError());
+    return vfmb_dp_final(cfg, tab, tail, eps_global, adam, stats, stream_);
+}
+
+extern "C" int vfmb_dp_final(const vfmb_config* cfg, const vfmb_tables* tab, const float* tail,
+                             const float* eps_global, const vfmb_adam* adam, float* stats, vfmb_stream stream_) {
+    if (!cfg || !tab || !tail || !adam || !stats || !tab->scalars || !tab->scalars_m || !tab->scalars_v || !tab->adam_step)
+        return set_error(VFMB_EINVAL, "vfmb_dp_final: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DevCfg dc = make_dev(cfg);
+    AdamDev h = make_adam(adam);
 #define LAUNCH_DPF(LINK, LIK)                                                                           \
     k_dp_final<LINK, LIK><<<1, 32, 0, stream>>>(dc, tab->scalars, tab->scalars_m, tab->scalars_v, tail,  \
                                                 eps_global, h, tab->adam_step, stats)

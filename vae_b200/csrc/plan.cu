@@ -103,7 +103,8 @@ k_plan_scatter(const int32_t* __restrict__ keys_s, const int32_t* __restrict__ v
 
 // ---- P4: flat records the step kernels read with one load each -----------------------------
 //   partner[i]  per sorted position: F==2 the rank of the sample's other field, else sample n
-//   urec[u]     {row id, batch count, segment offset, 0}
+//   urec[u]     {row id, segment length, segment offset, batch count (= length; the owner of a
+//               sharded row overwrites it with the count summed over ranks)}
 struct ClassBounds { int n; int bound[kMaxFields]; };
 __device__ __forceinline__ int plan_class_of(const ClassBounds& cb, int row) {
     int k = 0;
@@ -126,7 +127,7 @@ k_plan_finish(const int32_t* __restrict__ uniq, const int32_t* __restrict__ seg_
     for (int u = tid; u < U; u += nth) {
         const int seg0 = seg_off[u];
         const int rowid = uniq[u];
-        reinterpret_cast<int4*>(urec)[u] = make_int4(rowid, seg_off[u + 1] - seg0, seg0, 0);
+        reinterpret_cast<int4*>(urec)[u] = make_int4(rowid, seg_off[u + 1] - seg0, seg0, seg_off[u + 1] - seg0);
         // class_off[g] = first rank whose class is >= g (uniq is sorted, classes are id ranges)
         const int cls = plan_class_of(cb, rowid);
         const int prev = (u == 0) ? -1 : plan_class_of(cb, uniq[u - 1]);

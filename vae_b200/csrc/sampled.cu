@@ -75,16 +75,17 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
             prefetch_row(entity + (size_t)rowid_l * 2 * d, 8 * d);
             const float2 ab = *reinterpret_cast<const float2*>(bias + (size_t)rowid_l * 2);
             const float tcnt = __ldg(train_counts + rowid_l);
-            const float eb = bias_eps(eps_bias, c, ul, rowid_l, step);
+            const int gid_l = rowid_l * c.row_stride + c.row_offset;     // global id (row-sharded tables)
+            const float eb = bias_eps(eps_bias, c, ul, gid_l, step);
             if (!eps_bias) ebs[ul] = eb;
             const float tau = link_fn<LINK>(ab.y);
             ws[ul] = fmaf(eb, tau, ab.x);
             klb = kl_std_normal(ab.x, tau);
-            const int cls = class_of(c, rowid_l);
+            const int cls = class_of(c, gid_l);
             float csz = 0.f, zc = 1.f;
 #pragma unroll
             for (int i = 0; i < kMaxFields; ++i) if (i == cls) { csz = c.class_size[i]; zc = __ldg(z + i); }
-            cqv = ((float)rec.y / tcnt) * (csz / zc);        // c_u of SURVEY 8-Maths
+            cqv = ((float)rec.w / tcnt) * (csz / zc);        // c_u of SURVEY 8-Maths (rec.w: batch count)
             cq[ul] = cqv;
         }
         float klrow = 0.f;
@@ -102,7 +103,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                     int k = (gl + i * LPR) * VEC;
                     if (k < d) {
                         const Vec<VEC> mu = ld_vec<VEC>(erow + k), rho = ld_vec<VEC>(erow + d + k);
-                        Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid, k, step), out;
+                        Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step), out;
                         if (!eps_entity) st_vec<VEC>(es + (size_t)u * d + k, e);
                         // sum_k KL(N(mu,sig)||N(0,1)) = 0.5 (sum sig^2 + mu^2 - 1) - 0.5 log prod sig^2:
                         // one logarithm per lane instead of one per element
@@ -308,7 +309,7 @@ k_scatter_resid(const float* __restrict__ resid, const int32_t* __restrict__ pos
 // (row starts here and continues); k_adam_rows adds a row's partials in tile order.  Fixed
 // summation order, no atomics => bitwise reproducible.
 // Everything read here is L2-resident scratch written by k_stage / k_score.
-template <int VEC, int LPR, int NV>
+template <int VEC, int LPR, int NV, int UNIT>
 __global__ void __launch_bounds__(256)
 k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
          const float* __restrict__ vs, const float* __restrict__ msg, const float* __restrict__ rsorted,
@@ -398,7 +399,8 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
                             int k = (gl + i * LPR) * VEC;
                             if (k < d)
 #pragma unroll
-                                for (int q = 0; q < VEC; ++q) acc[i].v[q] = fmaf(rj[e], t[e][i].v[q], acc[i].v[q]);
+                                for (int q = 0; q < VEC; ++q)
+                                    acc[i].v[q] = UNIT ? acc[i].v[q] + t[e][i].v[q] : fmaf(rj[e], t[e][i].v[q], acc[i].v[q]);
                         }
                     }
                 }
@@ -592,18 +594,6 @@ bool pick_layout(int d, Layout* out) {
     return true;
 }
 
-static int check_cfg(const vfmb_config* cfg, const char* who) {
-    if (!cfg) return set_error(VFMB_EINVAL, "%s: null config", who);
-    if (cfg->B <= 0 || cfg->R <= 0 || cfg->d <= 0) return set_error(VFMB_EINVAL, "%s: bad B/R/d", who);
-    if (cfg->F < 2 || cfg->F > VFMB_MAX_FIELDS) return set_error(VFMB_ESHAPE, "%s: F must be 2..%d", who, VFMB_MAX_FIELDS);
-    if (cfg->S != 1) return set_error(VFMB_ESHAPE, "%s: S=%d variational samples not supported yet (S=1)", who, cfg->S);
-    if (cfg->n_classes < 1 || cfg->n_classes > cfg->F) return set_error(VFMB_EINVAL, "%s: bad n_classes", who);
-    if (cfg->likelihood != VFMB_GAUSSIAN && cfg->likelihood != VFMB_BERNOULLI) return set_error(VFMB_EINVAL, "%s: bad likelihood", who);
-    if (cfg->link != VFMB_LINK_ABS && cfg->link != VFMB_LINK_SOFTPLUS) return set_error(VFMB_EINVAL, "%s: bad link", who);
-    return 0;
-}
-
-
 }  // namespace vfmb
 
 using namespace vfmb;
@@ -615,95 +605,136 @@ extern "C" int64_t vfmb_partials_doubles(const vfmb_config* cfg) {
     return (int64_t)scratch_map(cfg->B, cfg->F, cfg->d, u_cap).total_doubles;
 }
 
-extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                                    const vfmb_step_io* io, vfmb_stream stream_) {
-    int rc = check_cfg(cfg, "vfmb_sampled_forward");
-    if (rc) return rc;
-    if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: null argument");
-    if (cfg->F > 2 && io->y && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: msg scratch required for F>2");
-    if (!io->eps_entity && !io->es) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: noise scratch (es/ebs) required");
-    cudaStream_t stream = (cudaStream_t)stream_;
+// ---- shared host-side preparation of one phase launch
+struct Prep {
+    cudaStream_t stream;
     Layout L;
-    if (!pick_layout(cfg->d, &L)) return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
-    DevCfg dc = make_dev(cfg);
+    DevCfg dc;
     vfmb_plan_capacity_t cap;
-    rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &cap);
+    int ch;
+};
+static int prep(const vfmb_config* cfg, const char* who, vfmb_stream stream_, int min_fields, Prep* p) {
+    if (!cfg) return set_error(VFMB_EINVAL, "%s: null config", who);
+    if (cfg->B <= 0 || cfg->R <= 0 || cfg->d <= 0) return set_error(VFMB_EINVAL, "%s: bad B/R/d", who);
+    if (cfg->F < min_fields || cfg->F > VFMB_MAX_FIELDS) return set_error(VFMB_ESHAPE, "%s: F must be %d..%d", who, min_fields, VFMB_MAX_FIELDS);
+    if (cfg->S != 1) return set_error(VFMB_ESHAPE, "%s: S=%d variational samples not supported yet (S=1)", who, cfg->S);
+    if (cfg->n_classes < 1 || cfg->n_classes > VFMB_MAX_FIELDS) return set_error(VFMB_EINVAL, "%s: bad n_classes", who);
+    if (cfg->likelihood != VFMB_GAUSSIAN && cfg->likelihood != VFMB_BERNOULLI) return set_error(VFMB_EINVAL, "%s: bad likelihood", who);
+    if (cfg->link != VFMB_LINK_ABS && cfg->link != VFMB_LINK_SOFTPLUS) return set_error(VFMB_EINVAL, "%s: bad link", who);
+    p->stream = (cudaStream_t)stream_;
+    if (!pick_layout(cfg->d, &p->L)) return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
+    p->dc = make_dev(cfg);
+    int rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &p->cap);
     if (rc) return rc;
-    const int ch = kRounds * (32 / L.lpr);
-    const int grid_u = grid_warps(cap.u_cap, ch), grid_b = grid_warps(cfg->B, ch);
+    p->ch = kRounds * (32 / p->L.lpr);
+    return 0;
+}
+
+extern "C" int vfmb_sampled_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                  const vfmb_step_io* io, vfmb_stream stream_) {
+    Prep P;
+    int rc = prep(cfg, "vfmb_sampled_stage", stream_, 1, &P);
+    if (rc) return rc;
+    if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: null argument");
+    if (!io->eps_entity && (!io->es || !io->ebs)) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: noise scratch (es/ebs) required");
+    if (!io->vs || !io->ws || !io->cq || !io->partials || !io->counters || !io->stats)
+        return set_error(VFMB_EINVAL, "vfmb_sampled_stage: scratch required");
+    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch; const auto& cap = P.cap;
 #define LAUNCH_STAGE(LINK)                                                                             \
-    k_stage<VEC, LPR, NV, LINK><<<grid_resident(k_stage<VEC, LPR, NV, LINK>, cap.u_cap, ch), 256, 0, stream>>>(                                           \
+    k_stage<VEC, LPR, NV, LINK><<<grid_resident(k_stage<VEC, LPR, NV, LINK>, cap.u_cap, ch), 256, 0, stream>>>( \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
         io->eps_bias, io->eps_entity, tab->adam_step, io->vs, io->ws, io->es,                          \
         io->ebs, io->cq, io->partials, io->counters + 0, io->stats)
+    VFMB_LAYOUT_SWITCH(L, { if (cfg->link == VFMB_LINK_ABS) LAUNCH_STAGE(0); else LAUNCH_STAGE(1); });
+#undef LAUNCH_STAGE
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_sampled_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                  const vfmb_step_io* io, vfmb_stream stream_) {
+    Prep P;
+    int rc = prep(cfg, "vfmb_sampled_score", stream_, 2, &P);
+    if (rc) return rc;
+    if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_score: null argument");
+    if (cfg->F > 2 && io->y && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_score: msg scratch required for F>2");
+    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch;
 #define LAUNCH_SCORE(LINK, LIK)                                                                        \
-    k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, stream>>>(                                      \
+    k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, stream>>>( \
         dc, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->y, io->eps_global,          \
         tab->adam_step, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials,             \
         io->counters + 1, io->stats)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
-            LAUNCH_STAGE(0);
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SCORE(0, VFMB_GAUSSIAN); else LAUNCH_SCORE(0, VFMB_BERNOULLI);
         } else {
-            LAUNCH_STAGE(1);
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SCORE(1, VFMB_GAUSSIAN); else LAUNCH_SCORE(1, VFMB_BERNOULLI);
         }
     });
-#undef LAUNCH_STAGE
 #undef LAUNCH_SCORE
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                                     const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
-                                     float kl_grad_scale, vfmb_stream stream_) {
-    int rc = check_cfg(cfg, "vfmb_sampled_backward");
+extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                    const vfmb_step_io* io, vfmb_stream stream) {
+    int rc = vfmb_sampled_stage(cfg, tab, plan, io, stream);
     if (rc) return rc;
-    if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: null argument");
-    if (mode == VFMB_ADAM_TOUCHED && (!adam || !tab->entity_m || !tab->entity_v || !tab->bias_m || !tab->bias_v ||
-                                      !tab->scalars_m || !tab->scalars_v || !tab->adam_step))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: Adam state required");
-    if (mode == VFMB_GRAD_ONLY && (!io->grad_bias || !io->grad_entity))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: gradient outputs required");
-    if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: bad mode");
-    if (cfg->F > 2 && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: msg scratch required for F>2");
-    if (!io->grow || !io->gws || !io->cq || !io->rsorted) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: scratch required");
-    cudaStream_t stream = (cudaStream_t)stream_;
-    Layout L;
-    if (!pick_layout(cfg->d, &L)) return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
-    DevCfg dc = make_dev(cfg);
-    vfmb_plan_capacity_t cap;
-    rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &cap);
+    return vfmb_sampled_score(cfg, tab, plan, io, stream);
+}
+
+extern "C" int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
+                                   const float* table, int32_t unit_coef, vfmb_stream stream_) {
+    Prep P;
+    int rc = prep(cfg, "vfmb_sampled_gather", stream_, 1, &P);
     if (rc) return rc;
-    AdamDev h = make_adam(adam);
-    const int ch = kRounds * (32 / L.lpr);
-    const int grid_u = grid_warps(cap.u_cap, ch), grid_t = grid_warps(cap.n_tiles, 32 / L.lpr);
+    if (!plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: null argument");
+    if (!io->grow || !io->gws || !io->rsorted || !io->partials) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: scratch required");
+    const Layout& L = P.L; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
+    // F == 2: partner rows come from the sampled-row scratch; otherwise from `table`
+    // (F > 2: the per-sample field sums written by k_score; unit_coef: received gradient rows)
+    const float* tbl = table ? table : io->msg;
+    if (cfg->F != 2 && !tbl) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: table required for F != 2");
+    const int N = cfg->B * cfg->F;
+    VFMB_LAYOUT_SWITCH(L, {
+        if (unit_coef)
+            k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>(
+                cfg->d, cfg->F, N, plan->partner, plan->pos_rank, io->vs, tbl, io->rsorted, gslot, io->grow, io->gws);
+        else
+            k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>(
+                cfg->d, cfg->F, N, plan->partner, plan->pos_rank, io->vs, tbl, io->rsorted, gslot, io->grow, io->gws);
+        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float), stream>>>(
+            cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
+    });
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                      const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                                      float kl_grad_scale, vfmb_stream stream_) {
+    Prep P;
+    int rc = prep(cfg, "vfmb_sampled_adam_rows", stream_, 1, &P);
+    if (rc) return rc;
+    if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: null argument");
+    if (mode == VFMB_ADAM_TOUCHED && (!adam || !tab->entity_m || !tab->entity_v || !tab->bias_m || !tab->bias_v || !tab->adam_step))
+        return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: Adam state required");
+    if (mode == VFMB_GRAD_ONLY && (!io->grad_bias || !io->grad_entity))
+        return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: gradient outputs required");
+    if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: bad mode");
+    if (!io->grow || !io->gws || !io->cq) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: scratch required");
+    const Layout& L = P.L; cudaStream_t stream = P.stream; const int ch = P.ch; const auto& cap = P.cap;
+    AdamDev h = make_adam(adam);
     // the noise the forward used: injected arrays, or what k_stage wrote to scratch (Philox)
     const float* eps_e = io->eps_entity ? io->eps_entity : io->es;
     const float* eps_b = io->eps_bias ? io->eps_bias : io->ebs;
-    if (mode == VFMB_GRAD_ONLY) {
-        // the residuals may come from the caller's autograd: (re)build their sorted-order copy
-        if (!io->resid) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: resid required");
-        const int N = cfg->B * cfg->F;
-        int g = (N + 255) / 256;
-        if (g > 4 * kNumSMs) g = 4 * kNumSMs;
-        k_scatter_resid<<<g, 256, 0, stream>>>(io->resid, plan->pos_of, N, cfg->F, io->rsorted);
-        CUDA_TRY(cudaGetLastError());
-    }
 #define LAUNCH_ADAM(LINK, MODE)                                                                          \
-    k_adam_rows<VEC, LPR, NV, LINK, MODE><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE>, cap.u_cap, ch), 256, 0, stream>>>(                                   \
+    k_adam_rows<VEC, LPR, NV, LINK, MODE><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE>, cap.u_cap, ch), 256, 0, stream>>>( \
         cfg->d, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,          \
         plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, h, tab->adam_step,              \
         kl_grad_scale, io->grad_bias, io->grad_entity)
     VFMB_LAYOUT_SWITCH(L, {
-        k_gather<VEC, LPR, NV><<<grid_resident(k_gather<VEC, LPR, NV>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
-                                                           plan->pos_rank, io->vs, io->msg, io->rsorted,
-                                                           gslot, io->grow, io->gws);
-        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float), stream>>>(
-            cfg->d, cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
         cudaEvent_t ev0, ev1;
         profile_events(&ev0, &ev1);
         if (ev0 && ev1) cudaEventRecord(ev0, stream);
@@ -716,7 +747,35 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
     });
 #undef LAUNCH_ADAM
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                     const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                                     float kl_grad_scale, vfmb_stream stream_) {
+    Prep P;
+    int rc = prep(cfg, "vfmb_sampled_backward", stream_, 2, &P);
+    if (rc) return rc;
+    if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: null argument");
+    if (mode == VFMB_ADAM_TOUCHED && (!tab->scalars_m || !tab->scalars_v))
+        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: Adam state required");
+    cudaStream_t stream = P.stream;
+    if (mode == VFMB_GRAD_ONLY) {
+        // the residuals may come from the caller's autograd: (re)build their sorted-order copy
+        if (!io->resid || !io->rsorted) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: resid required");
+        const int N = cfg->B * cfg->F;
+        int g = (N + 255) / 256;
+        if (g > 4 * kNumSMs) g = 4 * kNumSMs;
+        k_scatter_resid<<<g, 256, 0, stream>>>(io->resid, plan->pos_of, N, cfg->F, io->rsorted);
+        CUDA_TRY(cudaGetLastError());
+    }
+    rc = vfmb_sampled_gather(cfg, plan, io, nullptr, 0, stream_);
+    if (rc) return rc;
+    rc = vfmb_sampled_adam_rows(cfg, tab, plan, io, adam, mode, kl_grad_scale, stream_);
+    if (rc) return rc;
     if (mode == VFMB_GRAD_ONLY && !io->grad_scalars) return 0;
+    AdamDev h = make_adam(adam);
+    const DevCfg& dc = P.dc;
 #define LAUNCH_FINAL(LINK, LIK, MODE)                                                                    \
     k_final<LINK, LIK, MODE><<<1, 32, 0, stream>>>(dc, tab->scalars, tab->scalars_m, tab->scalars_v,     \
                                                    io->stats, io->eps_global, h, tab->adam_step,         \

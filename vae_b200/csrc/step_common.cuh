@@ -7,6 +7,7 @@ namespace vfmb {
 
 struct DevCfg {
     int B, F, d, S, n_classes;
+    int row_stride, row_offset;                          // global id = row*stride + offset (sharding)
     int class_bound[kMaxFields];
     float class_size[kMaxFields];
     float n_train;
@@ -18,6 +19,8 @@ static DevCfg make_dev(const vfmb_config* c) {
     r.B = c->B; r.F = c->F; r.d = c->d; r.S = c->S; r.n_classes = c->n_classes;
     for (int i = 0; i < kMaxFields; ++i) { r.class_bound[i] = c->class_bound[i]; r.class_size[i] = c->class_size[i]; }
     r.n_train = c->n_train; r.seed = c->seed;
+    r.row_stride = c->row_stride > 0 ? c->row_stride : 1;
+    r.row_offset = c->row_stride > 0 ? c->row_offset : 0;
     return r;
 }
 

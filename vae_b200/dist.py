@@ -8,8 +8,9 @@ and step, never by rank or batch position), same global batch counts in the KL w
 Mode A -- ``DataParallelSampled``: replicated tables, batch data parallel, ONE dense all-reduce
 per step over ``[grad_entity | grad_bias | batch counts | tail]``.  Exact reference semantics
 (including dense Adam over every row) at a cost of ``R*(2d+3)*4`` bytes per step, so it is the
-mode for small tables (BASELINE configs 1-2).  Large tables need row sharding with an
-all-to-all of touched rows (mode B), which is not in this round.
+mode for small tables (BASELINE configs 1-2).  Mode B -- ``ShardedSampled``: row-sharded tables (``owner = row mod P``), three fixed-shape
+all-to-alls per step (unique ids, sampled rows, row gradients) and a 16-float all-reduce; what
+scales (BASELINE configs 3-5).
 """
 from __future__ import annotations
 
@@ -145,3 +146,250 @@ class DataParallelSampled:
         flat = self.local_backward(x_local, y_local, noise)
         allreduce_flat(flat, self.group)
         return self.apply(flat)
+
+
+# =============================================================================================
+# Mode B -- row-sharded tables, all-to-all of sampled rows and of row gradients
+# =============================================================================================
+T_KLROWS = 11
+
+
+class TorchExchange:
+    """The collectives of mode B over torch.distributed (NCCL on GPUs)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def all_to_all(self, send: torch.Tensor) -> torch.Tensor:
+        """send[q] goes to rank q; returns recv with recv[q] = what rank q sent to this rank."""
+        import torch.distributed as dist
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class ShardedSampled:
+    """Sampled-ELBO VFM with ROW-SHARDED tables (mode B).
+
+    Row ``r`` (parameters, Adam moments, train count) lives on rank ``r mod P`` at local index
+    ``r // P``.  One step on the global batch (each rank holds a slice):
+
+      1. local plan of the rank's slice; its unique ids are bucketed by owner into fixed-capacity
+         slots and exchanged (all-to-all #1: ids + local batch counts);
+      2. the owner plans the received ids (same plan kernels, F = 1), sums the batch counts,
+         draws the noise (Philox keyed by the GLOBAL id -> identical whoever asks) and returns
+         the sampled rows (all-to-all #2);
+      3. each rank scores its samples and runs the ordered segmented reduction locally, then
+         sends the row gradients back (all-to-all #3);
+      4. the owner adds the gradients of a row in source-rank order (deterministic), applies the
+         KL gradient with the global counts and Adam; a small all-reduce carries the scalar sums.
+
+    Slots are padded to a fixed capacity so that every exchange has a static shape (no host
+    synchronisation); padding maps to a sentinel row ``R_loc`` kept at the KL minimum.
+    """
+
+    def __init__(self, embedding_size: int, field_sizes: Sequence[int], train_counts: torch.Tensor,
+                 n_train: float, batch_local: int, world: int, rank: int, output: str = "reg",
+                 link: str = "abs", kl_weighting: str = "torch", seed: int = 7, lr: float = 1e-3,
+                 betas=(0.9, 0.999), eps: float = 1e-8, device="cuda", exchange=None,
+                 init: Optional[dict] = None, noise_tables=None, slack: float = 1.0):
+        from .engine import BatchPlan, StepBuffers, require_cuda
+        self.device = require_cuda(device)
+        L.lib()
+        self.d, self.P, self.p = int(embedding_size), int(world), int(rank)
+        self.field_sizes = list(map(int, field_sizes))
+        self.F, self.R = len(self.field_sizes), int(sum(self.field_sizes))
+        self.B, self.n_train = int(batch_local), float(n_train)
+        self.output, self.link = output, link
+        self.adam = L.Adam(lr, betas[0], betas[1], eps)
+        self.exchange = exchange if exchange is not None else TorchExchange()
+        self.noise_tables = noise_tables
+        dev, d, P, p = self.device, self.d, self.P, self.p
+        if kl_weighting == "torch":
+            bounds, sizes = [self.field_sizes[0] + 1], self.field_sizes[:2]
+        else:
+            import numpy as np
+            bounds, sizes = list(np.cumsum(self.field_sizes)[:-1]), self.field_sizes
+        self.R_loc = (self.R + P - 1) // P
+        Rl = self.R_loc + 1                                   # + sentinel row for padding slots
+        # ---- local shards
+        tc = torch.as_tensor(train_counts).reshape(-1).to(torch.float32)
+        self.train_counts = tc.to(dev)                        # replicated [R]: 4 B/row, feeds Z_f
+        tcl = torch.full((Rl,), float("inf"), dtype=torch.float32)
+        mine = tc[p::P]
+        tcl[: len(mine)] = mine
+        self.train_counts_loc = tcl.to(dev)
+        if init is not None:
+            bias = torch.zeros(Rl, 2); ent = torch.zeros(Rl, 2 * d)
+            bias[: len(mine)] = init["bias"][p::P]; ent[: len(mine)] = init["entity"][p::P]
+            scal = torch.zeros(L.S_COUNT)
+            scal[L.S_ALPHA], scal[L.S_GB_MEAN], scal[L.S_GB_SCALE] = (float(init["alpha"]), float(init["global_bias_mean"]),
+                                                                       float(init["global_bias_scale"]))
+        else:
+            g = torch.Generator().manual_seed(seed * 1000003 + p)
+            bias = torch.randn(Rl, 2, generator=g); ent = torch.randn(Rl, 2 * d, generator=g)
+            scal = torch.tensor([0.5, 0.0, 1.0, 0.0])
+        bias[len(mine):] = torch.tensor([0.0, 1.0])           # unused + sentinel rows: KL minimum
+        ent[len(mine):, :d] = 0.0
+        ent[len(mine):, d:] = 1.0
+        z = torch.zeros_like
+        self.bias, self.entity = bias.to(dev), ent.to(dev)
+        self.bias_m, self.bias_v, self.entity_m, self.entity_v = z(self.bias), z(self.bias), z(self.entity), z(self.entity)
+        self.scalars = scal.to(dev)
+        self.scalars_m, self.scalars_v = z(self.scalars), z(self.scalars)
+        self.adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        # ---- requester side (local slice, global ids)
+        mk = lambda B, F, R, n_tr, stride, off: self._cfg(B, F, R, n_tr, bounds, sizes, seed, stride, off)
+        self.cfg_l = mk(self.B, self.F, self.R, self.n_train / P, 0, 0)
+        self.cfg_g = mk(self.B * P, self.F, self.R, self.n_train, 0, 0)
+        self.plan_l = BatchPlan(self.B, self.F, self.R, dev)
+        self.buf_l = StepBuffers(self.cfg_l, self.plan_l, dev, L.S_COUNT, need_msg=self.F > 2)
+        # ---- owner side (received ids, local row indices)
+        u_cap = self.plan_l.u_cap
+        self.CAP = int(-(-int(u_cap * slack) // P))
+        self.M = self.CAP * P
+        self.cfg_o = mk(self.M, 1, Rl, self.n_train, P, p)
+        self.plan_o = BatchPlan(self.M, 1, Rl, dev)
+        self.buf_o = StepBuffers(self.cfg_o, self.plan_o, dev, L.S_COUNT, need_msg=False)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ar_P = torch.arange(P, device=dev)
+        self._ar_U = torch.arange(u_cap, device=dev)
+        self.tail = torch.zeros(DP_TAIL, dtype=torch.float32, device=dev)
+
+    def _cfg(self, B, F, R, n_train, bounds, sizes, seed, stride, off):
+        cfg = make_config(B, F, self.d, R, 1, self.output, self.link, bounds, sizes, n_train, seed)
+        cfg.row_stride, cfg.row_offset = int(stride), int(off)
+        return cfg
+
+    def _tables(self) -> L.Tables:
+        return L.Tables(L.ptr(self.bias), L.ptr(self.bias_m), L.ptr(self.bias_v), L.ptr(self.entity),
+                        L.ptr(self.entity_m), L.ptr(self.entity_v), L.ptr(self.train_counts_loc),
+                        L.ptr(self.scalars), L.ptr(self.scalars_m), L.ptr(self.scalars_v), L.ptr(self.adam_step))
+
+    # ------------------------------------------------------------------ phases
+    @torch.no_grad()
+    def phase_request(self, x: torch.Tensor, y: torch.Tensor):
+        """Local plan; unique ids bucketed by owner.  Returns (send [P,CAP,2] int32, z_local [8])."""
+        P, CAP, M = self.P, self.CAP, self.M
+        self._y = y.to(self.device, torch.float32).contiguous()
+        x = x.to(self.device).contiguous()
+        self.plan_l.build(self.cfg_l, x, self.train_counts)
+        pl = self.plan_l
+        valid = self._ar_U < pl.meta[0]
+        ids = pl.uniq
+        owner = torch.where(valid, ids % P, torch.zeros_like(ids)).long()
+        onehot = (owner[:, None] == self._ar_P[None, :]) & valid[:, None]
+        ordinal = (onehot.cumsum(0, dtype=torch.int32) - 1).gather(1, owner[:, None]).squeeze(1).long()
+        over = valid & (ordinal >= CAP)
+        self.overflow += over.any().int()
+        ok = valid & ~over
+        self._dest = torch.where(ok, owner * CAP + ordinal, torch.full_like(owner, M))
+        send = torch.full((M + 1, 2), -1, dtype=torch.int32, device=self.device)
+        cnt = pl.urec.view(-1, 4)[:, 1]
+        send[self._dest] = torch.stack((ids, cnt), dim=1)
+        return send[:M].view(P, CAP, 2).contiguous(), pl.z.clone()
+
+    @torch.no_grad()
+    def phase_owner_stage(self, recv: torch.Tensor, z_global: torch.Tensor) -> torch.Tensor:
+        """Owner: plan the received ids, global batch counts, sample the rows.  Returns the reply
+        [P,CAP,d+1] (sampled factor row | sampled bias) in the slot layout of the request."""
+        M, d, P, p = self.M, self.d, self.P, self.p
+        ids, cnts = recv.reshape(M, 2)[:, 0], recv.reshape(M, 2)[:, 1]
+        real = ids >= 0
+        loc = torch.where(real, ids // P, torch.full_like(ids, self.R_loc)).long().view(M, 1).contiguous()
+        po, bo = self.plan_o, self.buf_o
+        po.build(self.cfg_o, loc, self.train_counts_loc)
+        self._inv_o = po.inverse[:M].long()
+        gcnt = torch.zeros(po.u_cap, dtype=torch.float32, device=self.device)
+        gcnt.index_add_(0, self._inv_o, torch.where(real, cnts, torch.zeros_like(cnts)).float())   # integers: exact
+        po.urec.view(-1, 4)[:, 3] = gcnt.int()              # batch count summed over the ranks
+        po.z.copy_(z_global)
+        noise = None
+        if self.noise_tables is not None:                     # tests: per-entity noise tables
+            e0, eb_t, ee_t = self.noise_tables
+            gid = (po.uniq.long() * P + p).clamp_(min=0, max=self.R - 1)   # ranks >= U hold garbage ids
+            noise = (e0.reshape(1).contiguous(), eb_t[gid].contiguous(), ee_t[gid].contiguous())
+        self._noise_o = noise
+        self._io_o = bo.io(noise=noise)
+        L.check(L.lib().vfmb_sampled_stage(C.byref(self.cfg_o), C.byref(self._tables()), C.byref(po.struct),
+                                           C.byref(self._io_o), current_stream(self.device)), "vfmb_sampled_stage")
+        rows = bo.vs.view(po.u_cap, d)[self._inv_o]
+        return torch.cat((rows, bo.ws[self._inv_o][:, None]), dim=1).view(P, self.CAP, d + 1).contiguous()
+
+    @torch.no_grad()
+    def phase_local(self, recv_rows: torch.Tensor):
+        """Requester: place the sampled rows, score the samples, ordered segmented reduction.
+        Returns (row gradients [P,CAP,d+1] in slot layout, additive scalars tail [16])."""
+        M, d, P = self.M, self.d, self.P
+        pl, bl = self.plan_l, self.buf_l
+        got = recv_rows.reshape(M, d + 1)[self._dest.clamp(max=M - 1)]
+        bl.vs.view(pl.u_cap, d).copy_(got[:, :d])
+        bl.ws.copy_(got[:, d])
+        e0 = self.noise_tables[0].reshape(1).contiguous() if self.noise_tables is not None else None
+        io = bl.io(y=self._y)
+        io.eps_global = L.ptr(e0)
+        self._io_l = io
+        tab, s, lib = self._tables(), current_stream(self.device), L.lib()
+        L.check(lib.vfmb_sampled_score(C.byref(self.cfg_l), C.byref(tab), C.byref(pl.struct), C.byref(io), s),
+                "vfmb_sampled_score")
+        L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_l), C.byref(pl.struct), C.byref(io), None, 0, s),
+                "vfmb_sampled_gather")
+        g = torch.zeros((M + 1, d + 1), dtype=torch.float32, device=self.device)
+        g[self._dest] = torch.cat((bl.grow.view(pl.u_cap, d), bl.gws[:, None]), dim=1)
+        st = bl.stats
+        self.tail.zero_()
+        self.tail[T_NLL] = st[L.ST_NLL_MEAN] * self.B
+        self.tail[T_RESID], self.tail[T_SQERR] = st[L.ST_SUM_RESID], st[L.ST_SUM_SQERR]
+        self.tail[T_KLROWS] = self.buf_o.stats[L.ST_KL_ROWS]
+        return g[:M].view(P, self.CAP, d + 1).contiguous(), self.tail
+
+    @torch.no_grad()
+    def phase_owner_update(self, recv_g: torch.Tensor, tail_global: torch.Tensor) -> dict:
+        """Owner: add a row's gradients in source-rank order, KL gradient + Adam on the owned rows,
+        replicated scalar update."""
+        M, d = self.M, self.d
+        po, bo = self.plan_o, self.buf_o
+        G = recv_g.reshape(M, d + 1)
+        table = G[:, :d].contiguous()
+        bo.rsorted[:M] = G[:, d][po.occ[:M].long()]
+        io, tab, s, lib = self._io_o, self._tables(), current_stream(self.device), L.lib()
+        L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_o), C.byref(po.struct), C.byref(io), table.data_ptr(), 1, s),
+                "vfmb_sampled_gather")
+        L.check(lib.vfmb_sampled_adam_rows(C.byref(self.cfg_o), C.byref(tab), C.byref(po.struct), C.byref(io),
+                                           C.byref(self.adam), L.ADAM_TOUCHED, 1.0, s), "vfmb_sampled_adam_rows")
+        st = self.buf_l.stats
+        st[L.ST_KL_ROWS] = tail_global[T_KLROWS]
+        e0 = self.noise_tables[0].reshape(1).contiguous() if self.noise_tables is not None else None
+        L.check(lib.vfmb_dp_final(C.byref(self.cfg_g), C.byref(tab), tail_global.data_ptr(), L.ptr(e0),
+                                  C.byref(self.adam), st.data_ptr(), s), "vfmb_dp_final")
+        return {"loss": st[L.ST_LOSS], "kl": st[L.ST_KL], "nll_mean": st[L.ST_NLL_MEAN],
+                "pred": self.buf_l.mean[: self.B], "stats": st}
+
+    def step(self, x_local: torch.Tensor, y_local: torch.Tensor) -> dict:
+        ex = self.exchange
+        send, z = self.phase_request(x_local, y_local)
+        recv = ex.all_to_all(send)
+        z = ex.all_reduce(z)
+        reply = self.phase_owner_stage(recv, z)
+        rows = ex.all_to_all(reply)
+        grads, tail = self.phase_local(rows)
+        recv_g = ex.all_to_all(grads)
+        tail = ex.all_reduce(tail)
+        return self.phase_owner_update(recv_g, tail)
+
+    def check_overflow(self) -> None:
+        """Raises if a bucket ever exceeded the slot capacity (synchronises; call occasionally)."""
+        if int(self.overflow.item()) != 0:
+            raise RuntimeError("ShardedSampled: owner bucket overflow -- increase `slack`")
+
+    # ------------------------------------------------------------------ helpers (tests / checkpoints)
+    def gather_tables(self):
+        """This rank's rows as (global ids, bias rows, entity rows) -- for assembling full tables."""
+        n = len(range(self.p, self.R, self.P))
+        gid = torch.arange(self.p, self.R, self.P, device=self.device)
+        return gid, self.bias[:n], self.entity[:n]
