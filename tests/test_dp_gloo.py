@@ -109,3 +109,56 @@ def test_layout_and_slices():
     assert [local_slice(8, r, 2) for r in range(2)] == [slice(0, 4), slice(4, 8)]
     with pytest.raises(AssertionError):
         local_slice(7, 0, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# mode B host logic: owner bucketing + fixed-shape all-to-all (gloo, world_size 2)
+def _a2a_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vae_b200.dist import TorchExchange, bucket_by_owner
+        rng = np.random.default_rng(rank)
+        U_cap, CAP = 40, 24
+        ids = np.sort(rng.choice(100, size=30, replace=False)).astype(np.int32)
+        cnt = rng.integers(1, 9, size=30).astype(np.int32)
+        pad = np.full(U_cap - 30, -7, dtype=np.int32)                     # garbage beyond n_valid
+        send, dest, over = bucket_by_owner(torch.from_numpy(np.concatenate([ids, pad])),
+                                           torch.from_numpy(np.concatenate([cnt, pad])), torch.tensor(30), world, CAP)
+        assert not bool(over)
+        recv = TorchExchange().all_to_all(send[: world * CAP].view(world, CAP, 2).contiguous())
+        # every received real id is owned by this rank and carries its sender's count
+        real = recv[..., 0] >= 0
+        assert bool(((recv[..., 0][real] % world) == rank).all())
+        # echo the ids back through the same slots: the requester recovers its list via `dest`
+        back = TorchExchange().all_to_all(recv)
+        got = back.reshape(world * CAP, 2)[dest[:30]]
+        assert np.array_equal(got[:, 0].numpy(), ids) and np.array_equal(got[:, 1].numpy(), cnt)
+        t = TorchExchange().all_reduce(torch.tensor([float(rank + 1)]))
+        assert t.item() == 3.0
+        if rank == 0:
+            out_q.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mode_b_bucketing_and_all_to_all_round_trip():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_a2a_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=120) == "ok"
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+
+def test_bucket_overflow_is_flagged():
+    from vae_b200.dist import bucket_by_owner
+    ids = torch.arange(0, 20, 2, dtype=torch.int32)                       # all owned by rank 0 of 2
+    send, dest, over = bucket_by_owner(ids, torch.ones_like(ids), torch.tensor(10), 2, 4)
+    assert bool(over) and int((dest == 8).sum()) == 6                     # 6 ids went to the dump slot
+    assert send[:4, 0].tolist() == [0, 2, 4, 6] and send[4:8, 0].tolist() == [-1] * 4

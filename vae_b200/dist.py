@@ -154,6 +154,28 @@ class DataParallelSampled:
 T_KLROWS = 11
 
 
+def bucket_by_owner(ids: torch.Tensor, cnt: torch.Tensor, n_valid: torch.Tensor, P: int, CAP: int):
+    """Place the first ``n_valid`` sorted unique ids into fixed-capacity per-owner slots.
+
+    owner(id) = id mod P; inside an owner's bucket the ids keep their (ascending) order.
+    Returns ``send [P*CAP+1, 2] int32`` rows {id, count} (-1 = empty; the last row is a dump slot),
+    ``dest [len(ids)]`` = slot of every unique rank (dump slot for invalid / overflowing ones) and
+    the overflow flag.  Pure tensor code, no host synchronisation (``n_valid`` stays on the device)."""
+    M = P * CAP
+    dev = ids.device
+    valid = torch.arange(ids.numel(), device=dev) < n_valid
+    owner = torch.where(valid, ids % P, torch.zeros_like(ids)).long()
+    onehot = (owner[:, None] == torch.arange(P, device=dev)[None, :]) & valid[:, None]
+    ordinal = (onehot.cumsum(0, dtype=torch.int32) - 1).gather(1, owner[:, None]).squeeze(1).long()
+    over = valid & (ordinal >= CAP)
+    ok = valid & ~over
+    dest = torch.where(ok, owner * CAP + ordinal, torch.full_like(owner, M))
+    send = torch.full((M + 1, 2), -1, dtype=torch.int32, device=dev)
+    send[dest] = torch.stack((ids.int(), cnt.int()), dim=1)
+    send[M] = -1
+    return send, dest, over.any()
+
+
 class TorchExchange:
     """The collectives of mode B over torch.distributed (NCCL on GPUs)."""
 
@@ -280,18 +302,8 @@ class ShardedSampled:
         x = x.to(self.device).contiguous()
         self.plan_l.build(self.cfg_l, x, self.train_counts)
         pl = self.plan_l
-        valid = self._ar_U < pl.meta[0]
-        ids = pl.uniq
-        owner = torch.where(valid, ids % P, torch.zeros_like(ids)).long()
-        onehot = (owner[:, None] == self._ar_P[None, :]) & valid[:, None]
-        ordinal = (onehot.cumsum(0, dtype=torch.int32) - 1).gather(1, owner[:, None]).squeeze(1).long()
-        over = valid & (ordinal >= CAP)
-        self.overflow += over.any().int()
-        ok = valid & ~over
-        self._dest = torch.where(ok, owner * CAP + ordinal, torch.full_like(owner, M))
-        send = torch.full((M + 1, 2), -1, dtype=torch.int32, device=self.device)
-        cnt = pl.urec.view(-1, 4)[:, 1]
-        send[self._dest] = torch.stack((ids, cnt), dim=1)
+        send, self._dest, over = bucket_by_owner(pl.uniq, pl.urec.view(-1, 4)[:, 1], pl.meta[0], P, CAP)
+        self.overflow += over.int()
         return send[:M].view(P, CAP, 2).contiguous(), pl.z.clone()
 
     @torch.no_grad()
