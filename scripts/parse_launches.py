@@ -8,8 +8,8 @@ path = sys.argv[1]
 lines = [l for l in open(path) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 names = [(re.sub(r"<.*", "", r["Kernel Name"]).replace("void ", "")[:48], float(r["Metric Value"])) for r in rows]
-idx = [i for i, (n, _) in enumerate(names) if "k_plan_keys" in n]
-a, b = idx[-2], idx[-1]
+idx = [i for i, (n, _) in enumerate(names) if "k_plan_finish" in n]          # last kernel of a plan
+a, b = idx[-2] + 1, idx[-1] + 1                                             # one step: kernels + the next plan
 agg = OrderedDict()
 for n, t in names[a:b]:
     agg.setdefault(n, [0, 0.0])

@@ -71,7 +71,13 @@ def test_plan_is_bit_exact(name):
 
 
 @pytest.mark.parametrize("B,F,R,hot", [(1, 2, 10, 0), (7, 2, 5, 0), (1000, 2, 50, 1), (4096, 3, 100000, 0),
-                                       (5000, 8, 3000, 1), (65536, 2, 165237, 1)])
+                                       (5000, 8, 3000, 1), (65536, 2, 165237, 1),
+                                       (1, 1, 1, 0), (300, 2, 2, 1),                 # one bin / two rows
+                                       (1025, 2, 1024, 0), (2048, 2, 1025, 0),       # digit-width edges
+                                       (65536, 2, 5_000_000, 1),                     # 23 bits: 3 passes
+                                       (50000, 2, 100_000_000, 1),                   # 27 bits: 3 passes
+                                       (65536, 8, 1_000_000, 1),                     # 512 tiles
+                                       (100000, 8, 1_000_000, 1)])                   # tile of 2048 keys
 def test_plan_random_shapes_vs_torch_unique(B, F, R, hot):
     from vae_b200 import _lib as L
     from vae_b200.engine import BatchPlan, make_config

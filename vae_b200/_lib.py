@@ -13,13 +13,16 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libvfm_b200.so")
+# experiment hook: VFMB_VARIANT=name + VFMB_NVCC_EXTRA="-DX=1 ..." builds / loads libvfm_b200_name.so
+_VARIANT = os.environ.get("VFMB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, f"libvfm_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 SOURCES = ["api.cu", "plan.cu", "sampled.cu", "closed.cu", "dp.cu"]
 HEADERS = ["common.cuh", "internal.h", "step_common.cuh", os.path.join(_ROOT, "include", "vfm_b200.h")]
 # -prec-div/-prec-sqrt=false: MUFU-based division and square root (<= 2 ulp) instead of the IEEE
 # slow paths, which made the Adam epilogue instruction-bound; denormals and expf/logf stay precise
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-shared", "-w"]
+              "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-shared", "-w"] + \
+             os.environ.get("VFMB_NVCC_EXTRA", "").split()
 
 MAX_FIELDS = 8
 GAUSSIAN, BERNOULLI = 0, 1
@@ -144,12 +147,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    # one object per translation unit, compiled concurrently (the template instantiations make
+    # each .cu ~20-60 s of ptxas time), then one link step
+    obj_dir = os.path.join(_ROOT, "build", "obj" + ("_" + _VARIANT if _VARIANT else ""))
+    os.makedirs(obj_dir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs = []
+    for s in SOURCES:
+        obj = os.path.join(obj_dir, s.replace(".cu", ".o"))
+        cmd = [nvcc, *cflags, "-c", os.path.join(CSRC, s), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        jobs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    errs = []
+    for obj, p in jobs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            errs.append(out)
+    if errs:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(errs))
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH] + [obj for obj, _ in jobs]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     with open(LIB_PATH + ".sha256", "w") as fh:
         fh.write(_source_digest())
     return LIB_PATH

@@ -7,97 +7,264 @@
 // ascending batch order -- that fixed order is what makes the segmented
 // gradient reduction deterministic.
 //
-// Round-1 implementation: the sort and the two prefix sums use CUB device
-// primitives (library plumbing); keying, head flags, scatter of
-// uniq/inverse/segments, the per-column normalisers and the work-item list are
-// own kernels.
+//
+// The sort is an own tiled LSD radix sort (no library calls on the plan path): with B*F of a few
+// hundred thousand keys the problem is latency-bound, so it is built from few, wide-grid kernels
+// with plain dependencies instead of a chained look-back --
+//   k_sort_hist     per tile: digit histogram (pass 1: + range check and the normalisers Z_f)
+//   k_sort_scan     one CTA per bin: global offset of (bin, tile)
+//   k_sort_scatter  per tile: stable rank of every key among its digit (warp match + per-warp
+//                   counters), scatter
+// (per-key global atomics for the next pass's histogram were tried and cost 20 us: a Zipf head
+// row sends thousands of atomics to one address)
+// digits of <= 10 bits: 2 passes up to 2^20 rows, 3 passes up to 2^30.  Then
+//   k_plan_heads / k_plan_scatter  unique ranks (head-flag scan), uniq / inverse / segments
+//   k_plan_finish   flat records the step kernels read
 #include "common.cuh"
 #include "internal.h"
 
-#include <mutex>
-#include <unordered_map>
-
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-
 namespace vfmb {
 
-// ---- P1: keys + per-column normaliser Z_f = sum_n 1 / cnt_train(x[n,f]) --------------------
-// (equal to sum over uniq(x[:,f]) of cnt_f(u)/cnt_train(u), vfm-torch.py:305-306)
-__global__ void __launch_bounds__(256)
-k_plan_keys(const int64_t* __restrict__ x, const float* __restrict__ train_counts, int N, int F, int R,
-            int32_t* __restrict__ keys, int32_t* __restrict__ vals, int32_t* __restrict__ meta,
-            double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ z) {
-    __shared__ double s_part[kMaxFields][8];
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kMaxBins = 1024;
+constexpr int kMaxTiles = 512;      // tiles per pass (the tile grows with B*F beyond 512K keys)
+
+// ---- S1: digit histogram per tile; the first pass also range-checks the ids and accumulates
+// the per-column normalisers Z_f = sum_n 1 / cnt_train(x[n,f])
+// (Z_f equals the sum over uniq(x[:,f]) of cnt_f(u)/cnt_train(u), vfm-torch.py:305-306)
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads)
+k_sort_hist(const int64_t* __restrict__ x, const int32_t* __restrict__ kin,
+            const float* __restrict__ train_counts, int N, int F, int R,
+            int tile, int n_tiles, int shift, int bins, int32_t* __restrict__ hist, int32_t* __restrict__ gtot,
+            int32_t* __restrict__ meta, double* __restrict__ partials, float* __restrict__ z) {
+    __shared__ int s_hist[kMaxBins];
+    __shared__ double s_part[kMaxFields][kSortWarps];
     __shared__ bool s_last;
+    const int tid = threadIdx.x, t = blockIdx.x;
+    for (int b = tid; b < bins; b += kSortThreads) s_hist[b] = 0;
+    __syncthreads();
     double acc[kMaxFields];
 #pragma unroll
     for (int f = 0; f < kMaxFields; ++f) acc[f] = 0.0;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < N; o += gridDim.x * blockDim.x) {
-        int64_t id = x[o];
-        bool ok = id >= 0 && id < R;
-        if (!ok) { atomicOr(&meta[2], 1); id = 0; }
-        keys[o] = (int32_t)id;
-        vals[o] = o;
-        float t = 1.0f / __ldg(train_counts + id);
-        int f = o % F;
+    const int lo = t * tile, hi = min(N, lo + tile);
+    if (FIRST) {
+#pragma unroll 4
+        for (int o = lo + tid; o < hi; o += kSortThreads) {
+            int64_t id = x[o];
+            if (id < 0 || id >= R) { atomicOr(&meta[2], 1); id = 0; }
+            atomicAdd(&s_hist[(int)id & (bins - 1)], 1);
+            const float tc = 1.0f / __ldg(train_counts + id);
+            const int f = o % F;
 #pragma unroll
-        for (int g = 0; g < kMaxFields; ++g) if (g == f) acc[g] += (double)t;
-    }
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int f = 0; f < F; ++f) {
-        double s = warp_sum(acc[f]);
-        if (lane == 0) s_part[f][warp] = s;
+            for (int g = 0; g < kMaxFields; ++g) if (g == f) acc[g] += (double)tc;
+        }
+    } else {
+#pragma unroll 4
+        for (int o = lo + tid; o < hi; o += kSortThreads) atomicAdd(&s_hist[(kin[o] >> shift) & (bins - 1)], 1);
     }
     __syncthreads();
-    if (threadIdx.x < F) {
-        double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += s_part[threadIdx.x][w];
-        partials[(size_t)blockIdx.x * kMaxFields + threadIdx.x] = s;
+    for (int b = tid; b < bins; b += kSortThreads) {
+        const int c = s_hist[b];
+        hist[(size_t)b * n_tiles + t] = c;
+        if (c) atomicAdd(&gtot[b], c);
+    }
+    if (!FIRST) return;
+    // deterministic Z_f: block partials, the block that arrives last adds them in block order
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int f = 0; f < F; ++f) {
+        double sfw = warp_sum(acc[f]);
+        if (lane == 0) s_part[f][warp] = sfw;
+    }
+    __syncthreads();
+    if (tid < F) {
+        double sf = 0.0;
+        for (int w = 0; w < kSortWarps; ++w) sf += s_part[tid][w];
+        partials[(size_t)t * kMaxFields + tid] = sf;
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1) == (int)gridDim.x - 1);
+    if (tid == 0) s_last = (atomicAdd(&meta[4], 1) == (int)gridDim.x - 1);
     __syncthreads();
     if (s_last) {
         __threadfence();
-        // warp f reduces column f: lane l adds blocks l, l+32, ... then a fixed shuffle tree
-        if (warp < F) {
-            double s = 0.0;
-            for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * kMaxFields + warp);
-            s = warp_sum(s);
-            if (lane == 0) z[warp] = (float)s;
+        if (warp < F) {      // warp f reduces column f: lane l adds blocks l, l+32, ... then a fixed tree
+            double sf = 0.0;
+            for (unsigned b = lane; b < gridDim.x; b += 32) sf += __ldcg(partials + (size_t)b * kMaxFields + warp);
+            sf = warp_sum(sf);
+            if (lane == 0) z[warp] = (float)sf;
         }
-        if (threadIdx.x == 0) *counter = 0;
     }
 }
 
-struct HeadFlag {
-    const int32_t* keys;
-    __host__ __device__ int32_t operator()(int i) const {
-        return (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+// ---- S2: hist[bin][tile] -> global offset of the first key of (bin, tile) ----------------------
+__global__ void __launch_bounds__(128)
+k_sort_scan(int32_t* __restrict__ hist, const int32_t* __restrict__ gtot, int n_tiles) {
+    __shared__ int s_w[4];
+    __shared__ int s_carry;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int below = 0;                                         // keys in bins < b
+    for (int i = tid; i < b; i += 128) below += gtot[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0) s_w[warp] = below;
+    __syncthreads();
+    if (tid == 0) s_carry = s_w[0] + s_w[1] + s_w[2] + s_w[3];
+    __syncthreads();
+    int32_t* row = hist + (size_t)b * n_tiles;
+    for (int t0 = 0; t0 < n_tiles; t0 += 128) {
+        const int t = t0 + tid;
+        const int c = t < n_tiles ? row[t] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        __syncthreads();                                   // s_w / s_carry of the previous chunk are consumed
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_w[w];
+        const int carry = s_carry;
+        if (t < n_tiles) row[t] = carry + woff + incl - c;
+        __syncthreads();
+        if (tid == 127) s_carry = carry + woff + incl;
     }
-};
+}
 
-// ---- P3: scatter uniq / seg_off / inverse from the sorted pairs and their head-flag scan ---
-__global__ void __launch_bounds__(256)
+// ---- S3: stable scatter of one pass ------------------------------------------------------------
+// A tile is walked in chunks of 256 keys (the keys of 4 chunks are fetched up front, so the
+// memory latency is paid once per 1024 keys).  Inside a chunk a key's rank among equal digits is
+// (keys of earlier warps) + (earlier lanes of its warp, by match_any); s_base[digit] carries the
+// offset of the digit's next free slot for this tile.  FIRST reads the int64 ids.
+constexpr int kPre = 4;
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads)
+k_sort_scatter(const int64_t* __restrict__ x, int R, const int32_t* __restrict__ kin,
+               const int32_t* __restrict__ vin, int32_t* __restrict__ kout, int32_t* __restrict__ vout,
+               int N, int tile_shift, int n_tiles, int shift, int bins, const int32_t* __restrict__ base) {
+    __shared__ int s_base[kMaxBins];
+    __shared__ int s_cnt[kSortWarps][kMaxBins];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = blockIdx.x;
+    for (int b = tid; b < bins; b += kSortThreads) {
+        s_base[b] = base[(size_t)b * n_tiles + t];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) s_cnt[w][b] = 0;
+    }
+    __syncthreads();
+    const int lo = t << tile_shift, hi = min(N, lo + (1 << tile_shift));
+    for (int g0 = lo; g0 < hi; g0 += kPre * kSortThreads) {
+        int keys[kPre], vals[kPre];
+#pragma unroll
+        for (int c = 0; c < kPre; ++c) {
+            const int i = g0 + c * kSortThreads + tid;
+            keys[c] = 0; vals[c] = 0;
+            if (i < hi) {
+                if (FIRST) { const int64_t id = x[i]; keys[c] = (id < 0 || id >= R) ? 0 : (int)id; vals[c] = i; }
+                else { keys[c] = kin[i]; vals[c] = vin[i]; }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kPre; ++c) {
+            if (g0 + c * kSortThreads >= hi) break;            // block-uniform
+            const bool valid = g0 + c * kSortThreads + tid < hi;
+            const int key = keys[c];
+            const int digit = (key >> shift) & (bins - 1);
+            const unsigned dm = valid ? (unsigned)digit : (0x40000000u | (unsigned)lane);
+            const unsigned peers = __match_any_sync(0xffffffffu, dm);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int cnt = __popc(peers);
+            const bool leader = valid && rank == 0;
+            if (leader) s_cnt[warp][digit] = cnt;
+            __syncthreads();
+            int pos = 0;
+            if (valid) {
+                int off = 0;
+                for (int w = 0; w < warp; ++w) off += s_cnt[w][digit];
+                pos = s_base[digit] + off + rank;
+            }
+            __syncthreads();
+            if (leader) { atomicAdd(&s_base[digit], cnt); s_cnt[warp][digit] = 0; }
+            if (valid) { kout[pos] = key; vout[pos] = vals[c]; }
+        }
+    }
+}
+
+// ---- P2: number of segment heads per tile of the sorted keys -----------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+k_plan_heads(const int32_t* __restrict__ keys_s, int N, int tile_shift, int32_t* __restrict__ tile_heads) {
+    __shared__ int s_w[kSortWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = blockIdx.x;
+    const int lo = t << tile_shift, hi = min(N, lo + (1 << tile_shift));
+    int c = 0;
+    for (int i = lo + tid; i < hi; i += kSortThreads) c += (i == 0 || keys_s[i] != keys_s[i - 1]) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_w[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < kSortWarps; ++w) tot += s_w[w];
+        tile_heads[t] = tot;
+    }
+}
+
+// ---- P3: unique ranks (scan of the head flags) and scatter of uniq / seg_off / inverse --------
+__global__ void __launch_bounds__(kSortThreads)
 k_plan_scatter(const int32_t* __restrict__ keys_s, const int32_t* __restrict__ vals_s,
-               const int32_t* __restrict__ rank_incl, int N, int32_t* __restrict__ uniq,
+               const int32_t* __restrict__ tile_heads, int N, int tile_shift, int32_t* __restrict__ uniq,
                int32_t* __restrict__ seg_off, int32_t* __restrict__ inverse, int32_t* __restrict__ occ,
                int32_t* __restrict__ pos_of, int32_t* __restrict__ pos_rank, int32_t* __restrict__ meta) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        int r = rank_incl[i] - 1;
-        int k = keys_s[i];
-        int o = vals_s[i];
-        bool head = (i == 0) || (keys_s[i - 1] != k);
-        if (head) { uniq[r] = k; seg_off[r] = i; }
-        inverse[o] = r;
-        occ[i] = o;
-        pos_of[o] = i;
-        pos_rank[i] = r;
-        if (i == N - 1) { meta[0] = r + 1; seg_off[r + 1] = N; }
+    __shared__ int s_w[kSortWarps];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = blockIdx.x;
+    int below = 0;                                         // heads in the tiles before this one
+    for (int i = tid; i < t; i += kSortThreads) below += tile_heads[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0) s_w[warp] = below;
+    __syncthreads();
+    if (tid == 0) { int tot = 0; for (int w = 0; w < kSortWarps; ++w) tot += s_w[w]; s_carry = tot; }
+    __syncthreads();
+    const int lo = t << tile_shift, hi = min(N, lo + (1 << tile_shift));
+    for (int g0 = lo; g0 < hi; g0 += kPre * kSortThreads) {
+        int ks[kPre], os[kPre], hs[kPre];
+#pragma unroll
+        for (int c = 0; c < kPre; ++c) {
+            const int i = g0 + c * kSortThreads + tid;
+            ks[c] = 0; os[c] = 0; hs[c] = 0;
+            if (i < hi) {
+                ks[c] = keys_s[i];
+                os[c] = vals_s[i];
+                hs[c] = (i == 0 || keys_s[i - 1] != ks[c]) ? 1 : 0;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kPre; ++c) {
+            if (g0 + c * kSortThreads >= hi) break;            // block-uniform
+            const int i = g0 + c * kSortThreads + tid;
+            const bool valid = i < hi;
+            const int k = ks[c], o = os[c], head = hs[c];
+            int incl = head;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, sft); if (lane >= sft) incl += v; }
+            __syncthreads();                               // s_w / s_carry of the previous chunk are consumed
+            if (lane == 31) s_w[warp] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < warp; ++w) woff += s_w[w];
+            const int carry = s_carry;
+            const int r = carry + woff + incl - 1;         // unique rank of position i
+            if (valid) {
+                if (head) { uniq[r] = k; seg_off[r] = i; }
+                inverse[o] = r;
+                occ[i] = o;
+                pos_of[o] = i;
+                pos_rank[i] = r;
+                if (i == N - 1) { meta[0] = r + 1; seg_off[r + 1] = N; }
+            }
+            __syncthreads();
+            if (tid == kSortThreads - 1) s_carry = carry + woff + incl;
+        }
     }
 }
 
@@ -142,46 +309,50 @@ static inline int bits_for(int R) {
     return b;
 }
 
+// geometry of the sort for N keys of `bits` bits
+struct SortGeom {
+    int npass, w[3], shift[3], bins[3];
+    int tile_shift, n_tiles;
+};
+static SortGeom sort_geom(int64_t N, int R) {
+    SortGeom g{};
+    const int bits = bits_for(R);
+    g.npass = (bits + 9) / 10;
+    int done = 0;
+    for (int p = 0; p < g.npass; ++p) {
+        const int w = (bits - done + (g.npass - p) - 1) / (g.npass - p);
+        g.w[p] = w; g.shift[p] = done; g.bins[p] = 1 << w;
+        done += w;
+    }
+    g.tile_shift = 10;
+    while (((N + (1LL << g.tile_shift) - 1) >> g.tile_shift) > kMaxTiles) ++g.tile_shift;
+    g.n_tiles = (int)((N + (1LL << g.tile_shift) - 1) >> g.tile_shift);
+    return g;
+}
+
 struct PlanWs {
-    int32_t *keys, *vals, *keys_s, *vals_s, *rank;
+    int32_t *kA, *vA, *kB, *vB;
+    int32_t* counters;         // [3][kMaxBins] bin totals of the passes (accumulated: zeroed per build)
+    int32_t* hist;             // [bins][n_tiles] histogram of the current pass
+    int32_t* tile_heads;
     double* partials;
-    int32_t* counter;
-    void* cub;
-    size_t cub_bytes;
     size_t total;
 };
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-static PlanWs carve(void* base, int N, int u_cap) {
+static PlanWs carve(void* base, int64_t N, const SortGeom& g) {
     PlanWs w{};
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return (char*)base + o; };
-    w.keys = (int32_t*)take((size_t)N * 4);
-    w.vals = (int32_t*)take((size_t)N * 4);
-    w.keys_s = (int32_t*)take((size_t)N * 4);
-    w.vals_s = (int32_t*)take((size_t)N * 4);
-    w.rank = (int32_t*)take((size_t)N * 4);
-    w.partials = (double*)take((size_t)kPlanGrid * kMaxFields * 8);
-    w.counter = (int32_t*)take(256);
-    // CUB temp-storage sizes: host-side queries, cached per N (they cost microseconds per call)
-    static std::mutex mu;
-    static std::unordered_map<int, size_t> cache;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        auto it0 = cache.find(N);
-        if (it0 == cache.end()) {
-            size_t sort_b = 0, scan_b = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (int32_t*)nullptr, (int32_t*)nullptr,
-                                            (int32_t*)nullptr, (int32_t*)nullptr, N, 0, 31);
-            cub::TransformInputIterator<int32_t, HeadFlag, cub::CountingInputIterator<int>> it(
-                cub::CountingInputIterator<int>(0), HeadFlag{nullptr});
-            cub::DeviceScan::InclusiveSum(nullptr, scan_b, it, (int32_t*)nullptr, N);
-            it0 = cache.emplace(N, sort_b > scan_b ? sort_b : scan_b).first;
-        }
-        w.cub_bytes = it0->second;
-    }
-    w.cub = take(w.cub_bytes);
+    w.kA = (int32_t*)take((size_t)N * 4);
+    w.vA = (int32_t*)take((size_t)N * 4);
+    w.kB = (int32_t*)take((size_t)N * 4);
+    w.vB = (int32_t*)take((size_t)N * 4);
+    w.counters = (int32_t*)take(3 * (size_t)kMaxBins * 4);
+    w.hist = (int32_t*)take((size_t)kMaxBins * g.n_tiles * 4);
+    w.tile_heads = (int32_t*)take((size_t)g.n_tiles * 4);
+    w.partials = (double*)take((size_t)kMaxTiles * kMaxFields * 8);
     w.total = off;
     return w;
 }
@@ -198,7 +369,7 @@ extern "C" int vfmb_plan_capacity(int32_t B, int32_t F, int32_t R, vfmb_plan_cap
     out->u_cap = N < R ? N : R;
     out->n_tiles = (N + kTile - 1) / kTile;
     out->tile = kTile;
-    PlanWs w = carve(nullptr, (int)N, (int)out->u_cap);
+    PlanWs w = carve(nullptr, N, sort_geom(N, R));
     out->workspace_bytes = (int64_t)w.total;
     return 0;
 }
@@ -215,28 +386,41 @@ extern "C" int vfmb_plan_build(const vfmb_config* cfg, const int64_t* x, const f
     if (workspace_bytes < (size_t)cap.workspace_bytes)
         return set_error(VFMB_ESPACE, "vfmb_plan_build: workspace too small");
     const int N = cfg->B * cfg->F;
-    const int u_cap = (int)cap.u_cap;
-    PlanWs w = carve(workspace, N, u_cap);
+    const SortGeom g = sort_geom(N, cfg->R);
+    PlanWs w = carve(workspace, N, g);
+    int32_t* gtot[3] = {w.counters, w.counters + kMaxBins, w.counters + 2 * kMaxBins};
 
     CUDA_TRY(cudaMemsetAsync(plan->meta, 0, 8 * sizeof(int32_t), stream));
-    CUDA_TRY(cudaMemsetAsync(w.counter, 0, 4, stream));
-    int grid = (N + 255) / 256;
-    if (grid > kPlanGrid) grid = kPlanGrid;
-    k_plan_keys<<<grid, 256, 0, stream>>>(x, train_counts, N, cfg->F, cfg->R, w.keys, w.vals, plan->meta,
-                                          w.partials, w.counter, plan->z);
+    CUDA_TRY(cudaMemsetAsync(w.counters, 0, 3 * kMaxBins * sizeof(int32_t), stream));
+    const int32_t* kin = nullptr; const int32_t* vin = nullptr;
+    int32_t* kout = w.kA; int32_t* vout = w.vA;
+    for (int p = 0; p < g.npass; ++p) {
+        if (p == 0)
+            k_sort_hist<true><<<g.n_tiles, kSortThreads, 0, stream>>>(x, nullptr, train_counts, N, cfg->F, cfg->R,
+                1 << g.tile_shift, g.n_tiles, 0, g.bins[0], w.hist, gtot[0], plan->meta, w.partials, plan->z);
+        else
+            k_sort_hist<false><<<g.n_tiles, kSortThreads, 0, stream>>>(nullptr, kin, nullptr, N, cfg->F, cfg->R,
+                1 << g.tile_shift, g.n_tiles, g.shift[p], g.bins[p], w.hist, gtot[p], plan->meta, nullptr, nullptr);
+        k_sort_scan<<<g.bins[p], 128, 0, stream>>>(w.hist, gtot[p], g.n_tiles);
+        if (p == 0)
+            k_sort_scatter<true><<<g.n_tiles, kSortThreads, 0, stream>>>(x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
+                                                                         g.n_tiles, g.shift[p], g.bins[p], w.hist);
+        else
+            k_sort_scatter<false><<<g.n_tiles, kSortThreads, 0, stream>>>(x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
+                                                                          g.n_tiles, g.shift[p], g.bins[p], w.hist);
+        CUDA_TRY(cudaGetLastError());
+        kin = kout; vin = vout;
+        kout = (kout == w.kA) ? w.kB : w.kA;
+        vout = (vout == w.vA) ? w.vB : w.vA;
+    }
+    const int32_t* keys_s = kin; const int32_t* vals_s = vin;
+    k_plan_heads<<<g.n_tiles, kSortThreads, 0, stream>>>(keys_s, N, g.tile_shift, w.tile_heads);
+    k_plan_scatter<<<g.n_tiles, kSortThreads, 0, stream>>>(keys_s, vals_s, w.tile_heads, N, g.tile_shift, plan->uniq,
+                                                           plan->seg_off, plan->inverse, plan->occ, plan->pos_of,
+                                                           plan->pos_rank, plan->meta);
     CUDA_TRY(cudaGetLastError());
-    size_t cb = w.cub_bytes;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub, cb, w.keys, w.keys_s, w.vals, w.vals_s, N, 0,
-                                             bits_for(cfg->R), stream));
-    cub::TransformInputIterator<int32_t, HeadFlag, cub::CountingInputIterator<int>> heads(
-        cub::CountingInputIterator<int>(0), HeadFlag{w.keys_s});
-    cb = w.cub_bytes;
-    CUDA_TRY(cub::DeviceScan::InclusiveSum(w.cub, cb, heads, w.rank, N, stream));
     int grid2 = (N + 255) / 256;
     if (grid2 > 4 * kPlanGrid) grid2 = 4 * kPlanGrid;
-    k_plan_scatter<<<grid2, 256, 0, stream>>>(w.keys_s, w.vals_s, w.rank, N, plan->uniq, plan->seg_off,
-                                              plan->inverse, plan->occ, plan->pos_of, plan->pos_rank, plan->meta);
-    CUDA_TRY(cudaGetLastError());
     ClassBounds cbd{};
     cbd.n = cfg->n_classes;
     for (int i = 0; i < kMaxFields; ++i) cbd.bound[i] = cfg->class_bound[i];

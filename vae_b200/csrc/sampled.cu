@@ -1,16 +1,19 @@
 // Sampled-ELBO VFM step (vfm-torch.py:189-324 forward, :359 loss, :368-370 backward + Adam).
 //
-// Four kernels per training step, all HBM/L2-bound (no dense contraction exists on this path):
-//   k_stage  one lane group per UNIQUE row: gather [mean|raw scale], draw eps (Philox or
-//            injected), write the sampled row v = mu + eps*|rho| and bias w to an L2-resident
-//            scratch, accumulate the count-rescaled KL.          (vfm-torch.py:207-241, 290-317)
-//   k_score  one lane group per SAMPLE: FM interaction of the sampled rows, likelihood,
-//            residual dloss/dpred.                                (vfm-torch.py:244-270, 359)
-//   k_rows   one lane group per (unique row, <=64-occurrence chunk): ordered segmented sum of
-//            residual * partner row, chain rule to (mu, rho) + KL gradient, Adam on the row.
-//            Deterministic: fixed summation order, no floating-point atomics. (:368-370)
-//   k_final  scalar parameters (alpha, global bias) and the step counter.
+// Five launches per fused training step, all HBM/L2-bound (no dense contraction on this path):
+//   k_stage    one lane group per UNIQUE row: gather [mean|raw scale], draw eps (Philox or
+//              injected), write the sampled row v = mu + eps*|rho| and bias w to an L2-resident
+//              scratch (+ the count-rescaled KL when not fused).   (vfm-torch.py:207-241, 290-317)
+//   k_score    one lane group per SAMPLE: FM interaction of the sampled rows, likelihood,
+//              residual dloss/dpred.                                (vfm-torch.py:244-270, 359)
+//   k_gather   ordered segmented sum of residual * partner row over the sorted occurrence list,
+//              tiled by position; k_combine finishes the rows cut by many tile boundaries.
+//   k_adam_rows  per unique row: chain rule to (mu, rho) + KL gradient + Adam; the last block
+//              also updates the scalar parameters (alpha, global bias) and the step counter.
+//              Deterministic: fixed summation order, no floating-point atomics.    (:368-370)
 #include "step_common.cuh"
+
+#include <cstdlib>
 
 namespace vfmb {
 
@@ -44,7 +47,9 @@ __device__ __forceinline__ float global_eps(const float* __restrict__ eps_global
 }
 
 // ------------------------------------------------------------------------------- k_stage
-template <int VEC, int LPR, int NV, int LINK>
+// LEAN = 1 (fused training step): no KL sum and no copy of the noise -- k_adam_rows, which holds
+// the row anyway and has idle issue slots, recomputes both (same Philox counters => same bits).
+template <int VEC, int LPR, int NV, int LINK, int LEAN>
 __global__ void __launch_bounds__(256)
 k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ entity,
         const float* __restrict__ train_counts, const int32_t* __restrict__ urec,
@@ -80,7 +85,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
             if (!eps_bias) ebs[ul] = eb;
             const float tau = link_fn<LINK>(ab.y);
             ws[ul] = fmaf(eb, tau, ab.x);
-            klb = kl_std_normal(ab.x, tau);
+            if (!LEAN) klb = kl_std_normal(ab.x, tau);
             const int cls = class_of(c, gid_l);
             float csz = 0.f, zc = 1.f;
 #pragma unroll
@@ -104,7 +109,13 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                     if (k < d) {
                         const Vec<VEC> mu = ld_vec<VEC>(erow + k), rho = ld_vec<VEC>(erow + d + k);
                         Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step), out;
-                        if (!eps_entity) st_vec<VEC>(es + (size_t)u * d + k, e);
+                        if (!LEAN && !eps_entity) st_vec<VEC>(es + (size_t)u * d + k, e);
+                        if (LEAN) {
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) out.v[j] = fmaf(e.v[j], link_fn<LINK>(rho.v[j]), mu.v[j]);
+                            st_vec<VEC>(vs + (size_t)u * d + k, out);
+                            continue;
+                        }
                         // sum_k KL(N(mu,sig)||N(0,1)) = 0.5 (sum sig^2 + mu^2 - 1) - 0.5 log prod sig^2:
                         // one logarithm per lane instead of one per element
                         float quad = 0.f, prodv = 1.f;
@@ -126,12 +137,13 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                         st_vec<VEC>(vs + (size_t)u * d + k, out);
                     }
                 }
-                kl = group_sum<LPR>(kl, gmask);
+                if (!LEAN) kl = group_sum<LPR>(kl, gmask);
             }
-            hand_back<LPR>(klrow, kl, it, lane);
+            if (!LEAN) hand_back<LPR>(klrow, kl, it, lane);
         }
         if (valid) facc = fmaf(cqv, klrow + klb, facc);
     }
+    if (LEAN) return;
     double acc[1] = {(double)facc};
     if (block_partials<1>(acc, partials, counter)) {
         double tot[1];
@@ -152,7 +164,8 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         const float* __restrict__ y, const float* __restrict__ eps_global,
         const int32_t* __restrict__ adam_step, float* __restrict__ pred, float* __restrict__ mean,
         float* __restrict__ resid, float* __restrict__ rsorted, float* __restrict__ msg,
-        double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
+        double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
+        int defer_kl) {
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
     const int d = c.d, F = c.F, B = c.B;
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
@@ -278,13 +291,17 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         final_sums<3>(partials, tot);
         if (threadIdx.x == 0) {
             double nll = tot[0], sr = tot[1], sq = tot[2];
-            float kl0 = kl_std_normal(mu0, sig0);
-            float kl = kl0 + stats[VFMB_ST_KL_ROWS];
             stats[VFMB_ST_NLL_MEAN] = (float)(nll / (double)B);
             stats[VFMB_ST_SUM_RESID] = (float)sr;
             stats[VFMB_ST_SUM_SQERR] = (float)sq;
-            stats[VFMB_ST_KL] = kl;
-            stats[VFMB_ST_LOSS] = (float)((double)c.n_train * nll / (double)B + (double)kl);
+            if (defer_kl) {                 // fused step: k_adam_rows adds the KL (data term only here)
+                stats[VFMB_ST_LOSS] = (float)((double)c.n_train * nll / (double)B);
+            } else {
+                float kl0 = kl_std_normal(mu0, sig0);
+                float kl = kl0 + stats[VFMB_ST_KL_ROWS];
+                stats[VFMB_ST_KL] = kl;
+                stats[VFMB_ST_LOSS] = (float)((double)c.n_train * nll / (double)B + (double)kl);
+            }
             stats[VFMB_ST_W0] = w0;
             *counter = 0;
         }
@@ -411,52 +428,238 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
 }
 
 // ------------------------------------------------------------------------------- k_adam_rows
-template <int VEC, int LPR, int NV, int LINK, int MODE>
-__global__ void __launch_bounds__(256)
-k_adam_rows(int d, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
+// Backward, phase B (the HBM-bound kernel of the step): per unique row, chain rule from
+// (g_v, g_w) to (mean, raw scale) + KL gradient, then Adam on the row -- parameters and both
+// moments of every touched row are read and written exactly once.
+//
+// FLAVOR 0  plain: row gradients are final in grow/gws (k_combine ran), nothing else.
+// FLAVOR 1  + rows cut by a tile boundary (<= kHotPartials tiles) add their tile partials here,
+//             in tile order (the hot rows were finished by k_combine<HOT_ONLY>);
+//           + the block that finishes last updates the scalar parameters and the step counter
+//             (what k_final did as a separate launch).
+// FLAVOR 2  + the count-rescaled KL of the rows (the row is in registers, the kernel is DRAM-bound
+//             with idle issue slots) and, without injected noise, the Philox draws recomputed
+//             instead of read back -- k_stage<LEAN> wrote neither.
+struct FinalArgs {
+    float* scalars; float* sm; float* sv; float* stats; const float* eps_global;
+    float* grad_scalars; double* partials; int32_t* counter; const float* gslot;
+    int likelihood;
+};
+
+template <int LINK, int MODE>
+__device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& fa, const AdamDev& h,
+                                              int32_t* __restrict__ adam_step, float kl_scale,
+                                              bool with_kl, double kl_rows, int U) {
+    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    float* scalars = fa.scalars; float* stats = fa.stats;
+    float alpha = scalars[VFMB_S_ALPHA], mu0 = scalars[VFMB_S_GB_MEAN], rho0 = scalars[VFMB_S_GB_SCALE];
+    const float sig0 = link_fn<LINK>(rho0), ap = link_fn<LINK>(alpha);
+    const float e0 = global_eps(fa.eps_global, c, step);
+    const double sr = (double)stats[VFMB_ST_SUM_RESID], sq = (double)stats[VFMB_ST_SUM_SQERR];
+    if (with_kl) {                                      // loss terms of the pre-update parameters
+        const float kl = kl_std_normal(mu0, sig0) + (float)kl_rows;
+        stats[VFMB_ST_KL_ROWS] = (float)kl_rows;
+        stats[VFMB_ST_KL] = kl;
+        stats[VFMB_ST_LOSS] = (float)((double)stats[VFMB_ST_LOSS] + (double)kl);
+        stats[VFMB_ST_U] = (float)U;
+    }
+    float g_mu0 = (float)(sr + (double)(kl_scale * mu0));
+    float g_rho0 = link_grad<LINK>(rho0) * (float)((double)e0 * sr + (double)(kl_scale * (sig0 - 1.f / sig0)));
+    float g_alpha = 0.f;
+    if (fa.likelihood == VFMB_GAUSSIAN) {
+        double sc = (double)c.n_train / ((double)c.S * (double)c.B);
+        g_alpha = link_grad<LINK>(alpha) * (float)(sc * (0.5 * sq - 0.5 * (double)c.S * (double)c.B / (double)ap));
+    }
+    if (MODE == VFMB_ADAM_TOUCHED) {
+        float ss, b2;
+        adam_coeffs(h, (int)step + 1, &ss, &b2);
+        adam_elem(mu0, fa.sm[VFMB_S_GB_MEAN], fa.sv[VFMB_S_GB_MEAN], g_mu0, h, ss, b2);
+        adam_elem(rho0, fa.sm[VFMB_S_GB_SCALE], fa.sv[VFMB_S_GB_SCALE], g_rho0, h, ss, b2);
+        scalars[VFMB_S_GB_MEAN] = mu0; scalars[VFMB_S_GB_SCALE] = rho0;
+        if (fa.likelihood == VFMB_GAUSSIAN) {  // Bernoulli: alpha has no gradient, Adam skips it (N10)
+            adam_elem(alpha, fa.sm[VFMB_S_ALPHA], fa.sv[VFMB_S_ALPHA], g_alpha, h, ss, b2);
+            scalars[VFMB_S_ALPHA] = alpha;
+        }
+        adam_step[0] = (int32_t)step + 1;
+    } else if (fa.grad_scalars) {
+        fa.grad_scalars[VFMB_S_ALPHA] = g_alpha;
+        fa.grad_scalars[VFMB_S_GB_MEAN] = g_mu0;
+        fa.grad_scalars[VFMB_S_GB_SCALE] = g_rho0;
+    }
+}
+
+#ifndef VFMB_ADAM_MINB
+#define VFMB_ADAM_MINB 3          // resident blocks/SM of the fused flavours (80 registers)
+#endif
+template <int VEC, int LPR, int NV, int LINK, int MODE, int FLAVOR>
+__global__ void __launch_bounds__(256, NV > 1 ? 2 : (FLAVOR == 0 ? 4 : VFMB_ADAM_MINB))
+k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
             float* __restrict__ entity, float* __restrict__ entity_m, float* __restrict__ entity_v,
             const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
             const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
             const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
-            AdamDev h, const int32_t* __restrict__ adam_step, float kl_scale,
-            float* __restrict__ grad_bias, float* __restrict__ grad_entity) {
+            AdamDev h, int32_t* __restrict__ adam_step, float kl_scale,
+            float* __restrict__ grad_bias, float* __restrict__ grad_entity, FinalArgs fa) {
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
+    constexpr bool CUT = FLAVOR >= 1, KLF = FLAVOR == 2;
     const int U = meta[0];
+    const int d = c.d, dp = c.d + 4;
+    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
+    const unsigned gmask = group_mask<LPR>();
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * (blockDim.x >> 5);
-    __shared__ float s_coef[2];
-    if (MODE == VFMB_ADAM_TOUCHED) {                      // fp64 pow once per block, not per thread
-        if (threadIdx.x == 0) adam_coeffs(h, adam_step[0] + 1, &s_coef[0], &s_coef[1]);
-        __syncthreads();
-    }
-    const float step_size = (MODE == VFMB_ADAM_TOUCHED) ? s_coef[0] : 0.f;
-    const float inv_bc2 = (MODE == VFMB_ADAM_TOUCHED) ? s_coef[1] : 1.f;
+    // bias corrections: fp64 pow per thread (~100 cycles per warp on the FP64 pipe) -- cheaper than
+    // a block barrier in front of the first loads
+    float step_size = 0.f, inv_bc2 = 1.f;
+    if (MODE == VFMB_ADAM_TOUCHED) adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
+    float facc = 0.f;                                     // sum_u c_u * KL_u over this thread's rows
 
+#ifdef VFMB_X_BALANCED
+    // contiguous, equally sized row range per warp (all warps finish together)
+    const int per_warp = ((U + nwarps - 1) / nwarps + GPW - 1) / GPW * GPW;
+    const int w_lo = gwarp * per_warp, w_hi = min(U, w_lo + per_warp);
+    for (int base = w_lo; base < w_hi; base += CH) {
+#else
     for (int base = gwarp * CH; base < U; base += nwarps * CH) {
-        // ---- lane-parallel: record, prefetch of the row's parameter / moment lines, bias update
+#endif
+        // ---- lane-parallel: record, prefetch of the row's parameter / moment lines
         const int ul = base + lane;
+#ifdef VFMB_X_BALANCED
+        const bool valid = lane < CH && ul < w_hi;
+#else
         const bool valid = lane < CH && ul < U;
-        int rowid_l = 0;
-        float cfac_l = 0.f;
+#endif
+        int rowid_l = 0, tA_l = 0, P_l = 0;
+        float cfac_l = 0.f, cq_l = 0.f, gw_l = 0.f, eb_l = 0.f;
+        float2 ab = make_float2(0.f, 1.f), bm = make_float2(0.f, 0.f), bv = make_float2(0.f, 0.f);
         if (valid) {
-            rowid_l = __ldg(urec + 4 * (size_t)ul);
+            const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
+            rowid_l = rec.x;
             const size_t eoff = (size_t)rowid_l * 2 * d;
+#ifndef VFMB_X_NOPREFETCH
             prefetch_row(entity + eoff, 8 * d);
             if (MODE == VFMB_ADAM_TOUCHED) {
                 prefetch_row(entity_m + eoff, 8 * d);
                 prefetch_row(entity_v + eoff, 8 * d);
             }
-            cfac_l = kl_scale * __ldg(cq + ul);
+#endif
+            cq_l = __ldg(cq + ul);
+            cfac_l = kl_scale * cq_l;
+            gw_l = __ldg(gws + ul);
+            // bias row: loaded here so that its DRAM latency overlaps the wide work below
             const size_t boff = (size_t)rowid_l * 2;
-            float2 ab = *reinterpret_cast<const float2*>(bias + boff);
-            const float gw = __ldg(gws + ul), eb = __ldg(eps_bias + ul);
-            const float tau = link_fn<LINK>(ab.y);
-            const float ga = fmaf(cfac_l, ab.x, gw);
-            const float gb = link_grad<LINK>(ab.y) * fmaf(gw, eb, cfac_l * (tau - fast_rcp(tau)));
+            ab = *reinterpret_cast<const float2*>(bias + boff);
+            eb_l = __ldg(eps_bias + ul);
             if (MODE == VFMB_ADAM_TOUCHED) {
-                float2 bm = *reinterpret_cast<const float2*>(bias_m + boff);
-                float2 bv = *reinterpret_cast<const float2*>(bias_v + boff);
+                bm = *reinterpret_cast<const float2*>(bias_m + boff);
+                bv = *reinterpret_cast<const float2*>(bias_v + boff);
+            }
+            if (CUT) {                                     // tiles the row's segment spans beyond its first
+                tA_l = rec.z / kTile;
+                P_l = (rec.z + rec.y - 1) / kTile - tA_l;
+                if (P_l > kHotPartials) P_l = 0;           // hot row: k_combine<HOT_ONLY> finished it
+            }
+        }
+        float klrow = 0.f, gwh = 0.f;
+        // ---- wide work: GPW rows per round
+#pragma unroll 1
+        for (int it = 0; it < kRounds; ++it) {
+            const int sel = it * GPW + gidx;
+            const int rowid = bcast(rowid_l, sel);
+            const float cfac = bcast(cfac_l, sel);
+            const int tA = CUT ? bcast(tA_l, sel) : 0, P = CUT ? bcast(P_l, sel) : 0;
+            const int u = base + sel;
+            float kl = 0.f, gwc = 0.f;
+#ifdef VFMB_X_BALANCED
+            if (u < w_hi) {
+#else
+            if (u < U) {
+#endif
+                const size_t eoff = (size_t)rowid * 2 * d;
+                Vec<VEC> gsum[NV];
+                if (CUT && P > 0) {                        // group-uniform: tail(tA) + heads(tA+1 .. tA+P)
+                    sum_head_slots<VEC, LPR, NV, 2>(fa.gslot, dp, d, gl, tA + 1, tA + P + 1, gsum, gwc);
+                    const float* tp = fa.gslot + ((size_t)tA * 2 + 1) * dp;
+                    gwc = __ldg(tp + d) + gwc;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        int k = (gl + i * LPR) * VEC;
+                        if (k < d) {
+                            const Vec<VEC> t = ld_vec_nc<VEC>(tp + k);
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) gsum[i].v[j] = t.v[j] + gsum[i].v[j];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    int k = (gl + i * LPR) * VEC;
+                    if (k < d) {
+                        Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
+                        Vec<VEC> m1, m2, v1, v2;
+                        if (MODE == VFMB_ADAM_TOUCHED) {
+                            m1 = ld_vec_cs<VEC>(entity_m + eoff + k); m2 = ld_vec_cs<VEC>(entity_m + eoff + d + k);
+                            v1 = ld_vec_cs<VEC>(entity_v + eoff + k); v2 = ld_vec_cs<VEC>(entity_v + eoff + d + k);
+                        }
+                        Vec<VEC> g;
+                        if (CUT && P > 0) g = gsum[i]; else g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
+                        Vec<VEC> e;                         // the noise k_stage used for this row
+                        if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step);
+                        else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
+                        Vec<VEC> gmu, grho;
+                        float quad = 0.f, prodv = 1.f;
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) {
+                            const float sig = link_fn<LINK>(rho.v[j]);
+                            if (CUT && P > 0 && c.F > 2)    // pairwise, cut row: sum r_n (S_n - v_u)
+                                g.v[j] = fmaf(-gwc, fmaf(e.v[j], sig, mu.v[j]), g.v[j]);
+                            gmu.v[j] = fmaf(cfac, mu.v[j], g.v[j]);
+                            grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(g.v[j], e.v[j], cfac * (sig - fast_rcp(sig)));
+                            if (KLF) {
+                                const float vr = sig * sig;
+                                quad += vr + mu.v[j] * mu.v[j] - 1.f;
+                                prodv *= vr;
+                            }
+                        }
+                        if (KLF) {       // sum_k KL(N(mu,sig)||N(0,1)), one logarithm per lane (as k_stage)
+                            float lg = __logf(prodv);
+                            if (!(prodv > 1e-30f && prodv < 1e30f)) {
+                                lg = 0.f;
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho.v[j]); lg += logf(sg * sg); }
+                            }
+                            kl += 0.5f * (quad - lg);
+                        }
+                        if (MODE == VFMB_ADAM_TOUCHED) {
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) {
+                                adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu.v[j], h, step_size, inv_bc2);
+                                adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, inv_bc2);
+                            }
+                            st_vec<VEC>(entity + eoff + k, mu);        st_vec<VEC>(entity + eoff + d + k, rho);
+                            st_vec_cs<VEC>(entity_m + eoff + k, m1);   st_vec_cs<VEC>(entity_m + eoff + d + k, m2);
+                            st_vec_cs<VEC>(entity_v + eoff + k, v1);   st_vec_cs<VEC>(entity_v + eoff + d + k, v2);
+                        } else {
+                            st_vec<VEC>(grad_entity + eoff + k, gmu);  st_vec<VEC>(grad_entity + eoff + d + k, grho);
+                        }
+                    }
+                }
+                if (KLF) kl = group_sum<LPR>(kl, gmask);
+            }
+            if (KLF) hand_back<LPR>(klrow, kl, it, lane);
+            if (CUT) hand_back<LPR>(gwh, gwc, it, lane);
+        }
+        // ---- lane-parallel: bias row (after the wide work: a cut row's g_w comes from its group)
+        if (valid) {
+            if (CUT && P_l > 0) gw_l = gwh;
+            const size_t boff = (size_t)rowid_l * 2;
+            const float eb = eb_l;
+            const float tau = link_fn<LINK>(ab.y);
+            if (KLF) facc = fmaf(cq_l, klrow + kl_std_normal(ab.x, tau), facc);
+            const float ga = fmaf(cfac_l, ab.x, gw_l);
+            const float gb = link_grad<LINK>(ab.y) * fmaf(gw_l, eb, cfac_l * (tau - fast_rcp(tau)));
+            if (MODE == VFMB_ADAM_TOUCHED) {
                 adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
                 adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
                 *reinterpret_cast<float2*>(bias + boff) = ab;
@@ -466,86 +669,19 @@ k_adam_rows(int d, float* __restrict__ bias, float* __restrict__ bias_m, float* 
                 *reinterpret_cast<float2*>(grad_bias + boff) = make_float2(ga, gb);
             }
         }
-        // ---- wide work: GPW rows per round
-#pragma unroll 1
-        for (int it = 0; it < kRounds; ++it) {
-            const int sel = it * GPW + gidx;
-            const int rowid = bcast(rowid_l, sel);
-            const float cfac = bcast(cfac_l, sel);
-            const int u = base + sel;
-            if (u >= U) continue;
-            const size_t eoff = (size_t)rowid * 2 * d;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                int k = (gl + i * LPR) * VEC;
-                if (k < d) {
-                    Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
-                    Vec<VEC> m1, m2, v1, v2;
-                    if (MODE == VFMB_ADAM_TOUCHED) {
-                        m1 = ld_vec_cs<VEC>(entity_m + eoff + k); m2 = ld_vec_cs<VEC>(entity_m + eoff + d + k);
-                        v1 = ld_vec_cs<VEC>(entity_v + eoff + k); v2 = ld_vec_cs<VEC>(entity_v + eoff + d + k);
-                    }
-                    const Vec<VEC> g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
-                    const Vec<VEC> e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
-                    Vec<VEC> gmu, grho;
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        float sig = link_fn<LINK>(rho.v[j]);
-                        gmu.v[j] = fmaf(cfac, mu.v[j], g.v[j]);
-                        grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(g.v[j], e.v[j], cfac * (sig - fast_rcp(sig)));
-                    }
-                    if (MODE == VFMB_ADAM_TOUCHED) {
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu.v[j], h, step_size, inv_bc2);
-                            adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, inv_bc2);
-                        }
-                        st_vec<VEC>(entity + eoff + k, mu);        st_vec<VEC>(entity + eoff + d + k, rho);
-                        st_vec_cs<VEC>(entity_m + eoff + k, m1);   st_vec_cs<VEC>(entity_m + eoff + d + k, m2);
-                        st_vec_cs<VEC>(entity_v + eoff + k, v1);   st_vec_cs<VEC>(entity_v + eoff + d + k, v2);
-                    } else {
-                        st_vec<VEC>(grad_entity + eoff + k, gmu);  st_vec<VEC>(grad_entity + eoff + d + k, grho);
-                    }
-                }
+    }
+    if (FLAVOR >= 1) {
+        // the block that finishes last owns the scalar parameters: every block has read the step
+        // counter / Adam coefficients before it signalled, so updating them here is race-free
+        double acc[1] = {(double)facc};
+        if (block_partials<1>(acc, fa.partials, fa.counter)) {
+            double tot[1] = {0.0};
+            if (KLF) final_sums<1>(fa.partials, tot);
+            if (threadIdx.x == 0) {
+                final_scalars<LINK, MODE>(c, fa, h, adam_step, kl_scale, KLF, tot[0], U);
+                *fa.counter = 0;
             }
         }
-    }
-}
-
-// ------------------------------------------------------------------------------- k_final
-template <int LINK, int LIK, int MODE>
-__global__ void k_final(DevCfg c, float* __restrict__ scalars, float* __restrict__ sm,
-                        float* __restrict__ sv, const float* __restrict__ stats,
-                        const float* __restrict__ eps_global, AdamDev h, int32_t* __restrict__ adam_step,
-                        float kl_scale, float* __restrict__ grad_scalars) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const uint32_t step = (uint32_t)adam_step[0];
-    float alpha = scalars[VFMB_S_ALPHA], mu0 = scalars[VFMB_S_GB_MEAN], rho0 = scalars[VFMB_S_GB_SCALE];
-    const float sig0 = link_fn<LINK>(rho0), ap = link_fn<LINK>(alpha);
-    const float e0 = global_eps(eps_global, c, step);
-    const double sr = (double)stats[VFMB_ST_SUM_RESID], sq = (double)stats[VFMB_ST_SUM_SQERR];
-    float g_mu0 = (float)(sr + (double)(kl_scale * mu0));
-    float g_rho0 = link_grad<LINK>(rho0) * (float)((double)e0 * sr + (double)(kl_scale * (sig0 - 1.f / sig0)));
-    float g_alpha = 0.f;
-    if (LIK == VFMB_GAUSSIAN) {
-        double sc = (double)c.n_train / ((double)c.S * (double)c.B);
-        g_alpha = link_grad<LINK>(alpha) * (float)(sc * (0.5 * sq - 0.5 * (double)c.S * (double)c.B / (double)ap));
-    }
-    if (MODE == VFMB_ADAM_TOUCHED) {
-        float ss, b2;
-        adam_coeffs(h, (int)step + 1, &ss, &b2);
-        adam_elem(mu0, sm[VFMB_S_GB_MEAN], sv[VFMB_S_GB_MEAN], g_mu0, h, ss, b2);
-        adam_elem(rho0, sm[VFMB_S_GB_SCALE], sv[VFMB_S_GB_SCALE], g_rho0, h, ss, b2);
-        scalars[VFMB_S_GB_MEAN] = mu0; scalars[VFMB_S_GB_SCALE] = rho0;
-        if (LIK == VFMB_GAUSSIAN) {          // Bernoulli: alpha has no gradient, Adam skips it (N10)
-            adam_elem(alpha, sm[VFMB_S_ALPHA], sv[VFMB_S_ALPHA], g_alpha, h, ss, b2);
-            scalars[VFMB_S_ALPHA] = alpha;
-        }
-        adam_step[0] = (int32_t)step + 1;
-    } else {
-        grad_scalars[VFMB_S_ALPHA] = g_alpha;
-        grad_scalars[VFMB_S_GB_MEAN] = g_mu0;
-        grad_scalars[VFMB_S_GB_SCALE] = g_rho0;
     }
 }
 
@@ -630,29 +766,34 @@ static int prep(const vfmb_config* cfg, const char* who, vfmb_stream stream_, in
     return 0;
 }
 
-extern "C" int vfmb_sampled_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                                  const vfmb_step_io* io, vfmb_stream stream_) {
+// ---- internal launchers (the public entry points below are thin wrappers)
+static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                        const vfmb_step_io* io, vfmb_stream stream_, bool lean) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_stage", stream_, 1, &P);
     if (rc) return rc;
     if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: null argument");
-    if (!io->eps_entity && (!io->es || !io->ebs)) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: noise scratch (es/ebs) required");
+    if (!lean && !io->eps_entity && !io->es) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: noise scratch (es) required");
+    if (!io->eps_bias && !io->ebs) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: noise scratch (ebs) required");
     if (!io->vs || !io->ws || !io->cq || !io->partials || !io->counters || !io->stats)
         return set_error(VFMB_EINVAL, "vfmb_sampled_stage: scratch required");
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch; const auto& cap = P.cap;
-#define LAUNCH_STAGE(LINK)                                                                             \
-    k_stage<VEC, LPR, NV, LINK><<<grid_resident(k_stage<VEC, LPR, NV, LINK>, cap.u_cap, ch), 256, 0, stream>>>( \
+#define LAUNCH_STAGE(LINK, LEAN)                                                                       \
+    k_stage<VEC, LPR, NV, LINK, LEAN><<<grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, ch), 256, 0, stream>>>( \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
         io->eps_bias, io->eps_entity, tab->adam_step, io->vs, io->ws, io->es,                          \
         io->ebs, io->cq, io->partials, io->counters + 0, io->stats)
-    VFMB_LAYOUT_SWITCH(L, { if (cfg->link == VFMB_LINK_ABS) LAUNCH_STAGE(0); else LAUNCH_STAGE(1); });
+    VFMB_LAYOUT_SWITCH(L, {
+        if (cfg->link == VFMB_LINK_ABS) { if (lean) LAUNCH_STAGE(0, 1); else LAUNCH_STAGE(0, 0); }
+        else                            { if (lean) LAUNCH_STAGE(1, 1); else LAUNCH_STAGE(1, 0); }
+    });
 #undef LAUNCH_STAGE
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-extern "C" int vfmb_sampled_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                                  const vfmb_step_io* io, vfmb_stream stream_) {
+static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                        const vfmb_step_io* io, vfmb_stream stream_, int defer_kl) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_score", stream_, 2, &P);
     if (rc) return rc;
@@ -663,7 +804,7 @@ extern "C" int vfmb_sampled_score(const vfmb_config* cfg, const vfmb_tables* tab
     k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, stream>>>( \
         dc, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->y, io->eps_global,          \
         tab->adam_step, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials,             \
-        io->counters + 1, io->stats)
+        io->counters + 1, io->stats, defer_kl)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SCORE(0, VFMB_GAUSSIAN); else LAUNCH_SCORE(0, VFMB_BERNOULLI);
@@ -676,15 +817,27 @@ extern "C" int vfmb_sampled_score(const vfmb_config* cfg, const vfmb_tables* tab
     return 0;
 }
 
-extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                                    const vfmb_step_io* io, vfmb_stream stream) {
-    int rc = vfmb_sampled_stage(cfg, tab, plan, io, stream);
-    if (rc) return rc;
-    return vfmb_sampled_score(cfg, tab, plan, io, stream);
+extern "C" int vfmb_sampled_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                  const vfmb_step_io* io, vfmb_stream stream) {
+    return launch_stage(cfg, tab, plan, io, stream, false);
 }
 
-extern "C" int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
-                                   const float* table, int32_t unit_coef, vfmb_stream stream_) {
+extern "C" int vfmb_sampled_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                  const vfmb_step_io* io, vfmb_stream stream) {
+    return launch_score(cfg, tab, plan, io, stream, 0);
+}
+
+extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                    const vfmb_step_io* io, vfmb_stream stream) {
+    int rc = launch_stage(cfg, tab, plan, io, stream, false);
+    if (rc) return rc;
+    return launch_score(cfg, tab, plan, io, stream, 0);
+}
+
+// hot_only: k_combine finishes only the rows spanning > kHotPartials tiles; the other cut rows
+// are summed inside k_adam_rows<FLAVOR >= 1>
+static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
+                         const float* table, int32_t unit_coef, bool hot_only, vfmb_stream stream_) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_gather", stream_, 1, &P);
     if (rc) return rc;
@@ -704,16 +857,27 @@ extern "C" int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan
         else
             k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>(
                 cfg->d, cfg->F, N, plan->partner, plan->pos_rank, io->vs, tbl, io->rsorted, gslot, io->grow, io->gws);
-        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float), stream>>>(
-            cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
+        const size_t smem = 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float);
+        if (hot_only)
+            k_combine<VEC, LPR, NV, 1><<<grid_warps(cap.u_cap, 32), 256, smem, stream>>>(
+                cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
+        else
+            k_combine<VEC, LPR, NV, 0><<<grid_warps(cap.u_cap, 32), 256, smem, stream>>>(
+                cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
     });
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-extern "C" int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                                      const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
-                                      float kl_grad_scale, vfmb_stream stream_) {
+extern "C" int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
+                                   const float* table, int32_t unit_coef, vfmb_stream stream) {
+    return launch_gather(cfg, plan, io, table, unit_coef, false, stream);
+}
+
+// flavor: see k_adam_rows
+static int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                       const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode, float kl_grad_scale,
+                       int flavor, vfmb_stream stream_) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_adam_rows", stream_, 1, &P);
     if (rc) return rc;
@@ -724,41 +888,62 @@ extern "C" int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables*
         return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: gradient outputs required");
     if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: bad mode");
     if (!io->grow || !io->gws || !io->cq) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: scratch required");
+    if (flavor >= 1 && mode == VFMB_ADAM_TOUCHED && (!tab->scalars_m || !tab->scalars_v))
+        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: Adam state required");
+    if (flavor >= 1 && (!tab->scalars || !io->stats || !io->partials || !io->counters))
+        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: scalars / stats required");
     const Layout& L = P.L; cudaStream_t stream = P.stream; const int ch = P.ch; const auto& cap = P.cap;
+    const DevCfg& dc = P.dc;
     AdamDev h = make_adam(adam);
-    // the noise the forward used: injected arrays, or what k_stage wrote to scratch (Philox)
-    const float* eps_e = io->eps_entity ? io->eps_entity : io->es;
+    // the noise the forward used: injected arrays, or what k_stage wrote to scratch (Philox);
+    // flavor 2 recomputes the Philox draws of the rows instead
+    const float* eps_e = io->eps_entity ? io->eps_entity : (flavor == 2 ? nullptr : io->es);
     const float* eps_b = io->eps_bias ? io->eps_bias : io->ebs;
-#define LAUNCH_ADAM(LINK, MODE)                                                                          \
-    k_adam_rows<VEC, LPR, NV, LINK, MODE><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE>, cap.u_cap, ch), 256, 0, stream>>>( \
-        cfg->d, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,          \
+    if (!eps_b || (flavor != 2 && !eps_e)) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: noise of the forward required");
+    FinalArgs fa{};
+    fa.scalars = tab->scalars; fa.sm = tab->scalars_m; fa.sv = tab->scalars_v; fa.stats = io->stats;
+    fa.eps_global = io->eps_global; fa.grad_scalars = io->grad_scalars; fa.partials = io->partials;
+    fa.counter = io->counters ? io->counters + 2 : nullptr;
+    fa.gslot = io->partials ? (const float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off : nullptr;
+    fa.likelihood = cfg->likelihood;
+#define LAUNCH_ADAM(LINK, MODE, FLAVOR)                                                                  \
+    k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR>, cap.u_cap, ch), 256, 0, stream>>>( \
+        dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,              \
         plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, h, tab->adam_step,              \
-        kl_grad_scale, io->grad_bias, io->grad_entity)
+        kl_grad_scale, io->grad_bias, io->grad_entity, fa)
+#define LAUNCH_ADAM_F(LINK, MODE)                                                                        \
+    do { if (flavor == 0) LAUNCH_ADAM(LINK, MODE, 0); else if (flavor == 1) LAUNCH_ADAM(LINK, MODE, 1);  \
+         else LAUNCH_ADAM(LINK, MODE, 2); } while (0)
     VFMB_LAYOUT_SWITCH(L, {
         cudaEvent_t ev0, ev1;
         profile_events(&ev0, &ev1);
         if (ev0 && ev1) cudaEventRecord(ev0, stream);
         if (cfg->link == VFMB_LINK_ABS) {
-            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM(0, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM(0, VFMB_GRAD_ONLY);
+            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM_F(0, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM_F(0, VFMB_GRAD_ONLY);
         } else {
-            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM(1, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM(1, VFMB_GRAD_ONLY);
+            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM_F(1, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM_F(1, VFMB_GRAD_ONLY);
         }
         if (ev0 && ev1) cudaEventRecord(ev1, stream);
     });
+#undef LAUNCH_ADAM_F
 #undef LAUNCH_ADAM
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                                     const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
-                                     float kl_grad_scale, vfmb_stream stream_) {
+extern "C" int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                      const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                                      float kl_grad_scale, vfmb_stream stream) {
+    return launch_adam(cfg, tab, plan, io, adam, mode, kl_grad_scale, 0, stream);
+}
+
+static int backward_impl(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                         const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                         float kl_grad_scale, int flavor, vfmb_stream stream_) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_backward", stream_, 2, &P);
     if (rc) return rc;
     if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: null argument");
-    if (mode == VFMB_ADAM_TOUCHED && (!tab->scalars_m || !tab->scalars_v))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: Adam state required");
     cudaStream_t stream = P.stream;
     if (mode == VFMB_GRAD_ONLY) {
         // the residuals may come from the caller's autograd: (re)build their sorted-order copy
@@ -769,39 +954,29 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
         k_scatter_resid<<<g, 256, 0, stream>>>(io->resid, plan->pos_of, N, cfg->F, io->rsorted);
         CUDA_TRY(cudaGetLastError());
     }
-    rc = vfmb_sampled_gather(cfg, plan, io, nullptr, 0, stream_);
+    rc = launch_gather(cfg, plan, io, nullptr, 0, true, stream_);
     if (rc) return rc;
-    rc = vfmb_sampled_adam_rows(cfg, tab, plan, io, adam, mode, kl_grad_scale, stream_);
-    if (rc) return rc;
-    if (mode == VFMB_GRAD_ONLY && !io->grad_scalars) return 0;
-    AdamDev h = make_adam(adam);
-    const DevCfg& dc = P.dc;
-#define LAUNCH_FINAL(LINK, LIK, MODE)                                                                    \
-    k_final<LINK, LIK, MODE><<<1, 32, 0, stream>>>(dc, tab->scalars, tab->scalars_m, tab->scalars_v,     \
-                                                   io->stats, io->eps_global, h, tab->adam_step,         \
-                                                   kl_grad_scale, io->grad_scalars)
-    const int key = cfg->link * 4 + cfg->likelihood * 2 + (mode == VFMB_GRAD_ONLY ? 1 : 0);
-    switch (key) {
-        case 0: LAUNCH_FINAL(0, 0, VFMB_ADAM_TOUCHED); break;
-        case 1: LAUNCH_FINAL(0, 0, VFMB_GRAD_ONLY); break;
-        case 2: LAUNCH_FINAL(0, 1, VFMB_ADAM_TOUCHED); break;
-        case 3: LAUNCH_FINAL(0, 1, VFMB_GRAD_ONLY); break;
-        case 4: LAUNCH_FINAL(1, 0, VFMB_ADAM_TOUCHED); break;
-        case 5: LAUNCH_FINAL(1, 0, VFMB_GRAD_ONLY); break;
-        case 6: LAUNCH_FINAL(1, 1, VFMB_ADAM_TOUCHED); break;
-        default: LAUNCH_FINAL(1, 1, VFMB_GRAD_ONLY); break;
-    }
-#undef LAUNCH_FINAL
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    return launch_adam(cfg, tab, plan, io, adam, mode, kl_grad_scale, flavor, stream_);
 }
 
+extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                     const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                                     float kl_grad_scale, vfmb_stream stream) {
+    return backward_impl(cfg, tab, plan, io, adam, mode, kl_grad_scale, 1, stream);
+}
+
+// The fused training step: 5 launches -- k_stage<LEAN>, k_score, k_gather, k_combine<HOT_ONLY>,
+// k_adam_rows<FLAVOR 2> (KL, scalar parameters and the step counter folded in).
 extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                  const vfmb_step_io* io, const vfmb_adam* adam, vfmb_stream stream) {
     if (io && !io->y) return set_error(VFMB_EINVAL, "vfmb_sampled_step: targets required");
-    int rc = vfmb_sampled_forward(cfg, tab, plan, io, stream);
+    static const int flavor = [] { const char* e = getenv("VFMB_STEP_FLAVOR"); return e ? atoi(e) : 2; }();
+    const bool lean = flavor == 2 && io && (io->eps_entity || true);
+    int rc = launch_stage(cfg, tab, plan, io, stream, lean);
     if (rc) return rc;
-    return vfmb_sampled_backward(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, stream);
+    rc = launch_score(cfg, tab, plan, io, stream, lean ? 1 : 0);
+    if (rc) return rc;
+    return backward_impl(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, lean ? 2 : 1, stream);
 }
 
 extern "C" int vfmb_adam_dense(float* p, float* m, float* v, const float* g, int64_t n, const vfmb_adam* adam,

@@ -3,7 +3,11 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <cstdlib>
+
 namespace vfmb {
+
+constexpr int kGridCap = 2048;      // most blocks a step kernel is launched with (block partials are sized for it)
 
 struct DevCfg {
     int B, F, d, S, n_classes;
@@ -92,7 +96,10 @@ __device__ __forceinline__ void final_sums(const double* __restrict__ partials, 
 // wide (d-element) work, fetching each unit's scalars by shuffle.  Rows of the later rounds are
 // prefetched into L2 up front.  This keeps ~50 warps per SM busy while taking the per-row scalar
 // code out of the wide path, where it ran at 1/LPR lane efficiency.
-constexpr int kRounds = 4;
+#ifndef VFMB_ROUNDS
+#define VFMB_ROUNDS 4
+#endif
+constexpr int kRounds = VFMB_ROUNDS;
 #define GPW_OF(LPR) (32 / (LPR))
 
 template <typename T>
@@ -191,7 +198,7 @@ __device__ __forceinline__ void sum_head_slots(const float* __restrict__ gslot, 
     }
 }
 
-template <int VEC, int LPR, int NV>
+template <int VEC, int LPR, int NV, int HOT_ONLY = 0>
 __global__ void __launch_bounds__(256)
 k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
           const float* __restrict__ gslot, const float* __restrict__ vs,
@@ -216,7 +223,8 @@ k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restr
         }
         const int P_l = tB_l - tA_l;
         if (P_l > kHotPartials) s_hot[atomicAdd(&s_nhot, 1)] = ul;   // order only affects scheduling
-        unsigned todo = __ballot_sync(0xffffffffu, P_l > 0 && P_l <= kHotPartials);
+        // HOT_ONLY: the rows with few partials are summed by the consumer (k_adam_rows<FLAVOR >= 1>)
+        unsigned todo = HOT_ONLY ? 0u : __ballot_sync(0xffffffffu, P_l > 0 && P_l <= kHotPartials);
         // ---- per-warp: rows with few partials
         while (todo) {
             const int src = __ffs(todo) - 1;
@@ -331,7 +339,7 @@ static inline ScratchMap scratch_map(int B, int F, int d, int64_t u_cap) {
     const int64_t n = (int64_t)B * F;
     const int64_t slots = 2 * ((n + kTile - 1) / kTile + 1);
     m.nblk_max = (int)(u_cap / 32 + kMaxFields + 1);
-    const size_t nred = (size_t)(m.nblk_max > kMaxGrid ? m.nblk_max : kMaxGrid);
+    const size_t nred = (size_t)(m.nblk_max > kGridCap ? m.nblk_max : kGridCap);
     size_t off = nred * 16 * 2;                             // block partials (doubles), in floats
     m.gslot_off = off;        off += (size_t)slots * (3 * d + 4);
     m.pg_width = 2 * d + 4;
@@ -342,7 +350,10 @@ static inline ScratchMap scratch_map(int B, int F, int d, int64_t u_cap) {
     return m;
 }
 
-// one resident wave for a grid-stride kernel: blocks/SM from the occupancy calculator (cached)
+// Grid of a (grid-stride) step kernel: one persistent resident wave (blocks/SM from the occupancy
+// calculator).  VFMB_PERSISTENT=0 launches one warp per `per_warp` units instead (as many blocks as
+// the work needs, capped at kGridCap); measured 4 % slower on the ml20m step (more block
+// prologues, no gain from hardware load balancing).
 template <typename K>
 static inline int resident_blocks(K kernel, int block, size_t smem) {
     static int cached = 0;                                  // one instance per kernel type
@@ -356,9 +367,10 @@ static inline int resident_blocks(K kernel, int block, size_t smem) {
 }
 template <typename K>
 static inline int grid_resident(K kernel, int64_t units, int per_warp, size_t smem = 0) {
+    static const bool persistent = [] { const char* e = getenv("VFMB_PERSISTENT"); return !e || atoi(e) != 0; }();
     int64_t warps = (units + per_warp - 1) / per_warp;
     int64_t g = (warps + 7) / 8;
-    const int cap = resident_blocks(kernel, 256, smem);
+    const int cap = persistent ? resident_blocks(kernel, 256, smem) : kGridCap;
     if (g < 1) g = 1;
     if (g > cap) g = cap;
     return (int)g;
