@@ -114,7 +114,9 @@ typedef struct vfmb_plan {
     int32_t* class_off;  /* [VFMB_MAX_FIELDS+1] first unique rank of each KL class (class_bound
                                       of the config); class_off[n_classes] = U               */
     float* z;            /* [VFMB_MAX_FIELDS] per-column normaliser Z_f             */
-    int32_t* meta;       /* [8] 0:U 2:error flag (id out of range); rest reserved   */
+    int32_t* meta;       /* [8] 0:U 2:error flag (id out of range) 3:number of hot rows; rest reserved */
+    int32_t* hot;        /* [n_tiles/30+2] unique ranks of the rows whose segment spans more than 32
+                                      backward tiles (order unspecified; it only schedules work)  */
 } vfmb_plan;
 
 typedef struct vfmb_plan_capacity_t {

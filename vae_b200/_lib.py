@@ -60,7 +60,7 @@ class Adam(C.Structure):
 class Plan(C.Structure):
     _fields_ = [("uniq", _i32p), ("inverse", _i32p), ("seg_off", _i32p), ("occ", _i32p),
                 ("pos_of", _i32p), ("pos_rank", _i32p), ("partner", _i32p), ("urec", _i32p),
-                ("class_off", _i32p), ("z", _f32p), ("meta", _i32p)]
+                ("class_off", _i32p), ("z", _f32p), ("meta", _i32p), ("hot", _i32p)]
 
 
 class PlanCapacity(C.Structure):

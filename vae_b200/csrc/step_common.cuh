@@ -163,7 +163,6 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g,
 // the rare hot rows (> kHotPartials tiles: a Zipf head row with thousands of occurrences) are
 // handled by the whole block, 8*GPW groups over contiguous ranges and a fixed-order shared-memory
 // reduction.  Every association is fixed by the plan, so the result is bitwise reproducible.
-constexpr int kHotPartials = 32;
 
 template <int VEC, int LPR, int NV, int UNR>
 __device__ __forceinline__ void sum_head_slots(const float* __restrict__ gslot, int dp, int d, int gl,
@@ -196,6 +195,67 @@ __device__ __forceinline__ void sum_head_slots(const float* __restrict__ gslot, 
                 gw += pw[q];
             }
     }
+}
+
+// one hot row (> kHotPartials tile partials), summed by the whole block: 8*GPW lane groups over
+// contiguous slot ranges, then a fixed-order shared-memory reduction by one group
+template <int VEC, int LPR, int NV>
+__device__ __forceinline__ void combine_hot_row(int u, int d, int F, const int32_t* __restrict__ urec,
+                                                const float* __restrict__ gslot, const float* __restrict__ vs,
+                                                float* __restrict__ grow, float* __restrict__ gws, float* s_part) {
+    constexpr int GPW = kWarp / LPR, NG = 8 * GPW;
+    const int dp = d + 4;
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR, warp = threadIdx.x >> 5;
+    const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
+    const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;
+    const int g = warp * GPW + gidx;                        // group id 0 .. NG-1
+    const int per = (tB - tA + NG - 1) / NG;
+    const int lo = min(tB + 1, tA + 1 + g * per), hi = min(tB + 1, lo + per);
+    Vec<VEC> acc[NV]; float gw;
+    sum_head_slots<VEC, LPR, NV, 8>(gslot, dp, d, gl, lo, hi, acc, gw);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        int k = (gl + i * LPR) * VEC;
+        if (k < d) st_vec<VEC>(s_part + (size_t)g * dp + k, acc[i]);
+    }
+    if (gl == 0) s_part[(size_t)g * dp + d] = gw;
+    __syncthreads();
+    if (warp == 0 && gidx == 0) {                          // one lane group adds the NG sums in order
+        const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
+        float gw_tot = __ldg(tp + d);
+        for (int q = 0; q < NG; ++q) gw_tot += s_part[(size_t)q * dp + d];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            int k = (gl + i * LPR) * VEC;
+            if (k < d) {
+                Vec<VEC> tot = ld_vec_nc<VEC>(tp + k);
+                for (int q = 0; q < NG; ++q)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) tot.v[j] += s_part[(size_t)q * dp + k + j];
+                if (F > 2) {
+                    Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) tot.v[j] = fmaf(-gw_tot, own.v[j], tot.v[j]);
+                }
+                st_vec<VEC>(grow + (size_t)u * d + k, tot);
+            }
+        }
+        if (gl == 0) gws[u] = gw_tot;
+    }
+    __syncthreads();
+}
+
+// the hot rows alone, from the plan's hot list (meta[3] entries): what the fused step launches --
+// the other cut rows are summed by their consumer (k_adam_rows<FLAVOR >= 1>)
+template <int VEC, int LPR, int NV>
+__global__ void __launch_bounds__(256)
+k_combine_hot(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
+              const int32_t* __restrict__ hot, const float* __restrict__ gslot, const float* __restrict__ vs,
+              float* __restrict__ grow, float* __restrict__ gws) {
+    extern __shared__ float s_part[];                    // [8*GPW][d+4] block-level partial sums
+    const int n_hot = meta[3];
+    for (int i = blockIdx.x; i < n_hot; i += gridDim.x)
+        combine_hot_row<VEC, LPR, NV>(__ldg(hot + i), d, F, urec, gslot, vs, grow, gws, s_part);
 }
 
 template <int VEC, int LPR, int NV, int HOT_ONLY = 0>
@@ -267,46 +327,8 @@ k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restr
         __syncthreads();
         // ---- whole block: hot rows
         const int nhot = s_nhot;
-        for (int hi_ = 0; hi_ < nhot; ++hi_) {
-            const int u = s_hot[hi_];
-            const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
-            const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;
-            const int g = warp * GPW + gidx;                // group id 0 .. NG-1
-            const int per = (tB - tA + NG - 1) / NG;
-            const int lo = min(tB + 1, tA + 1 + g * per), hi = min(tB + 1, lo + per);
-            Vec<VEC> acc[NV]; float gw;
-            sum_head_slots<VEC, LPR, NV, 8>(gslot, dp, d, gl, lo, hi, acc, gw);
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                int k = (gl + i * LPR) * VEC;
-                if (k < d) st_vec<VEC>(s_part + (size_t)g * dp + k, acc[i]);
-            }
-            if (gl == 0) s_part[(size_t)g * dp + d] = gw;
-            __syncthreads();
-            if (warp == 0 && gidx == 0) {                  // one lane group adds the NG sums in order
-                const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
-                float gw_tot = __ldg(tp + d);
-                for (int q = 0; q < NG; ++q) gw_tot += s_part[(size_t)q * dp + d];
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-                        Vec<VEC> tot = ld_vec_nc<VEC>(tp + k);
-                        for (int q = 0; q < NG; ++q)
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) tot.v[j] += s_part[(size_t)q * dp + k + j];
-                        if (F > 2) {
-                            Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) tot.v[j] = fmaf(-gw_tot, own.v[j], tot.v[j]);
-                        }
-                        st_vec<VEC>(grow + (size_t)u * d + k, tot);
-                    }
-                }
-                if (gl == 0) gws[u] = gw_tot;
-            }
-            __syncthreads();
-        }
+        for (int hi_ = 0; hi_ < nhot; ++hi_)
+            combine_hot_row<VEC, LPR, NV>(s_hot[hi_], d, F, urec, gslot, vs, grow, gws, s_part);
         __syncthreads();                                   // s_nhot / s_hot are reused by the next pass
     }
 }

@@ -43,11 +43,13 @@ class BatchPlan:
         self.class_off = torch.zeros(L.MAX_FIELDS + 1, dtype=torch.int32, device=device)
         self.z = torch.zeros(L.MAX_FIELDS, dtype=torch.float32, device=device)
         self.meta = torch.zeros(8, dtype=torch.int32, device=device)
+        self.hot = torch.zeros(self.n_tiles // 30 + 2, dtype=torch.int32, device=device)
         self.workspace = torch.empty(int(cap.workspace_bytes), dtype=torch.uint8, device=device)
         self.B = 0
         self.struct = L.Plan(L.ptr(self.uniq), L.ptr(self.inverse), L.ptr(self.seg_off),
                              L.ptr(self.occ), L.ptr(self.pos_of), L.ptr(self.pos_rank), L.ptr(self.partner),
-                             L.ptr(self.urec), L.ptr(self.class_off), L.ptr(self.z), L.ptr(self.meta))
+                             L.ptr(self.urec), L.ptr(self.class_off), L.ptr(self.z), L.ptr(self.meta),
+                             L.ptr(self.hot))
 
     def build(self, cfg: L.Config, x: torch.Tensor, train_counts: torch.Tensor) -> "BatchPlan":
         assert x.dtype == torch.int64 and x.is_cuda and x.is_contiguous(), "x: contiguous CUDA int64 [B,F]"
