@@ -114,14 +114,17 @@ typedef struct vfmb_plan {
     int32_t* class_off;  /* [VFMB_MAX_FIELDS+1] first unique rank of each KL class (class_bound
                                       of the config); class_off[n_classes] = U               */
     float* z;            /* [VFMB_MAX_FIELDS] per-column normaliser Z_f             */
-    int32_t* meta;       /* [8] 0:U 2:error flag (id out of range) 3:number of hot rows; rest reserved */
-    int32_t* hot;        /* [n_tiles/30+2] unique ranks of the rows whose segment spans more than 32
-                                      backward tiles (order unspecified; it only schedules work)  */
+    int32_t* meta;       /* [8] 0:U 2:error flag (id out of range) 3:number of hot rows 5:number of
+                                      other cut rows; rest reserved                           */
+    int32_t* hot;        /* [cut_rows_cap of vfmb_plan_capacity] unique ranks of the rows cut by
+                                      backward-tile boundaries: <= 32 tiles from the front, more
+                                      ("hot" rows) from the back; order unspecified           */
 } vfmb_plan;
 
 typedef struct vfmb_plan_capacity_t {
     int64_t u_cap, n_tiles, workspace_bytes;
     int32_t tile;        /* sorted positions per backward tile */
+    int32_t cut_rows_cap; /* entries of vfmb_plan.hot */
 } vfmb_plan_capacity_t;
 
 int vfmb_plan_capacity(int32_t B, int32_t F, int32_t R, vfmb_plan_capacity_t* out /*host*/);

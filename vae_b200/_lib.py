@@ -65,7 +65,7 @@ class Plan(C.Structure):
 
 class PlanCapacity(C.Structure):
     _fields_ = [("u_cap", C.c_int64), ("n_tiles", C.c_int64), ("workspace_bytes", C.c_int64),
-                ("tile", C.c_int32)]
+                ("tile", C.c_int32), ("cut_rows_cap", C.c_int32)]
 
 
 class StepIO(C.Structure):

@@ -14,6 +14,10 @@ constexpr int kPlanGrid = 2 * kNumSMs;
 constexpr int kMaxGrid = 4 * kNumSMs;   // grid-stride kernels: one resident wave at 4 blocks/SM
 constexpr int kPriorGrid = 2 * kNumSMs; // blocks that carry prior-gradient partials (closed form)
 
+// entries of vfmb_plan.hot: every backward-tile boundary cuts at most one row (front of the list),
+// a hot row spans > kHotPartials tiles (back of the list)
+static inline int64_t cut_list_capacity(int64_t n_tiles) { return n_tiles + n_tiles / (kHotPartials - 2) + 4; }
+
 int set_error(int code, const char* fmt, ...);
 // optional events around the dominant kernel (see vfmb_profile_events)
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop);

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256)
 k_plan_finish(const int32_t* __restrict__ uniq, const int32_t* __restrict__ seg_off,
               const int32_t* __restrict__ occ, const int32_t* __restrict__ inverse, int N, int F,
               ClassBounds cb, int32_t* __restrict__ partner, int32_t* __restrict__ urec,
-              int32_t* __restrict__ class_off, int32_t* __restrict__ meta, int32_t* __restrict__ hot) {
+              int32_t* __restrict__ class_off, int32_t* __restrict__ meta, int32_t* __restrict__ hot, int hot_cap) {
     const int U = meta[0];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int i = tid; i < N; i += nth) {
@@ -296,8 +296,13 @@ k_plan_finish(const int32_t* __restrict__ uniq, const int32_t* __restrict__ seg_
         const int rowid = uniq[u];
         const int len = seg_off[u + 1] - seg0;
         reinterpret_cast<int4*>(urec)[u] = make_int4(rowid, len, seg0, len);
-        // rows spanning many backward tiles are finished by k_combine_hot (one block per row)
-        if (hot && (seg0 + len - 1) / kTile - seg0 / kTile > kHotPartials) hot[atomicAdd(&meta[3], 1)] = u;
+        // rows cut by backward-tile boundaries (k_combine_cut): few partials -> front of the list
+        // (a warp each), many -> back of the list (a block each); the order only schedules work
+        if (hot) {
+            const int span = (seg0 + len - 1) / kTile - seg0 / kTile;
+            if (span > kHotPartials) hot[hot_cap - 1 - atomicAdd(&meta[3], 1)] = u;
+            else if (span > 0) hot[atomicAdd(&meta[5], 1)] = u;
+        }
         // class_off[g] = first rank whose class is >= g (uniq is sorted, classes are id ranges)
         const int cls = plan_class_of(cb, rowid);
         const int prev = (u == 0) ? -1 : plan_class_of(cb, uniq[u - 1]);
@@ -372,6 +377,7 @@ extern "C" int vfmb_plan_capacity(int32_t B, int32_t F, int32_t R, vfmb_plan_cap
     out->u_cap = N < R ? N : R;
     out->n_tiles = (N + kTile - 1) / kTile;
     out->tile = kTile;
+    out->cut_rows_cap = (int32_t)cut_list_capacity(out->n_tiles);
     PlanWs w = carve(nullptr, N, sort_geom(N, R));
     out->workspace_bytes = (int64_t)w.total;
     return 0;
@@ -428,7 +434,8 @@ extern "C" int vfmb_plan_build(const vfmb_config* cfg, const int64_t* x, const f
     cbd.n = cfg->n_classes;
     for (int i = 0; i < kMaxFields; ++i) cbd.bound[i] = cfg->class_bound[i];
     k_plan_finish<<<grid2, 256, 0, stream>>>(plan->uniq, plan->seg_off, plan->occ, plan->inverse, N, cfg->F,
-                                             cbd, plan->partner, plan->urec, plan->class_off, plan->meta, plan->hot);
+                                             cbd, plan->partner, plan->urec, plan->class_off, plan->meta, plan->hot,
+                                             (int)cut_list_capacity(cap.n_tiles));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -432,10 +432,9 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
 // (g_v, g_w) to (mean, raw scale) + KL gradient, then Adam on the row -- parameters and both
 // moments of every touched row are read and written exactly once.
 //
-// FLAVOR 0  plain: row gradients are final in grow/gws (k_combine ran), nothing else.
-// FLAVOR 1  + rows cut by a tile boundary (<= kHotPartials tiles) add their tile partials here,
-//             in tile order (the hot rows were finished by k_combine<HOT_ONLY>);
-//           + the block that finishes last updates the scalar parameters and the step counter
+// Row gradients are final in grow/gws (k_combine_cut finished the rows cut by tile boundaries).
+// FLAVOR 0  plain.
+// FLAVOR 1  + the block that finishes last updates the scalar parameters and the step counter
 //             (what k_final did as a separate launch).
 // FLAVOR 2  + the count-rescaled KL of the rows (the row is in registers, the kernel is DRAM-bound
 //             with idle issue slots) and, without injected noise, the Philox draws recomputed
@@ -489,8 +488,34 @@ __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& 
 }
 
 #ifndef VFMB_ADAM_MINB
-#define VFMB_ADAM_MINB 3          // resident blocks/SM of the fused flavours (80 registers)
+#define VFMB_ADAM_MINB 4          // resident blocks/SM of the fused flavours (64 registers)
 #endif
+// bias row of one unique row: chain rule + KL gradient + Adam (or the dense-gradient store).
+// klw: in c_u, out c_u * KL(N(a, tau) || N(0,1)) of the pre-update row (when KLF)
+template <int LINK, int MODE, bool KLF>
+__device__ __forceinline__ void bias_update(float* __restrict__ bias, float* __restrict__ bias_m,
+                                            float* __restrict__ bias_v, float* __restrict__ grad_bias,
+                                            int rowid, float gw, float eb, float cfac, const AdamDev& h,
+                                            float step_size, float inv_bc2, float& klw) {
+    const size_t boff = (size_t)rowid * 2;
+    float2 ab = *reinterpret_cast<const float2*>(bias + boff);
+    const float tau = link_fn<LINK>(ab.y);
+    if (KLF) klw *= kl_std_normal(ab.x, tau);
+    const float ga = fmaf(cfac, ab.x, gw);
+    const float gb = link_grad<LINK>(ab.y) * fmaf(gw, eb, cfac * (tau - fast_rcp(tau)));
+    if (MODE == VFMB_ADAM_TOUCHED) {
+        float2 bm = *reinterpret_cast<const float2*>(bias_m + boff);
+        float2 bv = *reinterpret_cast<const float2*>(bias_v + boff);
+        adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
+        adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
+        *reinterpret_cast<float2*>(bias + boff) = ab;
+        *reinterpret_cast<float2*>(bias_m + boff) = bm;
+        *reinterpret_cast<float2*>(bias_v + boff) = bv;
+    } else {
+        *reinterpret_cast<float2*>(grad_bias + boff) = make_float2(ga, gb);
+    }
+}
+
 template <int VEC, int LPR, int NV, int LINK, int MODE, int FLAVOR>
 __global__ void __launch_bounds__(256, NV > 1 ? 2 : (FLAVOR == 0 ? 4 : VFMB_ADAM_MINB))
 k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
@@ -501,7 +526,9 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             AdamDev h, int32_t* __restrict__ adam_step, float kl_scale,
             float* __restrict__ grad_bias, float* __restrict__ grad_entity, FinalArgs fa) {
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
-    constexpr bool CUT = FLAVOR >= 1, KLF = FLAVOR == 2;
+        // CUT (rows cut by tile boundaries summed here) costs 16 registers = one resident block per SM,
+    // which slowed the kernel by more than k_combine_cut takes: off
+    constexpr bool CUT = false, KLF = FLAVOR == 2;
     const int U = meta[0];
     const int d = c.d, dp = c.d + 4;
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
@@ -531,8 +558,7 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
         const bool valid = lane < CH && ul < U;
 #endif
         int rowid_l = 0, tA_l = 0, P_l = 0;
-        float cfac_l = 0.f, cq_l = 0.f, gw_l = 0.f, eb_l = 0.f;
-        float2 ab = make_float2(0.f, 1.f), bm = make_float2(0.f, 0.f), bv = make_float2(0.f, 0.f);
+        float cfac_l = 0.f, klw_l = 0.f;                  // KL weight c_u, and c_u * KL(bias) of the lane's row
         if (valid) {
             const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
             rowid_l = rec.x;
@@ -544,22 +570,19 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
                 prefetch_row(entity_v + eoff, 8 * d);
             }
 #endif
-            cq_l = __ldg(cq + ul);
+            const float cq_l = __ldg(cq + ul);
             cfac_l = kl_scale * cq_l;
-            gw_l = __ldg(gws + ul);
-            // bias row: loaded here so that its DRAM latency overlaps the wide work below
-            const size_t boff = (size_t)rowid_l * 2;
-            ab = *reinterpret_cast<const float2*>(bias + boff);
-            eb_l = __ldg(eps_bias + ul);
-            if (MODE == VFMB_ADAM_TOUCHED) {
-                bm = *reinterpret_cast<const float2*>(bias_m + boff);
-                bv = *reinterpret_cast<const float2*>(bias_v + boff);
-            }
+            klw_l = cq_l;
             if (CUT) {                                     // tiles the row's segment spans beyond its first
                 tA_l = rec.z / kTile;
                 P_l = (rec.z + rec.y - 1) / kTile - tA_l;
-                if (P_l > kHotPartials) P_l = 0;           // hot row: k_combine<HOT_ONLY> finished it
+                if (P_l > kHotPartials) P_l = 0;           // hot row: k_combine_hot finished it
             }
+            // bias row now (nothing stays live across the wide work), unless the row is cut by a
+            // tile boundary: its g_w only exists after the group below has summed the partials
+            if (!CUT || P_l == 0)
+                bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, grad_bias, rowid_l, __ldg(gws + ul),
+                                             __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
         }
         float klrow = 0.f, gwh = 0.f;
         // ---- wide work: GPW rows per round
@@ -596,6 +619,9 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
                 for (int i = 0; i < NV; ++i) {
                     int k = (gl + i * LPR) * VEC;
                     if (k < d) {
+                        Vec<VEC> e;                         // the noise k_stage used for this row
+                        if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step);
+                        else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
                         Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
                         Vec<VEC> m1, m2, v1, v2;
                         if (MODE == VFMB_ADAM_TOUCHED) {
@@ -604,9 +630,6 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
                         }
                         Vec<VEC> g;
                         if (CUT && P > 0) g = gsum[i]; else g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
-                        Vec<VEC> e;                         // the noise k_stage used for this row
-                        if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step);
-                        else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
                         Vec<VEC> gmu, grho;
                         float quad = 0.f, prodv = 1.f;
 #pragma unroll
@@ -650,24 +673,13 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             if (KLF) hand_back<LPR>(klrow, kl, it, lane);
             if (CUT) hand_back<LPR>(gwh, gwc, it, lane);
         }
-        // ---- lane-parallel: bias row (after the wide work: a cut row's g_w comes from its group)
+        // ---- lane-parallel: KL of the rows; bias rows of the cut rows
         if (valid) {
-            if (CUT && P_l > 0) gw_l = gwh;
-            const size_t boff = (size_t)rowid_l * 2;
-            const float eb = eb_l;
-            const float tau = link_fn<LINK>(ab.y);
-            if (KLF) facc = fmaf(cq_l, klrow + kl_std_normal(ab.x, tau), facc);
-            const float ga = fmaf(cfac_l, ab.x, gw_l);
-            const float gb = link_grad<LINK>(ab.y) * fmaf(gw_l, eb, cfac_l * (tau - fast_rcp(tau)));
-            if (MODE == VFMB_ADAM_TOUCHED) {
-                adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
-                adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
-                *reinterpret_cast<float2*>(bias + boff) = ab;
-                *reinterpret_cast<float2*>(bias_m + boff) = bm;
-                *reinterpret_cast<float2*>(bias_v + boff) = bv;
-            } else {
-                *reinterpret_cast<float2*>(grad_bias + boff) = make_float2(ga, gb);
-            }
+            if (CUT && P_l > 0)
+                bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, grad_bias, rowid_l, gwh,
+                                             __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
+            // klw_l is now c_u * KL(bias row) (bias_update), klrow the entity part of the row's KL
+            if (KLF) facc += fmaf(__ldg(cq + ul), klrow, klw_l);
         }
     }
     if (FLAVOR >= 1) {
@@ -851,10 +863,7 @@ k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
                 ab = *reinterpret_cast<const float2*>(bias + boff);
                 bm = *reinterpret_cast<const float2*>(bias_m + boff);
                 bv = *reinterpret_cast<const float2*>(bias_v + boff);
-                tA_l = rec.z / kTile;
-                P_l = (rec.z + rec.y - 1) / kTile - tA_l;
-                if (P_l > kHotPartials) P_l = 0;           // hot row: k_combine<HOT_ONLY> finished it
-            }
+            }                                              // (cut rows: k_combine_cut finished them)
             const float cfac_l = kl_scale * cq_l;
             float* sp = s_ring + (size_t)st * stage_f;
             mbar_wait(&s_full[st], ph);
@@ -1115,10 +1124,8 @@ extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* t
     return launch_score(cfg, tab, plan, io, stream, 0);
 }
 
-// hot_only: k_combine finishes only the rows spanning > kHotPartials tiles; the other cut rows
-// are summed inside k_adam_rows<FLAVOR >= 1>
 static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
-                         const float* table, int32_t unit_coef, bool hot_only, vfmb_stream stream_) {
+                         const float* table, int32_t unit_coef, vfmb_stream stream_) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_gather", stream_, 1, &P);
     if (rc) return rc;
@@ -1139,12 +1146,10 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
             k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>(
                 cfg->d, cfg->F, N, plan->partner, plan->pos_rank, io->vs, tbl, io->rsorted, gslot, io->grow, io->gws);
         const size_t smem = 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float);
-        if (hot_only && plan->hot)
-            k_combine_hot<VEC, LPR, NV><<<32, 256, smem, stream>>>(
-                cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, plan->hot, gslot, io->vs, io->grow, io->gws);
-        else if (hot_only)
-            k_combine<VEC, LPR, NV, 1><<<grid_warps(cap.u_cap, 32), 256, smem, stream>>>(
-                cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
+        if (plan->hot)      // lists of the cut rows from the plan: no scan over the unique rows
+            k_combine_cut<VEC, LPR, NV><<<grid_warps(cap.n_tiles, 1), 256, smem, stream>>>(
+                cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, plan->hot, (int)cut_list_capacity(cap.n_tiles),
+                gslot, io->vs, io->grow, io->gws);
         else
             k_combine<VEC, LPR, NV, 0><<<grid_warps(cap.u_cap, 32), 256, smem, stream>>>(
                 cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
@@ -1155,7 +1160,7 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
 
 extern "C" int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
                                    const float* table, int32_t unit_coef, vfmb_stream stream) {
-    return launch_gather(cfg, plan, io, table, unit_coef, false, stream);
+    return launch_gather(cfg, plan, io, table, unit_coef, stream);
 }
 
 // flavor: see k_adam_rows
@@ -1278,7 +1283,7 @@ static int backward_impl(const vfmb_config* cfg, const vfmb_tables* tab, const v
         k_scatter_resid<<<g, 256, 0, stream>>>(io->resid, plan->pos_of, N, cfg->F, io->rsorted);
         CUDA_TRY(cudaGetLastError());
     }
-    rc = launch_gather(cfg, plan, io, nullptr, 0, true, stream_);
+    rc = launch_gather(cfg, plan, io, nullptr, 0, stream_);
     if (rc) return rc;
     return launch_adam(cfg, tab, plan, io, adam, mode, kl_grad_scale, flavor, stream_);
 }
@@ -1289,7 +1294,7 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
     return backward_impl(cfg, tab, plan, io, adam, mode, kl_grad_scale, 1, stream);
 }
 
-// The fused training step: 5 launches -- k_stage<LEAN>, k_score, k_gather, k_combine<HOT_ONLY>,
+// The fused training step: 5 launches -- k_stage<LEAN>, k_score, k_gather, k_combine_cut,
 // k_adam_rows<FLAVOR 2> (KL, scalar parameters and the step counter folded in).
 extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                  const vfmb_step_io* io, const vfmb_adam* adam, vfmb_stream stream) {

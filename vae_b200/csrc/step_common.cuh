@@ -197,6 +197,49 @@ __device__ __forceinline__ void sum_head_slots(const float* __restrict__ gslot, 
     }
 }
 
+// one row cut by few tile boundaries, summed by a warp: its GPW lane groups take contiguous slot
+// ranges; total = tail(tA) + group 0 + group 1 + ... (fixed order)
+template <int VEC, int LPR, int NV>
+__device__ __forceinline__ void combine_warp_row(int u, int tA, int tB, int d, int F,
+                                                 const float* __restrict__ gslot, const float* __restrict__ vs,
+                                                 float* __restrict__ grow, float* __restrict__ gws) {
+    constexpr int GPW = kWarp / LPR;
+    const int dp = d + 4;
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
+    const int per = (tB - tA + GPW - 1) / GPW;
+    const int lo = tA + 1 + gidx * per, hi = min(tB + 1, lo + per);
+    Vec<VEC> acc[NV]; float gw;
+    sum_head_slots<VEC, LPR, NV, 4>(gslot, dp, d, gl, lo, hi, acc, gw);
+    // total = tail(tA) + group 0 + group 1 + ...
+    const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
+    float gw_tot = __ldg(tp + d);
+#pragma unroll
+    for (int g = 0; g < GPW; ++g) gw_tot += __shfl_sync(0xffffffffu, gw, g * LPR);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        int k = (gl + i * LPR) * VEC;
+        Vec<VEC> tot;
+        if (k < d) tot = ld_vec_nc<VEC>(tp + k);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+#pragma unroll
+            for (int g = 0; g < GPW; ++g) {
+                float v = __shfl_sync(0xffffffffu, acc[i].v[j], g * LPR + gl);
+                if (k < d) tot.v[j] += v;
+            }
+        }
+        if (k < d && gidx == 0) {
+            if (F > 2) {                           // pairwise: sum r_n (S_n - v_u)
+                Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) tot.v[j] = fmaf(-gw_tot, own.v[j], tot.v[j]);
+            }
+            st_vec<VEC>(grow + (size_t)u * d + k, tot);
+        }
+    }
+    if (lane == 0) gws[u] = gw_tot;
+}
+
 // one hot row (> kHotPartials tile partials), summed by the whole block: 8*GPW lane groups over
 // contiguous slot ranges, then a fixed-order shared-memory reduction by one group
 template <int VEC, int LPR, int NV>
@@ -245,17 +288,25 @@ __device__ __forceinline__ void combine_hot_row(int u, int d, int F, const int32
     __syncthreads();
 }
 
-// the hot rows alone, from the plan's hot list (meta[3] entries): what the fused step launches --
-// the other cut rows are summed by their consumer (k_adam_rows<FLAVOR >= 1>)
+// every row cut by a tile boundary, from the plan's lists (no scan over the unique rows): the
+// `cut` list holds the rows with <= kHotPartials partials from its front (meta[5] entries, one
+// warp each), the hot rows from its back (meta[3] entries, one block each).
 template <int VEC, int LPR, int NV>
 __global__ void __launch_bounds__(256)
-k_combine_hot(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
-              const int32_t* __restrict__ hot, const float* __restrict__ gslot, const float* __restrict__ vs,
-              float* __restrict__ grow, float* __restrict__ gws) {
+k_combine_cut(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
+              const int32_t* __restrict__ cut, int cut_cap, const float* __restrict__ gslot,
+              const float* __restrict__ vs, float* __restrict__ grow, float* __restrict__ gws) {
     extern __shared__ float s_part[];                    // [8*GPW][d+4] block-level partial sums
-    const int n_hot = meta[3];
+    const int n_hot = meta[3], n_cut = meta[5];
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int i = gwarp; i < n_cut; i += nwarps) {
+        const int u = __ldg(cut + i);
+        const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
+        combine_warp_row<VEC, LPR, NV>(u, rec.z / kTile, (rec.z + rec.y - 1) / kTile, d, F, gslot, vs, grow, gws);
+    }
+    __syncthreads();
     for (int i = blockIdx.x; i < n_hot; i += gridDim.x)
-        combine_hot_row<VEC, LPR, NV>(__ldg(hot + i), d, F, urec, gslot, vs, grow, gws, s_part);
+        combine_hot_row<VEC, LPR, NV>(__ldg(cut + cut_cap - 1 - i), d, F, urec, gslot, vs, grow, gws, s_part);
 }
 
 template <int VEC, int LPR, int NV, int HOT_ONLY = 0>
@@ -291,38 +342,7 @@ k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restr
             todo &= todo - 1;
             const int u = base + src;
             const int tA = __shfl_sync(0xffffffffu, tA_l, src), tB = __shfl_sync(0xffffffffu, tB_l, src);
-            const int per = (tB - tA + GPW - 1) / GPW;
-            const int lo = tA + 1 + gidx * per, hi = min(tB + 1, lo + per);
-            Vec<VEC> acc[NV]; float gw;
-            sum_head_slots<VEC, LPR, NV, 4>(gslot, dp, d, gl, lo, hi, acc, gw);
-            // total = tail(tA) + group 0 + group 1 + ...
-            const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
-            float gw_tot = __ldg(tp + d);
-#pragma unroll
-            for (int g = 0; g < GPW; ++g) gw_tot += __shfl_sync(0xffffffffu, gw, g * LPR);
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                int k = (gl + i * LPR) * VEC;
-                Vec<VEC> tot;
-                if (k < d) tot = ld_vec_nc<VEC>(tp + k);
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-#pragma unroll
-                    for (int g = 0; g < GPW; ++g) {
-                        float v = __shfl_sync(0xffffffffu, acc[i].v[j], g * LPR + gl);
-                        if (k < d) tot.v[j] += v;
-                    }
-                }
-                if (k < d && gidx == 0) {
-                    if (F > 2) {                           // pairwise: sum r_n (S_n - v_u)
-                        Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) tot.v[j] = fmaf(-gw_tot, own.v[j], tot.v[j]);
-                    }
-                    st_vec<VEC>(grow + (size_t)u * d + k, tot);
-                }
-            }
-            if (lane == 0) gws[u] = gw_tot;
+            combine_warp_row<VEC, LPR, NV>(u, tA, tB, d, F, gslot, vs, grow, gws);
         }
         __syncthreads();
         // ---- whole block: hot rows

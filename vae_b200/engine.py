@@ -43,7 +43,7 @@ class BatchPlan:
         self.class_off = torch.zeros(L.MAX_FIELDS + 1, dtype=torch.int32, device=device)
         self.z = torch.zeros(L.MAX_FIELDS, dtype=torch.float32, device=device)
         self.meta = torch.zeros(8, dtype=torch.int32, device=device)
-        self.hot = torch.zeros(self.n_tiles // 30 + 2, dtype=torch.int32, device=device)
+        self.hot = torch.zeros(int(cap.cut_rows_cap), dtype=torch.int32, device=device)
         self.workspace = torch.empty(int(cap.workspace_bytes), dtype=torch.uint8, device=device)
         self.B = 0
         self.struct = L.Plan(L.ptr(self.uniq), L.ptr(self.inverse), L.ptr(self.seg_off),
