@@ -82,6 +82,7 @@ _P = C.POINTER
 SYMBOLS = {
     "vfmb_version": (C.c_int, []),
     "vfmb_profile_events": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vfmb_set_grid_reserve": (C.c_int, [C.c_int]),
     "vfmb_last_error": (C.c_char_p, []),
     "vfmb_closed_off_bias_prior_mean": (C.c_int32, [C.c_int32] * 3),
     "vfmb_closed_off_bias_prior_scale": (C.c_int32, [C.c_int32] * 3),

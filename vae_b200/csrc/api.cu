@@ -19,7 +19,16 @@ int set_error(int code, const char* fmt, ...) {
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop) { *start = g_prof_start; *stop = g_prof_stop; }
 
+static int g_grid_reserve = 0;
+int grid_reserve() { return g_grid_reserve; }
+
 }  // namespace vfmb
+
+extern "C" int vfmb_set_grid_reserve(int blocks_per_sm) {
+    if (blocks_per_sm < 0 || blocks_per_sm > 8) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_grid_reserve: 0..8");
+    vfmb::g_grid_reserve = blocks_per_sm;
+    return 0;
+}
 
 extern "C" int vfmb_profile_events(void* start_event, void* stop_event) {
     vfmb::g_prof_start = (cudaEvent_t)start_event;

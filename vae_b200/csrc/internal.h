@@ -19,6 +19,8 @@ constexpr int kPriorGrid = 2 * kNumSMs; // blocks that carry prior-gradient part
 static inline int64_t cut_list_capacity(int64_t n_tiles) { return n_tiles + n_tiles / (kHotPartials - 2) + 4; }
 
 int set_error(int code, const char* fmt, ...);
+// block slots per SM the persistent step kernels leave free (see vfmb_set_grid_reserve)
+int grid_reserve();
 // optional events around the dominant kernel (see vfmb_profile_events)
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
 

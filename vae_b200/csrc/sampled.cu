@@ -427,6 +427,162 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
     }
 }
 
+// ------------------------------------------------------------------------------- k_gather_score
+// F == 2 fused step: k_score and k_gather in one pass over the SORTED occurrence list.  An
+// occurrence (row u, sample n) needs the residual r_n = dloss/dpred_n and the partner row; the
+// partner row is being loaded anyway, so the group forms the score <v_u, v_partner> itself --
+// every sample is scored twice, once from each of its rows, with bit-identical results (products
+// and bias sums commute, the lane mapping and the shuffle tree are those of k_score).  The
+// occurrence of field 0 writes the sample's outputs and its likelihood terms.  Saves a launch, the
+// residual round trip through memory and one of the two passes over the sampled rows.
+template <int VEC, int LPR, int NV, int LINK, int LIK>
+__global__ void __launch_bounds__(256)
+k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__ partner,
+               const int32_t* __restrict__ pos_rank, const int32_t* __restrict__ occ,
+               const float* __restrict__ vs, const float* __restrict__ ws, const float* __restrict__ y,
+               const float* __restrict__ eps_global, const int32_t* __restrict__ adam_step,
+               float* __restrict__ pred, float* __restrict__ mean, float* __restrict__ resid,
+               float* __restrict__ gslot, float* __restrict__ grow, float* __restrict__ gws,
+               double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
+    constexpr int GPW = kWarp / LPR, UNR = 4;
+    const int d = c.d, B = c.B, N = 2 * c.B;
+    const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
+    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const int lane = threadIdx.x & 31, gl = lane % LPR;
+    const unsigned gmask = group_mask<LPR>();
+    const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
+    const int ngroups = gridDim.x * (blockDim.x >> 5) * GPW;
+    const int n_tiles = (N + kTile - 1) / kTile;
+    const float mu0 = scalars[VFMB_S_GB_MEAN];
+    const float sig0 = link_fn<LINK>(scalars[VFMB_S_GB_SCALE]);
+    const float w0 = mu0 + global_eps(eps_global, c, step) * sig0;
+    const float alpha = link_fn<LINK>(scalars[VFMB_S_ALPHA]);
+    const float half_log_alpha = 0.5f * logf(alpha);
+    const float scale = c.n_train / ((float)c.S * (float)B);
+    double acc3[3] = {0.0, 0.0, 0.0};                   // nll, resid, squared error (field-0 occurrences)
+
+    for (int tile = group; tile < n_tiles; tile += ngroups) {
+        const int t0 = tile * kTile, t1 = min(N, t0 + kTile);
+        const bool head_open = t0 > 0 && __ldg(pos_rank + t0 - 1) == __ldg(pos_rank + t0);
+        const bool tail_open = t1 < N && __ldg(pos_rank + t1) == __ldg(pos_rank + t1 - 1);
+        const int first_u = __ldg(pos_rank + t0), last_u = __ldg(pos_rank + t1 - 1);
+        int cur = first_u;
+        Vec<VEC> acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
+        float gw = 0.f;
+
+        auto flush = [&](int u) {
+            const bool open_h = head_open && u == first_u, open_t = tail_open && u == last_u;
+            float* dst; float* dstw;
+            if (open_h)      { dst = gslot + ((size_t)tile * 2) * dp;     dstw = dst + d; }
+            else if (open_t) { dst = gslot + ((size_t)tile * 2 + 1) * dp; dstw = dst + d; }
+            else             { dst = grow + (size_t)u * d;                dstw = gws + u; }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                int k = (gl + i * LPR) * VEC;
+                if (k < d) st_vec<VEC>(dst + k, acc[i]);
+            }
+            if (gl == 0) *dstw = gw;
+        };
+
+        for (int b0 = t0; b0 < t1; b0 += LPR) {
+            // ---- lane-parallel: one position per lane of the group
+            const int idx = b0 + gl;
+            const bool ok = idx < t1;
+            const int src = ok ? __ldg(partner + idx) : 0;
+            const int ur = ok ? __ldg(pos_rank + idx) : 0;
+            const int o = ok ? __ldg(occ + idx) : 1;
+            // bias sum in field order (as k_score: ws[rank of field 0] + ws[rank of field 1])
+            const float bs = ok ? ((o & 1) ? __ldg(ws + src) + __ldg(ws + ur) : __ldg(ws + ur) + __ldg(ws + src)) : 0.f;
+            const float yl = ok ? __ldg(y + (o >> 1)) : 0.f;
+            const int cnt = min(LPR, t1 - b0);
+            const int src0 = __shfl_sync(gmask, src, 0, LPR), ur0 = __shfl_sync(gmask, ur, 0, LPR);
+            for (int j = 0; j < cnt; j += UNR) {               // UNR row pairs in flight
+                int uj[UNR], sj[UNR];
+                Vec<VEC> t[UNR][NV], own[UNR][NV];
+#pragma unroll
+                for (int e = 0; e < UNR; ++e) {
+                    uj[e] = __shfl_sync(gmask, ur, (j + e) & (LPR - 1), LPR);
+                    sj[e] = __shfl_sync(gmask, src, (j + e) & (LPR - 1), LPR);
+                    if (j + e >= cnt) { sj[e] = src0; uj[e] = ur0; }
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        int k = (gl + i * LPR) * VEC;
+                        if (k < d) {
+                            t[e][i] = ld_vec_nc<VEC>(vs + (size_t)sj[e] * d + k);
+                            own[e][i] = ld_vec_nc<VEC>(vs + (size_t)uj[e] * d + k);   // L1 hit inside a segment
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < UNR; ++e) {
+                    if (j + e < cnt) {                         // group-uniform
+                        const int oj = __shfl_sync(gmask, o, (j + e) & (LPR - 1), LPR);
+                        const float bsj = __shfl_sync(gmask, bs, (j + e) & (LPR - 1), LPR);
+                        const float yn = __shfl_sync(gmask, yl, (j + e) & (LPR - 1), LPR);
+                        // field-0 row first, as k_score multiplies them (a * b is commutative; kept for clarity)
+                        float part = 0.f;
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            int k = (gl + i * LPR) * VEC;
+                            if (k < d)
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) part = fmaf(own[e][i].v[q], t[e][i].v[q], part);
+                        }
+                        part = group_sum<LPR>(part, gmask);
+                        const float p = w0 + bsj + part;
+                        float r, mu_out = p;
+                        if (LIK == VFMB_BERNOULLI) { mu_out = 1.f / (1.f + expf(-p)); r = scale * (mu_out - yn); }
+                        else r = scale * alpha * (p - yn);
+                        if (!(oj & 1) && gl == 0) {            // the field-0 occurrence owns the sample's outputs
+                            const int n = oj >> 1;
+                            const float err = yn - p;
+                            float nll;
+                            if (LIK == VFMB_GAUSSIAN) nll = 0.5f * alpha * err * err - half_log_alpha + 0.9189385332046727f;
+                            else nll = fmaxf(p, 0.f) - yn * p + log1pf(expf(-fabsf(p)));
+                            pred[n] = p; mean[n] = mu_out; resid[n] = r;
+                            acc3[0] += (double)nll; acc3[1] += (double)r; acc3[2] += (double)err * (double)err;
+                        }
+                        if (uj[e] != cur) {
+                            flush(cur);
+                            cur = uj[e];
+#pragma unroll
+                            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) acc[i].v[q] = 0.f;
+                            gw = 0.f;
+                        }
+                        gw += r;
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            int k = (gl + i * LPR) * VEC;
+                            if (k < d)
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) acc[i].v[q] = fmaf(r, t[e][i].v[q], acc[i].v[q]);
+                        }
+                    }
+                }
+            }
+        }
+        flush(cur);
+    }
+    if (block_partials<3>(acc3, partials, counter)) {
+        double tot[3];
+        final_sums<3>(partials, tot);
+        if (threadIdx.x == 0) {     // the KL is added by k_adam_rows<FLAVOR 2> (data term only here)
+            stats[VFMB_ST_NLL_MEAN] = (float)(tot[0] / (double)B);
+            stats[VFMB_ST_SUM_RESID] = (float)tot[1];
+            stats[VFMB_ST_SUM_SQERR] = (float)tot[2];
+            stats[VFMB_ST_LOSS] = (float)((double)c.n_train * tot[0] / (double)B);
+            stats[VFMB_ST_W0] = w0;
+            *counter = 0;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- k_adam_rows
 // Backward, phase B (the HBM-bound kernel of the step): per unique row, chain rule from
 // (g_v, g_w) to (mean, raw scale) + KL gradient, then Adam on the row -- parameters and both
@@ -1158,6 +1314,37 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
     return 0;
 }
 
+// F == 2 fused step: k_gather_score (score + ordered segmented sum) + k_combine_cut
+static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                               const vfmb_step_io* io, vfmb_stream stream_) {
+    Prep P;
+    int rc = prep(cfg, "vfmb_sampled_step", stream_, 2, &P);
+    if (rc) return rc;
+    if (!io->grow || !io->gws || !io->partials || !io->pred || !io->mean || !io->resid || !plan->hot || !plan->occ)
+        return set_error(VFMB_EINVAL, "vfmb_sampled_step: scratch required");
+    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
+    float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
+#define LAUNCH_GS(LINK, LIK)                                                                             \
+    k_gather_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_gather_score<VEC, LPR, NV, LINK, LIK>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>( \
+        dc, tab->scalars, plan->partner, plan->pos_rank, plan->occ, io->vs, io->ws, io->y, io->eps_global, \
+        tab->adam_step, io->pred, io->mean, io->resid, gslot, io->grow, io->gws, io->partials,           \
+        io->counters + 1, io->stats)
+    VFMB_LAYOUT_SWITCH(L, {
+        if (cfg->link == VFMB_LINK_ABS) {
+            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_GS(0, VFMB_GAUSSIAN); else LAUNCH_GS(0, VFMB_BERNOULLI);
+        } else {
+            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_GS(1, VFMB_GAUSSIAN); else LAUNCH_GS(1, VFMB_BERNOULLI);
+        }
+        const size_t smem = 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float);
+        k_combine_cut<VEC, LPR, NV><<<grid_warps(cap.n_tiles, 1), 256, smem, stream>>>(
+            cfg->d, cfg->F, plan->urec, plan->meta, plan->hot, (int)cut_list_capacity(cap.n_tiles),
+            gslot, io->vs, io->grow, io->gws);
+    });
+#undef LAUNCH_GS
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
                                    const float* table, int32_t unit_coef, vfmb_stream stream) {
     return launch_gather(cfg, plan, io, table, unit_coef, stream);
@@ -1299,13 +1486,22 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
 extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                  const vfmb_step_io* io, const vfmb_adam* adam, vfmb_stream stream) {
     if (io && !io->y) return set_error(VFMB_EINVAL, "vfmb_sampled_step: targets required");
-    static const int flavor = [] { const char* e = getenv("VFMB_STEP_FLAVOR"); return e ? atoi(e) : 2; }();
-    const bool lean = flavor == 2 && io && (io->eps_entity || true);
-    int rc = launch_stage(cfg, tab, plan, io, stream, lean);
+    int rc = launch_stage(cfg, tab, plan, io, stream, true);
     if (rc) return rc;
-    rc = launch_score(cfg, tab, plan, io, stream, lean ? 1 : 0);
+    // measured (ml20m): alone the fused kernel saves 5 us per step (104 -> 99 us); next to a
+    // concurrently running plan it loses 6 us -- it needs 111 registers per thread, which leaves no
+    // room on an SM for the plan's blocks.  So: fused unless the caller reserved room for the plan.
+    static const int fuse_env = [] { const char* e = getenv("VFMB_FUSE_SCORE"); return e ? atoi(e) : -1; }();
+    const bool fuse_gs = fuse_env >= 0 ? fuse_env != 0 : grid_reserve() == 0;
+    if (cfg && cfg->F == 2 && plan && plan->hot && fuse_gs) {
+        // F == 2: 4 launches -- k_stage<LEAN>, k_gather_score, k_combine_cut, k_adam_rows<FLAVOR 2>
+        rc = launch_gather_score(cfg, tab, plan, io, stream);
+        if (rc) return rc;
+        return launch_adam(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, 2, stream);
+    }
+    rc = launch_score(cfg, tab, plan, io, stream, 1);
     if (rc) return rc;
-    return backward_impl(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, lean ? 2 : 1, stream);
+    return backward_impl(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, 2, stream);
 }
 
 extern "C" int vfmb_adam_dense(float* p, float* m, float* v, const float* g, int64_t n, const vfmb_adam* adam,

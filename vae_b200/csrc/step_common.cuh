@@ -412,7 +412,10 @@ static inline int grid_resident(K kernel, int64_t units, int per_warp, size_t sm
     static const bool persistent = [] { const char* e = getenv("VFMB_PERSISTENT"); return !e || atoi(e) != 0; }();
     int64_t warps = (units + per_warp - 1) / per_warp;
     int64_t g = (warps + 7) / 8;
-    const int cap = persistent ? resident_blocks(kernel, 256, smem) : kGridCap;
+    // leave `reserve` block slots per SM free: room for the plan kernels running concurrently
+    const int reserve = grid_reserve();
+    int cap = persistent ? resident_blocks(kernel, 256, smem) : kGridCap;
+    if (persistent && reserve > 0 && cap / kNumSMs > reserve + 1) cap -= reserve * kNumSMs;
     if (g < 1) g = 1;
     if (g > cap) g = cap;
     return (int)g;

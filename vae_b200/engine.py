@@ -197,17 +197,23 @@ class GraphedLoop:
                 self.plans[s].build(self.cfg, self.xs[s], model.train_counts)
         torch.cuda.current_stream(self.device).wait_stream(warm)
         torch.cuda.synchronize(self.device)
-        for s in range(D):
-            nxt = (s + 1) % D
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                cur = torch.cuda.current_stream(self.device)
-                self.side.wait_stream(cur)                   # fork
-                with torch.cuda.stream(self.side):
-                    self.plans[nxt].build(self.cfg, self.xs[nxt], model.train_counts)
-                step_fn(self.plans[s], self.ys[s])           # main branch
-                cur.wait_stream(self.side)                   # join
-            self.graphs.append(g)
+        # the step kernels are captured one block slot per SM short of a full wave, so that the
+        # plan's blocks (side branch) are placed immediately instead of displacing step blocks
+        L.check(L.lib().vfmb_set_grid_reserve(1), "vfmb_set_grid_reserve")
+        try:
+            for s in range(D):
+                nxt = (s + 1) % D
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    cur = torch.cuda.current_stream(self.device)
+                    self.side.wait_stream(cur)                   # fork
+                    with torch.cuda.stream(self.side):
+                        self.plans[nxt].build(self.cfg, self.xs[nxt], model.train_counts)
+                    step_fn(self.plans[s], self.ys[s])           # main branch
+                    cur.wait_stream(self.side)                   # join
+                self.graphs.append(g)
+        finally:
+            L.lib().vfmb_set_grid_reserve(0)
 
     def stage(self, x: torch.Tensor, y: torch.Tensor) -> None:
         """Copy a batch (device or pinned host) into the next free staging slot."""
