@@ -346,6 +346,125 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
 
 
 # ------------------------------------------------------------------------------------------
+def run_sharded(args):
+    """N > 1: mode B -- tables row-sharded over the ranks (owner = row mod P), every rank feeds its
+    own batch of `batch` samples (weak scaling); per step 3 all-to-alls (ids, sampled rows, row
+    gradients) + 2 small all-reduces over NCCL.  The step on the global batch equals the
+    single-process step on that batch (tests/test_gpu_dp.py)."""
+    import torch.distributed as dist
+    from vae_b200.dist import ShardedSampled
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    w = synth.make_workload(args.workload, n_rows=args.rows)
+    B, F, d = w.batch, w.n_fields, w.d
+    n_batches = w.n_train // B
+    tc = w.train_counts()
+    tc[tc == 0] = 1                                            # rows never seen in training: weight 1 (SURVEY N9)
+    lr = 1.0 / (1 + w.n_train // B)
+    kl = "torch" if F == 2 else "group"
+    model = ShardedSampled(d, w.field_sizes, torch.from_numpy(tc), w.n_train, B, world, rank,
+                           output=w.output, kl_weighting=kl, seed=synth.NOISE_SEED, lr=lr, device=device,
+                           slack=args.slack)
+    x_all = torch.from_numpy(w.x[: n_batches * B]).to(device)
+    y_all = torch.from_numpy(w.y[: n_batches * B]).to(device)
+
+    def batch(i):
+        j = (i * world + rank) % n_batches
+        return x_all[j * B:(j + 1) * B], y_all[j * B:(j + 1) * B]
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = args.warmup, args.steps
+    for i in range(W):
+        out = model.step(*batch(i))
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(W, W + K):
+        out = model.step(*batch(i))
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    model.check_overflow()
+    loss = float(out["loss"].item())
+
+    # end to end: pinned host ids/targets -> device every step, loss/KL/NLL back every step
+    xh = torch.from_numpy(w.x[: n_batches * B]).pin_memory()
+    yh = torch.from_numpy(w.y[: n_batches * B]).pin_memory()
+    Ke = min(K, 200)
+    xd, yd = torch.empty((B, F), dtype=torch.int64, device=device), torch.empty(B, dtype=torch.float32, device=device)
+    res = torch.empty((Ke, 16), dtype=torch.float32).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Ke):
+        j = ((W + K + i) * world + rank) % n_batches
+        xd.copy_(xh[j * B:(j + 1) * B], non_blocking=True)
+        yd.copy_(yh[j * B:(j + 1) * B], non_blocking=True)
+        o = model.step(xd, yd)
+        res[i].copy_(o["stats"], non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e = e0.elapsed_time(e1)
+
+    # where the step time goes: CUDA events between the phases, over a few extra steps
+    model.enable_timing(True)
+    for i in range(W + K, W + K + 20):
+        model.step(*batch(i))
+    phases = {k: round(v, 4) for k, v in model.phase_times().items()}
+    model.enable_timing(False)
+
+    # unique rows of the GLOBAL batches (outside the timed region) for the algorithmic bytes
+    us = []
+    for i in range(W, W + min(K, 16)):
+        xb = batch(i)[0].reshape(-1)
+        allx = [torch.empty_like(xb) for _ in range(world)]
+        dist.all_gather(allx, xb)
+        us.append(int(torch.unique(torch.cat(allx)).numel()))
+    U = float(np.mean(us))
+    t = torch.tensor([ms, ms_e], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e = float(t[0].item()), float(t[1].item())
+    if rank == 0:
+        peak, peak_src = peaks()
+        # per step: every rank reads its ids/targets and writes predictions; every touched row of the
+        # global batch is read and written once by its owner (parameters + both moments)
+        step_bytes = world * B * (8 * F + 8) + U * ((2 * d + 2) * 4 * 6 + 8)
+        a2a = model.M * (2 * 4 + 2 * (d + 1) * 4)
+        out_json = {
+            "metric": METRIC, "value": K * B * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{w.name}: {'+'.join(map(str, w.field_sizes))} rows, d={d}, batch {B} per GPU, "
+                                   f"{w.variant} ELBO, {w.output}",
+                       "fields": F, "unique_rows_per_global_step": U, "adam": "touched rows (lazy), on the owner",
+                       "noise": "Philox4x32-10 in-kernel, keyed by the global row id (rank-invariant)",
+                       "plan": "built every step on the step's stream (requester and owner side)",
+                       "l2": "consecutive distinct batches, no flush",
+                       "parallelism": f"sharded{world}: rows r mod {world}; per step 3 NCCL all-to-alls (ids, sampled "
+                                      f"rows, row gradients; {a2a / 1e6:.1f} MB padded slots per rank) + 2 small "
+                                      f"all-reduces; global batch {B * world}"},
+            "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": step_bytes / (ms / K * 1e-3) / 1e9,
+                         "peak": peak * world, "unit": "GB/s", "frac": step_bytes / (ms / K * 1e-3) / 1e9 / (peak * world),
+                         "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes": step_bytes},
+            "e2e": {"value": Ke * B * world / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * F * 8 + B * 4,
+                    "d2h_bytes_per_step": 16 * 4, "steps": Ke, "ms_per_step": ms_e / Ke},
+            "gpu_launches": None, "clocks": clocks, "final_loss": loss, "phase_ms": phases,
+        }
+        print(json.dumps(out_json), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
 def cpu_baseline(args, budget_s=20.0):
     """The oracle port (torch CPU, same ATen ops as the reference: unique, embedding, distributions,
     autograd, dense Adam) on this box's host cores, on a bounded number of full-size steps."""
@@ -420,10 +539,17 @@ def main():
     ap.add_argument("--plan", default="graph", choices=["inline", "prefetch", "graph", "cached"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--parallel", default="auto", choices=["auto", "dp", "sharded"],
+                    help="N>1: dp = replicated tables + dense all-reduce (mode A), sharded = row-sharded tables + "
+                         "all-to-all (mode B); auto = sharded unless the dense gradient is under 8 MB")
+    ap.add_argument("--slack", type=float, default=0.75, help="mode B: slot capacity as a fraction of B*F/P")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args)
+    elif world > 1 and (args.parallel == "sharded" or (args.parallel == "auto" and args.workload != "ml100k")):
+        run_sharded(args)
     else:
         run_ours(args)
 

@@ -210,6 +210,38 @@ int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfm
 int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                            const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
                            float kl_grad_scale, vfmb_stream stream);
+/* ---- mode B (row-sharded tables, owner = row mod P): glue between the plan / step kernels and the
+ * three all-to-alls of a step.  No reference counterpart (the reference is single-process); the
+ * contract is that the sharded step on the global batch equals the single-process step.
+ * Slot layout of every exchange buffer: [P, CAP, w] -- slot q*CAP + j holds the j-th unique id
+ * (ascending) this rank asks of owner q; w = 2 int32 {id, local batch count} for requests (-1 =
+ * empty), d+1 floats {row, bias} for sampled rows and for row gradients (zeros = empty).         */
+int64_t vfmb_shard_bucket_workspace(int32_t u_cap);
+/* requester: unique ids of `plan` -> request slots `send` [P*CAP,2]; dest[u] = slot of unique rank
+ * u (P*CAP = none); *overflow |= 1 when an owner's bucket exceeds CAP                             */
+int vfmb_shard_bucket(const vfmb_plan* plan, int32_t u_cap, int32_t P, int32_t CAP, int32_t* send,
+                      int32_t* dest, int32_t* overflow, void* workspace, vfmb_stream stream);
+/* owner: received requests -> local row indices loc [M] (int64, the plan's input; padding -> R_loc) */
+int vfmb_shard_owner_ids(const int32_t* recv, int32_t M, int32_t P, int32_t R_loc, int64_t* loc,
+                         vfmb_stream stream);
+/* owner: counts_only != 0 -> urec[u].w = batch count of row u summed over the requesters;
+ *        counts_only == 0 -> reply[s] = {vs[inverse[s]], ws[inverse[s]]} for every slot s           */
+int vfmb_shard_owner_pack(const vfmb_plan* plan_o, const int32_t* recv, int32_t M, int32_t d,
+                          const float* vs, const float* ws, float* reply, int32_t counts_only,
+                          vfmb_stream stream);
+/* requester: received sampled rows -> vs / ws in unique-rank order                                  */
+int vfmb_shard_unpack_rows(const vfmb_plan* plan_l, const float* recv_rows, const int32_t* dest,
+                           int32_t u_cap, int32_t M, int32_t d, float* vs, float* ws, vfmb_stream stream);
+/* requester: row gradients -> slots; tail[tail_idx[0..3]] = {NLL sum, residual sum, squared-error
+ * sum of this rank's samples, KL sum of this rank's owned rows} (tail_idx: host array of 4)         */
+int vfmb_shard_pack_grads(const vfmb_plan* plan_l, const float* grow, const float* gws, const int32_t* dest,
+                          int32_t u_cap, int32_t M, int32_t d, float* out, const float* stats_local,
+                          const float* stats_owner, float n_local, float* tail, const int32_t* tail_idx,
+                          int32_t n_tail, vfmb_stream stream);
+/* owner: received gradient slots -> gather table [M,d] + bias gradients in sorted-occurrence order  */
+int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, int32_t M, int32_t d,
+                            float* table, float* rsorted, vfmb_stream stream);
+
 int vfmb_dp_final(const vfmb_config* cfg_global, const vfmb_tables* tab, const float* tail,
                   const float* eps_global, const vfmb_adam* adam, float* stats, vfmb_stream stream);
 

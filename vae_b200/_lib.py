@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # experiment hook: VFMB_VARIANT=name + VFMB_NVCC_EXTRA="-DX=1 ..." builds / loads libvfm_b200_name.so
 _VARIANT = os.environ.get("VFMB_VARIANT", "")
 LIB_PATH = os.path.join(_HERE, f"libvfm_b200{'_' + _VARIANT if _VARIANT else ''}.so")
-SOURCES = ["api.cu", "plan.cu", "sampled.cu", "closed.cu", "dp.cu"]
+SOURCES = ["api.cu", "plan.cu", "sampled.cu", "closed.cu", "dp.cu", "shard.cu"]
 HEADERS = ["common.cuh", "internal.h", "step_common.cuh", os.path.join(_ROOT, "include", "vfm_b200.h")]
 # -prec-div/-prec-sqrt=false: MUFU-based division and square root (<= 2 ulp) instead of the IEEE
 # slow paths, which made the Adam epilogue instruction-bound; denormals and expf/logf stay precise
@@ -107,6 +107,18 @@ SYMBOLS = {
     "vfmb_dp_apply_sampled": (C.c_int, [_P(Config), _P(Tables), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, _P(Adam), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
+    "vfmb_shard_bucket_workspace": (C.c_int64, [C.c_int32]),
+    "vfmb_shard_bucket": (C.c_int, [_P(Plan), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "vfmb_shard_owner_ids": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vfmb_shard_owner_pack": (C.c_int, [_P(Plan), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p]),
+    "vfmb_shard_unpack_rows": (C.c_int, [_P(Plan), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "vfmb_shard_pack_grads": (C.c_int, [_P(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_void_p]),
+    "vfmb_shard_unpack_grads": (C.c_int, [_P(Plan), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vfmb_adam_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   _P(Adam), C.c_void_p, C.c_void_p]),
     "vfmb_adam_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1,0 +1,277 @@
+// Mode B (row-sharded tables) -- the glue between the plan / step kernels and
+// the three all-to-alls of a step, as own kernels instead of framework tensor ops:
+//
+//   requester   vfmb_shard_bucket        unique ids -> fixed-capacity slots per owner (id mod P)
+//   owner       vfmb_shard_owner_ids     received ids -> local row indices (plan input)
+//               vfmb_shard_owner_pack    summed batch counts; sampled rows -> reply slots
+//   requester   vfmb_shard_unpack_rows   reply slots -> sampled-row scratch in unique-rank order
+//               vfmb_shard_pack_grads    row gradients -> slots; additive scalars of the rank
+//   owner       vfmb_shard_unpack_grads  received gradient rows -> gather table + coefficients
+//
+// Slot layout of every exchange: [P, CAP, w] (w = 2 ints for ids, d+1 floats for rows), slot
+// q*CAP + j holds the j-th id (ascending) this rank asks of owner q; -1 / zeros = empty.
+#include "common.cuh"
+#include "internal.h"
+
+namespace vfmb {
+
+constexpr int kBkt = 256;          // threads per block
+constexpr int kBktTile = 1024;     // unique ids per block
+
+__device__ __forceinline__ int owner_of(int id, int P) { return id % P; }
+
+// ---- bucket, pass 1: ids per owner in every tile of the sorted unique list
+__global__ void __launch_bounds__(kBkt)
+k_bucket_count(const int32_t* __restrict__ uniq, const int32_t* __restrict__ meta, int P,
+               int32_t* __restrict__ blk_cnt /*[nblk][8]*/) {
+    __shared__ int s_cnt[kMaxFields];
+    const int U = meta[0];
+    if (threadIdx.x < kMaxFields) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int lo = blockIdx.x * kBktTile;
+    for (int c = 0; c < kBktTile; c += kBkt) {
+        const int u = lo + c + threadIdx.x;
+        const int q = u < U ? owner_of(uniq[u], P) : -1;
+        for (int k = 0; k < P; ++k) {
+            const unsigned b = __ballot_sync(0xffffffffu, q == k);
+            if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_cnt[k], __popc(b));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxFields) blk_cnt[blockIdx.x * kMaxFields + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// ---- bucket, pass 2: slot of every unique rank (stable inside an owner), request records
+__global__ void __launch_bounds__(kBkt)
+k_bucket_place(const int32_t* __restrict__ uniq, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
+               int u_cap, int P, int CAP, const int32_t* __restrict__ blk_cnt, int32_t* __restrict__ send,
+               int32_t* __restrict__ dest, int32_t* __restrict__ overflow) {
+    __shared__ int s_base[kMaxFields];
+    __shared__ int s_w[kBkt / 32][kMaxFields];
+    const int U = meta[0], M = P * CAP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < kMaxFields) {
+        int b = 0;
+        for (int i = 0; i < (int)blockIdx.x; ++i) b += blk_cnt[i * kMaxFields + threadIdx.x];
+        s_base[threadIdx.x] = b;
+    }
+    __syncthreads();
+    const int lo = blockIdx.x * kBktTile;
+    for (int c = 0; c < kBktTile; c += kBkt) {
+        const int u = lo + c + threadIdx.x;
+        const bool valid = u < U;
+        const int id = valid ? uniq[u] : 0;
+        const int q = valid ? owner_of(id, P) : -1;
+        int rank = 0;
+        for (int k = 0; k < P; ++k) {
+            const unsigned b = __ballot_sync(0xffffffffu, q == k);
+            if (q == k) rank = __popc(b & ((1u << lane) - 1u));
+            if (lane == 0) s_w[warp][k] = __popc(b);
+        }
+        __syncthreads();
+        int slot = M;
+        if (valid) {
+            int off = s_base[q];
+            for (int w = 0; w < warp; ++w) off += s_w[w][q];
+            const int ord = off + rank;
+            if (ord < CAP) slot = q * CAP + ord; else atomicOr(overflow, 1);
+            if (slot < M) {
+                send[2 * slot] = id;
+                send[2 * slot + 1] = urec[4 * (size_t)u + 1];     // occurrences in this rank's batch
+            }
+        }
+        if (u < u_cap) dest[u] = slot;
+        __syncthreads();
+        if (threadIdx.x < P) {
+            int tot = 0;
+            for (int w = 0; w < kBkt / 32; ++w) tot += s_w[w][threadIdx.x];
+            s_base[threadIdx.x] += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- owner: received global ids -> local row index (padding -> the sentinel row R_loc)
+__global__ void __launch_bounds__(256)
+k_owner_ids(const int32_t* __restrict__ recv, int M, int P, int R_loc, int64_t* __restrict__ loc) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < M; s += gridDim.x * blockDim.x) {
+        const int id = recv[2 * s];
+        loc[s] = id >= 0 ? (int64_t)(id / P) : (int64_t)R_loc;
+    }
+}
+
+// ---- owner: batch count of a row summed over the requesting ranks (integers, fixed order)
+__global__ void __launch_bounds__(256)
+k_owner_counts(const int32_t* __restrict__ recv, const int32_t* __restrict__ occ, const int32_t* __restrict__ meta,
+               int32_t* __restrict__ urec) {
+    const int U = meta[0];
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
+        int len = urec[4 * (size_t)u + 1];
+        const int seg = urec[4 * (size_t)u + 2];
+        // a real row is requested at most once per rank; the padding slots all share the sentinel
+        // row (tens of thousands of occurrences, count 0): only look at the first few
+        if (len > kMaxFields) len = recv[2 * occ[seg]] >= 0 ? kMaxFields : 0;
+        int tot = 0;
+        for (int i = 0; i < len; ++i) {
+            const int s = occ[seg + i];
+            tot += recv[2 * s] >= 0 ? recv[2 * s + 1] : 0;
+        }
+        urec[4 * (size_t)u + 3] = tot;
+    }
+}
+
+// ---- rows <-> slots: one warp per slot / unique rank, d+1 floats (sampled row | bias)
+__global__ void __launch_bounds__(256)
+k_pack_rows(const float* __restrict__ vs, const float* __restrict__ ws, const int32_t* __restrict__ inverse,
+            int M, int d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    for (int s = gw; s < M; s += nw) {
+        const int u = __ldg(inverse + s);
+        const float* src = vs + (size_t)u * d;
+        float* dst = out + (size_t)s * (d + 1);
+        for (int k = lane; k < d; k += 32) dst[k] = __ldg(src + k);
+        if (lane == 0) dst[d] = __ldg(ws + u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack_rows(const float* __restrict__ recv, const int32_t* __restrict__ dest, const int32_t* __restrict__ meta,
+              int M, int d, float* __restrict__ vs, float* __restrict__ ws) {
+    const int U = meta[0];
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    for (int u = gw; u < U; u += nw) {
+        const int s = min(__ldg(dest + u), M - 1);
+        const float* src = recv + (size_t)s * (d + 1);
+        float* dst = vs + (size_t)u * d;
+        for (int k = lane; k < d; k += 32) dst[k] = __ldg(src + k);
+        if (lane == 0) ws[u] = __ldg(src + d);
+    }
+}
+
+// gradients of the requester's unique rows -> slots (empty slots were zeroed by the caller);
+// thread 0 also assembles the additive scalars of this rank
+__global__ void __launch_bounds__(256)
+k_pack_grads(const float* __restrict__ grow, const float* __restrict__ gws, const int32_t* __restrict__ dest,
+             const int32_t* __restrict__ meta, int M, int d, float* __restrict__ out,
+             const float* __restrict__ stats_l, const float* __restrict__ stats_o, float n_local,
+             float* __restrict__ tail, int t_nll, int t_resid, int t_sqerr, int t_klrows, int n_tail) {
+    const int U = meta[0];
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x < n_tail) {
+        float v = 0.f;
+        const int t = threadIdx.x;
+        if (t == t_nll) v = stats_l[VFMB_ST_NLL_MEAN] * n_local;
+        else if (t == t_resid) v = stats_l[VFMB_ST_SUM_RESID];
+        else if (t == t_sqerr) v = stats_l[VFMB_ST_SUM_SQERR];
+        else if (t == t_klrows) v = stats_o[VFMB_ST_KL_ROWS];
+        tail[t] = v;
+    }
+    for (int u = gw; u < U; u += nw) {
+        const int s = __ldg(dest + u);
+        if (s >= M) continue;                              // overflowed (flagged at bucketing)
+        const float* src = grow + (size_t)u * d;
+        float* dst = out + (size_t)s * (d + 1);
+        for (int k = lane; k < d; k += 32) dst[k] = __ldg(src + k);
+        if (lane == 0) dst[d] = __ldg(gws + u);
+    }
+}
+
+// owner: received [M, d+1] -> gather table [M, d] (16-byte aligned rows) and the per-position
+// coefficient (the bias gradient) in the plan's sorted-occurrence order
+__global__ void __launch_bounds__(256)
+k_unpack_grads(const float* __restrict__ recv, const int32_t* __restrict__ occ, int M, int d,
+               float* __restrict__ table, float* __restrict__ rsorted) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    for (int s = gw; s < M; s += nw) {
+        const float* src = recv + (size_t)s * (d + 1);
+        float* dst = table + (size_t)s * d;
+        for (int k = lane; k < d; k += 32) dst[k] = __ldg(src + k);
+        if (lane == 0) rsorted[s] = __ldg(recv + (size_t)__ldg(occ + s) * (d + 1) + d);
+    }
+}
+
+static inline int warp_grid(int64_t items) {
+    int64_t g = (items + 7) / 8;
+    if (g < 1) g = 1;
+    if (g > 8 * kNumSMs) g = 8 * kNumSMs;
+    return (int)g;
+}
+
+}  // namespace vfmb
+
+using namespace vfmb;
+
+extern "C" int64_t vfmb_shard_bucket_workspace(int32_t u_cap) {
+    return (int64_t)((u_cap + kBktTile - 1) / kBktTile) * kMaxFields * 4;
+}
+
+extern "C" int vfmb_shard_bucket(const vfmb_plan* plan, int32_t u_cap, int32_t P, int32_t CAP, int32_t* send,
+                                 int32_t* dest, int32_t* overflow, void* workspace, vfmb_stream stream_) {
+    if (!plan || !send || !dest || !overflow || !workspace || P < 1 || P > kMaxFields || CAP < 1 || u_cap < 1)
+        return set_error(VFMB_EINVAL, "vfmb_shard_bucket: bad argument (1 <= P <= %d)", kMaxFields);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int nblk = (u_cap + kBktTile - 1) / kBktTile;
+    CUDA_TRY(cudaMemsetAsync(send, 0xFF, (size_t)P * CAP * 2 * sizeof(int32_t), stream));   // -1: empty slot
+    k_bucket_count<<<nblk, kBkt, 0, stream>>>(plan->uniq, plan->meta, P, (int32_t*)workspace);
+    k_bucket_place<<<nblk, kBkt, 0, stream>>>(plan->uniq, plan->urec, plan->meta, u_cap, P, CAP,
+                                              (const int32_t*)workspace, send, dest, overflow);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_shard_owner_ids(const int32_t* recv, int32_t M, int32_t P, int32_t R_loc, int64_t* loc,
+                                    vfmb_stream stream_) {
+    if (!recv || !loc || M < 1 || P < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_ids: bad argument");
+    k_owner_ids<<<(M + 255) / 256 > 2 * kNumSMs ? 2 * kNumSMs : (M + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(recv, M, P, R_loc, loc);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_shard_owner_pack(const vfmb_plan* plan_o, const int32_t* recv, int32_t M, int32_t d,
+                                     const float* vs, const float* ws, float* reply, int32_t counts_only,
+                                     vfmb_stream stream_) {
+    if (!plan_o || !recv || M < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_pack: bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (counts_only) {
+        k_owner_counts<<<2 * kNumSMs, 256, 0, stream>>>(recv, plan_o->occ, plan_o->meta, plan_o->urec);
+    } else {
+        if (!vs || !ws || !reply || d < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_pack: bad argument");
+        k_pack_rows<<<warp_grid(M), 256, 0, stream>>>(vs, ws, plan_o->inverse, M, d, reply);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_shard_unpack_rows(const vfmb_plan* plan_l, const float* recv_rows, const int32_t* dest,
+                                      int32_t u_cap, int32_t M, int32_t d, float* vs, float* ws, vfmb_stream stream_) {
+    if (!plan_l || !recv_rows || !dest || !vs || !ws) return set_error(VFMB_EINVAL, "vfmb_shard_unpack_rows: bad argument");
+    k_unpack_rows<<<warp_grid(u_cap), 256, 0, (cudaStream_t)stream_>>>(recv_rows, dest, plan_l->meta, M, d, vs, ws);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_shard_pack_grads(const vfmb_plan* plan_l, const float* grow, const float* gws, const int32_t* dest,
+                                     int32_t u_cap, int32_t M, int32_t d, float* out, const float* stats_local,
+                                     const float* stats_owner, float n_local, float* tail, const int32_t* tail_idx,
+                                     int32_t n_tail, vfmb_stream stream_) {
+    if (!plan_l || !grow || !gws || !dest || !out || !stats_local || !stats_owner || !tail || !tail_idx || n_tail > 256)
+        return set_error(VFMB_EINVAL, "vfmb_shard_pack_grads: bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)M * (d + 1) * sizeof(float), stream));
+    k_pack_grads<<<warp_grid(u_cap), 256, 0, stream>>>(grow, gws, dest, plan_l->meta, M, d, out, stats_local, stats_owner,
+                                                       n_local, tail, tail_idx[0], tail_idx[1], tail_idx[2], tail_idx[3], n_tail);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, int32_t M, int32_t d,
+                                       float* table, float* rsorted, vfmb_stream stream_) {
+    if (!plan_o || !recv_g || !table || !rsorted) return set_error(VFMB_EINVAL, "vfmb_shard_unpack_grads: bad argument");
+    k_unpack_grads<<<warp_grid(M), 256, 0, (cudaStream_t)stream_>>>(recv_g, plan_o->occ, M, d, table, rsorted);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -165,8 +165,9 @@ def bucket_by_owner(ids: torch.Tensor, cnt: torch.Tensor, n_valid: torch.Tensor,
     dev = ids.device
     valid = torch.arange(ids.numel(), device=dev) < n_valid
     owner = torch.where(valid, ids % P, torch.zeros_like(ids)).long()
-    onehot = (owner[:, None] == torch.arange(P, device=dev)[None, :]) & valid[:, None]
-    ordinal = (onehot.cumsum(0, dtype=torch.int32) - 1).gather(1, owner[:, None]).squeeze(1).long()
+    # [P, n] layout: the scan runs along the contiguous dimension (a [n, P] cumsum over dim 0 took 8 ms)
+    onehot = (owner[None, :] == torch.arange(P, device=dev)[:, None]) & valid[None, :]
+    ordinal = (onehot.cumsum(1, dtype=torch.int32) - 1).gather(0, owner[None, :]).squeeze(0).long()
     over = valid & (ordinal >= CAP)
     ok = valid & ~over
     dest = torch.where(ok, owner * CAP + ordinal, torch.full_like(owner, M))
@@ -253,10 +254,12 @@ class ShardedSampled:
             scal[L.S_ALPHA], scal[L.S_GB_MEAN], scal[L.S_GB_SCALE] = (float(init["alpha"]), float(init["global_bias_mean"]),
                                                                        float(init["global_bias_scale"]))
         else:
-            g = torch.Generator().manual_seed(seed * 1000003 + p)
-            bias = torch.randn(Rl, 2, generator=g); ent = torch.randn(Rl, 2 * d, generator=g)
+            # random init straight on the device: a shard of the 100 M-row table is tens of GB
+            g = torch.Generator(device=dev).manual_seed(seed * 1000003 + p)
+            bias = torch.randn(Rl, 2, generator=g, device=dev)
+            ent = torch.randn(Rl, 2 * d, generator=g, device=dev)
             scal = torch.tensor([0.5, 0.0, 1.0, 0.0])
-        bias[len(mine):] = torch.tensor([0.0, 1.0])           # unused + sentinel rows: KL minimum
+        bias[len(mine):] = torch.tensor([0.0, 1.0], device=bias.device)   # unused + sentinel rows: KL minimum
         ent[len(mine):, :d] = 0.0
         ent[len(mine):, d:] = 1.0
         z = torch.zeros_like
@@ -279,9 +282,16 @@ class ShardedSampled:
         self.plan_o = BatchPlan(self.M, 1, Rl, dev)
         self.buf_o = StepBuffers(self.cfg_o, self.plan_o, dev, L.S_COUNT, need_msg=False)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._ar_P = torch.arange(P, device=dev)
-        self._ar_U = torch.arange(u_cap, device=dev)
         self.tail = torch.zeros(DP_TAIL, dtype=torch.float32, device=dev)
+        # exchange buffers (slot layout [P, CAP, w]) and glue scratch, allocated once
+        M = self.M
+        i32 = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=dev)
+        f32 = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        self._send, self._dest = i32(M, 2), i32(u_cap)
+        self._bws = torch.zeros(int(L.lib().vfmb_shard_bucket_workspace(u_cap)), dtype=torch.uint8, device=dev)
+        self._loc = torch.zeros((M, 1), dtype=torch.int64, device=dev)
+        self._reply, self._gsend, self._table = f32(M, d + 1), f32(M, d + 1), f32(M, d)
+        self._tail_idx = (C.c_int32 * 4)(T_NLL, T_RESID, T_SQERR, T_KLROWS)
 
     def _cfg(self, B, F, R, n_train, bounds, sizes, seed, stride, off):
         cfg = make_config(B, F, self.d, R, 1, self.output, self.link, bounds, sizes, n_train, seed)
@@ -302,24 +312,24 @@ class ShardedSampled:
         x = x.to(self.device).contiguous()
         self.plan_l.build(self.cfg_l, x, self.train_counts)
         pl = self.plan_l
-        send, self._dest, over = bucket_by_owner(pl.uniq, pl.urec.view(-1, 4)[:, 1], pl.meta[0], P, CAP)
-        self.overflow += over.int()
-        return send[:M].view(P, CAP, 2).contiguous(), pl.z.clone()
+        L.check(L.lib().vfmb_shard_bucket(C.byref(pl.struct), pl.u_cap, P, CAP, self._send.data_ptr(),
+                                          self._dest.data_ptr(), self.overflow.data_ptr(), self._bws.data_ptr(),
+                                          current_stream(self.device)), "vfmb_shard_bucket")
+        return self._send.view(P, CAP, 2), pl.z.clone()
 
     @torch.no_grad()
     def phase_owner_stage(self, recv: torch.Tensor, z_global: torch.Tensor) -> torch.Tensor:
         """Owner: plan the received ids, global batch counts, sample the rows.  Returns the reply
         [P,CAP,d+1] (sampled factor row | sampled bias) in the slot layout of the request."""
         M, d, P, p = self.M, self.d, self.P, self.p
-        ids, cnts = recv.reshape(M, 2)[:, 0], recv.reshape(M, 2)[:, 1]
-        real = ids >= 0
-        loc = torch.where(real, ids // P, torch.full_like(ids, self.R_loc)).long().view(M, 1).contiguous()
-        po, bo = self.plan_o, self.buf_o
-        po.build(self.cfg_o, loc, self.train_counts_loc)
-        self._inv_o = po.inverse[:M].long()
-        gcnt = torch.zeros(po.u_cap, dtype=torch.float32, device=self.device)
-        gcnt.index_add_(0, self._inv_o, torch.where(real, cnts, torch.zeros_like(cnts)).float())   # integers: exact
-        po.urec.view(-1, 4)[:, 3] = gcnt.int()              # batch count summed over the ranks
+        recv = recv.contiguous()
+        self._recv_ids = recv
+        po, bo, lib, s = self.plan_o, self.buf_o, L.lib(), current_stream(self.device)
+        L.check(lib.vfmb_shard_owner_ids(recv.data_ptr(), M, P, self.R_loc, self._loc.data_ptr(), s), "vfmb_shard_owner_ids")
+        po.build(self.cfg_o, self._loc, self.train_counts_loc)
+        # batch count of every owned row summed over the requesting ranks -> urec[:, 3]
+        L.check(lib.vfmb_shard_owner_pack(C.byref(po.struct), recv.data_ptr(), M, d, None, None, None, 1, s),
+                "vfmb_shard_owner_pack")
         po.z.copy_(z_global)
         noise = None
         if self.noise_tables is not None:                     # tests: per-entity noise tables
@@ -330,8 +340,9 @@ class ShardedSampled:
         self._io_o = bo.io(noise=noise)
         L.check(L.lib().vfmb_sampled_stage(C.byref(self.cfg_o), C.byref(self._tables()), C.byref(po.struct),
                                            C.byref(self._io_o), current_stream(self.device)), "vfmb_sampled_stage")
-        rows = bo.vs.view(po.u_cap, d)[self._inv_o]
-        return torch.cat((rows, bo.ws[self._inv_o][:, None]), dim=1).view(P, self.CAP, d + 1).contiguous()
+        L.check(lib.vfmb_shard_owner_pack(C.byref(po.struct), recv.data_ptr(), M, d, bo.vs.data_ptr(), bo.ws.data_ptr(),
+                                          self._reply.data_ptr(), 0, s), "vfmb_shard_owner_pack")
+        return self._reply.view(P, self.CAP, d + 1)
 
     @torch.no_grad()
     def phase_local(self, recv_rows: torch.Tensor):
@@ -339,9 +350,10 @@ class ShardedSampled:
         Returns (row gradients [P,CAP,d+1] in slot layout, additive scalars tail [16])."""
         M, d, P = self.M, self.d, self.P
         pl, bl = self.plan_l, self.buf_l
-        got = recv_rows.reshape(M, d + 1)[self._dest.clamp(max=M - 1)]
-        bl.vs.view(pl.u_cap, d).copy_(got[:, :d])
-        bl.ws.copy_(got[:, d])
+        recv_rows = recv_rows.contiguous()
+        lib, s = L.lib(), current_stream(self.device)
+        L.check(lib.vfmb_shard_unpack_rows(C.byref(pl.struct), recv_rows.data_ptr(), self._dest.data_ptr(), pl.u_cap, M, d,
+                                           bl.vs.data_ptr(), bl.ws.data_ptr(), s), "vfmb_shard_unpack_rows")
         e0 = self.noise_tables[0].reshape(1).contiguous() if self.noise_tables is not None else None
         io = bl.io(y=self._y)
         io.eps_global = L.ptr(e0)
@@ -351,14 +363,11 @@ class ShardedSampled:
                 "vfmb_sampled_score")
         L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_l), C.byref(pl.struct), C.byref(io), None, 0, s),
                 "vfmb_sampled_gather")
-        g = torch.zeros((M + 1, d + 1), dtype=torch.float32, device=self.device)
-        g[self._dest] = torch.cat((bl.grow.view(pl.u_cap, d), bl.gws[:, None]), dim=1)
-        st = bl.stats
-        self.tail.zero_()
-        self.tail[T_NLL] = st[L.ST_NLL_MEAN] * self.B
-        self.tail[T_RESID], self.tail[T_SQERR] = st[L.ST_SUM_RESID], st[L.ST_SUM_SQERR]
-        self.tail[T_KLROWS] = self.buf_o.stats[L.ST_KL_ROWS]
-        return g[:M].view(P, self.CAP, d + 1).contiguous(), self.tail
+        L.check(lib.vfmb_shard_pack_grads(C.byref(pl.struct), bl.grow.data_ptr(), bl.gws.data_ptr(), self._dest.data_ptr(),
+                                          pl.u_cap, M, d, self._gsend.data_ptr(), bl.stats.data_ptr(),
+                                          self.buf_o.stats.data_ptr(), float(self.B), self.tail.data_ptr(),
+                                          self._tail_idx, DP_TAIL, s), "vfmb_shard_pack_grads")
+        return self._gsend.view(P, self.CAP, d + 1), self.tail
 
     @torch.no_grad()
     def phase_owner_update(self, recv_g: torch.Tensor, tail_global: torch.Tensor) -> dict:
@@ -366,11 +375,11 @@ class ShardedSampled:
         replicated scalar update."""
         M, d = self.M, self.d
         po, bo = self.plan_o, self.buf_o
-        G = recv_g.reshape(M, d + 1)
-        table = G[:, :d].contiguous()
-        bo.rsorted[:M] = G[:, d][po.occ[:M].long()]
+        recv_g = recv_g.contiguous()
         io, tab, s, lib = self._io_o, self._tables(), current_stream(self.device), L.lib()
-        L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_o), C.byref(po.struct), C.byref(io), table.data_ptr(), 1, s),
+        L.check(lib.vfmb_shard_unpack_grads(C.byref(po.struct), recv_g.data_ptr(), M, d, self._table.data_ptr(),
+                                            bo.rsorted.data_ptr(), s), "vfmb_shard_unpack_grads")
+        L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_o), C.byref(po.struct), C.byref(io), self._table.data_ptr(), 1, s),
                 "vfmb_sampled_gather")
         L.check(lib.vfmb_sampled_adam_rows(C.byref(self.cfg_o), C.byref(tab), C.byref(po.struct), C.byref(io),
                                            C.byref(self.adam), L.ADAM_TOUCHED, 1.0, s), "vfmb_sampled_adam_rows")
@@ -384,15 +393,47 @@ class ShardedSampled:
 
     def step(self, x_local: torch.Tensor, y_local: torch.Tensor) -> dict:
         ex = self.exchange
+        mark = self._mark
+        mark("start")
         send, z = self.phase_request(x_local, y_local)
+        mark("request")
         recv = ex.all_to_all(send)
         z = ex.all_reduce(z)
+        mark("a2a_ids")
         reply = self.phase_owner_stage(recv, z)
+        mark("owner_stage")
         rows = ex.all_to_all(reply)
+        mark("a2a_rows")
         grads, tail = self.phase_local(rows)
+        mark("local")
         recv_g = ex.all_to_all(grads)
         tail = ex.all_reduce(tail)
-        return self.phase_owner_update(recv_g, tail)
+        mark("a2a_grads")
+        out = self.phase_owner_update(recv_g, tail)
+        mark("owner_update")
+        return out
+
+    # ---- optional per-phase timing (CUDA events on the step's stream; read with phase_times())
+    def enable_timing(self, on: bool = True) -> None:
+        self._timing = [] if on else None
+
+    def _mark(self, name: str) -> None:
+        if getattr(self, "_timing", None) is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._timing.append((name, ev))
+
+    def phase_times(self) -> dict:
+        """Mean milliseconds per phase over the steps recorded since enable_timing() (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        acc, cnt = {}, {}
+        tl = self._timing or []
+        for (n0, e0), (n1, e1) in zip(tl[:-1], tl[1:]):
+            if n1 == "start":
+                continue
+            acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        return {k: acc[k] / cnt[k] for k in acc}
 
     def check_overflow(self) -> None:
         """Raises if a bucket ever exceeded the slot capacity (synchronises; call occasionally)."""
