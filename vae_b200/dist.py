@@ -413,6 +413,28 @@ class ShardedSampled:
         mark("owner_update")
         return out
 
+    def graphed_step(self):
+        """Capture one whole step -- both plans, every kernel and the NCCL collectives -- in a CUDA
+        graph; returns ``run(x_local, y_local) -> dict`` that copies the batch into the graph's
+        static input buffers and replays it.  The eager step is host-bound (~45 launches and 5
+        collectives enqueued from Python per step take longer than the GPU needs to run them).
+        Call after at least one eager ``step`` (communicators and lazy allocations exist)."""
+        assert getattr(self, "_timing", None) is None, "disable phase timing before capturing"
+        xs = torch.zeros((self.B, self.F), dtype=torch.int64, device=self.device)
+        ys = torch.zeros(self.B, dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.step(xs, ys)
+
+        def run(x_local: torch.Tensor, y_local: torch.Tensor) -> dict:
+            xs.copy_(x_local, non_blocking=True)
+            ys.copy_(y_local, non_blocking=True)
+            g.replay()
+            return out
+        run.graph = g
+        return run
+
     # ---- optional per-phase timing (CUDA events on the step's stream; read with phase_times())
     def enable_timing(self, on: bool = True) -> None:
         self._timing = [] if on else None
