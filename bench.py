@@ -366,9 +366,21 @@ def run_sharded(args):
     tc[tc == 0] = 1                                            # rows never seen in training: weight 1
     lr = 1.0 / (1 + w.n_train // B)
     kl = "torch" if F == 2 else "group"
+    exchange = args.exchange
+    if exchange == "peer":                                     # NVLink peer memory; all ranks must agree
+        ok = 1
+        try:
+            import importlib
+            importlib.import_module("torch.distributed._symmetric_memory")
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            exchange = "nccl"
     model = ShardedSampled(d, w.field_sizes, torch.from_numpy(tc), w.n_train, B, world, rank,
                            output=w.output, kl_weighting=kl, seed=synth.NOISE_SEED, lr=lr, device=device,
-                           slack=args.slack)
+                           slack=args.slack, exchange="peer" if exchange == "peer" else None)
     x_all = torch.from_numpy(w.x[: n_batches * B]).to(device)
     y_all = torch.from_numpy(w.y[: n_batches * B]).to(device)
 
@@ -468,9 +480,12 @@ def run_sharded(args):
                        "plan": "built every step on the step's stream (requester and owner side)"
                                + ("; whole step incl. the NCCL collectives replayed as one CUDA graph" if graphed else ""),
                        "l2": "consecutive distinct batches, no flush",
-                       "parallelism": f"sharded{world}: rows r mod {world}; per step 3 NCCL all-to-alls (ids, sampled "
-                                      f"rows, row gradients; {a2a / 1e6:.1f} MB padded slots per rank) + 2 small "
-                                      f"all-reduces; global batch {B * world}"},
+                       "parallelism": (f"sharded{world}: rows r mod {world}; per step 3 exchanges (ids, sampled rows, row "
+                                       f"gradients; {a2a / 1e6:.1f} MB of slots per rank) "
+                                       + ("written by the pack kernels straight into the peers' buffers over NVLink "
+                                          "(symmetric memory), 3 signal-pad barriers, no collective calls"
+                                          if exchange == "peer" else "as NCCL all-to-alls + 2 small all-reduces")
+                                       + f"; global batch {B * world}")},
             "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": step_bytes / (ms / K * 1e-3) / 1e9,
                          "peak": peak * world, "unit": "GB/s", "frac": step_bytes / (ms / K * 1e-3) / 1e9 / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes": step_bytes},
@@ -568,6 +583,8 @@ def main():
                     help="N>1: dp = replicated tables + dense all-reduce (mode A), sharded = row-sharded tables + "
                          "all-to-all (mode B); auto = sharded unless the dense gradient is under 8 MB")
     ap.add_argument("--slack", type=float, default=0.75, help="mode B: slot capacity as a fraction of B*F/P")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="mode B data path: NVLink peer memory written by the pack kernels, or NCCL all-to-alls")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", "1"))

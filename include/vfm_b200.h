@@ -217,30 +217,45 @@ int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables* tab, const
  * (ascending) this rank asks of owner q; w = 2 int32 {id, local batch count} for requests (-1 =
  * empty), d+1 floats {row, bias} for sampled rows and for row gradients (zeros = empty).         */
 int64_t vfmb_shard_bucket_workspace(int32_t u_cap);
-/* requester: unique ids of `plan` -> request slots `send` [P*CAP,2]; dest[u] = slot of unique rank
- * u (P*CAP = none); *overflow |= 1 when an owner's bucket exceeds CAP                             */
+/* Every pack function takes an optional PEER TABLE: `peers` = host array of P device pointers, the
+ * same exchange buffer of every rank mapped into this process (NVLink peer memory, e.g. torch
+ * symmetric memory), `rank` = this process.  With a peer table the kernel stores slot (q, j) straight
+ * into chunk `rank` of rank q's buffer -- the pack kernel IS the all-to-all; the caller only needs a
+ * cross-rank barrier before the consumer.  With peers == NULL the slots go to the local `send` /
+ * `reply` / `out` buffer and the caller runs a collective (NCCL all-to-all) on it.
+ *
+ * requester: unique ids of `plan` -> request slots [P*CAP,2]; dest[u] = slot of unique rank u
+ * (P*CAP = none); *overflow |= 1 when an owner's bucket exceeds CAP                               */
 int vfmb_shard_bucket(const vfmb_plan* plan, int32_t u_cap, int32_t P, int32_t CAP, int32_t* send,
-                      int32_t* dest, int32_t* overflow, void* workspace, vfmb_stream stream);
-/* owner: received requests -> local row indices loc [M] (int64, the plan's input; padding -> R_loc) */
+                      int32_t* dest, int32_t* overflow, void* workspace, const void* const* peers,
+                      int32_t rank, vfmb_stream stream);
+/* peer mode all-reduce of a small vector: put `vec[n]` into slot `rank` (pitch floats apart) of
+ * every rank; after the barrier every rank adds the P slots in rank order (bitwise equal results) */
+int vfmb_shard_put_small(const float* vec, int32_t n, int32_t pitch, const void* const* peers, int32_t P,
+                         int32_t rank, vfmb_stream stream);
+int vfmb_shard_sum_small(const float* slots, int32_t P, int32_t n, int32_t pitch, float* out, vfmb_stream stream);
+/* owner: received requests -> local row indices loc [M] (int64, the plan's input; padding -> R_loc);
+ * recv_copy (optional) = private copy of the requests                                              */
 int vfmb_shard_owner_ids(const int32_t* recv, int32_t M, int32_t P, int32_t R_loc, int64_t* loc,
-                         vfmb_stream stream);
+                         int32_t* recv_copy, vfmb_stream stream);
 /* owner: counts_only != 0 -> urec[u].w = batch count of row u summed over the requesters;
- *        counts_only == 0 -> reply[s] = {vs[inverse[s]], ws[inverse[s]]} for every slot s           */
-int vfmb_shard_owner_pack(const vfmb_plan* plan_o, const int32_t* recv, int32_t M, int32_t d,
+ *        counts_only == 0 -> reply slot s = {vs[inverse[s]], ws[inverse[s]]}                        */
+int vfmb_shard_owner_pack(const vfmb_plan* plan_o, const int32_t* recv, int32_t M, int32_t CAP, int32_t d,
                           const float* vs, const float* ws, float* reply, int32_t counts_only,
-                          vfmb_stream stream);
+                          const void* const* peers, int32_t rank, vfmb_stream stream);
 /* requester: received sampled rows -> vs / ws in unique-rank order                                  */
 int vfmb_shard_unpack_rows(const vfmb_plan* plan_l, const float* recv_rows, const int32_t* dest,
                            int32_t u_cap, int32_t M, int32_t d, float* vs, float* ws, vfmb_stream stream);
 /* requester: row gradients -> slots; tail[tail_idx[0..3]] = {NLL sum, residual sum, squared-error
  * sum of this rank's samples, KL sum of this rank's owned rows} (tail_idx: host array of 4)         */
 int vfmb_shard_pack_grads(const vfmb_plan* plan_l, const float* grow, const float* gws, const int32_t* dest,
-                          int32_t u_cap, int32_t M, int32_t d, float* out, const float* stats_local,
+                          int32_t u_cap, int32_t M, int32_t CAP, int32_t d, float* out, const float* stats_local,
                           const float* stats_owner, float n_local, float* tail, const int32_t* tail_idx,
-                          int32_t n_tail, vfmb_stream stream);
-/* owner: received gradient slots -> gather table [M,d] + bias gradients in sorted-occurrence order  */
-int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, int32_t M, int32_t d,
-                            float* table, float* rsorted, vfmb_stream stream);
+                          int32_t n_tail, const void* const* peers, int32_t rank, vfmb_stream stream);
+/* owner: received gradient slots -> gather table [M,d] + bias gradients in sorted-occurrence order;
+ * recv_ids (peer mode) = the requests: empty slots were never written and read as zeros            */
+int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, const int32_t* recv_ids, int32_t M,
+                            int32_t d, float* table, float* rsorted, vfmb_stream stream);
 
 int vfmb_dp_final(const vfmb_config* cfg_global, const vfmb_tables* tab, const float* tail,
                   const float* eps_global, const vfmb_adam* adam, float* stats, vfmb_stream stream);

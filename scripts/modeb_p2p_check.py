@@ -1,0 +1,46 @@
+"""torchrun -N: mode B over NVLink peer memory vs over NCCL all-to-alls -- same inputs, same init;
+parameters, loss and predictions must agree (only the small all-reduces differ in summation order)."""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vae_b200 import synth
+from vae_b200.dist import ShardedSampled
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+w = synth.make_workload("ml20m", n_rows=2_000_000)
+B, d = w.batch, w.d
+tc = w.train_counts(); tc[tc == 0] = 1
+mk = lambda ex: ShardedSampled(d, w.field_sizes, torch.from_numpy(tc), w.n_train, B, world, rank, output="reg", lr=1e-2,
+                               device=dev, exchange=ex, slack=0.75)
+a, b = mk(None), mk("peer")
+x = torch.from_numpy(w.x).to(dev); y = torch.from_numpy(w.y).to(dev)
+for it in range(4):
+    j = it * world + rank
+    xa, ya = x[j * B:(j + 1) * B], y[j * B:(j + 1) * B]
+    oa = a.step(xa, ya)
+    la, pa = oa["loss"].item(), oa["pred"].clone()
+    ob = b.step(xa, ya)
+    lb, pb = ob["loss"].item(), ob["pred"].clone()
+    assert abs(la - lb) <= 1e-6 * abs(la), (it, la, lb)
+    assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-6), (it, (pa - pb).abs().max().item())
+a.check_overflow(); b.check_overflow()
+for name in ("entity", "bias", "entity_m", "entity_v", "scalars"):
+    ta, tb = getattr(a, name), getattr(b, name)
+    diff = (ta - tb).abs().max().item()
+    assert torch.allclose(ta, tb, rtol=1e-5, atol=1e-7), (name, diff)
+    if rank == 0:
+        print(f"{name:10s} max |nccl - peer| = {diff:.3e}  bitwise equal: {bool(torch.equal(ta, tb))}")
+# graph capture of the peer step
+run = b.graphed_step()
+for it in range(4, 8):
+    j = it * world + rank
+    o = run(x[j * B:(j + 1) * B], y[j * B:(j + 1) * B])
+torch.cuda.synchronize()
+if rank == 0:
+    print("peer-mode parity OK; graphed peer step loss", o["loss"].item())
+dist.barrier()
+sys.stdout.flush()
+os._exit(0)

@@ -109,16 +109,19 @@ SYMBOLS = {
                                         C.c_void_p]),
     "vfmb_shard_bucket_workspace": (C.c_int64, [C.c_int32]),
     "vfmb_shard_bucket": (C.c_int, [_P(Plan), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_void_p]),
-    "vfmb_shard_owner_ids": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
-    "vfmb_shard_owner_pack": (C.c_int, [_P(Plan), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_int32, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vfmb_shard_put_small": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "vfmb_shard_sum_small": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vfmb_shard_owner_ids": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vfmb_shard_owner_pack": (C.c_int, [_P(Plan), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "vfmb_shard_unpack_rows": (C.c_int, [_P(Plan), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "vfmb_shard_pack_grads": (C.c_int, [_P(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
-                                        C.c_void_p]),
-    "vfmb_shard_unpack_grads": (C.c_int, [_P(Plan), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vfmb_shard_unpack_grads": (C.c_int, [_P(Plan), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
     "vfmb_adam_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   _P(Adam), C.c_void_p, C.c_void_p]),
     "vfmb_adam_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),

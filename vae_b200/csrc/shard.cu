@@ -20,6 +20,21 @@ constexpr int kBktTile = 1024;     // unique ids per block
 
 __device__ __forceinline__ int owner_of(int id, int P) { return id % P; }
 
+// Destination of an exchange.  n == 0: a local send buffer in slot order (the caller runs an NCCL
+// all-to-all on it).  n == P: the exchange buffers of all ranks, peer-mapped over NVLink -- slot
+// (q, j) of this rank is written straight into chunk `rank` of rank q's buffer, so the pack kernel
+// IS the all-to-all (stores over NVSwitch; a barrier separates it from the consumer).
+struct Peers {
+    void* base[kMaxFields];
+    int n, rank;
+};
+template <typename T>
+__device__ __forceinline__ T* slot_ptr(const Peers& pe, T* local, int slot, int CAP, int width) {
+    if (pe.n == 0) return local + (size_t)slot * width;
+    const int q = slot / CAP, j = slot - q * CAP;
+    return reinterpret_cast<T*>(pe.base[q]) + ((size_t)pe.rank * CAP + j) * width;
+}
+
 // ---- bucket, pass 1: ids per owner in every tile of the sorted unique list
 __global__ void __launch_bounds__(kBkt)
 k_bucket_count(const int32_t* __restrict__ uniq, const int32_t* __restrict__ meta, int P,
@@ -45,7 +60,7 @@ k_bucket_count(const int32_t* __restrict__ uniq, const int32_t* __restrict__ met
 __global__ void __launch_bounds__(kBkt)
 k_bucket_place(const int32_t* __restrict__ uniq, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
                int u_cap, int P, int CAP, const int32_t* __restrict__ blk_cnt, int32_t* __restrict__ send,
-               int32_t* __restrict__ dest, int32_t* __restrict__ overflow) {
+               int32_t* __restrict__ dest, int32_t* __restrict__ overflow, Peers pe) {
     __shared__ int s_base[kMaxFields];
     __shared__ int s_w[kBkt / 32][kMaxFields];
     const int U = meta[0], M = P * CAP;
@@ -76,8 +91,9 @@ k_bucket_place(const int32_t* __restrict__ uniq, const int32_t* __restrict__ ure
             const int ord = off + rank;
             if (ord < CAP) slot = q * CAP + ord; else atomicOr(overflow, 1);
             if (slot < M) {
-                send[2 * slot] = id;
-                send[2 * slot + 1] = urec[4 * (size_t)u + 1];     // occurrences in this rank's batch
+                int32_t* rq = slot_ptr<int32_t>(pe, send, slot, CAP, 2);
+                rq[0] = id;
+                rq[1] = urec[4 * (size_t)u + 1];                  // occurrences in this rank's batch
             }
         }
         if (u < u_cap) dest[u] = slot;
@@ -91,12 +107,39 @@ k_bucket_place(const int32_t* __restrict__ uniq, const int32_t* __restrict__ ure
     }
 }
 
-// ---- owner: received global ids -> local row index (padding -> the sentinel row R_loc)
+// ---- peer mode: this rank's chunk of every rank's request buffer := empty (-1)
 __global__ void __launch_bounds__(256)
-k_owner_ids(const int32_t* __restrict__ recv, int M, int P, int R_loc, int64_t* __restrict__ loc) {
+k_fill_peers(Peers pe, int words_per_chunk, int32_t value) {
+    for (int q = 0; q < pe.n; ++q) {
+        int32_t* dst = reinterpret_cast<int32_t*>(pe.base[q]) + (size_t)pe.rank * words_per_chunk;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words_per_chunk; i += gridDim.x * blockDim.x) dst[i] = value;
+    }
+}
+
+// ---- peer mode: small vectors (Z_f, scalar sums): put into slot `rank` of every rank, then every
+// rank adds the P vectors in rank order -- an all-reduce whose result is bitwise equal everywhere
+__global__ void k_put_small(Peers pe, const float* __restrict__ vec, int n, int pitch) {
+    const int q = blockIdx.x;
+    float* dst = reinterpret_cast<float*>(pe.base[q]) + (size_t)pe.rank * pitch;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vec[i];
+}
+__global__ void k_sum_small(const float* __restrict__ slots, int P, int n, int pitch, float* __restrict__ out) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float acc = 0.f;
+        for (int q = 0; q < P; ++q) acc += slots[(size_t)q * pitch + i];
+        out[i] = acc;
+    }
+}
+
+// ---- owner: received global ids -> local row index (padding -> the sentinel row R_loc); optional
+// private copy of the requests (peer mode: the shared buffer is rewritten by the next step)
+__global__ void __launch_bounds__(256)
+k_owner_ids(const int32_t* __restrict__ recv, int M, int P, int R_loc, int64_t* __restrict__ loc,
+            int32_t* __restrict__ copy) {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < M; s += gridDim.x * blockDim.x) {
-        const int id = recv[2 * s];
-        loc[s] = id >= 0 ? (int64_t)(id / P) : (int64_t)R_loc;
+        const int2 rq = reinterpret_cast<const int2*>(recv)[s];
+        loc[s] = rq.x >= 0 ? (int64_t)(rq.x / P) : (int64_t)R_loc;
+        if (copy) reinterpret_cast<int2*>(copy)[s] = rq;
     }
 }
 
@@ -123,13 +166,14 @@ k_owner_counts(const int32_t* __restrict__ recv, const int32_t* __restrict__ occ
 // ---- rows <-> slots: one warp per slot / unique rank, d+1 floats (sampled row | bias)
 __global__ void __launch_bounds__(256)
 k_pack_rows(const float* __restrict__ vs, const float* __restrict__ ws, const int32_t* __restrict__ inverse,
-            int M, int d, float* __restrict__ out) {
+            const int32_t* __restrict__ ids, int M, int CAP, int d, float* __restrict__ out, Peers pe) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
     for (int s = gw; s < M; s += nw) {
+        if (pe.n && __ldg(ids + 2 * s) < 0) continue;     // peer mode: nobody reads an empty slot's reply
         const int u = __ldg(inverse + s);
         const float* src = vs + (size_t)u * d;
-        float* dst = out + (size_t)s * (d + 1);
+        float* dst = slot_ptr<float>(pe, out, s, CAP, d + 1);
         for (int k = lane; k < d; k += 32) dst[k] = __ldg(src + k);
         if (lane == 0) dst[d] = __ldg(ws + u);
     }
@@ -156,7 +200,8 @@ __global__ void __launch_bounds__(256)
 k_pack_grads(const float* __restrict__ grow, const float* __restrict__ gws, const int32_t* __restrict__ dest,
              const int32_t* __restrict__ meta, int M, int d, float* __restrict__ out,
              const float* __restrict__ stats_l, const float* __restrict__ stats_o, float n_local,
-             float* __restrict__ tail, int t_nll, int t_resid, int t_sqerr, int t_klrows, int n_tail) {
+             float* __restrict__ tail, int t_nll, int t_resid, int t_sqerr, int t_klrows, int n_tail,
+             int CAP, Peers pe) {
     const int U = meta[0];
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
@@ -173,7 +218,7 @@ k_pack_grads(const float* __restrict__ grow, const float* __restrict__ gws, cons
         const int s = __ldg(dest + u);
         if (s >= M) continue;                              // overflowed (flagged at bucketing)
         const float* src = grow + (size_t)u * d;
-        float* dst = out + (size_t)s * (d + 1);
+        float* dst = slot_ptr<float>(pe, out, s, CAP, d + 1);
         for (int k = lane; k < d; k += 32) dst[k] = __ldg(src + k);
         if (lane == 0) dst[d] = __ldg(gws + u);
     }
@@ -182,15 +227,20 @@ k_pack_grads(const float* __restrict__ grow, const float* __restrict__ gws, cons
 // owner: received [M, d+1] -> gather table [M, d] (16-byte aligned rows) and the per-position
 // coefficient (the bias gradient) in the plan's sorted-occurrence order
 __global__ void __launch_bounds__(256)
-k_unpack_grads(const float* __restrict__ recv, const int32_t* __restrict__ occ, int M, int d,
-               float* __restrict__ table, float* __restrict__ rsorted) {
+k_unpack_grads(const float* __restrict__ recv, const int32_t* __restrict__ occ, const int32_t* __restrict__ ids,
+               int M, int d, float* __restrict__ table, float* __restrict__ rsorted) {
+    // ids != NULL (peer mode): empty slots were never written by their requester -> zeros
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
     for (int s = gw; s < M; s += nw) {
+        const bool live = !ids || __ldg(ids + 2 * s) >= 0;
         const float* src = recv + (size_t)s * (d + 1);
         float* dst = table + (size_t)s * d;
-        for (int k = lane; k < d; k += 32) dst[k] = __ldg(src + k);
-        if (lane == 0) rsorted[s] = __ldg(recv + (size_t)__ldg(occ + s) * (d + 1) + d);
+        for (int k = lane; k < d; k += 32) dst[k] = live ? __ldg(src + k) : 0.f;
+        if (lane == 0) {
+            const int so = __ldg(occ + s);
+            rsorted[s] = (!ids || __ldg(ids + 2 * so) >= 0) ? __ldg(recv + (size_t)so * (d + 1) + d) : 0.f;
+        }
     }
 }
 
@@ -209,38 +259,80 @@ extern "C" int64_t vfmb_shard_bucket_workspace(int32_t u_cap) {
     return (int64_t)((u_cap + kBktTile - 1) / kBktTile) * kMaxFields * 4;
 }
 
+static int make_peers(const void* const* peers, int32_t P, int32_t rank, Peers* out) {
+    Peers pe{};
+    if (peers) {
+        if (P < 1 || P > kMaxFields || rank < 0 || rank >= P) return set_error(VFMB_EINVAL, "peer table: bad P / rank");
+        for (int q = 0; q < P; ++q) {
+            if (!peers[q]) return set_error(VFMB_EINVAL, "peer table: null buffer of rank %d", q);
+            pe.base[q] = const_cast<void*>(peers[q]);
+        }
+        pe.n = P; pe.rank = rank;
+    }
+    *out = pe;
+    return 0;
+}
+
 extern "C" int vfmb_shard_bucket(const vfmb_plan* plan, int32_t u_cap, int32_t P, int32_t CAP, int32_t* send,
-                                 int32_t* dest, int32_t* overflow, void* workspace, vfmb_stream stream_) {
-    if (!plan || !send || !dest || !overflow || !workspace || P < 1 || P > kMaxFields || CAP < 1 || u_cap < 1)
+                                 int32_t* dest, int32_t* overflow, void* workspace, const void* const* peers,
+                                 int32_t rank, vfmb_stream stream_) {
+    if (!plan || (!send && !peers) || !dest || !overflow || !workspace || P < 1 || P > kMaxFields || CAP < 1 || u_cap < 1)
         return set_error(VFMB_EINVAL, "vfmb_shard_bucket: bad argument (1 <= P <= %d)", kMaxFields);
     cudaStream_t stream = (cudaStream_t)stream_;
+    Peers pe;
+    int rc = make_peers(peers, P, rank, &pe);
+    if (rc) return rc;
     const int nblk = (u_cap + kBktTile - 1) / kBktTile;
-    CUDA_TRY(cudaMemsetAsync(send, 0xFF, (size_t)P * CAP * 2 * sizeof(int32_t), stream));   // -1: empty slot
+    if (pe.n) k_fill_peers<<<32, 256, 0, stream>>>(pe, CAP * 2, -1);                        // -1: empty slot
+    else CUDA_TRY(cudaMemsetAsync(send, 0xFF, (size_t)P * CAP * 2 * sizeof(int32_t), stream));
     k_bucket_count<<<nblk, kBkt, 0, stream>>>(plan->uniq, plan->meta, P, (int32_t*)workspace);
     k_bucket_place<<<nblk, kBkt, 0, stream>>>(plan->uniq, plan->urec, plan->meta, u_cap, P, CAP,
-                                              (const int32_t*)workspace, send, dest, overflow);
+                                              (const int32_t*)workspace, send, dest, overflow, pe);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_shard_put_small(const float* vec, int32_t n, int32_t pitch, const void* const* peers, int32_t P,
+                                    int32_t rank, vfmb_stream stream_) {
+    Peers pe;
+    int rc = make_peers(peers, P, rank, &pe);
+    if (rc) return rc;
+    if (!vec || !peers || n < 1 || n > pitch) return set_error(VFMB_EINVAL, "vfmb_shard_put_small: bad argument");
+    k_put_small<<<P, 32, 0, (cudaStream_t)stream_>>>(pe, vec, n, pitch);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_shard_sum_small(const float* slots, int32_t P, int32_t n, int32_t pitch, float* out,
+                                    vfmb_stream stream_) {
+    if (!slots || !out || P < 1 || n < 1 || n > pitch) return set_error(VFMB_EINVAL, "vfmb_shard_sum_small: bad argument");
+    k_sum_small<<<1, 32, 0, (cudaStream_t)stream_>>>(slots, P, n, pitch, out);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 extern "C" int vfmb_shard_owner_ids(const int32_t* recv, int32_t M, int32_t P, int32_t R_loc, int64_t* loc,
-                                    vfmb_stream stream_) {
+                                    int32_t* recv_copy, vfmb_stream stream_) {
     if (!recv || !loc || M < 1 || P < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_ids: bad argument");
-    k_owner_ids<<<(M + 255) / 256 > 2 * kNumSMs ? 2 * kNumSMs : (M + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(recv, M, P, R_loc, loc);
+    k_owner_ids<<<(M + 255) / 256 > 2 * kNumSMs ? 2 * kNumSMs : (M + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(
+        recv, M, P, R_loc, loc, recv_copy);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-extern "C" int vfmb_shard_owner_pack(const vfmb_plan* plan_o, const int32_t* recv, int32_t M, int32_t d,
+extern "C" int vfmb_shard_owner_pack(const vfmb_plan* plan_o, const int32_t* recv, int32_t M, int32_t CAP, int32_t d,
                                      const float* vs, const float* ws, float* reply, int32_t counts_only,
-                                     vfmb_stream stream_) {
-    if (!plan_o || !recv || M < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_pack: bad argument");
+                                     const void* const* peers, int32_t rank, vfmb_stream stream_) {
+    if (!plan_o || !recv || M < 1 || CAP < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_pack: bad argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (counts_only) {
         k_owner_counts<<<2 * kNumSMs, 256, 0, stream>>>(recv, plan_o->occ, plan_o->meta, plan_o->urec);
     } else {
-        if (!vs || !ws || !reply || d < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_pack: bad argument");
-        k_pack_rows<<<warp_grid(M), 256, 0, stream>>>(vs, ws, plan_o->inverse, M, d, reply);
+        if (!vs || !ws || (!reply && !peers) || d < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_pack: bad argument");
+        Peers pe;
+        int rc = make_peers(peers, M / CAP, rank, &pe);
+        if (rc) return rc;
+        k_pack_rows<<<warp_grid(M), 256, 0, stream>>>(vs, ws, plan_o->inverse, recv, M, CAP, d, reply, pe);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -255,23 +347,28 @@ extern "C" int vfmb_shard_unpack_rows(const vfmb_plan* plan_l, const float* recv
 }
 
 extern "C" int vfmb_shard_pack_grads(const vfmb_plan* plan_l, const float* grow, const float* gws, const int32_t* dest,
-                                     int32_t u_cap, int32_t M, int32_t d, float* out, const float* stats_local,
+                                     int32_t u_cap, int32_t M, int32_t CAP, int32_t d, float* out, const float* stats_local,
                                      const float* stats_owner, float n_local, float* tail, const int32_t* tail_idx,
-                                     int32_t n_tail, vfmb_stream stream_) {
-    if (!plan_l || !grow || !gws || !dest || !out || !stats_local || !stats_owner || !tail || !tail_idx || n_tail > 256)
+                                     int32_t n_tail, const void* const* peers, int32_t rank, vfmb_stream stream_) {
+    if (!plan_l || !grow || !gws || !dest || (!out && !peers) || !stats_local || !stats_owner || !tail || !tail_idx ||
+        n_tail > 256 || CAP < 1)
         return set_error(VFMB_EINVAL, "vfmb_shard_pack_grads: bad argument");
     cudaStream_t stream = (cudaStream_t)stream_;
-    CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)M * (d + 1) * sizeof(float), stream));
+    Peers pe;
+    int rc = make_peers(peers, M / CAP, rank, &pe);
+    if (rc) return rc;
+    if (!pe.n) CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)M * (d + 1) * sizeof(float), stream));
     k_pack_grads<<<warp_grid(u_cap), 256, 0, stream>>>(grow, gws, dest, plan_l->meta, M, d, out, stats_local, stats_owner,
-                                                       n_local, tail, tail_idx[0], tail_idx[1], tail_idx[2], tail_idx[3], n_tail);
+                                                       n_local, tail, tail_idx[0], tail_idx[1], tail_idx[2], tail_idx[3], n_tail,
+                                                       CAP, pe);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-extern "C" int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, int32_t M, int32_t d,
-                                       float* table, float* rsorted, vfmb_stream stream_) {
+extern "C" int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, const int32_t* recv_ids, int32_t M,
+                                       int32_t d, float* table, float* rsorted, vfmb_stream stream_) {
     if (!plan_o || !recv_g || !table || !rsorted) return set_error(VFMB_EINVAL, "vfmb_shard_unpack_grads: bad argument");
-    k_unpack_grads<<<warp_grid(M), 256, 0, (cudaStream_t)stream_>>>(recv_g, plan_o->occ, M, d, table, rsorted);
+    k_unpack_grads<<<warp_grid(M), 256, 0, (cudaStream_t)stream_>>>(recv_g, plan_o->occ, recv_ids, M, d, table, rsorted);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -196,6 +196,44 @@ class TorchExchange:
         return t
 
 
+SMALL_PITCH = 32                                            # floats per rank slot of the small-vector regions
+
+
+class PeerExchange:
+    """Exchange buffers of mode B as NVLink peer memory (torch symmetric memory): one symmetric
+    allocation per rank, carved into the request / sampled-row / gradient / small-vector regions
+    and mapped into every process.  The pack kernels of ``csrc/shard.cu`` store straight into the
+    peers' regions, so there is no collective call on the data path -- only ``barrier()`` (a
+    signal-pad barrier kernel on the current stream) between a pack kernel and its consumer."""
+
+    def __init__(self, M: int, d: int, P: int, rank: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.P, self.rank, self.M, self.d = P, rank, M, d
+        sizes = [("ids", M * 2 * 4), ("rows", M * (d + 1) * 4), ("grads", M * (d + 1) * 4),
+                 ("small0", P * SMALL_PITCH * 4), ("small1", P * SMALL_PITCH * 4)]
+        self.off, total = {}, 0
+        for name, nbytes in sizes:
+            self.off[name] = total
+            total += (nbytes + 255) // 256 * 256
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(ptrs) == P and ptrs[rank] == self.buf.data_ptr()
+        self.tables = {name: (C.c_void_p * P)(*[p + off for p in ptrs]) for name, off in self.off.items()}
+        view = lambda name, n, dt: self.buf[self.off[name]: self.off[name] + n * 4].view(dt)
+        self.ids = view("ids", M * 2, torch.int32).view(M, 2)
+        self.rows = view("rows", M * (d + 1), torch.float32).view(M, d + 1)
+        self.grads = view("grads", M * (d + 1), torch.float32).view(M, d + 1)
+        self.small = [view("small0", P * SMALL_PITCH, torch.float32), view("small1", P * SMALL_PITCH, torch.float32)]
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def barrier(self, channel: int = 0) -> None:
+        self.hdl.barrier(channel=channel)
+
+
 class ShardedSampled:
     """Sampled-ELBO VFM with ROW-SHARDED tables (mode B).
 
@@ -230,7 +268,9 @@ class ShardedSampled:
         self.B, self.n_train = int(batch_local), float(n_train)
         self.output, self.link = output, link
         self.adam = L.Adam(lr, betas[0], betas[1], eps)
-        self.exchange = exchange if exchange is not None else TorchExchange()
+        self._want_peer = isinstance(exchange, str) and exchange == "peer"
+        self.exchange = TorchExchange() if (exchange is None or self._want_peer) else exchange
+        self.peer = None
         self.noise_tables = noise_tables
         dev, d, P, p = self.device, self.d, self.P, self.p
         if kl_weighting == "torch":
@@ -292,6 +332,10 @@ class ShardedSampled:
         self._loc = torch.zeros((M, 1), dtype=torch.int64, device=dev)
         self._reply, self._gsend, self._table = f32(M, d + 1), f32(M, d + 1), f32(M, d)
         self._tail_idx = (C.c_int32 * 4)(T_NLL, T_RESID, T_SQERR, T_KLROWS)
+        self._ids_copy = i32(M, 2)
+        self._zg, self._tailg = f32(L.MAX_FIELDS), f32(DP_TAIL)
+        if self._want_peer:                                  # collective: every rank constructs it
+            self.peer = PeerExchange(M, d, P, p, dev)
 
     def _cfg(self, B, F, R, n_train, bounds, sizes, seed, stride, off):
         cfg = make_config(B, F, self.d, R, 1, self.output, self.link, bounds, sizes, n_train, seed)
@@ -312,9 +356,15 @@ class ShardedSampled:
         x = x.to(self.device).contiguous()
         self.plan_l.build(self.cfg_l, x, self.train_counts)
         pl = self.plan_l
+        pe = self.peer
         L.check(L.lib().vfmb_shard_bucket(C.byref(pl.struct), pl.u_cap, P, CAP, self._send.data_ptr(),
                                           self._dest.data_ptr(), self.overflow.data_ptr(), self._bws.data_ptr(),
+                                          pe.tables["ids"] if pe else None, self.p,
                                           current_stream(self.device)), "vfmb_shard_bucket")
+        if pe:
+            L.check(L.lib().vfmb_shard_put_small(pl.z.data_ptr(), L.MAX_FIELDS, SMALL_PITCH, pe.tables["small0"], P, self.p,
+                                                 current_stream(self.device)), "vfmb_shard_put_small")
+            return None, None
         return self._send.view(P, CAP, 2), pl.z.clone()
 
     @torch.no_grad()
@@ -322,14 +372,25 @@ class ShardedSampled:
         """Owner: plan the received ids, global batch counts, sample the rows.  Returns the reply
         [P,CAP,d+1] (sampled factor row | sampled bias) in the slot layout of the request."""
         M, d, P, p = self.M, self.d, self.P, self.p
-        recv = recv.contiguous()
-        self._recv_ids = recv
+        pe = self.peer
         po, bo, lib, s = self.plan_o, self.buf_o, L.lib(), current_stream(self.device)
-        L.check(lib.vfmb_shard_owner_ids(recv.data_ptr(), M, P, self.R_loc, self._loc.data_ptr(), s), "vfmb_shard_owner_ids")
+        if pe:      # the requests are in this rank's peer region; keep a private copy (the region is
+            # rewritten by the next step), Z_f = sum of the ranks' slots in rank order
+            L.check(lib.vfmb_shard_owner_ids(pe.ids.data_ptr(), M, P, self.R_loc, self._loc.data_ptr(),
+                                             self._ids_copy.data_ptr(), s), "vfmb_shard_owner_ids")
+            recv = self._ids_copy
+            L.check(lib.vfmb_shard_sum_small(pe.small[0].data_ptr(), P, L.MAX_FIELDS, SMALL_PITCH, self._zg.data_ptr(), s),
+                    "vfmb_shard_sum_small")
+            z_global = self._zg
+        else:
+            recv = recv.contiguous()
+            L.check(lib.vfmb_shard_owner_ids(recv.data_ptr(), M, P, self.R_loc, self._loc.data_ptr(), None, s),
+                    "vfmb_shard_owner_ids")
+        self._recv_ids = recv
         po.build(self.cfg_o, self._loc, self.train_counts_loc)
         # batch count of every owned row summed over the requesting ranks -> urec[:, 3]
-        L.check(lib.vfmb_shard_owner_pack(C.byref(po.struct), recv.data_ptr(), M, d, None, None, None, 1, s),
-                "vfmb_shard_owner_pack")
+        L.check(lib.vfmb_shard_owner_pack(C.byref(po.struct), recv.data_ptr(), M, self.CAP, d, None, None, None, 1,
+                                          None, self.p, s), "vfmb_shard_owner_pack")
         po.z.copy_(z_global)
         noise = None
         if self.noise_tables is not None:                     # tests: per-entity noise tables
@@ -340,9 +401,10 @@ class ShardedSampled:
         self._io_o = bo.io(noise=noise)
         L.check(L.lib().vfmb_sampled_stage(C.byref(self.cfg_o), C.byref(self._tables()), C.byref(po.struct),
                                            C.byref(self._io_o), current_stream(self.device)), "vfmb_sampled_stage")
-        L.check(lib.vfmb_shard_owner_pack(C.byref(po.struct), recv.data_ptr(), M, d, bo.vs.data_ptr(), bo.ws.data_ptr(),
-                                          self._reply.data_ptr(), 0, s), "vfmb_shard_owner_pack")
-        return self._reply.view(P, self.CAP, d + 1)
+        L.check(lib.vfmb_shard_owner_pack(C.byref(po.struct), recv.data_ptr(), M, self.CAP, d, bo.vs.data_ptr(),
+                                          bo.ws.data_ptr(), self._reply.data_ptr(), 0,
+                                          pe.tables["rows"] if pe else None, self.p, s), "vfmb_shard_owner_pack")
+        return None if pe else self._reply.view(P, self.CAP, d + 1)
 
     @torch.no_grad()
     def phase_local(self, recv_rows: torch.Tensor):
@@ -350,7 +412,8 @@ class ShardedSampled:
         Returns (row gradients [P,CAP,d+1] in slot layout, additive scalars tail [16])."""
         M, d, P = self.M, self.d, self.P
         pl, bl = self.plan_l, self.buf_l
-        recv_rows = recv_rows.contiguous()
+        pe = self.peer
+        recv_rows = pe.rows if pe else recv_rows.contiguous()
         lib, s = L.lib(), current_stream(self.device)
         L.check(lib.vfmb_shard_unpack_rows(C.byref(pl.struct), recv_rows.data_ptr(), self._dest.data_ptr(), pl.u_cap, M, d,
                                            bl.vs.data_ptr(), bl.ws.data_ptr(), s), "vfmb_shard_unpack_rows")
@@ -364,9 +427,14 @@ class ShardedSampled:
         L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_l), C.byref(pl.struct), C.byref(io), None, 0, s),
                 "vfmb_sampled_gather")
         L.check(lib.vfmb_shard_pack_grads(C.byref(pl.struct), bl.grow.data_ptr(), bl.gws.data_ptr(), self._dest.data_ptr(),
-                                          pl.u_cap, M, d, self._gsend.data_ptr(), bl.stats.data_ptr(),
+                                          pl.u_cap, M, self.CAP, d, self._gsend.data_ptr(), bl.stats.data_ptr(),
                                           self.buf_o.stats.data_ptr(), float(self.B), self.tail.data_ptr(),
-                                          self._tail_idx, DP_TAIL, s), "vfmb_shard_pack_grads")
+                                          self._tail_idx, DP_TAIL, pe.tables["grads"] if pe else None, self.p, s),
+                "vfmb_shard_pack_grads")
+        if pe:
+            L.check(lib.vfmb_shard_put_small(self.tail.data_ptr(), DP_TAIL, SMALL_PITCH, pe.tables["small1"], P, self.p, s),
+                    "vfmb_shard_put_small")
+            return None, None
         return self._gsend.view(P, self.CAP, d + 1), self.tail
 
     @torch.no_grad()
@@ -375,9 +443,17 @@ class ShardedSampled:
         replicated scalar update."""
         M, d = self.M, self.d
         po, bo = self.plan_o, self.buf_o
-        recv_g = recv_g.contiguous()
+        pe = self.peer
         io, tab, s, lib = self._io_o, self._tables(), current_stream(self.device), L.lib()
-        L.check(lib.vfmb_shard_unpack_grads(C.byref(po.struct), recv_g.data_ptr(), M, d, self._table.data_ptr(),
+        if pe:
+            recv_g = pe.grads
+            L.check(lib.vfmb_shard_sum_small(pe.small[1].data_ptr(), self.P, DP_TAIL, SMALL_PITCH, self._tailg.data_ptr(), s),
+                    "vfmb_shard_sum_small")
+            tail_global = self._tailg
+        else:
+            recv_g = recv_g.contiguous()
+        L.check(lib.vfmb_shard_unpack_grads(C.byref(po.struct), recv_g.data_ptr(),
+                                            self._ids_copy.data_ptr() if pe else None, M, d, self._table.data_ptr(),
                                             bo.rsorted.data_ptr(), s), "vfmb_shard_unpack_grads")
         L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_o), C.byref(po.struct), C.byref(io), self._table.data_ptr(), 1, s),
                 "vfmb_sampled_gather")
@@ -394,6 +470,24 @@ class ShardedSampled:
     def step(self, x_local: torch.Tensor, y_local: torch.Tensor) -> dict:
         ex = self.exchange
         mark = self._mark
+        if self.peer is not None:       # peer memory: the pack kernels are the all-to-alls
+            pe = self.peer
+            mark("start")
+            self.phase_request(x_local, y_local)
+            mark("request")
+            pe.barrier(0)
+            mark("a2a_ids")
+            self.phase_owner_stage(None, None)
+            mark("owner_stage")
+            pe.barrier(1)
+            mark("a2a_rows")
+            self.phase_local(None)
+            mark("local")
+            pe.barrier(2)
+            mark("a2a_grads")
+            out = self.phase_owner_update(None, None)
+            mark("owner_update")
+            return out
         mark("start")
         send, z = self.phase_request(x_local, y_local)
         mark("request")
