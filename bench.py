@@ -398,9 +398,14 @@ def run_sharded(args):
     barrier()
     step = model.step
     graphed = False
+    pipe = None
     if args.plan == "graph":                                  # whole step incl. the collectives as one CUDA graph
         try:
-            step = model.graphed_step()
+            if exchange == "peer" and not args.no_pipeline:
+                from vae_b200.dist import ShardedPipeline
+                pipe = ShardedPipeline(model)                 # + plans / id exchange of batch i+1 under step i
+            else:
+                step = model.graphed_step()
             graphed = True
         except Exception as exc:                              # capture of NCCL collectives unsupported: stay eager
             print(f"[bench] rank {rank}: graph capture failed ({type(exc).__name__}: {exc}); eager steps", file=sys.stderr)
@@ -408,17 +413,31 @@ def run_sharded(args):
         flag = torch.tensor([1 if graphed else 0], device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # all ranks must agree
         if int(flag.item()) == 0:
-            step, graphed = model.step, False
-        for i in range(W):
-            out = step(*batch(i))
+            step, graphed, pipe = model.step, False, None
+        if pipe is not None:
+            nxt = {"i": 0}
+
+            def step(xb, yb):                                 # same call shape as model.step: the batch passed
+                # is the one staged for the FOLLOWING replay; batches are consumed in order
+                return pipe.step(xb, yb)
+            pipe.start(*batch(0))
+            for i in range(W):
+                out = pipe.step(*batch(i + 1))
+        else:
+            for i in range(W):
+                out = step(*batch(i))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for i in range(W, W + K):
-        out = step(*batch(i))
+    if pipe is not None:
+        for i in range(W, W + K):
+            out = pipe.step(*batch(i + 1))                    # runs batch i, stages batch i+1
+    else:
+        for i in range(W, W + K):
+            out = step(*batch(i))
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -437,9 +456,12 @@ def run_sharded(args):
     e0.record()
     for i in range(Ke):
         j = ((W + K + i) * world + rank) % n_batches
-        xd.copy_(xh[j * B:(j + 1) * B], non_blocking=True)
-        yd.copy_(yh[j * B:(j + 1) * B], non_blocking=True)
-        o = step(xd, yd)
+        if pipe is not None:                                  # pinned host -> the pipeline's staging slot
+            o = pipe.step(xh[j * B:(j + 1) * B], yh[j * B:(j + 1) * B])
+        else:
+            xd.copy_(xh[j * B:(j + 1) * B], non_blocking=True)
+            yd.copy_(yh[j * B:(j + 1) * B], non_blocking=True)
+            o = step(xd, yd)
         res[i].copy_(o["stats"], non_blocking=True)
     e1.record()
     barrier()
@@ -478,7 +500,9 @@ def run_sharded(args):
                        "fields": F, "unique_rows_per_global_step": U, "adam": "touched rows (lazy), on the owner",
                        "noise": "Philox4x32-10 in-kernel, keyed by the global row id (rank-invariant)",
                        "plan": "built every step on the step's stream (requester and owner side)"
-                               + ("; whole step incl. the NCCL collectives replayed as one CUDA graph" if graphed else ""),
+                               + ("; plans and id exchange of batch i+1 run under step i (side branch of the step's "
+                                  "CUDA graph)" if pipe is not None else
+                                  "; whole step incl. the collectives replayed as one CUDA graph" if graphed else ""),
                        "l2": "consecutive distinct batches, no flush",
                        "parallelism": (f"sharded{world}: rows r mod {world}; per step 3 exchanges (ids, sampled rows, row "
                                        f"gradients; {a2a / 1e6:.1f} MB of slots per rank) "
@@ -583,6 +607,7 @@ def main():
                     help="N>1: dp = replicated tables + dense all-reduce (mode A), sharded = row-sharded tables + "
                          "all-to-all (mode B); auto = sharded unless the dense gradient is under 8 MB")
     ap.add_argument("--slack", type=float, default=0.75, help="mode B: slot capacity as a fraction of B*F/P")
+    ap.add_argument("--no-pipeline", action="store_true", help="mode B peer: serial graphed step instead of the pipeline")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="mode B data path: NVLink peer memory written by the pack kernels, or NCCL all-to-alls")
     args = ap.parse_args()

@@ -33,6 +33,22 @@ for name in ("entity", "bias", "entity_m", "entity_v", "scalars"):
     assert torch.allclose(ta, tb, rtol=1e-5, atol=1e-7), (name, diff)
     if rank == 0:
         print(f"{name:10s} max |nccl - peer| = {diff:.3e}  bitwise equal: {bool(torch.equal(ta, tb))}")
+# software-pipelined graphed loop (plans + id exchange of batch i+1 under step i) vs the serial steps
+from vae_b200.dist import ShardedPipeline
+c = mk("peer")
+pipe = ShardedPipeline(c)
+nb = 4
+bat = lambda it: (x[(it * world + rank) * B:(it * world + rank + 1) * B], y[(it * world + rank) * B:(it * world + rank + 1) * B])
+pipe.start(*bat(0))
+for it in range(nb):
+    o = pipe.step(*bat(it + 1)) if it + 1 < nb else pipe.step()
+torch.cuda.synchronize()
+for name in ("entity", "bias", "entity_m", "entity_v", "scalars"):
+    ta, tc_ = getattr(a, name), getattr(c, name)
+    assert torch.equal(ta, tc_), (name, (ta - tc_).abs().max().item())
+assert abs(o["loss"].item() - la) <= 1e-6 * abs(la)
+if rank == 0:
+    print("pipelined graphed loop == serial steps (bitwise), loss", o["loss"].item())
 # graph capture of the peer step
 run = b.graphed_step()
 for it in range(4, 8):

@@ -210,8 +210,10 @@ class PeerExchange:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         self.P, self.rank, self.M, self.d = P, rank, M, d
-        sizes = [("ids", M * 2 * 4), ("rows", M * (d + 1) * 4), ("grads", M * (d + 1) * 4),
-                 ("small0", P * SMALL_PITCH * 4), ("small1", P * SMALL_PITCH * 4)]
+        # the request and Z_f regions exist twice: the requests of batch i+1 are exchanged while
+        # step i still runs (ShardedPipeline)
+        sizes = [("ids0", M * 2 * 4), ("ids1", M * 2 * 4), ("rows", M * (d + 1) * 4), ("grads", M * (d + 1) * 4),
+                 ("z0", P * SMALL_PITCH * 4), ("z1", P * SMALL_PITCH * 4), ("tail", P * SMALL_PITCH * 4)]
         self.off, total = {}, 0
         for name, nbytes in sizes:
             self.off[name] = total
@@ -223,10 +225,11 @@ class PeerExchange:
         assert len(ptrs) == P and ptrs[rank] == self.buf.data_ptr()
         self.tables = {name: (C.c_void_p * P)(*[p + off for p in ptrs]) for name, off in self.off.items()}
         view = lambda name, n, dt: self.buf[self.off[name]: self.off[name] + n * 4].view(dt)
-        self.ids = view("ids", M * 2, torch.int32).view(M, 2)
+        self.ids = [view(f"ids{k}", M * 2, torch.int32).view(M, 2) for k in (0, 1)]
         self.rows = view("rows", M * (d + 1), torch.float32).view(M, d + 1)
         self.grads = view("grads", M * (d + 1), torch.float32).view(M, d + 1)
-        self.small = [view("small0", P * SMALL_PITCH, torch.float32), view("small1", P * SMALL_PITCH, torch.float32)]
+        self.z = [view(f"z{k}", P * SMALL_PITCH, torch.float32) for k in (0, 1)]
+        self.tail = view("tail", P * SMALL_PITCH, torch.float32)
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
 
@@ -334,6 +337,18 @@ class ShardedSampled:
         self._tail_idx = (C.c_int32 * 4)(T_NLL, T_RESID, T_SQERR, T_KLROWS)
         self._ids_copy = i32(M, 2)
         self._zg, self._tailg = f32(L.MAX_FIELDS), f32(DP_TAIL)
+        self._y = self._io_o = self._recv_ids = self._noise_o = None
+        # Per-batch state exists twice ("slots"): everything that depends only on the ids of a batch
+        # -- both plans, the slot map, the owner's copy of the requests, Z_f -- so that it can be
+        # prepared for batch i+1 while step i runs (ShardedPipeline).  _use_slot(k) makes slot k
+        # the one the phase methods work on.
+        self._slot_keys = ("plan_l", "plan_o", "_dest", "_ids_copy", "_loc", "_zg", "_y", "_io_o", "_recv_ids", "_noise_o")
+        self._slots = [{k: getattr(self, k) for k in self._slot_keys},
+                       {"plan_l": BatchPlan(self.B, self.F, self.R, dev), "plan_o": BatchPlan(self.M, 1, Rl, dev),
+                        "_dest": i32(u_cap), "_ids_copy": i32(M, 2),
+                        "_loc": torch.zeros((M, 1), dtype=torch.int64, device=dev), "_zg": f32(L.MAX_FIELDS),
+                        "_y": None, "_io_o": None, "_recv_ids": None, "_noise_o": None}]
+        self._k = 0
         if self._want_peer:                                  # collective: every rank constructs it
             self.peer = PeerExchange(M, d, P, p, dev)
 
@@ -347,6 +362,13 @@ class ShardedSampled:
                         L.ptr(self.entity_m), L.ptr(self.entity_v), L.ptr(self.train_counts_loc),
                         L.ptr(self.scalars), L.ptr(self.scalars_m), L.ptr(self.scalars_v), L.ptr(self.adam_step))
 
+    def _use_slot(self, k: int) -> None:
+        for key in self._slot_keys:                           # save what the phases assigned, switch
+            self._slots[self._k][key] = getattr(self, key)
+        self._k = k
+        for key in self._slot_keys:
+            setattr(self, key, self._slots[k][key])
+
     # ------------------------------------------------------------------ phases
     @torch.no_grad()
     def phase_request(self, x: torch.Tensor, y: torch.Tensor):
@@ -359,27 +381,32 @@ class ShardedSampled:
         pe = self.peer
         L.check(L.lib().vfmb_shard_bucket(C.byref(pl.struct), pl.u_cap, P, CAP, self._send.data_ptr(),
                                           self._dest.data_ptr(), self.overflow.data_ptr(), self._bws.data_ptr(),
-                                          pe.tables["ids"] if pe else None, self.p,
+                                          pe.tables[f"ids{self._k}"] if pe else None, self.p,
                                           current_stream(self.device)), "vfmb_shard_bucket")
         if pe:
-            L.check(L.lib().vfmb_shard_put_small(pl.z.data_ptr(), L.MAX_FIELDS, SMALL_PITCH, pe.tables["small0"], P, self.p,
+            L.check(L.lib().vfmb_shard_put_small(pl.z.data_ptr(), L.MAX_FIELDS, SMALL_PITCH, pe.tables[f"z{self._k}"], P, self.p,
                                                  current_stream(self.device)), "vfmb_shard_put_small")
             return None, None
         return self._send.view(P, CAP, 2), pl.z.clone()
 
-    @torch.no_grad()
     def phase_owner_stage(self, recv: torch.Tensor, z_global: torch.Tensor) -> torch.Tensor:
         """Owner: plan the received ids, global batch counts, sample the rows.  Returns the reply
         [P,CAP,d+1] (sampled factor row | sampled bias) in the slot layout of the request."""
+        self._owner_prepare(recv, z_global)
+        return self._owner_sample()
+
+    @torch.no_grad()
+    def _owner_prepare(self, recv, z_global) -> None:
+        """The part of the owner's work that depends only on the requested ids."""
         M, d, P, p = self.M, self.d, self.P, self.p
         pe = self.peer
         po, bo, lib, s = self.plan_o, self.buf_o, L.lib(), current_stream(self.device)
         if pe:      # the requests are in this rank's peer region; keep a private copy (the region is
             # rewritten by the next step), Z_f = sum of the ranks' slots in rank order
-            L.check(lib.vfmb_shard_owner_ids(pe.ids.data_ptr(), M, P, self.R_loc, self._loc.data_ptr(),
+            L.check(lib.vfmb_shard_owner_ids(pe.ids[self._k].data_ptr(), M, P, self.R_loc, self._loc.data_ptr(),
                                              self._ids_copy.data_ptr(), s), "vfmb_shard_owner_ids")
             recv = self._ids_copy
-            L.check(lib.vfmb_shard_sum_small(pe.small[0].data_ptr(), P, L.MAX_FIELDS, SMALL_PITCH, self._zg.data_ptr(), s),
+            L.check(lib.vfmb_shard_sum_small(pe.z[self._k].data_ptr(), P, L.MAX_FIELDS, SMALL_PITCH, self._zg.data_ptr(), s),
                     "vfmb_shard_sum_small")
             z_global = self._zg
         else:
@@ -392,6 +419,14 @@ class ShardedSampled:
         L.check(lib.vfmb_shard_owner_pack(C.byref(po.struct), recv.data_ptr(), M, self.CAP, d, None, None, None, 1,
                                           None, self.p, s), "vfmb_shard_owner_pack")
         po.z.copy_(z_global)
+
+    @torch.no_grad()
+    def _owner_sample(self):
+        """Owner: draw the noise of the requested rows, reply with the sampled rows."""
+        M, d, P, p = self.M, self.d, self.P, self.p
+        pe = self.peer
+        recv = self._ids_copy if pe else self._recv_ids      # peer mode: the slot's private copy of the requests
+        po, bo, lib, s = self.plan_o, self.buf_o, L.lib(), current_stream(self.device)
         noise = None
         if self.noise_tables is not None:                     # tests: per-entity noise tables
             e0, eb_t, ee_t = self.noise_tables
@@ -432,7 +467,7 @@ class ShardedSampled:
                                           self._tail_idx, DP_TAIL, pe.tables["grads"] if pe else None, self.p, s),
                 "vfmb_shard_pack_grads")
         if pe:
-            L.check(lib.vfmb_shard_put_small(self.tail.data_ptr(), DP_TAIL, SMALL_PITCH, pe.tables["small1"], P, self.p, s),
+            L.check(lib.vfmb_shard_put_small(self.tail.data_ptr(), DP_TAIL, SMALL_PITCH, pe.tables["tail"], P, self.p, s),
                     "vfmb_shard_put_small")
             return None, None
         return self._gsend.view(P, self.CAP, d + 1), self.tail
@@ -447,7 +482,7 @@ class ShardedSampled:
         io, tab, s, lib = self._io_o, self._tables(), current_stream(self.device), L.lib()
         if pe:
             recv_g = pe.grads
-            L.check(lib.vfmb_shard_sum_small(pe.small[1].data_ptr(), self.P, DP_TAIL, SMALL_PITCH, self._tailg.data_ptr(), s),
+            L.check(lib.vfmb_shard_sum_small(pe.tail.data_ptr(), self.P, DP_TAIL, SMALL_PITCH, self._tailg.data_ptr(), s),
                     "vfmb_shard_sum_small")
             tail_global = self._tailg
         else:
@@ -471,23 +506,10 @@ class ShardedSampled:
         ex = self.exchange
         mark = self._mark
         if self.peer is not None:       # peer memory: the pack kernels are the all-to-alls
-            pe = self.peer
+            self._use_slot(0)
             mark("start")
-            self.phase_request(x_local, y_local)
-            mark("request")
-            pe.barrier(0)
-            mark("a2a_ids")
-            self.phase_owner_stage(None, None)
-            mark("owner_stage")
-            pe.barrier(1)
-            mark("a2a_rows")
-            self.phase_local(None)
-            mark("local")
-            pe.barrier(2)
-            mark("a2a_grads")
-            out = self.phase_owner_update(None, None)
-            mark("owner_update")
-            return out
+            self._phase_a(x_local, y_local, mark)
+            return self._phase_b(mark)
         mark("start")
         send, z = self.phase_request(x_local, y_local)
         mark("request")
@@ -504,6 +526,29 @@ class ShardedSampled:
         tail = ex.all_reduce(tail)
         mark("a2a_grads")
         out = self.phase_owner_update(recv_g, tail)
+        mark("owner_update")
+        return out
+
+    def _phase_a(self, x_local, y_local, mark=lambda name: None) -> None:
+        """Peer mode, everything that depends only on the ids of the batch (current slot): local
+        plan, request exchange, the owner's plan and global counts."""
+        self.phase_request(x_local, y_local)
+        mark("request")
+        self.peer.barrier(0)
+        mark("a2a_ids")
+        self._owner_prepare(None, None)
+
+    def _phase_b(self, mark=lambda name: None) -> dict:
+        """Peer mode, the parameter-dependent part of the step (current slot)."""
+        self._owner_sample()
+        mark("owner_stage")
+        self.peer.barrier(1)
+        mark("a2a_rows")
+        self.phase_local(None)
+        mark("local")
+        self.peer.barrier(2)
+        mark("a2a_grads")
+        out = self.phase_owner_update(None, None)
         mark("owner_update")
         return out
 
@@ -562,3 +607,67 @@ class ShardedSampled:
         n = len(range(self.p, self.R, self.P))
         gid = torch.arange(self.p, self.R, self.P, device=self.device)
         return gid, self.bias[:n], self.entity[:n]
+
+
+class ShardedPipeline:
+    """Software-pipelined, CUDA-graphed mode-B loop over NVLink peer memory (fixed batch size).
+
+    A step has an id-only part A (local plan, request exchange, owner's plan and global counts) and
+    a parameter-dependent part B (sample rows -> exchange -> score / segmented sums -> exchange ->
+    owner update).  Graph s holds B of the batch in slot s on the main branch and A of the NEXT
+    batch (slot s^1) on a side branch: both plans and the id exchange leave the critical path.
+    A uses barrier channel 0, B channels 1 and 2; the request / Z_f regions are double-buffered.
+
+        pipe = ShardedPipeline(model)
+        pipe.start(x0, y0)
+        for x_next, y_next in batches[1:]:
+            out = pipe.step(x_next, y_next)      # runs the step on the previously staged batch
+        out = pipe.step()                         # last staged batch
+    """
+
+    def __init__(self, model: ShardedSampled):
+        assert model.peer is not None, "ShardedPipeline needs exchange='peer'"
+        assert getattr(model, "_timing", None) is None, "disable phase timing before capturing"
+        m, dev = model, model.device
+        self.m = m
+        self.xs = [torch.zeros((m.B, m.F), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.ys = [torch.zeros(m.B, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=dev, priority=-1)
+        self.head = 0
+        self.graphs, self.outs = [], []
+        torch.cuda.synchronize(dev)
+        L.check(L.lib().vfmb_set_grid_reserve(1), "vfmb_set_grid_reserve")
+        try:
+            for s in (0, 1):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    cur = torch.cuda.current_stream(dev)
+                    self.side.wait_stream(cur)                   # fork
+                    with torch.cuda.stream(self.side):
+                        m._use_slot(s ^ 1)
+                        m._phase_a(self.xs[s ^ 1], self.ys[s ^ 1])
+                    m._use_slot(s)
+                    m._y = self.ys[s]                            # targets of the batch staged in slot s
+                    out = m._phase_b()
+                    cur.wait_stream(self.side)                   # join
+                self.graphs.append(g)
+                self.outs.append(out)
+        finally:
+            L.lib().vfmb_set_grid_reserve(0)
+
+    def start(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Stage the first batch and run its part A (outside the graphs)."""
+        self.head = 0
+        self.xs[0].copy_(x, non_blocking=True)
+        self.ys[0].copy_(y, non_blocking=True)
+        self.m._use_slot(0)
+        self.m._phase_a(self.xs[0], self.ys[0])
+
+    def step(self, x_next: Optional[torch.Tensor] = None, y_next: Optional[torch.Tensor] = None) -> dict:
+        s = self.head
+        if x_next is not None:
+            self.xs[s ^ 1].copy_(x_next, non_blocking=True)
+            self.ys[s ^ 1].copy_(y_next, non_blocking=True)
+        self.graphs[s].replay()
+        self.head = s ^ 1
+        return self.outs[s]
