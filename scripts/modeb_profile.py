@@ -6,6 +6,7 @@ from vae_b200 import synth
 from vae_b200.dist import ShardedSampled
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+NIT = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 dev = torch.device("cuda", 0)
 w = synth.make_workload("ml20m", n_rows=2_000_000)
 B, d = w.batch, w.d
@@ -26,10 +27,10 @@ def timed(name, fn, acc):
 acc = {}
 nb = x.shape[0] // B
 import cProfile, pstats
-for it in range(6):
+for it in range(NIT):
     xs = [x[((it * P + p) % nb) * B:((it * P + p) % nb + 1) * B] for p in range(P)]
     ys = [y[((it * P + p) % nb) * B:((it * P + p) % nb + 1) * B] for p in range(P)]
-    if it == 5:
+    if it == 5 and NIT == 6:
         torch.cuda.synchronize()
         pr = cProfile.Profile(); pr.enable(); ranks[0].phase_request(xs[0], ys[0]); pr.disable()
         pstats.Stats(pr).sort_stats("tottime").print_stats(8)
@@ -42,6 +43,9 @@ for it in range(6):
     tail = sum(t[1].clone() for t in loc)
     grads = a2a([t[0] for t in loc])
     outs = [timed("owner_update", lambda r=r, g=g: r.phase_owner_update(g, tail.clone()), acc) for r, g in zip(ranks, grads)]
+    if NIT > 6 and it % 5 == 0:
+        print("it", it, "loss", outs[0]["loss"].item(), "kl", outs[0]["kl"].item(), "scalars", ranks[0].scalars.tolist(),
+              "finite params", all(bool(torch.isfinite(r.entity).all()) for r in ranks), flush=True)
 for k, v in acc.items():
     v = np.array(v[P * 2:])
     print(f"{k:14s} gpu {v[:, 0].mean():8.3f} ms   host-enqueue {v[:, 1].mean():8.3f} ms (per rank)")

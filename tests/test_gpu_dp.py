@@ -89,7 +89,7 @@ def _run_sharded_emulated(ranks, xs, ys):
     return [r.phase_owner_update(g_, tail.clone()) for r, g_ in zip(ranks, grads)]
 
 
-@pytest.mark.parametrize("P", [2, 3, 4])
+@pytest.mark.parametrize("P", [2, 3, 4, 8])
 @pytest.mark.parametrize("name", ["sampled_reg_d64", "sampled_fraction"])
 def test_row_sharded_mode_b_equals_single_process_step(name, P):
     """Mode B (row-sharded tables, all-to-all of sampled rows and gradients), P ranks emulated on one

@@ -301,6 +301,11 @@ class ShardedSampled:
             g = torch.Generator(device=dev).manual_seed(seed * 1000003 + p)
             bias = torch.randn(Rl, 2, generator=g, device=dev)
             ent = torch.randn(Rl, 2 * d, generator=g, device=dev)
+            # CUDA randn returns exactly 0 with probability ~2^-24 per draw (Box-Muller on u = 1): a raw
+            # scale of 0 is sigma = 0 under the abs link, i.e. an infinite KL -- in the reference too
+            # (vfm-torch.py:126, 290-295).  Millions of draws per shard hit it; keep |raw scale| >= 1e-4.
+            for t in (bias[:, 1:], ent[:, d:]):
+                t.copy_(torch.where(t.abs() < 1e-4, torch.full_like(t, 1e-4), t))
             scal = torch.tensor([0.5, 0.0, 1.0, 0.0])
         bias[len(mine):] = torch.tensor([0.0, 1.0], device=bias.device)   # unused + sentinel rows: KL minimum
         ent[len(mine):, :d] = 0.0
