@@ -50,11 +50,7 @@ template <int VEC>
 __device__ __forceinline__ Vec<VEC> ld_vec_cs(const float* p) {
     Vec<VEC> r;
     if constexpr (VEC == 4) {
-#ifdef VFMB_X_NOCS
-        float4 t = *reinterpret_cast<const float4*>(p);
-#else
         float4 t = __ldcs(reinterpret_cast<const float4*>(p));
-#endif
         r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
     } else {
         r.v[0] = __ldcs(p);
@@ -64,11 +60,7 @@ __device__ __forceinline__ Vec<VEC> ld_vec_cs(const float* p) {
 template <int VEC>
 __device__ __forceinline__ void st_vec_cs(float* p, const Vec<VEC>& r) {
     if constexpr (VEC == 4) {
-#ifdef VFMB_X_NOCS
-        *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-#else
         __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
-#endif
     } else {
         __stcs(p, r.v[0]);
     }

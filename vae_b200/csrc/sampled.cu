@@ -682,11 +682,11 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             AdamDev h, int32_t* __restrict__ adam_step, float kl_scale,
             float* __restrict__ grad_bias, float* __restrict__ grad_entity, FinalArgs fa) {
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
-        // CUT (rows cut by tile boundaries summed here) costs 16 registers = one resident block per SM,
-    // which slowed the kernel by more than k_combine_cut takes: off
-    constexpr bool CUT = false, KLF = FLAVOR == 2;
+    // (summing the rows cut by tile boundaries in here was tried: +16 registers = one resident block
+    // per SM less, which cost more than the separate k_combine_cut launch)
+    constexpr bool KLF = FLAVOR == 2;
     const int U = meta[0];
-    const int d = c.d, dp = c.d + 4;
+    const int d = c.d;
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
     const unsigned gmask = group_mask<LPR>();
@@ -698,79 +698,39 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
     if (MODE == VFMB_ADAM_TOUCHED) adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
     float facc = 0.f;                                     // sum_u c_u * KL_u over this thread's rows
 
-#ifdef VFMB_X_BALANCED
-    // contiguous, equally sized row range per warp (all warps finish together)
-    const int per_warp = ((U + nwarps - 1) / nwarps + GPW - 1) / GPW * GPW;
-    const int w_lo = gwarp * per_warp, w_hi = min(U, w_lo + per_warp);
-    for (int base = w_lo; base < w_hi; base += CH) {
-#else
     for (int base = gwarp * CH; base < U; base += nwarps * CH) {
-#endif
         // ---- lane-parallel: record, prefetch of the row's parameter / moment lines
         const int ul = base + lane;
-#ifdef VFMB_X_BALANCED
-        const bool valid = lane < CH && ul < w_hi;
-#else
         const bool valid = lane < CH && ul < U;
-#endif
-        int rowid_l = 0, tA_l = 0, P_l = 0;
+        int rowid_l = 0;
         float cfac_l = 0.f, klw_l = 0.f;                  // KL weight c_u, and c_u * KL(bias) of the lane's row
         if (valid) {
             const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
             rowid_l = rec.x;
             const size_t eoff = (size_t)rowid_l * 2 * d;
-#ifndef VFMB_X_NOPREFETCH
             prefetch_row(entity + eoff, 8 * d);
             if (MODE == VFMB_ADAM_TOUCHED) {
                 prefetch_row(entity_m + eoff, 8 * d);
                 prefetch_row(entity_v + eoff, 8 * d);
             }
-#endif
             const float cq_l = __ldg(cq + ul);
             cfac_l = kl_scale * cq_l;
             klw_l = cq_l;
-            if (CUT) {                                     // tiles the row's segment spans beyond its first
-                tA_l = rec.z / kTile;
-                P_l = (rec.z + rec.y - 1) / kTile - tA_l;
-                if (P_l > kHotPartials) P_l = 0;           // hot row: k_combine_hot finished it
-            }
-            // bias row now (nothing stays live across the wide work), unless the row is cut by a
-            // tile boundary: its g_w only exists after the group below has summed the partials
-            if (!CUT || P_l == 0)
-                bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, grad_bias, rowid_l, __ldg(gws + ul),
-                                             __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
+            // bias row now: nothing of it stays live across the wide work
+            bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, grad_bias, rowid_l, __ldg(gws + ul),
+                                         __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
         }
-        float klrow = 0.f, gwh = 0.f;
+        float klrow = 0.f;
         // ---- wide work: GPW rows per round
 #pragma unroll 1
         for (int it = 0; it < kRounds; ++it) {
             const int sel = it * GPW + gidx;
             const int rowid = bcast(rowid_l, sel);
             const float cfac = bcast(cfac_l, sel);
-            const int tA = CUT ? bcast(tA_l, sel) : 0, P = CUT ? bcast(P_l, sel) : 0;
             const int u = base + sel;
-            float kl = 0.f, gwc = 0.f;
-#ifdef VFMB_X_BALANCED
-            if (u < w_hi) {
-#else
+            float kl = 0.f;
             if (u < U) {
-#endif
                 const size_t eoff = (size_t)rowid * 2 * d;
-                Vec<VEC> gsum[NV];
-                if (CUT && P > 0) {                        // group-uniform: tail(tA) + heads(tA+1 .. tA+P)
-                    sum_head_slots<VEC, LPR, NV, 2>(fa.gslot, dp, d, gl, tA + 1, tA + P + 1, gsum, gwc);
-                    const float* tp = fa.gslot + ((size_t)tA * 2 + 1) * dp;
-                    gwc = __ldg(tp + d) + gwc;
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        int k = (gl + i * LPR) * VEC;
-                        if (k < d) {
-                            const Vec<VEC> t = ld_vec_nc<VEC>(tp + k);
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) gsum[i].v[j] = t.v[j] + gsum[i].v[j];
-                        }
-                    }
-                }
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     int k = (gl + i * LPR) * VEC;
@@ -784,15 +744,12 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
                             m1 = ld_vec_cs<VEC>(entity_m + eoff + k); m2 = ld_vec_cs<VEC>(entity_m + eoff + d + k);
                             v1 = ld_vec_cs<VEC>(entity_v + eoff + k); v2 = ld_vec_cs<VEC>(entity_v + eoff + d + k);
                         }
-                        Vec<VEC> g;
-                        if (CUT && P > 0) g = gsum[i]; else g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
+                        const Vec<VEC> g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
                         Vec<VEC> gmu, grho;
                         float quad = 0.f, prodv = 1.f;
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) {
                             const float sig = link_fn<LINK>(rho.v[j]);
-                            if (CUT && P > 0 && c.F > 2)    // pairwise, cut row: sum r_n (S_n - v_u)
-                                g.v[j] = fmaf(-gwc, fmaf(e.v[j], sig, mu.v[j]), g.v[j]);
                             gmu.v[j] = fmaf(cfac, mu.v[j], g.v[j]);
                             grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(g.v[j], e.v[j], cfac * (sig - fast_rcp(sig)));
                             if (KLF) {
@@ -827,16 +784,10 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
                 if (KLF) kl = group_sum<LPR>(kl, gmask);
             }
             if (KLF) hand_back<LPR>(klrow, kl, it, lane);
-            if (CUT) hand_back<LPR>(gwh, gwc, it, lane);
         }
-        // ---- lane-parallel: KL of the rows; bias rows of the cut rows
-        if (valid) {
-            if (CUT && P_l > 0)
-                bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, grad_bias, rowid_l, gwh,
-                                             __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
-            // klw_l is now c_u * KL(bias row) (bias_update), klrow the entity part of the row's KL
-            if (KLF) facc += fmaf(__ldg(cq + ul), klrow, klw_l);
-        }
+        // ---- lane-parallel: KL of the rows -- klw_l is c_u * KL(bias row) (bias_update), klrow the
+        // entity part of the row's KL
+        if (KLF && valid) facc += fmaf(__ldg(cq + ul), klrow, klw_l);
     }
     if (FLAVOR >= 1) {
         // the block that finishes last owns the scalar parameters: every block has read the step
@@ -918,7 +869,7 @@ k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
     extern __shared__ __align__(128) float s_ring[];
     __shared__ __align__(8) uint64_t s_full[NS], s_done[NS], s_empty[NS];
     const int U = meta[0];
-    const int d = c.d, dp = c.d + 4, rowf = 2 * c.d;
+    const int d = c.d, rowf = 2 * c.d;
     const int stage_f = bulk_stage_floats(d, RPS);
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1013,7 +964,6 @@ k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             const bool valid = lane < GPW && ul < hi;
             // bias row of this lane's row: in flight while the stage is awaited and processed
             float2 ab = make_float2(0.f, 1.f), bm = make_float2(0.f, 0.f), bv = make_float2(0.f, 0.f);
-            int tA_l = 0, P_l = 0;
             if (valid) {
                 const size_t boff = (size_t)rec.x * 2;
                 ab = *reinterpret_cast<const float2*>(bias + boff);
@@ -1028,24 +978,8 @@ k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             const int u = u0 + r;
             const int rowid = bcast(rec.x, gidx);
             const float cfac = bcast(cfac_l, gidx);
-            const int tA = bcast(tA_l, gidx), P = bcast(P_l, gidx);
-            float kl = 0.f, gwc = 0.f;
+            float kl = 0.f;
             if (u < hi) {
-                Vec<VEC> gsum[NV];
-                if (P > 0) {                               // group-uniform: tail(tA) + heads(tA+1 .. tA+P)
-                    sum_head_slots<VEC, LPR, NV, 2>(fa.gslot, dp, d, gl, tA + 1, tA + P + 1, gsum, gwc);
-                    const float* tp = fa.gslot + ((size_t)tA * 2 + 1) * dp;
-                    gwc = __ldg(tp + d) + gwc;
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        int k = (gl + i * LPR) * VEC;
-                        if (k < d) {
-                            const Vec<VEC> t = ld_vec_nc<VEC>(tp + k);
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) gsum[i].v[j] = t.v[j] + gsum[i].v[j];
-                        }
-                    }
-                }
                 float* pP = sp + (0 * RPS + r) * rowf;
                 float* pM = sp + (1 * RPS + r) * rowf;
                 float* pV = sp + (2 * RPS + r) * rowf;
@@ -1058,8 +992,7 @@ k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
                         Vec<VEC> mu = ld_vec<VEC>(pP + k), rho = ld_vec<VEC>(pP + d + k);
                         Vec<VEC> m1 = ld_vec<VEC>(pM + k), m2 = ld_vec<VEC>(pM + d + k);
                         Vec<VEC> v1 = ld_vec<VEC>(pV + k), v2 = ld_vec<VEC>(pV + d + k);
-                        Vec<VEC> g;
-                        if (P > 0) g = gsum[i]; else g = ld_vec<VEC>(pG + k);
+                        const Vec<VEC> g = ld_vec<VEC>(pG + k);
                         Vec<VEC> e;
                         if (eps_entity) e = ld_vec<VEC>(pE + k);
                         else e = entity_eps<VEC>(nullptr, c, u, rowid * c.row_stride + c.row_offset, k, step);
@@ -1067,8 +1000,7 @@ k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) {
                             const float sig = link_fn<LINK>(rho.v[j]);
-                            float gj = g.v[j];
-                            if (P > 0 && c.F > 2) gj = fmaf(-gwc, fmaf(e.v[j], sig, mu.v[j]), gj);
+                            const float gj = g.v[j];
                             const float gmu = fmaf(cfac, mu.v[j], gj);
                             const float grho = link_grad<LINK>(rho.v[j]) * fmaf(gj, e.v[j], cfac * (sig - fast_rcp(sig)));
                             const float vr = sig * sig;
@@ -1098,14 +1030,13 @@ k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_done[st]);
             // ---- lane-parallel: bias row, KL of the row
-            float klrow = 0.f, gwh = 0.f;
+            float klrow = 0.f;
 #pragma unroll
             for (int g = 0; g < GPW; ++g) {
-                const float kv = __shfl_sync(0xffffffffu, kl, g * LPR), gv = __shfl_sync(0xffffffffu, gwc, g * LPR);
-                if (lane == g) { klrow = kv; gwh = gv; }
+                const float kv = __shfl_sync(0xffffffffu, kl, g * LPR);
+                if (lane == g) klrow = kv;
             }
             if (valid) {
-                if (P_l > 0) gw_l = gwh;
                 const size_t boff = (size_t)rec.x * 2;
                 const float tau = link_fn<LINK>(ab.y);
                 facc = fmaf(cq_l, klrow + kl_std_normal(ab.x, tau), facc);
