@@ -267,7 +267,8 @@ def run_ours(args):
                           "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak, "unit": "GB/s"},
         # own kernels per step: plan 9 (sort 2 x [hist, scan, scatter] + heads, scatter, finish) + step 5
         # (stage, score, gather, combine_cut, adam_rows); eager F=2 steps fuse score+gather (4)
-        "e2e": e2e, "gpu_launches": {"graph": 14, "prefetch": 13, "inline": 13, "cached": 4}[args.plan] * K,
+        "e2e": e2e, "gpu_launches": ({"graph": 14, "prefetch": 13, "inline": 13, "cached": 4}[args.plan] if world == 1
+                                     else 18) * K * world,   # mode A: plan 9 + 6 step kernels + 3 all-reduce glue
         "library_launches_per_step": "none (2 cudaMemsetAsync nodes in the plan)" if args.plan != "cached" else "none",
         "clocks": clocks, "final_loss": loss,
     }
@@ -515,7 +516,10 @@ def run_sharded(args):
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes": step_bytes},
             "e2e": {"value": Ke * B * world / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * F * 8 + B * 4,
                     "d2h_bytes_per_step": 16 * 4, "steps": Ke, "ms_per_step": ms_e / Ke},
-            "gpu_launches": None, "clocks": clocks, "final_loss": loss, "phase_ms": phases,
+            # own kernels per rank and step: part A 25 (two plans of 9, bucketing 3, request / Z_f glue 4),
+            # part B 14 (stage, pack, unpack, score, gather + combine twice, pack, glue 3, adam_rows, scalars);
+            # the 3 barriers are torch symmetric-memory kernels (peer) / the collectives are NCCL (nccl)
+            "gpu_launches": 39 * K * world, "clocks": clocks, "final_loss": loss, "phase_ms": phases,
         }
         print(json.dumps(out_json), flush=True)
     torch.cuda.synchronize()
