@@ -1255,8 +1255,15 @@ static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, c
         return set_error(VFMB_EINVAL, "vfmb_sampled_step: scratch required");
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
+    // one lane group per tile.  (Smaller blocks were tried for the plan-overlapped step -- 121.9 us with
+    // 128 threads, 125.2 us with 64, against 113.4 us for the unfused pair: the fused kernel does not
+    // lose to the plan through SM slots; VFMB_GS_BLOCK overrides for experiments.)
+    static const int gs_block_env = [] { const char* e = getenv("VFMB_GS_BLOCK"); return e ? atoi(e) : 0; }();
+    const int gs_block = gs_block_env ? gs_block_env : 256;
+    const int64_t gs_warps = (cap.n_tiles + (32 / L.lpr) - 1) / (32 / L.lpr);
+    const int gs_grid = (int)((gs_warps + gs_block / 32 - 1) / (gs_block / 32));
 #define LAUNCH_GS(LINK, LIK)                                                                             \
-    k_gather_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_gather_score<VEC, LPR, NV, LINK, LIK>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>( \
+    k_gather_score<VEC, LPR, NV, LINK, LIK><<<gs_grid, gs_block, 0, stream>>>(                           \
         dc, tab->scalars, plan->partner, plan->pos_rank, plan->occ, io->vs, io->ws, io->y, io->eps_global, \
         tab->adam_step, io->pred, io->mean, io->resid, gslot, io->grow, io->gws, io->partials,           \
         io->counters + 1, io->stats)
