@@ -1261,7 +1261,8 @@ static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, c
     static const int gs_block_env = [] { const char* e = getenv("VFMB_GS_BLOCK"); return e ? atoi(e) : 0; }();
     const int gs_block = gs_block_env ? gs_block_env : 256;
     const int64_t gs_warps = (cap.n_tiles + (32 / L.lpr) - 1) / (32 / L.lpr);
-    const int gs_grid = (int)((gs_warps + gs_block / 32 - 1) / (gs_block / 32));
+    int gs_grid = (int)((gs_warps + gs_block / 32 - 1) / (gs_block / 32));
+    if (gs_grid > kGridCap) gs_grid = kGridCap;            // block partials are sized for kGridCap blocks
 #define LAUNCH_GS(LINK, LIK)                                                                             \
     k_gather_score<VEC, LPR, NV, LINK, LIK><<<gs_grid, gs_block, 0, stream>>>(                           \
         dc, tab->scalars, plan->partner, plan->pos_rank, plan->occ, io->vs, io->ws, io->y, io->eps_global, \
