@@ -172,7 +172,10 @@ enum { VFMB_ST_LOSS = 0,      /* n_train*mean(nll) + kl           (vfm-torch.py:
        VFMB_ST_NLL_MEAN = 1,  /* mean over batch of -log_prob                        */
        VFMB_ST_KL = 2,        /* KL(global) + rescaled row KL     (vfm-torch.py:320-324) */
        VFMB_ST_SUM_RESID = 3, VFMB_ST_SUM_SQERR = 4, VFMB_ST_KL_ROWS = 5,
-       VFMB_ST_W0 = 6, VFMB_ST_U = 7, VFMB_STATS = 16 };
+       VFMB_ST_W0 = 6, VFMB_ST_U = 7,
+       VFMB_ST_RESID_S = 8,   /* [8] S > 1: sum_n dloss/dpred[s, n] per variational sample  */
+       VFMB_ST_W0_S = 16,     /* [8] S > 1: sampled global bias per variational sample      */
+       VFMB_STATS = 32 };
 
 /* size (in doubles) of vfmb_step_io.partials for this problem */
 int64_t vfmb_partials_doubles(const vfmb_config* cfg /*host*/);

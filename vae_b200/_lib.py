@@ -28,7 +28,8 @@ MAX_FIELDS = 8
 GAUSSIAN, BERNOULLI = 0, 1
 LINK_ABS, LINK_SOFTPLUS = 0, 1
 ADAM_TOUCHED, GRAD_ONLY = 0, 1
-STATS = 16
+STATS = 32
+ST_RESID_S, ST_W0_S, MAX_SAMPLES = 8, 16, 8
 ST_LOSS, ST_NLL_MEAN, ST_KL, ST_SUM_RESID, ST_SUM_SQERR, ST_KL_ROWS, ST_W0, ST_U = range(8)
 S_ALPHA, S_GB_MEAN, S_GB_SCALE, S_COUNT = 0, 1, 2, 4
 C_ALPHA, C_GB_MEAN, C_GB_SCALE, C_GB_PRIOR_MEAN, C_GB_PRIOR_SCALE = 0, 1, 2, 3, 4

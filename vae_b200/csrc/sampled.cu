@@ -17,32 +17,34 @@
 
 namespace vfmb {
 
+// Noise of variational sample s (vfm-torch.py:238-241 draws [S,1], [S,U], [S,U,d]): injected arrays are
+// indexed [s][unique rank] (U = number of unique rows of the batch), Philox carries s in the tag word.
 template <int VEC>
 __device__ __forceinline__ Vec<VEC> entity_eps(const float* __restrict__ eps_entity, const DevCfg& c,
-                                              int u, int rowid, int k, uint32_t step) {
+                                              int u, int rowid, int k, uint32_t step, int s = 0, int U = 0) {
     Vec<VEC> e;
     if (eps_entity) {
-        e = ld_vec_nc<VEC>(eps_entity + (size_t)u * c.d + k);
+        e = ld_vec_nc<VEC>(eps_entity + ((size_t)s * U + u) * c.d + k);
     } else {
         float n4[4];
-        philox_normal4(c.seed, (uint32_t)rowid, (uint32_t)(k / VEC), step, philox_tag(kTagEntity, 0), n4);
+        philox_normal4(c.seed, (uint32_t)rowid, (uint32_t)(k / VEC), step, philox_tag(kTagEntity, s), n4);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) e.v[i] = n4[i];
     }
     return e;
 }
 __device__ __forceinline__ float bias_eps(const float* __restrict__ eps_bias, const DevCfg& c, int u,
-                                          int rowid, uint32_t step) {
-    if (eps_bias) return __ldg(eps_bias + u);
+                                          int rowid, uint32_t step, int s = 0, int U = 0) {
+    if (eps_bias) return __ldg(eps_bias + (size_t)s * U + u);
     float n4[4];
-    philox_normal4(c.seed, (uint32_t)rowid, 0xFFFFFFFFu, step, philox_tag(kTagBias, 0), n4);
+    philox_normal4(c.seed, (uint32_t)rowid, 0xFFFFFFFFu, step, philox_tag(kTagBias, s), n4);
     return n4[0];
 }
 __device__ __forceinline__ float global_eps(const float* __restrict__ eps_global, const DevCfg& c,
-                                            uint32_t step) {
-    if (eps_global) return __ldg(eps_global);
+                                            uint32_t step, int s = 0) {
+    if (eps_global) return __ldg(eps_global + s);
     float n4[4];
-    philox_normal4(c.seed, 0xFFFFFFFFu, 0xFFFFFFFFu, step, philox_tag(kTagGlobal, 0), n4);
+    philox_normal4(c.seed, 0xFFFFFFFFu, 0xFFFFFFFFu, step, philox_tag(kTagGlobal, s), n4);
     return n4[0];
 }
 
@@ -57,10 +59,16 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
         const int32_t* __restrict__ adam_step, float* __restrict__ vs, float* __restrict__ ws,
         float* __restrict__ es, float* __restrict__ ebs, float* __restrict__ cq,
-        double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
+        double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
+        int smp, int u_stride) {
+    // smp: variational sample this launch draws (S > 1: one launch per sample, outputs [S][u_stride]);
+    // the KL and the KL weights do not depend on the sample and are formed by sample 0
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
     const int U = meta[0];
     const int d = c.d;
+    vs += (size_t)smp * u_stride * d; ws += (size_t)smp * u_stride;
+    if (es) es += (size_t)smp * u_stride * d;
+    if (ebs) ebs += (size_t)smp * u_stride;
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
     const unsigned gmask = group_mask<LPR>();
@@ -81,7 +89,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
             const float2 ab = *reinterpret_cast<const float2*>(bias + (size_t)rowid_l * 2);
             const float tcnt = __ldg(train_counts + rowid_l);
             const int gid_l = rowid_l * c.row_stride + c.row_offset;     // global id (row-sharded tables)
-            const float eb = bias_eps(eps_bias, c, ul, gid_l, step);
+            const float eb = bias_eps(eps_bias, c, ul, gid_l, step, smp, U);
             if (!eps_bias) ebs[ul] = eb;
             const float tau = link_fn<LINK>(ab.y);
             ws[ul] = fmaf(eb, tau, ab.x);
@@ -108,7 +116,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                     int k = (gl + i * LPR) * VEC;
                     if (k < d) {
                         const Vec<VEC> mu = ld_vec<VEC>(erow + k), rho = ld_vec<VEC>(erow + d + k);
-                        Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step), out;
+                        Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step, smp, U), out;
                         if (!LEAN && !eps_entity) st_vec<VEC>(es + (size_t)u * d + k, e);
                         if (LEAN) {
 #pragma unroll
@@ -143,7 +151,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         }
         if (valid) facc = fmaf(cqv, klrow + klb, facc);
     }
-    if (LEAN) return;
+    if (LEAN || smp > 0) return;
     double acc[1] = {(double)facc};
     if (block_partials<1>(acc, partials, counter)) {
         double tot[1];
@@ -303,6 +311,142 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
                 stats[VFMB_ST_LOSS] = (float)((double)c.n_train * nll / (double)B + (double)kl);
             }
             stats[VFMB_ST_W0] = w0;
+            *counter = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- k_score_multi
+// S > 1 variational samples (N_VARIATIONAL_SAMPLES, vfm-torch.py:238-245, 264-270): the bias and FM
+// terms are averaged over the samples BEFORE the likelihood, the global bias is not --
+//   pred[s, n] = w0_s + mean_s'(sum_f w_{s'}) + mean_s'(FM_{s'}),   likelihood batch shape [S, B].
+// One lane group per sample n walks the S sampled copies of its rows.  The residual handed to the
+// backward is rho_n = (1/S) sum_s dloss/dpred[s, n] (every sampled copy of a row sees it, since
+// dpred[s', n]/dv_{s,u} = partner_s / S).  Plain structure on purpose: S = 1 is the tuned path.
+constexpr int kMaxSamples = 8;
+template <int VEC, int LPR, int NV, int LINK, int LIK>
+__global__ void __launch_bounds__(256)
+k_score_multi(DevCfg c, int u_stride, const float* __restrict__ scalars, const int32_t* __restrict__ inverse,
+              const int32_t* __restrict__ pos_of, const float* __restrict__ vs, const float* __restrict__ ws,
+              const float* __restrict__ y, const float* __restrict__ eps_global,
+              const int32_t* __restrict__ adam_step, float* __restrict__ pred, float* __restrict__ mean,
+              float* __restrict__ resid, float* __restrict__ rsorted, float* __restrict__ msg,
+              double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
+    constexpr int GPW = kWarp / LPR;
+    const int d = c.d, F = c.F, B = c.B, S = c.S;
+    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const int lane = threadIdx.x & 31, gl = lane % LPR;
+    const unsigned gmask = group_mask<LPR>();
+    const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
+    const int ngroups = gridDim.x * (blockDim.x >> 5) * GPW;
+    const float mu0 = scalars[VFMB_S_GB_MEAN];
+    const float sig0 = link_fn<LINK>(scalars[VFMB_S_GB_SCALE]);
+    const float alpha = link_fn<LINK>(scalars[VFMB_S_ALPHA]);
+    const float half_log_alpha = 0.5f * logf(alpha);
+    const float scale = c.n_train / ((float)S * (float)B);
+    const float inv_s = 1.f / (float)S;
+    float w0s[kMaxSamples];
+#pragma unroll
+    for (int q = 0; q < kMaxSamples; ++q) w0s[q] = q < S ? mu0 + global_eps(eps_global, c, step, q) * sig0 : 0.f;
+    double acc[2 + kMaxSamples];                          // nll, squared error, residual sum per sample
+#pragma unroll
+    for (int q = 0; q < 2 + kMaxSamples; ++q) acc[q] = 0.0;
+
+    for (int n = group; n < B; n += ngroups) {
+        float bsum = 0.f, fmsum = 0.f;
+        for (int q = 0; q < S; ++q) {
+            const float* vq = vs + (size_t)q * u_stride * d;
+            const float* wq = ws + (size_t)q * u_stride;
+            float b = 0.f, part = 0.f;
+            if (F == 2) {
+                const int2 rr = __ldg(reinterpret_cast<const int2*>(inverse) + n);
+                b = __ldg(wq + rr.x) + __ldg(wq + rr.y);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    int k = (gl + i * LPR) * VEC;
+                    if (k < d) {
+                        const Vec<VEC> a = ld_vec_nc<VEC>(vq + (size_t)rr.x * d + k), bb = ld_vec_nc<VEC>(vq + (size_t)rr.y * d + k);
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) part = fmaf(a.v[j], bb.v[j], part);
+                    }
+                }
+            } else {
+                Vec<VEC> ssum[NV], sq[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) { ssum[i].v[j] = 0.f; sq[i].v[j] = 0.f; }
+                for (int f = 0; f < F; ++f) {
+                    const int r = __ldg(inverse + (size_t)n * F + f);
+                    b += __ldg(wq + r);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        int k = (gl + i * LPR) * VEC;
+                        if (k < d) {
+                            const Vec<VEC> a = ld_vec_nc<VEC>(vq + (size_t)r * d + k);
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) { ssum[i].v[j] += a.v[j]; sq[i].v[j] = fmaf(a.v[j], a.v[j], sq[i].v[j]); }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    int k = (gl + i * LPR) * VEC;
+                    if (k < d) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) part += 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]);
+                        if (msg) st_vec<VEC>(msg + ((size_t)q * B + n) * d + k, ssum[i]);   // S_n of sample q
+                    }
+                }
+            }
+            part = group_sum<LPR>(part, gmask);
+            bsum += b; fmsum += part;
+        }
+        if (gl == 0) {
+            const float mb = bsum * inv_s, mf = fmsum * inv_s;
+            const float yn = y ? __ldg(y + n) : 0.f;
+            float rsum = 0.f;
+            for (int q = 0; q < S; ++q) {
+                const float p = w0s[q] + mb + mf;
+                float mu_out = p;
+                if (LIK == VFMB_BERNOULLI) mu_out = 1.f / (1.f + expf(-p));
+                pred[(size_t)q * B + n] = p;
+                mean[(size_t)q * B + n] = mu_out;
+                if (y) {
+                    float nll, r;
+                    const float err = yn - p;
+                    if (LIK == VFMB_GAUSSIAN) {
+                        nll = 0.5f * alpha * err * err - half_log_alpha + 0.9189385332046727f;
+                        r = scale * alpha * (p - yn);
+                    } else {
+                        nll = fmaxf(p, 0.f) - yn * p + log1pf(expf(-fabsf(p)));
+                        r = scale * (mu_out - yn);
+                    }
+                    acc[0] += (double)nll; acc[1] += (double)err * (double)err; acc[2 + q] += (double)r;
+                    rsum += r;
+                }
+            }
+            if (y) {
+                const float rho = rsum * inv_s;
+                resid[n] = rho;
+                for (int f = 0; f < F; ++f) rsorted[__ldg(pos_of + (size_t)n * F + f)] = rho;
+            }
+        }
+    }
+    if (block_partials<2 + kMaxSamples>(acc, partials, counter)) {
+        double tot[2 + kMaxSamples];
+        final_sums<2 + kMaxSamples>(partials, tot);
+        if (threadIdx.x == 0) {
+            const double cnt = (double)S * (double)B;
+            double sr = 0.0;
+            for (int q = 0; q < S; ++q) { sr += tot[2 + q]; stats[VFMB_ST_RESID_S + q] = (float)tot[2 + q]; stats[VFMB_ST_W0_S + q] = w0s[q]; }
+            const float kl = kl_std_normal(mu0, sig0) + stats[VFMB_ST_KL_ROWS];
+            stats[VFMB_ST_NLL_MEAN] = (float)(tot[0] / cnt);
+            stats[VFMB_ST_SUM_RESID] = (float)sr;
+            stats[VFMB_ST_SUM_SQERR] = (float)tot[1];
+            stats[VFMB_ST_KL] = kl;
+            stats[VFMB_ST_LOSS] = (float)((double)c.n_train * tot[0] / cnt + (double)kl);
+            stats[VFMB_ST_W0] = w0s[0];
             *counter = 0;
         }
     }
@@ -609,8 +753,14 @@ __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& 
     float* scalars = fa.scalars; float* stats = fa.stats;
     float alpha = scalars[VFMB_S_ALPHA], mu0 = scalars[VFMB_S_GB_MEAN], rho0 = scalars[VFMB_S_GB_SCALE];
     const float sig0 = link_fn<LINK>(rho0), ap = link_fn<LINK>(alpha);
-    const float e0 = global_eps(fa.eps_global, c, step);
     const double sr = (double)stats[VFMB_ST_SUM_RESID], sq = (double)stats[VFMB_ST_SUM_SQERR];
+    // sum_s eps0_s * (sum_n dloss/dpred[s, n]); one sample: eps0 * sr
+    double e0sr = 0.0;
+    if (c.S > 1) {
+        for (int q = 0; q < c.S; ++q) e0sr += (double)global_eps(fa.eps_global, c, step, q) * (double)stats[VFMB_ST_RESID_S + q];
+    } else {
+        e0sr = (double)global_eps(fa.eps_global, c, step) * sr;
+    }
     if (with_kl) {                                      // loss terms of the pre-update parameters
         const float kl = kl_std_normal(mu0, sig0) + (float)kl_rows;
         stats[VFMB_ST_KL_ROWS] = (float)kl_rows;
@@ -619,7 +769,7 @@ __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& 
         stats[VFMB_ST_U] = (float)U;
     }
     float g_mu0 = (float)(sr + (double)(kl_scale * mu0));
-    float g_rho0 = link_grad<LINK>(rho0) * (float)((double)e0 * sr + (double)(kl_scale * (sig0 - 1.f / sig0)));
+    float g_rho0 = link_grad<LINK>(rho0) * (float)(e0sr + (double)(kl_scale * (sig0 - 1.f / sig0)));
     float g_alpha = 0.f;
     if (fa.likelihood == VFMB_GAUSSIAN) {
         double sc = (double)c.n_train / ((double)c.S * (double)c.B);
@@ -800,6 +950,104 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
                 final_scalars<LINK, MODE>(c, fa, h, adam_step, kl_scale, KLF, tot[0], U);
                 *fa.counter = 0;
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- k_adam_rows_multi
+// S > 1: the row gradient is the sum over the S sampled copies of the row,
+//   d/dmu = sum_s g_s + c_u mu,   d/drho = sign(rho) (sum_s g_s * eps_s + c_u (sigma - 1/sigma)),
+//   d/da = S g_w + c_u a,         d/db = sign(b) (g_w sum_s eps^w_s + c_u (tau - 1/tau))
+// (g_s = sum_n rho_n partner_s(n): k_gather on sample s; g_w = sum_n rho_n is the same for every s).
+// One lane group per unique row, plain structure (S = 1 is the tuned path).  The block that finishes
+// last updates the scalar parameters, as in k_adam_rows<FLAVOR 1>.
+template <int VEC, int LPR, int NV, int LINK, int MODE>
+__global__ void __launch_bounds__(256)
+k_adam_rows_multi(DevCfg c, int u_stride, float* __restrict__ bias, float* __restrict__ bias_m,
+                  float* __restrict__ bias_v, float* __restrict__ entity, float* __restrict__ entity_m,
+                  float* __restrict__ entity_v, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
+                  const float* __restrict__ eps_bias, const float* __restrict__ eps_entity, int eps_stride,
+                  const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
+                  AdamDev h, int32_t* __restrict__ adam_step, float kl_scale,
+                  float* __restrict__ grad_bias, float* __restrict__ grad_entity, FinalArgs fa) {
+    constexpr int GPW = kWarp / LPR;
+    const int U = meta[0], d = c.d, S = c.S;
+    if (eps_stride < 0) eps_stride = U;                    // injected noise: [S, U, ...]; scratch: [S, u_stride, ...]
+    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const int lane = threadIdx.x & 31, gl = lane % LPR;
+    const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
+    const int ngroups = gridDim.x * (blockDim.x >> 5) * GPW;
+    float step_size = 0.f, inv_bc2 = 1.f;
+    if (MODE == VFMB_ADAM_TOUCHED) adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
+
+    for (int u = group; u < U; u += ngroups) {
+        const int rowid = __ldg(urec + 4 * (size_t)u);
+        const float cfac = kl_scale * __ldg(cq + u);
+        const size_t eoff = (size_t)rowid * 2 * d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            int k = (gl + i * LPR) * VEC;
+            if (k < d) {
+                Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
+                Vec<VEC> gs, ges;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { gs.v[j] = 0.f; ges.v[j] = 0.f; }
+                for (int q = 0; q < S; ++q) {
+                    const Vec<VEC> g = ld_vec_nc<VEC>(grow + ((size_t)q * u_stride + u) * d + k);
+                    const Vec<VEC> e = ld_vec_nc<VEC>(eps_entity + ((size_t)q * eps_stride + u) * d + k);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) { gs.v[j] += g.v[j]; ges.v[j] = fmaf(g.v[j], e.v[j], ges.v[j]); }
+                }
+                Vec<VEC> gmu, grho;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float sig = link_fn<LINK>(rho.v[j]);
+                    gmu.v[j] = fmaf(cfac, mu.v[j], gs.v[j]);
+                    grho.v[j] = link_grad<LINK>(rho.v[j]) * (ges.v[j] + cfac * (sig - fast_rcp(sig)));
+                }
+                if (MODE == VFMB_ADAM_TOUCHED) {
+                    Vec<VEC> m1 = ld_vec<VEC>(entity_m + eoff + k), m2 = ld_vec<VEC>(entity_m + eoff + d + k);
+                    Vec<VEC> v1 = ld_vec<VEC>(entity_v + eoff + k), v2 = ld_vec<VEC>(entity_v + eoff + d + k);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu.v[j], h, step_size, inv_bc2);
+                        adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, inv_bc2);
+                    }
+                    st_vec<VEC>(entity + eoff + k, mu);     st_vec<VEC>(entity + eoff + d + k, rho);
+                    st_vec<VEC>(entity_m + eoff + k, m1);   st_vec<VEC>(entity_m + eoff + d + k, m2);
+                    st_vec<VEC>(entity_v + eoff + k, v1);   st_vec<VEC>(entity_v + eoff + d + k, v2);
+                } else {
+                    st_vec<VEC>(grad_entity + eoff + k, gmu);  st_vec<VEC>(grad_entity + eoff + d + k, grho);
+                }
+            }
+        }
+        if (gl == 0) {                                     // bias row
+            const size_t boff = (size_t)rowid * 2;
+            float2 ab = *reinterpret_cast<const float2*>(bias + boff);
+            const float gw = __ldg(gws + u);
+            float ebsum = 0.f;
+            for (int q = 0; q < S; ++q) ebsum += __ldg(eps_bias + (size_t)q * eps_stride + u);
+            const float tau = link_fn<LINK>(ab.y);
+            const float ga = fmaf(cfac, ab.x, (float)S * gw);
+            const float gb = link_grad<LINK>(ab.y) * fmaf(gw, ebsum, cfac * (tau - fast_rcp(tau)));
+            if (MODE == VFMB_ADAM_TOUCHED) {
+                float2 bm = *reinterpret_cast<const float2*>(bias_m + boff);
+                float2 bv = *reinterpret_cast<const float2*>(bias_v + boff);
+                adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
+                adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
+                *reinterpret_cast<float2*>(bias + boff) = ab;
+                *reinterpret_cast<float2*>(bias_m + boff) = bm;
+                *reinterpret_cast<float2*>(bias_v + boff) = bv;
+            } else {
+                *reinterpret_cast<float2*>(grad_bias + boff) = make_float2(ga, gb);
+            }
+        }
+    }
+    double acc[1] = {0.0};
+    if (block_partials<1>(acc, fa.partials, fa.counter)) {
+        if (threadIdx.x == 0) {
+            final_scalars<LINK, MODE>(c, fa, h, adam_step, kl_scale, false, 0.0, U);
+            *fa.counter = 0;
         }
     }
 }
@@ -1082,16 +1330,20 @@ __global__ void k_step_advance(int32_t* adam_step) { adam_step[0] += 1; }
 template <int VEC>
 __global__ void k_philox_export(DevCfg c, const int32_t* __restrict__ uniq, int U, uint32_t step,
                                 float* eps_global, float* eps_bias, float* eps_entity) {
+    // layout of the reference's draws (vfm-torch.py:238-241): [S,1], [S,U], [S,U,d]
     int nvec = (c.d + VEC - 1) / VEC;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)U * nvec;
+    const int64_t per = (int64_t)U * nvec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per * c.S;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int u = (int)(i / nvec), j = (int)(i % nvec);
+        const int q = (int)(i / per);
+        const int64_t r = i - (int64_t)q * per;
+        int u = (int)(r / nvec), j = (int)(r % nvec);
         int rowid = uniq[u];
-        Vec<VEC> e = entity_eps<VEC>(nullptr, c, u, rowid, j * VEC, step);
+        Vec<VEC> e = entity_eps<VEC>(nullptr, c, u, rowid, j * VEC, step, q, U);
         for (int t = 0; t < VEC; ++t)
-            if (j * VEC + t < c.d) eps_entity[(size_t)u * c.d + j * VEC + t] = e.v[t];
-        if (j == 0) eps_bias[u] = bias_eps(nullptr, c, u, rowid, step);
-        if (i == 0) eps_global[0] = global_eps(nullptr, c, step);
+            if (j * VEC + t < c.d) eps_entity[((size_t)q * U + u) * c.d + j * VEC + t] = e.v[t];
+        if (j == 0) eps_bias[(size_t)q * U + u] = bias_eps(nullptr, c, u, rowid, step, q, U);
+        if (r == 0) eps_global[q] = global_eps(nullptr, c, step, q);
     }
 }
 
@@ -1130,7 +1382,7 @@ static int prep(const vfmb_config* cfg, const char* who, vfmb_stream stream_, in
     if (!cfg) return set_error(VFMB_EINVAL, "%s: null config", who);
     if (cfg->B <= 0 || cfg->R <= 0 || cfg->d <= 0) return set_error(VFMB_EINVAL, "%s: bad B/R/d", who);
     if (cfg->F < min_fields || cfg->F > VFMB_MAX_FIELDS) return set_error(VFMB_ESHAPE, "%s: F must be %d..%d", who, min_fields, VFMB_MAX_FIELDS);
-    if (cfg->S != 1) return set_error(VFMB_ESHAPE, "%s: S=%d variational samples not supported yet (S=1)", who, cfg->S);
+    if (cfg->S < 1 || cfg->S > kMaxSamples) return set_error(VFMB_ESHAPE, "%s: S=%d variational samples (1..%d)", who, cfg->S, kMaxSamples);
     if (cfg->n_classes < 1 || cfg->n_classes > VFMB_MAX_FIELDS) return set_error(VFMB_EINVAL, "%s: bad n_classes", who);
     if (cfg->likelihood != VFMB_GAUSSIAN && cfg->likelihood != VFMB_BERNOULLI) return set_error(VFMB_EINVAL, "%s: bad likelihood", who);
     if (cfg->link != VFMB_LINK_ABS && cfg->link != VFMB_LINK_SOFTPLUS) return set_error(VFMB_EINVAL, "%s: bad link", who);
@@ -1145,7 +1397,7 @@ static int prep(const vfmb_config* cfg, const char* who, vfmb_stream stream_, in
 
 // ---- internal launchers (the public entry points below are thin wrappers)
 static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                        const vfmb_step_io* io, vfmb_stream stream_, bool lean) {
+                        const vfmb_step_io* io, vfmb_stream stream_, bool lean, int smp = 0) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_stage", stream_, 1, &P);
     if (rc) return rc;
@@ -1159,7 +1411,7 @@ static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     k_stage<VEC, LPR, NV, LINK, LEAN><<<grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, ch), 256, 0, stream>>>( \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
         io->eps_bias, io->eps_entity, tab->adam_step, io->vs, io->ws, io->es,                          \
-        io->ebs, io->cq, io->partials, io->counters + 0, io->stats)
+        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) { if (lean) LAUNCH_STAGE(0, 1); else LAUNCH_STAGE(0, 0); }
         else                            { if (lean) LAUNCH_STAGE(1, 1); else LAUNCH_STAGE(1, 0); }
@@ -1194,29 +1446,80 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     return 0;
 }
 
+#define VFMB_PHASE_S1(who)                                                                             \
+    if (cfg && cfg->S != 1) return set_error(VFMB_ESHAPE, who ": the phase entry points take S = 1 (use "    \
+                                             "vfmb_sampled_forward / _backward / _step for S > 1)")
+
 extern "C" int vfmb_sampled_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                   const vfmb_step_io* io, vfmb_stream stream) {
+    VFMB_PHASE_S1("vfmb_sampled_stage");
     return launch_stage(cfg, tab, plan, io, stream, false);
 }
 
 extern "C" int vfmb_sampled_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                   const vfmb_step_io* io, vfmb_stream stream) {
+    VFMB_PHASE_S1("vfmb_sampled_score");
     return launch_score(cfg, tab, plan, io, stream, 0);
+}
+
+// S > 1: one k_stage launch per variational sample (non-lean: the noise of every sample is kept in
+// the [S][u_cap] scratch for the backward), then k_score_multi
+static int forward_multi(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                         const vfmb_step_io* io, vfmb_stream stream_) {
+    for (int q = 0; q < cfg->S; ++q) {
+        int rc = launch_stage(cfg, tab, plan, io, stream_, false, q);
+        if (rc) return rc;
+    }
+    Prep P;
+    int rc = prep(cfg, "vfmb_sampled_forward", stream_, 2, &P);
+    if (rc) return rc;
+    if (cfg->F > 2 && io->y && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: msg scratch required for F>2");
+    if (!io->pred || !io->mean || !io->resid || !io->rsorted) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: outputs required");
+    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream;
+    int grid = (int)((cfg->B + 8 * (32 / L.lpr) - 1) / (8 * (32 / L.lpr)));
+    if (grid > kGridCap) grid = kGridCap;
+#define LAUNCH_SM(LINK, LIK)                                                                             \
+    k_score_multi<VEC, LPR, NV, LINK, LIK><<<grid, 256, 0, stream>>>(                                    \
+        dc, (int)P.cap.u_cap, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->y, io->eps_global, \
+        tab->adam_step, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials, io->counters + 1, io->stats)
+    VFMB_LAYOUT_SWITCH(L, {
+        if (cfg->link == VFMB_LINK_ABS) {
+            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SM(0, VFMB_GAUSSIAN); else LAUNCH_SM(0, VFMB_BERNOULLI);
+        } else {
+            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SM(1, VFMB_GAUSSIAN); else LAUNCH_SM(1, VFMB_BERNOULLI);
+        }
+    });
+#undef LAUNCH_SM
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                     const vfmb_step_io* io, vfmb_stream stream) {
+    if (cfg && cfg->S > 1) {
+        if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_forward: null argument");
+        return forward_multi(cfg, tab, plan, io, stream);
+    }
     int rc = launch_stage(cfg, tab, plan, io, stream, false);
     if (rc) return rc;
     return launch_score(cfg, tab, plan, io, stream, 0);
 }
 
-static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
-                         const float* table, int32_t unit_coef, vfmb_stream stream_) {
+static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io_,
+                         const float* table, int32_t unit_coef, vfmb_stream stream_, int smp = 0) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_gather", stream_, 1, &P);
     if (rc) return rc;
-    if (!plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: null argument");
+    if (!plan || !io_) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: null argument");
+    vfmb_step_io shifted = *io_;                           // sample smp of the [S][u_cap] / [S][B] scratch
+    if (smp > 0) {
+        const size_t us = (size_t)P.cap.u_cap;
+        shifted.vs += smp * us * cfg->d;
+        if (shifted.grow) shifted.grow += smp * us * cfg->d;
+        if (shifted.gws) shifted.gws += smp * us;
+        if (shifted.msg) shifted.msg += (size_t)smp * cfg->B * cfg->d;
+    }
+    const vfmb_step_io* io = &shifted;
     if (!io->grow || !io->gws || !io->rsorted || !io->partials) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: scratch required");
     const Layout& L = P.L; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
@@ -1286,6 +1589,7 @@ static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, c
 
 extern "C" int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
                                    const float* table, int32_t unit_coef, vfmb_stream stream) {
+    VFMB_PHASE_S1("vfmb_sampled_gather");
     return launch_gather(cfg, plan, io, table, unit_coef, stream);
 }
 
@@ -1391,7 +1695,54 @@ static int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfm
 extern "C" int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                       const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
                                       float kl_grad_scale, vfmb_stream stream) {
+    VFMB_PHASE_S1("vfmb_sampled_adam_rows");
     return launch_adam(cfg, tab, plan, io, adam, mode, kl_grad_scale, 0, stream);
+}
+
+// S > 1: k_adam_rows_multi on the [S][u_cap] gradients / noise
+static int launch_adam_multi(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                             const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode, float kl_grad_scale,
+                             vfmb_stream stream_) {
+    Prep P;
+    int rc = prep(cfg, "vfmb_sampled_backward", stream_, 2, &P);
+    if (rc) return rc;
+    if (mode == VFMB_ADAM_TOUCHED && (!adam || !tab->entity_m || !tab->entity_v || !tab->bias_m || !tab->bias_v ||
+                                      !tab->adam_step || !tab->scalars_m || !tab->scalars_v))
+        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: Adam state required");
+    if (mode == VFMB_GRAD_ONLY && (!io->grad_bias || !io->grad_entity))
+        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: gradient outputs required");
+    if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: bad mode");
+    if (!io->grow || !io->gws || !io->cq || !tab->scalars || !io->stats || !io->partials || !io->counters)
+        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: scratch required");
+    // the noise of the forward: injected arrays [S, U, ...] or what k_stage kept [S, u_cap, ...]
+    const float* eps_e = io->eps_entity ? io->eps_entity : io->es;
+    const float* eps_b = io->eps_bias ? io->eps_bias : io->ebs;
+    if (!eps_e || !eps_b || (io->eps_entity != nullptr) != (io->eps_bias != nullptr))
+        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: noise of the forward required (both arrays injected, or none)");
+    const int eps_stride = io->eps_entity ? -1 : (int)P.cap.u_cap;
+    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
+    AdamDev h = make_adam(adam);
+    FinalArgs fa{};
+    fa.scalars = tab->scalars; fa.sm = tab->scalars_m; fa.sv = tab->scalars_v; fa.stats = io->stats;
+    fa.eps_global = io->eps_global; fa.grad_scalars = io->grad_scalars; fa.partials = io->partials;
+    fa.counter = io->counters + 2; fa.gslot = nullptr; fa.likelihood = cfg->likelihood;
+    int grid = (int)((cap.u_cap + 8 * (32 / L.lpr) - 1) / (8 * (32 / L.lpr)));
+    if (grid > kGridCap) grid = kGridCap;
+#define LAUNCH_AM(LINK, MODE)                                                                            \
+    k_adam_rows_multi<VEC, LPR, NV, LINK, MODE><<<grid, 256, 0, stream>>>(                               \
+        dc, (int)cap.u_cap, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v, \
+        plan->urec, plan->meta, eps_b, eps_e, eps_stride, io->cq, io->grow, io->gws, h, tab->adam_step,  \
+        kl_grad_scale, io->grad_bias, io->grad_entity, fa)
+    VFMB_LAYOUT_SWITCH(L, {
+        if (cfg->link == VFMB_LINK_ABS) {
+            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_AM(0, VFMB_ADAM_TOUCHED); else LAUNCH_AM(0, VFMB_GRAD_ONLY);
+        } else {
+            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_AM(1, VFMB_ADAM_TOUCHED); else LAUNCH_AM(1, VFMB_GRAD_ONLY);
+        }
+    });
+#undef LAUNCH_AM
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 static int backward_impl(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
@@ -1411,6 +1762,13 @@ static int backward_impl(const vfmb_config* cfg, const vfmb_tables* tab, const v
         k_scatter_resid<<<g, 256, 0, stream>>>(io->resid, plan->pos_of, N, cfg->F, io->rsorted);
         CUDA_TRY(cudaGetLastError());
     }
+    if (cfg->S > 1) {       // one ordered segmented sum per variational sample, then the summed row update
+        for (int q = 0; q < cfg->S; ++q) {
+            rc = launch_gather(cfg, plan, io, nullptr, 0, stream_, q);
+            if (rc) return rc;
+        }
+        return launch_adam_multi(cfg, tab, plan, io, adam, mode, kl_grad_scale, stream_);
+    }
     rc = launch_gather(cfg, plan, io, nullptr, 0, stream_);
     if (rc) return rc;
     return launch_adam(cfg, tab, plan, io, adam, mode, kl_grad_scale, flavor, stream_);
@@ -1427,6 +1785,12 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
 extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                  const vfmb_step_io* io, const vfmb_adam* adam, vfmb_stream stream) {
     if (io && !io->y) return set_error(VFMB_EINVAL, "vfmb_sampled_step: targets required");
+    if (cfg && cfg->S > 1) {
+        if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_step: null argument");
+        int rc = forward_multi(cfg, tab, plan, io, stream);
+        if (rc) return rc;
+        return backward_impl(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, 1, stream);
+    }
     int rc = launch_stage(cfg, tab, plan, io, stream, true);
     if (rc) return rc;
     // measured (ml20m): alone the fused kernel saves 5 us per step (104 -> 99 us); next to a
@@ -1470,7 +1834,8 @@ extern "C" int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, 
     if (U == 0) return 0;
     DevCfg dc = make_dev(cfg);
     int vec = (cfg->d % 4 == 0) ? 4 : 1;
-    int64_t work = (int64_t)U * ((cfg->d + vec - 1) / vec);
+    if (cfg->S < 1 || cfg->S > kMaxSamples) return set_error(VFMB_ESHAPE, "vfmb_philox_normals: S=%d (1..%d)", cfg->S, kMaxSamples);
+    int64_t work = (int64_t)U * ((cfg->d + vec - 1) / vec) * cfg->S;
     int grid = (int)((work + 255) / 256 > 4096 ? 4096 : (work + 255) / 256);
     if (vec == 4) k_philox_export<4><<<grid, 256, 0, (cudaStream_t)stream_>>>(dc, uniq, U, (uint32_t)step, eps_global, eps_bias, eps_entity);
     else k_philox_export<1><<<grid, 256, 0, (cudaStream_t)stream_>>>(dc, uniq, U, (uint32_t)step, eps_global, eps_bias, eps_entity);

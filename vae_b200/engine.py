@@ -265,16 +265,18 @@ class StepBuffers:
                  closed: bool = False):
         B, d = plan.B_cap, cfg.d
         wv, wg = (2, 3) if closed else (1, 1)              # closed form: vs=[mu|rho^2], grow=[A|B|C]
-        self.vs = _f32(plan.u_cap * d * wv, device)
-        self.ws = _f32(plan.u_cap, device)
-        self.es = _f32(plan.u_cap * d, device)
-        self.ebs = _f32(plan.u_cap, device)
+        S = 1 if closed else max(1, int(cfg.S))            # S > 1: [S][u_cap] sampled rows / noise / gradients
+        self.S = S
+        self.vs = _f32(S * plan.u_cap * d * wv, device)
+        self.ws = _f32(S * plan.u_cap, device)
+        self.es = _f32(S * plan.u_cap * d, device)
+        self.ebs = _f32(S * plan.u_cap, device)
         self.cq = _f32(plan.u_cap, device)
-        self.grow = _f32(plan.u_cap * d * wg, device)
-        self.gws = _f32(plan.u_cap, device)
-        self.msg = _f32(B * d * wg, device) if need_msg else None
-        self.pred = _f32(B, device)
-        self.mean = _f32(B, device)
+        self.grow = _f32(S * plan.u_cap * d * wg, device)
+        self.gws = _f32(S * plan.u_cap, device)
+        self.msg = _f32(S * B * d * wg, device) if need_msg else None
+        self.pred = _f32(S * B, device)                    # [S, B] (likelihood batch shape, vfm-torch.py:265)
+        self.mean = _f32(S * B, device)
         self.resid = _f32(B, device)
         self.rsorted = _f32(B * plan.F, device)
         n_part = int(L.lib().vfmb_partials_doubles(C.byref(cfg)))
@@ -314,9 +316,9 @@ class StepResult:
         if key == "stats":
             return self._buf.stats
         if key == "pred":
-            return self._buf.mean[: self._B]
+            return self._buf.mean[: self._B] if self._buf.S == 1 else self._buf.mean[: self._buf.S * self._B].view(self._buf.S, self._B)
         if key == "logits":
-            return self._buf.pred[: self._B]
+            return self._buf.pred[: self._B] if self._buf.S == 1 else self._buf.pred[: self._buf.S * self._B].view(self._buf.S, self._B)
         raise KeyError(key)
 
     def keys(self):

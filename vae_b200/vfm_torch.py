@@ -48,22 +48,25 @@ class _SampledFn(torch.autograd.Function):
         ctx.model, ctx.noise = model, noise
         ctx.e0 = model._global_eps(out)
         ctx.save_for_backward(gb_scale)
-        return out["pred"].reshape(1, -1).clone(), out["kl_rows"].reshape(1).clone()
+        return out["pred"].reshape(model.S, -1).clone(), out["kl_rows"].reshape(1).clone()
 
     @staticmethod
     def backward(ctx, g_pred, g_kl):
         model = ctx.model
         (gb_scale,) = ctx.saved_tensors
-        resid = g_pred.reshape(-1).contiguous().float()
+        # dloss/dpred is [S, B]; every sampled copy of a row sees rho_n = mean_s dloss/dpred[s, n]
+        g_sb = g_pred.reshape(model.S, -1).float()
+        resid = g_sb.mean(dim=0).contiguous()
         g_bias = torch.zeros_like(model.bias_params.weight)
         g_entity = torch.zeros_like(model.entity_params.weight)
         kl_scale = float(g_kl.reshape(-1)[0].item()) if g_kl is not None else 0.0
         model._backward_kernels(ctx.noise, L.GRAD_ONLY, kl_scale, resid=resid, grad_bias=g_bias,
                                 grad_entity=g_entity, want_scalars=False)
-        total = resid.sum()
+        total_s = g_sb.sum(dim=1)                            # [S]: w0_s enters pred[s, :] only
         link = model.link_name
         dlink = torch.sign(gb_scale) if link == "abs" else torch.sigmoid(gb_scale)
-        return g_bias, g_entity, total.reshape(1), (dlink * ctx.e0 * total).reshape(1), None, None, None
+        return (g_bias, g_entity, total_s.sum().reshape(1), (dlink * (ctx.e0 * total_s).sum()).reshape(1),
+                None, None, None)
 
 
 class CF(nn.Module):
@@ -233,17 +236,20 @@ class CF(nn.Module):
         L.check(L.lib().vfmb_sampled_forward(C.byref(self._cfg), C.byref(tab), C.byref(self._plan.struct),
                                              C.byref(io), current_stream(self.device)),
                 "vfmb_sampled_forward")
-        B = self._cfg.B
+        B, S = self._cfg.B, self.S
         st = self._buf.stats
-        return {"pred": self._buf.pred[:B], "mean": self._buf.mean[:B], "stats": st,
+        shape = (B,) if S == 1 else (S, B)                  # likelihood batch shape [S, B] (vfm-torch.py:265)
+        return {"pred": self._buf.pred[:S * B].view(shape), "mean": self._buf.mean[:S * B].view(shape), "stats": st,
                 "kl_rows": st[L.ST_KL_ROWS], "noise": noise}
 
     def _global_eps(self, out):
-        """The N(0,1) draw behind the sampled global bias of the last forward."""
+        """The N(0,1) draws ``[S]`` behind the sampled global bias of the last forward."""
+        S = self.S
         if out["noise"] is not None:
-            return out["noise"][0].reshape(-1)[0].detach()
+            return out["noise"][0].reshape(-1)[:S].detach()
         sig0 = _LINKS[self.link_name](self._scalars[L.S_GB_SCALE])
-        return ((out["stats"][L.ST_W0] - self._scalars[L.S_GB_MEAN]) / sig0).detach()
+        w0 = out["stats"][L.ST_W0:L.ST_W0 + 1] if S == 1 else out["stats"][L.ST_W0_S:L.ST_W0_S + S]
+        return ((w0 - self._scalars[L.S_GB_MEAN]) / sig0).detach()
 
     def _backward_kernels(self, noise, mode, kl_scale, resid=None, grad_bias=None, grad_entity=None,
                           want_scalars=True):
@@ -430,10 +436,11 @@ class CF(nn.Module):
         uniq = uniq.to(self.device, torch.int32).contiguous()
         U = int(uniq.numel())
         step = int(self.adam_step.item()) if step is None else int(step)
-        e0 = torch.empty(1, device=self.device)
-        eb = torch.empty(U, device=self.device)
-        ee = torch.empty(U * self.d, device=self.device)
+        S = self.S
+        e0 = torch.empty(S, device=self.device)
+        eb = torch.empty(S * U, device=self.device)
+        ee = torch.empty(S * U * self.d, device=self.device)
         cfg = self._config(1)
         L.check(L.lib().vfmb_philox_normals(C.byref(cfg), uniq.data_ptr(), U, step, e0.data_ptr(),
                                             eb.data_ptr(), ee.data_ptr(), current_stream(self.device)))
-        return e0.reshape(1, 1), eb.reshape(1, U), ee.reshape(1, U, self.d)
+        return e0.reshape(S, 1), eb.reshape(S, U), ee.reshape(S, U, self.d)
