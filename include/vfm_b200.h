@@ -47,7 +47,9 @@ typedef struct vfmb_config {
     int32_t F;            /* fields (columns of x), 2..VFMB_MAX_FIELDS             */
     int32_t d;            /* embedding size                                        */
     int32_t R;            /* table rows                                            */
-    int32_t S;            /* variational samples (vfm-torch.py:19), currently 1    */
+    int32_t S;            /* variational samples (vfm-torch.py:19), 1 ... 8; S > 1: the
+                             per-row scratch of vfmb_step_io is [S][u_cap,...], pred / mean
+                             are [S,B], the noise arrays [S], [S,U], [S,U,d]              */
     int32_t likelihood;   /* VFMB_GAUSSIAN | VFMB_BERNOULLI                        */
     int32_t link;         /* VFMB_LINK_*                                           */
     int32_t n_classes;    /* KL weighting classes (<= F)                           */
@@ -146,7 +148,7 @@ typedef struct vfmb_step_io {
     const float* eps_global; /* [S]     injected N(0,1) draws, or NULL -> Philox      */
     const float* eps_bias;   /* [S,U]   indexed by unique rank (vfm-torch.py:239)     */
     const float* eps_entity; /* [S,U,d] (vfm-torch.py:241)                            */
-    float* vs;               /* scratch: sampled factor rows  [U_cap,d]               */
+    float* vs;               /* scratch: sampled factor rows  [S][U_cap,d]            */
     float* ws;               /* scratch: sampled biases       [U_cap]                 */
     float* es;               /* scratch: the step's factor noise [U_cap,d] (Philox)   */
     float* ebs;              /* scratch: the step's bias noise   [U_cap]   (Philox)   */
@@ -154,9 +156,9 @@ typedef struct vfmb_step_io {
     float* grow;             /* scratch: dloss/dv per unique row [U_cap,d]            */
     float* gws;              /* scratch: dloss/dw per unique row [U_cap]              */
     float* msg;              /* scratch [B,d], only F>2 (may be NULL for F==2)        */
-    float* pred;             /* [B] unscaled_pred (vfm-torch.py:265)                  */
-    float* mean;             /* [B] likelihood mean: pred or sigmoid(pred) (:363)     */
-    float* resid;            /* [B] dloss/dpred                                       */
+    float* pred;             /* [S,B] unscaled_pred (vfm-torch.py:265)                */
+    float* mean;             /* [S,B] likelihood mean: pred or sigmoid(pred) (:363)   */
+    float* resid;            /* [B] dloss/dpred (S > 1: mean over s of dloss/dpred[s,n]) */
     float* rsorted;          /* [B*F] dloss/dpred per sorted occurrence (scratch)     */
     double* partials;        /* scratch for deterministic reductions                  */
     int32_t* counters;       /* [8] zero-initialised once by the caller               */

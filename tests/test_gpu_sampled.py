@@ -258,15 +258,17 @@ def test_dropin_autograd_path_equals_reference_loop(name):
             assert bad.mean() <= 1e-4, (t, k, float(bad.mean()))
 
 
-def test_philox_mode_matches_oracle_with_exported_noise():
-    meta, g = gu.load("sampled_reg_d64")
+@pytest.mark.parametrize("name", ["sampled_reg_d64", "sampled_class_s2"])
+def test_philox_mode_matches_oracle_with_exported_noise(name):
+    meta, g = gu.load(name)
     m = _model(meta, g, 0, seed=1234)
     x, y = gu.batch_of(meta, g, 0)
     xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
     uniq = torch.from_numpy(g["step0.uniq"])
     noise = m.philox_noise(uniq)
     e = noise[2].reshape(-1).cpu().numpy()
-    assert abs(e.mean()) < 0.02 and abs(e.std() - 1.0) < 0.02 and np.abs(e).max() < 6.5
+    tol = 0.02 if e.size > 50_000 else 0.1                              # the S = 2 golden has 1 600 draws
+    assert abs(e.mean()) < tol and abs(e.std() - 1.0) < tol and np.abs(e).max() < 6.5
     assert torch.equal(m.philox_noise(uniq)[2], noise[2])                 # counter-based: reproducible
     assert not torch.equal(m.philox_noise(uniq, step=1)[2], noise[2])     # new step, new draws
     out = m.fused_step(xd, yd)                                            # Philox inside the kernels
