@@ -416,3 +416,24 @@ def test_graphed_loop_depth3_from_pinned_host_matches_eager():
         losses.append(loop.step()["loss"].item())
     assert losses == ref_losses
     assert torch.equal(m.entity_params.weight, ref.entity_params.weight)
+
+
+def test_training_loop_learns_and_metrics_path():
+    """The reference's loop shape (vfm-torch.py:347-384, 402-422) on the bundled fraction data (golden
+    batch): fused steps with in-kernel Philox noise drive the ELBO down and the train AUC up; the
+    evaluation helper returns the script's test metrics."""
+    from vae_b200 import metrics
+    meta, g = gu.load("sampled_fraction")
+    m = _model(meta, g, 0, seed=11)
+    m.configure_adam(0.05)
+    x, y = gu.batch_of(meta, g, 0)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    first = m.fused_step(xd, yd)
+    loss0, auc0 = first["loss"].item(), metrics.roc_auc(yd, first["pred"]).item()
+    for _ in range(150):
+        out = m.fused_step(xd, yd)
+    loss1, auc1 = out["loss"].item(), metrics.roc_auc(yd, out["pred"]).item()
+    assert np.isfinite(loss1) and loss1 < 0.7 * loss0, (loss0, loss1)
+    assert auc1 > max(0.75, auc0 + 0.1), (auc0, auc1)
+    ev = metrics.evaluate(m, xd[:2000], yd[:2000])
+    assert set(ev) == {"auc", "map"} and 0.7 < ev["auc"].item() <= 1.0 and 0.5 < ev["map"].item() <= 1.0
