@@ -143,3 +143,52 @@ def test_row_sharded_mode_b_equals_single_process_step(name, P):
     # predictions of each rank's slice
     pred = torch.cat([o["pred"] for o in outs])
     assert torch.allclose(pred, out_ref["pred"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("F,d,P", [(3, 8, 2), (8, 64, 4)])
+def test_row_sharded_mode_b_multi_field_equals_single_process_step(F, d, P):
+    """Mode B with F > 2 fields (config 4: pairwise interaction, per-group KL weights): P ranks
+    emulated on one GPU against the single-process fused step on the global batch."""
+    from vae_b200.dist import ShardedSampled
+    from vae_b200.vfm_torch import CF
+    fs = [37, 23, 11, 9, 7, 5, 4, 3][:F]
+    R, B = sum(fs), 256 * P
+    rng = np.random.default_rng(F * 10 + P)
+    offs = np.concatenate(([0], np.cumsum(fs)[:-1]))
+    x = np.stack([offs[f] + rng.integers(0, fs[f], B) for f in range(F)], 1).astype(np.int64)
+    y = (rng.random(B) < 0.5).astype(np.float32)
+    tc = np.bincount(x.reshape(-1), minlength=R)
+    tc[tc == 0] = 1
+    torch.manual_seed(3)
+    ref = CF(d, output="class", n_users=fs[0], n_items=fs[1], train_counts=torch.from_numpy(tc),
+             field_sizes=fs, kl_weighting="group", n_train=B, max_batch=B, lr=0.05)
+    with torch.no_grad():
+        ref.entity_params.weight.mul_(0.3)
+    ini = {"bias": ref.bias_params.weight.detach().cpu().clone(), "entity": ref.entity_params.weight.detach().cpu().clone(),
+           "alpha": float(ref.alpha.item()), "global_bias_mean": float(ref.global_bias_mean.item()),
+           "global_bias_scale": float(ref.global_bias_scale.item())}
+    gen = torch.Generator().manual_seed(5)
+    e0 = torch.randn(1, generator=gen).to(DEV)
+    eb_t, ee_t = torch.randn(R, generator=gen).to(DEV), torch.randn(R, d, generator=gen).to(DEV)
+    uniq = torch.from_numpy(np.unique(x)).to(DEV)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    for _ in range(2):
+        out_ref = ref.fused_step(xd, yd, noise=(e0.reshape(1, 1), eb_t[uniq][None], ee_t[uniq][None]))
+    ranks = [ShardedSampled(d, fs, torch.from_numpy(tc), B, B // P, P, p, output="class", kl_weighting="group",
+                            lr=0.05, init=ini, noise_tables=(e0, eb_t, ee_t), exchange=object()) for p in range(P)]
+    xs = [xd[p * (B // P):(p + 1) * (B // P)] for p in range(P)]
+    ys = [yd[p * (B // P):(p + 1) * (B // P)] for p in range(P)]
+    for _ in range(2):
+        outs = _run_sharded_emulated(ranks, xs, ys)
+    ent, bias = torch.zeros(R, 2 * d, device=DEV), torch.zeros(R, 2, device=DEV)
+    for r in ranks:
+        r.check_overflow()
+        gid, b, e = r.gather_tables()
+        ent[gid], bias[gid] = e, b
+    for got, want in ((ent, ref.entity_params.weight.detach()), (bias, ref.bias_params.weight.detach())):
+        bad = (got - want).abs() > 1e-5 * want.abs() + 2e-5 * 0.05 + 1e-6
+        assert bad.float().mean().item() <= 1e-4, float(bad.float().mean())
+    for o in outs:
+        np.testing.assert_allclose(o["loss"].item(), out_ref["loss"].item(), rtol=1e-5)
+    pred = torch.cat([o["pred"] for o in outs])
+    assert torch.allclose(pred, out_ref["pred"], rtol=1e-5, atol=2e-6)
