@@ -117,8 +117,13 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 
 // ---------------------------------------------------------------- link functions
 // LINK 0: abs (vfm-torch.py:126, vfm-tomasrch.py:201), 1: softplus (vfm-torch.py:125)
+// A raw scale of exactly 0 (it happens: N(0,1) initialisation of 10^8 values returns a few exact
+// zeros, on the CPU too) is sigma = 0 under the abs link -- an infinite KL here and a ValueError in the
+// reference (torch Normal rejects scale = 0).  sigma is floored at 1e-18 (sigma^2 stays a normal
+// float): everything stays finite, and nothing changes for |raw| >= 1e-18.
+constexpr float kSigmaFloor = 1e-18f;
 template <int LINK> __device__ __forceinline__ float link_fn(float raw) {
-    if constexpr (LINK == 0) return fabsf(raw);
+    if constexpr (LINK == 0) return fmaxf(fabsf(raw), kSigmaFloor);
     else return raw > 20.f ? raw : log1pf(expf(raw));      // torch softplus threshold
 }
 template <int LINK> __device__ __forceinline__ float link_grad(float raw) {

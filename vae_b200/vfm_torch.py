@@ -118,6 +118,10 @@ class CF(nn.Module):
         self.prec_item_bias_prior = nn.Parameter(torch.ones(1, device=device))
         self.prec_user_entity_prior = nn.Parameter(torch.ones(embedding_size, device=device))
         self.prec_item_entity_prior = nn.Parameter(torch.ones(embedding_size, device=device))
+        with torch.no_grad():       # a raw scale of exactly 0 is sigma = 0: invalid in the reference too
+            # (Normal(scale=0) raises); N(0,1) init of >= 10^8 values returns a few -- nudge them
+            for t in (bias.weight[:, 1:], entity.weight[:, embedding_size:]):
+                t[t == 0] = 1e-4
         self.bias_params = bias.to(device)
         self.entity_params = entity.to(device)
 
