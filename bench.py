@@ -379,9 +379,25 @@ def run_sharded(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             exchange = "nccl"
-    model = ShardedSampled(d, w.field_sizes, torch.from_numpy(tc), w.n_train, B, world, rank,
-                           output=w.output, kl_weighting=kl, seed=synth.NOISE_SEED, lr=lr, device=device,
-                           slack=args.slack, exchange="peer" if exchange == "peer" else None)
+    def build(ex):
+        return ShardedSampled(d, w.field_sizes, torch.from_numpy(tc), w.n_train, B, world, rank,
+                              output=w.output, kl_weighting=kl, seed=synth.NOISE_SEED, lr=lr, device=device,
+                              slack=args.slack, exchange=ex)
+    model = None
+    if exchange == "peer":
+        try:
+            model = build("peer")
+            ok = 1
+        except Exception as exc:                              # no peer mapping on this box: NCCL all-to-alls
+            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using NCCL",
+                  file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            exchange, model = "nccl", None
+    if model is None:
+        model = build(None)
     x_all = torch.from_numpy(w.x[: n_batches * B]).to(device)
     y_all = torch.from_numpy(w.y[: n_batches * B]).to(device)
 
