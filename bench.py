@@ -351,9 +351,11 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
 # ------------------------------------------------------------------------------------------
 def run_sharded(args):
     """N > 1: mode B -- tables row-sharded over the ranks (owner = row mod P), every rank feeds its
-    own batch of `batch` samples (weak scaling); per step 3 all-to-alls (ids, sampled rows, row
-    gradients) + 2 small all-reduces over NCCL.  The step on the global batch equals the
-    single-process step on that batch (tests/test_gpu_dp.py)."""
+    own batch of `batch` samples (weak scaling); per step 3 exchanges (ids, sampled rows, row
+    gradients), written by the pack kernels straight into the peers' buffers over NVLink
+    (`--exchange peer`, default) or run as NCCL all-to-alls (`--exchange nccl`), with the plans and
+    the id exchange of the next batch under the current step (ShardedPipeline).  The step on the
+    global batch equals the single-process step on that batch (tests/test_gpu_dp.py)."""
     import torch.distributed as dist
     from vae_b200.dist import ShardedSampled
     rank, world, local = dist_env()
