@@ -1052,6 +1052,7 @@ k_adam_rows_multi(DevCfg c, int u_stride, float* __restrict__ bias, float* __res
     }
 }
 
+#ifdef VFMB_WITH_BULK      // experimental bulk-copy variant (slower on 512-byte rows): -DVFMB_WITH_BULK + VFMB_ADAM_BULK=1
 // ------------------------------------------------------------------------------- k_adam_bulk
 // The same row update as k_adam_rows<ADAM_TOUCHED, FLAVOR 2>, fed by the bulk-copy engine instead
 // of register-staged loads.  k_adam_rows is latency-bound (80 % of the issue slots idle waiting on
@@ -1309,6 +1310,8 @@ k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
         }
     }
 }
+
+#endif  // VFMB_WITH_BULK
 
 // ------------------------------------------------------------------------------- dense Adam
 __global__ void __launch_bounds__(256)
@@ -1625,6 +1628,7 @@ static int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfm
     fa.counter = io->counters ? io->counters + 2 : nullptr;
     fa.gslot = io->partials ? (const float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off : nullptr;
     fa.likelihood = cfg->likelihood;
+#ifdef VFMB_WITH_BULK
     // measured on ml20m: 60.7 us vs 53.9 us for k_adam_rows -- 512-byte rows are too small for the
     // bulk-copy engine (per-copy overhead); kept selectable for wide rows (VFMB_ADAM_BULK=1)
     static const bool use_bulk = [] { const char* e = getenv("VFMB_ADAM_BULK"); return e && atoi(e) != 0; }();
@@ -1665,6 +1669,7 @@ static int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfm
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+#endif  // VFMB_WITH_BULK
     // the HBM-bound kernel keeps its full wave even next to the plan (measured: 113.8 vs 116.2 us/step)
     static const bool adam_reserve = [] { const char* e = getenv("VFMB_RESERVE_ADAM"); return e && atoi(e) != 0; }();
 #define LAUNCH_ADAM(LINK, MODE, FLAVOR)                                                                  \
