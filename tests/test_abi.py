@@ -49,3 +49,34 @@ def test_struct_sizes_match_header():
     assert C.sizeof(L.Plan) == 12 * 8
     assert C.sizeof(L.StepIO) == 24 * 8
     assert C.sizeof(L.Adam) == 32
+
+
+def test_capacity_invariants_and_host_side_argument_checks():
+    """Host-only entry points: capacities grow with the batch, the cut-row list can hold one row per
+    backward-tile boundary plus the hot rows, scratch covers the block partials; bad arguments are
+    reported through the return code + vfmb_last_error (nothing is launched)."""
+    lib = L.lib()
+    prev = 0
+    for B, F, R in ((1, 1, 1), (512, 2, 100), (65536, 2, 165237), (65536, 8, 1_000_000), (100_000, 8, 100_000_000)):
+        cap = L.PlanCapacity()
+        assert lib.vfmb_plan_capacity(B, F, R, C.byref(cap)) == 0
+        n = B * F
+        assert cap.u_cap == min(n, R) and cap.tile == 32 and cap.n_tiles == (n + 31) // 32
+        assert cap.cut_rows_cap >= cap.n_tiles + cap.n_tiles // 30
+        assert cap.workspace_bytes >= 4 * 4 * n and cap.workspace_bytes >= prev          # 4 key/value arrays
+        prev = cap.workspace_bytes
+        cfg = L.Config()
+        cfg.B, cfg.F, cfg.d, cfg.R, cfg.S = B, F, 64, R, 1
+        assert lib.vfmb_partials_doubles(C.byref(cfg)) >= 2048 * 16                      # block partials of 2048 blocks
+    assert lib.vfmb_plan_capacity(1 << 28, 8, 10, C.byref(L.PlanCapacity())) != 0         # B*F >= 2^30
+    assert lib.vfmb_set_grid_reserve(1) == 0 and lib.vfmb_set_grid_reserve(0) == 0
+    assert lib.vfmb_set_grid_reserve(9) != 0 and b"vfmb_set_grid_reserve" in lib.vfmb_last_error()
+    assert lib.vfmb_shard_bucket_workspace(131072) == 128 * 8 * 4
+    # null arguments never reach a launch
+    assert lib.vfmb_plan_build(None, None, None, None, None, 0, None) != 0
+    assert lib.vfmb_sampled_step(None, None, None, None, None, None) != 0
+    assert lib.vfmb_shard_bucket(None, 1, 2, 4, None, None, None, None, None, 0, None) != 0
+    cfg = L.Config()
+    cfg.B, cfg.F, cfg.d, cfg.R, cfg.S, cfg.n_classes = 8, 2, 4, 10, 9, 2                  # S out of range
+    assert lib.vfmb_sampled_forward(C.byref(cfg), C.byref(L.Tables()), C.byref(L.Plan()), C.byref(L.StepIO()), None) != 0
+    assert b"variational samples" in lib.vfmb_last_error()
