@@ -1,16 +1,20 @@
 // Sampled-ELBO VFM step (vfm-torch.py:189-324 forward, :359 loss, :368-370 backward + Adam).
 //
-// Five launches per fused training step, all HBM/L2-bound (no dense contraction on this path):
-//   k_stage    one lane group per UNIQUE row: gather [mean|raw scale], draw eps (Philox or
-//              injected), write the sampled row v = mu + eps*|rho| and bias w to an L2-resident
-//              scratch (+ the count-rescaled KL when not fused).   (vfm-torch.py:207-241, 290-317)
-//   k_score    one lane group per SAMPLE: FM interaction of the sampled rows, likelihood,
-//              residual dloss/dpred.                                (vfm-torch.py:244-270, 359)
-//   k_gather   ordered segmented sum of residual * partner row over the sorted occurrence list,
-//              tiled by position; k_combine finishes the rows cut by many tile boundaries.
-//   k_adam_rows  per unique row: chain rule to (mu, rho) + KL gradient + Adam; the last block
-//              also updates the scalar parameters (alpha, global bias) and the step counter.
-//              Deterministic: fixed summation order, no floating-point atomics.    (:368-370)
+// Five launches per fused training step (S = 1), all HBM/L2-bound (no dense contraction on this path):
+//   k_stage      one lane group per UNIQUE row: gather [mean|raw scale], draw eps (Philox or
+//                injected), write the sampled row v = mu + eps*|rho| and bias w to an L2-resident
+//                scratch (+ the count-rescaled KL when not fused).   (vfm-torch.py:207-241, 290-317)
+//   k_score      one lane group per SAMPLE: FM interaction of the sampled rows, likelihood,
+//                residual dloss/dpred.                                (vfm-torch.py:244-270, 359)
+//   k_gather     ordered segmented sum of residual * partner row over the sorted occurrence list,
+//                tiled by position; k_combine_cut finishes the rows cut by tile boundaries.
+//   k_gather_score  F = 2, step running alone: k_score + k_gather in one pass (4 launches).
+//   k_adam_rows  per unique row: chain rule to (mu, rho) + KL gradient + Adam; FLAVOR 2 also forms
+//                the KL and recomputes the Philox draws; the last block updates the scalar
+//                parameters (alpha, global bias) and the step counter.
+//                Deterministic: fixed summation order, no floating-point atomics.    (:368-370)
+// S > 1 variational samples: k_stage / k_gather once per sample, k_score_multi, k_adam_rows_multi.
+// Host side: launch_* (internal) and the extern "C" entry points at the end of the file.
 #include "step_common.cuh"
 
 #include <cstdlib>
