@@ -16,8 +16,8 @@ CSRC = os.path.join(_HERE, "csrc")
 # experiment hook: VFMB_VARIANT=name + VFMB_NVCC_EXTRA="-DX=1 ..." builds / loads libvfm_b200_name.so
 _VARIANT = os.environ.get("VFMB_VARIANT", "")
 LIB_PATH = os.path.join(_HERE, f"libvfm_b200{'_' + _VARIANT if _VARIANT else ''}.so")
-SOURCES = ["api.cu", "plan.cu", "sampled.cu", "closed.cu", "dp.cu", "shard.cu"]
-HEADERS = ["common.cuh", "internal.h", "step_common.cuh", os.path.join(_ROOT, "include", "vfm_b200.h")]
+SOURCES = ["api.cu", "plan.cu", "sampled.cu", "sampled_adam.cu", "closed.cu", "dp.cu", "shard.cu"]
+HEADERS = ["common.cuh", "internal.h", "step_common.cuh", "sampled_common.cuh", os.path.join(_ROOT, "include", "vfm_b200.h")]
 # -prec-div/-prec-sqrt=false: MUFU-based division and square root (<= 2 ulp) instead of the IEEE
 # slow paths, which made the Adam epilogue instruction-bound; denormals and expf/logf stay precise
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

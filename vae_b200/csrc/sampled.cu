@@ -15,42 +15,9 @@
 //                Deterministic: fixed summation order, no floating-point atomics.    (:368-370)
 // S > 1 variational samples: k_stage / k_gather once per sample, k_score_multi, k_adam_rows_multi.
 // Host side: launch_* (internal) and the extern "C" entry points at the end of the file.
-#include "step_common.cuh"
-
-#include <cstdlib>
+#include "sampled_common.cuh"
 
 namespace vfmb {
-
-// Noise of variational sample s (vfm-torch.py:238-241 draws [S,1], [S,U], [S,U,d]): injected arrays are
-// indexed [s][unique rank] (U = number of unique rows of the batch), Philox carries s in the tag word.
-template <int VEC>
-__device__ __forceinline__ Vec<VEC> entity_eps(const float* __restrict__ eps_entity, const DevCfg& c,
-                                              int u, int rowid, int k, uint32_t step, int s = 0, int U = 0) {
-    Vec<VEC> e;
-    if (eps_entity) {
-        e = ld_vec_nc<VEC>(eps_entity + ((size_t)s * U + u) * c.d + k);
-    } else {
-        float n4[4];
-        philox_normal4(c.seed, (uint32_t)rowid, (uint32_t)(k / VEC), step, philox_tag(kTagEntity, s), n4);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) e.v[i] = n4[i];
-    }
-    return e;
-}
-__device__ __forceinline__ float bias_eps(const float* __restrict__ eps_bias, const DevCfg& c, int u,
-                                          int rowid, uint32_t step, int s = 0, int U = 0) {
-    if (eps_bias) return __ldg(eps_bias + (size_t)s * U + u);
-    float n4[4];
-    philox_normal4(c.seed, (uint32_t)rowid, 0xFFFFFFFFu, step, philox_tag(kTagBias, s), n4);
-    return n4[0];
-}
-__device__ __forceinline__ float global_eps(const float* __restrict__ eps_global, const DevCfg& c,
-                                            uint32_t step, int s = 0) {
-    if (eps_global) return __ldg(eps_global + s);
-    float n4[4];
-    philox_normal4(c.seed, 0xFFFFFFFFu, 0xFFFFFFFFu, step, philox_tag(kTagGlobal, s), n4);
-    return n4[0];
-}
 
 // ------------------------------------------------------------------------------- k_stage
 // LEAN = 1 (fused training step): no KL sum and no copy of the noise -- k_adam_rows, which holds
@@ -327,7 +294,6 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
 // One lane group per sample n walks the S sampled copies of its rows.  The residual handed to the
 // backward is rho_n = (1/S) sum_s dloss/dpred[s, n] (every sampled copy of a row sees it, since
 // dpred[s', n]/dv_{s,u} = partner_s / S).  Plain structure on purpose: S = 1 is the tuned path.
-constexpr int kMaxSamples = 8;
 template <int VEC, int LPR, int NV, int LINK, int LIK>
 __global__ void __launch_bounds__(256)
 k_score_multi(DevCfg c, int u_stride, const float* __restrict__ scalars, const int32_t* __restrict__ inverse,
@@ -731,608 +697,6 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
     }
 }
 
-// ------------------------------------------------------------------------------- k_adam_rows
-// Backward, phase B (the HBM-bound kernel of the step): per unique row, chain rule from
-// (g_v, g_w) to (mean, raw scale) + KL gradient, then Adam on the row -- parameters and both
-// moments of every touched row are read and written exactly once.
-//
-// Row gradients are final in grow/gws (k_combine_cut finished the rows cut by tile boundaries).
-// FLAVOR 0  plain.
-// FLAVOR 1  + the block that finishes last updates the scalar parameters and the step counter
-//             (what k_final did as a separate launch).
-// FLAVOR 2  + the count-rescaled KL of the rows (the row is in registers, the kernel is DRAM-bound
-//             with idle issue slots) and, without injected noise, the Philox draws recomputed
-//             instead of read back -- k_stage<LEAN> wrote neither.
-struct FinalArgs {
-    float* scalars; float* sm; float* sv; float* stats; const float* eps_global;
-    float* grad_scalars; double* partials; int32_t* counter; const float* gslot;
-    int likelihood;
-};
-
-template <int LINK, int MODE>
-__device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& fa, const AdamDev& h,
-                                              int32_t* __restrict__ adam_step, float kl_scale,
-                                              bool with_kl, double kl_rows, int U) {
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
-    float* scalars = fa.scalars; float* stats = fa.stats;
-    float alpha = scalars[VFMB_S_ALPHA], mu0 = scalars[VFMB_S_GB_MEAN], rho0 = scalars[VFMB_S_GB_SCALE];
-    const float sig0 = link_fn<LINK>(rho0), ap = link_fn<LINK>(alpha);
-    const double sr = (double)stats[VFMB_ST_SUM_RESID], sq = (double)stats[VFMB_ST_SUM_SQERR];
-    // sum_s eps0_s * (sum_n dloss/dpred[s, n]); one sample: eps0 * sr
-    double e0sr = 0.0;
-    if (c.S > 1) {
-        for (int q = 0; q < c.S; ++q) e0sr += (double)global_eps(fa.eps_global, c, step, q) * (double)stats[VFMB_ST_RESID_S + q];
-    } else {
-        e0sr = (double)global_eps(fa.eps_global, c, step) * sr;
-    }
-    if (with_kl) {                                      // loss terms of the pre-update parameters
-        const float kl = kl_std_normal(mu0, sig0) + (float)kl_rows;
-        stats[VFMB_ST_KL_ROWS] = (float)kl_rows;
-        stats[VFMB_ST_KL] = kl;
-        stats[VFMB_ST_LOSS] = (float)((double)stats[VFMB_ST_LOSS] + (double)kl);
-        stats[VFMB_ST_U] = (float)U;
-    }
-    float g_mu0 = (float)(sr + (double)(kl_scale * mu0));
-    float g_rho0 = link_grad<LINK>(rho0) * (float)(e0sr + (double)(kl_scale * (sig0 - 1.f / sig0)));
-    float g_alpha = 0.f;
-    if (fa.likelihood == VFMB_GAUSSIAN) {
-        double sc = (double)c.n_train / ((double)c.S * (double)c.B);
-        g_alpha = link_grad<LINK>(alpha) * (float)(sc * (0.5 * sq - 0.5 * (double)c.S * (double)c.B / (double)ap));
-    }
-    if (MODE == VFMB_ADAM_TOUCHED) {
-        float ss, b2;
-        adam_coeffs(h, (int)step + 1, &ss, &b2);
-        adam_elem(mu0, fa.sm[VFMB_S_GB_MEAN], fa.sv[VFMB_S_GB_MEAN], g_mu0, h, ss, b2);
-        adam_elem(rho0, fa.sm[VFMB_S_GB_SCALE], fa.sv[VFMB_S_GB_SCALE], g_rho0, h, ss, b2);
-        scalars[VFMB_S_GB_MEAN] = mu0; scalars[VFMB_S_GB_SCALE] = rho0;
-        if (fa.likelihood == VFMB_GAUSSIAN) {  // Bernoulli: alpha has no gradient, Adam skips it (N10)
-            adam_elem(alpha, fa.sm[VFMB_S_ALPHA], fa.sv[VFMB_S_ALPHA], g_alpha, h, ss, b2);
-            scalars[VFMB_S_ALPHA] = alpha;
-        }
-        adam_step[0] = (int32_t)step + 1;
-    } else if (fa.grad_scalars) {
-        fa.grad_scalars[VFMB_S_ALPHA] = g_alpha;
-        fa.grad_scalars[VFMB_S_GB_MEAN] = g_mu0;
-        fa.grad_scalars[VFMB_S_GB_SCALE] = g_rho0;
-    }
-}
-
-#ifndef VFMB_ADAM_MINB
-#define VFMB_ADAM_MINB 4          // resident blocks/SM of the fused flavours (64 registers)
-#endif
-// bias row of one unique row: chain rule + KL gradient + Adam (or the dense-gradient store).
-// klw: in c_u, out c_u * KL(N(a, tau) || N(0,1)) of the pre-update row (when KLF)
-template <int LINK, int MODE, bool KLF>
-__device__ __forceinline__ void bias_update(float* __restrict__ bias, float* __restrict__ bias_m,
-                                            float* __restrict__ bias_v, float* __restrict__ grad_bias,
-                                            int rowid, float gw, float eb, float cfac, const AdamDev& h,
-                                            float step_size, float inv_bc2, float& klw) {
-    const size_t boff = (size_t)rowid * 2;
-    float2 ab = *reinterpret_cast<const float2*>(bias + boff);
-    const float tau = link_fn<LINK>(ab.y);
-    if (KLF) klw *= kl_std_normal(ab.x, tau);
-    const float ga = fmaf(cfac, ab.x, gw);
-    const float gb = link_grad<LINK>(ab.y) * fmaf(gw, eb, cfac * (tau - fast_rcp(tau)));
-    if (MODE == VFMB_ADAM_TOUCHED) {
-        float2 bm = *reinterpret_cast<const float2*>(bias_m + boff);
-        float2 bv = *reinterpret_cast<const float2*>(bias_v + boff);
-        adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
-        adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
-        *reinterpret_cast<float2*>(bias + boff) = ab;
-        *reinterpret_cast<float2*>(bias_m + boff) = bm;
-        *reinterpret_cast<float2*>(bias_v + boff) = bv;
-    } else {
-        *reinterpret_cast<float2*>(grad_bias + boff) = make_float2(ga, gb);
-    }
-}
-
-template <int VEC, int LPR, int NV, int LINK, int MODE, int FLAVOR>
-__global__ void __launch_bounds__(256, NV > 1 ? 2 : (FLAVOR == 0 ? 4 : VFMB_ADAM_MINB))
-k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
-            float* __restrict__ entity, float* __restrict__ entity_m, float* __restrict__ entity_v,
-            const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
-            const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
-            const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
-            AdamDev h, int32_t* __restrict__ adam_step, float kl_scale,
-            float* __restrict__ grad_bias, float* __restrict__ grad_entity, FinalArgs fa) {
-    constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
-    // (summing the rows cut by tile boundaries in here was tried: +16 registers = one resident block
-    // per SM less, which cost more than the separate k_combine_cut launch)
-    constexpr bool KLF = FLAVOR == 2;
-    const int U = meta[0];
-    const int d = c.d;
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
-    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
-    const unsigned gmask = group_mask<LPR>();
-    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
-    // bias corrections: fp64 pow per thread (~100 cycles per warp on the FP64 pipe) -- cheaper than
-    // a block barrier in front of the first loads
-    float step_size = 0.f, inv_bc2 = 1.f;
-    if (MODE == VFMB_ADAM_TOUCHED) adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
-    float facc = 0.f;                                     // sum_u c_u * KL_u over this thread's rows
-
-    for (int base = gwarp * CH; base < U; base += nwarps * CH) {
-        // ---- lane-parallel: record, prefetch of the row's parameter / moment lines
-        const int ul = base + lane;
-        const bool valid = lane < CH && ul < U;
-        int rowid_l = 0;
-        float cfac_l = 0.f, klw_l = 0.f;                  // KL weight c_u, and c_u * KL(bias) of the lane's row
-        if (valid) {
-            const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
-            rowid_l = rec.x;
-            const size_t eoff = (size_t)rowid_l * 2 * d;
-            prefetch_row(entity + eoff, 8 * d);
-            if (MODE == VFMB_ADAM_TOUCHED) {
-                prefetch_row(entity_m + eoff, 8 * d);
-                prefetch_row(entity_v + eoff, 8 * d);
-            }
-            const float cq_l = __ldg(cq + ul);
-            cfac_l = kl_scale * cq_l;
-            klw_l = cq_l;
-            // bias row now: nothing of it stays live across the wide work
-            bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, grad_bias, rowid_l, __ldg(gws + ul),
-                                         __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
-        }
-        float klrow = 0.f;
-        // ---- wide work: GPW rows per round
-#pragma unroll 1
-        for (int it = 0; it < kRounds; ++it) {
-            const int sel = it * GPW + gidx;
-            const int rowid = bcast(rowid_l, sel);
-            const float cfac = bcast(cfac_l, sel);
-            const int u = base + sel;
-            float kl = 0.f;
-            if (u < U) {
-                const size_t eoff = (size_t)rowid * 2 * d;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-                        Vec<VEC> e;                         // the noise k_stage used for this row
-                        if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step);
-                        else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
-                        Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
-                        Vec<VEC> m1, m2, v1, v2;
-                        if (MODE == VFMB_ADAM_TOUCHED) {
-                            m1 = ld_vec_cs<VEC>(entity_m + eoff + k); m2 = ld_vec_cs<VEC>(entity_m + eoff + d + k);
-                            v1 = ld_vec_cs<VEC>(entity_v + eoff + k); v2 = ld_vec_cs<VEC>(entity_v + eoff + d + k);
-                        }
-                        const Vec<VEC> g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
-                        Vec<VEC> gmu, grho;
-                        float quad = 0.f, prodv = 1.f;
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            const float sig = link_fn<LINK>(rho.v[j]);
-                            gmu.v[j] = fmaf(cfac, mu.v[j], g.v[j]);
-                            grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(g.v[j], e.v[j], cfac * (sig - fast_rcp(sig)));
-                            if (KLF) {
-                                const float vr = sig * sig;
-                                quad += vr + mu.v[j] * mu.v[j] - 1.f;
-                                prodv *= vr;
-                            }
-                        }
-                        if (KLF) {       // sum_k KL(N(mu,sig)||N(0,1)), one logarithm per lane (as k_stage)
-                            float lg = __logf(prodv);
-                            if (!(prodv > 1e-30f && prodv < 1e30f)) {
-                                lg = 0.f;
-#pragma unroll
-                                for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho.v[j]); lg += logf(sg * sg); }
-                            }
-                            kl += 0.5f * (quad - lg);
-                        }
-                        if (MODE == VFMB_ADAM_TOUCHED) {
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) {
-                                adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu.v[j], h, step_size, inv_bc2);
-                                adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, inv_bc2);
-                            }
-                            st_vec<VEC>(entity + eoff + k, mu);        st_vec<VEC>(entity + eoff + d + k, rho);
-                            st_vec_cs<VEC>(entity_m + eoff + k, m1);   st_vec_cs<VEC>(entity_m + eoff + d + k, m2);
-                            st_vec_cs<VEC>(entity_v + eoff + k, v1);   st_vec_cs<VEC>(entity_v + eoff + d + k, v2);
-                        } else {
-                            st_vec<VEC>(grad_entity + eoff + k, gmu);  st_vec<VEC>(grad_entity + eoff + d + k, grho);
-                        }
-                    }
-                }
-                if (KLF) kl = group_sum<LPR>(kl, gmask);
-            }
-            if (KLF) hand_back<LPR>(klrow, kl, it, lane);
-        }
-        // ---- lane-parallel: KL of the rows -- klw_l is c_u * KL(bias row) (bias_update), klrow the
-        // entity part of the row's KL
-        if (KLF && valid) facc += fmaf(__ldg(cq + ul), klrow, klw_l);
-    }
-    if (FLAVOR >= 1) {
-        // the block that finishes last owns the scalar parameters: every block has read the step
-        // counter / Adam coefficients before it signalled, so updating them here is race-free
-        double acc[1] = {(double)facc};
-        if (block_partials<1>(acc, fa.partials, fa.counter)) {
-            double tot[1] = {0.0};
-            if (KLF) final_sums<1>(fa.partials, tot);
-            if (threadIdx.x == 0) {
-                final_scalars<LINK, MODE>(c, fa, h, adam_step, kl_scale, KLF, tot[0], U);
-                *fa.counter = 0;
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------- k_adam_rows_multi
-// S > 1: the row gradient is the sum over the S sampled copies of the row,
-//   d/dmu = sum_s g_s + c_u mu,   d/drho = sign(rho) (sum_s g_s * eps_s + c_u (sigma - 1/sigma)),
-//   d/da = S g_w + c_u a,         d/db = sign(b) (g_w sum_s eps^w_s + c_u (tau - 1/tau))
-// (g_s = sum_n rho_n partner_s(n): k_gather on sample s; g_w = sum_n rho_n is the same for every s).
-// One lane group per unique row, plain structure (S = 1 is the tuned path).  The block that finishes
-// last updates the scalar parameters, as in k_adam_rows<FLAVOR 1>.
-template <int VEC, int LPR, int NV, int LINK, int MODE>
-__global__ void __launch_bounds__(256)
-k_adam_rows_multi(DevCfg c, int u_stride, float* __restrict__ bias, float* __restrict__ bias_m,
-                  float* __restrict__ bias_v, float* __restrict__ entity, float* __restrict__ entity_m,
-                  float* __restrict__ entity_v, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
-                  const float* __restrict__ eps_bias, const float* __restrict__ eps_entity, int eps_stride,
-                  const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
-                  AdamDev h, int32_t* __restrict__ adam_step, float kl_scale,
-                  float* __restrict__ grad_bias, float* __restrict__ grad_entity, FinalArgs fa) {
-    constexpr int GPW = kWarp / LPR;
-    const int U = meta[0], d = c.d, S = c.S;
-    if (eps_stride < 0) eps_stride = U;                    // injected noise: [S, U, ...]; scratch: [S, u_stride, ...]
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
-    const int lane = threadIdx.x & 31, gl = lane % LPR;
-    const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
-    const int ngroups = gridDim.x * (blockDim.x >> 5) * GPW;
-    float step_size = 0.f, inv_bc2 = 1.f;
-    if (MODE == VFMB_ADAM_TOUCHED) adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
-
-    for (int u = group; u < U; u += ngroups) {
-        const int rowid = __ldg(urec + 4 * (size_t)u);
-        const float cfac = kl_scale * __ldg(cq + u);
-        const size_t eoff = (size_t)rowid * 2 * d;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            int k = (gl + i * LPR) * VEC;
-            if (k < d) {
-                Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
-                Vec<VEC> gs, ges;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) { gs.v[j] = 0.f; ges.v[j] = 0.f; }
-                for (int q = 0; q < S; ++q) {
-                    const Vec<VEC> g = ld_vec_nc<VEC>(grow + ((size_t)q * u_stride + u) * d + k);
-                    const Vec<VEC> e = ld_vec_nc<VEC>(eps_entity + ((size_t)q * eps_stride + u) * d + k);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) { gs.v[j] += g.v[j]; ges.v[j] = fmaf(g.v[j], e.v[j], ges.v[j]); }
-                }
-                Vec<VEC> gmu, grho;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const float sig = link_fn<LINK>(rho.v[j]);
-                    gmu.v[j] = fmaf(cfac, mu.v[j], gs.v[j]);
-                    grho.v[j] = link_grad<LINK>(rho.v[j]) * (ges.v[j] + cfac * (sig - fast_rcp(sig)));
-                }
-                if (MODE == VFMB_ADAM_TOUCHED) {
-                    Vec<VEC> m1 = ld_vec<VEC>(entity_m + eoff + k), m2 = ld_vec<VEC>(entity_m + eoff + d + k);
-                    Vec<VEC> v1 = ld_vec<VEC>(entity_v + eoff + k), v2 = ld_vec<VEC>(entity_v + eoff + d + k);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu.v[j], h, step_size, inv_bc2);
-                        adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, inv_bc2);
-                    }
-                    st_vec<VEC>(entity + eoff + k, mu);     st_vec<VEC>(entity + eoff + d + k, rho);
-                    st_vec<VEC>(entity_m + eoff + k, m1);   st_vec<VEC>(entity_m + eoff + d + k, m2);
-                    st_vec<VEC>(entity_v + eoff + k, v1);   st_vec<VEC>(entity_v + eoff + d + k, v2);
-                } else {
-                    st_vec<VEC>(grad_entity + eoff + k, gmu);  st_vec<VEC>(grad_entity + eoff + d + k, grho);
-                }
-            }
-        }
-        if (gl == 0) {                                     // bias row
-            const size_t boff = (size_t)rowid * 2;
-            float2 ab = *reinterpret_cast<const float2*>(bias + boff);
-            const float gw = __ldg(gws + u);
-            float ebsum = 0.f;
-            for (int q = 0; q < S; ++q) ebsum += __ldg(eps_bias + (size_t)q * eps_stride + u);
-            const float tau = link_fn<LINK>(ab.y);
-            const float ga = fmaf(cfac, ab.x, (float)S * gw);
-            const float gb = link_grad<LINK>(ab.y) * fmaf(gw, ebsum, cfac * (tau - fast_rcp(tau)));
-            if (MODE == VFMB_ADAM_TOUCHED) {
-                float2 bm = *reinterpret_cast<const float2*>(bias_m + boff);
-                float2 bv = *reinterpret_cast<const float2*>(bias_v + boff);
-                adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
-                adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
-                *reinterpret_cast<float2*>(bias + boff) = ab;
-                *reinterpret_cast<float2*>(bias_m + boff) = bm;
-                *reinterpret_cast<float2*>(bias_v + boff) = bv;
-            } else {
-                *reinterpret_cast<float2*>(grad_bias + boff) = make_float2(ga, gb);
-            }
-        }
-    }
-    double acc[1] = {0.0};
-    if (block_partials<1>(acc, fa.partials, fa.counter)) {
-        if (threadIdx.x == 0) {
-            final_scalars<LINK, MODE>(c, fa, h, adam_step, kl_scale, false, 0.0, U);
-            *fa.counter = 0;
-        }
-    }
-}
-
-#ifdef VFMB_WITH_BULK      // experimental bulk-copy variant (slower on 512-byte rows): -DVFMB_WITH_BULK + VFMB_ADAM_BULK=1
-// ------------------------------------------------------------------------------- k_adam_bulk
-// The same row update as k_adam_rows<ADAM_TOUCHED, FLAVOR 2>, fed by the bulk-copy engine instead
-// of register-staged loads.  k_adam_rows is latency-bound (80 % of the issue slots idle waiting on
-// L1TEX scoreboards, DRAM at 55 %): the bytes a warp keeps in flight are limited by its registers.
-// Here a CTA is a three-role pipeline over a ring of NS shared-memory stages:
-//   warp 0 (loader)   per stage: cp.async.bulk of the parameter / moment rows of RPS unique rows
-//                     (3 x 8d bytes each, gathered by row id) + one contiguous block of their
-//                     gradient rows (+ injected noise) -> smem, completion on an mbarrier;
-//   warps 2.. (consumers)  chain rule + KL + Adam in place in shared memory (LPR lanes per row);
-//   warp 1 (storer)   cp.async.bulk smem -> global of the updated rows, then frees the stage.
-// Bytes in flight per SM = NS x stage bytes x resident CTAs (~170 KB), independent of registers.
-// Rows are split into equal contiguous ranges per CTA (all CTAs finish together).
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-constexpr int kBulkConsumers = 4;                     // consumer warps per CTA
-constexpr int kBulkThreads = 32 * (2 + kBulkConsumers);
-constexpr int kBulkStages = 4;
-
-// floats of one stage: P | M | V rows (2d each), gradient rows, noise rows (d each), then row ids
-__host__ __device__ inline int bulk_stage_floats(int d, int rps) { return rps * 8 * d + ((rps + 3) / 4) * 4; }
-
-template <int LPR, int NV, int LINK>
-__global__ void __launch_bounds__(kBulkThreads, 3)
-k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
-            float* __restrict__ entity, float* __restrict__ entity_m, float* __restrict__ entity_v,
-            const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
-            const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
-            const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
-            AdamDev h, int32_t* __restrict__ adam_step, float kl_scale, FinalArgs fa) {
-    constexpr int VEC = 4, GPW = kWarp / LPR, RPS = kBulkConsumers * GPW, NS = kBulkStages;
-    extern __shared__ __align__(128) float s_ring[];
-    __shared__ __align__(8) uint64_t s_full[NS], s_done[NS], s_empty[NS];
-    const int U = meta[0];
-    const int d = c.d, rowf = 2 * c.d;
-    const int stage_f = bulk_stage_floats(d, RPS);
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s2 = 0; s2 < NS; ++s2) { mbar_init(&s_full[s2], 1); mbar_init(&s_done[s2], kBulkConsumers); mbar_init(&s_empty[s2], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // equal contiguous ranges of unique rows per CTA, in whole stages
-    const int per = ((U + (int)gridDim.x - 1) / (int)gridDim.x + RPS - 1) / RPS * RPS;
-    const int lo = min(U, (int)blockIdx.x * per), hi = min(U, lo + per);
-    const int n_it = (hi - lo + RPS - 1) / RPS;
-    float facc = 0.f;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------ loader
-        int rowid_next = (lane < RPS && lo + lane < hi) ? __ldg(urec + 4 * (size_t)(lo + lane)) : 0;
-        for (int it = 0; it < n_it; ++it) {
-            const int st = it % NS, ph = (it / NS) & 1;
-            const int u0 = lo + it * RPS, nrows = min(RPS, hi - u0);
-            const int rowid = rowid_next;
-            const int un = u0 + RPS + lane;
-            rowid_next = (lane < RPS && un < hi) ? __ldg(urec + 4 * (size_t)un) : 0;
-            float* sp = s_ring + (size_t)st * stage_f;
-            mbar_wait(&s_empty[st], ph ^ 1);
-            if (lane < nrows) reinterpret_cast<int*>(sp + RPS * 8 * d)[lane] = rowid;
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t bytes = (uint32_t)nrows * (uint32_t)(3 * rowf + d + (eps_entity ? d : 0)) * 4u;
-                mbar_expect_tx(&s_full[st], bytes);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                bulk_load(sp + 3 * RPS * rowf, grow + (size_t)u0 * d, nrows * d * 4, &s_full[st]);
-                if (eps_entity)
-                    bulk_load(sp + 3 * RPS * rowf + RPS * d, eps_entity + (size_t)u0 * d, nrows * d * 4, &s_full[st]);
-            }
-            if (lane < nrows) {
-                const size_t eoff = (size_t)rowid * rowf;
-                bulk_load(sp + (0 * RPS + lane) * rowf, entity + eoff, rowf * 4, &s_full[st]);
-                bulk_load(sp + (1 * RPS + lane) * rowf, entity_m + eoff, rowf * 4, &s_full[st]);
-                bulk_load(sp + (2 * RPS + lane) * rowf, entity_v + eoff, rowf * 4, &s_full[st]);
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ storer
-        for (int it = 0; it < n_it; ++it) {
-            const int st = it % NS, ph = (it / NS) & 1;
-            const int u0 = lo + it * RPS, nrows = min(RPS, hi - u0);
-            float* sp = s_ring + (size_t)st * stage_f;
-            mbar_wait(&s_done[st], ph);
-            if (lane < nrows) {
-                const int rowid = reinterpret_cast<const int*>(sp + RPS * 8 * d)[lane];
-                const size_t eoff = (size_t)rowid * rowf;
-                bulk_store(entity + eoff, sp + (0 * RPS + lane) * rowf, rowf * 4);
-                bulk_store(entity_m + eoff, sp + (1 * RPS + lane) * rowf, rowf * 4);
-                bulk_store(entity_v + eoff, sp + (2 * RPS + lane) * rowf, rowf * 4);
-            }
-            bulk_commit();
-            bulk_wait_read<1>();                              // the stores of stage it-1 have left smem
-            __syncwarp();
-            if (lane == 0 && it > 0) mbar_arrive(&s_empty[(it - 1) % NS]);
-        }
-        bulk_wait_read<0>();
-        __syncwarp();
-        if (lane == 0 && n_it > 0) mbar_arrive(&s_empty[(n_it - 1) % NS]);
-        bulk_wait<0>();                                        // writes complete before the CTA retires
-    } else {
-        // ------------------------------------------------------------ consumers
-        const int cw = warp - 2, gl = lane % LPR, gidx = lane / LPR;
-        const unsigned gmask = group_mask<LPR>();
-        float step_size, inv_bc2;
-        adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
-        // scalars of the rows this warp handles: lane g < GPW owns row cw*GPW + g of every stage;
-        // fetched one stage ahead
-        auto fetch = [&](int it, int4& rec, float& cqv, float& gwv, float& ebv) {
-            const int u = lo + it * RPS + cw * GPW + lane;
-            rec = make_int4(0, 0, 0, 0); cqv = 0.f; gwv = 0.f; ebv = 0.f;
-            if (lane < GPW && it < n_it && u < hi) {
-                rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
-                cqv = __ldg(cq + u); gwv = __ldg(gws + u); ebv = __ldg(eps_bias + u);
-            }
-        };
-        int4 rec_n; float cq_n, gw_n, eb_n;
-        fetch(0, rec_n, cq_n, gw_n, eb_n);
-        for (int it = 0; it < n_it; ++it) {
-            const int st = it % NS, ph = (it / NS) & 1;
-            const int u0 = lo + it * RPS;
-            const int4 rec = rec_n; const float cq_l = cq_n, eb_l = eb_n; float gw_l = gw_n;
-            fetch(it + 1, rec_n, cq_n, gw_n, eb_n);
-            const int ul = u0 + cw * GPW + lane;
-            const bool valid = lane < GPW && ul < hi;
-            // bias row of this lane's row: in flight while the stage is awaited and processed
-            float2 ab = make_float2(0.f, 1.f), bm = make_float2(0.f, 0.f), bv = make_float2(0.f, 0.f);
-            if (valid) {
-                const size_t boff = (size_t)rec.x * 2;
-                ab = *reinterpret_cast<const float2*>(bias + boff);
-                bm = *reinterpret_cast<const float2*>(bias_m + boff);
-                bv = *reinterpret_cast<const float2*>(bias_v + boff);
-            }                                              // (cut rows: k_combine_cut finished them)
-            const float cfac_l = kl_scale * cq_l;
-            float* sp = s_ring + (size_t)st * stage_f;
-            mbar_wait(&s_full[st], ph);
-            // ---- wide work: this warp's GPW rows, LPR lanes per row
-            const int r = cw * GPW + gidx;                  // row slot in the stage
-            const int u = u0 + r;
-            const int rowid = bcast(rec.x, gidx);
-            const float cfac = bcast(cfac_l, gidx);
-            float kl = 0.f;
-            if (u < hi) {
-                float* pP = sp + (0 * RPS + r) * rowf;
-                float* pM = sp + (1 * RPS + r) * rowf;
-                float* pV = sp + (2 * RPS + r) * rowf;
-                const float* pG = sp + 3 * RPS * rowf + r * d;
-                const float* pE = pG + RPS * d;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-                        Vec<VEC> mu = ld_vec<VEC>(pP + k), rho = ld_vec<VEC>(pP + d + k);
-                        Vec<VEC> m1 = ld_vec<VEC>(pM + k), m2 = ld_vec<VEC>(pM + d + k);
-                        Vec<VEC> v1 = ld_vec<VEC>(pV + k), v2 = ld_vec<VEC>(pV + d + k);
-                        const Vec<VEC> g = ld_vec<VEC>(pG + k);
-                        Vec<VEC> e;
-                        if (eps_entity) e = ld_vec<VEC>(pE + k);
-                        else e = entity_eps<VEC>(nullptr, c, u, rowid * c.row_stride + c.row_offset, k, step);
-                        float quad = 0.f, prodv = 1.f;
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            const float sig = link_fn<LINK>(rho.v[j]);
-                            const float gj = g.v[j];
-                            const float gmu = fmaf(cfac, mu.v[j], gj);
-                            const float grho = link_grad<LINK>(rho.v[j]) * fmaf(gj, e.v[j], cfac * (sig - fast_rcp(sig)));
-                            const float vr = sig * sig;
-                            quad += vr + mu.v[j] * mu.v[j] - 1.f;
-                            prodv *= vr;
-                            adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu, h, step_size, inv_bc2);
-                            adam_elem(rho.v[j], m2.v[j], v2.v[j], grho, h, step_size, inv_bc2);
-                        }
-                        // KL of the pre-update row (quad / prodv were formed before adam_elem touched
-                        // element j); one logarithm per lane as in k_stage
-                        float lg = __logf(prodv);
-                        if (!(prodv > 1e-30f && prodv < 1e30f)) {       // tiny / huge scales: no product trick
-                            const Vec<VEC> rho0 = ld_vec<VEC>(pP + d + k);   // still the old row in smem
-                            lg = 0.f;
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho0.v[j]); lg += logf(sg * sg); }
-                        }
-                        kl += 0.5f * (quad - lg);
-                        st_vec<VEC>(pP + k, mu); st_vec<VEC>(pP + d + k, rho);
-                        st_vec<VEC>(pM + k, m1); st_vec<VEC>(pM + d + k, m2);
-                        st_vec<VEC>(pV + k, v1); st_vec<VEC>(pV + d + k, v2);
-                    }
-                }
-                kl = group_sum<LPR>(kl, gmask);
-            }
-            fence_async_smem();                             // generic-proxy writes -> visible to the bulk store
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_done[st]);
-            // ---- lane-parallel: bias row, KL of the row
-            float klrow = 0.f;
-#pragma unroll
-            for (int g = 0; g < GPW; ++g) {
-                const float kv = __shfl_sync(0xffffffffu, kl, g * LPR);
-                if (lane == g) klrow = kv;
-            }
-            if (valid) {
-                const size_t boff = (size_t)rec.x * 2;
-                const float tau = link_fn<LINK>(ab.y);
-                facc = fmaf(cq_l, klrow + kl_std_normal(ab.x, tau), facc);
-                const float ga = fmaf(cfac_l, ab.x, gw_l);
-                const float gb = link_grad<LINK>(ab.y) * fmaf(gw_l, eb_l, cfac_l * (tau - fast_rcp(tau)));
-                adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
-                adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
-                *reinterpret_cast<float2*>(bias + boff) = ab;
-                *reinterpret_cast<float2*>(bias_m + boff) = bm;
-                *reinterpret_cast<float2*>(bias_v + boff) = bv;
-            }
-        }
-    }
-    // the block that finishes last owns the scalar parameters (see k_adam_rows)
-    double acc[1] = {(double)facc};
-    if (block_partials<1>(acc, fa.partials, fa.counter)) {
-        double tot[1] = {0.0};
-        final_sums<1>(fa.partials, tot);
-        if (threadIdx.x == 0) {
-            final_scalars<LINK, VFMB_ADAM_TOUCHED>(c, fa, h, adam_step, kl_scale, true, tot[0], U);
-            *fa.counter = 0;
-        }
-    }
-}
-
-#endif  // VFMB_WITH_BULK
-
-// ------------------------------------------------------------------------------- dense Adam
-__global__ void __launch_bounds__(256)
-k_adam_dense(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-             const float* __restrict__ g, int64_t n, AdamDev h, const int32_t* __restrict__ adam_step) {
-    __shared__ float s_coef[2];
-    if (threadIdx.x == 0) adam_coeffs(h, adam_step[0] + 1, &s_coef[0], &s_coef[1]);
-    __syncthreads();
-    const float ss = s_coef[0], b2 = s_coef[1];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float pi = p[i], mi = m[i], vi = v[i];
-        adam_elem(pi, mi, vi, g[i], h, ss, b2);
-        p[i] = pi; m[i] = mi; v[i] = vi;
-    }
-}
-__global__ void k_step_advance(int32_t* adam_step) { adam_step[0] += 1; }
-
 // ------------------------------------------------------------------------------- philox export
 template <int VEC>
 __global__ void k_philox_export(DevCfg c, const int32_t* __restrict__ uniq, int U, uint32_t step,
@@ -1375,31 +739,6 @@ extern "C" int64_t vfmb_partials_doubles(const vfmb_config* cfg) {
     int64_t n = (int64_t)cfg->B * cfg->F;
     int64_t u_cap = n < cfg->R ? n : cfg->R;
     return (int64_t)scratch_map(cfg->B, cfg->F, cfg->d, u_cap).total_doubles;
-}
-
-// ---- shared host-side preparation of one phase launch
-struct Prep {
-    cudaStream_t stream;
-    Layout L;
-    DevCfg dc;
-    vfmb_plan_capacity_t cap;
-    int ch;
-};
-static int prep(const vfmb_config* cfg, const char* who, vfmb_stream stream_, int min_fields, Prep* p) {
-    if (!cfg) return set_error(VFMB_EINVAL, "%s: null config", who);
-    if (cfg->B <= 0 || cfg->R <= 0 || cfg->d <= 0) return set_error(VFMB_EINVAL, "%s: bad B/R/d", who);
-    if (cfg->F < min_fields || cfg->F > VFMB_MAX_FIELDS) return set_error(VFMB_ESHAPE, "%s: F must be %d..%d", who, min_fields, VFMB_MAX_FIELDS);
-    if (cfg->S < 1 || cfg->S > kMaxSamples) return set_error(VFMB_ESHAPE, "%s: S=%d variational samples (1..%d)", who, cfg->S, kMaxSamples);
-    if (cfg->n_classes < 1 || cfg->n_classes > VFMB_MAX_FIELDS) return set_error(VFMB_EINVAL, "%s: bad n_classes", who);
-    if (cfg->likelihood != VFMB_GAUSSIAN && cfg->likelihood != VFMB_BERNOULLI) return set_error(VFMB_EINVAL, "%s: bad likelihood", who);
-    if (cfg->link != VFMB_LINK_ABS && cfg->link != VFMB_LINK_SOFTPLUS) return set_error(VFMB_EINVAL, "%s: bad link", who);
-    p->stream = (cudaStream_t)stream_;
-    if (!pick_layout(cfg->d, &p->L)) return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
-    p->dc = make_dev(cfg);
-    int rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &p->cap);
-    if (rc) return rc;
-    p->ch = kRounds * (32 / p->L.lpr);
-    return 0;
 }
 
 // ---- internal launchers (the public entry points below are thin wrappers)
@@ -1452,10 +791,6 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-
-#define VFMB_PHASE_S1(who)                                                                             \
-    if (cfg && cfg->S != 1) return set_error(VFMB_ESHAPE, who ": the phase entry points take S = 1 (use "    \
-                                             "vfmb_sampled_forward / _backward / _step for S > 1)")
 
 extern "C" int vfmb_sampled_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                   const vfmb_step_io* io, vfmb_stream stream) {
@@ -1600,160 +935,6 @@ extern "C" int vfmb_sampled_gather(const vfmb_config* cfg, const vfmb_plan* plan
     return launch_gather(cfg, plan, io, table, unit_coef, stream);
 }
 
-// flavor: see k_adam_rows
-static int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                       const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode, float kl_grad_scale,
-                       int flavor, vfmb_stream stream_) {
-    Prep P;
-    int rc = prep(cfg, "vfmb_sampled_adam_rows", stream_, 1, &P);
-    if (rc) return rc;
-    if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: null argument");
-    if (mode == VFMB_ADAM_TOUCHED && (!adam || !tab->entity_m || !tab->entity_v || !tab->bias_m || !tab->bias_v || !tab->adam_step))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: Adam state required");
-    if (mode == VFMB_GRAD_ONLY && (!io->grad_bias || !io->grad_entity))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: gradient outputs required");
-    if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: bad mode");
-    if (!io->grow || !io->gws || !io->cq) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: scratch required");
-    if (flavor >= 1 && mode == VFMB_ADAM_TOUCHED && (!tab->scalars_m || !tab->scalars_v))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: Adam state required");
-    if (flavor >= 1 && (!tab->scalars || !io->stats || !io->partials || !io->counters))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: scalars / stats required");
-    const Layout& L = P.L; cudaStream_t stream = P.stream; const int ch = P.ch; const auto& cap = P.cap;
-    const DevCfg& dc = P.dc;
-    AdamDev h = make_adam(adam);
-    // the noise the forward used: injected arrays, or what k_stage wrote to scratch (Philox);
-    // flavor 2 recomputes the Philox draws of the rows instead
-    const float* eps_e = io->eps_entity ? io->eps_entity : (flavor == 2 ? nullptr : io->es);
-    const float* eps_b = io->eps_bias ? io->eps_bias : io->ebs;
-    if (!eps_b || (flavor != 2 && !eps_e)) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: noise of the forward required");
-    FinalArgs fa{};
-    fa.scalars = tab->scalars; fa.sm = tab->scalars_m; fa.sv = tab->scalars_v; fa.stats = io->stats;
-    fa.eps_global = io->eps_global; fa.grad_scalars = io->grad_scalars; fa.partials = io->partials;
-    fa.counter = io->counters ? io->counters + 2 : nullptr;
-    fa.gslot = io->partials ? (const float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off : nullptr;
-    fa.likelihood = cfg->likelihood;
-#ifdef VFMB_WITH_BULK
-    // measured on ml20m: 60.7 us vs 53.9 us for k_adam_rows -- 512-byte rows are too small for the
-    // bulk-copy engine (per-copy overhead); kept selectable for wide rows (VFMB_ADAM_BULK=1)
-    static const bool use_bulk = [] { const char* e = getenv("VFMB_ADAM_BULK"); return e && atoi(e) != 0; }();
-    if (use_bulk && flavor == 2 && mode == VFMB_ADAM_TOUCHED && L.vec == 4) {
-        // bulk-copy pipeline (k_adam_bulk): same arithmetic, rows staged through shared memory
-        cudaEvent_t ev0, ev1;
-        profile_events(&ev0, &ev1);
-        if (ev0 && ev1) cudaEventRecord(ev0, stream);
-#define LAUNCH_BULK(LPR_, NV_, LINK)                                                                     \
-        do {                                                                                             \
-            auto kern = k_adam_bulk<LPR_, NV_, LINK>;                                                    \
-            const int rps = kBulkConsumers * (32 / LPR_);                                                \
-            const size_t smem = (size_t)kBulkStages * bulk_stage_floats(cfg->d, rps) * sizeof(float);    \
-            static int blocks = 0;                                                                       \
-            static size_t smem_set = 0;                                                                  \
-            if (smem_set != smem) {                                                                      \
-                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                int per_sm = 0;                                                                          \
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBulkThreads, smem)); \
-                blocks = (per_sm < 1 ? 1 : per_sm) * kNumSMs;                                            \
-                smem_set = smem;                                                                         \
-            }                                                                                            \
-            int64_t need = (cap.u_cap + rps - 1) / rps;                                                  \
-            int grid = (int)(need < blocks ? (need < 1 ? 1 : need) : blocks);                            \
-            kern<<<grid, kBulkThreads, smem, stream>>>(dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, \
-                tab->entity_m, tab->entity_v, plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow,    \
-                io->gws, h, tab->adam_step, kl_grad_scale, fa);                                          \
-        } while (0)
-#define LAUNCH_BULK_L(LPR_, NV_) do { if (cfg->link == VFMB_LINK_ABS) LAUNCH_BULK(LPR_, NV_, 0); else LAUNCH_BULK(LPR_, NV_, 1); } while (0)
-        if (L.lpr == 4) LAUNCH_BULK_L(4, 1);
-        else if (L.lpr == 8) LAUNCH_BULK_L(8, 1);
-        else if (L.lpr == 16) LAUNCH_BULK_L(16, 1);
-        else if (L.nv == 1) LAUNCH_BULK_L(32, 1);
-        else LAUNCH_BULK_L(32, 2);
-#undef LAUNCH_BULK_L
-#undef LAUNCH_BULK
-        if (ev0 && ev1) cudaEventRecord(ev1, stream);
-        CUDA_TRY(cudaGetLastError());
-        return 0;
-    }
-#endif  // VFMB_WITH_BULK
-    // the HBM-bound kernel keeps its full wave even next to the plan (measured: 113.8 vs 116.2 us/step)
-    static const bool adam_reserve = [] { const char* e = getenv("VFMB_RESERVE_ADAM"); return e && atoi(e) != 0; }();
-#define LAUNCH_ADAM(LINK, MODE, FLAVOR)                                                                  \
-    k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR>, cap.u_cap, ch, 0, adam_reserve), 256, 0, stream>>>( \
-        dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,              \
-        plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, h, tab->adam_step,              \
-        kl_grad_scale, io->grad_bias, io->grad_entity, fa)
-#define LAUNCH_ADAM_F(LINK, MODE)                                                                        \
-    do { if (flavor == 0) LAUNCH_ADAM(LINK, MODE, 0); else if (flavor == 1) LAUNCH_ADAM(LINK, MODE, 1);  \
-         else LAUNCH_ADAM(LINK, MODE, 2); } while (0)
-    VFMB_LAYOUT_SWITCH(L, {
-        cudaEvent_t ev0, ev1;
-        profile_events(&ev0, &ev1);
-        if (ev0 && ev1) cudaEventRecord(ev0, stream);
-        if (cfg->link == VFMB_LINK_ABS) {
-            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM_F(0, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM_F(0, VFMB_GRAD_ONLY);
-        } else {
-            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM_F(1, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM_F(1, VFMB_GRAD_ONLY);
-        }
-        if (ev0 && ev1) cudaEventRecord(ev1, stream);
-    });
-#undef LAUNCH_ADAM_F
-#undef LAUNCH_ADAM
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int vfmb_sampled_adam_rows(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                                      const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
-                                      float kl_grad_scale, vfmb_stream stream) {
-    VFMB_PHASE_S1("vfmb_sampled_adam_rows");
-    return launch_adam(cfg, tab, plan, io, adam, mode, kl_grad_scale, 0, stream);
-}
-
-// S > 1: k_adam_rows_multi on the [S][u_cap] gradients / noise
-static int launch_adam_multi(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                             const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode, float kl_grad_scale,
-                             vfmb_stream stream_) {
-    Prep P;
-    int rc = prep(cfg, "vfmb_sampled_backward", stream_, 2, &P);
-    if (rc) return rc;
-    if (mode == VFMB_ADAM_TOUCHED && (!adam || !tab->entity_m || !tab->entity_v || !tab->bias_m || !tab->bias_v ||
-                                      !tab->adam_step || !tab->scalars_m || !tab->scalars_v))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: Adam state required");
-    if (mode == VFMB_GRAD_ONLY && (!io->grad_bias || !io->grad_entity))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: gradient outputs required");
-    if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_sampled_backward: bad mode");
-    if (!io->grow || !io->gws || !io->cq || !tab->scalars || !io->stats || !io->partials || !io->counters)
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: scratch required");
-    // the noise of the forward: injected arrays [S, U, ...] or what k_stage kept [S, u_cap, ...]
-    const float* eps_e = io->eps_entity ? io->eps_entity : io->es;
-    const float* eps_b = io->eps_bias ? io->eps_bias : io->ebs;
-    if (!eps_e || !eps_b || (io->eps_entity != nullptr) != (io->eps_bias != nullptr))
-        return set_error(VFMB_EINVAL, "vfmb_sampled_backward: noise of the forward required (both arrays injected, or none)");
-    const int eps_stride = io->eps_entity ? -1 : (int)P.cap.u_cap;
-    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
-    AdamDev h = make_adam(adam);
-    FinalArgs fa{};
-    fa.scalars = tab->scalars; fa.sm = tab->scalars_m; fa.sv = tab->scalars_v; fa.stats = io->stats;
-    fa.eps_global = io->eps_global; fa.grad_scalars = io->grad_scalars; fa.partials = io->partials;
-    fa.counter = io->counters + 2; fa.gslot = nullptr; fa.likelihood = cfg->likelihood;
-    int grid = (int)((cap.u_cap + 8 * (32 / L.lpr) - 1) / (8 * (32 / L.lpr)));
-    if (grid > kGridCap) grid = kGridCap;
-#define LAUNCH_AM(LINK, MODE)                                                                            \
-    k_adam_rows_multi<VEC, LPR, NV, LINK, MODE><<<grid, 256, 0, stream>>>(                               \
-        dc, (int)cap.u_cap, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v, \
-        plan->urec, plan->meta, eps_b, eps_e, eps_stride, io->cq, io->grow, io->gws, h, tab->adam_step,  \
-        kl_grad_scale, io->grad_bias, io->grad_entity, fa)
-    VFMB_LAYOUT_SWITCH(L, {
-        if (cfg->link == VFMB_LINK_ABS) {
-            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_AM(0, VFMB_ADAM_TOUCHED); else LAUNCH_AM(0, VFMB_GRAD_ONLY);
-        } else {
-            if (mode == VFMB_ADAM_TOUCHED) LAUNCH_AM(1, VFMB_ADAM_TOUCHED); else LAUNCH_AM(1, VFMB_GRAD_ONLY);
-        }
-    });
-#undef LAUNCH_AM
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
 static int backward_impl(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                          const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
                          float kl_grad_scale, int flavor, vfmb_stream stream_) {
@@ -1816,25 +997,6 @@ extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab,
     rc = launch_score(cfg, tab, plan, io, stream, 1);
     if (rc) return rc;
     return backward_impl(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, 2, stream);
-}
-
-extern "C" int vfmb_adam_dense(float* p, float* m, float* v, const float* g, int64_t n, const vfmb_adam* adam,
-                               const int32_t* adam_step, vfmb_stream stream_) {
-    if (!p || !m || !v || !g || !adam || !adam_step || n < 0) return set_error(VFMB_EINVAL, "vfmb_adam_dense: bad argument");
-    if (n == 0) return 0;
-    AdamDev h = make_adam(adam);
-    int64_t grid = (n + 255) / 256;
-    if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
-    k_adam_dense<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(p, m, v, g, n, h, adam_step);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int vfmb_adam_step_advance(int32_t* adam_step, vfmb_stream stream_) {
-    if (!adam_step) return set_error(VFMB_EINVAL, "vfmb_adam_step_advance: null");
-    k_step_advance<<<1, 1, 0, (cudaStream_t)stream_>>>(adam_step);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
 }
 
 extern "C" int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, int32_t U, int32_t step,

@@ -1,0 +1,89 @@
+// Shared by sampled.cu (stage / score / gather kernels, step entry points) and sampled_adam.cu
+// (row-update kernels): noise helpers, the scalar-update argument block, launch preparation.
+#pragma once
+#include "step_common.cuh"
+
+#include <cstdlib>
+
+namespace vfmb {
+
+constexpr int kMaxSamples = 8;      // variational samples per step (vfm-torch.py:19) the kernels take
+
+// Noise of variational sample s (vfm-torch.py:238-241 draws [S,1], [S,U], [S,U,d]): injected arrays are
+// indexed [s][unique rank] (U = number of unique rows of the batch), Philox carries s in the tag word.
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> entity_eps(const float* __restrict__ eps_entity, const DevCfg& c,
+                                              int u, int rowid, int k, uint32_t step, int s = 0, int U = 0) {
+    Vec<VEC> e;
+    if (eps_entity) {
+        e = ld_vec_nc<VEC>(eps_entity + ((size_t)s * U + u) * c.d + k);
+    } else {
+        float n4[4];
+        philox_normal4(c.seed, (uint32_t)rowid, (uint32_t)(k / VEC), step, philox_tag(kTagEntity, s), n4);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) e.v[i] = n4[i];
+    }
+    return e;
+}
+__device__ __forceinline__ float bias_eps(const float* __restrict__ eps_bias, const DevCfg& c, int u,
+                                          int rowid, uint32_t step, int s = 0, int U = 0) {
+    if (eps_bias) return __ldg(eps_bias + (size_t)s * U + u);
+    float n4[4];
+    philox_normal4(c.seed, (uint32_t)rowid, 0xFFFFFFFFu, step, philox_tag(kTagBias, s), n4);
+    return n4[0];
+}
+__device__ __forceinline__ float global_eps(const float* __restrict__ eps_global, const DevCfg& c,
+                                            uint32_t step, int s = 0) {
+    if (eps_global) return __ldg(eps_global + s);
+    float n4[4];
+    philox_normal4(c.seed, 0xFFFFFFFFu, 0xFFFFFFFFu, step, philox_tag(kTagGlobal, s), n4);
+    return n4[0];
+}
+
+// arguments of the scalar-parameter update folded into the row kernels (final_scalars)
+struct FinalArgs {
+    float* scalars; float* sm; float* sv; float* stats; const float* eps_global;
+    float* grad_scalars; double* partials; int32_t* counter; const float* gslot;
+    int likelihood;
+};
+
+}  // namespace vfmb
+
+using namespace vfmb;
+
+// ---- shared host-side preparation of one phase launch
+struct Prep {
+    cudaStream_t stream;
+    Layout L;
+    DevCfg dc;
+    vfmb_plan_capacity_t cap;
+    int ch;
+};
+static inline int prep(const vfmb_config* cfg, const char* who, vfmb_stream stream_, int min_fields, Prep* p) {
+    if (!cfg) return set_error(VFMB_EINVAL, "%s: null config", who);
+    if (cfg->B <= 0 || cfg->R <= 0 || cfg->d <= 0) return set_error(VFMB_EINVAL, "%s: bad B/R/d", who);
+    if (cfg->F < min_fields || cfg->F > VFMB_MAX_FIELDS) return set_error(VFMB_ESHAPE, "%s: F must be %d..%d", who, min_fields, VFMB_MAX_FIELDS);
+    if (cfg->S < 1 || cfg->S > kMaxSamples) return set_error(VFMB_ESHAPE, "%s: S=%d variational samples (1..%d)", who, cfg->S, kMaxSamples);
+    if (cfg->n_classes < 1 || cfg->n_classes > VFMB_MAX_FIELDS) return set_error(VFMB_EINVAL, "%s: bad n_classes", who);
+    if (cfg->likelihood != VFMB_GAUSSIAN && cfg->likelihood != VFMB_BERNOULLI) return set_error(VFMB_EINVAL, "%s: bad likelihood", who);
+    if (cfg->link != VFMB_LINK_ABS && cfg->link != VFMB_LINK_SOFTPLUS) return set_error(VFMB_EINVAL, "%s: bad link", who);
+    p->stream = (cudaStream_t)stream_;
+    if (!pick_layout(cfg->d, &p->L)) return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
+    p->dc = make_dev(cfg);
+    int rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &p->cap);
+    if (rc) return rc;
+    p->ch = kRounds * (32 / p->L.lpr);
+    return 0;
+}
+
+
+#define VFMB_PHASE_S1(who)                                                                             \
+    if (cfg && cfg->S != 1) return set_error(VFMB_ESHAPE, who ": the phase entry points take S = 1 (use "    \
+                                             "vfmb_sampled_forward / _backward / _step for S > 1)")
+
+
+// row update (sampled_adam.cu); flavor: see k_adam_rows
+int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan, const vfmb_step_io* io,
+                const vfmb_adam* adam, int32_t mode, float kl_grad_scale, int flavor, vfmb_stream stream_);
+int launch_adam_multi(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan, const vfmb_step_io* io,
+                      const vfmb_adam* adam, int32_t mode, float kl_grad_scale, vfmb_stream stream_);
