@@ -114,10 +114,18 @@ def make_model(w: synth.Workload, device, train_counts, lr):
               n_train=w.n_train, max_batch=w.batch, seed=synth.NOISE_SEED, lr=lr, device=device)
 
 
+def apply_tuning(args):
+    from vae_b200 import _lib as L
+    for kv in args.tune:
+        k, v = kv.split("=")
+        L.check(L.lib().vfmb_set_tuning(k.encode(), int(v)), "vfmb_set_tuning")
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    apply_tuning(args)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
@@ -153,18 +161,15 @@ def run_ours(args):
     def run_steps(lo, hi):
         """Software-pipelined loop: the plan of batch i+1 is built on a side stream while the
         kernels of batch i run (every batch still gets its own plan, built on the GPU)."""
+        out = None
         if dp is not None:
             for i in range(lo, hi):
-                dp.step(*batch(i))
-            return
-        if args.plan == "graph":                             # CUDA-graph replay of the same pipelined loop
-            loop.start(*batch(lo))
-            for i in range(lo, hi):
-                if i + 1 < hi:
-                    loop.step(*batch(i + 1))
-                else:
-                    loop.step()
-            return
+                out = dp.step(*batch(i))
+            return out
+        if args.plan == "graph":                             # CUDA-graph replay of the same pipelined loop:
+            for i in range(lo, hi):                          # run batch i, stage batch i+1 (its plan is built
+                out = loop.step(*batch(i + 1))               # on the side branch of the same graph)
+            return out
         if args.plan == "prefetch":
             model.prefetch_plan(batch(lo)[0])
         for i in range(lo, hi):
@@ -172,11 +177,15 @@ def run_ours(args):
             if args.plan == "prefetch" and i + 1 < hi:
                 model.prefetch_plan(batch(i + 1)[0])
             if args.plan == "cached":
-                model.fused_step(xb, yb, plan=static_plans[(i * world + rank) % n_batches])
+                out = model.fused_step(xb, yb, plan=static_plans[(i * world + rank) % n_batches])
             else:
-                model.fused_step(xb, yb)
+                out = model.fused_step(xb, yb)
+        return out
 
+    from vae_b200 import _lib as L
     loop = model.graphed_loop(B) if (args.plan == "graph" and dp is None) else None
+    if loop is not None:
+        loop.start(*batch(0))                                # the pipeline runs on from here: warm-up, then timed
     static_plans = {}
     if args.plan == "cached":                               # never-shuffled loader: plans recur every epoch
         for i in range(W, W + K):
@@ -189,17 +198,22 @@ def run_ours(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    n_launch0 = int(L.lib().vfmb_launch_count())
     ev0.record()
-    run_steps(W, W + K)
+    last = run_steps(W, W + K)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
-    loss = float(model._buf.stats[0].item())
+    loss = float(last["loss"].item())
+    # own kernels launched inside the timed region: counted by the library at every launch site
+    # (eager launches), plus the kernel nodes of the replayed graphs (counted when they were captured)
+    gpu_launches = int(L.lib().vfmb_launch_count()) - n_launch0
+    if loop is not None:
+        gpu_launches += loop.launches_per_graph * K
 
     # dominant kernel (k_adam_rows), timed per launch with CUDA events recorded by the library on the
     # launch stream immediately around it (vfmb_profile_events), over live training steps
-    from vae_b200 import _lib as L
     kr = []
     if dp is None:
         for i in range(W + K, W + K + min(K, 200)):
@@ -265,15 +279,14 @@ def run_ours(args):
                      "kernel_ms": rows_ms if rows_ms == rows_ms else None, "algorithmic_bytes": rk_bytes},
         "roofline_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms / K * 1e-3) / 1e9,
                           "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak, "unit": "GB/s"},
-        # own kernels per step: plan 9 (sort 2 x [hist, scan, scatter] + heads, scatter, finish) + step 5
-        # (stage, score, gather, combine_cut, adam_rows); eager F=2 steps fuse score+gather (4)
-        "e2e": e2e, "gpu_launches": ({"graph": 14, "prefetch": 13, "inline": 13, "cached": 4}[args.plan] if world == 1
-                                     else 18) * K * world,   # mode A: plan 9 + 6 step kernels + 3 all-reduce glue
+        "e2e": e2e, "gpu_launches": gpu_launches * world,
+        "gpu_launches_per_step": gpu_launches / K,
         "library_launches_per_step": "none (2 cudaMemsetAsync nodes in the plan)" if args.plan != "cached" else "none",
         "clocks": clocks, "final_loss": loss,
     }
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_budget)
+        out["parity"] = parity_vs_port(args, device)
     print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -288,6 +301,8 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
     xd = [torch.empty((B, F), dtype=torch.int64, device=device) for _ in range(3)]
     yd = [torch.empty(B, dtype=torch.float32, device=device) for _ in range(3)]
     res = torch.empty((K + W, 16), dtype=torch.float32).pin_memory()
+    # the reference loop pulls the predictions of every batch to the host (vfm-torch.py:363)
+    predh = torch.empty((4, B), dtype=torch.float32).pin_memory()
 
     copied = [torch.cuda.Event() for _ in range(3)]
 
@@ -307,17 +322,30 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
 
     hloop = model.graphed_loop(B, depth=3) if loop is not None else None
 
+    started = []
+    d2h = torch.cuda.Stream(device=device)
+    d2h_done = [torch.cuda.Event() for _ in range(3)]
+
     def run_graph(lo, hi):
         """graphed loop fed straight from pinned host memory: the staging copies ARE the H2D copies
-        (batch i+2 is copied on a copy stream while step i runs and the plan of i+1 is built)"""
-        hloop.start(*host_batch(lo))
-        if lo + 1 < hi:
+        (batch i+2 is copied on a copy stream while step i runs and the plan of i+1 is built); the
+        outputs of step i (its own slot) go back to the host on a third stream while step i+1 runs;
+        the pipeline is started once and runs on through warm-up and the timed steps"""
+        cur = torch.cuda.current_stream(device)
+        if not started:
+            hloop.start(*host_batch(lo))
             hloop.stage(*host_batch(lo + 1))
+            started.append(True)
         for i in range(lo, hi):
-            if i + 2 < hi:
-                hloop.stage(*host_batch(i + 2))
+            hloop.stage(*host_batch(i + 2))
+            s = hloop.head
+            cur.wait_event(d2h_done[s])                       # this replay rewrites the outputs of slot s
             out = hloop.step()
-            res[i].copy_(out["stats"][:16], non_blocking=True)
+            d2h.wait_event(hloop.done[s])
+            with torch.cuda.stream(d2h):
+                res[i].copy_(out["stats"][:16], non_blocking=True)
+                predh[i % 4].copy_(out["pred"], non_blocking=True)
+                d2h_done[s].record(d2h)
 
     def run(lo, hi):
         if loop is not None:
@@ -329,12 +357,14 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
             s = i % 3
             out = model.fused_step(xd[s], yd[s]) if dp is None else dp.step(xd[s], yd[s])
             res[i].copy_(out["stats"][:16], non_blocking=True)      # loss / KL / NLL back to the host
+            predh[i % 4].copy_(out["pred"], non_blocking=True)      # and the batch's predictions
 
     run(0, W)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     run(W, W + K)
+    torch.cuda.current_stream(device).wait_stream(d2h)         # the last outputs have reached the host
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -345,7 +375,7 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
     ms = float(t.item())
     assert np.isfinite(res[W:W + K, 0].numpy()).all(), "non-finite loss in the e2e run"
     return {"value": K * B * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * F * 8 + B * 4,
-            "d2h_bytes_per_step": 16 * 4, "steps": K, "ms_per_step": ms / K}
+            "d2h_bytes_per_step": 16 * 4 + B * 4, "steps": K, "ms_per_step": ms / K}
 
 
 # ------------------------------------------------------------------------------------------
@@ -590,6 +620,49 @@ def cpu_baseline(args, budget_s=20.0):
             "sample": f"{len(times)} full-size steps (batch {B}) after 2 warm-ups, median step {med * 1e3:.1f} ms"}
 
 
+def parity_vs_port(args, device):
+    """Part of the CPU leg (the only place bench.py runs the oracle): one training step of the timed
+    configuration -- same code path as the timed steps (in-kernel Philox noise, fused step), first batch,
+    fresh parameters -- against the torch port of the reference fed the exported Philox draws."""
+    from oracle import vfm_port
+    w = synth.make_workload(args.workload, n_rows=args.rows)
+    if w.rows > 20_000_000:
+        return {"skipped": "dense reference cannot allocate this table"}
+    B = w.batch
+    tc = w.train_counts()
+    lr = 1.0 / (1 + w.n_train // B)
+    model = make_model(w, device, tc, lr)
+    kl = "torch" if w.n_fields == 2 else "group"
+    port = vfm_port.SampledPort(w.field_sizes[0], w.field_sizes[1], w.d, torch.from_numpy(tc), output=w.output,
+                                field_sizes=w.field_sizes, kl_weighting=kl,
+                                interaction="prod" if w.n_fields == 2 else "pairwise", faithful_cost=False)
+    own = port.state_dict()
+    port.load_state_dict({k: v.detach().cpu().reshape(own[k].shape) for k, v in model.state_dict().items() if k in own},
+                         strict=False)
+    opt = torch.optim.Adam(port.parameters(), lr=lr)
+    x, y = torch.from_numpy(w.x[:B]), torch.from_numpy(w.y[:B])
+    uniq = torch.unique(x)
+    noise = [n.cpu() for n in model.philox_noise(uniq)]
+    res = model.fused_step(x.to(device), y.to(device))
+    torch.cuda.synchronize()
+    po = vfm_port.sampled_port_step(port, opt, x, y, w.n_train, noise)
+    pred, want = res["pred"].cpu().numpy().astype(np.float64), po["pred"].numpy().astype(np.float64)
+    out = {"oracle": "oracle/vfm_port.py (fp32 torch restatement of vfm-torch.py), same Philox draws injected",
+           "pred_max_rel_err": float(np.max(np.abs(pred - want) / np.maximum(np.abs(want), 1e-3))),
+           "loss_rel_err": float(abs(res["loss"].item() - po["loss"].item()) / abs(po["loss"].item())),
+           "kl_rel_err": float(abs(res["kl"].item() - po["kl"].item()) / abs(po["kl"].item()))}
+    u = uniq.numpy()
+    got = model.entity_params.weight.detach().cpu().numpy()[u].astype(np.float64)
+    ref = port.entity_params.weight.detach().numpy()[u].astype(np.float64)
+    err = np.abs(got - ref)
+    outside = err > 1e-5 * np.abs(ref) + 1e-4 * lr
+    out.update({"params_rows_checked": int(len(u)), "params_max_err_over_lr": float(err.max() / lr),
+                "params_fraction_outside_1e-5rel+1e-4lr": float(outside.mean()),
+                "note": "first Adam step from zero moments moves every element by ~lr*sign(g): elements outside the "
+                        "bound are those whose gradient is ~0 in fp32 (tests/test_gpu_bench_shapes.py proves it per element)"})
+    return out
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path.  The reference is pure
     Python/torch and is not present on the GPU box, so this times the oracle port
@@ -597,6 +670,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)               # torchrun exports OMP_NUM_THREADS=1: use every host core
     w = synth.make_workload(args.workload, n_rows=args.rows)
     t0 = time.time()
     cb = cpu_baseline(args, budget_s=max(20.0, min(150.0, 0.05 * args.steps)))
@@ -624,6 +698,8 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="override the synthetic dataset size")
     ap.add_argument("--plan", default="graph", choices=["inline", "prefetch", "graph", "cached"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
+                    help="library launch knob (vfmb_set_tuning), e.g. prefetch_mv=3; repeatable")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--parallel", default="auto", choices=["auto", "dp", "sharded"],
                     help="N>1: dp = replicated tables + dense all-reduce (mode A), sharded = row-sharded tables + "

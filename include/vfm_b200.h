@@ -75,6 +75,14 @@ typedef struct vfmb_tables {
     float* scalars;   float* scalars_m; float* scalars_v;
     /* device step counter: int32[1], number of Adam steps already applied */
     int32_t* adam_step;
+    /* device noise counter: int32[2] = {index the NEXT sampled forward draws with, index the LAST
+     * forward drew with}.  It is the `step` word of the Philox counter.  Every sampled forward
+     * (vfmb_sampled_forward / _score / _step) reads [0], records it in [1] and advances [0] when its
+     * last kernel finishes, so consecutive forwards never share noise whether or not an Adam step
+     * lies between them (the reference draws fresh noise in every forward, vfm-torch.py:238-241,
+     * also at test time :402-403); backward-side kernels re-create the draws of their forward from
+     * [1].  Required by the sampled entry points, unused by the closed form. */
+    int32_t* noise_step;
 } vfmb_tables;
 
 /* sampled variant scalar block (vfm-torch.py:136-138): */
@@ -320,12 +328,23 @@ int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, int32_t U, 
  * roofline of that kernel; no effect on results. */
 int vfmb_profile_events(void* start_event, void* stop_event);
 
+/* Number of kernels this library has enqueued (or captured into a CUDA graph) in this process so
+ * far: bench.py derives its `gpu_launches` from it (per captured graph x replays + eager launches). */
+int64_t vfmb_launch_count(void);
+
 /* Grid sizing of the (persistent, one-resident-wave) step kernels: leave `blocks_per_sm` block
  * slots per SM unused.  Set to 1 while enqueueing / capturing steps that run concurrently with
  * vfmb_plan_build on another stream -- the plan's small blocks then start at once instead of
  * displacing step blocks at every kernel boundary (ml20m: 121 -> 116 us per step).  Process-wide;
  * affects launches made after the call.  Default 0. */
 int vfmb_set_grid_reserve(int blocks_per_sm);
+
+/* Other process-wide launch knobs (host side only; results never depend on them -- every variant
+ * is bitwise identical, tests/test_gpu_sampled.py): key = "grid_reserve" (as above), "fuse_score"
+ * (-1 auto / 0 / 1: score the samples inside the backward's segmented reduction when F == 2),
+ * "adam_reserve" (0 / 1), "prefetch_mv" (bit mask: which earlier phase of the fused step pulls the
+ * Adam moments of the touched rows into L2 ahead of the row update). */
+int vfmb_set_tuning(const char* key, int value);
 
 const char* vfmb_last_error(void);
 int vfmb_version(void);

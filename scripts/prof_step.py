@@ -17,9 +17,13 @@ ap.add_argument("--warmup", type=int, default=4)
 ap.add_argument("--reserve", type=int, default=0,
                 help="1: the kernels of the default (graphed, plan-overlapped) bench: unfused score/gather, "
                      "one block slot per SM left free")
+ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE")
 a = ap.parse_args()
 from vae_b200 import _lib as L                                  # noqa: E402
 L.check(L.lib().vfmb_set_grid_reserve(a.reserve))
+for kv in a.tune:
+    k, v = kv.split("=")
+    L.check(L.lib().vfmb_set_tuning(k.encode(), int(v)))
 w = synth.make_workload(a.workload, n_rows=a.rows)
 model = bench.make_model(w, torch.device("cuda", 0), w.train_counts(), 1.0 / (1 + w.n_train // w.batch))
 B = w.batch

@@ -45,7 +45,7 @@ def test_host_only_queries_and_error_reporting():
 def test_struct_sizes_match_header():
     # the ctypes mirrors must have the C layout: 8 int32 + 8 int32 + 8 float + float (+pad) + u64
     assert C.sizeof(L.Config) == 8 * 4 + 8 * 4 + 8 * 4 + 4 + 4 + 8 + 4 + 4
-    assert C.sizeof(L.Tables) == 11 * 8
+    assert C.sizeof(L.Tables) == 12 * 8
     assert C.sizeof(L.Plan) == 12 * 8
     assert C.sizeof(L.StepIO) == 24 * 8
     assert C.sizeof(L.Adam) == 32

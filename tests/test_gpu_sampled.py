@@ -286,6 +286,64 @@ def test_philox_mode_matches_oracle_with_exported_noise(name):
     np.testing.assert_allclose(loss_philox, exact["loss"], rtol=1e-5)
 
 
+def test_dropin_forward_draws_fresh_noise_every_call():
+    """The advertised drop-in loop (model(x) -> loss.backward() -> torch.optim.Adam.step(), default
+    noise) never advances the Adam step counter of the fused path; the Philox stream is therefore
+    indexed by its own device counter that every sampled forward advances (vfm-torch.py:238-241 draws
+    fresh noise in every forward).  Each call must use philox_noise(step = call index), consecutive
+    calls must differ, and the backward must re-create the draws of ITS forward."""
+    meta, g = gu.load("sampled_reg_d64")
+    m = _model(meta, g, 0, seed=99)
+    x, y = gu.batch_of(meta, g, 0)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    uniq = torch.from_numpy(g["step0.uniq"])
+    opt = torch.optim.Adam(m.parameters(), lr=meta["lr"])
+    preds = []
+    for call in range(3):
+        assert m.noise_step.tolist()[0] == call
+        noise = m.philox_noise(uniq)                                    # what the next forward will draw
+        twin = _model(meta, g, 0, seed=99)
+        twin.load_state_dict(m.state_dict())
+        want = twin.gradients(xd, yd, noise=noise)                      # same draws, injected
+        likelihood, _, _, kl_term = m(xd)
+        assert m.noise_step.tolist() == [call + 1, call]
+        loss = -likelihood.log_prob(yd).mean() * meta["n_train"] + kl_term
+        pred = likelihood.mean.detach().clone()
+        assert torch.allclose(pred, want["pred"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(loss.item(), want["loss"].item(), rtol=1e-6)
+        opt.zero_grad()
+        loss.backward()
+        for k in ("entity_params.weight", "bias_params.weight", "global_bias_scale"):
+            got = dict(m.named_parameters())[k].grad
+            assert gu.rel_err(got.cpu().numpy(), want[k].cpu().numpy()) < 2e-6, (call, k)
+        opt.step()
+        preds.append(pred)
+    assert not torch.allclose(preds[0], preds[1], atol=1e-3)
+    # evaluation forwards consume noise too (vfm-torch.py:402-403 samples at test time)
+    a = m.fused_step(xd, yd, update=False)["pred"].clone()
+    b = m.fused_step(xd, yd, update=False)["pred"].clone()
+    assert not torch.allclose(a, b, atol=1e-3) and m.noise_step.tolist() == [5, 4]
+
+
+def test_out_of_range_id_poisons_the_loss():
+    """The reference raises IndexError from nn.Embedding; here the plan flags the id (meta[2]), maps it
+    to row 0 and the forward turns the loss into NaN -- a signal that needs no host synchronisation."""
+    from vae_b200.vfm_torch import CF
+    torch.manual_seed(0)
+    m = CF(8, output="reg", n_users=5, n_items=4, train_counts=torch.ones(9), n_train=6, max_batch=6, device=DEV)
+    x = torch.tensor([[0, 5], [1, 6], [2, 7], [3, 8], [4, 5], [1, 8]])
+    y = torch.ones(6)
+    ok = m.fused_step(x.to(DEV), y.to(DEV))
+    assert np.isfinite(ok["loss"].item())
+    x[2, 1] = 9                                                         # one past the last row
+    out = m.fused_step(x.to(DEV), y.to(DEV))
+    assert np.isnan(out["loss"].item())
+    with pytest.raises(IndexError):
+        m._plan.check_ids()
+    out = m.fused_step(x.to(DEV), y.to(DEV), noise=None, update=False)
+    assert np.isnan(out["loss"].item())
+
+
 @pytest.mark.parametrize("F,d", [(3, 8), (8, 64), (4, 20)])
 def test_multi_field_pairwise_matches_fp64_maths(F, d):
     """Config-4 shape: F>2 fields, pairwise interaction, per-group KL weights.  The reference has

@@ -51,7 +51,7 @@ class Tables(C.Structure):
                 ("entity", _f32p), ("entity_m", _f32p), ("entity_v", _f32p),
                 ("train_counts", _f32p),
                 ("scalars", _f32p), ("scalars_m", _f32p), ("scalars_v", _f32p),
-                ("adam_step", _i32p)]
+                ("adam_step", _i32p), ("noise_step", _i32p)]
 
 
 class Adam(C.Structure):
@@ -84,6 +84,8 @@ SYMBOLS = {
     "vfmb_version": (C.c_int, []),
     "vfmb_profile_events": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vfmb_set_grid_reserve": (C.c_int, [C.c_int]),
+    "vfmb_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
+    "vfmb_launch_count": (C.c_int64, []),
     "vfmb_last_error": (C.c_char_p, []),
     "vfmb_closed_off_bias_prior_mean": (C.c_int32, [C.c_int32] * 3),
     "vfmb_closed_off_bias_prior_scale": (C.c_int32, [C.c_int32] * 3),

@@ -1,6 +1,7 @@
 // C-ABI glue: error reporting, version, closed-form scalar-block layout.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "internal.h"
 
@@ -19,15 +20,26 @@ int set_error(int code, const char* fmt, ...) {
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop) { *start = g_prof_start; *stop = g_prof_stop; }
 
-static int g_grid_reserve = 0;
-int grid_reserve() { return g_grid_reserve; }
+unsigned long long g_launch_count = 0;
+static Tuning g_tuning;
+const Tuning& tuning() { return g_tuning; }
 
 }  // namespace vfmb
 
 extern "C" int vfmb_set_grid_reserve(int blocks_per_sm) {
     if (blocks_per_sm < 0 || blocks_per_sm > 8) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_grid_reserve: 0..8");
-    vfmb::g_grid_reserve = blocks_per_sm;
+    vfmb::g_tuning.grid_reserve = blocks_per_sm;
     return 0;
+}
+
+extern "C" int vfmb_set_tuning(const char* key, int value) {
+    if (!key) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: null key");
+    vfmb::Tuning& t = vfmb::g_tuning;
+    if (!strcmp(key, "grid_reserve")) return vfmb_set_grid_reserve(value);
+    if (!strcmp(key, "fuse_score")) { if (value < -1 || value > 1) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: fuse_score -1..1"); t.fuse_score = value; return 0; }
+    if (!strcmp(key, "adam_reserve")) { t.adam_reserve = value != 0; return 0; }
+    if (!strcmp(key, "prefetch_mv")) { if (value < 0 || value > 15) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: prefetch_mv 0..15"); t.prefetch_mv = value; return 0; }
+    return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: unknown key '%s'", key);
 }
 
 extern "C" int vfmb_profile_events(void* start_event, void* stop_event) {
@@ -36,6 +48,7 @@ extern "C" int vfmb_profile_events(void* start_event, void* stop_event) {
     return 0;
 }
 
+extern "C" int64_t vfmb_launch_count(void) { return (int64_t)vfmb::g_launch_count; }
 extern "C" const char* vfmb_last_error(void) { return vfmb::g_error; }
 extern "C" int vfmb_version(void) { return 100; }
 

@@ -687,7 +687,7 @@ extern "C" int vfmb_predict_mean(const vfmb_config* cfg, const float* bias, cons
     int64_t g = ((int64_t)cfg->B + gpb - 1) / gpb;
     if (g > kMaxGrid) g = kMaxGrid;
     VFMB_LAYOUT_SWITCH3(L, {
-        k_predict_mean<VEC, LPR, NV><<<(int)g, 256, 0, (cudaStream_t)stream_>>>(
+        k_predict_mean<VEC, LPR, NV><<<(int)g, 256, 0, counted((cudaStream_t)stream_)>>>(
             cfg->B, cfg->F, cfg->d, cfg->R, bias, entity, global_bias, x, out);
     });
     CUDA_TRY(cudaGetLastError());
@@ -741,11 +741,11 @@ extern "C" int vfmb_closed_forward(const vfmb_config* cfg, const vfmb_tables* ta
     const int grid_b = grid_warps(cfg->B, ch);
     const size_t smem = (size_t)8 * (2 * cfg->d + 4) * sizeof(float);
     VFMB_LAYOUT_SWITCH(L, {
-        k_cstage<VEC, LPR, NV><<<nblk, 256, smem, stream>>>(
+        k_cstage<VEC, LPR, NV><<<nblk, 256, smem, counted(stream)>>>(
             cc, tab->bias, tab->entity, tab->train_counts, tab->scalars, plan->urec, plan->class_off, plan->z,
             io->vs, io->ws, io->ebs, io->cq, io->kl_bias_out, io->kl_entity_out, io->partials,
             io->counters + 0, pg_part, blk_class, io->stats);
-        k_cscore<VEC, LPR, NV><<<grid_b, 256, 0, stream>>>(
+        k_cscore<VEC, LPR, NV><<<grid_b, 256, 0, counted(stream)>>>(
             cc, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->ebs, io->y, io->pred,
             io->resid, io->rsorted, io->msg, io->partials, io->counters + 1, io->stats);
     });
@@ -788,33 +788,33 @@ extern "C" int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* t
     const int grid_u = grid_warps(cap.u_cap, ch), grid_t = grid_warps(cap.n_tiles, 32 / L.lpr);
     const int d3 = 3 * cfg->d;
     VFMB_LAYOUT_SWITCH(L, {
-        k_cgather<VEC, LPR, NV><<<grid_t, 256, 0, stream>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
+        k_cgather<VEC, LPR, NV><<<grid_t, 256, 0, counted(stream)>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
                                                             plan->pos_rank, io->vs, io->msg, io->rsorted,
                                                             gslot, io->grow, io->gws);
     });
     // rows cut by tile boundaries: same combine kernel, viewing [A|Bq|C] as one 3d-wide row
     VFMB_LAYOUT_SWITCH(L3, {
-        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (d3 + 4) * sizeof(float), stream>>>(
+        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (d3 + 4) * sizeof(float), counted(stream)>>>(
             d3, 2, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
     });
     VFMB_LAYOUT_SWITCH(L, {
         if (mode == VFMB_ADAM_TOUCHED)
-            k_cadam<VEC, LPR, NV, VFMB_ADAM_TOUCHED><<<grid_u, 256, 0, stream>>>(
+            k_cadam<VEC, LPR, NV, VFMB_ADAM_TOUCHED><<<grid_u, 256, 0, counted(stream)>>>(
                 cc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v, tab->scalars,
                 plan->urec, plan->meta, io->cq, io->grow, io->gws, h, tab->adam_step, io->grad_bias, io->grad_entity);
         else
-            k_cadam<VEC, LPR, NV, VFMB_GRAD_ONLY><<<grid_u, 256, 0, stream>>>(
+            k_cadam<VEC, LPR, NV, VFMB_GRAD_ONLY><<<grid_u, 256, 0, counted(stream)>>>(
                 cc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v, tab->scalars,
                 plan->urec, plan->meta, io->cq, io->grow, io->gws, h, tab->adam_step, io->grad_bias, io->grad_entity);
     });
     const int items = cfg->F * (2 * cfg->d + 3);
     const int grid_f = (items + 7) / 8;
     if (mode == VFMB_ADAM_TOUCHED)
-        k_cfinal<VFMB_ADAM_TOUCHED><<<grid_f, 256, 0, stream>>>(cc, tab->scalars, tab->scalars_m, tab->scalars_v, io->stats,
+        k_cfinal<VFMB_ADAM_TOUCHED><<<grid_f, 256, 0, counted(stream)>>>(cc, tab->scalars, tab->scalars_m, tab->scalars_v, io->stats,
                                                                 pg_part, blk_class, nblk, pg_sum, io->counters + 2, h,
                                                                 tab->adam_step, io->grad_scalars);
     else
-        k_cfinal<VFMB_GRAD_ONLY><<<grid_f, 256, 0, stream>>>(cc, tab->scalars, tab->scalars_m, tab->scalars_v, io->stats,
+        k_cfinal<VFMB_GRAD_ONLY><<<grid_f, 256, 0, counted(stream)>>>(cc, tab->scalars, tab->scalars_m, tab->scalars_v, io->stats,
                                                              pg_part, blk_class, nblk, pg_sum, io->counters + 2, h,
                                                              tab->adam_step, io->grad_scalars);
     CUDA_TRY(cudaGetLastError());

@@ -119,16 +119,18 @@ k_dp_apply(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float
 template <int LINK, int LIK>
 __global__ void k_dp_final(DevCfg c, float* __restrict__ scalars, float* __restrict__ sm, float* __restrict__ sv,
                            const float* __restrict__ tail, const float* __restrict__ eps_global, AdamDev h,
-                           int32_t* __restrict__ adam_step, float* __restrict__ stats) {
+                           int32_t* __restrict__ adam_step, const int32_t* __restrict__ noise_step,
+                           float* __restrict__ stats) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint32_t step = (uint32_t)adam_step[0];
+    const uint32_t nstep = noise_step ? (uint32_t)noise_step[1] : step;    // noise index of the forward
     float alpha = scalars[VFMB_S_ALPHA], mu0 = scalars[VFMB_S_GB_MEAN], rho0 = scalars[VFMB_S_GB_SCALE];
     const float sig0 = link_fn<LINK>(rho0), ap = link_fn<LINK>(alpha);
     float e0;
     if (eps_global) e0 = eps_global[0];
     else {
         float n4[4];
-        philox_normal4(c.seed, 0xFFFFFFFFu, 0xFFFFFFFFu, step, philox_tag(kTagGlobal, 0), n4);
+        philox_normal4(c.seed, 0xFFFFFFFFu, 0xFFFFFFFFu, nstep, philox_tag(kTagGlobal, 0), n4);
         e0 = n4[0];
     }
     const double nll = (double)tail[VFMB_DP_T_NLL], sr = (double)tail[VFMB_DP_T_RESID], sq = (double)tail[VFMB_DP_T_SQERR];
@@ -164,7 +166,7 @@ extern "C" int vfmb_dp_scatter_counts(const vfmb_config* cfg, const vfmb_plan* p
     int64_t u_cap = n < cfg->R ? n : cfg->R;
     int g = (int)((u_cap + 255) / 256);
     if (g > 4 * kNumSMs) g = 4 * kNumSMs;
-    k_dp_scatter_counts<<<g, 256, 0, (cudaStream_t)stream_>>>(plan->urec, plan->meta, plan->z, io->stats, cfg->B,
+    k_dp_scatter_counts<<<g, 256, 0, counted((cudaStream_t)stream_)>>>(plan->urec, plan->meta, plan->z, io->stats, cfg->B,
                                                                cfg->F, counts, tail);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -187,7 +189,7 @@ extern "C" int vfmb_dp_apply_sampled(const vfmb_config* cfg, const vfmb_tables* 
     if (g > kMaxGrid) g = kMaxGrid;
     if (g < 1) g = 1;
 #define LAUNCH_APPLY(LINK)                                                                              \
-    k_dp_apply<VEC, LPR, NV, LINK><<<(int)g, 256, 0, stream>>>(                                         \
+    k_dp_apply<VEC, LPR, NV, LINK><<<(int)g, 256, 0, counted(stream)>>>(                                         \
         dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,             \
         tab->train_counts, grad_entity, grad_bias, counts, tail, cfg->R, h, tab->adam_step, dense_adam, \
         partials, counters + 3, stats)
@@ -205,8 +207,8 @@ extern "C" int vfmb_dp_final(const vfmb_config* cfg, const vfmb_tables* tab, con
     DevCfg dc = make_dev(cfg);
     AdamDev h = make_adam(adam);
 #define LAUNCH_DPF(LINK, LIK)                                                                           \
-    k_dp_final<LINK, LIK><<<1, 32, 0, stream>>>(dc, tab->scalars, tab->scalars_m, tab->scalars_v, tail,  \
-                                                eps_global, h, tab->adam_step, stats)
+    k_dp_final<LINK, LIK><<<1, 32, 0, counted(stream)>>>(dc, tab->scalars, tab->scalars_m, tab->scalars_v, tail,  \
+                                                eps_global, h, tab->adam_step, tab->noise_step, stats)
     switch (cfg->link * 2 + cfg->likelihood) {
         case 0: LAUNCH_DPF(0, 0); break;
         case 1: LAUNCH_DPF(0, 1); break;

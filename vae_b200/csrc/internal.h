@@ -19,8 +19,22 @@ constexpr int kPriorGrid = 2 * kNumSMs; // blocks that carry prior-gradient part
 static inline int64_t cut_list_capacity(int64_t n_tiles) { return n_tiles + n_tiles / (kHotPartials - 2) + 4; }
 
 int set_error(int code, const char* fmt, ...);
-// block slots per SM the persistent step kernels leave free (see vfmb_set_grid_reserve)
-int grid_reserve();
+// Process-wide launch tuning (vfmb_set_tuning / vfmb_set_grid_reserve); read at launch time on the
+// host, never by device code.  Defaults are the measured best for the BASELINE shapes.
+struct Tuning {
+    int grid_reserve = 0;    // block slots per SM the persistent step kernels leave free
+    int fuse_score = -1;     // F == 2 fused step: -1 = k_gather_score unless a slot is reserved, 0 / 1 = force
+    int adam_reserve = 0;    // 1: k_adam_rows also leaves the reserved slot free
+    int prefetch_mv = 0;     // fused step: earlier phases pull the Adam moments of the touched rows into L2
+                             //   (bit 0: k_stage fetches m, bit 1: k_stage fetches v, bit 2: k_gather fetches m,
+                             //    bit 3: k_gather fetches v)
+};
+const Tuning& tuning();
+static inline int grid_reserve() { return tuning().grid_reserve; }
+// every kernel launch of the library passes its stream through counted(): vfmb_launch_count() is the
+// number of own kernels enqueued (or captured into a CUDA graph) by this process so far
+extern unsigned long long g_launch_count;
+static inline cudaStream_t counted(cudaStream_t s) { ++g_launch_count; return s; }
 // optional events around the dominant kernel (see vfmb_profile_events)
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
 

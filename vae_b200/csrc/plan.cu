@@ -405,17 +405,17 @@ extern "C" int vfmb_plan_build(const vfmb_config* cfg, const int64_t* x, const f
     int32_t* kout = w.kA; int32_t* vout = w.vA;
     for (int p = 0; p < g.npass; ++p) {
         if (p == 0)
-            k_sort_hist<true><<<g.n_tiles, kSortThreads, 0, stream>>>(x, nullptr, train_counts, N, cfg->F, cfg->R,
+            k_sort_hist<true><<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(x, nullptr, train_counts, N, cfg->F, cfg->R,
                 1 << g.tile_shift, g.n_tiles, 0, g.bins[0], w.hist, gtot[0], plan->meta, w.partials, plan->z);
         else
-            k_sort_hist<false><<<g.n_tiles, kSortThreads, 0, stream>>>(nullptr, kin, nullptr, N, cfg->F, cfg->R,
+            k_sort_hist<false><<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(nullptr, kin, nullptr, N, cfg->F, cfg->R,
                 1 << g.tile_shift, g.n_tiles, g.shift[p], g.bins[p], w.hist, gtot[p], plan->meta, nullptr, nullptr);
-        k_sort_scan<<<g.bins[p], 128, 0, stream>>>(w.hist, gtot[p], g.n_tiles);
+        k_sort_scan<<<g.bins[p], 128, 0, counted(stream)>>>(w.hist, gtot[p], g.n_tiles);
         if (p == 0)
-            k_sort_scatter<true><<<g.n_tiles, kSortThreads, 0, stream>>>(x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
+            k_sort_scatter<true><<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
                                                                          g.n_tiles, g.shift[p], g.bins[p], w.hist);
         else
-            k_sort_scatter<false><<<g.n_tiles, kSortThreads, 0, stream>>>(x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
+            k_sort_scatter<false><<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
                                                                           g.n_tiles, g.shift[p], g.bins[p], w.hist);
         CUDA_TRY(cudaGetLastError());
         kin = kout; vin = vout;
@@ -423,8 +423,8 @@ extern "C" int vfmb_plan_build(const vfmb_config* cfg, const int64_t* x, const f
         vout = (vout == w.vA) ? w.vB : w.vA;
     }
     const int32_t* keys_s = kin; const int32_t* vals_s = vin;
-    k_plan_heads<<<g.n_tiles, kSortThreads, 0, stream>>>(keys_s, N, g.tile_shift, w.tile_heads);
-    k_plan_scatter<<<g.n_tiles, kSortThreads, 0, stream>>>(keys_s, vals_s, w.tile_heads, N, g.tile_shift, plan->uniq,
+    k_plan_heads<<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(keys_s, N, g.tile_shift, w.tile_heads);
+    k_plan_scatter<<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(keys_s, vals_s, w.tile_heads, N, g.tile_shift, plan->uniq,
                                                            plan->seg_off, plan->inverse, plan->occ, plan->pos_of,
                                                            plan->pos_rank, plan->meta);
     CUDA_TRY(cudaGetLastError());
@@ -433,7 +433,7 @@ extern "C" int vfmb_plan_build(const vfmb_config* cfg, const int64_t* x, const f
     ClassBounds cbd{};
     cbd.n = cfg->n_classes;
     for (int i = 0; i < kMaxFields; ++i) cbd.bound[i] = cfg->class_bound[i];
-    k_plan_finish<<<grid2, 256, 0, stream>>>(plan->uniq, plan->seg_off, plan->occ, plan->inverse, N, cfg->F,
+    k_plan_finish<<<grid2, 256, 0, counted(stream)>>>(plan->uniq, plan->seg_off, plan->occ, plan->inverse, N, cfg->F,
                                              cbd, plan->partner, plan->urec, plan->class_off, plan->meta, plan->hot,
                                              (int)cut_list_capacity(cap.n_tiles));
     CUDA_TRY(cudaGetLastError());

@@ -28,10 +28,12 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         const float* __restrict__ train_counts, const int32_t* __restrict__ urec,
         const int32_t* __restrict__ meta, const float* __restrict__ z,
         const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
-        const int32_t* __restrict__ adam_step, float* __restrict__ vs, float* __restrict__ ws,
+        const int32_t* __restrict__ noise_step, float* __restrict__ vs, float* __restrict__ ws,
         float* __restrict__ es, float* __restrict__ ebs, float* __restrict__ cq,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
-        int smp, int u_stride) {
+        int smp, int u_stride, const float* __restrict__ pf_m, const float* __restrict__ pf_v) {
+    // pf_m / pf_v (optional): Adam moment tables whose touched rows are pulled into L2 here, while
+    // this kernel is issue-bound on Philox and the DRAM pipe idles -- k_adam_rows finds them there
     // smp: variational sample this launch draws (S > 1: one launch per sample, outputs [S][u_stride]);
     // the KL and the KL weights do not depend on the sample and are formed by sample 0
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
@@ -40,7 +42,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
     vs += (size_t)smp * u_stride * d; ws += (size_t)smp * u_stride;
     if (es) es += (size_t)smp * u_stride * d;
     if (ebs) ebs += (size_t)smp * u_stride;
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
     const unsigned gmask = group_mask<LPR>();
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -57,6 +59,8 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
             const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
             rowid_l = rec.x;
             prefetch_row(entity + (size_t)rowid_l * 2 * d, 8 * d);
+            if (pf_m) prefetch_row(pf_m + (size_t)rowid_l * 2 * d, 8 * d);
+            if (pf_v) prefetch_row(pf_v + (size_t)rowid_l * 2 * d, 8 * d);
             const float2 ab = *reinterpret_cast<const float2*>(bias + (size_t)rowid_l * 2);
             const float tcnt = __ldg(train_counts + rowid_l);
             const int gid_l = rowid_l * c.row_stride + c.row_offset;     // global id (row-sharded tables)
@@ -141,13 +145,13 @@ __global__ void __launch_bounds__(256)
 k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__ inverse,
         const int32_t* __restrict__ pos_of, const float* __restrict__ vs, const float* __restrict__ ws,
         const float* __restrict__ y, const float* __restrict__ eps_global,
-        const int32_t* __restrict__ adam_step, float* __restrict__ pred, float* __restrict__ mean,
+        int32_t* noise_step, const int32_t* __restrict__ meta, float* __restrict__ pred, float* __restrict__ mean,
         float* __restrict__ resid, float* __restrict__ rsorted, float* __restrict__ msg,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
         int defer_kl) {
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
     const int d = c.d, F = c.F, B = c.B;
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
     const unsigned gmask = group_mask<LPR>();
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -282,6 +286,7 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
                 stats[VFMB_ST_LOSS] = (float)((double)c.n_train * nll / (double)B + (double)kl);
             }
             stats[VFMB_ST_W0] = w0;
+            forward_done(noise_step, step, meta, stats);
             *counter = 0;
         }
     }
@@ -299,12 +304,12 @@ __global__ void __launch_bounds__(256)
 k_score_multi(DevCfg c, int u_stride, const float* __restrict__ scalars, const int32_t* __restrict__ inverse,
               const int32_t* __restrict__ pos_of, const float* __restrict__ vs, const float* __restrict__ ws,
               const float* __restrict__ y, const float* __restrict__ eps_global,
-              const int32_t* __restrict__ adam_step, float* __restrict__ pred, float* __restrict__ mean,
+              int32_t* noise_step, const int32_t* __restrict__ meta, float* __restrict__ pred, float* __restrict__ mean,
               float* __restrict__ resid, float* __restrict__ rsorted, float* __restrict__ msg,
               double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
     constexpr int GPW = kWarp / LPR;
     const int d = c.d, F = c.F, B = c.B, S = c.S;
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR;
     const unsigned gmask = group_mask<LPR>();
     const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
@@ -417,6 +422,7 @@ k_score_multi(DevCfg c, int u_stride, const float* __restrict__ scalars, const i
             stats[VFMB_ST_KL] = kl;
             stats[VFMB_ST_LOSS] = (float)((double)c.n_train * tot[0] / cnt + (double)kl);
             stats[VFMB_ST_W0] = w0s[0];
+            forward_done(noise_step, step, meta, stats);
             *counter = 0;
         }
     }
@@ -554,14 +560,14 @@ __global__ void __launch_bounds__(256)
 k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__ partner,
                const int32_t* __restrict__ pos_rank, const int32_t* __restrict__ occ,
                const float* __restrict__ vs, const float* __restrict__ ws, const float* __restrict__ y,
-               const float* __restrict__ eps_global, const int32_t* __restrict__ adam_step,
+               const float* __restrict__ eps_global, int32_t* noise_step, const int32_t* __restrict__ meta,
                float* __restrict__ pred, float* __restrict__ mean, float* __restrict__ resid,
                float* __restrict__ gslot, float* __restrict__ grow, float* __restrict__ gws,
                double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
     constexpr int GPW = kWarp / LPR, UNR = 4;
     const int d = c.d, B = c.B, N = 2 * c.B;
     const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR;
     const unsigned gmask = group_mask<LPR>();
     const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
@@ -692,6 +698,7 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
             stats[VFMB_ST_SUM_SQERR] = (float)tot[2];
             stats[VFMB_ST_LOSS] = (float)((double)c.n_train * tot[0] / (double)B);
             stats[VFMB_ST_W0] = w0;
+            forward_done(noise_step, step, meta, stats);
             *counter = 0;
         }
     }
@@ -748,16 +755,20 @@ static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     int rc = prep(cfg, "vfmb_sampled_stage", stream_, 1, &P);
     if (rc) return rc;
     if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: null argument");
+    if (!tab->noise_step) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: tables.noise_step required");
     if (!lean && !io->eps_entity && !io->es) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: noise scratch (es) required");
     if (!io->eps_bias && !io->ebs) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: noise scratch (ebs) required");
     if (!io->vs || !io->ws || !io->cq || !io->partials || !io->counters || !io->stats)
         return set_error(VFMB_EINVAL, "vfmb_sampled_stage: scratch required");
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch; const auto& cap = P.cap;
+    // fused training step only: the row update follows within the same step
+    const float* pf_m = (lean && (tuning().prefetch_mv & 1)) ? tab->entity_m : nullptr;
+    const float* pf_v = (lean && (tuning().prefetch_mv & 2)) ? tab->entity_v : nullptr;
 #define LAUNCH_STAGE(LINK, LEAN)                                                                       \
-    k_stage<VEC, LPR, NV, LINK, LEAN><<<grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, ch), 256, 0, stream>>>( \
+    k_stage<VEC, LPR, NV, LINK, LEAN><<<grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, ch), 256, 0, counted(stream)>>>( \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
-        io->eps_bias, io->eps_entity, tab->adam_step, io->vs, io->ws, io->es,                          \
-        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap)
+        io->eps_bias, io->eps_entity, tab->noise_step, io->vs, io->ws, io->es,                         \
+        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap, pf_m, pf_v)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) { if (lean) LAUNCH_STAGE(0, 1); else LAUNCH_STAGE(0, 0); }
         else                            { if (lean) LAUNCH_STAGE(1, 1); else LAUNCH_STAGE(1, 0); }
@@ -773,12 +784,13 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     int rc = prep(cfg, "vfmb_sampled_score", stream_, 2, &P);
     if (rc) return rc;
     if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_score: null argument");
+    if (!tab->noise_step) return set_error(VFMB_EINVAL, "vfmb_sampled_score: tables.noise_step required");
     if (cfg->F > 2 && io->y && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_score: msg scratch required for F>2");
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch;
 #define LAUNCH_SCORE(LINK, LIK)                                                                        \
-    k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, stream>>>( \
+    k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, counted(stream)>>>( \
         dc, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->y, io->eps_global,          \
-        tab->adam_step, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials,             \
+        tab->noise_step, plan->meta, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials, \
         io->counters + 1, io->stats, defer_kl)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
@@ -821,9 +833,9 @@ static int forward_multi(const vfmb_config* cfg, const vfmb_tables* tab, const v
     int grid = (int)((cfg->B + 8 * (32 / L.lpr) - 1) / (8 * (32 / L.lpr)));
     if (grid > kGridCap) grid = kGridCap;
 #define LAUNCH_SM(LINK, LIK)                                                                             \
-    k_score_multi<VEC, LPR, NV, LINK, LIK><<<grid, 256, 0, stream>>>(                                    \
+    k_score_multi<VEC, LPR, NV, LINK, LIK><<<grid, 256, 0, counted(stream)>>>(                                    \
         dc, (int)P.cap.u_cap, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->y, io->eps_global, \
-        tab->adam_step, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials, io->counters + 1, io->stats)
+        tab->noise_step, plan->meta, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials, io->counters + 1, io->stats)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SM(0, VFMB_GAUSSIAN); else LAUNCH_SM(0, VFMB_BERNOULLI);
@@ -872,18 +884,18 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
     const int N = cfg->B * cfg->F;
     VFMB_LAYOUT_SWITCH(L, {
         if (unit_coef)
-            k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>(
+            k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
                 cfg->d, cfg->F, N, plan->partner, plan->pos_rank, io->vs, tbl, io->rsorted, gslot, io->grow, io->gws);
         else
-            k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, stream>>>(
+            k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
                 cfg->d, cfg->F, N, plan->partner, plan->pos_rank, io->vs, tbl, io->rsorted, gslot, io->grow, io->gws);
         const size_t smem = 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float);
         if (plan->hot)      // lists of the cut rows from the plan: no scan over the unique rows
-            k_combine_cut<VEC, LPR, NV><<<grid_warps(cap.n_tiles, 1), 256, smem, stream>>>(
+            k_combine_cut<VEC, LPR, NV><<<grid_warps(cap.n_tiles, 1), 256, smem, counted(stream)>>>(
                 cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, plan->hot, (int)cut_list_capacity(cap.n_tiles),
                 gslot, io->vs, io->grow, io->gws);
         else
-            k_combine<VEC, LPR, NV, 0><<<grid_warps(cap.u_cap, 32), 256, smem, stream>>>(
+            k_combine<VEC, LPR, NV, 0><<<grid_warps(cap.u_cap, 32), 256, smem, counted(stream)>>>(
                 cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
     });
     CUDA_TRY(cudaGetLastError());
@@ -902,16 +914,15 @@ static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, c
     float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
     // one lane group per tile.  (Smaller blocks were tried for the plan-overlapped step -- 121.9 us with
     // 128 threads, 125.2 us with 64, against 113.4 us for the unfused pair: the fused kernel does not
-    // lose to the plan through SM slots; VFMB_GS_BLOCK overrides for experiments.)
-    static const int gs_block_env = [] { const char* e = getenv("VFMB_GS_BLOCK"); return e ? atoi(e) : 0; }();
-    const int gs_block = gs_block_env ? gs_block_env : 256;
+    // lose to the plan through SM slots.)
+    const int gs_block = 256;
     const int64_t gs_warps = (cap.n_tiles + (32 / L.lpr) - 1) / (32 / L.lpr);
     int gs_grid = (int)((gs_warps + gs_block / 32 - 1) / (gs_block / 32));
     if (gs_grid > kGridCap) gs_grid = kGridCap;            // block partials are sized for kGridCap blocks
 #define LAUNCH_GS(LINK, LIK)                                                                             \
-    k_gather_score<VEC, LPR, NV, LINK, LIK><<<gs_grid, gs_block, 0, stream>>>(                           \
+    k_gather_score<VEC, LPR, NV, LINK, LIK><<<gs_grid, gs_block, 0, counted(stream)>>>(                           \
         dc, tab->scalars, plan->partner, plan->pos_rank, plan->occ, io->vs, io->ws, io->y, io->eps_global, \
-        tab->adam_step, io->pred, io->mean, io->resid, gslot, io->grow, io->gws, io->partials,           \
+        tab->noise_step, plan->meta, io->pred, io->mean, io->resid, gslot, io->grow, io->gws, io->partials, \
         io->counters + 1, io->stats)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
@@ -920,7 +931,7 @@ static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, c
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_GS(1, VFMB_GAUSSIAN); else LAUNCH_GS(1, VFMB_BERNOULLI);
         }
         const size_t smem = 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float);
-        k_combine_cut<VEC, LPR, NV><<<grid_warps(cap.n_tiles, 1), 256, smem, stream>>>(
+        k_combine_cut<VEC, LPR, NV><<<grid_warps(cap.n_tiles, 1), 256, smem, counted(stream)>>>(
             cfg->d, cfg->F, plan->urec, plan->meta, plan->hot, (int)cut_list_capacity(cap.n_tiles),
             gslot, io->vs, io->grow, io->gws);
     });
@@ -949,7 +960,7 @@ static int backward_impl(const vfmb_config* cfg, const vfmb_tables* tab, const v
         const int N = cfg->B * cfg->F;
         int g = (N + 255) / 256;
         if (g > 4 * kNumSMs) g = 4 * kNumSMs;
-        k_scatter_resid<<<g, 256, 0, stream>>>(io->resid, plan->pos_of, N, cfg->F, io->rsorted);
+        k_scatter_resid<<<g, 256, 0, counted(stream)>>>(io->resid, plan->pos_of, N, cfg->F, io->rsorted);
         CUDA_TRY(cudaGetLastError());
     }
     if (cfg->S > 1) {       // one ordered segmented sum per variational sample, then the summed row update
@@ -986,8 +997,8 @@ extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab,
     // measured (ml20m): alone the fused kernel saves 5 us per step (104 -> 99 us); next to a
     // concurrently running plan it loses 6 us -- it needs 111 registers per thread, which leaves no
     // room on an SM for the plan's blocks.  So: fused unless the caller reserved room for the plan.
-    static const int fuse_env = [] { const char* e = getenv("VFMB_FUSE_SCORE"); return e ? atoi(e) : -1; }();
-    const bool fuse_gs = fuse_env >= 0 ? fuse_env != 0 : grid_reserve() == 0;
+    const int fuse_knob = tuning().fuse_score;
+    const bool fuse_gs = fuse_knob >= 0 ? fuse_knob != 0 : grid_reserve() == 0;
     if (cfg && cfg->F == 2 && plan && plan->hot && fuse_gs) {
         // F == 2: 4 launches -- k_stage<LEAN>, k_gather_score, k_combine_cut, k_adam_rows<FLAVOR 2>
         rc = launch_gather_score(cfg, tab, plan, io, stream);
@@ -1008,8 +1019,8 @@ extern "C" int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, 
     if (cfg->S < 1 || cfg->S > kMaxSamples) return set_error(VFMB_ESHAPE, "vfmb_philox_normals: S=%d (1..%d)", cfg->S, kMaxSamples);
     int64_t work = (int64_t)U * ((cfg->d + vec - 1) / vec) * cfg->S;
     int grid = (int)((work + 255) / 256 > 4096 ? 4096 : (work + 255) / 256);
-    if (vec == 4) k_philox_export<4><<<grid, 256, 0, (cudaStream_t)stream_>>>(dc, uniq, U, (uint32_t)step, eps_global, eps_bias, eps_entity);
-    else k_philox_export<1><<<grid, 256, 0, (cudaStream_t)stream_>>>(dc, uniq, U, (uint32_t)step, eps_global, eps_bias, eps_entity);
+    if (vec == 4) k_philox_export<4><<<grid, 256, 0, counted((cudaStream_t)stream_)>>>(dc, uniq, U, (uint32_t)step, eps_global, eps_bias, eps_entity);
+    else k_philox_export<1><<<grid, 256, 0, counted((cudaStream_t)stream_)>>>(dc, uniq, U, (uint32_t)step, eps_global, eps_bias, eps_entity);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -21,7 +21,8 @@ template <int LINK, int MODE>
 __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& fa, const AdamDev& h,
                                               int32_t* __restrict__ adam_step, float kl_scale,
                                               bool with_kl, double kl_rows, int U) {
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;            // Adam steps applied so far
+    const uint32_t nstep = fa.noise_step ? (uint32_t)fa.noise_step[1] : 0u;   // noise index of the forward
     float* scalars = fa.scalars; float* stats = fa.stats;
     float alpha = scalars[VFMB_S_ALPHA], mu0 = scalars[VFMB_S_GB_MEAN], rho0 = scalars[VFMB_S_GB_SCALE];
     const float sig0 = link_fn<LINK>(rho0), ap = link_fn<LINK>(alpha);
@@ -29,9 +30,9 @@ __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& 
     // sum_s eps0_s * (sum_n dloss/dpred[s, n]); one sample: eps0 * sr
     double e0sr = 0.0;
     if (c.S > 1) {
-        for (int q = 0; q < c.S; ++q) e0sr += (double)global_eps(fa.eps_global, c, step, q) * (double)stats[VFMB_ST_RESID_S + q];
+        for (int q = 0; q < c.S; ++q) e0sr += (double)global_eps(fa.eps_global, c, nstep, q) * (double)stats[VFMB_ST_RESID_S + q];
     } else {
-        e0sr = (double)global_eps(fa.eps_global, c, step) * sr;
+        e0sr = (double)global_eps(fa.eps_global, c, nstep) * sr;
     }
     if (with_kl) {                                      // loss terms of the pre-update parameters
         const float kl = kl_std_normal(mu0, sig0) + (float)kl_rows;
@@ -67,6 +68,12 @@ __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& 
 
 #ifndef VFMB_ADAM_MINB
 #define VFMB_ADAM_MINB 4          // resident blocks/SM of the fused flavours (64 registers)
+#endif
+#ifndef VFMB_ADAM_SCHED
+#define VFMB_ADAM_SCHED 0         // 0: grid-stride chunks of CH rows; 1: equal contiguous row ranges per warp
+#endif
+#ifndef VFMB_ADAM_PF
+#define VFMB_ADAM_PF 1            // L2 prefetch of the chunk's parameter / moment rows up front
 #endif
 // bias row of one unique row: chain rule + KL gradient + Adam (or the dense-gradient store).
 // klw: in c_u, out c_u * KL(N(a, tau) || N(0,1)) of the pre-update row (when KLF)
@@ -110,6 +117,7 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
     const int U = meta[0];
     const int d = c.d;
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
+    const uint32_t nstep = fa.noise_step ? (uint32_t)fa.noise_step[1] : 0u;   // the forward's noise index
     const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
     const unsigned gmask = group_mask<LPR>();
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -120,21 +128,33 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
     if (MODE == VFMB_ADAM_TOUCHED) adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
     float facc = 0.f;                                     // sum_u c_u * KL_u over this thread's rows
 
+#if VFMB_ADAM_SCHED == 1
+    // equal contiguous ranges: warp w handles rows [w U / nwarps, (w+1) U / nwarps), so all warps
+    // finish together whatever U is
+    const int lo = (int)((int64_t)gwarp * U / nwarps), hi = (int)((int64_t)(gwarp + 1) * U / nwarps);
+    for (int base = lo; base < hi; base += CH) {
+        const int ul = base + lane;
+        const bool valid = lane < CH && ul < hi;
+#else
+    const int hi = U;
     for (int base = gwarp * CH; base < U; base += nwarps * CH) {
         // ---- lane-parallel: record, prefetch of the row's parameter / moment lines
         const int ul = base + lane;
         const bool valid = lane < CH && ul < U;
+#endif
         int rowid_l = 0;
         float cfac_l = 0.f, klw_l = 0.f;                  // KL weight c_u, and c_u * KL(bias) of the lane's row
         if (valid) {
             const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
             rowid_l = rec.x;
             const size_t eoff = (size_t)rowid_l * 2 * d;
+#if VFMB_ADAM_PF
             prefetch_row(entity + eoff, 8 * d);
             if (MODE == VFMB_ADAM_TOUCHED) {
                 prefetch_row(entity_m + eoff, 8 * d);
                 prefetch_row(entity_v + eoff, 8 * d);
             }
+#endif
             const float cq_l = __ldg(cq + ul);
             cfac_l = kl_scale * cq_l;
             klw_l = cq_l;
@@ -151,14 +171,14 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             const float cfac = bcast(cfac_l, sel);
             const int u = base + sel;
             float kl = 0.f;
-            if (u < U) {
+            if (u < hi) {
                 const size_t eoff = (size_t)rowid * 2 * d;
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     int k = (gl + i * LPR) * VEC;
                     if (k < d) {
                         Vec<VEC> e;                         // the noise k_stage used for this row
-                        if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step);
+                        if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, nstep);
                         else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
                         Vec<VEC> mu = ld_vec<VEC>(entity + eoff + k), rho = ld_vec<VEC>(entity + eoff + d + k);
                         Vec<VEC> m1, m2, v1, v2;
@@ -324,267 +344,6 @@ k_adam_rows_multi(DevCfg c, int u_stride, float* __restrict__ bias, float* __res
     }
 }
 
-#ifdef VFMB_WITH_BULK      // experimental bulk-copy variant (slower on 512-byte rows): -DVFMB_WITH_BULK + VFMB_ADAM_BULK=1
-// ------------------------------------------------------------------------------- k_adam_bulk
-// The same row update as k_adam_rows<ADAM_TOUCHED, FLAVOR 2>, fed by the bulk-copy engine instead
-// of register-staged loads.  k_adam_rows is latency-bound (80 % of the issue slots idle waiting on
-// L1TEX scoreboards, DRAM at 55 %): the bytes a warp keeps in flight are limited by its registers.
-// Here a CTA is a three-role pipeline over a ring of NS shared-memory stages:
-//   warp 0 (loader)   per stage: cp.async.bulk of the parameter / moment rows of RPS unique rows
-//                     (3 x 8d bytes each, gathered by row id) + one contiguous block of their
-//                     gradient rows (+ injected noise) -> smem, completion on an mbarrier;
-//   warps 2.. (consumers)  chain rule + KL + Adam in place in shared memory (LPR lanes per row);
-//   warp 1 (storer)   cp.async.bulk smem -> global of the updated rows, then frees the stage.
-// Bytes in flight per SM = NS x stage bytes x resident CTAs (~170 KB), independent of registers.
-// Rows are split into equal contiguous ranges per CTA (all CTAs finish together).
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-constexpr int kBulkConsumers = 4;                     // consumer warps per CTA
-constexpr int kBulkThreads = 32 * (2 + kBulkConsumers);
-constexpr int kBulkStages = 4;
-
-// floats of one stage: P | M | V rows (2d each), gradient rows, noise rows (d each), then row ids
-__host__ __device__ inline int bulk_stage_floats(int d, int rps) { return rps * 8 * d + ((rps + 3) / 4) * 4; }
-
-template <int LPR, int NV, int LINK>
-__global__ void __launch_bounds__(kBulkThreads, 3)
-k_adam_bulk(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
-            float* __restrict__ entity, float* __restrict__ entity_m, float* __restrict__ entity_v,
-            const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
-            const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
-            const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
-            AdamDev h, int32_t* __restrict__ adam_step, float kl_scale, FinalArgs fa) {
-    constexpr int VEC = 4, GPW = kWarp / LPR, RPS = kBulkConsumers * GPW, NS = kBulkStages;
-    extern __shared__ __align__(128) float s_ring[];
-    __shared__ __align__(8) uint64_t s_full[NS], s_done[NS], s_empty[NS];
-    const int U = meta[0];
-    const int d = c.d, rowf = 2 * c.d;
-    const int stage_f = bulk_stage_floats(d, RPS);
-    const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s2 = 0; s2 < NS; ++s2) { mbar_init(&s_full[s2], 1); mbar_init(&s_done[s2], kBulkConsumers); mbar_init(&s_empty[s2], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // equal contiguous ranges of unique rows per CTA, in whole stages
-    const int per = ((U + (int)gridDim.x - 1) / (int)gridDim.x + RPS - 1) / RPS * RPS;
-    const int lo = min(U, (int)blockIdx.x * per), hi = min(U, lo + per);
-    const int n_it = (hi - lo + RPS - 1) / RPS;
-    float facc = 0.f;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------ loader
-        int rowid_next = (lane < RPS && lo + lane < hi) ? __ldg(urec + 4 * (size_t)(lo + lane)) : 0;
-        for (int it = 0; it < n_it; ++it) {
-            const int st = it % NS, ph = (it / NS) & 1;
-            const int u0 = lo + it * RPS, nrows = min(RPS, hi - u0);
-            const int rowid = rowid_next;
-            const int un = u0 + RPS + lane;
-            rowid_next = (lane < RPS && un < hi) ? __ldg(urec + 4 * (size_t)un) : 0;
-            float* sp = s_ring + (size_t)st * stage_f;
-            mbar_wait(&s_empty[st], ph ^ 1);
-            if (lane < nrows) reinterpret_cast<int*>(sp + RPS * 8 * d)[lane] = rowid;
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t bytes = (uint32_t)nrows * (uint32_t)(3 * rowf + d + (eps_entity ? d : 0)) * 4u;
-                mbar_expect_tx(&s_full[st], bytes);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                bulk_load(sp + 3 * RPS * rowf, grow + (size_t)u0 * d, nrows * d * 4, &s_full[st]);
-                if (eps_entity)
-                    bulk_load(sp + 3 * RPS * rowf + RPS * d, eps_entity + (size_t)u0 * d, nrows * d * 4, &s_full[st]);
-            }
-            if (lane < nrows) {
-                const size_t eoff = (size_t)rowid * rowf;
-                bulk_load(sp + (0 * RPS + lane) * rowf, entity + eoff, rowf * 4, &s_full[st]);
-                bulk_load(sp + (1 * RPS + lane) * rowf, entity_m + eoff, rowf * 4, &s_full[st]);
-                bulk_load(sp + (2 * RPS + lane) * rowf, entity_v + eoff, rowf * 4, &s_full[st]);
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ storer
-        for (int it = 0; it < n_it; ++it) {
-            const int st = it % NS, ph = (it / NS) & 1;
-            const int u0 = lo + it * RPS, nrows = min(RPS, hi - u0);
-            float* sp = s_ring + (size_t)st * stage_f;
-            mbar_wait(&s_done[st], ph);
-            if (lane < nrows) {
-                const int rowid = reinterpret_cast<const int*>(sp + RPS * 8 * d)[lane];
-                const size_t eoff = (size_t)rowid * rowf;
-                bulk_store(entity + eoff, sp + (0 * RPS + lane) * rowf, rowf * 4);
-                bulk_store(entity_m + eoff, sp + (1 * RPS + lane) * rowf, rowf * 4);
-                bulk_store(entity_v + eoff, sp + (2 * RPS + lane) * rowf, rowf * 4);
-            }
-            bulk_commit();
-            bulk_wait_read<1>();                              // the stores of stage it-1 have left smem
-            __syncwarp();
-            if (lane == 0 && it > 0) mbar_arrive(&s_empty[(it - 1) % NS]);
-        }
-        bulk_wait_read<0>();
-        __syncwarp();
-        if (lane == 0 && n_it > 0) mbar_arrive(&s_empty[(n_it - 1) % NS]);
-        bulk_wait<0>();                                        // writes complete before the CTA retires
-    } else {
-        // ------------------------------------------------------------ consumers
-        const int cw = warp - 2, gl = lane % LPR, gidx = lane / LPR;
-        const unsigned gmask = group_mask<LPR>();
-        float step_size, inv_bc2;
-        adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
-        // scalars of the rows this warp handles: lane g < GPW owns row cw*GPW + g of every stage;
-        // fetched one stage ahead
-        auto fetch = [&](int it, int4& rec, float& cqv, float& gwv, float& ebv) {
-            const int u = lo + it * RPS + cw * GPW + lane;
-            rec = make_int4(0, 0, 0, 0); cqv = 0.f; gwv = 0.f; ebv = 0.f;
-            if (lane < GPW && it < n_it && u < hi) {
-                rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
-                cqv = __ldg(cq + u); gwv = __ldg(gws + u); ebv = __ldg(eps_bias + u);
-            }
-        };
-        int4 rec_n; float cq_n, gw_n, eb_n;
-        fetch(0, rec_n, cq_n, gw_n, eb_n);
-        for (int it = 0; it < n_it; ++it) {
-            const int st = it % NS, ph = (it / NS) & 1;
-            const int u0 = lo + it * RPS;
-            const int4 rec = rec_n; const float cq_l = cq_n, eb_l = eb_n; float gw_l = gw_n;
-            fetch(it + 1, rec_n, cq_n, gw_n, eb_n);
-            const int ul = u0 + cw * GPW + lane;
-            const bool valid = lane < GPW && ul < hi;
-            // bias row of this lane's row: in flight while the stage is awaited and processed
-            float2 ab = make_float2(0.f, 1.f), bm = make_float2(0.f, 0.f), bv = make_float2(0.f, 0.f);
-            if (valid) {
-                const size_t boff = (size_t)rec.x * 2;
-                ab = *reinterpret_cast<const float2*>(bias + boff);
-                bm = *reinterpret_cast<const float2*>(bias_m + boff);
-                bv = *reinterpret_cast<const float2*>(bias_v + boff);
-            }                                              // (cut rows: k_combine_cut finished them)
-            const float cfac_l = kl_scale * cq_l;
-            float* sp = s_ring + (size_t)st * stage_f;
-            mbar_wait(&s_full[st], ph);
-            // ---- wide work: this warp's GPW rows, LPR lanes per row
-            const int r = cw * GPW + gidx;                  // row slot in the stage
-            const int u = u0 + r;
-            const int rowid = bcast(rec.x, gidx);
-            const float cfac = bcast(cfac_l, gidx);
-            float kl = 0.f;
-            if (u < hi) {
-                float* pP = sp + (0 * RPS + r) * rowf;
-                float* pM = sp + (1 * RPS + r) * rowf;
-                float* pV = sp + (2 * RPS + r) * rowf;
-                const float* pG = sp + 3 * RPS * rowf + r * d;
-                const float* pE = pG + RPS * d;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-                        Vec<VEC> mu = ld_vec<VEC>(pP + k), rho = ld_vec<VEC>(pP + d + k);
-                        Vec<VEC> m1 = ld_vec<VEC>(pM + k), m2 = ld_vec<VEC>(pM + d + k);
-                        Vec<VEC> v1 = ld_vec<VEC>(pV + k), v2 = ld_vec<VEC>(pV + d + k);
-                        const Vec<VEC> g = ld_vec<VEC>(pG + k);
-                        Vec<VEC> e;
-                        if (eps_entity) e = ld_vec<VEC>(pE + k);
-                        else e = entity_eps<VEC>(nullptr, c, u, rowid * c.row_stride + c.row_offset, k, step);
-                        float quad = 0.f, prodv = 1.f;
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            const float sig = link_fn<LINK>(rho.v[j]);
-                            const float gj = g.v[j];
-                            const float gmu = fmaf(cfac, mu.v[j], gj);
-                            const float grho = link_grad<LINK>(rho.v[j]) * fmaf(gj, e.v[j], cfac * (sig - fast_rcp(sig)));
-                            const float vr = sig * sig;
-                            quad += vr + mu.v[j] * mu.v[j] - 1.f;
-                            prodv *= vr;
-                            adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu, h, step_size, inv_bc2);
-                            adam_elem(rho.v[j], m2.v[j], v2.v[j], grho, h, step_size, inv_bc2);
-                        }
-                        // KL of the pre-update row (quad / prodv were formed before adam_elem touched
-                        // element j); one logarithm per lane as in k_stage
-                        float lg = __logf(prodv);
-                        if (!(prodv > 1e-30f && prodv < 1e30f)) {       // tiny / huge scales: no product trick
-                            const Vec<VEC> rho0 = ld_vec<VEC>(pP + d + k);   // still the old row in smem
-                            lg = 0.f;
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho0.v[j]); lg += logf(sg * sg); }
-                        }
-                        kl += 0.5f * (quad - lg);
-                        st_vec<VEC>(pP + k, mu); st_vec<VEC>(pP + d + k, rho);
-                        st_vec<VEC>(pM + k, m1); st_vec<VEC>(pM + d + k, m2);
-                        st_vec<VEC>(pV + k, v1); st_vec<VEC>(pV + d + k, v2);
-                    }
-                }
-                kl = group_sum<LPR>(kl, gmask);
-            }
-            fence_async_smem();                             // generic-proxy writes -> visible to the bulk store
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_done[st]);
-            // ---- lane-parallel: bias row, KL of the row
-            float klrow = 0.f;
-#pragma unroll
-            for (int g = 0; g < GPW; ++g) {
-                const float kv = __shfl_sync(0xffffffffu, kl, g * LPR);
-                if (lane == g) klrow = kv;
-            }
-            if (valid) {
-                const size_t boff = (size_t)rec.x * 2;
-                const float tau = link_fn<LINK>(ab.y);
-                facc = fmaf(cq_l, klrow + kl_std_normal(ab.x, tau), facc);
-                const float ga = fmaf(cfac_l, ab.x, gw_l);
-                const float gb = link_grad<LINK>(ab.y) * fmaf(gw_l, eb_l, cfac_l * (tau - fast_rcp(tau)));
-                adam_elem(ab.x, bm.x, bv.x, ga, h, step_size, inv_bc2);
-                adam_elem(ab.y, bm.y, bv.y, gb, h, step_size, inv_bc2);
-                *reinterpret_cast<float2*>(bias + boff) = ab;
-                *reinterpret_cast<float2*>(bias_m + boff) = bm;
-                *reinterpret_cast<float2*>(bias_v + boff) = bv;
-            }
-        }
-    }
-    // the block that finishes last owns the scalar parameters (see k_adam_rows)
-    double acc[1] = {(double)facc};
-    if (block_partials<1>(acc, fa.partials, fa.counter)) {
-        double tot[1] = {0.0};
-        final_sums<1>(fa.partials, tot);
-        if (threadIdx.x == 0) {
-            final_scalars<LINK, VFMB_ADAM_TOUCHED>(c, fa, h, adam_step, kl_scale, true, tot[0], U);
-            *fa.counter = 0;
-        }
-    }
-}
-
-#endif  // VFMB_WITH_BULK
-
 // ------------------------------------------------------------------------------- dense Adam
 __global__ void __launch_bounds__(256)
 k_adam_dense(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
@@ -636,53 +395,11 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
     fa.eps_global = io->eps_global; fa.grad_scalars = io->grad_scalars; fa.partials = io->partials;
     fa.counter = io->counters ? io->counters + 2 : nullptr;
     fa.gslot = io->partials ? (const float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off : nullptr;
-    fa.likelihood = cfg->likelihood;
-#ifdef VFMB_WITH_BULK
-    // measured on ml20m: 60.7 us vs 53.9 us for k_adam_rows -- 512-byte rows are too small for the
-    // bulk-copy engine (per-copy overhead); kept selectable for wide rows (VFMB_ADAM_BULK=1)
-    static const bool use_bulk = [] { const char* e = getenv("VFMB_ADAM_BULK"); return e && atoi(e) != 0; }();
-    if (use_bulk && flavor == 2 && mode == VFMB_ADAM_TOUCHED && L.vec == 4) {
-        // bulk-copy pipeline (k_adam_bulk): same arithmetic, rows staged through shared memory
-        cudaEvent_t ev0, ev1;
-        profile_events(&ev0, &ev1);
-        if (ev0 && ev1) cudaEventRecord(ev0, stream);
-#define LAUNCH_BULK(LPR_, NV_, LINK)                                                                     \
-        do {                                                                                             \
-            auto kern = k_adam_bulk<LPR_, NV_, LINK>;                                                    \
-            const int rps = kBulkConsumers * (32 / LPR_);                                                \
-            const size_t smem = (size_t)kBulkStages * bulk_stage_floats(cfg->d, rps) * sizeof(float);    \
-            static int blocks = 0;                                                                       \
-            static size_t smem_set = 0;                                                                  \
-            if (smem_set != smem) {                                                                      \
-                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                int per_sm = 0;                                                                          \
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBulkThreads, smem)); \
-                blocks = (per_sm < 1 ? 1 : per_sm) * kNumSMs;                                            \
-                smem_set = smem;                                                                         \
-            }                                                                                            \
-            int64_t need = (cap.u_cap + rps - 1) / rps;                                                  \
-            int grid = (int)(need < blocks ? (need < 1 ? 1 : need) : blocks);                            \
-            kern<<<grid, kBulkThreads, smem, stream>>>(dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, \
-                tab->entity_m, tab->entity_v, plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow,    \
-                io->gws, h, tab->adam_step, kl_grad_scale, fa);                                          \
-        } while (0)
-#define LAUNCH_BULK_L(LPR_, NV_) do { if (cfg->link == VFMB_LINK_ABS) LAUNCH_BULK(LPR_, NV_, 0); else LAUNCH_BULK(LPR_, NV_, 1); } while (0)
-        if (L.lpr == 4) LAUNCH_BULK_L(4, 1);
-        else if (L.lpr == 8) LAUNCH_BULK_L(8, 1);
-        else if (L.lpr == 16) LAUNCH_BULK_L(16, 1);
-        else if (L.nv == 1) LAUNCH_BULK_L(32, 1);
-        else LAUNCH_BULK_L(32, 2);
-#undef LAUNCH_BULK_L
-#undef LAUNCH_BULK
-        if (ev0 && ev1) cudaEventRecord(ev1, stream);
-        CUDA_TRY(cudaGetLastError());
-        return 0;
-    }
-#endif  // VFMB_WITH_BULK
+    fa.likelihood = cfg->likelihood; fa.noise_step = tab->noise_step;
     // the HBM-bound kernel keeps its full wave even next to the plan (measured: 113.8 vs 116.2 us/step)
-    static const bool adam_reserve = [] { const char* e = getenv("VFMB_RESERVE_ADAM"); return e && atoi(e) != 0; }();
+    const bool adam_reserve = tuning().adam_reserve != 0;
 #define LAUNCH_ADAM(LINK, MODE, FLAVOR)                                                                  \
-    k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR>, cap.u_cap, ch, 0, adam_reserve), 256, 0, stream>>>( \
+    k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR>, cap.u_cap, ch, 0, adam_reserve), 256, 0, counted(stream)>>>( \
         dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,              \
         plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, h, tab->adam_step,              \
         kl_grad_scale, io->grad_bias, io->grad_entity, fa)
@@ -739,11 +456,11 @@ int launch_adam_multi(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb
     FinalArgs fa{};
     fa.scalars = tab->scalars; fa.sm = tab->scalars_m; fa.sv = tab->scalars_v; fa.stats = io->stats;
     fa.eps_global = io->eps_global; fa.grad_scalars = io->grad_scalars; fa.partials = io->partials;
-    fa.counter = io->counters + 2; fa.gslot = nullptr; fa.likelihood = cfg->likelihood;
+    fa.counter = io->counters + 2; fa.gslot = nullptr; fa.likelihood = cfg->likelihood; fa.noise_step = tab->noise_step;
     int grid = (int)((cap.u_cap + 8 * (32 / L.lpr) - 1) / (8 * (32 / L.lpr)));
     if (grid > kGridCap) grid = kGridCap;
 #define LAUNCH_AM(LINK, MODE)                                                                            \
-    k_adam_rows_multi<VEC, LPR, NV, LINK, MODE><<<grid, 256, 0, stream>>>(                               \
+    k_adam_rows_multi<VEC, LPR, NV, LINK, MODE><<<grid, 256, 0, counted(stream)>>>(                               \
         dc, (int)cap.u_cap, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v, \
         plan->urec, plan->meta, eps_b, eps_e, eps_stride, io->cq, io->grow, io->gws, h, tab->adam_step,  \
         kl_grad_scale, io->grad_bias, io->grad_entity, fa)
@@ -766,14 +483,14 @@ extern "C" int vfmb_adam_dense(float* p, float* m, float* v, const float* g, int
     AdamDev h = make_adam(adam);
     int64_t grid = (n + 255) / 256;
     if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
-    k_adam_dense<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(p, m, v, g, n, h, adam_step);
+    k_adam_dense<<<(int)grid, 256, 0, counted((cudaStream_t)stream_)>>>(p, m, v, g, n, h, adam_step);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 extern "C" int vfmb_adam_step_advance(int32_t* adam_step, vfmb_stream stream_) {
     if (!adam_step) return set_error(VFMB_EINVAL, "vfmb_adam_step_advance: null");
-    k_step_advance<<<1, 1, 0, (cudaStream_t)stream_>>>(adam_step);
+    k_step_advance<<<1, 1, 0, counted((cudaStream_t)stream_)>>>(adam_step);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

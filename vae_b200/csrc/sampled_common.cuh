@@ -3,8 +3,6 @@
 #pragma once
 #include "step_common.cuh"
 
-#include <cstdlib>
-
 namespace vfmb {
 
 constexpr int kMaxSamples = 8;      // variational samples per step (vfm-torch.py:19) the kernels take
@@ -40,10 +38,25 @@ __device__ __forceinline__ float global_eps(const float* __restrict__ eps_global
     return n4[0];
 }
 
+// End of a sampled forward (thread 0 of the block that finishes the scoring kernel last -- every
+// block has read the counter by then): record the noise index this forward drew with, advance the
+// counter (see vfmb_tables.noise_step), and poison the loss when the plan saw a row id outside the
+// table (the reference raises IndexError from nn.Embedding; here the id was remapped to row 0 and
+// plan.meta[2] set -- a NaN loss is the device-side signal that needs no host synchronisation).
+__device__ __forceinline__ void forward_done(int32_t* noise_step, uint32_t step, const int32_t* __restrict__ meta,
+                                             float* __restrict__ stats) {
+    if (noise_step) { noise_step[1] = (int32_t)step; noise_step[0] = (int32_t)step + 1; }
+    if (meta && meta[2] != 0) {
+        stats[VFMB_ST_LOSS] = __int_as_float(0x7fc00000);
+        stats[VFMB_ST_NLL_MEAN] = __int_as_float(0x7fc00000);
+    }
+}
+
 // arguments of the scalar-parameter update folded into the row kernels (final_scalars)
 struct FinalArgs {
     float* scalars; float* sm; float* sv; float* stats; const float* eps_global;
     float* grad_scalars; double* partials; int32_t* counter; const float* gslot;
+    const int32_t* noise_step;          // [1] = noise index of the forward this backward belongs to
     int likelihood;
 };
 

@@ -283,10 +283,10 @@ extern "C" int vfmb_shard_bucket(const vfmb_plan* plan, int32_t u_cap, int32_t P
     int rc = make_peers(peers, P, rank, &pe);
     if (rc) return rc;
     const int nblk = (u_cap + kBktTile - 1) / kBktTile;
-    if (pe.n) k_fill_peers<<<32, 256, 0, stream>>>(pe, CAP * 2, -1);                        // -1: empty slot
+    if (pe.n) k_fill_peers<<<32, 256, 0, counted(stream)>>>(pe, CAP * 2, -1);                        // -1: empty slot
     else CUDA_TRY(cudaMemsetAsync(send, 0xFF, (size_t)P * CAP * 2 * sizeof(int32_t), stream));
-    k_bucket_count<<<nblk, kBkt, 0, stream>>>(plan->uniq, plan->meta, P, (int32_t*)workspace);
-    k_bucket_place<<<nblk, kBkt, 0, stream>>>(plan->uniq, plan->urec, plan->meta, u_cap, P, CAP,
+    k_bucket_count<<<nblk, kBkt, 0, counted(stream)>>>(plan->uniq, plan->meta, P, (int32_t*)workspace);
+    k_bucket_place<<<nblk, kBkt, 0, counted(stream)>>>(plan->uniq, plan->urec, plan->meta, u_cap, P, CAP,
                                               (const int32_t*)workspace, send, dest, overflow, pe);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -298,7 +298,7 @@ extern "C" int vfmb_shard_put_small(const float* vec, int32_t n, int32_t pitch, 
     int rc = make_peers(peers, P, rank, &pe);
     if (rc) return rc;
     if (!vec || !peers || n < 1 || n > pitch) return set_error(VFMB_EINVAL, "vfmb_shard_put_small: bad argument");
-    k_put_small<<<P, 32, 0, (cudaStream_t)stream_>>>(pe, vec, n, pitch);
+    k_put_small<<<P, 32, 0, counted((cudaStream_t)stream_)>>>(pe, vec, n, pitch);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -306,7 +306,7 @@ extern "C" int vfmb_shard_put_small(const float* vec, int32_t n, int32_t pitch, 
 extern "C" int vfmb_shard_sum_small(const float* slots, int32_t P, int32_t n, int32_t pitch, float* out,
                                     vfmb_stream stream_) {
     if (!slots || !out || P < 1 || n < 1 || n > pitch) return set_error(VFMB_EINVAL, "vfmb_shard_sum_small: bad argument");
-    k_sum_small<<<1, 32, 0, (cudaStream_t)stream_>>>(slots, P, n, pitch, out);
+    k_sum_small<<<1, 32, 0, counted((cudaStream_t)stream_)>>>(slots, P, n, pitch, out);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -314,7 +314,7 @@ extern "C" int vfmb_shard_sum_small(const float* slots, int32_t P, int32_t n, in
 extern "C" int vfmb_shard_owner_ids(const int32_t* recv, int32_t M, int32_t P, int32_t R_loc, int64_t* loc,
                                     int32_t* recv_copy, vfmb_stream stream_) {
     if (!recv || !loc || M < 1 || P < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_ids: bad argument");
-    k_owner_ids<<<(M + 255) / 256 > 2 * kNumSMs ? 2 * kNumSMs : (M + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(
+    k_owner_ids<<<(M + 255) / 256 > 2 * kNumSMs ? 2 * kNumSMs : (M + 255) / 256, 256, 0, counted((cudaStream_t)stream_)>>>(
         recv, M, P, R_loc, loc, recv_copy);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -326,13 +326,13 @@ extern "C" int vfmb_shard_owner_pack(const vfmb_plan* plan_o, const int32_t* rec
     if (!plan_o || !recv || M < 1 || CAP < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_pack: bad argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (counts_only) {
-        k_owner_counts<<<2 * kNumSMs, 256, 0, stream>>>(recv, plan_o->occ, plan_o->meta, plan_o->urec);
+        k_owner_counts<<<2 * kNumSMs, 256, 0, counted(stream)>>>(recv, plan_o->occ, plan_o->meta, plan_o->urec);
     } else {
         if (!vs || !ws || (!reply && !peers) || d < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_pack: bad argument");
         Peers pe;
         int rc = make_peers(peers, M / CAP, rank, &pe);
         if (rc) return rc;
-        k_pack_rows<<<warp_grid(M), 256, 0, stream>>>(vs, ws, plan_o->inverse, recv, M, CAP, d, reply, pe);
+        k_pack_rows<<<warp_grid(M), 256, 0, counted(stream)>>>(vs, ws, plan_o->inverse, recv, M, CAP, d, reply, pe);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -341,7 +341,7 @@ extern "C" int vfmb_shard_owner_pack(const vfmb_plan* plan_o, const int32_t* rec
 extern "C" int vfmb_shard_unpack_rows(const vfmb_plan* plan_l, const float* recv_rows, const int32_t* dest,
                                       int32_t u_cap, int32_t M, int32_t d, float* vs, float* ws, vfmb_stream stream_) {
     if (!plan_l || !recv_rows || !dest || !vs || !ws) return set_error(VFMB_EINVAL, "vfmb_shard_unpack_rows: bad argument");
-    k_unpack_rows<<<warp_grid(u_cap), 256, 0, (cudaStream_t)stream_>>>(recv_rows, dest, plan_l->meta, M, d, vs, ws);
+    k_unpack_rows<<<warp_grid(u_cap), 256, 0, counted((cudaStream_t)stream_)>>>(recv_rows, dest, plan_l->meta, M, d, vs, ws);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -358,7 +358,7 @@ extern "C" int vfmb_shard_pack_grads(const vfmb_plan* plan_l, const float* grow,
     int rc = make_peers(peers, M / CAP, rank, &pe);
     if (rc) return rc;
     if (!pe.n) CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)M * (d + 1) * sizeof(float), stream));
-    k_pack_grads<<<warp_grid(u_cap), 256, 0, stream>>>(grow, gws, dest, plan_l->meta, M, d, out, stats_local, stats_owner,
+    k_pack_grads<<<warp_grid(u_cap), 256, 0, counted(stream)>>>(grow, gws, dest, plan_l->meta, M, d, out, stats_local, stats_owner,
                                                        n_local, tail, tail_idx[0], tail_idx[1], tail_idx[2], tail_idx[3], n_tail,
                                                        CAP, pe);
     CUDA_TRY(cudaGetLastError());
@@ -368,7 +368,7 @@ extern "C" int vfmb_shard_pack_grads(const vfmb_plan* plan_l, const float* grow,
 extern "C" int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, const int32_t* recv_ids, int32_t M,
                                        int32_t d, float* table, float* rsorted, vfmb_stream stream_) {
     if (!plan_o || !recv_g || !table || !rsorted) return set_error(VFMB_EINVAL, "vfmb_shard_unpack_grads: bad argument");
-    k_unpack_grads<<<warp_grid(M), 256, 0, (cudaStream_t)stream_>>>(recv_g, plan_o->occ, recv_ids, M, d, table, rsorted);
+    k_unpack_grads<<<warp_grid(M), 256, 0, counted((cudaStream_t)stream_)>>>(recv_g, plan_o->occ, recv_ids, M, d, table, rsorted);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

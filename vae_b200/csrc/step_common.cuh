@@ -3,8 +3,6 @@
 #include "common.cuh"
 #include "internal.h"
 
-#include <cstdlib>
-
 namespace vfmb {
 
 constexpr int kGridCap = 2048;      // most blocks a step kernel is launched with (block partials are sized for it)
@@ -393,9 +391,8 @@ static inline ScratchMap scratch_map(int B, int F, int d, int64_t u_cap) {
 }
 
 // Grid of a (grid-stride) step kernel: one persistent resident wave (blocks/SM from the occupancy
-// calculator).  VFMB_PERSISTENT=0 launches one warp per `per_warp` units instead (as many blocks as
-// the work needs, capped at kGridCap); measured 4 % slower on the ml20m step (more block
-// prologues, no gain from hardware load balancing).
+// calculator).  (One warp per `per_warp` units -- as many blocks as the work needs -- measured 4 %
+// slower on the ml20m step: more block prologues, no gain from hardware load balancing.)
 template <typename K>
 static inline int resident_blocks(K kernel, int block, size_t smem) {
     static int cached = 0;                                  // one instance per kernel type
@@ -409,13 +406,12 @@ static inline int resident_blocks(K kernel, int block, size_t smem) {
 }
 template <typename K>
 static inline int grid_resident(K kernel, int64_t units, int per_warp, size_t smem = 0, bool may_reserve = true) {
-    static const bool persistent = [] { const char* e = getenv("VFMB_PERSISTENT"); return !e || atoi(e) != 0; }();
     int64_t warps = (units + per_warp - 1) / per_warp;
     int64_t g = (warps + 7) / 8;
     // leave `reserve` block slots per SM free: room for the plan kernels running concurrently
     const int reserve = may_reserve ? grid_reserve() : 0;
-    int cap = persistent ? resident_blocks(kernel, 256, smem) : kGridCap;
-    if (persistent && reserve > 0 && cap / kNumSMs > reserve + 1) cap -= reserve * kNumSMs;
+    int cap = resident_blocks(kernel, 256, smem);
+    if (reserve > 0 && cap / kNumSMs > reserve + 1) cap -= reserve * kNumSMs;
     if (g < 1) g = 1;
     if (g > cap) g = cap;
     return (int)g;

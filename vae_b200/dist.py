@@ -316,6 +316,7 @@ class ShardedSampled:
         self.scalars = scal.to(dev)
         self.scalars_m, self.scalars_v = z(self.scalars), z(self.scalars)
         self.adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.noise_step = torch.zeros(2, dtype=torch.int32, device=dev)    # see vfmb_tables.noise_step
         # ---- requester side (local slice, global ids)
         mk = lambda B, F, R, n_tr, stride, off: self._cfg(B, F, R, n_tr, bounds, sizes, seed, stride, off)
         self.cfg_l = mk(self.B, self.F, self.R, self.n_train / P, 0, 0)
@@ -365,7 +366,8 @@ class ShardedSampled:
     def _tables(self) -> L.Tables:
         return L.Tables(L.ptr(self.bias), L.ptr(self.bias_m), L.ptr(self.bias_v), L.ptr(self.entity),
                         L.ptr(self.entity_m), L.ptr(self.entity_v), L.ptr(self.train_counts_loc),
-                        L.ptr(self.scalars), L.ptr(self.scalars_m), L.ptr(self.scalars_v), L.ptr(self.adam_step))
+                        L.ptr(self.scalars), L.ptr(self.scalars_m), L.ptr(self.scalars_v), L.ptr(self.adam_step),
+                        L.ptr(self.noise_step))
 
     def _use_slot(self, k: int) -> None:
         for key in self._slot_keys:                           # save what the phases assigned, switch

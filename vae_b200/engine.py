@@ -178,6 +178,10 @@ class GraphedLoop:
         self.xs = [torch.zeros((B, F), dtype=torch.int64, device=self.device) for _ in range(D)]
         self.ys = [torch.zeros(B, dtype=torch.float32, device=self.device) for _ in range(D)]
         self.plans = [BatchPlan(B, F, model.R, self.device) for _ in range(D)]
+        # outputs per staging slot (predictions, logits, loss terms): step i+1 writes another slot, so a
+        # caller can copy step i's outputs to the host on its own stream while step i+1 runs
+        S = int(getattr(model, "S", 1))
+        self.outs = [SlotOutputs(S, B, self.device) for _ in range(D)]
         # high priority: the plan kernels are tiny and latency-bound; they should slip in as soon
         # as blocks of the (machine-filling) step kernels retire
         self.side = torch.cuda.Stream(device=self.device, priority=-1)
@@ -200,6 +204,7 @@ class GraphedLoop:
         # the step kernels are captured one block slot per SM short of a full wave, so that the
         # plan's blocks (side branch) are placed immediately instead of displacing step blocks
         L.check(L.lib().vfmb_set_grid_reserve(1), "vfmb_set_grid_reserve")
+        n0 = int(L.lib().vfmb_launch_count())
         try:
             for s in range(D):
                 nxt = (s + 1) % D
@@ -209,11 +214,13 @@ class GraphedLoop:
                     self.side.wait_stream(cur)                   # fork
                     with torch.cuda.stream(self.side):
                         self.plans[nxt].build(self.cfg, self.xs[nxt], model.train_counts)
-                    step_fn(self.plans[s], self.ys[s])           # main branch
+                    step_fn(self.plans[s], self.ys[s], self.outs[s])   # main branch
                     cur.wait_stream(self.side)                   # join
                 self.graphs.append(g)
         finally:
             L.lib().vfmb_set_grid_reserve(0)
+        # own kernel nodes per captured graph (the library counts every launch it makes)
+        self.launches_per_graph = (int(L.lib().vfmb_launch_count()) - n0) // D
 
     def stage(self, x: torch.Tensor, y: torch.Tensor) -> None:
         """Copy a batch (device or pinned host) into the next free staging slot."""
@@ -255,7 +262,18 @@ class GraphedLoop:
         self.done[s].record(cur)
         self.head = (s + 1) % self.depth
         self.n_staged -= 1
-        return StepResult(self.model._buf, self.B)
+        self.last_slot = s
+        return StepResult(self.outs[s], self.B)
+
+
+class SlotOutputs:
+    """Outputs of the step captured in one graph of a GraphedLoop (duck-types StepBuffers for StepResult)."""
+
+    def __init__(self, S: int, B: int, device):
+        self.S = S
+        self.pred = _f32(S * B, device)
+        self.mean = _f32(S * B, device)
+        self.stats = torch.zeros(L.STATS, dtype=torch.float32, device=device)
 
 
 class StepBuffers:

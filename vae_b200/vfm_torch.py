@@ -132,6 +132,10 @@ class CF(nn.Module):
         self.register_buffer("entity_v", z(self.entity_params.weight), persistent=False)
         self._scalars_m, self._scalars_v = z(self._scalars), z(self._scalars)
         self.adam_step = torch.zeros(1, dtype=torch.int32, device=device)
+        # Philox step word: [0] = index the next forward draws with, [1] = index of the last forward.
+        # Separate from adam_step: the drop-in path (model(x) -> loss.backward() -> torch.optim.Adam)
+        # never advances adam_step, and evaluation forwards draw fresh noise too (vfm-torch.py:402-403)
+        self.noise_step = torch.zeros(2, dtype=torch.int32, device=device)
 
         # posterior-mean snapshots (vfm-torch.py:155-160, 179-185)
         self.saved_global_biases, self.saved_mean_biases, self.saved_mean_entities = [], [], []
@@ -193,7 +197,7 @@ class CF(nn.Module):
         return L.Tables(L.ptr(self.bias_params.weight), L.ptr(self.bias_m), L.ptr(self.bias_v),
                         L.ptr(self.entity_params.weight), L.ptr(self.entity_m), L.ptr(self.entity_v),
                         L.ptr(self.train_counts), L.ptr(self._scalars), L.ptr(self._scalars_m),
-                        L.ptr(self._scalars_v), L.ptr(self.adam_step))
+                        L.ptr(self._scalars_v), L.ptr(self.adam_step), L.ptr(self.noise_step))
 
     def _prep_noise(self, noise):
         if noise is None:
@@ -362,9 +366,10 @@ class CF(nn.Module):
         self._ensure(B)
         self._sync_scalars()
 
-        def step_fn(plan, y):
+        def step_fn(plan, y, outs):
             self._cfg, self._plan = self._config(B), plan
             io = self._buf.io(y=y)
+            io.pred, io.mean, io.stats = L.ptr(outs.pred), L.ptr(outs.mean), L.ptr(outs.stats)
             self._graph_io = getattr(self, "_graph_io", []) + [io]      # keep the structs alive
             L.check(L.lib().vfmb_sampled_step(C.byref(self._cfg), C.byref(self._tables()), C.byref(plan.struct),
                                               C.byref(io), C.byref(self.adam), current_stream(self.device)),
@@ -436,10 +441,11 @@ class CF(nn.Module):
 
     @torch.no_grad()
     def philox_noise(self, uniq: torch.Tensor, step: Optional[int] = None):
-        """The N(0,1) draws the Philox path uses at ``step`` for the given unique rows."""
+        """The N(0,1) draws the Philox path uses at noise index ``step`` for the given unique rows
+        (default: the index the NEXT forward will draw with; ``noise_step[1]`` is the last one used)."""
         uniq = uniq.to(self.device, torch.int32).contiguous()
         U = int(uniq.numel())
-        step = int(self.adam_step.item()) if step is None else int(step)
+        step = int(self.noise_step[0].item()) if step is None else int(step)
         S = self.S
         e0 = torch.empty(S, device=self.device)
         eb = torch.empty(S * U, device=self.device)
