@@ -167,8 +167,8 @@ def run_ours(args):
                 out = dp.step(*batch(i))
             return out
         if args.plan == "graph":                             # CUDA-graph replay of the same pipelined loop:
-            for i in range(lo, hi):                          # run batch i, stage batch i+1 (its plan is built
-                out = loop.step(*batch(i + 1))               # on the side branch of the same graph)
+            for i in range(lo, hi):                          # run batch i (the plan of batch i+1 is built on the
+                out = loop.step(*batch(i + 2))               # side branch of the same graph), stage batch i+2
             return out
         if args.plan == "prefetch":
             model.prefetch_plan(batch(lo)[0])
@@ -183,9 +183,11 @@ def run_ours(args):
         return out
 
     from vae_b200 import _lib as L
-    loop = model.graphed_loop(B) if (args.plan == "graph" and dp is None) else None
+    # three staging slots: the copy of batch i+2 into its slot runs on a copy stream, off the step's stream
+    loop = model.graphed_loop(B, depth=3) if (args.plan == "graph" and dp is None) else None
     if loop is not None:
         loop.start(*batch(0))                                # the pipeline runs on from here: warm-up, then timed
+        loop.stage(*batch(1))
     static_plans = {}
     if args.plan == "cached":                               # never-shuffled loader: plans recur every epoch
         for i in range(W, W + K):

@@ -16,8 +16,10 @@ reference (``oracle/vfm_port.py``) for the F = 2 cases.  Two consecutive steps a
           (``k_score`` + ``k_gather`` vs the fused ``k_gather_score``) -- replayed in the oracle from
           the GPU's exact state (p, m, v, t = 1) and the exported Philox draws.
 
-Tolerances (north_star: fp32 within 1e-5 relative): predictions / ELBO / KL rtol 1e-5; gradients in
-max-norm 3e-6 against fp64 maths; updated parameters elementwise |d| <= 1e-5 |p| + 1e-4 lr, where
+Tolerances (north_star: fp32 within 1e-5 relative): ELBO / KL rtol 1e-5; predictions rtol 1e-5 plus an
+absolute floor of 1e-6 x rms(pred) (a prediction is a d-term dot product of O(1) factors that may cancel
+to ~0: fp32 rounding of the terms, ~6e-8 x sum |terms|, is all that is left of it there -- the fp32
+reference restatement is off by the same amount against fp64); gradients in max-norm 3e-6 against fp64 maths; updated parameters elementwise |d| <= 1e-5 |p| + 1e-4 lr, where
 every element outside that bound must be PROVABLY ill-conditioned: Adam maps g to ~ lr * g/(|g|+eps),
 so an element whose fp64 gradient is below 1e-4 of its row's largest turns fp32 rounding of g into an
 O(lr) change (the reference's own 1-thread vs N-thread runs differ on exactly those elements; the test
@@ -101,6 +103,11 @@ def _param_check(got, want, g64, lr, label, rec):
     assert bad.mean() <= 2e-5, (label, rec[label])
 
 
+def _pred_close(got, want, msg=""):
+    want = np.asarray(want, dtype=np.float64)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6 * float(np.sqrt(np.mean(want ** 2))), err_msg=msg)
+
+
 def _record(rec):
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
@@ -138,7 +145,7 @@ def test_two_steps_at_benchmark_shape_match_oracle(name):
         assert n_hot > 0, "the hot-row branch (rows spanning > 32 backward tiles) must be exercised"
     assert np.array_equal(plan.as_unique()[0].cpu().numpy(), ex["plan"]["uniq"])
     np.testing.assert_allclose(gr["loss"].item(), ex["loss"], rtol=1e-5)
-    np.testing.assert_allclose(gr["pred"].cpu().numpy(), ex["mean"].squeeze(), rtol=1e-5, atol=2e-6)
+    _pred_close(gr["pred"].cpu().numpy(), ex["mean"].squeeze())
     ge, gb = gr["entity_params.weight"].cpu().numpy(), gr["bias_params.weight"].cpu().numpy()
     rec["grad_entity_vs_fp64"] = gu.rel_err(ge, ex["grads"]["entity"])
     rec["grad_bias_vs_fp64"] = gu.rel_err(gb, ex["grads"]["bias"])
@@ -167,7 +174,7 @@ def test_two_steps_at_benchmark_shape_match_oracle(name):
         rec["grad_entity_vs_port"] = gu.rel_err(ge, pn["grads"]["entity_params.weight"].numpy())
         assert rec["grad_entity_vs_port"] < max(3e-5, 2 * rec["reference_self_diff_grad"]), rec
         np.testing.assert_allclose(gr["loss"].item(), pn["loss"].item(), rtol=1e-5)
-        np.testing.assert_allclose(gr["pred"].cpu().numpy(), pn["pred"].numpy(), rtol=1e-5, atol=2e-6)
+        _pred_close(gr["pred"].cpu().numpy(), pn["pred"].numpy(), "vs port")
 
     before = {k: v.detach().clone() for k, v in m.state_dict().items()}
     out = m.fused_step(xd0, yd0, noise=nd)
@@ -205,7 +212,7 @@ def test_two_steps_at_benchmark_shape_match_oracle(name):
         tag = f"step2.reserve{reserve}"
         np.testing.assert_allclose(out2["loss"].item(), ex2["loss"], rtol=1e-5, err_msg=tag)
         np.testing.assert_allclose(out2["kl"].item(), ex2["kl"], rtol=1e-5, err_msg=tag)
-        np.testing.assert_allclose(out2["pred"].cpu().numpy(), ex2["mean"].squeeze(), rtol=1e-5, atol=2e-6, err_msg=tag)
+        _pred_close(out2["pred"].cpu().numpy(), ex2["mean"].squeeze(), tag)
         for key, gk, mk, vk in (("entity_params.weight", "entity", "entity_m", "entity_v"),
                                 ("bias_params.weight", "bias", "bias_m", "bias_v")):
             want = _adam_rows(sd1[key][uniq1], ex2["grads"][gk][uniq1], mom[mk][uniq1], mom[vk][uniq1], 2, lr)

@@ -1,14 +1,15 @@
 // Closed-form Gaussian VFM step (vfm-tomasrch.py:323-453 forward, :569-594 loss/backward/Adam) and
 // the plan-free posterior-mean prediction (vfm-torch.py:248-259, vfm-tomasrch.py:342-348).
 //
-// Same skeleton as the sampled step (plan -> stage -> score -> gather -> combine -> Adam), no RNG:
+// Same skeleton as the sampled step (plan -> stage -> score -> gather -> Adam), no RNG:
 //   k_cstage   per unique row: stage [mean | raw scale^2] and the bias pair in L2-resident scratch,
 //              KL against the learnable per-group priors, per-group sums feeding the prior-
 //              parameter gradients.  Blocks are assigned to (group, row range) from the plan's
 //              class offsets, so a block only ever sees one group's prior.   (:262-313, 363-367)
 //   k_cscore   per sample: y_bar, T_n, partial_loss, product-form prediction.        (:342-348, 369-449)
 //   k_cgather  position-tiled segmented sums A = sum delta*mu_partner, Bq = sum rho_partner^2,
-//              C = sum mu_partner^2 per unique row (deterministic, no atomics).
+//              C = sum mu_partner^2 per unique row (deterministic: fixed order, no floating-point
+//              atomics; rows cut by tile boundaries are finished in tile order by finish_cut_row).
 //   k_cadam    chain rule + KL gradient + Adam on the touched rows.                       (:592-594)
 //   k_cfinal   prior / scalar parameter gradients (fixed-order reductions) and their Adam step.
 #include "step_common.cuh"
@@ -301,8 +302,9 @@ k_cscore(ClosedCfg c, const float* __restrict__ scalars, const int32_t* __restri
 template <int VEC, int LPR, int NV>
 __global__ void __launch_bounds__(256)
 k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
-          const float* __restrict__ vs2, const float* __restrict__ msg, const float* __restrict__ rsorted,
-          float* __restrict__ gslot, float* __restrict__ grow, float* __restrict__ gws) {
+          const int32_t* __restrict__ urec, const float* __restrict__ vs2, const float* __restrict__ msg,
+          const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
+          int32_t* arrive) {
     constexpr int GPW = kWarp / LPR;
     const int dp = 3 * d + 4;
     const int lane = threadIdx.x & 31, gl = lane % LPR;
@@ -399,6 +401,10 @@ k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_
             }
         }
         flush(cur);
+        // the group storing the last partial of a cut row adds them in tile order (step_common.cuh)
+        if (head_open) finish_cut_row<VEC, LPR, NV, 3>(first_u, d, false, urec, gslot, vs2, grow, gws, arrive);
+        if (tail_open && !(head_open && last_u == first_u))
+            finish_cut_row<VEC, LPR, NV, 3>(last_u, d, false, urec, gslot, vs2, grow, gws, arrive);
     }
 }
 
@@ -768,9 +774,8 @@ extern "C" int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* t
     if (!io->grad_scalars) return set_error(VFMB_EINVAL, "vfmb_closed_backward: grad_scalars scratch required");
     if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_closed_backward: bad mode");
     cudaStream_t stream = (cudaStream_t)stream_;
-    Layout L, L3;
-    if (!pick_layout(cfg->d, &L) || !pick_layout(3 * cfg->d, &L3))
-        return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
+    Layout L;
+    if (!pick_layout(cfg->d, &L)) return set_error(VFMB_ESHAPE, "unsupported embedding size %d", cfg->d);
     vfmb_plan_capacity_t cap;
     rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &cap);
     if (rc) return rc;
@@ -786,16 +791,11 @@ extern "C" int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* t
     int nblk = (int)(cap.u_cap / (8 * ch)) + cfg->F + 1;
     if (nblk > sm.nblk_max) nblk = sm.nblk_max;
     const int grid_u = grid_warps(cap.u_cap, ch), grid_t = grid_warps(cap.n_tiles, 32 / L.lpr);
-    const int d3 = 3 * cfg->d;
+    int32_t* arrive = (int32_t*)(fbase + sm.arrive_off);
     VFMB_LAYOUT_SWITCH(L, {
         k_cgather<VEC, LPR, NV><<<grid_t, 256, 0, counted(stream)>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
-                                                            plan->pos_rank, io->vs, io->msg, io->rsorted,
-                                                            gslot, io->grow, io->gws);
-    });
-    // rows cut by tile boundaries: same combine kernel, viewing [A|Bq|C] as one 3d-wide row
-    VFMB_LAYOUT_SWITCH(L3, {
-        k_combine<VEC, LPR, NV><<<grid_warps(cap.u_cap, 32), 256, 8 * GPW_OF(LPR) * (d3 + 4) * sizeof(float), counted(stream)>>>(
-            d3, 2, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
+                                                            plan->pos_rank, plan->urec, io->vs, io->msg, io->rsorted,
+                                                            gslot, io->grow, io->gws, arrive);
     });
     VFMB_LAYOUT_SWITCH(L, {
         if (mode == VFMB_ADAM_TOUCHED)

@@ -44,6 +44,19 @@ __device__ __forceinline__ Vec<VEC> ld_vec_nc(const float* p) {
     return r;
 }
 
+// L2-coherent load (bypasses L1): data written by OTHER blocks of the running kernel
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_vec_cg(const float* p) {
+    Vec<VEC> r;
+    if constexpr (VEC == 4) {
+        float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+        r.v[0] = __ldcg(p);
+    }
+    return r;
+}
+
 // streaming variants for data touched once per step (Adam moments): evict-first in L2 so that
 // the L2-resident scratch of the gather kernels is not displaced
 template <int VEC>

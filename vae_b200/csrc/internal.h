@@ -8,7 +8,7 @@
 namespace vfmb {
 
 constexpr int kTile = 32;           // sorted positions per backward tile (k_gather)
-constexpr int kHotPartials = 32;    // a row spanning more tiles than this is "hot" (summed by a whole block)
+constexpr int kHotPartials = 32;    // a row spanning more tiles than this is listed as "hot" in the plan
 constexpr int kNumSMs = 148;        // B200
 constexpr int kPlanGrid = 2 * kNumSMs;
 constexpr int kMaxGrid = 4 * kNumSMs;   // grid-stride kernels: one resident wave at 4 blocks/SM

@@ -296,8 +296,8 @@ k_plan_finish(const int32_t* __restrict__ uniq, const int32_t* __restrict__ seg_
         const int rowid = uniq[u];
         const int len = seg_off[u + 1] - seg0;
         reinterpret_cast<int4*>(urec)[u] = make_int4(rowid, len, seg0, len);
-        // rows cut by backward-tile boundaries (k_combine_cut): few partials -> front of the list
-        // (a warp each), many -> back of the list (a block each); the order only schedules work
+        // rows cut by backward-tile boundaries, as lists (diagnostics: the step kernels finish cut rows
+        // in place, see finish_cut_row): <= kHotPartials tiles from the front, more from the back
         if (hot) {
             const int span = (seg0 + len - 1) / kTile - seg0 / kTile;
             if (span > kHotPartials) hot[hot_cap - 1 - atomicAdd(&meta[3], 1)] = u;

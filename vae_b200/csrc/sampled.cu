@@ -1,14 +1,15 @@
 // Sampled-ELBO VFM step (vfm-torch.py:189-324 forward, :359 loss, :368-370 backward + Adam).
 //
-// Five launches per fused training step (S = 1), all HBM/L2-bound (no dense contraction on this path):
+// Four launches per fused training step (S = 1), all HBM/L2-bound (no dense contraction on this path):
 //   k_stage      one lane group per UNIQUE row: gather [mean|raw scale], draw eps (Philox or
 //                injected), write the sampled row v = mu + eps*|rho| and bias w to an L2-resident
 //                scratch (+ the count-rescaled KL when not fused).   (vfm-torch.py:207-241, 290-317)
 //   k_score      one lane group per SAMPLE: FM interaction of the sampled rows, likelihood,
 //                residual dloss/dpred.                                (vfm-torch.py:244-270, 359)
 //   k_gather     ordered segmented sum of residual * partner row over the sorted occurrence list,
-//                tiled by position; k_combine_cut finishes the rows cut by tile boundaries.
-//   k_gather_score  F = 2, step running alone: k_score + k_gather in one pass (4 launches).
+//                tiled by position; the group that stores the last partial of a row cut by tile
+//                boundaries adds the row's partials in tile order (finish_cut_row).
+//   k_gather_score  F = 2, step running alone: k_score + k_gather in one pass (3 launches).
 //   k_adam_rows  per unique row: chain rule to (mu, rho) + KL gradient + Adam; FLAVOR 2 also forms
 //                the KL and recomputes the Philox draws; the last block updates the scalar
 //                parameters (alpha, global bias) and the step counter.
@@ -447,10 +448,11 @@ k_scatter_resid(const float* __restrict__ resid, const int32_t* __restrict__ pos
 // summation order, no atomics => bitwise reproducible.
 // Everything read here is L2-resident scratch written by k_stage / k_score.
 template <int VEC, int LPR, int NV, int UNIT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
-         const float* __restrict__ vs, const float* __restrict__ msg, const float* __restrict__ rsorted,
-         float* __restrict__ gslot, float* __restrict__ grow, float* __restrict__ gws) {
+         const int32_t* __restrict__ urec, const float* __restrict__ vs, const float* __restrict__ msg,
+         const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
+         int32_t* arrive) {
     constexpr int GPW = kWarp / LPR;
     const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
     const int lane = threadIdx.x & 31, gl = lane % LPR;
@@ -544,6 +546,10 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
             }
         }
         flush(cur);
+        // rows cut by this tile's boundaries (at most two): whoever stores the last partial finishes the row
+        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, d, F > 2, urec, gslot, vs, grow, gws, arrive);
+        if (tail_open && !(head_open && last_u == first_u))
+            finish_cut_row<VEC, LPR, NV, 1>(last_u, d, F > 2, urec, gslot, vs, grow, gws, arrive);
     }
 }
 
@@ -559,10 +565,11 @@ template <int VEC, int LPR, int NV, int LINK, int LIK>
 __global__ void __launch_bounds__(256)
 k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__ partner,
                const int32_t* __restrict__ pos_rank, const int32_t* __restrict__ occ,
+               const int32_t* __restrict__ urec, int32_t* arrive,
                const float* __restrict__ vs, const float* __restrict__ ws, const float* __restrict__ y,
                const float* __restrict__ eps_global, int32_t* noise_step, const int32_t* __restrict__ meta,
                float* __restrict__ pred, float* __restrict__ mean, float* __restrict__ resid,
-               float* __restrict__ gslot, float* __restrict__ grow, float* __restrict__ gws,
+               float* gslot, float* __restrict__ grow, float* __restrict__ gws,
                double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
     constexpr int GPW = kWarp / LPR, UNR = 4;
     const int d = c.d, B = c.B, N = 2 * c.B;
@@ -688,6 +695,9 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
             }
         }
         flush(cur);
+        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, d, false, urec, gslot, vs, grow, gws, arrive);
+        if (tail_open && !(head_open && last_u == first_u))
+            finish_cut_row<VEC, LPR, NV, 1>(last_u, d, false, urec, gslot, vs, grow, gws, arrive);
     }
     if (block_partials<3>(acc3, partials, counter)) {
         double tot[3];
@@ -882,33 +892,28 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
     const float* tbl = table ? table : io->msg;
     if (cfg->F != 2 && !tbl) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: table required for F != 2");
     const int N = cfg->B * cfg->F;
+    int32_t* arrive = (int32_t*)((float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).arrive_off);
     VFMB_LAYOUT_SWITCH(L, {
         if (unit_coef)
             k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
-                cfg->d, cfg->F, N, plan->partner, plan->pos_rank, io->vs, tbl, io->rsorted, gslot, io->grow, io->gws);
+                cfg->d, cfg->F, N, plan->partner, plan->pos_rank, plan->urec, io->vs, tbl, io->rsorted,
+                gslot, io->grow, io->gws, arrive);
         else
             k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
-                cfg->d, cfg->F, N, plan->partner, plan->pos_rank, io->vs, tbl, io->rsorted, gslot, io->grow, io->gws);
-        const size_t smem = 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float);
-        if (plan->hot)      // lists of the cut rows from the plan: no scan over the unique rows
-            k_combine_cut<VEC, LPR, NV><<<grid_warps(cap.n_tiles, 1), 256, smem, counted(stream)>>>(
-                cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, plan->hot, (int)cut_list_capacity(cap.n_tiles),
-                gslot, io->vs, io->grow, io->gws);
-        else
-            k_combine<VEC, LPR, NV, 0><<<grid_warps(cap.u_cap, 32), 256, smem, counted(stream)>>>(
-                cfg->d, unit_coef ? 2 : cfg->F, plan->urec, plan->meta, gslot, io->vs, io->grow, io->gws);
+                cfg->d, cfg->F, N, plan->partner, plan->pos_rank, plan->urec, io->vs, tbl, io->rsorted, gslot, io->grow,
+                io->gws, arrive);
     });
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-// F == 2 fused step: k_gather_score (score + ordered segmented sum) + k_combine_cut
+// F == 2 fused step: k_gather_score (score + ordered segmented sum)
 static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                const vfmb_step_io* io, vfmb_stream stream_) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_step", stream_, 2, &P);
     if (rc) return rc;
-    if (!io->grow || !io->gws || !io->partials || !io->pred || !io->mean || !io->resid || !plan->hot || !plan->occ)
+    if (!io->grow || !io->gws || !io->partials || !io->pred || !io->mean || !io->resid || !plan->occ)
         return set_error(VFMB_EINVAL, "vfmb_sampled_step: scratch required");
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
@@ -919,21 +924,18 @@ static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, c
     const int64_t gs_warps = (cap.n_tiles + (32 / L.lpr) - 1) / (32 / L.lpr);
     int gs_grid = (int)((gs_warps + gs_block / 32 - 1) / (gs_block / 32));
     if (gs_grid > kGridCap) gs_grid = kGridCap;            // block partials are sized for kGridCap blocks
+    int32_t* arrive = (int32_t*)((float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).arrive_off);
 #define LAUNCH_GS(LINK, LIK)                                                                             \
-    k_gather_score<VEC, LPR, NV, LINK, LIK><<<gs_grid, gs_block, 0, counted(stream)>>>(                           \
-        dc, tab->scalars, plan->partner, plan->pos_rank, plan->occ, io->vs, io->ws, io->y, io->eps_global, \
-        tab->noise_step, plan->meta, io->pred, io->mean, io->resid, gslot, io->grow, io->gws, io->partials, \
-        io->counters + 1, io->stats)
+    k_gather_score<VEC, LPR, NV, LINK, LIK><<<gs_grid, gs_block, 0, counted(stream)>>>(                  \
+        dc, tab->scalars, plan->partner, plan->pos_rank, plan->occ, plan->urec, arrive, io->vs, io->ws, io->y, \
+        io->eps_global, tab->noise_step, plan->meta, io->pred, io->mean, io->resid, gslot, io->grow, io->gws, \
+        io->partials, io->counters + 1, io->stats)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_GS(0, VFMB_GAUSSIAN); else LAUNCH_GS(0, VFMB_BERNOULLI);
         } else {
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_GS(1, VFMB_GAUSSIAN); else LAUNCH_GS(1, VFMB_BERNOULLI);
         }
-        const size_t smem = 8 * GPW_OF(LPR) * (cfg->d + 4) * sizeof(float);
-        k_combine_cut<VEC, LPR, NV><<<grid_warps(cap.n_tiles, 1), 256, smem, counted(stream)>>>(
-            cfg->d, cfg->F, plan->urec, plan->meta, plan->hot, (int)cut_list_capacity(cap.n_tiles),
-            gslot, io->vs, io->grow, io->gws);
     });
 #undef LAUNCH_GS
     CUDA_TRY(cudaGetLastError());
@@ -981,8 +983,9 @@ extern "C" int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* 
     return backward_impl(cfg, tab, plan, io, adam, mode, kl_grad_scale, 1, stream);
 }
 
-// The fused training step: 5 launches -- k_stage<LEAN>, k_score, k_gather, k_combine_cut,
-// k_adam_rows<FLAVOR 2> (KL, scalar parameters and the step counter folded in).
+// The fused training step: 4 launches -- k_stage<LEAN>, k_score, k_gather (the group that stores the
+// last partial of a row cut by tile boundaries finishes it), k_adam_rows<FLAVOR 2> (KL, scalar
+// parameters and the step counter folded in).
 extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                  const vfmb_step_io* io, const vfmb_adam* adam, vfmb_stream stream) {
     if (io && !io->y) return set_error(VFMB_EINVAL, "vfmb_sampled_step: targets required");
@@ -999,8 +1002,8 @@ extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab,
     // room on an SM for the plan's blocks.  So: fused unless the caller reserved room for the plan.
     const int fuse_knob = tuning().fuse_score;
     const bool fuse_gs = fuse_knob >= 0 ? fuse_knob != 0 : grid_reserve() == 0;
-    if (cfg && cfg->F == 2 && plan && plan->hot && fuse_gs) {
-        // F == 2: 4 launches -- k_stage<LEAN>, k_gather_score, k_combine_cut, k_adam_rows<FLAVOR 2>
+    if (cfg && cfg->F == 2 && plan && plan->occ && fuse_gs) {
+        // F == 2: 3 launches -- k_stage<LEAN>, k_gather_score, k_adam_rows<FLAVOR 2>
         rc = launch_gather_score(cfg, tab, plan, io, stream);
         if (rc) return rc;
         return launch_adam(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, 2, stream);

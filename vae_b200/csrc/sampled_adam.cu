@@ -9,7 +9,7 @@ namespace vfmb {
 // (g_v, g_w) to (mean, raw scale) + KL gradient, then Adam on the row -- parameters and both
 // moments of every touched row are read and written exactly once.
 //
-// Row gradients are final in grow/gws (k_combine_cut finished the rows cut by tile boundaries).
+// Row gradients are final in grow/gws (the gather kernel finished the rows cut by tile boundaries).
 // FLAVOR 0  plain.
 // FLAVOR 1  + the block that finishes last updates the scalar parameters and the step counter
 //             (what k_final did as a separate launch).
@@ -111,8 +111,6 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             AdamDev h, int32_t* __restrict__ adam_step, float kl_scale,
             float* __restrict__ grad_bias, float* __restrict__ grad_entity, FinalArgs fa) {
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
-    // (summing the rows cut by tile boundaries in here was tried: +16 registers = one resident block
-    // per SM less, which cost more than the separate k_combine_cut launch)
     constexpr bool KLF = FLAVOR == 2;
     const int U = meta[0];
     const int d = c.d;

@@ -154,201 +154,85 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g,
 // gradient, then Adam on the row (or the dense-gradient store).  This is the HBM-bound kernel of
 // the step: parameters and both Adam moments of every touched row are read and written once.
 
-// ------------------------------------------------------------------------------- k_combine
-// Rows cut by tile boundaries: add the tile partials in tile order (tail slot of the first tile,
-// then the head slots of the following tiles).  A block scans 256 rows.  Rows with few partials
-// are handled per warp (GPW lane groups take contiguous ranges, group sums added in group order);
-// the rare hot rows (> kHotPartials tiles: a Zipf head row with thousands of occurrences) are
-// handled by the whole block, 8*GPW groups over contiguous ranges and a fixed-order shared-memory
-// reduction.  Every association is fixed by the plan, so the result is bitwise reproducible.
-
-template <int VEC, int LPR, int NV, int UNR>
-__device__ __forceinline__ void sum_head_slots(const float* __restrict__ gslot, int dp, int d, int gl,
-                                               int lo, int hi, Vec<VEC> (&acc)[NV], float& gw) {
+// ------------------------------------------------------------------------------- cut rows
+// The backward's segmented reduction (k_gather / k_gather_score / k_cgather) walks the sorted
+// occurrence list in tiles of kTile positions.  A row cut by tile boundaries leaves one partial per
+// tile it touches: in the tail slot of its first tile, in the head slots of the following ones.
+// The lane group that stores the LAST of a row's partials (per-row arrival counter, indexed by the
+// row's first tile: a tile boundary cuts at most one row) adds them in tile order -- tail(tA),
+// head(tA+1), ..., head(tB) -- so the association is fixed by the plan and the result is bitwise
+// reproducible whichever group happens to finish.  This replaces the separate combine launch of
+// round 1 (12 us of pure latency on the ml20m step).  NW = d-wide sections per slot (1: sampled
+// step; 3: closed form [A | Bq | C]).  A Zipf head row with thousands of occurrences spans a few
+// hundred tiles: its finisher streams the slots from L2 with UNR loads in flight.
+template <int VEC, int LPR, int NV, int NW>
+__device__ __forceinline__ void finish_cut_row(int u, int d, bool own_fix, const int32_t* __restrict__ urec,
+                                            const float* gslot, const float* __restrict__ vs,
+                                            float* __restrict__ grow, float* __restrict__ gws, int32_t* arrive) {
+    constexpr int UNR = (NW == 1) ? (NV == 1 ? 4 : 2) : 1;
+    const int lane = threadIdx.x & 31, gl = lane % LPR;
+    const unsigned gmask = group_mask<LPR>();
+    const int dp = NW * d + 4;
+    __threadfence();                                        // this group's partial is visible ...
+    __syncwarp(gmask);
+    const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
+    const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;
+    int old = 0;
+    if (gl == 0) old = atomicAdd(arrive + tA, 1);           // ... before it is counted
+    old = __shfl_sync(gmask, old, 0, LPR);
+    if (old != tB - tA) return;                             // tB - tA + 1 partials; the last one finishes
+    __threadfence();
+    const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;    // tail slot of the first tile
+    Vec<VEC> tot[NW][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int w = 0; w < NW; ++w)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
-    gw = 0.f;
-    for (int t = lo; t < hi; t += UNR) {
-        Vec<VEC> part[UNR][NV]; float pw[UNR];
+        for (int i = 0; i < NV; ++i) {
+            const int k = (gl + i * LPR) * VEC;
+            if (k < d) tot[w][i] = ld_vec_cg<VEC>(tp + w * d + k);
+        }
+    float gw = __ldcg(tp + NW * d);
+    for (int t = tA + 1; t <= tB; t += UNR) {
+        Vec<VEC> part[UNR][NW][NV]; float pw[UNR];
 #pragma unroll
         for (int q = 0; q < UNR; ++q) {
-            const int tt = min(t + q, hi - 1);
-            const float* sp = gslot + ((size_t)tt * 2) * dp;
+            const float* sp = gslot + ((size_t)min(t + q, tB) * 2) * dp;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                int k = (gl + i * LPR) * VEC;
-                if (k < d) part[q][i] = ld_vec_nc<VEC>(sp + k);
-            }
-            pw[q] = __ldg(sp + d);
+            for (int w = 0; w < NW; ++w)
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int k = (gl + i * LPR) * VEC;
+                    if (k < d) part[q][w][i] = ld_vec_cg<VEC>(sp + w * d + k);
+                }
+            pw[q] = __ldcg(sp + NW * d);
         }
 #pragma unroll
         for (int q = 0; q < UNR; ++q)
-            if (t + q < hi) {
+            if (t + q <= tB) {
 #pragma unroll
-                for (int i = 0; i < NV; ++i)
+                for (int w = 0; w < NW; ++w)
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) acc[i].v[j] += part[q][i].v[j];
+                    for (int i = 0; i < NV; ++i)
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) tot[w][i].v[j] += part[q][w][i].v[j];
                 gw += pw[q];
             }
     }
-}
-
-// one row cut by few tile boundaries, summed by a warp: its GPW lane groups take contiguous slot
-// ranges; total = tail(tA) + group 0 + group 1 + ... (fixed order)
-template <int VEC, int LPR, int NV>
-__device__ __forceinline__ void combine_warp_row(int u, int tA, int tB, int d, int F,
-                                                 const float* __restrict__ gslot, const float* __restrict__ vs,
-                                                 float* __restrict__ grow, float* __restrict__ gws) {
-    constexpr int GPW = kWarp / LPR;
-    const int dp = d + 4;
-    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
-    const int per = (tB - tA + GPW - 1) / GPW;
-    const int lo = tA + 1 + gidx * per, hi = min(tB + 1, lo + per);
-    Vec<VEC> acc[NV]; float gw;
-    sum_head_slots<VEC, LPR, NV, 4>(gslot, dp, d, gl, lo, hi, acc, gw);
-    // total = tail(tA) + group 0 + group 1 + ...
-    const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
-    float gw_tot = __ldg(tp + d);
 #pragma unroll
-    for (int g = 0; g < GPW; ++g) gw_tot += __shfl_sync(0xffffffffu, gw, g * LPR);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        int k = (gl + i * LPR) * VEC;
-        Vec<VEC> tot;
-        if (k < d) tot = ld_vec_nc<VEC>(tp + k);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-#pragma unroll
-            for (int g = 0; g < GPW; ++g) {
-                float v = __shfl_sync(0xffffffffu, acc[i].v[j], g * LPR + gl);
-                if (k < d) tot.v[j] += v;
-            }
-        }
-        if (k < d && gidx == 0) {
-            if (F > 2) {                           // pairwise: sum r_n (S_n - v_u)
-                Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) tot.v[j] = fmaf(-gw_tot, own.v[j], tot.v[j]);
-            }
-            st_vec<VEC>(grow + (size_t)u * d + k, tot);
-        }
-    }
-    if (lane == 0) gws[u] = gw_tot;
-}
-
-// one hot row (> kHotPartials tile partials), summed by the whole block: 8*GPW lane groups over
-// contiguous slot ranges, then a fixed-order shared-memory reduction by one group
-template <int VEC, int LPR, int NV>
-__device__ __forceinline__ void combine_hot_row(int u, int d, int F, const int32_t* __restrict__ urec,
-                                                const float* __restrict__ gslot, const float* __restrict__ vs,
-                                                float* __restrict__ grow, float* __restrict__ gws, float* s_part) {
-    constexpr int GPW = kWarp / LPR, NG = 8 * GPW;
-    const int dp = d + 4;
-    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR, warp = threadIdx.x >> 5;
-    const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
-    const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;
-    const int g = warp * GPW + gidx;                        // group id 0 .. NG-1
-    const int per = (tB - tA + NG - 1) / NG;
-    const int lo = min(tB + 1, tA + 1 + g * per), hi = min(tB + 1, lo + per);
-    Vec<VEC> acc[NV]; float gw;
-    sum_head_slots<VEC, LPR, NV, 8>(gslot, dp, d, gl, lo, hi, acc, gw);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        int k = (gl + i * LPR) * VEC;
-        if (k < d) st_vec<VEC>(s_part + (size_t)g * dp + k, acc[i]);
-    }
-    if (gl == 0) s_part[(size_t)g * dp + d] = gw;
-    __syncthreads();
-    if (warp == 0 && gidx == 0) {                          // one lane group adds the NG sums in order
-        const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;
-        float gw_tot = __ldg(tp + d);
-        for (int q = 0; q < NG; ++q) gw_tot += s_part[(size_t)q * dp + d];
+    for (int w = 0; w < NW; ++w)
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            int k = (gl + i * LPR) * VEC;
+            const int k = (gl + i * LPR) * VEC;
             if (k < d) {
-                Vec<VEC> tot = ld_vec_nc<VEC>(tp + k);
-                for (int q = 0; q < NG; ++q)
+                if (NW == 1 && own_fix) {                   // pairwise (F > 2): sum r_n (S_n - v_u)
+                    const Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) tot.v[j] += s_part[(size_t)q * dp + k + j];
-                if (F > 2) {
-                    Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) tot.v[j] = fmaf(-gw_tot, own.v[j], tot.v[j]);
+                    for (int j = 0; j < VEC; ++j) tot[w][i].v[j] = fmaf(-gw, own.v[j], tot[w][i].v[j]);
                 }
-                st_vec<VEC>(grow + (size_t)u * d + k, tot);
+                st_vec<VEC>(grow + (size_t)u * NW * d + w * d + k, tot[w][i]);
             }
         }
-        if (gl == 0) gws[u] = gw_tot;
-    }
-    __syncthreads();
-}
-
-// every row cut by a tile boundary, from the plan's lists (no scan over the unique rows): the
-// `cut` list holds the rows with <= kHotPartials partials from its front (meta[5] entries, one
-// warp each), the hot rows from its back (meta[3] entries, one block each).
-template <int VEC, int LPR, int NV>
-__global__ void __launch_bounds__(256)
-k_combine_cut(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
-              const int32_t* __restrict__ cut, int cut_cap, const float* __restrict__ gslot,
-              const float* __restrict__ vs, float* __restrict__ grow, float* __restrict__ gws) {
-    extern __shared__ float s_part[];                    // [8*GPW][d+4] block-level partial sums
-    const int n_hot = meta[3], n_cut = meta[5];
-    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int i = gwarp; i < n_cut; i += nwarps) {
-        const int u = __ldg(cut + i);
-        const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
-        combine_warp_row<VEC, LPR, NV>(u, rec.z / kTile, (rec.z + rec.y - 1) / kTile, d, F, gslot, vs, grow, gws);
-    }
-    __syncthreads();
-    for (int i = blockIdx.x; i < n_hot; i += gridDim.x)
-        combine_hot_row<VEC, LPR, NV>(__ldg(cut + cut_cap - 1 - i), d, F, urec, gslot, vs, grow, gws, s_part);
-}
-
-template <int VEC, int LPR, int NV, int HOT_ONLY = 0>
-__global__ void __launch_bounds__(256)
-k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
-          const float* __restrict__ gslot, const float* __restrict__ vs,
-          float* __restrict__ grow, float* __restrict__ gws) {
-    constexpr int GPW = kWarp / LPR, NG = 8 * GPW;
-    extern __shared__ float s_part[];                    // [NG][dp] block-level partial sums
-    __shared__ int s_hot[256];
-    __shared__ int s_nhot;
-    const int U = meta[0];
-    const int dp = d + 4;
-    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR, warp = threadIdx.x >> 5;
-    for (int bbase = blockIdx.x * 256; bbase < U; bbase += gridDim.x * 256) {
-        if (threadIdx.x == 0) s_nhot = 0;
-        __syncthreads();
-        const int base = bbase + warp * 32;
-        const int ul = base + lane;
-        int tA_l = 0, tB_l = 0;
-        if (ul < U) {
-            const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
-            tA_l = rec.z / kTile;                          // first / last tile of the row's segment
-            tB_l = (rec.z + rec.y - 1) / kTile;
-        }
-        const int P_l = tB_l - tA_l;
-        if (P_l > kHotPartials) s_hot[atomicAdd(&s_nhot, 1)] = ul;   // order only affects scheduling
-        // HOT_ONLY: the rows with few partials are summed by the consumer (k_adam_rows<FLAVOR >= 1>)
-        unsigned todo = HOT_ONLY ? 0u : __ballot_sync(0xffffffffu, P_l > 0 && P_l <= kHotPartials);
-        // ---- per-warp: rows with few partials
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int u = base + src;
-            const int tA = __shfl_sync(0xffffffffu, tA_l, src), tB = __shfl_sync(0xffffffffu, tB_l, src);
-            combine_warp_row<VEC, LPR, NV>(u, tA, tB, d, F, gslot, vs, grow, gws);
-        }
-        __syncthreads();
-        // ---- whole block: hot rows
-        const int nhot = s_nhot;
-        for (int hi_ = 0; hi_ < nhot; ++hi_)
-            combine_hot_row<VEC, LPR, NV>(s_hot[hi_], d, F, urec, gslot, vs, grow, gws, s_part);
-        __syncthreads();                                   // s_nhot / s_hot are reused by the next pass
-    }
+    if (gl == 0) { gws[u] = gw; arrive[tA] = 0; }           // counter ready for the next step
 }
 
 
@@ -371,7 +255,7 @@ k_combine(int d, int F, const int32_t* __restrict__ urec, const int32_t* __restr
 // Carving of vfmb_step_io.partials (doubles): block partials of the scalar reductions, the tile
 // head/tail slots of the gather kernels, and (closed form) the prior-gradient partials.
 struct ScratchMap {
-    size_t gslot_off, pg_part_off, pg_sum_off, blk_class_off, total_doubles;   // offsets in floats
+    size_t gslot_off, pg_part_off, pg_sum_off, blk_class_off, arrive_off, total_doubles;   // offsets in floats
     int nblk_max, pg_width;
 };
 static inline ScratchMap scratch_map(int B, int F, int d, int64_t u_cap) {
@@ -386,6 +270,8 @@ static inline ScratchMap scratch_map(int B, int F, int d, int64_t u_cap) {
     m.pg_part_off = off;      off += (size_t)m.nblk_max * m.pg_width;
     m.pg_sum_off = off;       off += (size_t)kMaxFields * m.pg_width;
     m.blk_class_off = off;    off += (size_t)m.nblk_max + 16;
+    m.arrive_off = off;       off += (size_t)slots / 2 + 16;   // per-tile arrival counters of the cut rows (int32,
+                                                              // zero-initialised with the buffer, self-resetting)
     m.total_doubles = (off + 1) / 2;
     return m;
 }
