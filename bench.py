@@ -105,13 +105,48 @@ def dist_env():
     return rank, world, local
 
 
+def learning_rate(w: synth.Workload) -> float:
+    """vfm-torch.py:92 (1 / (1 + N_train // batch)); vfm-tomasrch.py:518 (0.1)."""
+    return 0.1 if w.variant == "closed" else 1.0 / (1 + w.n_train // w.batch)
+
+
+def alpha_0(w: synth.Workload) -> float:
+    """vfm-tomasrch.py:742-743: alpha_0 = 0.5 * number of batches per epoch."""
+    return 0.5 * -(-w.n_train // w.batch)
+
+
 def make_model(w: synth.Workload, device, train_counts, lr):
-    from vae_b200.vfm_torch import CF
     torch.manual_seed(synth.PARAM_SEED)
+    if w.variant == "closed":                                 # vfm-tomasrch.py path (BASELINE config 2)
+        from vae_b200.vfm_tomasrch import CF as ClosedCF
+        return ClosedCF(w.d, w.n_fields, w.field_sizes, 1, alpha_0(w), "reg", train_counts=torch.from_numpy(train_counts),
+                        n_train=w.n_train, max_batch=w.batch, lr=lr, device=device)
+    from vae_b200.vfm_torch import CF
     kl = "torch" if w.n_fields == 2 else "group"
     return CF(w.d, output=w.output, n_users=w.field_sizes[0], n_items=w.field_sizes[1],
               train_counts=torch.from_numpy(train_counts), field_sizes=w.field_sizes, kl_weighting=kl,
               n_train=w.n_train, max_batch=w.batch, seed=synth.NOISE_SEED, lr=lr, device=device)
+
+
+def make_port(w: synth.Workload, train_counts, lr):
+    """The oracle's torch restatement of the reference model + its optimizer + a step function
+    (CPU leg only: cpu_baseline / parity_vs_port / --impl reference)."""
+    from oracle import vfm_port
+    tc = torch.from_numpy(train_counts)
+    torch.manual_seed(synth.PARAM_SEED)
+    if w.variant == "closed":
+        port = vfm_port.ClosedPort(w.d, w.field_sizes, alpha_0=alpha_0(w))
+        opt = torch.optim.Adam(port.parameters(), lr=lr)
+        tcf = tc.to(torch.float32)
+        step = lambda x, y, noise=None: vfm_port.closed_port_step(port, opt, x, y, w.n_train, tcf)
+        return port, opt, step
+    kl = "torch" if w.n_fields == 2 else "group"
+    port = vfm_port.SampledPort(w.field_sizes[0], w.field_sizes[1], w.d, tc, output=w.output,
+                                field_sizes=w.field_sizes, kl_weighting=kl,
+                                interaction="prod" if w.n_fields == 2 else "pairwise")
+    opt = torch.optim.Adam(port.parameters(), lr=lr)
+    step = lambda x, y, noise=None: vfm_port.sampled_port_step(port, opt, x, y, w.n_train, noise)
+    return port, opt, step
 
 
 def apply_tuning(args):
@@ -134,7 +169,8 @@ def run_ours(args):
     n_batches = w.n_train // B
     assert n_batches >= 1
     tc = w.train_counts()
-    lr = 1.0 / (1 + w.n_train // B)                           # vfm-torch.py:92
+    tc[tc == 0] = 1                                           # rows never seen in training: weight 1
+    lr = learning_rate(w)
     model = make_model(w, device, tc, lr)
     # weak scaling over independent replicas is NOT the multi-GPU mode of this path; see
     # vae_b200/dist.py.  For N>1 each rank takes every world-th batch of the global stream.
@@ -155,6 +191,7 @@ def run_ours(args):
 
     dp = None
     if world > 1:                                            # mode A: replicated tables, dense all-reduce
+        assert w.variant == "sampled", "multi-GPU modes exist for the sampled step"
         from vae_b200.dist import DataParallelSampled
         dp = DataParallelSampled(model, world, dense_adam=False)
 
@@ -262,18 +299,21 @@ def run_ours(args):
         "config": {"workload": f"{w.name}: {'+'.join(map(str, w.field_sizes))} rows, d={d}, "
                                f"{w.n_train} ratings, batch {B}, {w.variant} ELBO, {w.output}",
                    "fields": F, "unique_rows_per_step": U, "adam": "touched rows (lazy)",
-                   "noise": "Philox4x32-10 in-kernel", "plan": {"inline": "built every step on the step's stream",
+                   "noise": "none (closed form)" if w.variant == "closed" else "Philox4x32-10 in-kernel", "plan": {"inline": "built every step on the step's stream",
                             "prefetch": "built every step, one batch ahead on a side stream",
                             "graph": "built every step, one batch ahead on a side stream; step + plan "
                                      "replayed as one CUDA graph",
                             "cached": "precomputed per batch (never-shuffled loader)"}[args.plan]
                            + " (own tiled LSD radix sort, no library kernels)",
                    "l2": "params+Adam state 258 MB > 126 MB L2; consecutive distinct batches, no flush"
-                   if args.workload == "ml20m" else "consecutive distinct batches, no flush",
+                   if args.workload == "ml20m" else
+                   ("state fits L2: the step is launch/latency-bound, no roofline claim (BASELINE.md section 3)"
+                    if args.workload in ("ml100k", "fraction") else "consecutive distinct batches, no flush"),
                    "parallelism": (f"dp{world}: replicated tables, batch {B}/GPU, one NCCL all-reduce of the "
                                    f"dense gradient ({(w.rows * (2 * d + 3) + 16) * 4 / 1e6:.1f} MB) per step")
                    if world > 1 else "single"},
-        "roofline": {"bound": "hbm", "kernel": "k_adam_rows (chain rule + Adam on the touched rows)",
+        "roofline": {"bound": "hbm", "kernel": ("k_cadam" if w.variant == "closed" else "k_adam_rows")
+                                                + " (chain rule + Adam on the touched rows)",
                      "achieved": (rk_bytes / (rows_ms * 1e-3) / 1e9) if rows_ms == rows_ms else None,
                      "peak": peak, "unit": "GB/s",
                      "frac": (rk_bytes / (rows_ms * 1e-3) / 1e9 / peak) if rows_ms == rows_ms else None,
@@ -584,21 +624,16 @@ def run_sharded(args):
 
 # ------------------------------------------------------------------------------------------
 def cpu_baseline(args, budget_s=20.0):
-    """The oracle port (torch CPU, same ATen ops as the reference: unique, embedding, distributions,
-    autograd, dense Adam) on this box's host cores, on a bounded number of full-size steps."""
-    from oracle import vfm_port
+    """The oracle port (torch CPU, same ATen ops as the reference: unique, embedding / indexing,
+    distributions, autograd, dense Adam) on this box's host cores, on a bounded number of full-size steps."""
     w = synth.make_workload(args.workload, n_rows=args.rows)
     if w.rows > 20_000_000:                                   # dense grads + dense Adam cannot hold 100M rows
         return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                 "sample": "skipped: dense reference cannot allocate this table"}
     B = w.batch
-    tc = torch.from_numpy(w.train_counts())
-    torch.manual_seed(synth.PARAM_SEED)
-    kl = "torch" if w.n_fields == 2 else "group"
-    model = vfm_port.SampledPort(w.field_sizes[0], w.field_sizes[1], w.d, tc, output=w.output,
-                                 field_sizes=w.field_sizes, kl_weighting=kl,
-                                 interaction="prod" if w.n_fields == 2 else "pairwise")
-    opt = torch.optim.Adam(model.parameters(), lr=1.0 / (1 + w.n_train // B))
+    tc = w.train_counts()
+    tc[tc == 0] = 1
+    _, _, step = make_port(w, tc, learning_rate(w))
     x, y = torch.from_numpy(w.x), torch.from_numpy(w.y)
     n_batches = w.n_train // B
     times = []
@@ -607,7 +642,7 @@ def cpu_baseline(args, budget_s=20.0):
     while True:
         j = i % n_batches
         t0 = time.perf_counter()
-        vfm_port.sampled_port_step(model, opt, x[j * B:(j + 1) * B], y[j * B:(j + 1) * B], w.n_train)
+        step(x[j * B:(j + 1) * B], y[j * B:(j + 1) * B])
         dt = time.perf_counter() - t0
         if i >= 2:
             times.append(dt)
@@ -624,38 +659,36 @@ def cpu_baseline(args, budget_s=20.0):
 
 def parity_vs_port(args, device):
     """Part of the CPU leg (the only place bench.py runs the oracle): one training step of the timed
-    configuration -- same code path as the timed steps (in-kernel Philox noise, fused step), first batch,
-    fresh parameters -- against the torch port of the reference fed the exported Philox draws."""
-    from oracle import vfm_port
+    configuration -- same code path as the timed steps (fused step; in-kernel Philox noise for the sampled
+    variant), first batch, fresh parameters -- against the torch port of the reference (fed the exported
+    Philox draws)."""
     w = synth.make_workload(args.workload, n_rows=args.rows)
     if w.rows > 20_000_000:
         return {"skipped": "dense reference cannot allocate this table"}
     B = w.batch
     tc = w.train_counts()
-    lr = 1.0 / (1 + w.n_train // B)
+    tc[tc == 0] = 1
+    lr = learning_rate(w)
     model = make_model(w, device, tc, lr)
-    kl = "torch" if w.n_fields == 2 else "group"
-    port = vfm_port.SampledPort(w.field_sizes[0], w.field_sizes[1], w.d, torch.from_numpy(tc), output=w.output,
-                                field_sizes=w.field_sizes, kl_weighting=kl,
-                                interaction="prod" if w.n_fields == 2 else "pairwise", faithful_cost=False)
+    port, _, step = make_port(w, tc, lr)
     own = port.state_dict()
     port.load_state_dict({k: v.detach().cpu().reshape(own[k].shape) for k, v in model.state_dict().items() if k in own},
                          strict=False)
-    opt = torch.optim.Adam(port.parameters(), lr=lr)
     x, y = torch.from_numpy(w.x[:B]), torch.from_numpy(w.y[:B])
     uniq = torch.unique(x)
-    noise = [n.cpu() for n in model.philox_noise(uniq)]
+    noise = [n.cpu() for n in model.philox_noise(uniq)] if w.variant == "sampled" else None
     res = model.fused_step(x.to(device), y.to(device))
     torch.cuda.synchronize()
-    po = vfm_port.sampled_port_step(port, opt, x, y, w.n_train, noise)
+    po = step(x, y, noise)
     pred, want = res["pred"].cpu().numpy().astype(np.float64), po["pred"].numpy().astype(np.float64)
-    out = {"oracle": "oracle/vfm_port.py (fp32 torch restatement of vfm-torch.py), same Philox draws injected",
-           "pred_max_rel_err": float(np.max(np.abs(pred - want) / np.maximum(np.abs(want), 1e-3))),
-           "loss_rel_err": float(abs(res["loss"].item() - po["loss"].item()) / abs(po["loss"].item())),
-           "kl_rel_err": float(abs(res["kl"].item() - po["kl"].item()) / abs(po["kl"].item()))}
+    out = {"oracle": "oracle/vfm_port.py (fp32 torch restatement of the reference step)"
+                     + (", same Philox draws injected" if noise is not None else ""),
+           "pred_max_err_over_rms": float(np.max(np.abs(pred - want)) / np.sqrt(np.mean(want ** 2))),
+           "loss_rel_err": float(abs(res["loss"].item() - po["loss"].item()) / abs(po["loss"].item()))}
     u = uniq.numpy()
-    got = model.entity_params.weight.detach().cpu().numpy()[u].astype(np.float64)
-    ref = port.entity_params.weight.detach().numpy()[u].astype(np.float64)
+    ent = "entity_params" if w.variant == "closed" else "entity_params.weight"
+    got = dict(model.named_parameters())[ent].detach().cpu().numpy()[u].astype(np.float64)
+    ref = dict(port.named_parameters())[ent].detach().numpy()[u].astype(np.float64)
     err = np.abs(got - ref)
     outside = err > 1e-5 * np.abs(ref) + 1e-4 * lr
     out.update({"params_rows_checked": int(len(u)), "params_max_err_over_lr": float(err.max() / lr),
@@ -684,7 +717,10 @@ def run_reference(args):
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{w.name}: {'+'.join(map(str, w.field_sizes))} rows, d={w.d}, "
                                   f"{w.n_train} ratings, batch {w.batch}, {w.variant} ELBO, {w.output}",
-                      "fields": w.n_fields, "adam": "dense (torch.optim.Adam)", "wall_s": wall},
+                      "fields": w.n_fields, "adam": "dense (torch.optim.Adam)", "wall_s": wall,
+                      "implementation": "oracle/vfm_port.py: the reference's step restated with the same ATen calls "
+                                        "(== the AST-sliced reference to 1e-12, tests/test_oracle_vs_reference.py); "
+                                        "the reference scripts themselves cannot be imported (they train at import time)"},
            "cpu_baseline": cb,
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)

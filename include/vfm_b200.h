@@ -38,6 +38,11 @@ extern "C" {
 enum { VFMB_GAUSSIAN = 0, VFMB_BERNOULLI = 1 };           /* vfm-torch.py:267-270 */
 enum { VFMB_LINK_ABS = 0, VFMB_LINK_SOFTPLUS = 1 };       /* vfm-torch.py:125-126 */
 enum { VFMB_ADAM_TOUCHED = 0, VFMB_GRAD_ONLY = 1 };       /* backward epilogue     */
+/* factor interaction of the plan-free prediction entry points: the product over the fields
+ * (vfm-torch.py:245 / vfm-tomasrch.py:343 `prod(axis)`; the scripts' own formula) or the pairwise FM
+ * sum_{i<j} <v_i, v_j> (vfm-tomasrch.py:379-393, vfm.py:467-474).  Equal for F = 2.  The sampled
+ * training step always scores F > 2 fields pairwise. */
+enum { VFMB_INTER_PROD = 0, VFMB_INTER_PAIRWISE = 1 };
 
 typedef void* vfmb_stream; /* cudaStream_t */
 
@@ -62,7 +67,8 @@ typedef struct vfmb_config {
     int32_t row_stride;   /* row-sharded tables: global id of local row r is        */
     uint64_t seed;        /* Philox key                                            */
     int32_t row_offset;   /*   r*row_stride + row_offset (0 / 0 mean 1 / 0); the    */
-    int32_t reserved;     /*   noise and the KL class are keyed by the GLOBAL id    */
+    int32_t interaction;  /*   noise and the KL class are keyed by the GLOBAL id.
+                             interaction: VFMB_INTER_* of vfmb_predict_mean / vfmb_predict_sampled */
 } vfmb_config;
 
 /* Parameter tables and Adam state.  m/v may be NULL for forward-only use. */
@@ -310,10 +316,21 @@ int vfmb_closed_forward(const vfmb_config* cfg, const vfmb_tables* tab, const vf
 int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                          const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
                          vfmb_stream stream);
+/* The same backward for a caller whose autograd assembles the loss itself (the loop of
+ * vfm-tomasrch.py:569-588 run unchanged on the drop-in module): the upstream gradients arrive as
+ *   kl_weight [U]  d loss / d (kls[1][u] + sum_k kls[2][u,k])  per unique row (NULL: the c_u of :574-587),
+ *   data_scale     d loss / d (-partial_loss)                  (N_train / B in the script),
+ *   kl0_scale      weight of kls[0] in the scalar-parameter gradients (0 when autograd differentiates
+ *                  kls[0] itself).
+ * vfmb_closed_backward is this call with (NULL, n_train / B, 1). */
+int vfmb_closed_backward_weighted(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                  const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                                  const float* kl_weight, float data_scale, float kl0_scale,
+                                  vfmb_stream stream);
 
-/* Posterior-mean prediction without a plan: global + sum of bias means +
- * product over fields of factor means (vfm-torch.py:248-259 last_logits,
- * vfm-tomasrch.py:342-348). */
+/* Posterior-mean prediction without a plan: global + sum of bias means + interaction of the factor
+ * means -- cfg->interaction: product over the fields (vfm-torch.py:248-259 last_logits,
+ * vfm-tomasrch.py:342-348) or pairwise (the model a sampled step with F > 2 fields optimises). */
 int vfmb_predict_mean(const vfmb_config* cfg, const float* bias, const float* entity,
                       float global_bias, const int64_t* x, float* out, vfmb_stream stream);
 

@@ -120,6 +120,39 @@ def gen_sampled(name, N, M, d, x, y, n_train, batch, steps, output, lr, S=1, lin
     _save(name, meta, arrays)
 
 
+def gen_saved_logits(name, N, M, d, x, y, n_train, batch, steps, lr):
+    """Evaluation outputs of the reference (vfm-torch.py:179-185, 248-262): ``save_weights()`` after
+    each of ``steps`` training steps, then ``last_logits`` (last snapshot) and ``mean_logits`` (mean
+    over the snapshots) of a forward on an evaluation batch."""
+    torch.manual_seed(synth.PARAM_SEED)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    tc = torch.bincount(xt[:n_train].flatten(), minlength=N + M)
+    CF = ref_slice.sampled_cf_class(N, M, d, tc)
+    model = CF(d, output="reg")
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    arrays = {"x": x.astype(np.int32), "y": y, "train_counts": _np(tc).astype(np.int64)}
+    arrays.update({f"init.{k}": v for k, v in _state(model).items()})
+    gen = torch.Generator().manual_seed(synth.NOISE_SEED)
+    for t in range(steps):
+        lo = _batch_lo(t, batch, len(xt))
+        xb, yb = xt[lo:lo + batch], yt[lo:lo + batch]
+        U = len(torch.unique(xb))
+        noise = [torch.randn(1, 1, generator=gen), torch.randn(1, U, generator=gen), torch.randn(1, U, d, generator=gen)]
+        ref_slice.sampled_step(model, opt, xb, yb, n_train, noise)
+        model.save_weights()
+        arrays.update({f"step{t}.after.{k}": v for k, v in _state(model).items() if not k.startswith("prec_")})
+    x_eval = xt[-batch:]
+    with torch.no_grad():
+        _, last_logits, mean_logits, _ = model(x_eval)
+    arrays["x_eval"] = _np(x_eval).astype(np.int32)
+    arrays["last_logits"] = np.asarray(last_logits, dtype=np.float32)
+    arrays["mean_logits"] = np.asarray(mean_logits, dtype=np.float32)
+    meta = dict(variant="sampled", N=N, M=M, d=d, S=1, link="abs", output="reg", lr=lr, n_train=int(n_train),
+                batch=int(batch), steps=steps, source="vfm-torch.py:179-185,248-262 (AST-sliced, unmodified)",
+                torch=torch.__version__)
+    _save(name, meta, arrays)
+
+
 def gen_closed(name, group_sizes, d, x, y, n_train, batch, steps, lr, alpha_0, perturb=0.0):
     torch.manual_seed(synth.PARAM_SEED)
     G = len(group_sizes)
@@ -193,6 +226,7 @@ def main():
                 link="softplus")
     gen_sampled("sampled_class_s2", fs[0], fs[1], 8, x, (y > 3).astype(np.float32), len(x), 512,
                 2, "class", lr=0.05, S=2)
+    gen_saved_logits("sampled_saved_logits", fs[0], fs[1], 8, x, y, len(x), 512, 3, lr=0.05)
     # config 2: ML-100K-shaped closed form, d=20, B=8000, lr 0.1, alpha_0 = 0.5*ceil(80000/8000)
     w = synth.make_workload("ml100k")
     gen_closed("closed_ml100k", w.field_sizes, 20, w.x, w.y, w.n_train, 8000, 2, lr=0.1,

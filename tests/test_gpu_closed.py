@@ -173,3 +173,113 @@ def test_reference_forward_signature_values():
     likelihood2, kls2 = m(inverse, present)
     assert torch.equal(likelihood2.mean, likelihood.mean)
     np.testing.assert_allclose(m.predict(xt).cpu().numpy(), likelihood.mean.cpu().numpy(), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", gu.CLOSED)
+def test_per_group_plan_is_bit_exact(name):
+    """vfm-tomasrch.py:536-545: per column g, torch.unique(indices[:, g], return_inverse, return_counts).
+    The CUDA plan holds the same integers: rows are grouped by id range, so group g's ``present`` is the
+    slice [class_off[g], class_off[g+1]) of the sorted unique list, ``inverse`` the unique rank minus
+    that offset, ``counts`` the segment lengths."""
+    meta, g = gu.load(name)
+    fs = meta["group_sizes"]
+    G = len(fs)
+    m = _model(meta, g, 0)
+    for t in range(meta["steps"]):
+        x, y = gu.batch_of(meta, g, t)
+        m.fused_step(torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV), update=False)
+        plan = m._plan
+        plan.check_ids()
+        uniq, inverse, counts = (a.cpu().numpy() for a in plan.as_unique())
+        off = plan.class_off[: G + 1].cpu().numpy()
+        assert off[0] == 0 and off[G] == len(uniq)
+        for q in range(G):
+            lo, hi = off[q], off[q + 1]
+            assert np.array_equal(uniq[lo:hi], g[f"step{t}.present{q}"]), (t, q)
+            assert np.array_equal(inverse[:, q] - lo, g[f"step{t}.inverse{q}"]), (t, q)
+            assert np.array_equal(counts[lo:hi], g[f"step{t}.counts{q}"]), (t, q)
+
+
+@pytest.mark.parametrize("name", gu.CLOSED)
+def test_dropin_autograd_loop_equals_reference(name):
+    """The reference's own training loop (vfm-tomasrch.py:535-594) on the drop-in module: per-group
+    torch.unique, model(inverse_group, group_present, closed_form_loss=True, target=y), the script's loss
+    expression, loss.backward(), torch.optim.Adam (dense) -- against the goldens of the unmodified script."""
+    meta, g = gu.load(name)
+    fs, lr = meta["group_sizes"], meta["lr"]
+    n_groups = len(fs)
+    m = _model(meta, g, 0)
+    entity_count = torch.from_numpy(g["train_counts"]).float().to(DEV)
+    group_sizes = fs
+    n_train = meta["n_train"]
+    optimizer = torch.optim.Adam(m.parameters(), lr=lr)
+    for t in range(meta["steps"]):
+        if t > 0:                                          # replay from the exact reference state
+            _restore(m, g, t)
+            for k, p in m.named_parameters():
+                optimizer.state[p] = {"step": torch.tensor(float(t)),
+                                      "exp_avg": torch.from_numpy(g[f"step{t - 1}.adam.{k}.m"]).to(DEV).reshape(p.shape),
+                                      "exp_avg_sq": torch.from_numpy(g[f"step{t - 1}.adam.{k}.v"]).to(DEV).reshape(p.shape)}
+        x, y = gu.batch_of(meta, g, t)
+        indices, target = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+        group_present, inverse_group, batch_group_count = [], [], []
+        for i_group in range(n_groups):
+            present, inverse, batch_count = torch.unique(indices[:, i_group], return_inverse=True, return_counts=True)
+            group_present.append(present), inverse_group.append(inverse), batch_group_count.append(batch_count)
+        outputs, kls, partial_loss = m(inverse_group, group_present, closed_form_loss=True, target=target)
+        loss = (- n_train * partial_loss / len(indices)
+                + kls[0]
+                + ((kls[1] + kls[2].sum(axis=1))
+                   * torch.cat([(group_sizes[i_group]
+                                 / (batch_group_count[i_group] / entity_count[group_present[i_group]]).sum()
+                                 ).repeat(len(group_present[i_group])) for i_group in range(n_groups)])
+                   * torch.concat(batch_group_count)
+                   / entity_count[torch.concat(group_present)]).sum())
+        np.testing.assert_allclose(loss.item(), g[f"step{t}.loss"], rtol=1e-5)
+        np.testing.assert_allclose(outputs.mean.detach().cpu().numpy(), g[f"step{t}.pred"], rtol=1e-5, atol=2e-6)
+        optimizer.zero_grad()
+        loss.backward()
+        if t == 0:
+            for k, p in m.named_parameters():
+                assert p.grad is not None, k
+                assert gu.rel_err(p.grad.cpu().numpy().reshape(-1), g[f"step0.grad.{k}"].reshape(-1)) < 3e-5, k
+        optimizer.step()
+        after = gu.state(g, f"step{t}.after")
+        for k in after:                                   # dense Adam: every row, every prior parameter
+            got, want = m.state_dict()[k].cpu().numpy().reshape(-1), after[k].reshape(-1)
+            bad = np.abs(got - want) > 1e-5 * np.abs(want) + 5e-5 * lr + 1e-6
+            assert bad.mean() <= 1e-3, (name, t, k, float(bad.mean()))
+
+
+def test_dropin_autograd_rejects_non_uniform_kl_weights():
+    meta, g = gu.load("closed_3groups")
+    m = _model(meta, g, 0)
+    x, y = gu.batch_of(meta, g, 0)
+    xt = torch.from_numpy(x).to(DEV)
+    present, inverse = zip(*[torch.unique(xt[:, q], return_inverse=True) for q in range(len(meta["group_sizes"]))])
+    _, kls, partial = m(list(inverse), list(present), closed_form_loss=True, target=torch.from_numpy(y).to(DEV))
+    wk = torch.linspace(0.5, 1.5, meta["d"], device=DEV)
+    (-partial + (kls[2] * wk).sum() + kls[1].sum()).backward()
+    assert torch.isnan(m.entity_params.grad).all()
+
+
+def test_closed_form_wide_rows():
+    """d = 128 (3d = 384 floats per gathered row: beyond the 256-float layout limit of round 1)."""
+    from vae_b200.vfm_tomasrch import CF
+    fs, d, B = [50, 30], 128, 600
+    rng = np.random.default_rng(3)
+    x = np.stack([rng.integers(0, fs[0], B), fs[0] + rng.integers(0, fs[1], B)], 1).astype(np.int64)
+    y = np.clip(np.round(3.5 + rng.standard_normal(B)), 1, 5).astype(np.float32)
+    tc = np.bincount(x.reshape(-1), minlength=sum(fs))
+    tc[tc == 0] = 1
+    torch.manual_seed(1)
+    m = CF(embedding_size=d, n_groups=2, group_sizes=fs, alpha_0=2.0, train_counts=torch.from_numpy(tc), n_train=B,
+           max_batch=B, lr=0.1)
+    with torch.no_grad():
+        m.entity_params[:, :d].normal_(0, 0.1)
+    sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    gr = m.gradients(torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV))
+    exact = vfm_math.closed_step(gu.closed_math_params(sd, 2), x, y, tc.astype(np.float64), B, fs)
+    np.testing.assert_allclose(gr["loss"].item(), exact["loss"], rtol=1e-5)
+    assert gu.rel_err(gr["entity_params"].cpu().numpy(), exact["grads"]["entity"]) < 5e-6
+    assert gu.rel_err(gr["bias_params"].cpu().numpy(), exact["grads"]["bias"]) < 5e-6

@@ -402,6 +402,45 @@ def test_mean_prediction_and_saved_weights():
     np.testing.assert_allclose(mean_logits.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
 
 
+def test_last_and_mean_logits_match_reference_golden():
+    """vfm-torch.py:179-185, 248-262 on the unmodified reference: save_weights() after each of three
+    training steps, then last_logits (last snapshot) and mean_logits (mean of the three snapshots)."""
+    meta, g = gu.load("sampled_saved_logits")
+    m = _model(meta, g, 0)
+    for t in range(meta["steps"]):
+        sd = gu.state(g, f"step{t}.after")
+        own = m.state_dict()
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)).reshape(own[k].shape) for k, v in sd.items() if k in own},
+                          strict=False)
+        m.save_weights()
+    xe = torch.from_numpy(g["x_eval"].astype(np.int64)).to(DEV)
+    with torch.no_grad():
+        _, last_logits, mean_logits, _ = m(xe)
+    np.testing.assert_allclose(last_logits.cpu().numpy(), g["last_logits"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(mean_logits.cpu().numpy(), g["mean_logits"], rtol=1e-5, atol=2e-6)
+    assert not np.allclose(g["last_logits"], g["mean_logits"], atol=1e-3)      # the running mean matters
+
+
+def test_mean_prediction_of_multi_field_model_is_pairwise():
+    """F > 2: the sampled step optimises the pairwise FM, so predict_mean / last_logits evaluate the
+    pairwise interaction of the posterior means (interaction="prod" gives the scripts' formula)."""
+    from vae_b200.vfm_torch import CF
+    fs, d, B = [11, 7, 5], 8, 64
+    rng = np.random.default_rng(0)
+    offs = np.concatenate(([0], np.cumsum(fs)[:-1]))
+    x = np.stack([offs[f] + rng.integers(0, fs[f], B) for f in range(3)], 1).astype(np.int64)
+    for inter in ("pairwise", "prod"):
+        torch.manual_seed(1)
+        m = CF(d, output="reg", n_users=fs[0], n_items=fs[1], train_counts=torch.ones(sum(fs)), field_sizes=fs,
+               kl_weighting="group", interaction=inter if inter == "prod" else None, n_train=B, max_batch=B)
+        W = m.entity_params.weight.detach().cpu().numpy()[:, :d].astype(np.float64)
+        bw = m.bias_params.weight.detach().cpu().numpy()[:, 0].astype(np.float64)
+        v = W[x]                                            # [B, F, d]
+        fm = (0.5 * (v.sum(1) ** 2 - (v ** 2).sum(1))).sum(1) if inter == "pairwise" else v.prod(1).sum(1)
+        want = m.global_bias_mean.item() + bw[x].sum(1) + fm
+        np.testing.assert_allclose(m.predict_mean(torch.from_numpy(x).to(DEV)).cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
 def test_no_cpu_fallback():
     from vae_b200.vfm_torch import CF
     with pytest.raises(RuntimeError):

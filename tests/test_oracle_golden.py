@@ -118,3 +118,17 @@ def test_adam_recurrence_matches_torch():
         opt.step()
         pm, m, v = vfm_math.adam_update(pm, g, m, v, step, 0.05)
         np.testing.assert_allclose(pm, p.detach().numpy(), rtol=1e-12)
+
+
+def test_saved_weight_logits_golden_is_the_mean_of_the_snapshots():
+    """vfm-torch.py:179-185, 248-262: last_logits / mean_logits of the golden are the FM prediction from
+    the last / the averaged posterior-mean snapshots stored beside them (restated here in numpy)."""
+    meta, g = gu.load("sampled_saved_logits")
+    d, x = meta["d"], g["x_eval"].astype(np.int64)
+    snaps = [gu.state(g, f"step{t}.after") for t in range(meta["steps"])]
+    gb = [s["global_bias_mean"] for s in snaps]
+    mb = [s["bias_params.weight"][:, 0] for s in snaps]
+    me = [s["entity_params.weight"][:, :d] for s in snaps]
+    fm = lambda g0, b, e: g0 + b[x].sum(axis=1) + e[x].prod(axis=1).sum(axis=1)
+    np.testing.assert_allclose(fm(gb[-1], mb[-1], me[-1]), g["last_logits"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(fm(np.mean(gb, 0), np.mean(mb, 0), np.mean(me, 0)), g["mean_logits"], rtol=1e-5, atol=1e-6)

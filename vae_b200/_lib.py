@@ -27,6 +27,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 MAX_FIELDS = 8
 GAUSSIAN, BERNOULLI = 0, 1
 LINK_ABS, LINK_SOFTPLUS = 0, 1
+INTER_PROD, INTER_PAIRWISE = 0, 1
 ADAM_TOUCHED, GRAD_ONLY = 0, 1
 STATS = 32
 ST_RESID_S, ST_W0_S, MAX_SAMPLES = 8, 16, 8
@@ -43,7 +44,7 @@ class Config(C.Structure):
                 ("n_classes", C.c_int32), ("class_bound", C.c_int32 * MAX_FIELDS),
                 ("class_size", C.c_float * MAX_FIELDS), ("n_train", C.c_float),
                 ("row_stride", C.c_int32), ("seed", C.c_uint64), ("row_offset", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("interaction", C.c_int32)]
 
 
 class Tables(C.Structure):
@@ -131,6 +132,8 @@ SYMBOLS = {
     "vfmb_closed_forward": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), C.c_void_p]),
     "vfmb_closed_backward": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam),
                                        C.c_int32, C.c_void_p]),
+    "vfmb_closed_backward_weighted": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam),
+                                                C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "vfmb_predict_mean": (C.c_int, [_P(Config), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "vfmb_philox_normals": (C.c_int, [_P(Config), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,

@@ -21,6 +21,8 @@ struct ClosedCfg {
     int cls_bound[kMaxFields];
     float cls_size[kMaxFields];
     float n_train;
+    float data_scale;      // backward: d loss / d(-partial_loss); N_train / B for the script's loss (:571)
+    float kl0_scale;       // backward: weight of the global-bias KL term (1; 0 when the caller's autograd owns it)
     int off_pbm, off_pbs, off_pem, off_pes, n_scalars;   // offsets inside the scalar block
 };
 
@@ -40,7 +42,10 @@ k_cstage(ClosedCfg c, const float* __restrict__ bias, const float* __restrict__ 
          const float* __restrict__ z, float* __restrict__ vs2, float* __restrict__ as,
          float* __restrict__ b2s, float* __restrict__ cq, float* __restrict__ klb_out,
          float* __restrict__ kle_out, double* __restrict__ partials, int32_t* __restrict__ counter,
-         float* __restrict__ pg_part, int32_t* __restrict__ blk_class, float* __restrict__ stats) {
+         float* __restrict__ pg_part, int32_t* __restrict__ blk_class, float* __restrict__ stats,
+         const float* __restrict__ cq_in) {
+    // cq_in (optional, [U]): KL weight of every unique row supplied by the caller (the upstream gradient
+    // of the per-row KL terms under autograd) instead of c_u = cnt_b/cnt_train * G_g/Z_g (:574-587)
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW, RPB = 8 * CH;
     extern __shared__ float s_pg[];                      // [8 warps][2d+4]
     const int d = c.d, pgw = 2 * d + 4;
@@ -95,7 +100,7 @@ k_cstage(ClosedCfg c, const float* __restrict__ bias, const float* __restrict__ 
             b2s[ul] = ab.y * ab.y;
             klb = kl_normal(ab.x, tau, pbm, pbs);
             if (klb_out) klb_out[ul] = klb;
-            cqv = ((float)rec.w / tcnt) * csz_over_z;
+            cqv = cq_in ? __ldg(cq_in + ul) : ((float)rec.w / tcnt) * csz_over_z;
             cq[ul] = cqv;
             s0 += cqv;
             s1 = fmaf(cqv, ab.x, s1);
@@ -402,9 +407,9 @@ k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_
         }
         flush(cur);
         // the group storing the last partial of a cut row adds them in tile order (step_common.cuh)
-        if (head_open) finish_cut_row<VEC, LPR, NV, 3>(first_u, d, false, urec, gslot, vs2, grow, gws, arrive);
+        if (head_open) finish_cut_row<VEC, LPR, NV, 3>(first_u, tile, d, false, urec, gslot, vs2, grow, gws, arrive, n_tiles + 1);
         if (tail_open && !(head_open && last_u == first_u))
-            finish_cut_row<VEC, LPR, NV, 3>(last_u, d, false, urec, gslot, vs2, grow, gws, arrive);
+            finish_cut_row<VEC, LPR, NV, 3>(last_u, tile, d, false, urec, gslot, vs2, grow, gws, arrive, n_tiles + 1);
     }
 }
 
@@ -430,7 +435,7 @@ k_cadam(ClosedCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float
     }
     const float step_size = (MODE == VFMB_ADAM_TOUCHED) ? s_coef[0] : 0.f;
     const float inv_bc2 = (MODE == VFMB_ADAM_TOUCHED) ? s_coef[1] : 1.f;
-    const float kappa = c.n_train / (float)c.B * fabsf(scalars[VFMB_C_ALPHA]);
+    const float kappa = c.data_scale * fabsf(scalars[VFMB_C_ALPHA]);
 
     for (int base = gwarp * CH; base < U; base += nwarps * CH) {
         const int ul = base + lane;
@@ -560,8 +565,9 @@ k_cfinal(ClosedCfg c, float* __restrict__ scalars, float* __restrict__ sm, float
     const float alpha = scalars[VFMB_C_ALPHA], mu0 = scalars[VFMB_C_GB_MEAN], rho0 = scalars[VFMB_C_GB_SCALE];
     const float m0 = scalars[VFMB_C_GB_PRIOR_MEAN], s0r = scalars[VFMB_C_GB_PRIOR_SCALE];
     const float ap = fabsf(alpha), as0 = fabsf(s0r);
-    const double nb = (double)c.n_train / (double)c.B;
+    const double nb = (double)c.data_scale;
     const float kappa = (float)(nb * (double)ap);
+    const float k0 = c.kl0_scale;
     const double sum_d = (double)stats[VFMB_ST_SUM_RESID], sum_q = (double)stats[VFMB_ST_SUM_SQERR];
     auto sgn = [](float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); };
     // every scalar parameter gets its gradient from one thread (block-stride loop)
@@ -571,13 +577,13 @@ k_cfinal(ClosedCfg c, float* __restrict__ scalars, float* __restrict__ sm, float
         if (idx == VFMB_C_ALPHA) {
             g = -sgn(alpha) * (float)(nb * (0.5 * (double)c.B / (double)ap - 0.5 * sum_q));
         } else if (idx == VFMB_C_GB_MEAN) {
-            g = (float)(-(double)kappa * sum_d) + (mu0 - m0) / (as0 * as0);
+            g = (float)(-(double)kappa * sum_d) + k0 * (mu0 - m0) / (as0 * as0);
         } else if (idx == VFMB_C_GB_SCALE) {
-            g = kappa * (float)c.B * rho0 + sgn(rho0) * (fabsf(rho0) / (as0 * as0) - 1.f / fabsf(rho0));
+            g = kappa * (float)c.B * rho0 + k0 * sgn(rho0) * (fabsf(rho0) / (as0 * as0) - 1.f / fabsf(rho0));
         } else if (idx == VFMB_C_GB_PRIOR_MEAN) {
-            g = (m0 - mu0) / (as0 * as0);
+            g = k0 * (m0 - mu0) / (as0 * as0);
         } else if (idx == VFMB_C_GB_PRIOR_SCALE) {
-            g = sgn(s0r) * (1.f / as0 - (rho0 * rho0 + (mu0 - m0) * (mu0 - m0)) / (as0 * as0 * as0));
+            g = k0 * sgn(s0r) * (1.f / as0 - (rho0 * rho0 + (mu0 - m0) * (mu0 - m0)) / (as0 * as0 * as0));
         } else if (idx >= c.off_pbm && idx < c.off_pbm + G) {
             const int q = idx - c.off_pbm;
             const float m = scalars[idx], s = fabsf(scalars[c.off_pbs + q]);
@@ -624,18 +630,18 @@ k_cfinal(ClosedCfg c, float* __restrict__ scalars, float* __restrict__ sm, float
 // one lane group per sample; rows are read straight from the parameter table (means only)
 template <int VEC, int LPR, int NV>
 __global__ void __launch_bounds__(256)
-k_predict_mean(int B, int F, int d, int R, const float* __restrict__ bias, const float* __restrict__ entity,
+k_predict_mean(int B, int F, int d, int R, int pairwise, const float* __restrict__ bias, const float* __restrict__ entity,
                float global_bias, const int64_t* __restrict__ x, float* __restrict__ out) {
     constexpr int GPW = kWarp / LPR;
     const int lane = threadIdx.x & 31, gl = lane % LPR;
     const int group = (threadIdx.x >> 5) * GPW + lane / LPR;
     const int groups_per_block = (blockDim.x >> 5) * GPW;
     for (int n = blockIdx.x * groups_per_block + group; n < B; n += gridDim.x * groups_per_block) {
-        Vec<VEC> prod[NV];
+        Vec<VEC> prod[NV], ssum[NV], sq[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) prod[i].v[j] = 1.f;
+            for (int j = 0; j < VEC; ++j) { prod[i].v[j] = 1.f; ssum[i].v[j] = 0.f; sq[i].v[j] = 0.f; }
         float bsum = 0.f;
         for (int f = 0; f < F; ++f) {
             int64_t id = x[(size_t)n * F + f];
@@ -647,7 +653,11 @@ k_predict_mean(int B, int F, int d, int R, const float* __restrict__ bias, const
                 if (k < d) {
                     Vec<VEC> a = ld_vec_nc<VEC>(entity + id * 2 * d + k);
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) prod[i].v[j] *= a.v[j];
+                    for (int j = 0; j < VEC; ++j) {
+                        prod[i].v[j] *= a.v[j];
+                        ssum[i].v[j] += a.v[j];
+                        sq[i].v[j] = fmaf(a.v[j], a.v[j], sq[i].v[j]);
+                    }
                 }
             }
         }
@@ -657,7 +667,8 @@ k_predict_mean(int B, int F, int d, int R, const float* __restrict__ bias, const
             int k = (gl + i * LPR) * VEC;
             if (k < d)
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) part += prod[i].v[j];
+                for (int j = 0; j < VEC; ++j)
+                    part += pairwise ? 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]) : prod[i].v[j];
         }
         float inter = group_sum<LPR>(part, group_mask<LPR>());
         if (gl == 0) out[n] = global_bias + bsum + inter;
@@ -694,7 +705,8 @@ extern "C" int vfmb_predict_mean(const vfmb_config* cfg, const float* bias, cons
     if (g > kMaxGrid) g = kMaxGrid;
     VFMB_LAYOUT_SWITCH3(L, {
         k_predict_mean<VEC, LPR, NV><<<(int)g, 256, 0, counted((cudaStream_t)stream_)>>>(
-            cfg->B, cfg->F, cfg->d, cfg->R, bias, entity, global_bias, x, out);
+            cfg->B, cfg->F, cfg->d, cfg->R, (cfg->interaction == VFMB_INTER_PAIRWISE && cfg->F != 2) ? 1 : 0, bias, entity,
+            global_bias, x, out);
     });
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -716,6 +728,7 @@ static int closed_check(const vfmb_config* cfg, const vfmb_tables* tab, const vf
 static ClosedCfg make_closed(const vfmb_config* cfg) {
     ClosedCfg c{};
     c.B = cfg->B; c.F = cfg->F; c.d = cfg->d; c.n_train = cfg->n_train;
+    c.data_scale = cfg->n_train / (float)cfg->B; c.kl0_scale = 1.f;
     for (int i = 0; i < kMaxFields; ++i) { c.cls_bound[i] = cfg->class_bound[i]; c.cls_size[i] = cfg->class_size[i]; }
     c.off_pbm = vfmb_closed_off_bias_prior_mean(cfg->F, cfg->d, 0);
     c.off_pbs = vfmb_closed_off_bias_prior_scale(cfg->F, cfg->d, 0);
@@ -750,7 +763,7 @@ extern "C" int vfmb_closed_forward(const vfmb_config* cfg, const vfmb_tables* ta
         k_cstage<VEC, LPR, NV><<<nblk, 256, smem, counted(stream)>>>(
             cc, tab->bias, tab->entity, tab->train_counts, tab->scalars, plan->urec, plan->class_off, plan->z,
             io->vs, io->ws, io->ebs, io->cq, io->kl_bias_out, io->kl_entity_out, io->partials,
-            io->counters + 0, pg_part, blk_class, io->stats);
+            io->counters + 0, pg_part, blk_class, io->stats, nullptr);
         k_cscore<VEC, LPR, NV><<<grid_b, 256, 0, counted(stream)>>>(
             cc, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->ebs, io->y, io->pred,
             io->resid, io->rsorted, io->msg, io->partials, io->counters + 1, io->stats);
@@ -764,6 +777,14 @@ extern "C" int vfmb_closed_forward(const vfmb_config* cfg, const vfmb_tables* ta
 extern "C" int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                                     const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
                                     vfmb_stream stream_) {
+    if (!cfg) return set_error(VFMB_EINVAL, "vfmb_closed_backward: null argument");
+    return vfmb_closed_backward_weighted(cfg, tab, plan, io, adam, mode, nullptr, cfg->n_train / (float)cfg->B, 1.f, stream_);
+}
+
+extern "C" int vfmb_closed_backward_weighted(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
+                                             const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode,
+                                             const float* kl_weight, float data_scale, float kl0_scale,
+                                             vfmb_stream stream_) {
     int rc = closed_check(cfg, tab, plan, io, "vfmb_closed_backward");
     if (rc) return rc;
     if (mode == VFMB_ADAM_TOUCHED && (!adam || !tab->entity_m || !tab->entity_v || !tab->bias_m || !tab->bias_v ||
@@ -780,6 +801,7 @@ extern "C" int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* t
     rc = vfmb_plan_capacity(cfg->B, cfg->F, cfg->R, &cap);
     if (rc) return rc;
     ClosedCfg cc = make_closed(cfg);
+    cc.data_scale = data_scale; cc.kl0_scale = kl0_scale;
     AdamDev h = make_adam(adam);
     const ScratchMap sm = scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap);
     float* fbase = (float*)io->partials;
@@ -791,12 +813,26 @@ extern "C" int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* t
     int nblk = (int)(cap.u_cap / (8 * ch)) + cfg->F + 1;
     if (nblk > sm.nblk_max) nblk = sm.nblk_max;
     const int grid_u = grid_warps(cap.u_cap, ch), grid_t = grid_warps(cap.n_tiles, 32 / L.lpr);
+    if (kl_weight) {
+        // caller-supplied per-row KL weights: redo the per-row pass of the forward with them (KL weights,
+        // per-group sums behind the prior-parameter gradients); the staged rows are rewritten unchanged
+        const size_t smem = (size_t)8 * (2 * cfg->d + 4) * sizeof(float);
+        VFMB_LAYOUT_SWITCH(L, {
+            k_cstage<VEC, LPR, NV><<<nblk, 256, smem, counted(stream)>>>(
+                cc, tab->bias, tab->entity, tab->train_counts, tab->scalars, plan->urec, plan->class_off, plan->z,
+                io->vs, io->ws, io->ebs, io->cq, nullptr, nullptr, io->partials, io->counters + 0, pg_part,
+                blk_class, io->stats, kl_weight);
+        });
+    }
     int32_t* arrive = (int32_t*)(fbase + sm.arrive_off);
     VFMB_LAYOUT_SWITCH(L, {
         k_cgather<VEC, LPR, NV><<<grid_t, 256, 0, counted(stream)>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
                                                             plan->pos_rank, plan->urec, io->vs, io->msg, io->rsorted,
                                                             gslot, io->grow, io->gws, arrive);
     });
+    cudaEvent_t ev0, ev1;                                   // measurement hook (vfmb_profile_events)
+    profile_events(&ev0, &ev1);
+    if (ev0 && ev1) cudaEventRecord(ev0, stream);
     VFMB_LAYOUT_SWITCH(L, {
         if (mode == VFMB_ADAM_TOUCHED)
             k_cadam<VEC, LPR, NV, VFMB_ADAM_TOUCHED><<<grid_u, 256, 0, counted(stream)>>>(
@@ -807,6 +843,7 @@ extern "C" int vfmb_closed_backward(const vfmb_config* cfg, const vfmb_tables* t
                 cc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v, tab->scalars,
                 plan->urec, plan->meta, io->cq, io->grow, io->gws, h, tab->adam_step, io->grad_bias, io->grad_entity);
     });
+    if (ev0 && ev1) cudaEventRecord(ev1, stream);
     const int items = cfg->F * (2 * cfg->d + 3);
     const int grid_f = (items + 7) / 8;
     if (mode == VFMB_ADAM_TOUCHED)

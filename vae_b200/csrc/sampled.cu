@@ -18,6 +18,10 @@
 // Host side: launch_* (internal) and the extern "C" entry points at the end of the file.
 #include "sampled_common.cuh"
 
+#ifndef VFMB_SCORE_HOIST
+#define VFMB_SCORE_HOIST 1          // k_score, F == 2: fetch the row pairs of all rounds before the dot products
+#endif
+
 namespace vfmb {
 
 // ------------------------------------------------------------------------------- k_stage
@@ -183,21 +187,40 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         float inter_l = 0.f;
         // ---- wide work: interaction of GPW samples per round
         if (F == 2) {
+            // the row pairs of all rounds are fetched up front (2 * kRounds * NV independent 128-bit loads
+            // per lane): the kernel is bound by L2 latency, not by registers
+            constexpr int HR = VFMB_SCORE_HOIST ? kRounds : 1;
+            Vec<VEC> ra[HR][NV], rb[HR][NV];
+#if VFMB_SCORE_HOIST
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int it = 0; it < kRounds; ++it) {
                 const int sel = it * GPW + gidx;
                 const int r0 = bcast(rr.x, sel), r1 = bcast(rr.y, sel);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    int k = (gl + i * LPR) * VEC;
+                    if (k < d && base + sel < B) {
+                        ra[it % HR][i] = ld_vec_nc<VEC>(vs + (size_t)r0 * d + k);
+                        rb[it % HR][i] = ld_vec_nc<VEC>(vs + (size_t)r1 * d + k);
+                    }
+                }
+#if VFMB_SCORE_HOIST
+            }
+#pragma unroll
+            for (int it = 0; it < kRounds; ++it) {
+                const int sel = it * GPW + gidx;
+#endif
                 float part = 0.f;
                 if (base + sel < B) {
 #pragma unroll
                     for (int i = 0; i < NV; ++i) {
                         int k = (gl + i * LPR) * VEC;
-                        if (k < d) {
-                            const Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r0 * d + k);
-                            const Vec<VEC> b = ld_vec_nc<VEC>(vs + (size_t)r1 * d + k);
+                        if (k < d)
 #pragma unroll
-                            for (int j = 0; j < VEC; ++j) part = fmaf(a.v[j], b.v[j], part);
-                        }
+                            for (int j = 0; j < VEC; ++j) part = fmaf(ra[it % HR][i].v[j], rb[it % HR][i].v[j], part);
                     }
                 }
                 part = group_sum<LPR>(part, gmask);
@@ -547,9 +570,9 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
         }
         flush(cur);
         // rows cut by this tile's boundaries (at most two): whoever stores the last partial finishes the row
-        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, d, F > 2, urec, gslot, vs, grow, gws, arrive);
+        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, F > 2, urec, gslot, vs, grow, gws, arrive, n_tiles + 1);
         if (tail_open && !(head_open && last_u == first_u))
-            finish_cut_row<VEC, LPR, NV, 1>(last_u, d, F > 2, urec, gslot, vs, grow, gws, arrive);
+            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, F > 2, urec, gslot, vs, grow, gws, arrive, n_tiles + 1);
     }
 }
 
@@ -562,7 +585,7 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
 // occurrence of field 0 writes the sample's outputs and its likelihood terms.  Saves a launch, the
 // residual round trip through memory and one of the two passes over the sampled rows.
 template <int VEC, int LPR, int NV, int LINK, int LIK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__ partner,
                const int32_t* __restrict__ pos_rank, const int32_t* __restrict__ occ,
                const int32_t* __restrict__ urec, int32_t* arrive,
@@ -695,9 +718,9 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
             }
         }
         flush(cur);
-        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, d, false, urec, gslot, vs, grow, gws, arrive);
+        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, false, urec, gslot, vs, grow, gws, arrive, n_tiles + 1);
         if (tail_open && !(head_open && last_u == first_u))
-            finish_cut_row<VEC, LPR, NV, 1>(last_u, d, false, urec, gslot, vs, grow, gws, arrive);
+            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, false, urec, gslot, vs, grow, gws, arrive, n_tiles + 1);
     }
     if (block_partials<3>(acc3, partials, counter)) {
         double tot[3];

@@ -158,32 +158,25 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g,
 // The backward's segmented reduction (k_gather / k_gather_score / k_cgather) walks the sorted
 // occurrence list in tiles of kTile positions.  A row cut by tile boundaries leaves one partial per
 // tile it touches: in the tail slot of its first tile, in the head slots of the following ones.
-// The lane group that stores the LAST of a row's partials (per-row arrival counter, indexed by the
-// row's first tile: a tile boundary cuts at most one row) adds them in tile order -- tail(tA),
-// head(tA+1), ..., head(tB) -- so the association is fixed by the plan and the result is bitwise
-// reproducible whichever group happens to finish.  This replaces the separate combine launch of
-// round 1 (12 us of pure latency on the ml20m step).  NW = d-wide sections per slot (1: sampled
-// step; 3: closed form [A | Bq | C]).  A Zipf head row with thousands of occurrences spans a few
-// hundred tiles: its finisher streams the slots from L2 with UNR loads in flight.
+// The lane group that stores the LAST partial adds them -- no separate combine launch (12 us of
+// pure latency on the ml20m step in round 1).  To keep that serial sum short for a Zipf head row
+// (thousands of occurrences = hundreds of tiles) it is a two-level tree with a fixed shape:
+//   level 1  the row's partials in runs of kFan consecutive tiles; the group that completes a run
+//            (arrival counter of the run, indexed by its first tile: a tile boundary cuts at most
+//            one row, so (tile, head/tail) names a run) adds the run's slots in tile order;
+//   level 2  a row with more than kFan partials: the run sums are written back to the first slot
+//            of each run, and the group that completes the last run adds them in run order.
+// The association is fixed by the plan (tile order inside a run, run order across), so the result
+// is bitwise reproducible whichever groups happen to finish.  NW = d-wide sections per slot
+// (1: sampled step; 3: closed form [A | Bq | C]).  arrive: int32 [3 * n_tiles1], zero between steps
+// (every counter is reset by the group that completes it).
+constexpr int kFan = 32;
+
 template <int VEC, int LPR, int NV, int NW>
-__device__ __forceinline__ void finish_cut_row(int u, int d, bool own_fix, const int32_t* __restrict__ urec,
-                                            const float* gslot, const float* __restrict__ vs,
-                                            float* __restrict__ grow, float* __restrict__ gws, int32_t* arrive) {
+__device__ __forceinline__ void sum_slots(const float* gslot, int dp, int d, int gl, int t_first, bool first_is_tail,
+                                          int count, int stride, Vec<VEC> (&tot)[NW][NV], float& gw) {
     constexpr int UNR = (NW == 1) ? (NV == 1 ? 4 : 2) : 1;
-    const int lane = threadIdx.x & 31, gl = lane % LPR;
-    const unsigned gmask = group_mask<LPR>();
-    const int dp = NW * d + 4;
-    __threadfence();                                        // this group's partial is visible ...
-    __syncwarp(gmask);
-    const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
-    const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;
-    int old = 0;
-    if (gl == 0) old = atomicAdd(arrive + tA, 1);           // ... before it is counted
-    old = __shfl_sync(gmask, old, 0, LPR);
-    if (old != tB - tA) return;                             // tB - tA + 1 partials; the last one finishes
-    __threadfence();
-    const float* tp = gslot + ((size_t)tA * 2 + 1) * dp;    // tail slot of the first tile
-    Vec<VEC> tot[NW][NV];
+    const float* tp = gslot + ((size_t)t_first * 2 + (first_is_tail ? 1 : 0)) * dp;
 #pragma unroll
     for (int w = 0; w < NW; ++w)
 #pragma unroll
@@ -191,12 +184,12 @@ __device__ __forceinline__ void finish_cut_row(int u, int d, bool own_fix, const
             const int k = (gl + i * LPR) * VEC;
             if (k < d) tot[w][i] = ld_vec_cg<VEC>(tp + w * d + k);
         }
-    float gw = __ldcg(tp + NW * d);
-    for (int t = tA + 1; t <= tB; t += UNR) {
+    gw = __ldcg(tp + NW * d);
+    for (int q0 = 1; q0 < count; q0 += UNR) {
         Vec<VEC> part[UNR][NW][NV]; float pw[UNR];
 #pragma unroll
         for (int q = 0; q < UNR; ++q) {
-            const float* sp = gslot + ((size_t)min(t + q, tB) * 2) * dp;
+            const float* sp = gslot + ((size_t)(t_first + min(q0 + q, count - 1) * stride) * 2) * dp;   // head slots
 #pragma unroll
             for (int w = 0; w < NW; ++w)
 #pragma unroll
@@ -208,7 +201,7 @@ __device__ __forceinline__ void finish_cut_row(int u, int d, bool own_fix, const
         }
 #pragma unroll
         for (int q = 0; q < UNR; ++q)
-            if (t + q <= tB) {
+            if (q0 + q < count) {
 #pragma unroll
                 for (int w = 0; w < NW; ++w)
 #pragma unroll
@@ -217,6 +210,52 @@ __device__ __forceinline__ void finish_cut_row(int u, int d, bool own_fix, const
                         for (int j = 0; j < VEC; ++j) tot[w][i].v[j] += part[q][w][i].v[j];
                 gw += pw[q];
             }
+    }
+}
+
+// called by every lane of a group after it stored the partial of cut row u for `tile`
+template <int VEC, int LPR, int NV, int NW>
+__device__ __noinline__ void finish_cut_row(int u, int tile, int d, bool own_fix, const int32_t* __restrict__ urec,
+                                               float* gslot, const float* __restrict__ vs, float* __restrict__ grow,
+                                               float* __restrict__ gws, int32_t* arrive, int n_tiles1) {
+    const int lane = threadIdx.x & 31, gl = lane % LPR;
+    const unsigned gmask = group_mask<LPR>();
+    const int dp = NW * d + 4;
+    __threadfence();                                        // this group's partial is visible ...
+    __syncwarp(gmask);
+    const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
+    const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;
+    const int run = (tile - tA) / kFan;
+    const int first = tA + run * kFan, last = min(tB, first + kFan - 1);
+    int32_t* c1 = arrive + 2 * first + (run == 0 ? 1 : 0);
+    int old = 0;
+    if (gl == 0) old = atomicAdd(c1, 1);                    // ... before it is counted
+    old = __shfl_sync(gmask, old, 0, LPR);
+    if (old != last - first) return;                        // the group that completes the run goes on
+    __threadfence();
+    Vec<VEC> tot[NW][NV]; float gw;
+    sum_slots<VEC, LPR, NV, NW>(gslot, dp, d, gl, first, run == 0, last - first + 1, 1, tot, gw);
+    if (gl == 0) *c1 = 0;                                   // counter ready for the next step
+    if (tB - tA >= kFan) {                                  // more than one run: second level
+        float* sp = gslot + ((size_t)first * 2 + (run == 0 ? 1 : 0)) * dp;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int k = (gl + i * LPR) * VEC;
+                if (k < d) st_vec<VEC>(sp + w * d + k, tot[w][i]);
+            }
+        if (gl == 0) sp[NW * d] = gw;
+        __threadfence();
+        __syncwarp(gmask);
+        int32_t* c2 = arrive + 2 * n_tiles1 + tA;
+        const int n_runs = (tB - tA) / kFan + 1;
+        if (gl == 0) old = atomicAdd(c2, 1);
+        old = __shfl_sync(gmask, old, 0, LPR);
+        if (old != n_runs - 1) return;
+        __threadfence();
+        sum_slots<VEC, LPR, NV, NW>(gslot, dp, d, gl, tA, true, n_runs, kFan, tot, gw);
+        if (gl == 0) *c2 = 0;
     }
 #pragma unroll
     for (int w = 0; w < NW; ++w)
@@ -232,7 +271,7 @@ __device__ __forceinline__ void finish_cut_row(int u, int d, bool own_fix, const
                 st_vec<VEC>(grow + (size_t)u * NW * d + w * d + k, tot[w][i]);
             }
         }
-    if (gl == 0) { gws[u] = gw; arrive[tA] = 0; }           // counter ready for the next step
+    if (gl == 0) gws[u] = gw;
 }
 
 
@@ -270,8 +309,8 @@ static inline ScratchMap scratch_map(int B, int F, int d, int64_t u_cap) {
     m.pg_part_off = off;      off += (size_t)m.nblk_max * m.pg_width;
     m.pg_sum_off = off;       off += (size_t)kMaxFields * m.pg_width;
     m.blk_class_off = off;    off += (size_t)m.nblk_max + 16;
-    m.arrive_off = off;       off += (size_t)slots / 2 + 16;   // per-tile arrival counters of the cut rows (int32,
-                                                              // zero-initialised with the buffer, self-resetting)
+    m.arrive_off = off;       off += 3 * ((size_t)slots / 2) + 16;   // arrival counters of the cut rows (int32 [3][n_tiles
+                                                                    // + 1], zero-initialised with the buffer, self-resetting)
     m.total_doubles = (off + 1) / 2;
     return m;
 }

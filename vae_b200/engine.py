@@ -343,8 +343,10 @@ class StepResult:
         return ["loss", "kl", "nll_mean", "pred", "logits", "stats"]
 
 
-def make_config(B, F, d, R, S, likelihood, link, class_bounds, class_sizes, n_train, seed) -> L.Config:
+def make_config(B, F, d, R, S, likelihood, link, class_bounds, class_sizes, n_train, seed,
+                interaction: str = "prod") -> L.Config:
     cfg = L.Config()
+    cfg.interaction = {"prod": L.INTER_PROD, "pairwise": L.INTER_PAIRWISE}[interaction]
     cfg.B, cfg.F, cfg.d, cfg.R, cfg.S = int(B), int(F), int(d), int(R), int(S)
     cfg.likelihood = L.GAUSSIAN if likelihood == "reg" else L.BERNOULLI
     cfg.link = {"abs": L.LINK_ABS, "softplus": L.LINK_SOFTPLUS}[link]

@@ -91,9 +91,27 @@ def make_ids(field_sizes: Sequence[int], exponents: Sequence[float], n_rows: int
     return np.stack(cols, axis=1).astype(np.int64)
 
 
+def _fraction_workload() -> Workload:
+    """BASELINE config 1: the reference's bundled fixture ``data/fraction/data.csv`` (536 students x 20
+    items, binary outcome; SURVEY N13: X = [user, 536 + item], seeded 80/20 split, full batch).  The
+    training split travels as the inputs of the committed golden ``tests/golden/sampled_fraction.npz``
+    (written by ``oracle/gen_golden.py`` from the reference's file), so nothing outside the repo is read."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                        "sampled_fraction.npz")
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    x, y = z["x"].astype(np.int64), z["y"].astype(np.float32)
+    return Workload("fraction", [meta["N"], meta["M"]], meta["d"], len(x), x, y, len(x), "class", "sampled",
+                    "prod", [0, meta["N"]])
+
+
 def make_workload(name: str, n_rows: int | None = None, seed: int = DATA_SEED) -> Workload:
     """Named BASELINE.json configurations (sizes in SURVEY.md section 8a/8d)."""
     rng_y = np.random.default_rng(seed + 1)
+    if name == "fraction":          # config 1 (real fixture, full batch)
+        return _fraction_workload()
     if name == "ml100k":            # config 2
         fs, ex, d, B, R, frac = [943, 1682], [0.5, 1.0], 20, 8000, 100_000, 0.8
         variant, output, inter = "closed", "reg", "prod"

@@ -11,11 +11,14 @@ Same parameter names / shapes / ``[mean | raw scale]`` row layout and the same s
 initialisation order (:194-260).  ``entity_count`` (``bincount(X_train)``, :182) and ``N_train``
 are constructor arguments instead of module globals.
 
-``forward`` evaluates the same quantities with the CUDA kernels (values only -- it is the
-evaluation path of the reference, :664-678).  Training goes through ``fused_step(x, y)``: plan,
-forward, backward and Adam on the touched rows on the device, including the gradients of the
-prior parameters.  ``gradients(x, y)`` returns what ``loss.backward()`` leaves in ``.grad``.
-No CPU fallback.
+``forward`` evaluates the same quantities with the CUDA kernels.  Under autograd (grad mode on and
+``closed_form_loss=True``) it is differentiable, so the reference's own loop (:548-594: ``model(...)``,
+the loss expression, ``loss.backward()``, ``torch.optim.Adam.step()``) runs unchanged on this module:
+``partial_loss`` and the per-row KL terms ``kls[1]``, ``kls[2]`` come from a ``torch.autograd.Function``
+whose backward runs the CUDA backward with the upstream gradients; ``kls[0]`` is differentiated by
+torch.  The fast path is ``fused_step(x, y)``: plan, forward, backward and Adam on the touched rows on
+the device, including the gradients of the prior parameters.  ``gradients(x, y)`` returns what
+``loss.backward()`` leaves in ``.grad``.  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -27,8 +30,58 @@ import torch
 from torch import distributions, nn
 
 from . import _lib as L
-from .engine import (BatchPlan, PlanPipeline, StepBuffers, StepResult, current_stream, make_config,
+from .engine import (BatchPlan, GraphedLoop, PlanPipeline, StepBuffers, StepResult, current_stream, make_config,
                      require_cuda)
+
+
+class _ClosedFn(torch.autograd.Function):
+    """(pred, partial_loss, kls[1], kls[2]) = f(bias_params, entity_params, scalar parameters).
+
+    Forward = vfmb_closed_forward; backward = vfmb_closed_backward_weighted in gradient-only mode with
+    the upstream gradients: d loss / d partial_loss and the per-row weights of the KL terms.  The KL
+    weights must be uniform along a row and shared by kls[1][u] and kls[2][u, :] -- the structure of
+    both loss expressions of the script (:569-588: ``(kls[1] + kls[2].sum(axis=1)) * w``); anything else
+    poisons the gradients with NaN rather than returning wrong numbers."""
+
+    @staticmethod
+    def forward(ctx, model, raw, y, n_unique, bias_params, entity_params, *scalar_params):
+        klb = torch.empty(n_unique, dtype=torch.float32, device=model.device)
+        kle = torch.empty(n_unique, model.d, dtype=torch.float32, device=model.device)
+        model._run_forward(raw, y, kl_out=(klb, kle))
+        B = model._cfg.B
+        pred = model._buf.pred[:B].clone()
+        partial = model._buf.stats[L.ST_NLL_MEAN].clone()
+        ctx.model = model
+        ctx.mark_non_differentiable(pred)
+        return pred, partial, klb, kle
+
+    @staticmethod
+    def backward(ctx, g_pred, g_partial, g_klb, g_kle):
+        model = ctx.model
+        if (g_klb is None) != (g_kle is None):
+            raise RuntimeError("vae_b200.vfm_tomasrch: the loss must weight kls[1] and kls[2] together "
+                               "(vfm-tomasrch.py:569-588)")
+        U = model._io_n_unique
+        if g_klb is None:
+            w = torch.zeros(U, dtype=torch.float32, device=model.device)
+            bad = torch.zeros((), dtype=torch.bool, device=model.device)
+        else:
+            w = g_klb.to(torch.float32).contiguous()
+            spread = (g_kle.to(torch.float32) - w[:, None]).abs().max()
+            bad = spread > 1e-6 * w.abs().max().clamp_min(1e-30)
+        scale = 0.0 if g_partial is None else -float(g_partial.item())
+        g_bias = torch.zeros_like(model.bias_params.data)
+        g_entity = torch.zeros_like(model.entity_params.data)
+        model._io.grad_bias, model._io.grad_entity = L.ptr(g_bias), L.ptr(g_entity)
+        L.check(L.lib().vfmb_closed_backward_weighted(
+            C.byref(model._cfg), C.byref(model._tables()), C.byref(model._plan.struct), C.byref(model._io),
+            C.byref(model.adam), L.GRAD_ONLY, w.data_ptr(), scale, 0.0, current_stream(model.device)),
+            "vfmb_closed_backward_weighted")
+        model._pipe.release(model._plan)
+        poison = torch.where(bad, torch.full((), float("nan"), device=model.device), torch.ones((), device=model.device))
+        gs = model._buf.grad_scalars
+        outs = [(gs[off:off + p.numel()] * poison).reshape(p.shape) for p, off in model._scalar_params()]
+        return (None, None, None, None, g_bias * poison, g_entity * poison, *outs)
 
 
 class CF(nn.Module):
@@ -204,6 +257,25 @@ class CF(nn.Module):
             self._pipe.release(self._plan)
         return StepResult(self._buf, self._cfg.B)
 
+    def graphed_loop(self, B: int, depth: int = 2) -> GraphedLoop:
+        """CUDA-graph replay of the training loop for batches of exactly ``B`` samples (the step on
+        batch i and the plan of batch i+1 captured once): the ML-100K-sized step is launch-bound, so the
+        host launch overhead is what the eager loop measures.  See engine.GraphedLoop."""
+        self._ensure(B)
+        self._sync_scalars()
+
+        def step_fn(plan, y, outs):
+            self._cfg, self._plan = self._config(B), plan
+            io = self._buf.io(y=y)
+            io.pred, io.mean, io.stats = L.ptr(outs.pred), L.ptr(outs.mean), L.ptr(outs.stats)
+            self._graph_io = getattr(self, "_graph_io", []) + [io]      # keep the structs alive
+            tab, s = self._tables(), current_stream(self.device)
+            L.check(L.lib().vfmb_closed_forward(C.byref(self._cfg), C.byref(tab), C.byref(plan.struct), C.byref(io), s),
+                    "vfmb_closed_forward")
+            L.check(L.lib().vfmb_closed_backward(C.byref(self._cfg), C.byref(tab), C.byref(plan.struct), C.byref(io),
+                                                 C.byref(self.adam), L.ADAM_TOUCHED, s), "vfmb_closed_backward")
+        return GraphedLoop(self, B, step_fn, depth)
+
     @torch.no_grad()
     def gradients(self, x: torch.Tensor, y: torch.Tensor) -> dict:
         """Dense gradients of the step loss, keyed like ``named_parameters()``."""
@@ -226,30 +298,40 @@ class CF(nn.Module):
             out[f"scale_group_entity_prior.{g}"] = gs[o["pes"] + g * d: o["pes"] + (g + 1) * d].clone()
         return out
 
-    # ------------------------------------------------------------------ reference API (values only)
-    @torch.no_grad()
+    # ------------------------------------------------------------------ reference API
     def forward(self, x: List[torch.Tensor], x_unique: List[torch.Tensor], closed_form_loss: bool = False,
                 target=False):
         """``(likelihood, kls[, partial_loss])`` as vfm-tomasrch.py:323-453, from the per-group
         inverse indices ``x`` and unique lists ``x_unique`` the script's loop builds (:536-545).
-        Values only (no autograd graph): this is the reference's evaluation path (:664-678)."""
-        raw = torch.stack([x_unique[g].to(self.device)[x[g].to(self.device)] for g in range(self.G)], dim=1)
+        With grad mode on and ``closed_form_loss=True`` the outputs carry gradients (training loop,
+        :548-594); otherwise values only (the evaluation path, :664-678)."""
+        raw = torch.stack([x_unique[g].to(self.device)[x[g].to(self.device)] for g in range(self.G)], dim=1).contiguous()
         U = sum(int(len(u)) for u in x_unique)
-        klb = torch.empty(U, dtype=torch.float32, device=self.device)
-        kle = torch.empty(U, self.d, dtype=torch.float32, device=self.device)
-        y = target if closed_form_loss else None
-        self._run_forward(raw.contiguous(), y, kl_out=(klb, kle))
-        self._pipe.release(self._plan)
-        B = self._cfg.B
-        pred = self._buf.pred[:B].clone()
-        likelihood = distributions.normal.Normal(pred, torch.sqrt(1 / torch.abs(self.alpha.detach())))
-        q0 = distributions.normal.Normal(self.mean_global_bias.detach(), torch.abs(self.scale_global_bias.detach()))
-        p0 = distributions.normal.Normal(self.mean_global_bias_prior.detach(),
-                                         torch.abs(self.scale_global_bias_prior.detach()))
-        kls = [distributions.kl.kl_divergence(q0, p0), klb, kle]
-        if closed_form_loss:
-            return likelihood, kls, self._buf.stats[L.ST_NLL_MEAN].clone()
-        return likelihood, kls
+        self._io_n_unique = U
+        absl = torch.abs
+        if torch.is_grad_enabled() and closed_form_loss:
+            pred, partial, klb, kle = _ClosedFn.apply(self, raw, target, U, self.bias_params, self.entity_params,
+                                                      *[p for p, _ in self._scalar_params()])
+            likelihood = distributions.normal.Normal(pred, torch.sqrt(1 / absl(self.alpha)))
+            q0 = distributions.normal.Normal(self.mean_global_bias, absl(self.scale_global_bias))
+            p0 = distributions.normal.Normal(self.mean_global_bias_prior, absl(self.scale_global_bias_prior))
+            return likelihood, [distributions.kl.kl_divergence(q0, p0), klb, kle], partial
+        with torch.no_grad():
+            klb = torch.empty(U, dtype=torch.float32, device=self.device)
+            kle = torch.empty(U, self.d, dtype=torch.float32, device=self.device)
+            y = target if closed_form_loss else None
+            self._run_forward(raw, y, kl_out=(klb, kle))
+            self._pipe.release(self._plan)
+            B = self._cfg.B
+            pred = self._buf.pred[:B].clone()
+            likelihood = distributions.normal.Normal(pred, torch.sqrt(1 / absl(self.alpha.detach())))
+            q0 = distributions.normal.Normal(self.mean_global_bias.detach(), absl(self.scale_global_bias.detach()))
+            p0 = distributions.normal.Normal(self.mean_global_bias_prior.detach(),
+                                             absl(self.scale_global_bias_prior.detach()))
+            kls = [distributions.kl.kl_divergence(q0, p0), klb, kle]
+            if closed_form_loss:
+                return likelihood, kls, self._buf.stats[L.ST_NLL_MEAN].clone()
+            return likelihood, kls
 
     @torch.no_grad()
     def predict(self, x: torch.Tensor, bounds=None) -> torch.Tensor:

@@ -75,7 +75,7 @@ class CF(nn.Module):
     def __init__(self, embedding_size: int, output: str = "reg", *, n_users: int, n_items: int,
                  train_counts: torch.Tensor, n_var_samples: int = 1, link: str = "abs",
                  field_sizes: Optional[Sequence[int]] = None, kl_weighting: str = "torch",
-                 n_train: Optional[int] = None, max_batch: int = 65536, seed: int = 7,
+                 interaction: Optional[str] = None, n_train: Optional[int] = None, max_batch: int = 65536, seed: int = 7,
                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, device="cuda"):
         super().__init__()
         device = require_cuda(device)
@@ -86,6 +86,11 @@ class CF(nn.Module):
         self.F = len(self.field_sizes)
         self.R = int(sum(self.field_sizes))
         self.kl_weighting = kl_weighting
+        # factor interaction of the deterministic predictions (last_logits / mean_logits / predict_mean):
+        # the scripts' `prod(axis)` for two fields; for F > 2 the sampled step optimises the pairwise FM
+        # (SURVEY N6), so the mean prediction must evaluate that same model unless asked otherwise
+        self.interaction = interaction if interaction is not None else ("prod" if self.F == 2 else "pairwise")
+        assert self.interaction in ("prod", "pairwise")
         self.seed, self.max_batch = int(seed), int(max_batch)
         self.adam = L.Adam(lr, betas[0], betas[1], eps)
         if kl_weighting == "torch":                         # vfm-torch.py:316, `uniq <= N`
@@ -164,7 +169,7 @@ class CF(nn.Module):
         cfg = self._cfg_cache.get(B)
         if cfg is None:
             cfg = make_config(B, self.F, self.d, self.R, self.S, self.output, self.link_name,
-                              self._class_bounds, self._class_sizes, self.n_train, self.seed)
+                              self._class_bounds, self._class_sizes, self.n_train, self.seed, self.interaction)
             self._cfg_cache[B] = cfg
         return cfg
 
