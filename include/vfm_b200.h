@@ -359,7 +359,7 @@ int vfmb_set_grid_reserve(int blocks_per_sm);
 /* Other process-wide launch knobs (host side only; results never depend on them -- every variant
  * is bitwise identical, tests/test_gpu_sampled.py): key = "grid_reserve" (as above), "fuse_score"
  * (-1 auto / 0 / 1: score the samples inside the backward's segmented reduction when F == 2),
- * "adam_reserve" (0 / 1), "prefetch_mv" (bit mask: which earlier phase of the fused step pulls the
+ * "adam_reserve" (0 / 1), "adam_pipe" (1 / 0: cp.async-pipelined or register-staged row update), "prefetch_mv" (bit mask: which earlier phase of the fused step pulls the
  * Adam moments of the touched rows into L2 ahead of the row update). */
 int vfmb_set_tuning(const char* key, int value);
 

@@ -165,14 +165,18 @@ def test_reference_forward_signature_values():
     port = vfm_port.ClosedPort(meta["d"], fs, alpha_0=meta["alpha_0"])
     gu.load_state(port, gu.state(g, "init"))
     lik, pkls, ppart, _ = port(xt, torch.from_numpy(y))
-    np.testing.assert_allclose(likelihood.mean.cpu().numpy(), lik.mean.detach().numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(likelihood.mean.detach().cpu().numpy(), lik.mean.detach().numpy(), rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(partial.item(), ppart.item(), rtol=1e-5)
-    np.testing.assert_allclose(kls[0].cpu().numpy(), pkls[0].detach().numpy(), rtol=1e-5)
-    np.testing.assert_allclose(kls[1].cpu().numpy(), pkls[1].detach().numpy(), rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(kls[2].cpu().numpy(), pkls[2].detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(kls[0].detach().cpu().numpy(), pkls[0].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(kls[1].detach().cpu().numpy(), pkls[1].detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(kls[2].detach().cpu().numpy(), pkls[2].detach().numpy(), rtol=1e-5, atol=1e-6)
+    assert kls[1].requires_grad and kls[2].requires_grad and partial.requires_grad   # training outputs carry gradients
+    with torch.no_grad():                                                            # evaluation path: values only
+        lik_ng, kls_ng, part_ng = m(inverse, present, closed_form_loss=True, target=torch.from_numpy(y))
+    assert torch.equal(lik_ng.mean, likelihood.mean.detach()) and torch.equal(kls_ng[2], kls[2].detach())
     likelihood2, kls2 = m(inverse, present)
-    assert torch.equal(likelihood2.mean, likelihood.mean)
-    np.testing.assert_allclose(m.predict(xt).cpu().numpy(), likelihood.mean.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    assert torch.equal(likelihood2.mean, likelihood.mean.detach())
+    np.testing.assert_allclose(m.predict(xt).cpu().numpy(), likelihood.mean.detach().cpu().numpy(), rtol=1e-5, atol=2e-6)
 
 
 @pytest.mark.parametrize("name", gu.CLOSED)

@@ -441,6 +441,30 @@ def test_mean_prediction_of_multi_field_model_is_pairwise():
         np.testing.assert_allclose(m.predict_mean(torch.from_numpy(x).to(DEV)).cpu().numpy(), want, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("name", ["sampled_reg_d64", "sampled_fraction", "sampled_reg_softplus"])
+def test_pipelined_and_register_staged_row_updates_agree_bitwise(name):
+    """k_adam_rows_pipe (cp.async staging, default) and k_adam_rows do the same arithmetic per element:
+    identical parameters and moments; the KL sum is accumulated in a different (fixed) order."""
+    from vae_b200 import _lib as L
+    meta, g = gu.load(name)
+    x, y = gu.batch_of(meta, g, 0)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    res = []
+    for pipe in (1, 0):
+        L.check(L.lib().vfmb_set_tuning(b"adam_pipe", pipe))
+        try:
+            m = _model(meta, g, 0, seed=3)
+            losses = [m.fused_step(xd, yd)["loss"].item() for _ in range(3)]            # Philox path (flavour 2)
+            losses.append(m.fused_step(xd, yd, noise=_noise(g, 0))["loss"].item())       # injected (flavour 1)
+            res.append((losses, m.entity_params.weight.clone(), m.entity_m.clone(), m.entity_v.clone(),
+                        m.bias_params.weight.clone(), m._scalars.clone()))
+        finally:
+            L.lib().vfmb_set_tuning(b"adam_pipe", 1)
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-6)
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert torch.equal(a, b)
+
+
 def test_no_cpu_fallback():
     from vae_b200.vfm_torch import CF
     with pytest.raises(RuntimeError):

@@ -38,6 +38,7 @@ extern "C" int vfmb_set_tuning(const char* key, int value) {
     if (!strcmp(key, "grid_reserve")) return vfmb_set_grid_reserve(value);
     if (!strcmp(key, "fuse_score")) { if (value < -1 || value > 1) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: fuse_score -1..1"); t.fuse_score = value; return 0; }
     if (!strcmp(key, "adam_reserve")) { t.adam_reserve = value != 0; return 0; }
+    if (!strcmp(key, "adam_pipe")) { t.adam_pipe = value != 0; return 0; }
     if (!strcmp(key, "prefetch_mv")) { if (value < 0 || value > 15) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: prefetch_mv 0..15"); t.prefetch_mv = value; return 0; }
     return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: unknown key '%s'", key);
 }

@@ -25,6 +25,8 @@ struct Tuning {
     int grid_reserve = 0;    // block slots per SM the persistent step kernels leave free
     int fuse_score = -1;     // F == 2 fused step: -1 = k_gather_score unless a slot is reserved, 0 / 1 = force
     int adam_reserve = 0;    // 1: k_adam_rows also leaves the reserved slot free
+    int adam_pipe = 1;       // Adam on the touched rows: cp.async-pipelined kernel (k_adam_rows_pipe) when the row
+                             //   layout allows (d % 4 == 0, d <= 128); 0 = the register-staged k_adam_rows
     int prefetch_mv = 0;     // fused step: earlier phases pull the Adam moments of the touched rows into L2
                              //   (bit 0: k_stage fetches m, bit 1: k_stage fetches v, bit 2: k_gather fetches m,
                              //    bit 3: k_gather fetches v)

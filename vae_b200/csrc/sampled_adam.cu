@@ -244,6 +244,164 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
     }
 }
 
+// ------------------------------------------------------------------------------- k_adam_rows_pipe
+// The same row update (Adam on the touched rows, 128-bit rows: d % 4 == 0, one vector per lane),
+// software-pipelined: k_adam_rows alternates "issue 6 loads -> wait -> ~250 instructions of chain rule,
+// Philox and Adam -> 6 stores", so a warp has nothing in flight most of the time and the kernel sits at
+// ~0.57 of the HBM peak while a bare gather of the same bytes reaches 0.76 (scripts/stream_ceiling.cu).
+// Here the parameter / moment slices of the NEXT round travel with cp.async (LDGSTS: global -> shared
+// memory, no registers held) while the current round is computed: every warp always has a round of
+// rows (3 KB) in flight.  Each lane reads back exactly the 16-byte pieces it requested itself, so no
+// barrier is involved -- only cp.async.wait_group.  Noise (Philox) and the gradient row do not depend on
+// the staged data and are produced before the wait.
+// Work split: equal contiguous ranges of unique rows per warp (all warps finish together); inside a
+// range, chunks of 32 rows: the scalar work of a row (record, KL weight, bias row update) is done lane-
+// parallel by all 32 lanes, then the warp walks the chunk in rounds of GPW rows.
+// Shared memory: 8 warps x NSTAGE stages x 6 x 512 B = 48 KB per block at NSTAGE = 2 (4 blocks per SM).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+constexpr int kPipeStages = 2;
+
+template <int LPR, int LINK, int FLAVOR>
+__global__ void __launch_bounds__(256, 4)
+k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, float* __restrict__ bias_v,
+                 float* __restrict__ entity, float* __restrict__ entity_m, float* __restrict__ entity_v,
+                 const int32_t* __restrict__ urec, const int32_t* __restrict__ meta,
+                 const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
+                 const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
+                 AdamDev h, int32_t* __restrict__ adam_step, float kl_scale, FinalArgs fa) {
+    constexpr int VEC = 4, GPW = kWarp / LPR, NS = kPipeStages;
+    constexpr bool KLF = FLAVOR == 2;
+    constexpr int MODE = VFMB_ADAM_TOUCHED;
+    extern __shared__ float4 s_stage[];                   // [8 warps][NS][6][32 lanes]
+    const int U = meta[0];
+    const int d = c.d;
+    const uint32_t step = (uint32_t)adam_step[0];
+    const uint32_t nstep = fa.noise_step ? (uint32_t)fa.noise_step[1] : 0u;   // the forward's noise index
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR, warp = threadIdx.x >> 5;
+    const unsigned gmask = group_mask<LPR>();
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    float step_size, inv_bc2;
+    adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
+    float4* my = s_stage + (size_t)warp * (NS * 6 * 32) + lane;
+    const int lo = (int)((int64_t)gwarp * U / nwarps), hi = (int)((int64_t)(gwarp + 1) * U / nwarps);
+    const int k = gl * VEC;                               // this lane's 4 elements of the mean / scale halves
+    const bool kin = k < d;
+    float facc = 0.f;                                     // sum_u c_u * KL_u over this thread's rows
+
+    for (int cbase = lo; cbase < hi; cbase += 32) {
+        // ---- lane-parallel: one unique row per lane
+        const int ul = cbase + lane;
+        const bool valid = ul < hi;
+        int rowid_l = 0;
+        float cfac_l = 0.f, klw_l = 0.f, cq_l = 0.f;
+        if (valid) {
+            rowid_l = __ldg(reinterpret_cast<const int4*>(urec) + ul).x;
+            cq_l = __ldg(cq + ul);
+            cfac_l = kl_scale * cq_l;
+            klw_l = cq_l;
+        }
+        const int nrounds = (min(32, hi - cbase) + GPW - 1) / GPW;
+        auto issue = [&](int r) {                          // warp-uniform call: the shuffle needs every lane
+            const int sel = r * GPW + gidx;
+            const int rowid = bcast(rowid_l, sel);
+            if (cbase + sel < hi && kin) {
+                const size_t eoff = (size_t)rowid * 2 * d + k;
+                float4* dst = my + (r % NS) * (6 * 32);
+                cp_async16(dst + 0 * 32, entity + eoff);     cp_async16(dst + 1 * 32, entity + eoff + d);
+                cp_async16(dst + 2 * 32, entity_m + eoff);   cp_async16(dst + 3 * 32, entity_m + eoff + d);
+                cp_async16(dst + 4 * 32, entity_v + eoff);   cp_async16(dst + 5 * 32, entity_v + eoff + d);
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        // bias row of the lane's row while the first round is in flight
+        if (valid) bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, __ldg(gws + ul),
+                                                __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
+        float klrow = 0.f;
+#pragma unroll 1
+        for (int r = 0; r < nrounds; ++r) {
+            if (r + 1 < nrounds) issue(r + 1); else cp_async_commit();   // one group per iteration, always
+            const int sel = r * GPW + gidx;
+            const int rowid = bcast(rowid_l, sel);
+            const float cfac = bcast(cfac_l, sel);
+            const int u = cbase + sel;
+            const bool live = u < hi && kin;
+            // independent of the staged rows: the noise k_stage used for this row, the row gradient
+            Vec<VEC> e, g;
+            if (live) {
+                if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, nstep);
+                else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
+                g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
+            }
+            cp_async_wait<1>();                            // round r has landed (round r+1 may still fly)
+            float kl = 0.f;
+            if (live) {
+                const float4* src = my + (r % NS) * (6 * 32);
+                const float4 a0 = src[0 * 32], a1 = src[1 * 32], a2 = src[2 * 32], a3 = src[3 * 32], a4 = src[4 * 32], a5 = src[5 * 32];
+                Vec<VEC> mu = {a0.x, a0.y, a0.z, a0.w}, rho = {a1.x, a1.y, a1.z, a1.w};
+                Vec<VEC> m1 = {a2.x, a2.y, a2.z, a2.w}, m2 = {a3.x, a3.y, a3.z, a3.w};
+                Vec<VEC> v1 = {a4.x, a4.y, a4.z, a4.w}, v2 = {a5.x, a5.y, a5.z, a5.w};
+                Vec<VEC> gmu, grho;
+                float quad = 0.f, prodv = 1.f;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float sig = link_fn<LINK>(rho.v[j]);
+                    gmu.v[j] = fmaf(cfac, mu.v[j], g.v[j]);
+                    grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(g.v[j], e.v[j], cfac * (sig - fast_rcp(sig)));
+                    if (KLF) {
+                        const float vr = sig * sig;
+                        quad += vr + mu.v[j] * mu.v[j] - 1.f;
+                        prodv *= vr;
+                    }
+                }
+                if (KLF) {       // sum_k KL(N(mu,sig)||N(0,1)), one logarithm per lane (as k_stage)
+                    float lg = __logf(prodv);
+                    if (!(prodv > 1e-30f && prodv < 1e30f)) {
+                        lg = 0.f;
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho.v[j]); lg += logf(sg * sg); }
+                    }
+                    kl = 0.5f * (quad - lg);
+                }
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    adam_elem(mu.v[j], m1.v[j], v1.v[j], gmu.v[j], h, step_size, inv_bc2);
+                    adam_elem(rho.v[j], m2.v[j], v2.v[j], grho.v[j], h, step_size, inv_bc2);
+                }
+                const size_t eoff = (size_t)rowid * 2 * d + k;
+                st_vec<VEC>(entity + eoff, mu);        st_vec<VEC>(entity + eoff + d, rho);
+                st_vec_cs<VEC>(entity_m + eoff, m1);   st_vec_cs<VEC>(entity_m + eoff + d, m2);
+                st_vec_cs<VEC>(entity_v + eoff, v1);   st_vec_cs<VEC>(entity_v + eoff + d, v2);
+            }
+            if (KLF) {
+                kl = group_sum<LPR>(kl, gmask);
+                hand_back<LPR>(klrow, kl, r, lane);
+            }
+        }
+        // KL of the rows: klw_l is c_u * KL(bias row) (bias_update), klrow the entity part
+        if (KLF && valid) facc += fmaf(cq_l, klrow, klw_l);
+    }
+    cp_async_wait<0>();
+    if (FLAVOR >= 1) {
+        double acc[1] = {(double)facc};
+        if (block_partials<1>(acc, fa.partials, fa.counter)) {
+            double tot[1] = {0.0};
+            if (KLF) final_sums<1>(fa.partials, tot);
+            if (threadIdx.x == 0) {
+                final_scalars<LINK, MODE>(c, fa, h, adam_step, kl_scale, KLF, tot[0], U);
+                *fa.counter = 0;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- k_adam_rows_multi
 // S > 1: the row gradient is the sum over the S sampled copies of the row,
 //   d/dmu = sum_s g_s + c_u mu,   d/drho = sign(rho) (sum_s g_s * eps_s + c_u (sigma - 1/sigma)),
@@ -396,6 +554,46 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
     fa.likelihood = cfg->likelihood; fa.noise_step = tab->noise_step;
     // the HBM-bound kernel keeps its full wave even next to the plan (measured: 113.8 vs 116.2 us/step)
     const bool adam_reserve = tuning().adam_reserve != 0;
+    if (mode == VFMB_ADAM_TOUCHED && L.vec == 4 && L.nv == 1 && tuning().adam_pipe != 0) {
+        // software-pipelined row update (cp.async staging), see k_adam_rows_pipe
+        const size_t smem = (size_t)8 * kPipeStages * 6 * 32 * sizeof(float4);
+        cudaEvent_t ev0, ev1;
+        profile_events(&ev0, &ev1);
+        if (ev0 && ev1) cudaEventRecord(ev0, stream);
+#define LAUNCH_PIPE(LPR_, LINK, FLAVOR)                                                                   \
+        do {                                                                                              \
+            auto kern = k_adam_rows_pipe<LPR_, LINK, FLAVOR>;                                             \
+            static int blocks = 0;                                                                        \
+            if (blocks == 0) {                                                                            \
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                int per_sm = 0;                                                                           \
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));        \
+                blocks = (per_sm < 1 ? 1 : per_sm) * kNumSMs;                                             \
+            }                                                                                             \
+            int grid = blocks;                                                                            \
+            if (adam_reserve && grid_reserve() > 0 && grid / kNumSMs > grid_reserve() + 1) grid -= grid_reserve() * kNumSMs; \
+            const int64_t need = (cap.u_cap + 63) / 64;        /* >= 8 rows per warp */                    \
+            if (grid > need) grid = (int)(need < 1 ? 1 : need);                                           \
+            kern<<<grid, 256, smem, counted(stream)>>>(dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, \
+                tab->entity_m, tab->entity_v, plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, \
+                h, tab->adam_step, kl_grad_scale, fa);                                                    \
+        } while (0)
+#define LAUNCH_PIPE_F(LPR_, LINK)                                                                         \
+        do { if (flavor == 0) LAUNCH_PIPE(LPR_, LINK, 0); else if (flavor == 1) LAUNCH_PIPE(LPR_, LINK, 1); \
+             else LAUNCH_PIPE(LPR_, LINK, 2); } while (0)
+#define LAUNCH_PIPE_L(LPR_)                                                                               \
+        do { if (cfg->link == VFMB_LINK_ABS) LAUNCH_PIPE_F(LPR_, 0); else LAUNCH_PIPE_F(LPR_, 1); } while (0)
+        if (L.lpr == 4) LAUNCH_PIPE_L(4);
+        else if (L.lpr == 8) LAUNCH_PIPE_L(8);
+        else if (L.lpr == 16) LAUNCH_PIPE_L(16);
+        else LAUNCH_PIPE_L(32);
+#undef LAUNCH_PIPE_L
+#undef LAUNCH_PIPE_F
+#undef LAUNCH_PIPE
+        if (ev0 && ev1) cudaEventRecord(ev1, stream);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
 #define LAUNCH_ADAM(LINK, MODE, FLAVOR)                                                                  \
     k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR><<<grid_resident(k_adam_rows<VEC, LPR, NV, LINK, MODE, FLAVOR>, cap.u_cap, ch, 0, adam_reserve), 256, 0, counted(stream)>>>( \
         dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v,              \
