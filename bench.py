@@ -221,7 +221,8 @@ def run_ours(args):
 
     from vae_b200 import _lib as L
     # three staging slots: the copy of batch i+2 into its slot runs on a copy stream, off the step's stream
-    loop = model.graphed_loop(B, depth=3) if (args.plan == "graph" and dp is None) else None
+    gkw = dict(reserve=args.reserve, side_priority=args.side_priority)
+    loop = model.graphed_loop(B, depth=3, **gkw) if (args.plan == "graph" and dp is None) else None
     if loop is not None:
         loop.start(*batch(0))                                # the pipeline runs on from here: warm-up, then timed
         loop.stage(*batch(1))
@@ -271,7 +272,7 @@ def run_ours(args):
 
     # end to end through the public API with HOST inputs: pinned x/y -> device every step,
     # loss/KL scalars back to pinned host memory every step
-    e2e = measure_e2e(model, w, rank, world, n_batches, W, min(K, 500), device, barrier, dp, loop)
+    e2e = measure_e2e(model, w, rank, world, n_batches, W, min(K, 500), device, barrier, dp, loop, gkw)
 
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -336,7 +337,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None, loop=None):
+def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None, loop=None, gkw=None):
     B, F = w.batch, w.n_fields
     xh = torch.from_numpy(w.x[: n_batches * B]).pin_memory()
     yh = torch.from_numpy(w.y[: n_batches * B]).pin_memory()
@@ -362,7 +363,7 @@ def measure_e2e(model, w, rank, world, n_batches, W, K, device, barrier, dp=None
         j = (i * world + rank) % n_batches
         return xh[j * B:(j + 1) * B], yh[j * B:(j + 1) * B]
 
-    hloop = model.graphed_loop(B, depth=3) if loop is not None else None
+    hloop = model.graphed_loop(B, depth=3, **(gkw or {})) if loop is not None else None
 
     started = []
     d2h = torch.cuda.Stream(device=device)
@@ -736,6 +737,8 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="override the synthetic dataset size")
     ap.add_argument("--plan", default="graph", choices=["inline", "prefetch", "graph", "cached"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--reserve", type=int, default=1, help="graph mode: block slots per SM the step kernels leave to the plan")
+    ap.add_argument("--side-priority", type=int, default=-1, help="graph mode: stream priority of the plan branch")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
                     help="library launch knob (vfmb_set_tuning), e.g. prefetch_mv=3; repeatable")
     ap.add_argument("--cpu-budget", type=float, default=20.0)

@@ -19,7 +19,8 @@
 #include "sampled_common.cuh"
 
 #ifndef VFMB_SCORE_HOIST
-#define VFMB_SCORE_HOIST 1          // k_score, F == 2: fetch the row pairs of all rounds before the dot products
+#define VFMB_SCORE_HOIST 0          // k_score, F == 2: 1 = fetch the row pairs of all rounds before the dot products
+                                    // (measured: no gain -- 80 registers cost a resident block per SM)
 #endif
 
 namespace vfmb {

@@ -17,10 +17,17 @@ namespace vfmb {
 //             with idle issue slots) and, without injected noise, the Philox draws recomputed
 //             instead of read back -- k_stage<LEAN> wrote neither.
 
+// The scalar parameters (alpha, global bias) need only the sums k_score left in `stats`, not the row
+// gradients, so their update is split from the end-of-kernel bookkeeping:
+//   scalar_update   gradients of the scalar parameters + their Adam step (or the dense-gradient
+//                   store).  One thread.  Leaves KL(global bias) of the PRE-update parameters in
+//                   stats[VFMB_ST_KL] for finish_step.  Does not touch the step counter.
+//   finish_step     by the block that finishes last: loss terms (KL of the rows), step counter.
+// k_adam_rows_pipe runs scalar_update at kernel START on a block that takes no rows, which removes
+// ~4 us of serial tail (a dozen dependent L2 round trips + two fp64 pow) from the critical path.
 template <int LINK, int MODE>
-__device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& fa, const AdamDev& h,
-                                              int32_t* __restrict__ adam_step, float kl_scale,
-                                              bool with_kl, double kl_rows, int U) {
+__device__ __forceinline__ void scalar_update(const DevCfg& c, const FinalArgs& fa, const AdamDev& h,
+                                              const int32_t* __restrict__ adam_step, float kl_scale) {
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;            // Adam steps applied so far
     const uint32_t nstep = fa.noise_step ? (uint32_t)fa.noise_step[1] : 0u;   // noise index of the forward
     float* scalars = fa.scalars; float* stats = fa.stats;
@@ -34,13 +41,7 @@ __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& 
     } else {
         e0sr = (double)global_eps(fa.eps_global, c, nstep) * sr;
     }
-    if (with_kl) {                                      // loss terms of the pre-update parameters
-        const float kl = kl_std_normal(mu0, sig0) + (float)kl_rows;
-        stats[VFMB_ST_KL_ROWS] = (float)kl_rows;
-        stats[VFMB_ST_KL] = kl;
-        stats[VFMB_ST_LOSS] = (float)((double)stats[VFMB_ST_LOSS] + (double)kl);
-        stats[VFMB_ST_U] = (float)U;
-    }
+    stats[VFMB_ST_KL] = kl_std_normal(mu0, sig0);       // pre-update; finish_step adds the rows' KL
     float g_mu0 = (float)(sr + (double)(kl_scale * mu0));
     float g_rho0 = link_grad<LINK>(rho0) * (float)(e0sr + (double)(kl_scale * (sig0 - 1.f / sig0)));
     float g_alpha = 0.f;
@@ -58,12 +59,33 @@ __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& 
             adam_elem(alpha, fa.sm[VFMB_S_ALPHA], fa.sv[VFMB_S_ALPHA], g_alpha, h, ss, b2);
             scalars[VFMB_S_ALPHA] = alpha;
         }
-        adam_step[0] = (int32_t)step + 1;
     } else if (fa.grad_scalars) {
         fa.grad_scalars[VFMB_S_ALPHA] = g_alpha;
         fa.grad_scalars[VFMB_S_GB_MEAN] = g_mu0;
         fa.grad_scalars[VFMB_S_GB_SCALE] = g_rho0;
     }
+}
+
+template <int MODE>
+__device__ __forceinline__ void finish_step(const FinalArgs& fa, int32_t* __restrict__ adam_step, bool with_kl,
+                                            double kl_rows, int U) {
+    float* stats = fa.stats;
+    if (with_kl) {                                      // loss terms of the pre-update parameters
+        const float kl = stats[VFMB_ST_KL] + (float)kl_rows;
+        stats[VFMB_ST_KL_ROWS] = (float)kl_rows;
+        stats[VFMB_ST_KL] = kl;
+        stats[VFMB_ST_LOSS] = (float)((double)stats[VFMB_ST_LOSS] + (double)kl);
+        stats[VFMB_ST_U] = (float)U;
+    }
+    if (MODE == VFMB_ADAM_TOUCHED) adam_step[0] += 1;
+}
+
+template <int LINK, int MODE>
+__device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& fa, const AdamDev& h,
+                                              int32_t* __restrict__ adam_step, float kl_scale,
+                                              bool with_kl, double kl_rows, int U) {
+    scalar_update<LINK, MODE>(c, fa, h, adam_step, kl_scale);
+    finish_step<MODE>(fa, adam_step, with_kl, kl_rows, U);
 }
 
 #ifndef VFMB_ADAM_MINB
@@ -290,7 +312,14 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
     float step_size, inv_bc2;
     adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
     float4* my = s_stage + (size_t)warp * (NS * 6 * 32) + lane;
-    const int lo = (int)((int64_t)gwarp * U / nwarps), hi = (int)((int64_t)(gwarp + 1) * U / nwarps);
+    // FLAVOR >= 1: the last block takes no rows; its first thread updates the scalar parameters right
+    // away (they depend on the sums k_score left, not on the row gradients) -- off the critical path
+    const bool split = FLAVOR >= 1 && gridDim.x > 1;
+    const int row_warps = split ? nwarps - (int)(blockDim.x >> 5) : nwarps;
+    const bool scalar_block = split && blockIdx.x == gridDim.x - 1;
+    if (scalar_block && threadIdx.x == 0) scalar_update<LINK, MODE>(c, fa, h, adam_step, kl_scale);
+    const int lo = scalar_block ? 0 : (int)((int64_t)gwarp * U / row_warps);
+    const int hi = scalar_block ? 0 : (int)((int64_t)(gwarp + 1) * U / row_warps);
     const int k = gl * VEC;                               // this lane's 4 elements of the mean / scale halves
     const bool kin = k < d;
     float facc = 0.f;                                     // sum_u c_u * KL_u over this thread's rows
@@ -321,9 +350,29 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             cp_async_commit();
         };
         issue(0);
-        // bias row of the lane's row while the first round is in flight
-        if (valid) bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, __ldg(gws + ul),
-                                                __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
+        // bias row of the lane's row: loads now, arithmetic and stores after the rounds (the loads fly
+        // under the whole walk of the chunk)
+        float2 b_p = make_float2(0.f, 1.f), b_m = make_float2(0.f, 0.f), b_v = make_float2(0.f, 0.f);
+        float gw_l = 0.f, eb_l = 0.f;
+        if (valid) {
+            const size_t boff = (size_t)rowid_l * 2;
+            b_p = *reinterpret_cast<const float2*>(bias + boff);
+            b_m = *reinterpret_cast<const float2*>(bias_m + boff);
+            b_v = *reinterpret_cast<const float2*>(bias_v + boff);
+            gw_l = __ldg(gws + ul);
+            eb_l = __ldg(eps_bias + ul);
+        }
+        // the gradient row of a round is fetched one round ahead (registers): it comes from L2 scratch
+        // and its latency would otherwise sit between the wait and the first use
+        auto fetch_g = [&](int r) {
+            const int u = cbase + r * GPW + gidx;
+            Vec<VEC> g;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) g.v[j] = 0.f;
+            if (u < hi && kin) g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
+            return g;
+        };
+        Vec<VEC> g_next = fetch_g(0);
         float klrow = 0.f;
 #pragma unroll 1
         for (int r = 0; r < nrounds; ++r) {
@@ -333,12 +382,13 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             const float cfac = bcast(cfac_l, sel);
             const int u = cbase + sel;
             const bool live = u < hi && kin;
-            // independent of the staged rows: the noise k_stage used for this row, the row gradient
-            Vec<VEC> e, g;
+            const Vec<VEC> g = g_next;
+            if (r + 1 < nrounds) g_next = fetch_g(r + 1);
+            // independent of the staged rows: the noise k_stage used for this row
+            Vec<VEC> e;
             if (live) {
                 if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, nstep);
                 else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
-                g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
             }
             cp_async_wait<1>();                            // round r has landed (round r+1 may still fly)
             float kl = 0.f;
@@ -385,6 +435,18 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
                 hand_back<LPR>(klrow, kl, r, lane);
             }
         }
+        if (valid) {                                       // bias row: chain rule + KL gradient + Adam
+            const size_t boff = (size_t)rowid_l * 2;
+            const float tau = link_fn<LINK>(b_p.y);
+            if (KLF) klw_l *= kl_std_normal(b_p.x, tau);
+            const float ga = fmaf(cfac_l, b_p.x, gw_l);
+            const float gb = link_grad<LINK>(b_p.y) * fmaf(gw_l, eb_l, cfac_l * (tau - fast_rcp(tau)));
+            adam_elem(b_p.x, b_m.x, b_v.x, ga, h, step_size, inv_bc2);
+            adam_elem(b_p.y, b_m.y, b_v.y, gb, h, step_size, inv_bc2);
+            *reinterpret_cast<float2*>(bias + boff) = b_p;
+            *reinterpret_cast<float2*>(bias_m + boff) = b_m;
+            *reinterpret_cast<float2*>(bias_v + boff) = b_v;
+        }
         // KL of the rows: klw_l is c_u * KL(bias row) (bias_update), klrow the entity part
         if (KLF && valid) facc += fmaf(cq_l, klrow, klw_l);
     }
@@ -395,7 +457,8 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             double tot[1] = {0.0};
             if (KLF) final_sums<1>(fa.partials, tot);
             if (threadIdx.x == 0) {
-                final_scalars<LINK, MODE>(c, fa, h, adam_step, kl_scale, KLF, tot[0], U);
+                if (!split) scalar_update<LINK, MODE>(c, fa, h, adam_step, kl_scale);
+                finish_step<MODE>(fa, adam_step, KLF, tot[0], U);
                 *fa.counter = 0;
             }
         }

@@ -170,7 +170,7 @@ class GraphedLoop:
         res = loop.step()                         # last staged batch
     """
 
-    def __init__(self, model, B: int, step_fn, depth: int = 2):
+    def __init__(self, model, B: int, step_fn, depth: int = 2, reserve: int = 1, side_priority: int = -1):
         assert depth in (2, 3)
         self.model, self.B, self.device, self.depth = model, int(B), model.device, depth
         F = model.F if hasattr(model, "F") else model.G
@@ -184,7 +184,7 @@ class GraphedLoop:
         self.outs = [SlotOutputs(S, B, self.device) for _ in range(D)]
         # high priority: the plan kernels are tiny and latency-bound; they should slip in as soon
         # as blocks of the (machine-filling) step kernels retire
-        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self.side = torch.cuda.Stream(device=self.device, priority=side_priority)
         self.copy = torch.cuda.Stream(device=self.device) if depth == 3 else None
         self.copied = [torch.cuda.Event() for _ in range(D)]
         self.done = [torch.cuda.Event() for _ in range(D)]
@@ -203,7 +203,7 @@ class GraphedLoop:
         torch.cuda.synchronize(self.device)
         # the step kernels are captured one block slot per SM short of a full wave, so that the
         # plan's blocks (side branch) are placed immediately instead of displacing step blocks
-        L.check(L.lib().vfmb_set_grid_reserve(1), "vfmb_set_grid_reserve")
+        L.check(L.lib().vfmb_set_grid_reserve(reserve), "vfmb_set_grid_reserve")
         n0 = int(L.lib().vfmb_launch_count())
         try:
             for s in range(D):

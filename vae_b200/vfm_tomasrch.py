@@ -257,7 +257,7 @@ class CF(nn.Module):
             self._pipe.release(self._plan)
         return StepResult(self._buf, self._cfg.B)
 
-    def graphed_loop(self, B: int, depth: int = 2) -> GraphedLoop:
+    def graphed_loop(self, B: int, depth: int = 2, **kw) -> GraphedLoop:
         """CUDA-graph replay of the training loop for batches of exactly ``B`` samples (the step on
         batch i and the plan of batch i+1 captured once): the ML-100K-sized step is launch-bound, so the
         host launch overhead is what the eager loop measures.  See engine.GraphedLoop."""
@@ -274,7 +274,7 @@ class CF(nn.Module):
                     "vfmb_closed_forward")
             L.check(L.lib().vfmb_closed_backward(C.byref(self._cfg), C.byref(tab), C.byref(plan.struct), C.byref(io),
                                                  C.byref(self.adam), L.ADAM_TOUCHED, s), "vfmb_closed_backward")
-        return GraphedLoop(self, B, step_fn, depth)
+        return GraphedLoop(self, B, step_fn, depth, **kw)
 
     @torch.no_grad()
     def gradients(self, x: torch.Tensor, y: torch.Tensor) -> dict:

@@ -364,7 +364,7 @@ class CF(nn.Module):
         return {"loss": st[L.ST_LOSS], "kl": st[L.ST_KL], "nll_mean": st[L.ST_NLL_MEAN],
                 "pred": out["mean"], "logits": out["pred"], "stats": st}
 
-    def graphed_loop(self, B: int, depth: int = 2) -> GraphedLoop:
+    def graphed_loop(self, B: int, depth: int = 2, **kw) -> GraphedLoop:
         """CUDA-graph replay of the training loop for batches of exactly ``B`` samples: the step
         on the current batch and the plan of the next one are captured once and replayed, which
         removes the host launch overhead (the step is otherwise launch-bound).  See GraphedLoop."""
@@ -379,7 +379,7 @@ class CF(nn.Module):
             L.check(L.lib().vfmb_sampled_step(C.byref(self._cfg), C.byref(self._tables()), C.byref(plan.struct),
                                               C.byref(io), C.byref(self.adam), current_stream(self.device)),
                     "vfmb_sampled_step")
-        return GraphedLoop(self, B, step_fn, depth)
+        return GraphedLoop(self, B, step_fn, depth, **kw)
 
     def _fused_step_fast(self, x, y, plan):
         """Hot loop: cached ctypes structures, one C call for forward + backward + Adam."""
