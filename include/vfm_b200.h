@@ -334,6 +334,21 @@ int vfmb_closed_backward_weighted(const vfmb_config* cfg, const vfmb_tables* tab
 int vfmb_predict_mean(const vfmb_config* cfg, const float* bias, const float* entity,
                       float global_bias, const int64_t* x, float* out, vfmb_stream stream);
 
+/* Multi-sample predictive statistics without a plan (vfm.py:1047-1057 `predict_proba`, behind the
+ * active-learning question selection of vfm.py:1024-1045): n_samples variational samples of the
+ * logit of every row of x (int64 [cfg->B, cfg->F]) in ONE launch, nothing of size [S, ...] materialised:
+ *   proba_mean[n] = mean_s likelihood.mean()[s, n]  (sigmoid(logit) for Bernoulli, the logit for Gaussian)
+ *   logit_mean[n] = mean_s logit[s, n]              (optional, may be NULL)
+ *   logit_var[n]  = var_s logit[s, n]               (population variance, as numpy .var)
+ * Noise: Philox, sample index in the tag word, drawn at noise index tab->noise_step[0] (the caller
+ * advances the counter afterwards, vfmb_adam_step_advance works on it).  per_occurrence = 0: one draw
+ * per entity and sample, shared by all its occurrences (vfm-torch.py:238-245); 1: independent draws
+ * per row of x (vfm.py:440-445).  Interaction per cfg->interaction.  Needs tab->bias, entity,
+ * scalars (sampled layout), noise_step. */
+int vfmb_predict_sampled(const vfmb_config* cfg, const vfmb_tables* tab, const int64_t* x, int32_t n_samples,
+                         int32_t per_occurrence, float* proba_mean, float* logit_mean, float* logit_var,
+                         vfmb_stream stream);
+
 /* The N(0,1) draws the Philox path uses for `step` (for tests / reproducibility):
  * eps_bias [U], eps_entity [U,d] for the given unique row ids. */
 int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, int32_t U, int32_t step,

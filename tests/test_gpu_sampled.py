@@ -465,6 +465,53 @@ def test_pipelined_and_register_staged_row_updates_agree_bitwise(name):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("output,F", [("class", 2), ("reg", 2), ("class", 3)])
+def test_predict_proba_many_samples_matches_oracle(output, F):
+    """vfm.py:1047-1057: mean over S = 64 variational samples of the likelihood mean and the population
+    variance of the logits, from ONE launch; the oracle gets the same Philox draws (exported) in fp64."""
+    from vae_b200.vfm_torch import CF
+    fs, d, B, S = [40, 25, 9][:F], 16, 300, 64
+    rng = np.random.default_rng(5)
+    offs = np.concatenate(([0], np.cumsum(fs)[:-1]))
+    x = np.stack([offs[f] + rng.integers(0, fs[f], B) for f in range(F)], 1).astype(np.int64)
+    torch.manual_seed(2)
+    m = CF(d, output=output, n_users=fs[0], n_items=fs[1], train_counts=torch.ones(sum(fs)), field_sizes=fs,
+           kl_weighting="torch" if F == 2 else "group", n_train=B, max_batch=B, seed=21)
+    with torch.no_grad():
+        m.entity_params.weight.mul_(0.4)
+        m.global_bias_mean.fill_(0.3), m.global_bias_scale.fill_(0.5)
+    uniq = np.unique(x)
+    rank = np.searchsorted(uniq, x)                                   # [B, F] unique rank of every occurrence
+    from vae_b200 import _lib as L
+    from vae_b200.engine import make_config
+    import ctypes as C
+    U = len(uniq)
+    cfgS = make_config(1, F, d, sum(fs), S, output, "abs", m._class_bounds, m._class_sizes, B, 21)
+    e0 = torch.empty(S, device=DEV); eb = torch.empty(S * U, device=DEV); ee = torch.empty(S * U * d, device=DEV)
+    step = int(m.noise_step[0].item())
+    L.check(L.lib().vfmb_philox_normals(C.byref(cfgS), torch.from_numpy(uniq).int().to(DEV).data_ptr(), U, step,
+                                        e0.data_ptr(), eb.data_ptr(), ee.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    e0, eb, ee = e0.cpu().numpy().astype(np.float64), eb.cpu().numpy().reshape(S, U).astype(np.float64), \
+        ee.cpu().numpy().reshape(S, U, d).astype(np.float64)
+    W = m.entity_params.weight.detach().cpu().numpy().astype(np.float64)
+    Bw = m.bias_params.weight.detach().cpu().numpy().astype(np.float64)
+    v = W[uniq][None, :, :d] + ee * np.abs(W[uniq][None, :, d:])     # [S, U, d]
+    w = Bw[uniq][None, :, 0] + eb * np.abs(Bw[uniq][None, :, 1])      # [S, U]
+    vg = v[:, rank]                                                   # [S, B, F, d]
+    fm = vg.prod(2).sum(2) if F == 2 else (0.5 * (vg.sum(2) ** 2 - (vg ** 2).sum(2))).sum(2)
+    logits = (0.3 + e0 * 0.5)[:, None] + w[:, rank].sum(2) + fm       # [S, B]
+    lik_mean = 1 / (1 + np.exp(-logits)) if output == "class" else logits
+    pm, lv, lm = m.predict_proba(torch.from_numpy(x).to(DEV), n_samples=S, return_logit_mean=True)
+    assert m.noise_step.tolist()[0] == step + 1
+    np.testing.assert_allclose(lm.cpu().numpy(), logits.mean(0), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(pm.cpu().numpy(), lik_mean.mean(0), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(lv.cpu().numpy(), logits.var(0), rtol=1e-4, atol=1e-5)
+    # per-occurrence draws (vfm.py:440-445): same marginals -- compare the batch-averaged statistics loosely
+    pm2, lv2 = m.predict_proba(torch.from_numpy(x).to(DEV), n_samples=4 * S, per_occurrence=True)
+    assert abs(lv2.mean().item() - logits.var(0).mean()) < 0.25 * logits.var(0).mean()
+    assert abs(pm2.mean().item() - lik_mean.mean()) < 0.1 * max(abs(lik_mean.mean()), 0.1)
+
+
 def test_no_cpu_fallback():
     from vae_b200.vfm_torch import CF
     with pytest.raises(RuntimeError):

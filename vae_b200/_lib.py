@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # experiment hook: VFMB_VARIANT=name + VFMB_NVCC_EXTRA="-DX=1 ..." builds / loads libvfm_b200_name.so
 _VARIANT = os.environ.get("VFMB_VARIANT", "")
 LIB_PATH = os.path.join(_HERE, f"libvfm_b200{'_' + _VARIANT if _VARIANT else ''}.so")
-SOURCES = ["api.cu", "plan.cu", "sampled.cu", "sampled_adam.cu", "closed.cu", "dp.cu", "shard.cu"]
+SOURCES = ["api.cu", "plan.cu", "sampled.cu", "sampled_adam.cu", "closed.cu", "predict.cu", "dp.cu", "shard.cu"]
 HEADERS = ["common.cuh", "internal.h", "step_common.cuh", "sampled_common.cuh", os.path.join(_ROOT, "include", "vfm_b200.h")]
 # -prec-div/-prec-sqrt=false: MUFU-based division and square root (<= 2 ulp) instead of the IEEE
 # slow paths, which made the Adam epilogue instruction-bound; denormals and expf/logf stay precise
@@ -136,6 +136,8 @@ SYMBOLS = {
                                                 C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "vfmb_predict_mean": (C.c_int, [_P(Config), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "vfmb_predict_sampled": (C.c_int, [_P(Config), _P(Tables), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "vfmb_philox_normals": (C.c_int, [_P(Config), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
 }

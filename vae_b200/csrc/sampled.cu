@@ -1043,7 +1043,7 @@ extern "C" int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, 
     if (U == 0) return 0;
     DevCfg dc = make_dev(cfg);
     int vec = (cfg->d % 4 == 0) ? 4 : 1;
-    if (cfg->S < 1 || cfg->S > kMaxSamples) return set_error(VFMB_ESHAPE, "vfmb_philox_normals: S=%d (1..%d)", cfg->S, kMaxSamples);
+    if (cfg->S < 1) return set_error(VFMB_ESHAPE, "vfmb_philox_normals: S=%d", cfg->S);
     int64_t work = (int64_t)U * ((cfg->d + vec - 1) / vec) * cfg->S;
     int grid = (int)((work + 255) / 256 > 4096 ? 4096 : (work + 255) / 256);
     if (vec == 4) k_philox_export<4><<<grid, 256, 0, counted((cudaStream_t)stream_)>>>(dc, uniq, U, (uint32_t)step, eps_global, eps_bias, eps_entity);

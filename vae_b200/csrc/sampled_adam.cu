@@ -350,29 +350,9 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             cp_async_commit();
         };
         issue(0);
-        // bias row of the lane's row: loads now, arithmetic and stores after the rounds (the loads fly
-        // under the whole walk of the chunk)
-        float2 b_p = make_float2(0.f, 1.f), b_m = make_float2(0.f, 0.f), b_v = make_float2(0.f, 0.f);
-        float gw_l = 0.f, eb_l = 0.f;
-        if (valid) {
-            const size_t boff = (size_t)rowid_l * 2;
-            b_p = *reinterpret_cast<const float2*>(bias + boff);
-            b_m = *reinterpret_cast<const float2*>(bias_m + boff);
-            b_v = *reinterpret_cast<const float2*>(bias_v + boff);
-            gw_l = __ldg(gws + ul);
-            eb_l = __ldg(eps_bias + ul);
-        }
-        // the gradient row of a round is fetched one round ahead (registers): it comes from L2 scratch
-        // and its latency would otherwise sit between the wait and the first use
-        auto fetch_g = [&](int r) {
-            const int u = cbase + r * GPW + gidx;
-            Vec<VEC> g;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) g.v[j] = 0.f;
-            if (u < hi && kin) g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
-            return g;
-        };
-        Vec<VEC> g_next = fetch_g(0);
+        // bias row of the lane's row while the first round is in flight
+        if (valid) bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, __ldg(gws + ul),
+                                                __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
         float klrow = 0.f;
 #pragma unroll 1
         for (int r = 0; r < nrounds; ++r) {
@@ -382,13 +362,12 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             const float cfac = bcast(cfac_l, sel);
             const int u = cbase + sel;
             const bool live = u < hi && kin;
-            const Vec<VEC> g = g_next;
-            if (r + 1 < nrounds) g_next = fetch_g(r + 1);
-            // independent of the staged rows: the noise k_stage used for this row
-            Vec<VEC> e;
+            // independent of the staged rows: the noise k_stage used for this row, the row gradient
+            Vec<VEC> e, g;
             if (live) {
                 if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, nstep);
                 else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
+                g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
             }
             cp_async_wait<1>();                            // round r has landed (round r+1 may still fly)
             float kl = 0.f;
@@ -434,18 +413,6 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
                 kl = group_sum<LPR>(kl, gmask);
                 hand_back<LPR>(klrow, kl, r, lane);
             }
-        }
-        if (valid) {                                       // bias row: chain rule + KL gradient + Adam
-            const size_t boff = (size_t)rowid_l * 2;
-            const float tau = link_fn<LINK>(b_p.y);
-            if (KLF) klw_l *= kl_std_normal(b_p.x, tau);
-            const float ga = fmaf(cfac_l, b_p.x, gw_l);
-            const float gb = link_grad<LINK>(b_p.y) * fmaf(gw_l, eb_l, cfac_l * (tau - fast_rcp(tau)));
-            adam_elem(b_p.x, b_m.x, b_v.x, ga, h, step_size, inv_bc2);
-            adam_elem(b_p.y, b_m.y, b_v.y, gb, h, step_size, inv_bc2);
-            *reinterpret_cast<float2*>(bias + boff) = b_p;
-            *reinterpret_cast<float2*>(bias_m + boff) = b_m;
-            *reinterpret_cast<float2*>(bias_v + boff) = b_v;
         }
         // KL of the rows: klw_l is c_u * KL(bias row) (bias_update), klrow the entity part
         if (KLF && valid) facc += fmaf(cq_l, klrow, klw_l);

@@ -341,6 +341,28 @@ class CF(nn.Module):
                                           out.data_ptr(), current_stream(self.device)), "vfmb_predict_mean")
         return out
 
+    @torch.no_grad()
+    def predict_proba(self, x: torch.Tensor, n_samples: int = 64, per_occurrence: bool = False, return_logit_mean: bool = False):
+        """``(proba_means, logit_variances)`` over ``n_samples`` variational samples of every row of
+        ``x`` -- vfm.py:1047-1057 ``predict_proba`` (mean over the samples of the likelihood mean, and the
+        population variance of the logits), the statistic behind the active-learning question selection
+        (vfm.py:1024-1045).  One kernel launch for any ``n_samples``; consumes one noise index.
+        ``per_occurrence``: independent draws per row of ``x`` (vfm.py:440-445) instead of one draw per
+        entity (vfm-torch.py:238-245); the per-row statistics are the same in distribution."""
+        self._sync_scalars()
+        x = x.to(self.device).contiguous()
+        B = int(x.shape[0])
+        cfg = self._config(B)
+        pm = torch.empty(B, dtype=torch.float32, device=self.device)
+        lm = torch.empty(B, dtype=torch.float32, device=self.device)
+        lv = torch.empty(B, dtype=torch.float32, device=self.device)
+        s = current_stream(self.device)
+        L.check(L.lib().vfmb_predict_sampled(C.byref(cfg), C.byref(self._tables()), x.data_ptr(), int(n_samples),
+                                             int(bool(per_occurrence)), pm.data_ptr(), lm.data_ptr(), lv.data_ptr(), s),
+                "vfmb_predict_sampled")
+        L.check(L.lib().vfmb_adam_step_advance(self.noise_step.data_ptr(), s))       # next forward: fresh noise
+        return (pm, lv, lm) if return_logit_mean else (pm, lv)
+
     # ------------------------------------------------------------------ fast path
     def configure_adam(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8):
         self.adam = L.Adam(lr, betas[0], betas[1], eps)
