@@ -276,6 +276,42 @@ int vfmb_shard_pack_grads(const vfmb_plan* plan_l, const float* grow, const floa
 int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, const int32_t* recv_ids, int32_t M,
                             int32_t d, float* table, float* rsorted, vfmb_stream stream);
 
+/* ---- mode B, fused over NVLink peer memory: the exchanges are written / read in place by the step
+ * kernels themselves, two cross-rank barriers per step remain (after the rows, after the gradients).
+ * Slot pitch SP = d + 4 floats ([row | scalar, pad]: 16-byte aligned for 128-bit peer stores); the
+ * received-rows region has one spare slot M (zeros) that overflowed rows are routed to.
+ *   vfmb_shard_route         requester, id-only: per occurrence / sorted position the slot its row is read
+ *                            from, per unique rank the peer address its gradient row is stored to
+ *   vfmb_shard_stage_put     owner: k_stage; every sampled row goes straight into its requesters' slots
+ *                            (n_real = rows this rank owns; larger local indices are padding)
+ *   vfmb_shard_score         requester: k_score on the received slots; the block that finishes last puts the
+ *                            rank's additive scalars {NLL, residual, squared error, KL of its owned rows,
+ *                            overflow flag} into slot `rank` of every rank's tail region
+ *   vfmb_shard_gather_put    requester: k_gather on the received slots; finished gradient rows are stored
+ *                            through gptr into their owners' slots
+ *   vfmb_shard_owner_update  owner: ordered sum of the received gradient slots (source-rank order), Adam on
+ *                            the owned rows, scalar parameters + global-batch loss from the tail slots
+ *                            (NaN when any rank flagged a bucket overflow), step counter               */
+int vfmb_shard_route(const vfmb_plan* plan_l, const int32_t* dest, int32_t B, int32_t F, int32_t u_cap,
+                     int32_t M, int32_t CAP, int32_t SP, const void* const* peers_grads, int32_t P,
+                     int32_t rank, float* dump, int32_t* inv_slot, int32_t* partner_slot, float** gptr,
+                     vfmb_stream stream);
+int vfmb_shard_stage_put(const vfmb_config* cfg_o, const vfmb_tables* tab, const vfmb_plan* plan_o,
+                         const vfmb_step_io* io_o, int32_t CAP, int32_t SP, int32_t n_real,
+                         const void* const* peers_rows, int32_t P, int32_t rank, vfmb_stream stream);
+int vfmb_shard_score(const vfmb_config* cfg_l, const vfmb_tables* tab, const vfmb_plan* plan_l,
+                     const vfmb_step_io* io_l, const float* recv_rows, int32_t SP, const int32_t* inv_slot,
+                     const void* const* peers_tail, int32_t P, int32_t rank, const float* stats_owner,
+                     const int32_t* overflow, float n_local, int32_t tail_pitch, vfmb_stream stream);
+int vfmb_shard_gather_put(const vfmb_config* cfg_l, const vfmb_plan* plan_l, const vfmb_step_io* io_l,
+                          const float* recv_rows, int32_t SP, const int32_t* partner_slot,
+                          float* const* gptr, const int32_t* own_slot, vfmb_stream stream);
+int vfmb_shard_owner_update(const vfmb_config* cfg_o, const vfmb_tables* tab, const vfmb_plan* plan_o,
+                            const vfmb_step_io* io_o, const vfmb_adam* adam, const float* recv_grads,
+                            int32_t SP, const float* tail_slots, int32_t P, int32_t tail_pitch,
+                            int32_t B_global, float n_train_global, float* stats_out,
+                            const float* eps_global, vfmb_stream stream);
+
 int vfmb_dp_final(const vfmb_config* cfg_global, const vfmb_tables* tab, const float* tail,
                   const float* eps_global, const vfmb_adam* adam, float* stats, vfmb_stream stream);
 
@@ -300,7 +336,9 @@ int vfmb_adam_step_advance(int32_t* adam_step, vfmb_stream stream);
  * then vfmb_dp_apply_sampled on every rank: KL gradient with the global batch counts and
  * normalisers, Adam (dense = the reference's torch.optim.Adam over every row, or touched rows),
  * scalar parameters, step counter.  tail = {z[0..7], sum nll, sum resid, sum sq. err}. */
-enum { VFMB_DP_TAIL = 16, VFMB_DP_T_NLL = 8, VFMB_DP_T_RESID = 9, VFMB_DP_T_SQERR = 10 };
+enum { VFMB_DP_TAIL = 16, VFMB_DP_T_NLL = 8, VFMB_DP_T_RESID = 9, VFMB_DP_T_SQERR = 10,
+       VFMB_DP_T_KLROWS = 11,    /* mode B: KL of the rows a rank owns                         */
+       VFMB_DP_T_OVERFLOW = 12   /* mode B: > 0 when any rank's request bucket overflowed       */ };
 int vfmb_dp_scatter_counts(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io,
                            float* counts /*[R], zeroed*/, float* tail /*[VFMB_DP_TAIL]*/,
                            vfmb_stream stream);

@@ -89,9 +89,25 @@ def _run_sharded_emulated(ranks, xs, ys):
     return [r.phase_owner_update(g_, tail.clone()) for r, g_ in zip(ranks, grads)]
 
 
+def _run_sharded_fused(ranks, xs, ys):
+    """Lock-step emulation of the fused peer-memory step: the emulated ranks share a LocalPeerGroup, every
+    phase runs on all ranks before the next one starts (what the cross-rank barriers guarantee)."""
+    for r, x, y in zip(ranks, xs, ys):
+        r._use_slot(0)
+        r.phase_request(x, y)                 # local plan, requests into the owners' regions, routing tables
+    for r in ranks:
+        r._owner_prepare(None, None)          # owner's plan of the received ids, global batch counts
+    for r in ranks:
+        r._b_stage()
+    for r in ranks:
+        r._b_local()
+    return [r._b_update() for r in ranks]
+
+
+@pytest.mark.parametrize("mode", ["collective", "fused"])
 @pytest.mark.parametrize("P", [2, 3, 4, 8])
 @pytest.mark.parametrize("name", ["sampled_reg_d64", "sampled_fraction"])
-def test_row_sharded_mode_b_equals_single_process_step(name, P):
+def test_row_sharded_mode_b_equals_single_process_step(name, P, mode):
     """Mode B (row-sharded tables, all-to-all of sampled rows and gradients), P ranks emulated on one
     GPU, against the single-process fused step on the global batch with the same per-entity noise."""
     from vae_b200.dist import ShardedSampled
@@ -117,13 +133,15 @@ def test_row_sharded_mode_b_equals_single_process_step(name, P):
     ini = {"bias": torch.from_numpy(init["bias_params.weight"]), "entity": torch.from_numpy(init["entity_params.weight"]),
            "alpha": init["alpha"][0], "global_bias_mean": init["global_bias_mean"][0],
            "global_bias_scale": init["global_bias_scale"][0]}
+    from vae_b200.dist import LocalPeerGroup
+    ex = LocalPeerGroup(P) if mode == "fused" else object()
     ranks = [ShardedSampled(d, [N, M], torch.from_numpy(g["train_counts"]), meta["n_train"], n // P, P, p,
                             output=meta["output"], link=meta["link"], lr=meta["lr"], init=ini,
-                            noise_tables=(e0, eb_t, ee_t), exchange=object()) for p in range(P)]
+                            noise_tables=(e0, eb_t, ee_t), exchange=ex) for p in range(P)]
     xs = [torch.from_numpy(x[p * (n // P):(p + 1) * (n // P)]).to(DEV) for p in range(P)]
     ys = [torch.from_numpy(y[p * (n // P):(p + 1) * (n // P)]).to(DEV) for p in range(P)]
     for step in range(2):
-        outs = _run_sharded_emulated(ranks, xs, ys)
+        outs = (_run_sharded_fused if mode == "fused" else _run_sharded_emulated)(ranks, xs, ys)
     for r in ranks:
         r.check_overflow()
         assert int(r.adam_step.item()) == 2
@@ -145,8 +163,9 @@ def test_row_sharded_mode_b_equals_single_process_step(name, P):
     assert torch.allclose(pred, out_ref["pred"], rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("mode", ["collective", "fused"])
 @pytest.mark.parametrize("F,d,P", [(3, 8, 2), (8, 64, 4)])
-def test_row_sharded_mode_b_multi_field_equals_single_process_step(F, d, P):
+def test_row_sharded_mode_b_multi_field_equals_single_process_step(F, d, P, mode):
     """Mode B with F > 2 fields (config 4: pairwise interaction, per-group KL weights): P ranks
     emulated on one GPU against the single-process fused step on the global batch."""
     from vae_b200.dist import ShardedSampled
@@ -174,12 +193,14 @@ def test_row_sharded_mode_b_multi_field_equals_single_process_step(F, d, P):
     xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
     for _ in range(2):
         out_ref = ref.fused_step(xd, yd, noise=(e0.reshape(1, 1), eb_t[uniq][None], ee_t[uniq][None]))
+    from vae_b200.dist import LocalPeerGroup
+    ex = LocalPeerGroup(P) if mode == "fused" else object()
     ranks = [ShardedSampled(d, fs, torch.from_numpy(tc), B, B // P, P, p, output="class", kl_weighting="group",
-                            lr=0.05, init=ini, noise_tables=(e0, eb_t, ee_t), exchange=object()) for p in range(P)]
+                            lr=0.05, init=ini, noise_tables=(e0, eb_t, ee_t), exchange=ex) for p in range(P)]
     xs = [xd[p * (B // P):(p + 1) * (B // P)] for p in range(P)]
     ys = [yd[p * (B // P):(p + 1) * (B // P)] for p in range(P)]
     for _ in range(2):
-        outs = _run_sharded_emulated(ranks, xs, ys)
+        outs = (_run_sharded_fused if mode == "fused" else _run_sharded_emulated)(ranks, xs, ys)
     ent, bias = torch.zeros(R, 2 * d, device=DEV), torch.zeros(R, 2, device=DEV)
     for r in ranks:
         r.check_overflow()

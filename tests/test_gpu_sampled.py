@@ -201,6 +201,7 @@ def test_fused_step_updates_match_reference(name):
         mask[uniq] = False
         assert torch.equal(m.state_dict()["entity_params.weight"][mask], before["entity_params.weight"][mask])
         np.testing.assert_allclose(out["loss"].item(), g[f"step{t}.loss"][0], rtol=1e-5)
+        np.testing.assert_allclose(out["kl"].item(), g[f"step{t}.kl"][0], rtol=1e-5)
 
 
 def test_backward_is_bitwise_deterministic():
@@ -506,10 +507,70 @@ def test_predict_proba_many_samples_matches_oracle(output, F):
     np.testing.assert_allclose(lm.cpu().numpy(), logits.mean(0), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(pm.cpu().numpy(), lik_mean.mean(0), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(lv.cpu().numpy(), logits.var(0), rtol=1e-4, atol=1e-5)
-    # per-occurrence draws (vfm.py:440-445): same marginals -- compare the batch-averaged statistics loosely
-    pm2, lv2 = m.predict_proba(torch.from_numpy(x).to(DEV), n_samples=4 * S, per_occurrence=True)
+    # per-occurrence draws (vfm.py:440-445): same per-row marginals -- statistical comparison of the batch
+    # averages (the shared global-bias draw alone gives the mean logit a standard error of 0.5 / sqrt(S))
+    pm2, lv2, lm2 = m.predict_proba(torch.from_numpy(x).to(DEV), n_samples=4 * S, per_occurrence=True, return_logit_mean=True)
     assert abs(lv2.mean().item() - logits.var(0).mean()) < 0.25 * logits.var(0).mean()
-    assert abs(pm2.mean().item() - lik_mean.mean()) < 0.1 * max(abs(lik_mean.mean()), 0.1)
+    if F == 2:                                                        # E[logit] = the mean prediction when F = 2
+        assert abs(lm2.mean().item() - m.predict_mean(torch.from_numpy(x).to(DEV)).mean().item()) < 0.2
+
+
+def _guarded(t, pad=1024):
+    """A same-shape view into a larger allocation whose margins hold a canary pattern."""
+    flat = torch.empty(t.numel() + 2 * pad, dtype=t.dtype, device=t.device)
+    canary = torch.full((pad,), 0x5A if t.dtype == torch.uint8 else 12345, dtype=t.dtype, device=t.device)
+    flat[:pad], flat[-pad:] = canary, canary
+    view = flat[pad:pad + t.numel()].view(t.shape)
+    view.copy_(t)
+    return view, flat, canary
+
+
+@pytest.mark.parametrize("name", ["sampled_fraction", "sampled_reg_d64", "sampled_reg_d5"])
+def test_kernels_stay_inside_their_buffers(name):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are checked the plain way:
+    every plan array, scratch buffer and output of a step is re-homed inside a larger allocation with
+    canary margins (4 KB on both sides), full training steps run (plan, Philox and injected paths, F = 2
+    fused and unfused backward), and the margins must be untouched."""
+    from vae_b200 import _lib as L
+    from vae_b200.engine import BatchPlan
+    meta, g = gu.load(name)
+    m = _model(meta, g, 0, seed=13)
+    x, y = gu.batch_of(meta, g, 0)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    m.fused_step(xd, yd)                                    # allocates the pipeline and the step buffers
+    guards = []
+    buf = m._buf
+    for nm in ("vs", "ws", "es", "ebs", "cq", "grow", "gws", "pred", "mean", "resid", "rsorted", "partials",
+               "counters", "stats", "grad_scalars"):
+        t = getattr(buf, nm)
+        if t is not None:
+            v, flat, can = _guarded(t)
+            setattr(buf, nm, v)
+            guards.append((nm, flat, can))
+    m._fast_io = None
+    for plan in m._pipe.ring:
+        for nm in ("uniq", "inverse", "seg_off", "occ", "pos_of", "pos_rank", "partner", "urec", "class_off", "z",
+                   "meta", "hot", "workspace"):
+            v, flat, can = _guarded(getattr(plan, nm))
+            setattr(plan, nm, v)
+            guards.append((f"plan.{nm}", flat, can))
+        plan.struct = L.Plan(L.ptr(plan.uniq), L.ptr(plan.inverse), L.ptr(plan.seg_off), L.ptr(plan.occ),
+                             L.ptr(plan.pos_of), L.ptr(plan.pos_rank), L.ptr(plan.partner), L.ptr(plan.urec),
+                             L.ptr(plan.class_off), L.ptr(plan.z), L.ptr(plan.meta), L.ptr(plan.hot))
+    for reserve in (0, 1):                                  # fused k_gather_score / k_score + k_gather
+        L.check(L.lib().vfmb_set_grid_reserve(reserve))
+        try:
+            for _ in range(2):
+                out = m.fused_step(xd, yd)
+            m.fused_step(xd, yd, noise=_noise(g, 0))
+            m.gradients(xd, yd, noise=_noise(g, 0))
+        finally:
+            L.lib().vfmb_set_grid_reserve(0)
+    torch.cuda.synchronize()
+    assert np.isfinite(out["loss"].item())
+    pad = 1024
+    for nm, flat, can in guards:
+        assert torch.equal(flat[:pad], can) and torch.equal(flat[-pad:], can), f"write outside {nm}"
 
 
 def test_no_cpu_fallback():

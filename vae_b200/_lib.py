@@ -31,6 +31,7 @@ INTER_PROD, INTER_PAIRWISE = 0, 1
 ADAM_TOUCHED, GRAD_ONLY = 0, 1
 STATS = 32
 ST_RESID_S, ST_W0_S, MAX_SAMPLES = 8, 16, 8
+DP_TAIL, DP_T_NLL, DP_T_RESID, DP_T_SQERR, DP_T_KLROWS, DP_T_OVERFLOW = 16, 8, 9, 10, 11, 12
 ST_LOSS, ST_NLL_MEAN, ST_KL, ST_SUM_RESID, ST_SUM_SQERR, ST_KL_ROWS, ST_W0, ST_U = range(8)
 S_ALPHA, S_GB_MEAN, S_GB_SCALE, S_COUNT = 0, 1, 2, 4
 C_ALPHA, C_GB_MEAN, C_GB_SCALE, C_GB_PRIOR_MEAN, C_GB_PRIOR_SCALE = 0, 1, 2, 3, 4
@@ -125,6 +126,17 @@ SYMBOLS = {
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "vfmb_shard_unpack_grads": (C.c_int, [_P(Plan), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "vfmb_shard_route": (C.c_int, [_P(Plan), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vfmb_shard_stage_put": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "vfmb_shard_score": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
+    "vfmb_shard_gather_put": (C.c_int, [_P(Config), _P(Plan), _P(StepIO), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
+    "vfmb_shard_owner_update": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam), C.c_void_p, C.c_int32,
+                                          C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
                                           C.c_void_p]),
     "vfmb_adam_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   _P(Adam), C.c_void_p, C.c_void_p]),

@@ -407,9 +407,11 @@ k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_
         }
         flush(cur);
         // the group storing the last partial of a cut row adds them in tile order (step_common.cuh)
-        if (head_open) finish_cut_row<VEC, LPR, NV, 3>(first_u, tile, d, false, urec, gslot, vs2, grow, gws, arrive, n_tiles + 1);
+        if (head_open) finish_cut_row<VEC, LPR, NV, 3>(first_u, tile, d, nullptr, urec, gslot, grow + (size_t)first_u * 3 * d,
+                                                       gws + first_u, arrive, n_tiles + 1);
         if (tail_open && !(head_open && last_u == first_u))
-            finish_cut_row<VEC, LPR, NV, 3>(last_u, tile, d, false, urec, gslot, vs2, grow, gws, arrive, n_tiles + 1);
+            finish_cut_row<VEC, LPR, NV, 3>(last_u, tile, d, nullptr, urec, gslot, grow + (size_t)last_u * 3 * d, gws + last_u,
+                                            arrive, n_tiles + 1);
     }
 }
 

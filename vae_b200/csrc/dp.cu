@@ -2,7 +2,7 @@
 // gradient all-reduce (mode A).  The collective itself is NCCL through
 // torch.distributed; there is no reference counterpart (the reference is single-process), so
 // parity is defined against the single-process step on the global batch.
-#include "step_common.cuh"
+#include "sampled_common.cuh"
 
 namespace vfmb {
 
@@ -124,34 +124,8 @@ __global__ void k_dp_final(DevCfg c, float* __restrict__ scalars, float* __restr
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint32_t step = (uint32_t)adam_step[0];
     const uint32_t nstep = noise_step ? (uint32_t)noise_step[1] : step;    // noise index of the forward
-    float alpha = scalars[VFMB_S_ALPHA], mu0 = scalars[VFMB_S_GB_MEAN], rho0 = scalars[VFMB_S_GB_SCALE];
-    const float sig0 = link_fn<LINK>(rho0), ap = link_fn<LINK>(alpha);
-    float e0;
-    if (eps_global) e0 = eps_global[0];
-    else {
-        float n4[4];
-        philox_normal4(c.seed, 0xFFFFFFFFu, 0xFFFFFFFFu, nstep, philox_tag(kTagGlobal, 0), n4);
-        e0 = n4[0];
-    }
-    const double nll = (double)tail[VFMB_DP_T_NLL], sr = (double)tail[VFMB_DP_T_RESID], sq = (double)tail[VFMB_DP_T_SQERR];
-    const float kl0 = kl_std_normal(mu0, sig0);
-    const float kl = kl0 + stats[VFMB_ST_KL_ROWS];
-    stats[VFMB_ST_KL] = kl;
-    stats[VFMB_ST_NLL_MEAN] = (float)(nll / (double)c.B);
-    stats[VFMB_ST_LOSS] = (float)((double)c.n_train * nll / (double)c.B + (double)kl);
-    float g_mu0 = (float)(sr + (double)mu0);
-    float g_rho0 = link_grad<LINK>(rho0) * (float)((double)e0 * sr + (double)(sig0 - 1.f / sig0));
-    float ss, ib2;
-    adam_coeffs(h, (int)step + 1, &ss, &ib2);
-    adam_elem(mu0, sm[VFMB_S_GB_MEAN], sv[VFMB_S_GB_MEAN], g_mu0, h, ss, ib2);
-    adam_elem(rho0, sm[VFMB_S_GB_SCALE], sv[VFMB_S_GB_SCALE], g_rho0, h, ss, ib2);
-    scalars[VFMB_S_GB_MEAN] = mu0; scalars[VFMB_S_GB_SCALE] = rho0;
-    if (LIK == VFMB_GAUSSIAN) {
-        double sc = (double)c.n_train / ((double)c.S * (double)c.B);
-        float g_alpha = link_grad<LINK>(alpha) * (float)(sc * (0.5 * sq - 0.5 * (double)c.S * (double)c.B / (double)ap));
-        adam_elem(alpha, sm[VFMB_S_ALPHA], sv[VFMB_S_ALPHA], g_alpha, h, ss, ib2);
-        scalars[VFMB_S_ALPHA] = alpha;
-    }
+    dp_scalar_update<LINK>(LIK, c.S, c.B, c.n_train, c.seed, scalars, sm, sv, tail, eps_global, h, step, nstep, stats);
+    if (tail[VFMB_DP_T_OVERFLOW] > 0.f) stats[VFMB_ST_LOSS] = __int_as_float(0x7fc00000);   // a request bucket overflowed
     adam_step[0] = (int32_t)step + 1;
 }
 

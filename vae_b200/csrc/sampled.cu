@@ -37,7 +37,8 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         const int32_t* __restrict__ noise_step, float* __restrict__ vs, float* __restrict__ ws,
         float* __restrict__ es, float* __restrict__ ebs, float* __restrict__ cq,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
-        int smp, int u_stride, const float* __restrict__ pf_m, const float* __restrict__ pf_v) {
+        int smp, int u_stride, const float* __restrict__ pf_m, const float* __restrict__ pf_v, RowPut put) {
+    // put (mode B, owner side): the sampled row also goes into the slot of every rank that asked for it
     // pf_m / pf_v (optional): Adam moment tables whose touched rows are pulled into L2 here, while
     // this kernel is issue-bound on Philox and the DRAM pipe idles -- k_adam_rows finds them there
     // smp: variational sample this launch draws (S > 1: one launch per sample, outputs [S][u_stride]);
@@ -45,7 +46,8 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
     const int U = meta[0];
     const int d = c.d;
-    vs += (size_t)smp * u_stride * d; ws += (size_t)smp * u_stride;
+    if (vs) vs += (size_t)smp * u_stride * d;
+    if (ws) ws += (size_t)smp * u_stride;
     if (es) es += (size_t)smp * u_stride * d;
     if (ebs) ebs += (size_t)smp * u_stride;
     const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
@@ -59,11 +61,11 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         // ---- lane-parallel: one unique row per lane (first CH lanes)
         const int ul = base + lane;
         const bool valid = lane < CH && ul < U;
-        int rowid_l = 0;
-        float klb = 0.f, cqv = 0.f;
+        int rowid_l = 0, seg0_l = 0, len_l = 0;
+        float klb = 0.f, cqv = 0.f, w_l = 0.f;
         if (valid) {
             const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
-            rowid_l = rec.x;
+            rowid_l = rec.x; len_l = rec.y; seg0_l = rec.z;
             prefetch_row(entity + (size_t)rowid_l * 2 * d, 8 * d);
             if (pf_m) prefetch_row(pf_m + (size_t)rowid_l * 2 * d, 8 * d);
             if (pf_v) prefetch_row(pf_v + (size_t)rowid_l * 2 * d, 8 * d);
@@ -73,7 +75,8 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
             const float eb = bias_eps(eps_bias, c, ul, gid_l, step, smp, U);
             if (!eps_bias) ebs[ul] = eb;
             const float tau = link_fn<LINK>(ab.y);
-            ws[ul] = fmaf(eb, tau, ab.x);
+            w_l = fmaf(eb, tau, ab.x);
+            if (ws) ws[ul] = w_l;
             if (!LEAN) klb = kl_std_normal(ab.x, tau);
             const int cls = class_of(c, gid_l);
             float csz = 0.f, zc = 1.f;
@@ -89,6 +92,22 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
             const int sel = it * GPW + gidx;
             const int rowid = bcast(rowid_l, sel);
             const int u = base + sel;
+            // requesters of the row (mode B): its sorted occurrences in the owner's plan are request slots
+            int n_req = 0, seg0 = 0;
+            float w_u = 0.f;
+            if (put.pe.n) {
+                n_req = bcast(len_l, sel); seg0 = bcast(seg0_l, sel); w_u = bcast(w_l, sel);
+                if (u >= U || rowid >= put.n_real) n_req = 0;          // padding slots share a sentinel row
+            }
+            auto put_row = [&](int k, const Vec<VEC>& out) {
+                for (int i = 0; i < n_req; ++i) {
+                    const int sl = __ldg(put.occ + seg0 + i);
+                    const int q = sl / put.CAP, j = sl - q * put.CAP;
+                    float* dst = reinterpret_cast<float*>(put.pe.base[q]) + ((size_t)put.pe.rank * put.CAP + j) * put.SP;
+                    st_vec<VEC>(dst + k, out);
+                    if (k == 0) dst[d] = w_u;
+                }
+            };
             float kl = 0.f;
             if (u < U) {
                 const float* erow = entity + (size_t)rowid * 2 * d;
@@ -102,7 +121,8 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                         if (LEAN) {
 #pragma unroll
                             for (int j = 0; j < VEC; ++j) out.v[j] = fmaf(e.v[j], link_fn<LINK>(rho.v[j]), mu.v[j]);
-                            st_vec<VEC>(vs + (size_t)u * d + k, out);
+                            if (vs) st_vec<VEC>(vs + (size_t)u * d + k, out);
+                            put_row(k, out);
                             continue;
                         }
                         // sum_k KL(N(mu,sig)||N(0,1)) = 0.5 (sum sig^2 + mu^2 - 1) - 0.5 log prod sig^2:
@@ -123,7 +143,8 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                             for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho.v[j]); lg += logf(sg * sg); }
                         }
                         kl += 0.5f * (quad - lg);
-                        st_vec<VEC>(vs + (size_t)u * d + k, out);
+                        if (vs) st_vec<VEC>(vs + (size_t)u * d + k, out);
+                        put_row(k, out);
                     }
                 }
                 if (!LEAN) kl = group_sum<LPR>(kl, gmask);
@@ -154,7 +175,9 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         int32_t* noise_step, const int32_t* __restrict__ meta, float* __restrict__ pred, float* __restrict__ mean,
         float* __restrict__ resid, float* __restrict__ rsorted, float* __restrict__ msg,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
-        int defer_kl) {
+        int defer_kl, int vp, TailPut tp) {
+    // vp: pitch of the sampled rows in floats (d; mode B: the received slots, d + 4, bias sample at [d] and
+    // `inverse` holding slot indices; ws == NULL then).  tp: mode B, see TailPut.
     constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
     const int d = c.d, F = c.F, B = c.B;
     const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
@@ -179,9 +202,13 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         if (valid) {
             if (F == 2) {
                 rr = __ldg(reinterpret_cast<const int2*>(inverse) + nl);
-                bsum = __ldg(ws + rr.x) + __ldg(ws + rr.y);
+                bsum = ws ? __ldg(ws + rr.x) + __ldg(ws + rr.y)
+                          : __ldg(vs + (size_t)rr.x * vp + d) + __ldg(vs + (size_t)rr.y * vp + d);
             } else {
-                for (int f = 0; f < F; ++f) bsum += __ldg(ws + __ldg(inverse + (size_t)nl * F + f));
+                for (int f = 0; f < F; ++f) {
+                    const int r = __ldg(inverse + (size_t)nl * F + f);
+                    bsum += ws ? __ldg(ws + r) : __ldg(vs + (size_t)r * vp + d);
+                }
             }
             if (y) yn = __ldg(y + nl);
         }
@@ -204,8 +231,8 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
                 for (int i = 0; i < NV; ++i) {
                     int k = (gl + i * LPR) * VEC;
                     if (k < d && base + sel < B) {
-                        ra[it % HR][i] = ld_vec_nc<VEC>(vs + (size_t)r0 * d + k);
-                        rb[it % HR][i] = ld_vec_nc<VEC>(vs + (size_t)r1 * d + k);
+                        ra[it % HR][i] = ld_vec_nc<VEC>(vs + (size_t)r0 * vp + k);
+                        rb[it % HR][i] = ld_vec_nc<VEC>(vs + (size_t)r1 * vp + k);
                     }
                 }
 #if VFMB_SCORE_HOIST
@@ -246,7 +273,7 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
                         for (int i = 0; i < NV; ++i) {
                             int k = (gl + i * LPR) * VEC;
                             if (k < d) {
-                                Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r * d + k);
+                                Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r * vp + k);
 #pragma unroll
                                 for (int j = 0; j < VEC; ++j) { ssum[i].v[j] += a.v[j]; sq[i].v[j] = fmaf(a.v[j], a.v[j], sq[i].v[j]); }
                             }
@@ -313,6 +340,20 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
             stats[VFMB_ST_W0] = w0;
             forward_done(noise_step, step, meta, stats);
             *counter = 0;
+        }
+        if (tp.pe.n) {                       // mode B: this rank's additive scalars to every rank (peer stores)
+            __syncthreads();
+            if (threadIdx.x < VFMB_DP_TAIL) {
+                const int t = threadIdx.x;
+                float v = 0.f;
+                if (t == VFMB_DP_T_NLL) v = stats[VFMB_ST_NLL_MEAN] * tp.n_local;
+                else if (t == VFMB_DP_T_RESID) v = stats[VFMB_ST_SUM_RESID];
+                else if (t == VFMB_DP_T_SQERR) v = stats[VFMB_ST_SUM_SQERR];
+                else if (t == VFMB_DP_T_KLROWS) v = tp.stats_owner[VFMB_ST_KL_ROWS];
+                else if (t == VFMB_DP_T_OVERFLOW) v = (tp.overflow && tp.overflow[0]) ? 1.f : 0.f;
+                for (int q = 0; q < tp.pe.n; ++q)
+                    reinterpret_cast<float*>(tp.pe.base[q])[(size_t)tp.pe.rank * tp.pitch + t] = v;
+            }
         }
     }
 }
@@ -476,7 +517,10 @@ __global__ void __launch_bounds__(256, 2)
 k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
          const int32_t* __restrict__ urec, const float* __restrict__ vs, const float* __restrict__ msg,
          const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
-         int32_t* arrive) {
+         int32_t* arrive, int vp, float* const* __restrict__ gptr, const int32_t* __restrict__ own_slot) {
+    // mode B: vp = pitch of the gathered rows (received slots: d + 4); gptr[u] = where the finished gradient
+    // row of unique rank u goes (its owner's slot over NVLink, bias gradient at [d]); own_slot[u] = slot of
+    // the row itself (F > 2); rsorted == NULL (owner side, UNIT): the coefficient sits at [d] of the row
     constexpr int GPW = kWarp / LPR;
     const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
     const int lane = threadIdx.x & 31, gl = lane % LPR;
@@ -485,6 +529,7 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
     const int ngroups = gridDim.x * (blockDim.x >> 5) * GPW;
     const int n_tiles = (N + kTile - 1) / kTile;
     const float* table = (F == 2) ? vs : msg;
+    const int tpitch = (F == 2 || UNIT) ? vp : d;        // F > 2: the per-sample field sums are local, d wide
 
     for (int tile = group; tile < n_tiles; tile += ngroups) {
         const int t0 = tile * kTile, t1 = min(N, t0 + kTile);
@@ -500,18 +545,20 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
             for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
         float gw = 0.f;
 
+        auto row_out = [&](int u) { return gptr ? gptr[u] : grow + (size_t)u * d; };
+        auto own_row = [&](int u) { return vs + (size_t)(own_slot ? __ldg(own_slot + u) : u) * vp; };
         auto flush = [&](int u) {
             const bool open_h = head_open && u == first_u, open_t = tail_open && u == last_u;
             float* dst; float* dstw;
             if (open_h)      { dst = gslot + ((size_t)tile * 2) * dp;     dstw = dst + d; }
             else if (open_t) { dst = gslot + ((size_t)tile * 2 + 1) * dp; dstw = dst + d; }
-            else             { dst = grow + (size_t)u * d;                dstw = gws + u; }
+            else             { dst = row_out(u);                          dstw = gptr ? dst + d : gws + u; }
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 int k = (gl + i * LPR) * VEC;
                 if (k < d) {
                     if (F > 2 && !open_h && !open_t) {  // pairwise, complete row: sum r_n (S_n - v_u)
-                        Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
+                        Vec<VEC> own = ld_vec_nc<VEC>(own_row(u) + k);
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) acc[i].v[j] = fmaf(-gw, own.v[j], acc[i].v[j]);
                     }
@@ -524,8 +571,8 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
         for (int b0 = t0; b0 < t1; b0 += LPR) {
             const int idx = b0 + gl;
             const bool ok = idx < t1;
-            const float r = ok ? __ldg(rsorted + idx) : 0.f;
             const int src = ok ? __ldg(partner + idx) : 0;
+            const float r = !ok ? 0.f : (rsorted ? __ldg(rsorted + idx) : __ldg(table + (size_t)src * tpitch + d));
             const int ur = ok ? __ldg(pos_rank + idx) : 0;
             const int cnt = min(LPR, t1 - b0);
             const int src0 = __shfl_sync(gmask, src, 0, LPR);
@@ -541,7 +588,7 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
 #pragma unroll
                     for (int i = 0; i < NV; ++i) {
                         int k = (gl + i * LPR) * VEC;
-                        if (k < d) t[e][i] = ld_vec_nc<VEC>(table + (size_t)sj * d + k);
+                        if (k < d) t[e][i] = ld_vec_nc<VEC>(table + (size_t)sj * tpitch + k);
                     }
                 }
 #pragma unroll
@@ -571,9 +618,16 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
         }
         flush(cur);
         // rows cut by this tile's boundaries (at most two): whoever stores the last partial finishes the row
-        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, F > 2, urec, gslot, vs, grow, gws, arrive, n_tiles + 1);
-        if (tail_open && !(head_open && last_u == first_u))
-            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, F > 2, urec, gslot, vs, grow, gws, arrive, n_tiles + 1);
+        if (head_open) {
+            float* o = row_out(first_u);
+            finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, F > 2 ? own_row(first_u) : nullptr, urec, gslot, o,
+                                            gptr ? o + d : gws + first_u, arrive, n_tiles + 1);
+        }
+        if (tail_open && !(head_open && last_u == first_u)) {
+            float* o = row_out(last_u);
+            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, F > 2 ? own_row(last_u) : nullptr, urec, gslot, o,
+                                            gptr ? o + d : gws + last_u, arrive, n_tiles + 1);
+        }
     }
 }
 
@@ -719,9 +773,11 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
             }
         }
         flush(cur);
-        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, false, urec, gslot, vs, grow, gws, arrive, n_tiles + 1);
+        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, nullptr, urec, gslot, grow + (size_t)first_u * d,
+                                                       gws + first_u, arrive, n_tiles + 1);
         if (tail_open && !(head_open && last_u == first_u))
-            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, false, urec, gslot, vs, grow, gws, arrive, n_tiles + 1);
+            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, nullptr, urec, gslot, grow + (size_t)last_u * d, gws + last_u,
+                                            arrive, n_tiles + 1);
     }
     if (block_partials<3>(acc3, partials, counter)) {
         double tot[3];
@@ -784,7 +840,7 @@ extern "C" int64_t vfmb_partials_doubles(const vfmb_config* cfg) {
 
 // ---- internal launchers (the public entry points below are thin wrappers)
 static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                        const vfmb_step_io* io, vfmb_stream stream_, bool lean, int smp = 0) {
+                        const vfmb_step_io* io, vfmb_stream stream_, bool lean, int smp = 0, const RowPut* put_ = nullptr) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_stage", stream_, 1, &P);
     if (rc) return rc;
@@ -792,8 +848,10 @@ static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     if (!tab->noise_step) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: tables.noise_step required");
     if (!lean && !io->eps_entity && !io->es) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: noise scratch (es) required");
     if (!io->eps_bias && !io->ebs) return set_error(VFMB_EINVAL, "vfmb_sampled_stage: noise scratch (ebs) required");
-    if (!io->vs || !io->ws || !io->cq || !io->partials || !io->counters || !io->stats)
+    if (((!io->vs || !io->ws) && !put_) || !io->cq || !io->partials || !io->counters || !io->stats)
         return set_error(VFMB_EINVAL, "vfmb_sampled_stage: scratch required");
+    RowPut put{};
+    if (put_) put = *put_;
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch; const auto& cap = P.cap;
     // fused training step only: the row update follows within the same step
     const float* pf_m = (lean && (tuning().prefetch_mv & 1)) ? tab->entity_m : nullptr;
@@ -802,7 +860,7 @@ static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     k_stage<VEC, LPR, NV, LINK, LEAN><<<grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, ch), 256, 0, counted(stream)>>>( \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
         io->eps_bias, io->eps_entity, tab->noise_step, io->vs, io->ws, io->es,                         \
-        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap, pf_m, pf_v)
+        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap, pf_m, pf_v, put)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) { if (lean) LAUNCH_STAGE(0, 1); else LAUNCH_STAGE(0, 0); }
         else                            { if (lean) LAUNCH_STAGE(1, 1); else LAUNCH_STAGE(1, 0); }
@@ -812,8 +870,11 @@ static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     return 0;
 }
 
+// mode B, requester side: the sampled rows are read in place from the received slots
+struct ScoreB { const float* rows; int vp; const int32_t* inv_slot; TailPut tp; };
+
 static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                        const vfmb_step_io* io, vfmb_stream stream_, int defer_kl) {
+                        const vfmb_step_io* io, vfmb_stream stream_, int defer_kl, const ScoreB* sb = nullptr) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_score", stream_, 2, &P);
     if (rc) return rc;
@@ -821,11 +882,17 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     if (!tab->noise_step) return set_error(VFMB_EINVAL, "vfmb_sampled_score: tables.noise_step required");
     if (cfg->F > 2 && io->y && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_score: msg scratch required for F>2");
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch;
+    const float* rows = sb ? sb->rows : io->vs;
+    const float* wsp = sb ? nullptr : io->ws;
+    const int32_t* inv = sb ? sb->inv_slot : plan->inverse;
+    const int vp = sb ? sb->vp : cfg->d;
+    TailPut tp{};
+    if (sb) tp = sb->tp;
 #define LAUNCH_SCORE(LINK, LIK)                                                                        \
     k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, counted(stream)>>>( \
-        dc, tab->scalars, plan->inverse, plan->pos_of, io->vs, io->ws, io->y, io->eps_global,          \
+        dc, tab->scalars, inv, plan->pos_of, rows, wsp, io->y, io->eps_global,                         \
         tab->noise_step, plan->meta, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials, \
-        io->counters + 1, io->stats, defer_kl)
+        io->counters + 1, io->stats, defer_kl, vp, tp)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SCORE(0, VFMB_GAUSSIAN); else LAUNCH_SCORE(0, VFMB_BERNOULLI);
@@ -893,8 +960,13 @@ extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* t
     return launch_score(cfg, tab, plan, io, stream, 0);
 }
 
+// mode B: rows gathered in place from received slots (pitch vp), finished gradient rows stored through
+// gptr (requester side) / coefficient read from the row itself (owner side)
+struct GatherB { const float* rows; int vp; const int32_t* partner; float* const* gptr; const int32_t* own_slot; bool coef_in_row; };
+
 static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io_,
-                         const float* table, int32_t unit_coef, vfmb_stream stream_, int smp = 0) {
+                         const float* table, int32_t unit_coef, vfmb_stream stream_, int smp = 0,
+                         const GatherB* gb = nullptr) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_gather", stream_, 1, &P);
     if (rc) return rc;
@@ -908,7 +980,8 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
         if (shifted.msg) shifted.msg += (size_t)smp * cfg->B * cfg->d;
     }
     const vfmb_step_io* io = &shifted;
-    if (!io->grow || !io->gws || !io->rsorted || !io->partials) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: scratch required");
+    if (!io->grow || !io->gws || (!io->rsorted && !(gb && gb->coef_in_row)) || !io->partials)
+        return set_error(VFMB_EINVAL, "vfmb_sampled_gather: scratch required");
     const Layout& L = P.L; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
     // F == 2: partner rows come from the sampled-row scratch; otherwise from `table`
@@ -917,15 +990,21 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
     if (cfg->F != 2 && !tbl) return set_error(VFMB_EINVAL, "vfmb_sampled_gather: table required for F != 2");
     const int N = cfg->B * cfg->F;
     int32_t* arrive = (int32_t*)((float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).arrive_off);
+    const float* vsp = gb && gb->rows && !unit_coef ? gb->rows : io->vs;
+    const int vp = gb ? gb->vp : cfg->d;
+    const int32_t* partner = gb && gb->partner ? gb->partner : plan->partner;
+    float* const* gptr = gb ? gb->gptr : nullptr;
+    const int32_t* own_slot = gb ? gb->own_slot : nullptr;
+    const float* rs = (gb && gb->coef_in_row) ? nullptr : io->rsorted;
     VFMB_LAYOUT_SWITCH(L, {
         if (unit_coef)
             k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
-                cfg->d, cfg->F, N, plan->partner, plan->pos_rank, plan->urec, io->vs, tbl, io->rsorted,
-                gslot, io->grow, io->gws, arrive);
+                cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive,
+                vp, gptr, own_slot);
         else
             k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
-                cfg->d, cfg->F, N, plan->partner, plan->pos_rank, plan->urec, io->vs, tbl, io->rsorted, gslot, io->grow,
-                io->gws, arrive);
+                cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive,
+                vp, gptr, own_slot);
     });
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1035,6 +1114,83 @@ extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab,
     rc = launch_score(cfg, tab, plan, io, stream, 1);
     if (rc) return rc;
     return backward_impl(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, 2, stream);
+}
+
+// ------------------------------------------------------------------------------- mode B, fused
+// The phases of the row-sharded step with the exchanges written / read in place (NVLink peer memory):
+//   owner      vfmb_shard_stage_put     k_stage, the sampled row stored into every requester's slot
+//   requester  vfmb_shard_score         k_score on the received slots + the rank's additive scalars put
+//                                       into every rank's tail region by the block that finishes last
+//   requester  vfmb_shard_gather_put    k_gather on the received slots, finished gradient rows stored
+//                                       into their owners' slots
+//   owner      vfmb_shard_owner_update  k_gather over the received gradient slots (rank order) +
+//                                       k_adam_rows_pipe<3>: Adam on the owned rows, scalar parameters
+//                                       and loss from the ranks' tail slots
+// Two cross-rank barriers remain per step (after the rows, after the gradients); the caller issues them.
+static int make_peers_tab(const void* const* peers, int32_t P, int32_t rank, Peers* out) {
+    Peers pe{};
+    if (!peers || P < 1 || P > kMaxFields || rank < 0 || rank >= P) return set_error(VFMB_EINVAL, "peer table: bad P / rank");
+    for (int q = 0; q < P; ++q) {
+        if (!peers[q]) return set_error(VFMB_EINVAL, "peer table: null buffer of rank %d", q);
+        pe.base[q] = const_cast<void*>(peers[q]);
+    }
+    pe.n = P; pe.rank = rank;
+    *out = pe;
+    return 0;
+}
+
+extern "C" int vfmb_shard_stage_put(const vfmb_config* cfg_o, const vfmb_tables* tab, const vfmb_plan* plan_o,
+                                    const vfmb_step_io* io_o, int32_t CAP, int32_t SP, int32_t n_real,
+                                    const void* const* peers_rows, int32_t P, int32_t rank, vfmb_stream stream) {
+    if (!cfg_o || !plan_o || CAP < 1 || SP < cfg_o->d + 1 || (SP & 3)) return set_error(VFMB_EINVAL, "vfmb_shard_stage_put: bad argument");
+    if (cfg_o->S != 1) return set_error(VFMB_ESHAPE, "vfmb_shard_stage_put: S = 1 only");
+    RowPut put{};
+    int rc = make_peers_tab(peers_rows, P, rank, &put.pe);
+    if (rc) return rc;
+    put.occ = plan_o->occ; put.CAP = CAP; put.SP = SP; put.n_real = n_real;
+    return launch_stage(cfg_o, tab, plan_o, io_o, stream, false, 0, &put);
+}
+
+extern "C" int vfmb_shard_score(const vfmb_config* cfg_l, const vfmb_tables* tab, const vfmb_plan* plan_l,
+                                const vfmb_step_io* io_l, const float* recv_rows, int32_t SP, const int32_t* inv_slot,
+                                const void* const* peers_tail, int32_t P, int32_t rank, const float* stats_owner,
+                                const int32_t* overflow, float n_local, int32_t tail_pitch, vfmb_stream stream) {
+    if (!cfg_l || !recv_rows || !inv_slot || !stats_owner || tail_pitch < VFMB_DP_TAIL)
+        return set_error(VFMB_EINVAL, "vfmb_shard_score: bad argument");
+    if (cfg_l->S != 1) return set_error(VFMB_ESHAPE, "vfmb_shard_score: S = 1 only");
+    ScoreB sb{};
+    sb.rows = recv_rows; sb.vp = SP; sb.inv_slot = inv_slot;
+    int rc = make_peers_tab(peers_tail, P, rank, &sb.tp.pe);
+    if (rc) return rc;
+    sb.tp.stats_owner = stats_owner; sb.tp.overflow = overflow; sb.tp.n_local = n_local; sb.tp.pitch = tail_pitch;
+    return launch_score(cfg_l, tab, plan_l, io_l, stream, 0, &sb);
+}
+
+extern "C" int vfmb_shard_gather_put(const vfmb_config* cfg_l, const vfmb_plan* plan_l, const vfmb_step_io* io_l,
+                                     const float* recv_rows, int32_t SP, const int32_t* partner_slot,
+                                     float* const* gptr, const int32_t* own_slot, vfmb_stream stream) {
+    if (!cfg_l || !recv_rows || !partner_slot || !gptr || !own_slot) return set_error(VFMB_EINVAL, "vfmb_shard_gather_put: bad argument");
+    if (cfg_l->S != 1) return set_error(VFMB_ESHAPE, "vfmb_shard_gather_put: S = 1 only");
+    GatherB gb{};
+    gb.rows = recv_rows; gb.vp = SP; gb.partner = partner_slot; gb.gptr = gptr; gb.own_slot = own_slot; gb.coef_in_row = false;
+    return launch_gather(cfg_l, plan_l, io_l, nullptr, 0, stream, 0, &gb);
+}
+
+extern "C" int vfmb_shard_owner_update(const vfmb_config* cfg_o, const vfmb_tables* tab, const vfmb_plan* plan_o,
+                                       const vfmb_step_io* io_o, const vfmb_adam* adam, const float* recv_grads,
+                                       int32_t SP, const float* tail_slots, int32_t P, int32_t tail_pitch,
+                                       int32_t B_global, float n_train_global, float* stats_out,
+                                       const float* eps_global, vfmb_stream stream) {
+    if (!cfg_o || !recv_grads || !tail_slots || !stats_out || P < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_update: bad argument");
+    if (cfg_o->S != 1) return set_error(VFMB_ESHAPE, "vfmb_shard_owner_update: S = 1 only");
+    GatherB gb{};
+    gb.rows = nullptr; gb.vp = SP; gb.partner = nullptr; gb.gptr = nullptr; gb.own_slot = nullptr; gb.coef_in_row = true;
+    int rc = launch_gather(cfg_o, plan_o, io_o, recv_grads, 1, stream, 0, &gb);
+    if (rc) return rc;
+    DpTail dp{};
+    dp.tail_slots = tail_slots; dp.P = P; dp.pitch = tail_pitch; dp.B_global = B_global; dp.n_train_global = n_train_global;
+    dp.stats_out = stats_out; dp.eps_global = eps_global;
+    return launch_adam(cfg_o, tab, plan_o, io_o, adam, VFMB_ADAM_TOUCHED, 1.0f, 3, stream, &dp);
 }
 
 extern "C" int vfmb_philox_normals(const vfmb_config* cfg, const int32_t* uniq, int32_t U, int32_t step,

@@ -27,7 +27,7 @@ namespace vfmb {
 // ~4 us of serial tail (a dozen dependent L2 round trips + two fp64 pow) from the critical path.
 template <int LINK, int MODE>
 __device__ __forceinline__ void scalar_update(const DevCfg& c, const FinalArgs& fa, const AdamDev& h,
-                                              const int32_t* __restrict__ adam_step, float kl_scale) {
+                                              const int32_t* __restrict__ adam_step, float kl_scale, bool with_kl) {
     const uint32_t step = adam_step ? (uint32_t)adam_step[0] : 0u;            // Adam steps applied so far
     const uint32_t nstep = fa.noise_step ? (uint32_t)fa.noise_step[1] : 0u;   // noise index of the forward
     float* scalars = fa.scalars; float* stats = fa.stats;
@@ -41,7 +41,8 @@ __device__ __forceinline__ void scalar_update(const DevCfg& c, const FinalArgs& 
     } else {
         e0sr = (double)global_eps(fa.eps_global, c, nstep) * sr;
     }
-    stats[VFMB_ST_KL] = kl_std_normal(mu0, sig0);       // pre-update; finish_step adds the rows' KL
+    if (with_kl) stats[VFMB_ST_KL] = kl_std_normal(mu0, sig0);   // pre-update; finish_step adds the rows' KL
+                                                                 // (!with_kl: the forward already left the KL there)
     float g_mu0 = (float)(sr + (double)(kl_scale * mu0));
     float g_rho0 = link_grad<LINK>(rho0) * (float)(e0sr + (double)(kl_scale * (sig0 - 1.f / sig0)));
     float g_alpha = 0.f;
@@ -84,7 +85,7 @@ template <int LINK, int MODE>
 __device__ __forceinline__ void final_scalars(const DevCfg& c, const FinalArgs& fa, const AdamDev& h,
                                               int32_t* __restrict__ adam_step, float kl_scale,
                                               bool with_kl, double kl_rows, int U) {
-    scalar_update<LINK, MODE>(c, fa, h, adam_step, kl_scale);
+    scalar_update<LINK, MODE>(c, fa, h, adam_step, kl_scale, with_kl);
     finish_step<MODE>(fa, adam_step, with_kl, kl_rows, U);
 }
 
@@ -299,6 +300,7 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
                  AdamDev h, int32_t* __restrict__ adam_step, float kl_scale, FinalArgs fa) {
     constexpr int VEC = 4, GPW = kWarp / LPR, NS = kPipeStages;
     constexpr bool KLF = FLAVOR == 2;
+    constexpr bool DPF = FLAVOR == 3;    // mode B owner: scalar parameters + loss from the ranks' tail slots
     constexpr int MODE = VFMB_ADAM_TOUCHED;
     extern __shared__ float4 s_stage[];                   // [8 warps][NS][6][32 lanes]
     const int U = meta[0];
@@ -317,7 +319,23 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
     const bool split = FLAVOR >= 1 && gridDim.x > 1;
     const int row_warps = split ? nwarps - (int)(blockDim.x >> 5) : nwarps;
     const bool scalar_block = split && blockIdx.x == gridDim.x - 1;
-    if (scalar_block && threadIdx.x == 0) scalar_update<LINK, MODE>(c, fa, h, adam_step, kl_scale);
+    auto scalars_now = [&]() {
+        if (DPF) {                                        // the P ranks' additive scalars, added in rank order
+            float tail[VFMB_DP_TAIL];
+#pragma unroll
+            for (int t = 0; t < VFMB_DP_TAIL; ++t) tail[t] = 0.f;
+            for (int q = 0; q < fa.tail_P; ++q)
+#pragma unroll
+                for (int t = VFMB_DP_T_NLL; t <= VFMB_DP_T_OVERFLOW; ++t) tail[t] += __ldcg(fa.tail_slots + (size_t)q * fa.tail_pitch + t);
+            fa.stats[VFMB_ST_KL_ROWS] = tail[VFMB_DP_T_KLROWS];
+            dp_scalar_update<LINK>(fa.likelihood, c.S, fa.B_global, fa.n_train_global, c.seed, fa.scalars, fa.sm, fa.sv,
+                                   tail, fa.eps_global, h, step, nstep, fa.stats);
+            if (tail[VFMB_DP_T_OVERFLOW] > 0.f) fa.stats[VFMB_ST_LOSS] = __int_as_float(0x7fc00000);
+        } else {
+            scalar_update<LINK, MODE>(c, fa, h, adam_step, kl_scale, KLF);
+        }
+    };
+    if (scalar_block && threadIdx.x == 0) scalars_now();
     const int lo = scalar_block ? 0 : (int)((int64_t)gwarp * U / row_warps);
     const int hi = scalar_block ? 0 : (int)((int64_t)(gwarp + 1) * U / row_warps);
     const int k = gl * VEC;                               // this lane's 4 elements of the mean / scale halves
@@ -424,7 +442,7 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             double tot[1] = {0.0};
             if (KLF) final_sums<1>(fa.partials, tot);
             if (threadIdx.x == 0) {
-                if (!split) scalar_update<LINK, MODE>(c, fa, h, adam_step, kl_scale);
+                if (!split) scalars_now();
                 finish_step<MODE>(fa, adam_step, KLF, tot[0], U);
                 *fa.counter = 0;
             }
@@ -553,7 +571,7 @@ using namespace vfmb;
 // flavor: see k_adam_rows
 int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
                        const vfmb_step_io* io, const vfmb_adam* adam, int32_t mode, float kl_grad_scale,
-                       int flavor, vfmb_stream stream_) {
+                       int flavor, vfmb_stream stream_, const DpTail* dp) {
     Prep P;
     int rc = prep(cfg, "vfmb_sampled_adam_rows", stream_, 1, &P);
     if (rc) return rc;
@@ -582,6 +600,14 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
     fa.counter = io->counters ? io->counters + 2 : nullptr;
     fa.gslot = io->partials ? (const float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off : nullptr;
     fa.likelihood = cfg->likelihood; fa.noise_step = tab->noise_step;
+    if (flavor == 3) {
+        if (!dp || !dp->tail_slots || !dp->stats_out) return set_error(VFMB_EINVAL, "vfmb_shard_owner_update: tail slots required");
+        if (!(mode == VFMB_ADAM_TOUCHED && P.L.vec == 4 && P.L.nv == 1 && tuning().adam_pipe != 0))
+            return set_error(VFMB_ESHAPE, "vfmb_shard_owner_update: fused update needs d %% 4 == 0, d <= 128");
+        fa.tail_slots = dp->tail_slots; fa.tail_P = dp->P; fa.tail_pitch = dp->pitch;
+        fa.B_global = dp->B_global; fa.n_train_global = dp->n_train_global; fa.stats = dp->stats_out;
+        fa.eps_global = dp->eps_global;
+    }
     // the HBM-bound kernel keeps its full wave even next to the plan (measured: 113.8 vs 116.2 us/step)
     const bool adam_reserve = tuning().adam_reserve != 0;
     if (mode == VFMB_ADAM_TOUCHED && L.vec == 4 && L.nv == 1 && tuning().adam_pipe != 0) {
@@ -610,7 +636,7 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
         } while (0)
 #define LAUNCH_PIPE_F(LPR_, LINK)                                                                         \
         do { if (flavor == 0) LAUNCH_PIPE(LPR_, LINK, 0); else if (flavor == 1) LAUNCH_PIPE(LPR_, LINK, 1); \
-             else LAUNCH_PIPE(LPR_, LINK, 2); } while (0)
+             else if (flavor == 2) LAUNCH_PIPE(LPR_, LINK, 2); else LAUNCH_PIPE(LPR_, LINK, 3); } while (0)
 #define LAUNCH_PIPE_L(LPR_)                                                                               \
         do { if (cfg->link == VFMB_LINK_ABS) LAUNCH_PIPE_F(LPR_, 0); else LAUNCH_PIPE_F(LPR_, 1); } while (0)
         if (L.lpr == 4) LAUNCH_PIPE_L(4);

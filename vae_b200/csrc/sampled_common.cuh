@@ -58,7 +58,48 @@ struct FinalArgs {
     float* grad_scalars; double* partials; int32_t* counter; const float* gslot;
     const int32_t* noise_step;          // [1] = noise index of the forward this backward belongs to
     int likelihood;
+    // mode B owner update (k_adam_rows_pipe<FLAVOR 3>): the ranks' additive scalars, one slot per rank
+    const float* tail_slots; int tail_P, tail_pitch;
+    int B_global; float n_train_global;
 };
+
+// Mode B / mode A: scalar parameters (replicated on every rank, identical results) and the global-batch
+// loss from the ranks' additive scalars.  `tail` = the summed vector (VFMB_DP_T_*); stats[KL_ROWS] holds
+// the KL of the rows.  Does not touch the step counter.
+template <int LINK>
+__device__ __forceinline__ void dp_scalar_update(int likelihood, int S, int B, float n_train, uint64_t seed,
+                                                 float* __restrict__ scalars, float* __restrict__ sm, float* __restrict__ sv,
+                                                 const float* tail, const float* __restrict__ eps_global, const AdamDev& h,
+                                                 uint32_t step, uint32_t nstep, float* __restrict__ stats) {
+    float alpha = scalars[VFMB_S_ALPHA], mu0 = scalars[VFMB_S_GB_MEAN], rho0 = scalars[VFMB_S_GB_SCALE];
+    const float sig0 = link_fn<LINK>(rho0), ap = link_fn<LINK>(alpha);
+    float e0;
+    if (eps_global) e0 = eps_global[0];
+    else {
+        float n4[4];
+        philox_normal4(seed, 0xFFFFFFFFu, 0xFFFFFFFFu, nstep, philox_tag(kTagGlobal, 0), n4);
+        e0 = n4[0];
+    }
+    const double nll = (double)tail[VFMB_DP_T_NLL], sr = (double)tail[VFMB_DP_T_RESID], sq = (double)tail[VFMB_DP_T_SQERR];
+    const float kl0 = kl_std_normal(mu0, sig0);
+    const float kl = kl0 + stats[VFMB_ST_KL_ROWS];
+    stats[VFMB_ST_KL] = kl;
+    stats[VFMB_ST_NLL_MEAN] = (float)(nll / (double)B);
+    stats[VFMB_ST_LOSS] = (float)((double)n_train * nll / (double)B + (double)kl);
+    float g_mu0 = (float)(sr + (double)mu0);
+    float g_rho0 = link_grad<LINK>(rho0) * (float)((double)e0 * sr + (double)(sig0 - 1.f / sig0));
+    float ss, ib2;
+    adam_coeffs(h, (int)step + 1, &ss, &ib2);
+    adam_elem(mu0, sm[VFMB_S_GB_MEAN], sv[VFMB_S_GB_MEAN], g_mu0, h, ss, ib2);
+    adam_elem(rho0, sm[VFMB_S_GB_SCALE], sv[VFMB_S_GB_SCALE], g_rho0, h, ss, ib2);
+    scalars[VFMB_S_GB_MEAN] = mu0; scalars[VFMB_S_GB_SCALE] = rho0;
+    if (likelihood == VFMB_GAUSSIAN) {
+        double sc = (double)n_train / ((double)S * (double)B);
+        float g_alpha = link_grad<LINK>(alpha) * (float)(sc * (0.5 * sq - 0.5 * (double)S * (double)B / (double)ap));
+        adam_elem(alpha, sm[VFMB_S_ALPHA], sv[VFMB_S_ALPHA], g_alpha, h, ss, ib2);
+        scalars[VFMB_S_ALPHA] = alpha;
+    }
+}
 
 }  // namespace vfmb
 
@@ -95,8 +136,15 @@ static inline int prep(const vfmb_config* cfg, const char* who, vfmb_stream stre
                                              "vfmb_sampled_forward / _backward / _step for S > 1)")
 
 
-// row update (sampled_adam.cu); flavor: see k_adam_rows
+// mode B owner update: where the ranks' additive scalars sit and what the global batch is
+struct DpTail {
+    const float* tail_slots; int P, pitch;
+    int B_global; float n_train_global;
+    float* stats_out; const float* eps_global;
+};
+// row update (sampled_adam.cu); flavor: see k_adam_rows (3: mode B owner, needs `dp`)
 int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan, const vfmb_step_io* io,
-                const vfmb_adam* adam, int32_t mode, float kl_grad_scale, int flavor, vfmb_stream stream_);
+                const vfmb_adam* adam, int32_t mode, float kl_grad_scale, int flavor, vfmb_stream stream_,
+                const DpTail* dp = nullptr);
 int launch_adam_multi(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan, const vfmb_step_io* io,
                       const vfmb_adam* adam, int32_t mode, float kl_grad_scale, vfmb_stream stream_);

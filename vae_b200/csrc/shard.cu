@@ -10,8 +10,7 @@
 //
 // Slot layout of every exchange: [P, CAP, w] (w = 2 ints for ids, d+1 floats for rows), slot
 // q*CAP + j holds the j-th id (ascending) this rank asks of owner q; -1 / zeros = empty.
-#include "common.cuh"
-#include "internal.h"
+#include "step_common.cuh"
 
 namespace vfmb {
 
@@ -24,10 +23,6 @@ __device__ __forceinline__ int owner_of(int id, int P) { return id % P; }
 // all-to-all on it).  n == P: the exchange buffers of all ranks, peer-mapped over NVLink -- slot
 // (q, j) of this rank is written straight into chunk `rank` of rank q's buffer, so the pack kernel
 // IS the all-to-all (stores over NVSwitch; a barrier separates it from the consumer).
-struct Peers {
-    void* base[kMaxFields];
-    int n, rank;
-};
 template <typename T>
 __device__ __forceinline__ T* slot_ptr(const Peers& pe, T* local, int slot, int CAP, int width) {
     if (pe.n == 0) return local + (size_t)slot * width;
@@ -244,6 +239,34 @@ k_unpack_grads(const float* __restrict__ recv, const int32_t* __restrict__ occ, 
     }
 }
 
+// ---- fused mode B, requester side (id-only, off the critical path): where every row of the batch is
+// read from / written to once the exchanges are in place --
+//   inv_slot[o]      slot (in this rank's received-rows region) of the row of occurrence o = n*F + f
+//   partner_slot[i]  F == 2: slot of the partner row of sorted position i  (F > 2: the sample index)
+//   gptr[u]          where the gradient row of unique rank u goes: its owner's slot (over NVLink)
+// Overflowed rows (dest = M) map to the spare slot M (zeros) / the dump row.
+__global__ void __launch_bounds__(256)
+k_route(const int32_t* __restrict__ dest, const int32_t* __restrict__ inverse, const int32_t* __restrict__ partner,
+        const int32_t* __restrict__ meta, int N, int F, int u_cap, int M, int CAP, int SP, Peers pe, float* dump,
+        int32_t* __restrict__ inv_slot, int32_t* __restrict__ partner_slot, float** __restrict__ gptr) {
+    const int U = meta[0];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int o = tid; o < N; o += nth) {
+        inv_slot[o] = min(__ldg(dest + __ldg(inverse + o)), M);
+        const int pr = __ldg(partner + o);
+        partner_slot[o] = (F == 2) ? min(__ldg(dest + pr), M) : pr;
+    }
+    for (int u = tid; u < u_cap; u += nth) {
+        const int sl = u < U ? __ldg(dest + u) : M;
+        float* p = dump;
+        if (sl < M) {
+            const int q = sl / CAP, j = sl - q * CAP;
+            p = reinterpret_cast<float*>(pe.base[q]) + ((size_t)pe.rank * CAP + j) * SP;
+        }
+        gptr[u] = p;
+    }
+}
+
 static inline int warp_grid(int64_t items) {
     int64_t g = (items + 7) / 8;
     if (g < 1) g = 1;
@@ -288,6 +311,25 @@ extern "C" int vfmb_shard_bucket(const vfmb_plan* plan, int32_t u_cap, int32_t P
     k_bucket_count<<<nblk, kBkt, 0, counted(stream)>>>(plan->uniq, plan->meta, P, (int32_t*)workspace);
     k_bucket_place<<<nblk, kBkt, 0, counted(stream)>>>(plan->uniq, plan->urec, plan->meta, u_cap, P, CAP,
                                               (const int32_t*)workspace, send, dest, overflow, pe);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vfmb_shard_route(const vfmb_plan* plan_l, const int32_t* dest, int32_t B, int32_t F, int32_t u_cap,
+                                int32_t M, int32_t CAP, int32_t SP, const void* const* peers_grads, int32_t P,
+                                int32_t rank, float* dump, int32_t* inv_slot, int32_t* partner_slot, float** gptr,
+                                vfmb_stream stream_) {
+    if (!plan_l || !dest || !dump || !inv_slot || !partner_slot || !gptr || B < 1 || F < 1 || CAP < 1 || M != P * CAP)
+        return set_error(VFMB_EINVAL, "vfmb_shard_route: bad argument");
+    Peers pe;
+    int rc = make_peers(peers_grads, P, rank, &pe);
+    if (rc) return rc;
+    if (!pe.n) return set_error(VFMB_EINVAL, "vfmb_shard_route: peer table required");
+    const int N = B * F;
+    int g = (N + 255) / 256;
+    if (g > 4 * kNumSMs) g = 4 * kNumSMs;
+    k_route<<<g, 256, 0, counted((cudaStream_t)stream_)>>>(dest, plan_l->inverse, plan_l->partner, plan_l->meta, N, F, u_cap,
+                                                          M, CAP, SP, pe, dump, inv_slot, partner_slot, gptr);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -26,6 +26,30 @@ static DevCfg make_dev(const vfmb_config* c) {
     return r;
 }
 
+// ---- mode B (row-sharded tables): destinations in other ranks' exchange buffers (NVLink peer memory)
+// n == 0: not in use.  n == P: base[q] = the exchange region of rank q mapped into this process; this
+// rank owns chunk `rank` ([CAP] slots) of every region, slot (q, j) -> base[q] + (rank * CAP + j) * width.
+struct Peers {
+    void* base[kMaxFields];
+    int n, rank;
+};
+// k_stage, owner side: the sampled row of unique rank u goes straight into the slot of every rank that
+// asked for it (sorted occurrences of the owner's plan = request slots s; requester = s / CAP)
+struct RowPut {
+    Peers pe;
+    const int32_t* occ;
+    int CAP, SP, n_real;         // slot pitch in floats (d + 4: [row | bias, pad]); rows >= n_real are padding
+};
+// k_score, requester side: the rank's additive scalars {NLL sum, residual sum, squared-error sum, KL of
+// its owned rows, overflow flag} into slot `rank` of every rank's tail region (summed in rank order there)
+struct TailPut {
+    Peers pe;
+    const float* stats_owner;    // stats of this rank's owner-side stage (KL of the rows it owns)
+    const int32_t* overflow;     // sticky bucket-overflow flag of this rank
+    float n_local;
+    int pitch;
+};
+
 __device__ __forceinline__ int class_of(const DevCfg& c, int row) {
     int k = 0;
 #pragma unroll
@@ -215,9 +239,11 @@ __device__ __forceinline__ void sum_slots(const float* gslot, int dp, int d, int
 
 // called by every lane of a group after it stored the partial of cut row u for `tile`
 template <int VEC, int LPR, int NV, int NW>
-__device__ __noinline__ void finish_cut_row(int u, int tile, int d, bool own_fix, const int32_t* __restrict__ urec,
-                                               float* gslot, const float* __restrict__ vs, float* __restrict__ grow,
-                                               float* __restrict__ gws, int32_t* arrive, int n_tiles1) {
+__device__ __noinline__ void finish_cut_row(int u, int tile, int d, const float* __restrict__ own_row,
+                                            const int32_t* __restrict__ urec, float* gslot, float* __restrict__ out_row,
+                                            float* __restrict__ out_w, int32_t* arrive, int n_tiles1) {
+    // own_row (F > 2, pairwise): the row's own sampled vector, removed from the sum; out_row / out_w:
+    // where the finished gradient goes (the per-rank scratch, or the owner's slot over NVLink)
     const int lane = threadIdx.x & 31, gl = lane % LPR;
     const unsigned gmask = group_mask<LPR>();
     const int dp = NW * d + 4;
@@ -263,15 +289,15 @@ __device__ __noinline__ void finish_cut_row(int u, int tile, int d, bool own_fix
         for (int i = 0; i < NV; ++i) {
             const int k = (gl + i * LPR) * VEC;
             if (k < d) {
-                if (NW == 1 && own_fix) {                   // pairwise (F > 2): sum r_n (S_n - v_u)
-                    const Vec<VEC> own = ld_vec_nc<VEC>(vs + (size_t)u * d + k);
+                if (NW == 1 && own_row) {                   // pairwise (F > 2): sum r_n (S_n - v_u)
+                    const Vec<VEC> own = ld_vec_nc<VEC>(own_row + k);
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) tot[w][i].v[j] = fmaf(-gw, own.v[j], tot[w][i].v[j]);
                 }
-                st_vec<VEC>(grow + (size_t)u * NW * d + w * d + k, tot[w][i]);
+                st_vec<VEC>(out_row + w * d + k, tot[w][i]);
             }
         }
-    if (gl == 0) gws[u] = gw;
+    if (gl == 0) *out_w = gw;
 }
 
 

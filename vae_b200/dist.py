@@ -199,42 +199,77 @@ class TorchExchange:
 SMALL_PITCH = 32                                            # floats per rank slot of the small-vector regions
 
 
-class PeerExchange:
+def _region_layout(M: int, d: int, P: int):
+    """Regions of one rank's exchange buffer (bytes, 256-aligned): requests and Z_f twice (the requests of
+    batch i+1 travel while step i runs), sampled rows (+ one spare slot of zeros that overflowed rows are
+    routed to), row gradients, the ranks' additive scalars.  Slot pitch of rows / gradients: d + 4 floats."""
+    sp = d + 4
+    sizes = [("ids0", M * 2 * 4), ("ids1", M * 2 * 4), ("rows", (M + 1) * sp * 4), ("grads", M * sp * 4),
+             ("z0", P * SMALL_PITCH * 4), ("z1", P * SMALL_PITCH * 4), ("tail", P * SMALL_PITCH * 4)]
+    off, total = {}, 0
+    for name, nbytes in sizes:
+        off[name] = total
+        total += (nbytes + 255) // 256 * 256
+    return off, total
+
+
+class _ExchangeViews:
+    """Typed views of a rank's own exchange buffer + the pointer tables over all ranks' buffers."""
+
+    def _bind(self, buf: torch.Tensor, ptrs, M: int, d: int, P: int, rank: int):
+        self.P, self.rank, self.M, self.d, self.SP = P, rank, M, d, d + 4
+        self.buf = buf
+        self.tables = {name: (C.c_void_p * P)(*[p + o for p in ptrs]) for name, o in self.off.items()}
+        view = lambda name, n, dt: buf[self.off[name]: self.off[name] + n * 4].view(dt)
+        self.ids = [view(f"ids{k}", M * 2, torch.int32).view(M, 2) for k in (0, 1)]
+        self.rows = view("rows", (M + 1) * self.SP, torch.float32).view(M + 1, self.SP)
+        self.grads = view("grads", M * self.SP, torch.float32).view(M, self.SP)
+        self.z = [view(f"z{k}", P * SMALL_PITCH, torch.float32) for k in (0, 1)]
+        self.tail = view("tail", P * SMALL_PITCH, torch.float32)
+
+
+class PeerExchange(_ExchangeViews):
     """Exchange buffers of mode B as NVLink peer memory (torch symmetric memory): one symmetric
     allocation per rank, carved into the request / sampled-row / gradient / small-vector regions
-    and mapped into every process.  The pack kernels of ``csrc/shard.cu`` store straight into the
-    peers' regions, so there is no collective call on the data path -- only ``barrier()`` (a
-    signal-pad barrier kernel on the current stream) between a pack kernel and its consumer."""
+    and mapped into every process.  The step kernels of ``csrc/`` store straight into the peers'
+    regions and read their own in place, so there is no collective call on the data path -- only
+    ``barrier()`` (a signal-pad barrier kernel on the current stream) between producer and consumer."""
 
     def __init__(self, M: int, d: int, P: int, rank: int, device, group=None):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
-        self.P, self.rank, self.M, self.d = P, rank, M, d
-        # the request and Z_f regions exist twice: the requests of batch i+1 are exchanged while
-        # step i still runs (ShardedPipeline)
-        sizes = [("ids0", M * 2 * 4), ("ids1", M * 2 * 4), ("rows", M * (d + 1) * 4), ("grads", M * (d + 1) * 4),
-                 ("z0", P * SMALL_PITCH * 4), ("z1", P * SMALL_PITCH * 4), ("tail", P * SMALL_PITCH * 4)]
-        self.off, total = {}, 0
-        for name, nbytes in sizes:
-            self.off[name] = total
-            total += (nbytes + 255) // 256 * 256
-        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
-        self.buf.zero_()
-        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.off, total = _region_layout(M, d, P)
+        buf = symm.empty(total, dtype=torch.uint8, device=device)
+        buf.zero_()
+        self.hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        assert len(ptrs) == P and ptrs[rank] == self.buf.data_ptr()
-        self.tables = {name: (C.c_void_p * P)(*[p + off for p in ptrs]) for name, off in self.off.items()}
-        view = lambda name, n, dt: self.buf[self.off[name]: self.off[name] + n * 4].view(dt)
-        self.ids = [view(f"ids{k}", M * 2, torch.int32).view(M, 2) for k in (0, 1)]
-        self.rows = view("rows", M * (d + 1), torch.float32).view(M, d + 1)
-        self.grads = view("grads", M * (d + 1), torch.float32).view(M, d + 1)
-        self.z = [view(f"z{k}", P * SMALL_PITCH, torch.float32) for k in (0, 1)]
-        self.tail = view("tail", P * SMALL_PITCH, torch.float32)
+        assert len(ptrs) == P and ptrs[rank] == buf.data_ptr()
+        self._bind(buf, ptrs, M, d, P, rank)
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
 
     def barrier(self, channel: int = 0) -> None:
         self.hdl.barrier(channel=channel)
+
+
+class LocalPeerGroup:
+    """P emulated ranks on ONE device (tests, single-GPU debugging): the same exchange buffers as
+    ``PeerExchange``, ordinary allocations addressed through the same pointer tables.  Pass the group as
+    ``exchange=`` to every emulated ``ShardedSampled``.  The ranks must be driven phase by phase in lock
+    step (every rank finishes a phase before any rank starts the next); ``barrier()`` is then a no-op."""
+
+    def __init__(self, P: int):
+        self.P, self.bufs, self.off = int(P), None, None
+
+    def member(self, rank: int, M: int, d: int, device) -> "_ExchangeViews":
+        if self.bufs is None:
+            self.off, total = _region_layout(M, d, self.P)
+            self.bufs = [torch.zeros(total, dtype=torch.uint8, device=device) for _ in range(self.P)]
+        ex = _ExchangeViews()
+        ex.off = self.off
+        ex._bind(self.bufs[rank], [b.data_ptr() for b in self.bufs], M, d, self.P, rank)
+        ex.barrier = lambda channel=0: None
+        return ex
 
 
 class ShardedSampled:
@@ -261,7 +296,7 @@ class ShardedSampled:
                  n_train: float, batch_local: int, world: int, rank: int, output: str = "reg",
                  link: str = "abs", kl_weighting: str = "torch", seed: int = 7, lr: float = 1e-3,
                  betas=(0.9, 0.999), eps: float = 1e-8, device="cuda", exchange=None,
-                 init: Optional[dict] = None, noise_tables=None, slack: float = 1.0):
+                 init: Optional[dict] = None, noise_tables=None, slack: Optional[float] = None):
         from .engine import BatchPlan, StepBuffers, require_cuda
         self.device = require_cuda(device)
         L.lib()
@@ -272,7 +307,8 @@ class ShardedSampled:
         self.output, self.link = output, link
         self.adam = L.Adam(lr, betas[0], betas[1], eps)
         self._want_peer = isinstance(exchange, str) and exchange == "peer"
-        self.exchange = TorchExchange() if (exchange is None or self._want_peer) else exchange
+        self._local_group = exchange if isinstance(exchange, LocalPeerGroup) else None
+        self.exchange = TorchExchange() if (exchange is None or self._want_peer or self._local_group) else exchange
         self.peer = None
         self.noise_tables = noise_tables
         dev, d, P, p = self.device, self.d, self.P, self.p
@@ -325,7 +361,13 @@ class ShardedSampled:
         self.buf_l = StepBuffers(self.cfg_l, self.plan_l, dev, L.S_COUNT, need_msg=self.F > 2)
         # ---- owner side (received ids, local row indices)
         u_cap = self.plan_l.u_cap
-        self.CAP = int(-(-int(u_cap * slack) // P))
+        # slot capacity per owner.  Default: the expected share of a batch whose rows are all distinct plus
+        # six standard deviations of the multinomial split (ids are spread by id mod P), never more than an
+        # owner has rows.  `slack` (fraction of u_cap / P) overrides, e.g. 0.75 for Zipf batches whose unique
+        # count is known to stay below that; an overflow is flagged on the device and turns the loss into NaN
+        per = u_cap / P
+        cap = int(per + 6.0 * per ** 0.5 + 16) if slack is None else int(-(-int(u_cap * slack) // P))
+        self.CAP = max(1, min(cap, self.R_loc + 1))
         self.M = self.CAP * P
         self.cfg_o = mk(self.M, 1, Rl, self.n_train, P, p)
         self.plan_o = BatchPlan(self.M, 1, Rl, dev)
@@ -348,15 +390,27 @@ class ShardedSampled:
         # -- both plans, the slot map, the owner's copy of the requests, Z_f -- so that it can be
         # prepared for batch i+1 while step i runs (ShardedPipeline).  _use_slot(k) makes slot k
         # the one the phase methods work on.
-        self._slot_keys = ("plan_l", "plan_o", "_dest", "_ids_copy", "_loc", "_zg", "_y", "_io_o", "_recv_ids", "_noise_o")
+        # fused peer mode: where every row of the batch is read from / its gradient written to (vfmb_shard_route)
+        N = self.B * self.F
+        self.SP = d + 4
+        self.n_real = int(len(mine))
+        self._inv_slot, self._partner_slot = i32(N), i32(N)
+        self._gptr = torch.zeros(u_cap, dtype=torch.int64, device=dev)
+        self._dump = f32(self.SP)
+        self._slot_keys = ("plan_l", "plan_o", "_dest", "_ids_copy", "_loc", "_zg", "_y", "_io_o", "_recv_ids", "_noise_o",
+                           "_inv_slot", "_partner_slot", "_gptr")
         self._slots = [{k: getattr(self, k) for k in self._slot_keys},
                        {"plan_l": BatchPlan(self.B, self.F, self.R, dev), "plan_o": BatchPlan(self.M, 1, Rl, dev),
                         "_dest": i32(u_cap), "_ids_copy": i32(M, 2),
                         "_loc": torch.zeros((M, 1), dtype=torch.int64, device=dev), "_zg": f32(L.MAX_FIELDS),
-                        "_y": None, "_io_o": None, "_recv_ids": None, "_noise_o": None}]
+                        "_y": None, "_io_o": None, "_recv_ids": None, "_noise_o": None,
+                        "_inv_slot": i32(N), "_partner_slot": i32(N),
+                        "_gptr": torch.zeros(u_cap, dtype=torch.int64, device=dev)}]
         self._k = 0
         if self._want_peer:                                  # collective: every rank constructs it
             self.peer = PeerExchange(M, d, P, p, dev)
+        elif self._local_group is not None:
+            self.peer = self._local_group.member(p, M, d, dev)
 
     def _cfg(self, B, F, R, n_train, bounds, sizes, seed, stride, off):
         cfg = make_config(B, F, self.d, R, 1, self.output, self.link, bounds, sizes, n_train, seed)
@@ -391,8 +445,14 @@ class ShardedSampled:
                                           pe.tables[f"ids{self._k}"] if pe else None, self.p,
                                           current_stream(self.device)), "vfmb_shard_bucket")
         if pe:
+            s = current_stream(self.device)
             L.check(L.lib().vfmb_shard_put_small(pl.z.data_ptr(), L.MAX_FIELDS, SMALL_PITCH, pe.tables[f"z{self._k}"], P, self.p,
-                                                 current_stream(self.device)), "vfmb_shard_put_small")
+                                                 s), "vfmb_shard_put_small")
+            # id-only routing tables of the fused step: slots to read rows from, peer addresses of the gradients
+            L.check(L.lib().vfmb_shard_route(C.byref(pl.struct), self._dest.data_ptr(), self.B, self.F, pl.u_cap, M, CAP,
+                                             self.SP, pe.tables["grads"], P, self.p, self._dump.data_ptr(),
+                                             self._inv_slot.data_ptr(), self._partner_slot.data_ptr(), self._gptr.data_ptr(), s),
+                    "vfmb_shard_route")
             return None, None
         return self._send.view(P, CAP, 2), pl.z.clone()
 
@@ -429,10 +489,9 @@ class ShardedSampled:
 
     @torch.no_grad()
     def _owner_sample(self):
-        """Owner: draw the noise of the requested rows, reply with the sampled rows."""
+        """Owner (collective path): draw the noise of the requested rows, reply with the sampled rows."""
         M, d, P, p = self.M, self.d, self.P, self.p
-        pe = self.peer
-        recv = self._ids_copy if pe else self._recv_ids      # peer mode: the slot's private copy of the requests
+        recv = self._recv_ids
         po, bo, lib, s = self.plan_o, self.buf_o, L.lib(), current_stream(self.device)
         noise = None
         if self.noise_tables is not None:                     # tests: per-entity noise tables
@@ -444,18 +503,16 @@ class ShardedSampled:
         L.check(L.lib().vfmb_sampled_stage(C.byref(self.cfg_o), C.byref(self._tables()), C.byref(po.struct),
                                            C.byref(self._io_o), current_stream(self.device)), "vfmb_sampled_stage")
         L.check(lib.vfmb_shard_owner_pack(C.byref(po.struct), recv.data_ptr(), M, self.CAP, d, bo.vs.data_ptr(),
-                                          bo.ws.data_ptr(), self._reply.data_ptr(), 0,
-                                          pe.tables["rows"] if pe else None, self.p, s), "vfmb_shard_owner_pack")
-        return None if pe else self._reply.view(P, self.CAP, d + 1)
+                                          bo.ws.data_ptr(), self._reply.data_ptr(), 0, None, self.p, s), "vfmb_shard_owner_pack")
+        return self._reply.view(P, self.CAP, d + 1)
 
     @torch.no_grad()
     def phase_local(self, recv_rows: torch.Tensor):
-        """Requester: place the sampled rows, score the samples, ordered segmented reduction.
-        Returns (row gradients [P,CAP,d+1] in slot layout, additive scalars tail [16])."""
+        """Requester (collective path): place the sampled rows, score the samples, ordered segmented
+        reduction.  Returns (row gradients [P,CAP,d+1] in slot layout, additive scalars tail [16])."""
         M, d, P = self.M, self.d, self.P
         pl, bl = self.plan_l, self.buf_l
-        pe = self.peer
-        recv_rows = pe.rows if pe else recv_rows.contiguous()
+        recv_rows = recv_rows.contiguous()
         lib, s = L.lib(), current_stream(self.device)
         L.check(lib.vfmb_shard_unpack_rows(C.byref(pl.struct), recv_rows.data_ptr(), self._dest.data_ptr(), pl.u_cap, M, d,
                                            bl.vs.data_ptr(), bl.ws.data_ptr(), s), "vfmb_shard_unpack_rows")
@@ -463,7 +520,7 @@ class ShardedSampled:
         io = bl.io(y=self._y)
         io.eps_global = L.ptr(e0)
         self._io_l = io
-        tab, s, lib = self._tables(), current_stream(self.device), L.lib()
+        tab = self._tables()
         L.check(lib.vfmb_sampled_score(C.byref(self.cfg_l), C.byref(tab), C.byref(pl.struct), C.byref(io), s),
                 "vfmb_sampled_score")
         L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_l), C.byref(pl.struct), C.byref(io), None, 0, s),
@@ -471,31 +528,19 @@ class ShardedSampled:
         L.check(lib.vfmb_shard_pack_grads(C.byref(pl.struct), bl.grow.data_ptr(), bl.gws.data_ptr(), self._dest.data_ptr(),
                                           pl.u_cap, M, self.CAP, d, self._gsend.data_ptr(), bl.stats.data_ptr(),
                                           self.buf_o.stats.data_ptr(), float(self.B), self.tail.data_ptr(),
-                                          self._tail_idx, DP_TAIL, pe.tables["grads"] if pe else None, self.p, s),
-                "vfmb_shard_pack_grads")
-        if pe:
-            L.check(lib.vfmb_shard_put_small(self.tail.data_ptr(), DP_TAIL, SMALL_PITCH, pe.tables["tail"], P, self.p, s),
-                    "vfmb_shard_put_small")
-            return None, None
+                                          self._tail_idx, DP_TAIL, None, self.p, s), "vfmb_shard_pack_grads")
+        self.tail[L.DP_T_OVERFLOW] = self.overflow[0].to(torch.float32)      # any rank's overflow -> NaN loss everywhere
         return self._gsend.view(P, self.CAP, d + 1), self.tail
 
     @torch.no_grad()
     def phase_owner_update(self, recv_g: torch.Tensor, tail_global: torch.Tensor) -> dict:
-        """Owner: add a row's gradients in source-rank order, KL gradient + Adam on the owned rows,
-        replicated scalar update."""
+        """Owner (collective path): add a row's gradients in source-rank order, KL gradient + Adam on the
+        owned rows, replicated scalar update."""
         M, d = self.M, self.d
         po, bo = self.plan_o, self.buf_o
-        pe = self.peer
         io, tab, s, lib = self._io_o, self._tables(), current_stream(self.device), L.lib()
-        if pe:
-            recv_g = pe.grads
-            L.check(lib.vfmb_shard_sum_small(pe.tail.data_ptr(), self.P, DP_TAIL, SMALL_PITCH, self._tailg.data_ptr(), s),
-                    "vfmb_shard_sum_small")
-            tail_global = self._tailg
-        else:
-            recv_g = recv_g.contiguous()
-        L.check(lib.vfmb_shard_unpack_grads(C.byref(po.struct), recv_g.data_ptr(),
-                                            self._ids_copy.data_ptr() if pe else None, M, d, self._table.data_ptr(),
+        recv_g = recv_g.contiguous()
+        L.check(lib.vfmb_shard_unpack_grads(C.byref(po.struct), recv_g.data_ptr(), None, M, d, self._table.data_ptr(),
                                             bo.rsorted.data_ptr(), s), "vfmb_shard_unpack_grads")
         L.check(lib.vfmb_sampled_gather(C.byref(self.cfg_o), C.byref(po.struct), C.byref(io), self._table.data_ptr(), 1, s),
                 "vfmb_sampled_gather")
@@ -546,18 +591,67 @@ class ShardedSampled:
         self._owner_prepare(None, None)
 
     def _phase_b(self, mark=lambda name: None) -> dict:
-        """Peer mode, the parameter-dependent part of the step (current slot)."""
-        self._owner_sample()
+        """Peer mode, the parameter-dependent part of the step (current slot), fused: five kernels and two
+        barriers -- the sampled rows are stored by the stage kernel straight into the requesters' slots,
+        scored and gathered in place, the gradient rows stored by the gather kernel into the owners' slots
+        and summed / applied there together with the scalar parameters."""
+        self._b_stage()
         mark("owner_stage")
         self.peer.barrier(1)
         mark("a2a_rows")
-        self.phase_local(None)
+        self._b_local()
         mark("local")
         self.peer.barrier(2)
         mark("a2a_grads")
-        out = self.phase_owner_update(None, None)
+        out = self._b_update()
         mark("owner_update")
         return out
+
+    @torch.no_grad()
+    def _b_stage(self) -> None:
+        """Owner: sample the requested rows into the requesters' slots (k_stage with peer stores)."""
+        pe, po, bo, P, p = self.peer, self.plan_o, self.buf_o, self.P, self.p
+        noise = None
+        if self.noise_tables is not None:                     # tests: per-entity noise tables
+            e0_t, eb_t, ee_t = self.noise_tables
+            gid = (po.uniq.long() * P + p).clamp_(min=0, max=self.R - 1)   # ranks >= U hold garbage ids
+            noise = (e0_t.reshape(1).contiguous(), eb_t[gid].contiguous(), ee_t[gid].contiguous())
+        self._noise_o = noise
+        self._io_o = bo.io(noise=noise)
+        L.check(L.lib().vfmb_shard_stage_put(C.byref(self.cfg_o), C.byref(self._tables()), C.byref(po.struct),
+                                             C.byref(self._io_o), self.CAP, self.SP, self.n_real, pe.tables["rows"], P, p,
+                                             current_stream(self.device)), "vfmb_shard_stage_put")
+
+    @torch.no_grad()
+    def _b_local(self) -> None:
+        """Requester: score the samples and reduce the gradients on the received slots, in place; the
+        finished gradient rows and the rank's additive scalars go to their owners / to every rank."""
+        pe, pl, bl, bo, P, p, SP = self.peer, self.plan_l, self.buf_l, self.buf_o, self.P, self.p, self.SP
+        lib, s, tab = L.lib(), current_stream(self.device), self._tables()
+        e0 = self._noise_o[0] if self._noise_o is not None else None
+        io = bl.io(y=self._y)
+        io.eps_global = L.ptr(e0)
+        self._io_l = io
+        L.check(lib.vfmb_shard_score(C.byref(self.cfg_l), C.byref(tab), C.byref(pl.struct), C.byref(io), pe.rows.data_ptr(), SP,
+                                     self._inv_slot.data_ptr(), pe.tables["tail"], P, p, bo.stats.data_ptr(),
+                                     self.overflow.data_ptr(), float(self.B), SMALL_PITCH, s), "vfmb_shard_score")
+        L.check(lib.vfmb_shard_gather_put(C.byref(self.cfg_l), C.byref(pl.struct), C.byref(io), pe.rows.data_ptr(), SP,
+                                          self._partner_slot.data_ptr(), self._gptr.data_ptr(), self._dest.data_ptr(), s),
+                "vfmb_shard_gather_put")
+
+    @torch.no_grad()
+    def _b_update(self) -> dict:
+        """Owner: ordered sum of the received gradients, Adam on the owned rows, scalar parameters, loss."""
+        pe, po, bl = self.peer, self.plan_o, self.buf_l
+        e0 = self._noise_o[0] if self._noise_o is not None else None
+        st = bl.stats
+        L.check(L.lib().vfmb_shard_owner_update(C.byref(self.cfg_o), C.byref(self._tables()), C.byref(po.struct),
+                                                C.byref(self._io_o), C.byref(self.adam), pe.grads.data_ptr(), self.SP,
+                                                pe.tail.data_ptr(), self.P, SMALL_PITCH, self.B * self.P, float(self.n_train),
+                                                st.data_ptr(), L.ptr(e0), current_stream(self.device)),
+                "vfmb_shard_owner_update")
+        return {"loss": st[L.ST_LOSS], "kl": st[L.ST_KL], "nll_mean": st[L.ST_NLL_MEAN],
+                "pred": bl.mean[: self.B], "stats": st}
 
     def graphed_step(self):
         """Capture one whole step -- both plans, every kernel and the NCCL collectives -- in a CUDA
