@@ -560,9 +560,12 @@ def run_sharded(args):
     ms_e = e0.elapsed_time(e1)
 
     # where the step time goes: CUDA events between the phases, over a few extra steps
+    from vae_b200 import _lib as L
     model.enable_timing(True)
+    n0 = int(L.lib().vfmb_launch_count())
     for i in range(W + K, W + K + 20):
         model.step(*batch(i))
+    launches_per_step = (int(L.lib().vfmb_launch_count()) - n0) / 20
     phases = {k: round(v, 4) for k, v in model.phase_times().items()}
     model.enable_timing(False)
 
@@ -577,6 +580,10 @@ def run_sharded(args):
     t = torch.tensor([ms, ms_e], device=device, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e = float(t[0].item()), float(t[1].item())
+    try:
+        parity = sharded_parity(args, w, tc, lr, kl, exchange, device, rank, world)
+    except Exception as exc:                                   # never lose the timing line to the check
+        parity = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         peak, peak_src = peaks()
         # per step: every rank reads its ids/targets and writes predictions; every touched row of the
@@ -598,8 +605,8 @@ def run_sharded(args):
                        "l2": "consecutive distinct batches, no flush",
                        "parallelism": (f"sharded{world}: rows r mod {world}; per step 3 exchanges (ids, sampled rows, row "
                                        f"gradients; {a2a / 1e6:.1f} MB of slots per rank) "
-                                       + ("written by the pack kernels straight into the peers' buffers over NVLink "
-                                          "(symmetric memory), 3 signal-pad barriers, no collective calls"
+                                       + ("written by the step kernels themselves straight into the peers' buffers over "
+                                          "NVLink (symmetric memory) and read in place, 3 signal-pad barriers, no collective calls"
                                           if exchange == "peer" else "as NCCL all-to-alls + 2 small all-reduces")
                                        + f"; global batch {B * world}")},
             "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": step_bytes / (ms / K * 1e-3) / 1e9,
@@ -607,10 +614,10 @@ def run_sharded(args):
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes": step_bytes},
             "e2e": {"value": Ke * B * world / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * F * 8 + B * 4,
                     "d2h_bytes_per_step": 16 * 4, "steps": Ke, "ms_per_step": ms_e / Ke},
-            # own kernels per rank and step: part A 25 (two plans of 9, bucketing 3, request / Z_f glue 4),
-            # part B 14 (stage, pack, unpack, score, gather + combine twice, pack, glue 3, adam_rows, scalars);
-            # the 3 barriers are torch symmetric-memory kernels (peer) / the collectives are NCCL (nccl)
-            "gpu_launches": 39 * K * world, "clocks": clocks, "final_loss": loss, "phase_ms": phases,
+            # own kernels per rank and step, counted by the library over a few eager steps (the barriers are
+            # torch symmetric-memory kernels / the collectives NCCL and are not counted)
+            "gpu_launches": launches_per_step * K * world, "gpu_launches_per_step_per_rank": launches_per_step,
+            "clocks": clocks, "final_loss": loss, "phase_ms": phases, "parity": parity,
         }
         print(json.dumps(out_json), flush=True)
     torch.cuda.synchronize()
@@ -621,6 +628,66 @@ def run_sharded(args):
         sys.stdout.flush(); sys.stderr.flush()
         os._exit(0)
     dist.destroy_process_group()
+
+
+def sharded_parity(args, w, tc, lr, kl, exchange, device, rank, world):
+    """Real-rank parity of mode B (outside the timed region): one sharded step on the global batch (the
+    concatenation of the ranks' first batches, in-kernel Philox noise) against the single-process fused step
+    on that batch from the same seeded parameters.  Noise is keyed by the global row id, so both draw the
+    same values.  Tables that do not fit one GPU are skipped."""
+    import torch.distributed as dist
+    from vae_b200.dist import ShardedSampled
+    if w.rows > 5_000_000:
+        return {"skipped": "table does not fit one GPU for the single-process reference step"}
+    B, d = w.batch, w.d
+    torch.manual_seed(synth.PARAM_SEED)
+    from vae_b200.vfm_torch import CF
+    ref = CF(d, output=w.output, n_users=w.field_sizes[0], n_items=w.field_sizes[1], train_counts=torch.from_numpy(tc),
+             field_sizes=w.field_sizes, kl_weighting=kl, n_train=w.n_train, max_batch=B * world, seed=synth.NOISE_SEED,
+             lr=lr, device=device)                              # same seed on every rank: same initial parameters
+    init = {"bias": ref.bias_params.weight.detach().cpu(), "entity": ref.entity_params.weight.detach().cpu(),
+            "alpha": float(ref.alpha.item()), "global_bias_mean": float(ref.global_bias_mean.item()),
+            "global_bias_scale": float(ref.global_bias_scale.item())}
+    sh = ShardedSampled(d, w.field_sizes, torch.from_numpy(tc), w.n_train, B, world, rank, output=w.output,
+                        kl_weighting=kl, seed=synth.NOISE_SEED, lr=lr, device=device, slack=args.slack,
+                        exchange="peer" if exchange == "peer" else None, init=init)
+    xl = torch.from_numpy(w.x[rank * B:(rank + 1) * B]).to(device)
+    yl = torch.from_numpy(w.y[rank * B:(rank + 1) * B]).to(device)
+    out = sh.step(xl, yl)
+    torch.cuda.synchronize()
+    sh.check_overflow()
+    gid, bias_l, ent_l = sh.gather_tables()
+    n_max = (w.rows + world - 1) // world
+    pad = lambda t: torch.cat((t, torch.zeros((n_max - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=device)))
+    ents = [torch.empty((n_max, 2 * d), device=device) for _ in range(world)]
+    biases = [torch.empty((n_max, 2), device=device) for _ in range(world)]
+    dist.all_gather(ents, pad(ent_l))
+    dist.all_gather(biases, pad(bias_l))
+    res = None
+    if rank == 0:
+        xg = torch.from_numpy(w.x[: world * B]).to(device)
+        yg = torch.from_numpy(w.y[: world * B]).to(device)
+        r = ref.fused_step(xg, yg)
+        torch.cuda.synchronize()
+        ent = torch.empty((w.rows, 2 * d), device=device)
+        bia = torch.empty((w.rows, 2), device=device)
+        for q in range(world):
+            n = len(range(q, w.rows, world))
+            ent[q::world], bia[q::world] = ents[q][:n], biases[q][:n]
+        want = ref.entity_params.weight.detach()
+        err = (ent - want).abs()
+        tol = 1e-5 * want.abs() + 1e-4 * lr
+        res = {"what": f"one mode-B step on {world} ranks vs the single-process fused step on the global batch "
+                       f"({world * B} samples), same seeded parameters, in-kernel Philox noise",
+               "loss_rel_err": abs(out["loss"].item() - r["loss"].item()) / abs(r["loss"].item()),
+               "params_max_err_over_lr": float((err.max() / lr).item()),
+               "params_fraction_outside_1e-5rel+1e-4lr": float((err > tol).float().mean().item()),
+               "bias_max_err_over_lr": float(((bia - ref.bias_params.weight.detach()).abs().max() / lr).item()),
+               "scalars_max_abs_err": float((sh.scalars[:3] - ref._scalars[:3]).abs().max().item())}
+    dist.barrier()
+    del sh, ref
+    torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
-"""torchrun -N: mode B over NVLink peer memory vs over NCCL all-to-alls -- same inputs, same init;
-parameters, loss and predictions must agree (only the small all-reduces differ in summation order)."""
+"""torchrun -N: mode B fused over NVLink peer memory vs the unfused phases over NCCL all-to-alls -- same
+inputs, same init; parameters, loss and predictions must agree; the software-pipelined CUDA graphs must
+equal the serial peer steps bit for bit."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -44,7 +45,7 @@ for it in range(nb):
     o = pipe.step(*bat(it + 1)) if it + 1 < nb else pipe.step()
 torch.cuda.synchronize()
 for name in ("entity", "bias", "entity_m", "entity_v", "scalars"):
-    ta, tc_ = getattr(a, name), getattr(c, name)
+    ta, tc_ = getattr(b, name), getattr(c, name)             # serial peer steps vs the pipelined graphs
     assert torch.equal(ta, tc_), (name, (ta - tc_).abs().max().item())
 assert abs(o["loss"].item() - la) <= 1e-6 * abs(la)
 if rank == 0:
