@@ -289,9 +289,9 @@ int vfmb_shard_unpack_grads(const vfmb_plan* plan_o, const float* recv_g, const 
  *                            overflow flag} into slot `rank` of every rank's tail region
  *   vfmb_shard_gather_put    requester: k_gather on the received slots; finished gradient rows are stored
  *                            through gptr into their owners' slots
- *   vfmb_shard_owner_update  owner: ordered sum of the received gradient slots (source-rank order), Adam on
- *                            the owned rows, scalar parameters + global-batch loss from the tail slots
- *                            (NaN when any rank flagged a bucket overflow), step counter               */
+ *   vfmb_shard_owner_update  owner, ONE kernel: a row's gradient = the slots its requesters stored, added in
+ *                            source-rank order; Adam on the owned rows; scalar parameters + global-batch
+ *                            loss from the tail slots (NaN when any rank flagged a bucket overflow)      */
 int vfmb_shard_route(const vfmb_plan* plan_l, const int32_t* dest, int32_t B, int32_t F, int32_t u_cap,
                      int32_t M, int32_t CAP, int32_t SP, const void* const* peers_grads, int32_t P,
                      int32_t rank, float* dump, int32_t* inv_slot, int32_t* partner_slot, float** gptr,
@@ -308,7 +308,7 @@ int vfmb_shard_gather_put(const vfmb_config* cfg_l, const vfmb_plan* plan_l, con
                           float* const* gptr, const int32_t* own_slot, vfmb_stream stream);
 int vfmb_shard_owner_update(const vfmb_config* cfg_o, const vfmb_tables* tab, const vfmb_plan* plan_o,
                             const vfmb_step_io* io_o, const vfmb_adam* adam, const float* recv_grads,
-                            int32_t SP, const float* tail_slots, int32_t P, int32_t tail_pitch,
+                            int32_t SP, int32_t n_real, const float* tail_slots, int32_t P, int32_t tail_pitch,
                             int32_t B_global, float n_train_global, float* stats_out,
                             const float* eps_global, vfmb_stream stream);
 

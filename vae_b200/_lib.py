@@ -136,8 +136,8 @@ SYMBOLS = {
     "vfmb_shard_gather_put": (C.c_int, [_P(Config), _P(Plan), _P(StepIO), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
     "vfmb_shard_owner_update": (C.c_int, [_P(Config), _P(Tables), _P(Plan), _P(StepIO), _P(Adam), C.c_void_p, C.c_int32,
-                                          C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
-                                          C.c_void_p]),
+                                          C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     "vfmb_adam_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   _P(Adam), C.c_void_p, C.c_void_p]),
     "vfmb_adam_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),

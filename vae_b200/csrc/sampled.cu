@@ -1123,8 +1123,8 @@ extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab,
 //                                       into every rank's tail region by the block that finishes last
 //   requester  vfmb_shard_gather_put    k_gather on the received slots, finished gradient rows stored
 //                                       into their owners' slots
-//   owner      vfmb_shard_owner_update  k_gather over the received gradient slots (rank order) +
-//                                       k_adam_rows_pipe<3>: Adam on the owned rows, scalar parameters
+//   owner      vfmb_shard_owner_update  k_adam_rows_pipe<3>: a row's gradient = its requesters' slots added
+//                                       in source-rank order, Adam on the owned rows, scalar parameters
 //                                       and loss from the ranks' tail slots
 // Two cross-rank barriers remain per step (after the rows, after the gradients); the caller issues them.
 static int make_peers_tab(const void* const* peers, int32_t P, int32_t rank, Peers* out) {
@@ -1178,18 +1178,18 @@ extern "C" int vfmb_shard_gather_put(const vfmb_config* cfg_l, const vfmb_plan* 
 
 extern "C" int vfmb_shard_owner_update(const vfmb_config* cfg_o, const vfmb_tables* tab, const vfmb_plan* plan_o,
                                        const vfmb_step_io* io_o, const vfmb_adam* adam, const float* recv_grads,
-                                       int32_t SP, const float* tail_slots, int32_t P, int32_t tail_pitch,
+                                       int32_t SP, int32_t n_real, const float* tail_slots, int32_t P, int32_t tail_pitch,
                                        int32_t B_global, float n_train_global, float* stats_out,
                                        const float* eps_global, vfmb_stream stream) {
-    if (!cfg_o || !recv_grads || !tail_slots || !stats_out || P < 1) return set_error(VFMB_EINVAL, "vfmb_shard_owner_update: bad argument");
+    if (!cfg_o || !recv_grads || !tail_slots || !stats_out || P < 1 || !plan_o || !plan_o->occ)
+        return set_error(VFMB_EINVAL, "vfmb_shard_owner_update: bad argument");
     if (cfg_o->S != 1) return set_error(VFMB_ESHAPE, "vfmb_shard_owner_update: S = 1 only");
-    GatherB gb{};
-    gb.rows = nullptr; gb.vp = SP; gb.partner = nullptr; gb.gptr = nullptr; gb.own_slot = nullptr; gb.coef_in_row = true;
-    int rc = launch_gather(cfg_o, plan_o, io_o, recv_grads, 1, stream, 0, &gb);
-    if (rc) return rc;
+    // one kernel: a row's gradient is the sum of the <= P slots its requesters stored, taken in source-rank
+    // order straight from the received region (no separate ordered-sum pass over the slots)
     DpTail dp{};
     dp.tail_slots = tail_slots; dp.P = P; dp.pitch = tail_pitch; dp.B_global = B_global; dp.n_train_global = n_train_global;
     dp.stats_out = stats_out; dp.eps_global = eps_global;
+    dp.recv_grads = recv_grads; dp.slot_pitch = SP; dp.n_real = n_real;
     return launch_adam(cfg_o, tab, plan_o, io_o, adam, VFMB_ADAM_TOUCHED, 1.0f, 3, stream, &dp);
 }
 

@@ -346,13 +346,15 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
         // ---- lane-parallel: one unique row per lane
         const int ul = cbase + lane;
         const bool valid = ul < hi;
-        int rowid_l = 0;
+        int rowid_l = 0, seg0_l = 0, len_l = 0;
         float cfac_l = 0.f, klw_l = 0.f, cq_l = 0.f;
         if (valid) {
-            rowid_l = __ldg(reinterpret_cast<const int4*>(urec) + ul).x;
+            const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
+            rowid_l = rec.x; len_l = rec.y; seg0_l = rec.z;
             cq_l = __ldg(cq + ul);
             cfac_l = kl_scale * cq_l;
             klw_l = cq_l;
+            if (DPF && rowid_l >= fa.n_real) len_l = 0;        // padding slots share a sentinel row: not a row
         }
         const int nrounds = (min(32, hi - cbase) + GPW - 1) / GPW;
         auto issue = [&](int r) {                          // warp-uniform call: the shuffle needs every lane
@@ -369,8 +371,20 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
         };
         issue(0);
         // bias row of the lane's row while the first round is in flight
-        if (valid) bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, __ldg(gws + ul),
-                                                __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
+        if (DPF) {
+            // mode B owner: the row's gradient = the slots its requesters stored (sorted occurrences of the
+            // owner's plan, at most one per rank), added in source-rank order
+            if (valid && len_l > 0) {
+                float gw = 0.f;
+                for (int i = 0; i < len_l; ++i)
+                    gw += __ldcg(fa.recv_grads + (size_t)__ldg(fa.occ + seg0_l + i) * fa.slot_pitch + d);
+                bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, gw, __ldg(eps_bias + ul), cfac_l, h,
+                                             step_size, inv_bc2, klw_l);
+            }
+        } else if (valid) {
+            bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, __ldg(gws + ul), __ldg(eps_bias + ul),
+                                         cfac_l, h, step_size, inv_bc2, klw_l);
+        }
         float klrow = 0.f;
 #pragma unroll 1
         for (int r = 0; r < nrounds; ++r) {
@@ -379,13 +393,25 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             const int rowid = bcast(rowid_l, sel);
             const float cfac = bcast(cfac_l, sel);
             const int u = cbase + sel;
-            const bool live = u < hi && kin;
+            int n_req = 0, seg0 = 0;
+            if (DPF) { n_req = bcast(len_l, sel); seg0 = bcast(seg0_l, sel); }
+            const bool live = u < hi && kin && (!DPF || n_req > 0);
             // independent of the staged rows: the noise k_stage used for this row, the row gradient
             Vec<VEC> e, g;
             if (live) {
                 if (KLF) e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, nstep);
                 else e = ld_vec_nc<VEC>(eps_entity + (size_t)u * d + k);
-                g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
+                if (DPF) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) g.v[j] = 0.f;
+                    for (int i = 0; i < n_req; ++i) {
+                        const Vec<VEC> t = ld_vec_cg<VEC>(fa.recv_grads + (size_t)__ldg(fa.occ + seg0 + i) * fa.slot_pitch + k);
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) g.v[j] += t.v[j];
+                    }
+                } else {
+                    g = ld_vec_nc<VEC>(grow + (size_t)u * d + k);
+                }
             }
             cp_async_wait<1>();                            // round r has landed (round r+1 may still fly)
             float kl = 0.f;
@@ -581,7 +607,7 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
     if (mode == VFMB_GRAD_ONLY && (!io->grad_bias || !io->grad_entity))
         return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: gradient outputs required");
     if (mode != VFMB_ADAM_TOUCHED && mode != VFMB_GRAD_ONLY) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: bad mode");
-    if (!io->grow || !io->gws || !io->cq) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: scratch required");
+    if (((!io->grow || !io->gws) && flavor != 3) || !io->cq) return set_error(VFMB_EINVAL, "vfmb_sampled_adam_rows: scratch required");
     if (flavor >= 1 && mode == VFMB_ADAM_TOUCHED && (!tab->scalars_m || !tab->scalars_v))
         return set_error(VFMB_EINVAL, "vfmb_sampled_backward: Adam state required");
     if (flavor >= 1 && (!tab->scalars || !io->stats || !io->partials || !io->counters))
@@ -607,6 +633,7 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
         fa.tail_slots = dp->tail_slots; fa.tail_P = dp->P; fa.tail_pitch = dp->pitch;
         fa.B_global = dp->B_global; fa.n_train_global = dp->n_train_global; fa.stats = dp->stats_out;
         fa.eps_global = dp->eps_global;
+        fa.recv_grads = dp->recv_grads; fa.occ = plan->occ; fa.slot_pitch = dp->slot_pitch; fa.n_real = dp->n_real;
     }
     // the HBM-bound kernel keeps its full wave even next to the plan (measured: 113.8 vs 116.2 us/step)
     const bool adam_reserve = tuning().adam_reserve != 0;

@@ -61,6 +61,7 @@ struct FinalArgs {
     // mode B owner update (k_adam_rows_pipe<FLAVOR 3>): the ranks' additive scalars, one slot per rank
     const float* tail_slots; int tail_P, tail_pitch;
     int B_global; float n_train_global;
+    const float* recv_grads; const int32_t* occ; int slot_pitch, n_real;   // the requesters' gradient slots
 };
 
 // Mode B / mode A: scalar parameters (replicated on every rank, identical results) and the global-batch
@@ -141,6 +142,7 @@ struct DpTail {
     const float* tail_slots; int P, pitch;
     int B_global; float n_train_global;
     float* stats_out; const float* eps_global;
+    const float* recv_grads; int slot_pitch, n_real;
 };
 // row update (sampled_adam.cu); flavor: see k_adam_rows (3: mode B owner, needs `dp`)
 int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan, const vfmb_step_io* io,

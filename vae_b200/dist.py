@@ -647,7 +647,7 @@ class ShardedSampled:
         st = bl.stats
         L.check(L.lib().vfmb_shard_owner_update(C.byref(self.cfg_o), C.byref(self._tables()), C.byref(po.struct),
                                                 C.byref(self._io_o), C.byref(self.adam), pe.grads.data_ptr(), self.SP,
-                                                pe.tail.data_ptr(), self.P, SMALL_PITCH, self.B * self.P, float(self.n_train),
+                                                self.n_real, pe.tail.data_ptr(), self.P, SMALL_PITCH, self.B * self.P, float(self.n_train),
                                                 st.data_ptr(), L.ptr(e0), current_stream(self.device)),
                 "vfmb_shard_owner_update")
         return {"loss": st[L.ST_LOSS], "kl": st[L.ST_KL], "nll_mean": st[L.ST_NLL_MEAN],
