@@ -512,9 +512,9 @@ def run_sharded(args):
             def step(xb, yb):                                 # same call shape as model.step: the batch passed
                 # is the one staged for the FOLLOWING replay; batches are consumed in order
                 return pipe.step(xb, yb)
-            pipe.start(*batch(0))
+            pipe.start(*batch(0), *batch(1))
             for i in range(W):
-                out = pipe.step(*batch(i + 1))
+                out = pipe.step(*batch(i + 2))
         else:
             for i in range(W):
                 out = step(*batch(i))
@@ -526,7 +526,7 @@ def run_sharded(args):
     ev0.record()
     if pipe is not None:
         for i in range(W, W + K):
-            out = pipe.step(*batch(i + 1))                    # runs batch i, stages batch i+1
+            out = pipe.step(*batch(i + 2))                    # runs batch i, stages batch i+2
     else:
         for i in range(W, W + K):
             out = step(*batch(i))

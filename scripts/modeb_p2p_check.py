@@ -48,9 +48,9 @@ c = mk("peer")
 pipe = ShardedPipeline(c)
 nb = 4
 bat = lambda it: (x[(it * world + rank) * B:(it * world + rank + 1) * B], y[(it * world + rank) * B:(it * world + rank + 1) * B])
-pipe.start(*bat(0))
+pipe.start(*bat(0), *bat(1))
 for it in range(nb):
-    o = pipe.step(*bat(it + 1)) if it + 1 < nb else pipe.step()
+    o = pipe.step(*bat(it + 2)) if it + 2 < nb else pipe.step()
 torch.cuda.synchronize()
 for name in ("entity", "bias", "entity_m", "entity_v", "scalars"):
     ta, tc_ = getattr(b, name), getattr(c, name)             # serial peer steps vs the pipelined graphs

@@ -197,15 +197,16 @@ class TorchExchange:
 
 
 SMALL_PITCH = 32                                            # floats per rank slot of the small-vector regions
+N_SLOTS = 3                                                 # batches in flight in the pipelined loop (ShardedPipeline)
 
 
 def _region_layout(M: int, d: int, P: int):
-    """Regions of one rank's exchange buffer (bytes, 256-aligned): requests and Z_f twice (the requests of
-    batch i+1 travel while step i runs), sampled rows (+ one spare slot of zeros that overflowed rows are
+    """Regions of one rank's exchange buffer (bytes, 256-aligned): requests and Z_f once per pipeline slot (the
+    requests of batches i+1 and i+2 travel while step i runs), sampled rows (+ one spare slot of zeros that overflowed rows are
     routed to), row gradients, the ranks' additive scalars.  Slot pitch of rows / gradients: d + 4 floats."""
     sp = d + 4
-    sizes = [("ids0", M * 2 * 4), ("ids1", M * 2 * 4), ("rows", (M + 1) * sp * 4), ("grads", M * sp * 4),
-             ("z0", P * SMALL_PITCH * 4), ("z1", P * SMALL_PITCH * 4), ("tail", P * SMALL_PITCH * 4)]
+    sizes = [(f"ids{k}", M * 2 * 4) for k in range(N_SLOTS)] + [("rows", (M + 1) * sp * 4), ("grads", M * sp * 4)] + \
+            [(f"z{k}", P * SMALL_PITCH * 4) for k in range(N_SLOTS)] + [("tail", P * SMALL_PITCH * 4)]
     off, total = {}, 0
     for name, nbytes in sizes:
         off[name] = total
@@ -221,10 +222,10 @@ class _ExchangeViews:
         self.buf = buf
         self.tables = {name: (C.c_void_p * P)(*[p + o for p in ptrs]) for name, o in self.off.items()}
         view = lambda name, n, dt: buf[self.off[name]: self.off[name] + n * 4].view(dt)
-        self.ids = [view(f"ids{k}", M * 2, torch.int32).view(M, 2) for k in (0, 1)]
+        self.ids = [view(f"ids{k}", M * 2, torch.int32).view(M, 2) for k in range(N_SLOTS)]
         self.rows = view("rows", (M + 1) * self.SP, torch.float32).view(M + 1, self.SP)
         self.grads = view("grads", M * self.SP, torch.float32).view(M, self.SP)
-        self.z = [view(f"z{k}", P * SMALL_PITCH, torch.float32) for k in (0, 1)]
+        self.z = [view(f"z{k}", P * SMALL_PITCH, torch.float32) for k in range(N_SLOTS)]
         self.tail = view("tail", P * SMALL_PITCH, torch.float32)
 
 
@@ -386,10 +387,10 @@ class ShardedSampled:
         self._ids_copy = i32(M, 2)
         self._zg, self._tailg = f32(L.MAX_FIELDS), f32(DP_TAIL)
         self._y = self._io_o = self._recv_ids = self._noise_o = None
-        # Per-batch state exists twice ("slots"): everything that depends only on the ids of a batch
-        # -- both plans, the slot map, the owner's copy of the requests, Z_f -- so that it can be
-        # prepared for batch i+1 while step i runs (ShardedPipeline).  _use_slot(k) makes slot k
-        # the one the phase methods work on.
+        # Per-batch state exists N_SLOTS times ("slots"): everything that depends only on the ids of a
+        # batch -- both plans, the slot map, the routing tables, the owner's copy of the requests, Z_f --
+        # so that it can be prepared for batches i+1 and i+2 while step i runs (ShardedPipeline).
+        # _use_slot(k) makes slot k the one the phase methods work on.
         # fused peer mode: where every row of the batch is read from / its gradient written to (vfmb_shard_route)
         N = self.B * self.F
         self.SP = d + 4
@@ -399,13 +400,13 @@ class ShardedSampled:
         self._dump = f32(self.SP)
         self._slot_keys = ("plan_l", "plan_o", "_dest", "_ids_copy", "_loc", "_zg", "_y", "_io_o", "_recv_ids", "_noise_o",
                            "_inv_slot", "_partner_slot", "_gptr")
-        self._slots = [{k: getattr(self, k) for k in self._slot_keys},
-                       {"plan_l": BatchPlan(self.B, self.F, self.R, dev), "plan_o": BatchPlan(self.M, 1, Rl, dev),
-                        "_dest": i32(u_cap), "_ids_copy": i32(M, 2),
-                        "_loc": torch.zeros((M, 1), dtype=torch.int64, device=dev), "_zg": f32(L.MAX_FIELDS),
-                        "_y": None, "_io_o": None, "_recv_ids": None, "_noise_o": None,
-                        "_inv_slot": i32(N), "_partner_slot": i32(N),
-                        "_gptr": torch.zeros(u_cap, dtype=torch.int64, device=dev)}]
+        mk_slot = lambda: {"plan_l": BatchPlan(self.B, self.F, self.R, dev), "plan_o": BatchPlan(self.M, 1, Rl, dev),
+                           "_dest": i32(u_cap), "_ids_copy": i32(M, 2),
+                           "_loc": torch.zeros((M, 1), dtype=torch.int64, device=dev), "_zg": f32(L.MAX_FIELDS),
+                           "_y": None, "_io_o": None, "_recv_ids": None, "_noise_o": None,
+                           "_inv_slot": i32(N), "_partner_slot": i32(N),
+                           "_gptr": torch.zeros(u_cap, dtype=torch.int64, device=dev)}
+        self._slots = [{k: getattr(self, k) for k in self._slot_keys}] + [mk_slot() for _ in range(N_SLOTS - 1)]
         self._k = 0
         if self._want_peer:                                  # collective: every rank constructs it
             self.peer = PeerExchange(M, d, P, p, dev)
@@ -584,8 +585,17 @@ class ShardedSampled:
     def _phase_a(self, x_local, y_local, mark=lambda name: None) -> None:
         """Peer mode, everything that depends only on the ids of the batch (current slot): local
         plan, request exchange, the owner's plan and global counts."""
-        self.phase_request(x_local, y_local)
+        self._a1(x_local, y_local)
         mark("request")
+        self._a2(mark)
+
+    def _a1(self, x_local, y_local) -> None:
+        """Part A1 (requester, no barrier): local plan, requests and Z_f stored into the owners' regions
+        of the current slot, routing tables of the fused step."""
+        self.phase_request(x_local, y_local)
+
+    def _a2(self, mark=lambda name: None) -> None:
+        """Part A2 (owner): wait for every rank's requests of the current slot, plan them, global counts."""
         self.peer.barrier(0)
         mark("a2a_ids")
         self._owner_prepare(None, None)
@@ -713,62 +723,82 @@ class ShardedSampled:
 class ShardedPipeline:
     """Software-pipelined, CUDA-graphed mode-B loop over NVLink peer memory (fixed batch size).
 
-    A step has an id-only part A (local plan, request exchange, owner's plan and global counts) and
-    a parameter-dependent part B (sample rows -> exchange -> score / segmented sums -> exchange ->
-    owner update).  Graph s holds B of the batch in slot s on the main branch and A of the NEXT
-    batch (slot s^1) on a side branch: both plans and the id exchange leave the critical path.
-    A uses barrier channel 0, B channels 1 and 2; the request / Z_f regions are double-buffered.
+    A step has two id-only parts -- A1 (requester: local plan, requests into the owners' regions, routing
+    tables) and A2 (owner: plan of the received requests, global batch counts) -- and the parameter-
+    dependent part B (sample rows into the requesters' slots -> score / segmented sums in place, gradient
+    rows into the owners' slots -> owner update).  Three batches are in flight: graph s holds B of the
+    batch in slot s on the main branch, A2 of the next batch (slot s+1) and A1 of the one after (slot s+2)
+    on two side branches, so both plans and the id exchange are off the critical path and each of the
+    three chains is about as long as the others.  A2 uses barrier channel 0, B channels 1 and 2; the
+    request / Z_f regions exist once per slot.
 
         pipe = ShardedPipeline(model)
-        pipe.start(x0, y0)
-        for x_next, y_next in batches[1:]:
-            out = pipe.step(x_next, y_next)      # runs the step on the previously staged batch
-        out = pipe.step()                         # last staged batch
+        pipe.start(x0, y0, x1, y1)
+        for x_next, y_next in batches[2:]:
+            out = pipe.step(x_next, y_next)      # runs the oldest staged batch, stages (x_next, y_next)
+        out = pipe.step(); out = pipe.step()      # the last two staged batches
     """
 
     def __init__(self, model: ShardedSampled):
         assert model.peer is not None, "ShardedPipeline needs exchange='peer'"
         assert getattr(model, "_timing", None) is None, "disable phase timing before capturing"
         m, dev = model, model.device
-        self.m = m
-        self.xs = [torch.zeros((m.B, m.F), dtype=torch.int64, device=dev) for _ in range(2)]
-        self.ys = [torch.zeros(m.B, dtype=torch.float32, device=dev) for _ in range(2)]
-        self.side = torch.cuda.Stream(device=dev, priority=-1)
+        self.m, D = m, N_SLOTS
+        self.xs = [torch.zeros((m.B, m.F), dtype=torch.int64, device=dev) for _ in range(D)]
+        self.ys = [torch.zeros(m.B, dtype=torch.float32, device=dev) for _ in range(D)]
+        self.side1 = torch.cuda.Stream(device=dev, priority=-1)
+        self.side2 = torch.cuda.Stream(device=dev, priority=-1)
         self.head = 0
         self.graphs, self.outs = [], []
         torch.cuda.synchronize(dev)
         L.check(L.lib().vfmb_set_grid_reserve(1), "vfmb_set_grid_reserve")
+        n0 = int(L.lib().vfmb_launch_count())
         try:
-            for s in (0, 1):
+            for s in range(D):
+                s1, s2 = (s + 1) % D, (s + 2) % D
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     cur = torch.cuda.current_stream(dev)
-                    self.side.wait_stream(cur)                   # fork
-                    with torch.cuda.stream(self.side):
-                        m._use_slot(s ^ 1)
-                        m._phase_a(self.xs[s ^ 1], self.ys[s ^ 1])
-                    m._use_slot(s)
+                    self.side1.wait_stream(cur)                  # fork
+                    self.side2.wait_stream(cur)
+                    with torch.cuda.stream(self.side2):          # A1 of batch i+2
+                        m._use_slot(s2)
+                        m._a1(self.xs[s2], self.ys[s2])
+                    with torch.cuda.stream(self.side1):          # A2 of batch i+1
+                        m._use_slot(s1)
+                        m._a2()
+                    m._use_slot(s)                               # B of batch i
                     m._y = self.ys[s]                            # targets of the batch staged in slot s
                     out = m._phase_b()
-                    cur.wait_stream(self.side)                   # join
+                    cur.wait_stream(self.side1)                  # join
+                    cur.wait_stream(self.side2)
                 self.graphs.append(g)
                 self.outs.append(out)
         finally:
             L.lib().vfmb_set_grid_reserve(0)
+        self.launches_per_graph = (int(L.lib().vfmb_launch_count()) - n0) // D
 
-    def start(self, x: torch.Tensor, y: torch.Tensor) -> None:
-        """Stage the first batch and run its part A (outside the graphs)."""
+    def start(self, x0: torch.Tensor, y0: torch.Tensor, x1: torch.Tensor, y1: torch.Tensor) -> None:
+        """Stage the first two batches and run their id-only parts (outside the graphs): A1 and A2 of
+        batch 0, A1 of batch 1."""
+        m = self.m
         self.head = 0
-        self.xs[0].copy_(x, non_blocking=True)
-        self.ys[0].copy_(y, non_blocking=True)
-        self.m._use_slot(0)
-        self.m._phase_a(self.xs[0], self.ys[0])
+        for k, (x, y) in enumerate(((x0, y0), (x1, y1))):
+            self.xs[k].copy_(x, non_blocking=True)
+            self.ys[k].copy_(y, non_blocking=True)
+            m._use_slot(k)
+            m._a1(self.xs[k], self.ys[k])
+        m._use_slot(0)
+        m._a2()
 
     def step(self, x_next: Optional[torch.Tensor] = None, y_next: Optional[torch.Tensor] = None) -> dict:
+        """Run the step on the oldest staged batch; ``(x_next, y_next)`` is staged two batches ahead
+        (without it the slot's old contents are planned again, harmlessly, at the end of a run)."""
         s = self.head
         if x_next is not None:
-            self.xs[s ^ 1].copy_(x_next, non_blocking=True)
-            self.ys[s ^ 1].copy_(y_next, non_blocking=True)
+            t = (s + 2) % N_SLOTS
+            self.xs[t].copy_(x_next, non_blocking=True)
+            self.ys[t].copy_(y_next, non_blocking=True)
         self.graphs[s].replay()
-        self.head = s ^ 1
+        self.head = (s + 1) % N_SLOTS
         return self.outs[s]
