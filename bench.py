@@ -537,24 +537,53 @@ def run_sharded(args):
     model.check_overflow()
     loss = float(out["loss"].item())
 
-    # end to end: pinned host ids/targets -> device every step, loss/KL/NLL back every step
+    # end to end: pinned host ids/targets -> device every step (copy stream, one batch ahead), the step's
+    # predictions and loss terms back to pinned host memory every step (a third stream; the outputs of a step
+    # live in their own slot, the next step writes another one)
     xh = torch.from_numpy(w.x[: n_batches * B]).pin_memory()
     yh = torch.from_numpy(w.y[: n_batches * B]).pin_memory()
     Ke = min(K, 200)
-    xd, yd = torch.empty((B, F), dtype=torch.int64, device=device), torch.empty(B, dtype=torch.float32, device=device)
+    xd = [torch.empty((B, F), dtype=torch.int64, device=device) for _ in range(2)]
+    yd = [torch.empty(B, dtype=torch.float32, device=device) for _ in range(2)]
     res = torch.empty((Ke, 16), dtype=torch.float32).pin_memory()
+    predh = torch.empty((4, B), dtype=torch.float32).pin_memory()
+    h2d, d2h = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    up = [torch.cuda.Event() for _ in range(2)]               # batch uploaded into xd/yd[k]
+    used = [torch.cuda.Event() for _ in range(2)]             # xd/yd[k] consumed by the step's staging copy
+    outs_read = [torch.cuda.Event() for _ in range(4)]
+    cur = torch.cuda.current_stream(device)
+
+    def upload(i):
+        j = ((W + K + i) * world + rank) % n_batches
+        k = i % 2
+        h2d.wait_event(used[k])
+        with torch.cuda.stream(h2d):
+            xd[k].copy_(xh[j * B:(j + 1) * B], non_blocking=True)
+            yd[k].copy_(yh[j * B:(j + 1) * B], non_blocking=True)
+            up[k].record(h2d)
+
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    upload(0)
     for i in range(Ke):
-        j = ((W + K + i) * world + rank) % n_batches
-        if pipe is not None:                                  # pinned host -> the pipeline's staging slot
-            o = pipe.step(xh[j * B:(j + 1) * B], yh[j * B:(j + 1) * B])
-        else:
-            xd.copy_(xh[j * B:(j + 1) * B], non_blocking=True)
-            yd.copy_(yh[j * B:(j + 1) * B], non_blocking=True)
-            o = step(xd, yd)
-        res[i].copy_(o["stats"][:16], non_blocking=True)
+        k = i % 2
+        if i + 1 < Ke:
+            upload(i + 1)
+        cur.wait_event(up[k])
+        cur.wait_event(outs_read[i % 4])                      # (generous: a slot's outputs are rewritten 3 steps later)
+        if pipe is None:
+            cur.wait_stream(d2h)                              # unpipelined steps share one output slot
+        o = pipe.step(xd[k], yd[k]) if pipe is not None else step(xd[k], yd[k])
+        used[k].record(cur)
+        done = torch.cuda.Event()
+        done.record(cur)
+        d2h.wait_event(done)
+        with torch.cuda.stream(d2h):
+            res[i].copy_(o["stats"][:16], non_blocking=True)
+            predh[i % 4].copy_(o["pred"], non_blocking=True)
+            outs_read[(i + 3) % 4].record(d2h)
+    cur.wait_stream(d2h)
     e1.record()
     barrier()
     ms_e = e0.elapsed_time(e1)
@@ -613,7 +642,7 @@ def run_sharded(args):
                          "peak": peak * world, "unit": "GB/s", "frac": step_bytes / (ms / K * 1e-3) / 1e9 / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes": step_bytes},
             "e2e": {"value": Ke * B * world / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * F * 8 + B * 4,
-                    "d2h_bytes_per_step": 16 * 4, "steps": Ke, "ms_per_step": ms_e / Ke},
+                    "d2h_bytes_per_step": 16 * 4 + B * 4, "steps": Ke, "ms_per_step": ms_e / Ke},
             # own kernels per rank and step, counted by the library over a few eager steps (the barriers are
             # torch symmetric-memory kernels / the collectives NCCL and are not counted)
             "gpu_launches": launches_per_step * K * world, "gpu_launches_per_step_per_rank": launches_per_step,

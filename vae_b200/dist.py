@@ -398,14 +398,20 @@ class ShardedSampled:
         self._inv_slot, self._partner_slot = i32(N), i32(N)
         self._gptr = torch.zeros(u_cap, dtype=torch.int64, device=dev)
         self._dump = f32(self.SP)
+        # outputs of a step (predictions, loss terms) also exist per slot: step i+1 writes other buffers, so
+        # a caller may copy step i's outputs to the host on its own stream while step i+1 runs
+        self._pred, self._mean = f32(self.B), f32(self.B)
+        self._stats = torch.zeros(L.STATS, dtype=torch.float32, device=dev)
         self._slot_keys = ("plan_l", "plan_o", "_dest", "_ids_copy", "_loc", "_zg", "_y", "_io_o", "_recv_ids", "_noise_o",
-                           "_inv_slot", "_partner_slot", "_gptr")
+                           "_inv_slot", "_partner_slot", "_gptr", "_pred", "_mean", "_stats")
         mk_slot = lambda: {"plan_l": BatchPlan(self.B, self.F, self.R, dev), "plan_o": BatchPlan(self.M, 1, Rl, dev),
                            "_dest": i32(u_cap), "_ids_copy": i32(M, 2),
                            "_loc": torch.zeros((M, 1), dtype=torch.int64, device=dev), "_zg": f32(L.MAX_FIELDS),
                            "_y": None, "_io_o": None, "_recv_ids": None, "_noise_o": None,
                            "_inv_slot": i32(N), "_partner_slot": i32(N),
-                           "_gptr": torch.zeros(u_cap, dtype=torch.int64, device=dev)}
+                           "_gptr": torch.zeros(u_cap, dtype=torch.int64, device=dev),
+                           "_pred": f32(self.B), "_mean": f32(self.B),
+                           "_stats": torch.zeros(L.STATS, dtype=torch.float32, device=dev)}
         self._slots = [{k: getattr(self, k) for k in self._slot_keys}] + [mk_slot() for _ in range(N_SLOTS - 1)]
         self._k = 0
         if self._want_peer:                                  # collective: every rank constructs it
@@ -641,6 +647,7 @@ class ShardedSampled:
         e0 = self._noise_o[0] if self._noise_o is not None else None
         io = bl.io(y=self._y)
         io.eps_global = L.ptr(e0)
+        io.pred, io.mean, io.stats = L.ptr(self._pred), L.ptr(self._mean), L.ptr(self._stats)
         self._io_l = io
         L.check(lib.vfmb_shard_score(C.byref(self.cfg_l), C.byref(tab), C.byref(pl.struct), C.byref(io), pe.rows.data_ptr(), SP,
                                      self._inv_slot.data_ptr(), pe.tables["tail"], P, p, bo.stats.data_ptr(),
@@ -652,16 +659,16 @@ class ShardedSampled:
     @torch.no_grad()
     def _b_update(self) -> dict:
         """Owner: ordered sum of the received gradients, Adam on the owned rows, scalar parameters, loss."""
-        pe, po, bl = self.peer, self.plan_o, self.buf_l
+        pe, po = self.peer, self.plan_o
         e0 = self._noise_o[0] if self._noise_o is not None else None
-        st = bl.stats
+        st = self._stats
         L.check(L.lib().vfmb_shard_owner_update(C.byref(self.cfg_o), C.byref(self._tables()), C.byref(po.struct),
                                                 C.byref(self._io_o), C.byref(self.adam), pe.grads.data_ptr(), self.SP,
                                                 self.n_real, pe.tail.data_ptr(), self.P, SMALL_PITCH, self.B * self.P, float(self.n_train),
                                                 st.data_ptr(), L.ptr(e0), current_stream(self.device)),
                 "vfmb_shard_owner_update")
         return {"loss": st[L.ST_LOSS], "kl": st[L.ST_KL], "nll_mean": st[L.ST_NLL_MEAN],
-                "pred": bl.mean[: self.B], "stats": st}
+                "pred": self._mean[: self.B], "stats": st}
 
     def graphed_step(self):
         """Capture one whole step -- both plans, every kernel and the NCCL collectives -- in a CUDA
