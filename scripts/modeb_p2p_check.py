@@ -11,7 +11,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-w = synth.make_workload("ml20m", n_rows=2_000_000)
+w = synth.make_workload("ml20m", n_rows=max(2_000_000, 10 * world * 65536))
 B, d = w.batch, w.d
 tc = w.train_counts(); tc[tc == 0] = 1
 mk = lambda ex: ShardedSampled(d, w.field_sizes, torch.from_numpy(tc), w.n_train, B, world, rank, output="reg", lr=1e-2,
