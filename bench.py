@@ -495,7 +495,7 @@ def run_sharded(args):
         try:
             if exchange == "peer" and not args.no_pipeline:
                 from vae_b200.dist import ShardedPipeline
-                pipe = ShardedPipeline(model)                 # + plans / id exchange of batch i+1 under step i
+                pipe = ShardedPipeline(model, reserve=args.reserve, side_priority=args.side_priority)
             else:
                 step = model.graphed_step()
             graphed = True

@@ -746,19 +746,19 @@ class ShardedPipeline:
         out = pipe.step(); out = pipe.step()      # the last two staged batches
     """
 
-    def __init__(self, model: ShardedSampled):
+    def __init__(self, model: ShardedSampled, reserve: int = 1, side_priority: int = -1):
         assert model.peer is not None, "ShardedPipeline needs exchange='peer'"
         assert getattr(model, "_timing", None) is None, "disable phase timing before capturing"
         m, dev = model, model.device
         self.m, D = m, N_SLOTS
         self.xs = [torch.zeros((m.B, m.F), dtype=torch.int64, device=dev) for _ in range(D)]
         self.ys = [torch.zeros(m.B, dtype=torch.float32, device=dev) for _ in range(D)]
-        self.side1 = torch.cuda.Stream(device=dev, priority=-1)
-        self.side2 = torch.cuda.Stream(device=dev, priority=-1)
+        self.side1 = torch.cuda.Stream(device=dev, priority=side_priority)
+        self.side2 = torch.cuda.Stream(device=dev, priority=side_priority)
         self.head = 0
         self.graphs, self.outs = [], []
         torch.cuda.synchronize(dev)
-        L.check(L.lib().vfmb_set_grid_reserve(1), "vfmb_set_grid_reserve")
+        L.check(L.lib().vfmb_set_grid_reserve(reserve), "vfmb_set_grid_reserve")
         n0 = int(L.lib().vfmb_launch_count())
         try:
             for s in range(D):
