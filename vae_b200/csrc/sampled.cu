@@ -518,9 +518,11 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
          const int32_t* __restrict__ urec, const float* __restrict__ vs, const float* __restrict__ msg,
          const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
          int32_t* arrive, int vp, float* const* __restrict__ gptr, const int32_t* __restrict__ own_slot) {
+    // F > 2 (pairwise): the sums are over the per-sample field sums S_n; the row's own term (sum r_n) v_u is
+    // removed by the row kernel, which holds v_u anyway (DevCfg.pairwise).
     // mode B: vp = pitch of the gathered rows (received slots: d + 4); gptr[u] = where the finished gradient
-    // row of unique rank u goes (its owner's slot over NVLink, bias gradient at [d]); own_slot[u] = slot of
-    // the row itself (F > 2); rsorted == NULL (owner side, UNIT): the coefficient sits at [d] of the row
+    // row of unique rank u goes (its owner's slot over NVLink, bias gradient at [d]); rsorted == NULL (owner
+    // side, UNIT): the coefficient sits at [d] of the row
     constexpr int GPW = kWarp / LPR;
     const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
     const int lane = threadIdx.x & 31, gl = lane % LPR;
@@ -546,7 +548,6 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
         float gw = 0.f;
 
         auto row_out = [&](int u) { return gptr ? gptr[u] : grow + (size_t)u * d; };
-        auto own_row = [&](int u) { return vs + (size_t)(own_slot ? __ldg(own_slot + u) : u) * vp; };
         auto flush = [&](int u) {
             const bool open_h = head_open && u == first_u, open_t = tail_open && u == last_u;
             float* dst; float* dstw;
@@ -557,11 +558,6 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
             for (int i = 0; i < NV; ++i) {
                 int k = (gl + i * LPR) * VEC;
                 if (k < d) {
-                    if (F > 2 && !open_h && !open_t) {  // pairwise, complete row: sum r_n (S_n - v_u)
-                        Vec<VEC> own = ld_vec_nc<VEC>(own_row(u) + k);
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) acc[i].v[j] = fmaf(-gw, own.v[j], acc[i].v[j]);
-                    }
                     st_vec<VEC>(dst + k, acc[i]);
                 }
             }
@@ -620,12 +616,12 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
         // rows cut by this tile's boundaries (at most two): whoever stores the last partial finishes the row
         if (head_open) {
             float* o = row_out(first_u);
-            finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, F > 2 ? own_row(first_u) : nullptr, urec, gslot, o,
+            finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, nullptr, urec, gslot, o,
                                             gptr ? o + d : gws + first_u, arrive, n_tiles + 1);
         }
         if (tail_open && !(head_open && last_u == first_u)) {
             float* o = row_out(last_u);
-            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, F > 2 ? own_row(last_u) : nullptr, urec, gslot, o,
+            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, nullptr, urec, gslot, o,
                                             gptr ? o + d : gws + last_u, arrive, n_tiles + 1);
         }
     }

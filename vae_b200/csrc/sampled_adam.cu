@@ -164,7 +164,7 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
         const bool valid = lane < CH && ul < U;
 #endif
         int rowid_l = 0;
-        float cfac_l = 0.f, klw_l = 0.f;                  // KL weight c_u, and c_u * KL(bias) of the lane's row
+        float cfac_l = 0.f, klw_l = 0.f, gw_l = 0.f;      // KL weight c_u, c_u * KL(bias) of the lane's row, sum r_n
         if (valid) {
             const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
             rowid_l = rec.x;
@@ -180,7 +180,8 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             cfac_l = kl_scale * cq_l;
             klw_l = cq_l;
             // bias row now: nothing of it stays live across the wide work
-            bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, grad_bias, rowid_l, __ldg(gws + ul),
+            gw_l = __ldg(gws + ul);
+            bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, grad_bias, rowid_l, gw_l,
                                          __ldg(eps_bias + ul), cfac_l, h, step_size, inv_bc2, klw_l);
         }
         float klrow = 0.f;
@@ -190,6 +191,7 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
             const int sel = it * GPW + gidx;
             const int rowid = bcast(rowid_l, sel);
             const float cfac = bcast(cfac_l, sel);
+            const float gwr = c.pairwise ? bcast(gw_l, sel) : 0.f;      // pairwise: own term (sum r_n) v_u
             const int u = base + sel;
             float kl = 0.f;
             if (u < hi) {
@@ -213,8 +215,9 @@ k_adam_rows(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m, floa
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) {
                             const float sig = link_fn<LINK>(rho.v[j]);
-                            gmu.v[j] = fmaf(cfac, mu.v[j], g.v[j]);
-                            grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(g.v[j], e.v[j], cfac * (sig - fast_rcp(sig)));
+                            const float gj = fmaf(-gwr, fmaf(e.v[j], sig, mu.v[j]), g.v[j]);   // gwr = 0 unless pairwise
+                            gmu.v[j] = fmaf(cfac, mu.v[j], gj);
+                            grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(gj, e.v[j], cfac * (sig - fast_rcp(sig)));
                             if (KLF) {
                                 const float vr = sig * sig;
                                 quad += vr + mu.v[j] * mu.v[j] - 1.f;
@@ -371,18 +374,19 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
         };
         issue(0);
         // bias row of the lane's row while the first round is in flight
+        float gw_l = 0.f;                                  // sum r_n of the lane's row
         if (DPF) {
             // mode B owner: the row's gradient = the slots its requesters stored (sorted occurrences of the
             // owner's plan, at most one per rank), added in source-rank order
             if (valid && len_l > 0) {
-                float gw = 0.f;
                 for (int i = 0; i < len_l; ++i)
-                    gw += __ldcg(fa.recv_grads + (size_t)__ldg(fa.occ + seg0_l + i) * fa.slot_pitch + d);
-                bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, gw, __ldg(eps_bias + ul), cfac_l, h,
+                    gw_l += __ldcg(fa.recv_grads + (size_t)__ldg(fa.occ + seg0_l + i) * fa.slot_pitch + d);
+                bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, gw_l, __ldg(eps_bias + ul), cfac_l, h,
                                              step_size, inv_bc2, klw_l);
             }
         } else if (valid) {
-            bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, __ldg(gws + ul), __ldg(eps_bias + ul),
+            gw_l = __ldg(gws + ul);
+            bias_update<LINK, MODE, KLF>(bias, bias_m, bias_v, nullptr, rowid_l, gw_l, __ldg(eps_bias + ul),
                                          cfac_l, h, step_size, inv_bc2, klw_l);
         }
         float klrow = 0.f;
@@ -393,6 +397,7 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             const int rowid = bcast(rowid_l, sel);
             const float cfac = bcast(cfac_l, sel);
             const int u = cbase + sel;
+            const float gwr = c.pairwise ? bcast(gw_l, sel) : 0.f;      // pairwise: own term (sum r_n) v_u
             int n_req = 0, seg0 = 0;
             if (DPF) { n_req = bcast(len_l, sel); seg0 = bcast(seg0_l, sel); }
             const bool live = u < hi && kin && (!DPF || n_req > 0);
@@ -426,8 +431,9 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
                     const float sig = link_fn<LINK>(rho.v[j]);
-                    gmu.v[j] = fmaf(cfac, mu.v[j], g.v[j]);
-                    grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(g.v[j], e.v[j], cfac * (sig - fast_rcp(sig)));
+                    const float gj = fmaf(-gwr, fmaf(e.v[j], sig, mu.v[j]), g.v[j]);   // gwr = 0 unless pairwise
+                    gmu.v[j] = fmaf(cfac, mu.v[j], gj);
+                    grho.v[j] = link_grad<LINK>(rho.v[j]) * fmaf(gj, e.v[j], cfac * (sig - fast_rcp(sig)));
                     if (KLF) {
                         const float vr = sig * sig;
                         quad += vr + mu.v[j] * mu.v[j] - 1.f;
@@ -514,11 +520,15 @@ k_adam_rows_multi(DevCfg c, int u_stride, float* __restrict__ bias, float* __res
                 Vec<VEC> gs, ges;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) { gs.v[j] = 0.f; ges.v[j] = 0.f; }
+                const float gwr = c.pairwise ? __ldg(gws + u) : 0.f;       // pairwise: own term (sum r_n) v_{s,u}
                 for (int q = 0; q < S; ++q) {
                     const Vec<VEC> g = ld_vec_nc<VEC>(grow + ((size_t)q * u_stride + u) * d + k);
                     const Vec<VEC> e = ld_vec_nc<VEC>(eps_entity + ((size_t)q * eps_stride + u) * d + k);
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) { gs.v[j] += g.v[j]; ges.v[j] = fmaf(g.v[j], e.v[j], ges.v[j]); }
+                    for (int j = 0; j < VEC; ++j) {
+                        const float gj = fmaf(-gwr, fmaf(e.v[j], link_fn<LINK>(rho.v[j]), mu.v[j]), g.v[j]);
+                        gs.v[j] += gj; ges.v[j] = fmaf(gj, e.v[j], ges.v[j]);
+                    }
                 }
                 Vec<VEC> gmu, grho;
 #pragma unroll

@@ -9,6 +9,7 @@ constexpr int kGridCap = 2048;      // most blocks a step kernel is launched wit
 
 struct DevCfg {
     int B, F, d, S, n_classes;
+    int pairwise;                                        // row gradients hold sum r_n S_n: the row kernel removes (sum r_n) v_u
     int row_stride, row_offset;                          // global id = row*stride + offset (sharding)
     int class_bound[kMaxFields];
     float class_size[kMaxFields];
@@ -19,6 +20,9 @@ struct DevCfg {
 static DevCfg make_dev(const vfmb_config* c) {
     DevCfg r{};
     r.B = c->B; r.F = c->F; r.d = c->d; r.S = c->S; r.n_classes = c->n_classes;
+    // F > 2 fields are scored pairwise; F == 1 is the owner side of a row-sharded step, which
+    // is told through `interaction` what its requesters' model is
+    r.pairwise = (c->F > 2 || (c->F == 1 && c->interaction == VFMB_INTER_PAIRWISE)) ? 1 : 0;
     for (int i = 0; i < kMaxFields; ++i) { r.class_bound[i] = c->class_bound[i]; r.class_size[i] = c->class_size[i]; }
     r.n_train = c->n_train; r.seed = c->seed;
     r.row_stride = c->row_stride > 0 ? c->row_stride : 1;

@@ -420,7 +420,8 @@ class ShardedSampled:
             self.peer = self._local_group.member(p, M, d, dev)
 
     def _cfg(self, B, F, R, n_train, bounds, sizes, seed, stride, off):
-        cfg = make_config(B, F, self.d, R, 1, self.output, self.link, bounds, sizes, n_train, seed)
+        cfg = make_config(B, F, self.d, R, 1, self.output, self.link, bounds, sizes, n_train, seed,
+                          "pairwise" if self.F > 2 else "prod")      # the owner side (F = 1) learns the model's interaction
         cfg.row_stride, cfg.row_offset = int(stride), int(off)
         return cfg
 
