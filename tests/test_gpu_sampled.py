@@ -466,6 +466,40 @@ def test_pipelined_and_register_staged_row_updates_agree_bitwise(name):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_gather_launch_knobs_do_not_change_a_bit(fuse):
+    """Tile hand-out (static stride / atomic counter) and the fence flavour of the cut-row finisher are
+    scheduling only: parameters, moments and losses are identical.  The batch has Zipf head rows of
+    hundreds of occurrences (cut rows, two-level finisher) and thousands of short rows (kept whole)."""
+    from vae_b200 import _lib as L
+    from vae_b200.vfm_torch import CF
+    fs, d, B = [3000, 400], 32, 16384
+    rng = np.random.default_rng(11)
+    p1 = 1.0 / np.arange(1, fs[1] + 1); p1 /= p1.sum()
+    x = np.stack([rng.integers(0, fs[0], B), fs[0] + rng.choice(fs[1], B, p=p1)], 1).astype(np.int64)
+    y = rng.normal(size=B).astype(np.float32)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    counts = torch.from_numpy(np.bincount(x.reshape(-1), minlength=sum(fs)).astype(np.float32))
+    res = []
+    for dyn, fence in ((1, 1), (0, 0), (1, 0)):
+        L.check(L.lib().vfmb_set_tuning(b"gather_dyn", dyn))
+        L.check(L.lib().vfmb_set_tuning(b"gather_fence", fence))
+        L.check(L.lib().vfmb_set_tuning(b"fuse_score", fuse))
+        try:
+            torch.manual_seed(2)
+            m = CF(d, output="reg", n_users=fs[0], n_items=fs[1], train_counts=counts, n_train=B, max_batch=B, lr=0.01)
+            losses = [m.fused_step(xd, yd)["loss"].item() for _ in range(4)]
+            res.append((losses, m.entity_params.weight.clone(), m.entity_m.clone(), m.bias_params.weight.clone()))
+        finally:
+            L.lib().vfmb_set_tuning(b"gather_dyn", 1)
+            L.lib().vfmb_set_tuning(b"gather_fence", 1)
+            L.lib().vfmb_set_tuning(b"fuse_score", -1)
+    for r in res[1:]:
+        assert r[0] == res[0][0]
+        for a, b in zip(res[0][1:], r[1:]):
+            assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("output,F", [("class", 2), ("reg", 2), ("class", 3)])
 def test_predict_proba_many_samples_matches_oracle(output, F):
     """vfm.py:1047-1057: mean over S = 64 variational samples of the likelihood mean and the population

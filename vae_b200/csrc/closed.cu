@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256)
 k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
           const int32_t* __restrict__ urec, const float* __restrict__ vs2, const float* __restrict__ msg,
           const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
-          int32_t* arrive) {
+          int32_t* arrive, GatherKnobs kn) {
     constexpr int GPW = kWarp / LPR;
     const int dp = 3 * d + 4;
     const int lane = threadIdx.x & 31, gl = lane % LPR;
@@ -321,11 +321,10 @@ k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_
     const int pitch = (F == 2) ? 2 * d : 3 * d;
 
     for (int tile = group; tile < n_tiles; tile += ngroups) {
-        const int t0 = tile * kTile, t1 = min(N, t0 + kTile);
-        const bool head_open = t0 > 0 && __ldg(pos_rank + t0 - 1) == __ldg(pos_rank + t0);
-        const bool tail_open = t1 < N && __ldg(pos_rank + t1) == __ldg(pos_rank + t1 - 1);
-        const int first_u = __ldg(pos_rank + t0), last_u = __ldg(pos_rank + t1 - 1);
-        int cur = first_u;
+        const TileSpan ts = tile_span(tile, N, kn.keep, pos_rank, urec);    // short rows kept whole (step_common.cuh)
+        const int t0 = ts.t0, t1 = ts.t1;
+        if (t0 >= t1) continue;
+        int cur = ts.head_u;                                // else set from the first position
         Vec<VEC> aA[NV], aB[NV], aC[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i)
@@ -334,7 +333,7 @@ k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_
         float gd = 0.f;
 
         auto flush = [&](int u) {
-            const bool open_h = head_open && u == first_u, open_t = tail_open && u == last_u;
+            const bool open_h = u == ts.head_u, open_t = u == ts.tail_u;
             float* dst; float* dstw;
             if (open_h)      { dst = gslot + ((size_t)tile * 2) * dp;     dstw = dst + 3 * d; }
             else if (open_t) { dst = gslot + ((size_t)tile * 2 + 1) * dp; dstw = dst + 3 * d; }
@@ -357,6 +356,7 @@ k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_
             const int ur = ok ? __ldg(pos_rank + idx) : 0;
             const int cnt = min(LPR, t1 - b0);
             const int src0 = __shfl_sync(gmask, src, 0, LPR);
+            if (b0 == t0) cur = __shfl_sync(gmask, ur, 0, LPR);
             for (int j = 0; j < cnt; j += 2) {                 // 2 x (2 or 3) row slices in flight
                 float rj[2]; int uj[2]; Vec<VEC> tm[2][NV], tq[2][NV], tc[2][NV];
 #pragma unroll
@@ -407,11 +407,12 @@ k_cgather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_
         }
         flush(cur);
         // the group storing the last partial of a cut row adds them in tile order (step_common.cuh)
-        if (head_open) finish_cut_row<VEC, LPR, NV, 3>(first_u, tile, d, nullptr, urec, gslot, grow + (size_t)first_u * 3 * d,
-                                                       gws + first_u, arrive, n_tiles + 1);
-        if (tail_open && !(head_open && last_u == first_u))
-            finish_cut_row<VEC, LPR, NV, 3>(last_u, tile, d, nullptr, urec, gslot, grow + (size_t)last_u * 3 * d, gws + last_u,
-                                            arrive, n_tiles + 1);
+        if (ts.head_u >= 0)
+            finish_cut_row<VEC, LPR, NV, 3>(ts.head_u, tile, d, nullptr, urec, gslot, grow + (size_t)ts.head_u * 3 * d,
+                                            gws + ts.head_u, arrive, n_tiles + 1, kn.light_fence);
+        if (ts.tail_u >= 0 && ts.tail_u != ts.head_u)
+            finish_cut_row<VEC, LPR, NV, 3>(ts.tail_u, tile, d, nullptr, urec, gslot, grow + (size_t)ts.tail_u * 3 * d,
+                                            gws + ts.tail_u, arrive, n_tiles + 1, kn.light_fence);
     }
 }
 
@@ -830,7 +831,8 @@ extern "C" int vfmb_closed_backward_weighted(const vfmb_config* cfg, const vfmb_
     VFMB_LAYOUT_SWITCH(L, {
         k_cgather<VEC, LPR, NV><<<grid_t, 256, 0, counted(stream)>>>(cfg->d, cfg->F, cfg->B * cfg->F, plan->partner,
                                                             plan->pos_rank, plan->urec, io->vs, io->msg, io->rsorted,
-                                                            gslot, io->grow, io->gws, arrive);
+                                                            gslot, io->grow, io->gws, arrive,
+                                                            GatherKnobs{tuning().gather_keep, 0, tuning().gather_fence});
     });
     cudaEvent_t ev0, ev1;                                   // measurement hook (vfmb_profile_events)
     profile_events(&ev0, &ev1);

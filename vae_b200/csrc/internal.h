@@ -27,6 +27,10 @@ struct Tuning {
     int adam_reserve = 0;    // 1: k_adam_rows also leaves the reserved slot free
     int adam_pipe = 1;       // Adam on the touched rows: cp.async-pipelined kernel (k_adam_rows_pipe) when the row
                              //   layout allows (d % 4 == 0, d <= 128); 0 = the register-staged k_adam_rows
+    int gather_dyn = 1;      // backward gather: tiles after a group's first are handed out by an atomic counter
+                             //   (0 = static stride); results do not depend on it
+    int gather_keep = 32;    // backward gather: rows of up to this many occurrences are never cut by a tile boundary
+    int gather_fence = 1;    // finisher of cut rows: 1 = fence.acq_rel.gpu, 0 = __threadfence() (fence.sc)
     int prefetch_mv = 0;     // fused step: earlier phases pull the Adam moments of the touched rows into L2
                              //   (bit 0: k_stage fetches m, bit 1: k_stage fetches v, bit 2: k_gather fetches m,
                              //    bit 3: k_gather fetches v)

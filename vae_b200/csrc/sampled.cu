@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(256, 2)
 k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
          const int32_t* __restrict__ urec, const float* __restrict__ vs, const float* __restrict__ msg,
          const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
-         int32_t* arrive, int vp, float* const* __restrict__ gptr, const int32_t* __restrict__ own_slot) {
+         int32_t* arrive, int vp, float* const* __restrict__ gptr, const int32_t* __restrict__ own_slot,
+         GatherKnobs kn) {
     // F > 2 (pairwise): the sums are over the per-sample field sums S_n; the row's own term (sum r_n) v_u is
     // removed by the row kernel, which holds v_u anyway (DevCfg.pairwise).
     // mode B: vp = pitch of the gathered rows (received slots: d + 4); gptr[u] = where the finished gradient
@@ -533,13 +534,17 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
     const float* table = (F == 2) ? vs : msg;
     const int tpitch = (F == 2 || UNIT) ? vp : d;        // F > 2: the per-sample field sums are local, d wide
 
-    for (int tile = group; tile < n_tiles; tile += ngroups) {
-        const int t0 = tile * kTile, t1 = min(N, t0 + kTile);
-        // does the first row continue from the previous tile / the last row into the next one?
-        const bool head_open = t0 > 0 && __ldg(pos_rank + t0 - 1) == __ldg(pos_rank + t0);
-        const bool tail_open = t1 < N && __ldg(pos_rank + t1) == __ldg(pos_rank + t1 - 1);
-        const int first_u = __ldg(pos_rank + t0), last_u = __ldg(pos_rank + t1 - 1);
-        int cur = first_u;
+    // tiles: the first one by group index, the following ones from a counter (tile costs vary with the row
+    // lengths and correlate along the sorted list; a fixed stride left SMs idle for half of the kernel)
+    int32_t* tctr = arrive + 3 * (n_tiles + 1);         // [0] tiles handed out, [1] groups done; both end at zero
+    for (int tile = group, next; tile < n_tiles; tile = next) {
+        int fetched = 0;
+        if (kn.dyn && gl == 0) fetched = atomicAdd(tctr, 1);      // in flight during the tile
+        // [t0, t1): the tile's positions, short rows kept whole; head_u / tail_u: the long row that continues
+        // from the previous tile / into the next one
+        const TileSpan ts = tile_span(tile, N, kn.keep, pos_rank, urec);
+        const int t0 = ts.t0, t1 = ts.t1;
+        int cur = ts.head_u;                                // else set from the first position
         Vec<VEC> acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i)
@@ -549,7 +554,7 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
 
         auto row_out = [&](int u) { return gptr ? gptr[u] : grow + (size_t)u * d; };
         auto flush = [&](int u) {
-            const bool open_h = head_open && u == first_u, open_t = tail_open && u == last_u;
+            const bool open_h = u == ts.head_u, open_t = u == ts.tail_u;
             float* dst; float* dstw;
             if (open_h)      { dst = gslot + ((size_t)tile * 2) * dp;     dstw = dst + d; }
             else if (open_t) { dst = gslot + ((size_t)tile * 2 + 1) * dp; dstw = dst + d; }
@@ -572,6 +577,7 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
             const int ur = ok ? __ldg(pos_rank + idx) : 0;
             const int cnt = min(LPR, t1 - b0);
             const int src0 = __shfl_sync(gmask, src, 0, LPR);
+            if (b0 == t0) cur = __shfl_sync(gmask, ur, 0, LPR);
             constexpr int UNR = (NV == 1) ? 8 : 4;
             for (int j = 0; j < cnt; j += UNR) {               // UNR row gathers in flight
                 float rj[UNR]; int uj[UNR]; Vec<VEC> t[UNR][NV];
@@ -612,19 +618,21 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
                 }
             }
         }
-        flush(cur);
+        if (t0 < t1) flush(cur);                           // (a tile can be empty: its rows went to the left)
         // rows cut by this tile's boundaries (at most two): whoever stores the last partial finishes the row
-        if (head_open) {
-            float* o = row_out(first_u);
-            finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, nullptr, urec, gslot, o,
-                                            gptr ? o + d : gws + first_u, arrive, n_tiles + 1);
+        if (ts.head_u >= 0) {
+            float* o = row_out(ts.head_u);
+            finish_cut_row<VEC, LPR, NV, 1>(ts.head_u, tile, d, nullptr, urec, gslot, o,
+                                            gptr ? o + d : gws + ts.head_u, arrive, n_tiles + 1, kn.light_fence);
         }
-        if (tail_open && !(head_open && last_u == first_u)) {
-            float* o = row_out(last_u);
-            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, nullptr, urec, gslot, o,
-                                            gptr ? o + d : gws + last_u, arrive, n_tiles + 1);
+        if (ts.tail_u >= 0 && ts.tail_u != ts.head_u) {
+            float* o = row_out(ts.tail_u);
+            finish_cut_row<VEC, LPR, NV, 1>(ts.tail_u, tile, d, nullptr, urec, gslot, o,
+                                            gptr ? o + d : gws + ts.tail_u, arrive, n_tiles + 1, kn.light_fence);
         }
+        next = kn.dyn ? ngroups + __shfl_sync(gmask, fetched, 0, LPR) : tile + ngroups;
     }
+    if (kn.dyn && gl == 0 && atomicAdd(tctr + 1, 1) == ngroups - 1) { tctr[0] = 0; tctr[1] = 0; }   // last group out
 }
 
 // ------------------------------------------------------------------------------- k_gather_score
@@ -644,7 +652,8 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
                const float* __restrict__ eps_global, int32_t* noise_step, const int32_t* __restrict__ meta,
                float* __restrict__ pred, float* __restrict__ mean, float* __restrict__ resid,
                float* gslot, float* __restrict__ grow, float* __restrict__ gws,
-               double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats) {
+               double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
+               GatherKnobs kn) {
     constexpr int GPW = kWarp / LPR, UNR = 4;
     const int d = c.d, B = c.B, N = 2 * c.B;
     const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
@@ -663,11 +672,10 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
     double acc3[3] = {0.0, 0.0, 0.0};                   // nll, resid, squared error (field-0 occurrences)
 
     for (int tile = group; tile < n_tiles; tile += ngroups) {
-        const int t0 = tile * kTile, t1 = min(N, t0 + kTile);
-        const bool head_open = t0 > 0 && __ldg(pos_rank + t0 - 1) == __ldg(pos_rank + t0);
-        const bool tail_open = t1 < N && __ldg(pos_rank + t1) == __ldg(pos_rank + t1 - 1);
-        const int first_u = __ldg(pos_rank + t0), last_u = __ldg(pos_rank + t1 - 1);
-        int cur = first_u;
+        const TileSpan ts = tile_span(tile, N, kn.keep, pos_rank, urec);
+        const int t0 = ts.t0, t1 = ts.t1;
+        if (t0 >= t1) continue;
+        int cur = ts.head_u;                                // else set from the first position
         Vec<VEC> acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i)
@@ -676,7 +684,7 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
         float gw = 0.f;
 
         auto flush = [&](int u) {
-            const bool open_h = head_open && u == first_u, open_t = tail_open && u == last_u;
+            const bool open_h = u == ts.head_u, open_t = u == ts.tail_u;
             float* dst; float* dstw;
             if (open_h)      { dst = gslot + ((size_t)tile * 2) * dp;     dstw = dst + d; }
             else if (open_t) { dst = gslot + ((size_t)tile * 2 + 1) * dp; dstw = dst + d; }
@@ -701,6 +709,7 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
             const float yl = ok ? __ldg(y + (o >> 1)) : 0.f;
             const int cnt = min(LPR, t1 - b0);
             const int src0 = __shfl_sync(gmask, src, 0, LPR), ur0 = __shfl_sync(gmask, ur, 0, LPR);
+            if (b0 == t0) cur = ur0;
             for (int j = 0; j < cnt; j += UNR) {               // UNR row pairs in flight
                 int uj[UNR], sj[UNR];
                 Vec<VEC> t[UNR][NV], own[UNR][NV];
@@ -769,11 +778,12 @@ k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __res
             }
         }
         flush(cur);
-        if (head_open) finish_cut_row<VEC, LPR, NV, 1>(first_u, tile, d, nullptr, urec, gslot, grow + (size_t)first_u * d,
-                                                       gws + first_u, arrive, n_tiles + 1);
-        if (tail_open && !(head_open && last_u == first_u))
-            finish_cut_row<VEC, LPR, NV, 1>(last_u, tile, d, nullptr, urec, gslot, grow + (size_t)last_u * d, gws + last_u,
-                                            arrive, n_tiles + 1);
+        if (ts.head_u >= 0)
+            finish_cut_row<VEC, LPR, NV, 1>(ts.head_u, tile, d, nullptr, urec, gslot, grow + (size_t)ts.head_u * d,
+                                            gws + ts.head_u, arrive, n_tiles + 1, kn.light_fence);
+        if (ts.tail_u >= 0 && ts.tail_u != ts.head_u)
+            finish_cut_row<VEC, LPR, NV, 1>(ts.tail_u, tile, d, nullptr, urec, gslot, grow + (size_t)ts.tail_u * d,
+                                            gws + ts.tail_u, arrive, n_tiles + 1, kn.light_fence);
     }
     if (block_partials<3>(acc3, partials, counter)) {
         double tot[3];
@@ -992,15 +1002,16 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
     float* const* gptr = gb ? gb->gptr : nullptr;
     const int32_t* own_slot = gb ? gb->own_slot : nullptr;
     const float* rs = (gb && gb->coef_in_row) ? nullptr : io->rsorted;
+    const GatherKnobs kn{tuning().gather_keep, tuning().gather_dyn, tuning().gather_fence};
     VFMB_LAYOUT_SWITCH(L, {
         if (unit_coef)
             k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
                 cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive,
-                vp, gptr, own_slot);
+                vp, gptr, own_slot, kn);
         else
             k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
                 cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive,
-                vp, gptr, own_slot);
+                vp, gptr, own_slot, kn);
     });
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1024,11 +1035,12 @@ static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, c
     int gs_grid = (int)((gs_warps + gs_block / 32 - 1) / (gs_block / 32));
     if (gs_grid > kGridCap) gs_grid = kGridCap;            // block partials are sized for kGridCap blocks
     int32_t* arrive = (int32_t*)((float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).arrive_off);
+    const GatherKnobs kn{tuning().gather_keep, 0, tuning().gather_fence};
 #define LAUNCH_GS(LINK, LIK)                                                                             \
     k_gather_score<VEC, LPR, NV, LINK, LIK><<<gs_grid, gs_block, 0, counted(stream)>>>(                  \
         dc, tab->scalars, plan->partner, plan->pos_rank, plan->occ, plan->urec, arrive, io->vs, io->ws, io->y, \
         io->eps_global, tab->noise_step, plan->meta, io->pred, io->mean, io->resid, gslot, io->grow, io->gws, \
-        io->partials, io->counters + 1, io->stats)
+        io->partials, io->counters + 1, io->stats, kn)
     VFMB_LAYOUT_SWITCH(L, {
         if (cfg->link == VFMB_LINK_ABS) {
             if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_GS(0, VFMB_GAUSSIAN); else LAUNCH_GS(0, VFMB_BERNOULLI);

@@ -184,7 +184,8 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g,
 
 // ------------------------------------------------------------------------------- cut rows
 // The backward's segmented reduction (k_gather / k_gather_score / k_cgather) walks the sorted
-// occurrence list in tiles of kTile positions.  A row cut by tile boundaries leaves one partial per
+// occurrence list in tiles of kTile positions (tile_span below: rows of up to kTile occurrences are kept
+// whole).  A longer row is cut by the tile boundaries and leaves one partial per
 // tile it touches: in the tail slot of its first tile, in the head slots of the following ones.
 // The lane group that stores the LAST partial adds them -- no separate combine launch (12 us of
 // pure latency on the ml20m step in round 1).  To keep that serial sum short for a Zipf head row
@@ -241,20 +242,58 @@ __device__ __forceinline__ void sum_slots(const float* gslot, int dp, int d, int
     }
 }
 
+// Tile bounds, snapped to row boundaries: a row of at most kTile occurrences is never cut -- it
+// belongs whole to the tile in which it starts -- so only longer rows (the Zipf head) leave partials and
+// pay for the finisher's fences and atomics.  Tile t nominally covers positions [t kTile, (t+1) kTile);
+// a boundary that falls inside a short row moves to the end of that row (the tile on its left takes the
+// whole row, at most kTile - 1 extra positions; a tile can come out empty).  head_u / tail_u: the long
+// row cut at the tile's start / end, or -1.  Every lane computes the same values (broadcast loads).
+struct TileSpan { int t0, t1, head_u, tail_u; };
+// launch knobs of the gather kernels (host side: Tuning); none of them changes a result bit EXCEPT keep,
+// which moves the cuts (and with them the association of a long row's sum)
+struct GatherKnobs { int keep; int dyn; int light_fence; };
+__device__ __forceinline__ int snap_boundary(int b, int N, int keep, const int32_t* __restrict__ pos_rank,
+                                             const int32_t* __restrict__ urec, int* cut_u) {
+    *cut_u = -1;
+    if (b <= 0) return 0;
+    if (b >= N) return N;
+    const int u = __ldg(pos_rank + b);
+    if (__ldg(pos_rank + b - 1) != u) return b;
+    const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
+    if (rec.y <= keep) return rec.z + rec.y;
+    *cut_u = u;
+    return b;
+}
+__device__ __forceinline__ TileSpan tile_span(int tile, int N, int keep, const int32_t* __restrict__ pos_rank,
+                                              const int32_t* __restrict__ urec) {
+    TileSpan s;
+    s.t0 = snap_boundary(tile * kTile, N, keep, pos_rank, urec, &s.head_u);
+    s.t1 = snap_boundary((tile + 1) * kTile, N, keep, pos_rank, urec, &s.tail_u);
+    return s;
+}
+// release / acquire around the arrival counters: fence.acq_rel is enough for the last-arriver pattern (the
+// partials are stored before the fence, counted after it; read after the counter and a second fence);
+// __threadfence() is fence.sc
+__device__ __forceinline__ void fence_gpu(bool light) {
+    if (light) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    else __threadfence();
+}
+
 // called by every lane of a group after it stored the partial of cut row u for `tile`
 template <int VEC, int LPR, int NV, int NW>
 __device__ __noinline__ void finish_cut_row(int u, int tile, int d, const float* __restrict__ own_row,
                                             const int32_t* __restrict__ urec, float* gslot, float* __restrict__ out_row,
-                                            float* __restrict__ out_w, int32_t* arrive, int n_tiles1) {
+                                            float* __restrict__ out_w, int32_t* arrive, int n_tiles1,
+                                            bool light_fence) {
     // own_row (F > 2, pairwise): the row's own sampled vector, removed from the sum; out_row / out_w:
     // where the finished gradient goes (the per-rank scratch, or the owner's slot over NVLink)
     const int lane = threadIdx.x & 31, gl = lane % LPR;
     const unsigned gmask = group_mask<LPR>();
     const int dp = NW * d + 4;
-    __threadfence();                                        // this group's partial is visible ...
+    fence_gpu(light_fence);                                        // this group's partial is visible ...
     __syncwarp(gmask);
     const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
-    const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;
+    const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;     // long rows are cut at the nominal boundaries
     const int run = (tile - tA) / kFan;
     const int first = tA + run * kFan, last = min(tB, first + kFan - 1);
     int32_t* c1 = arrive + 2 * first + (run == 0 ? 1 : 0);
@@ -262,7 +301,7 @@ __device__ __noinline__ void finish_cut_row(int u, int tile, int d, const float*
     if (gl == 0) old = atomicAdd(c1, 1);                    // ... before it is counted
     old = __shfl_sync(gmask, old, 0, LPR);
     if (old != last - first) return;                        // the group that completes the run goes on
-    __threadfence();
+    fence_gpu(light_fence);
     Vec<VEC> tot[NW][NV]; float gw;
     sum_slots<VEC, LPR, NV, NW>(gslot, dp, d, gl, first, run == 0, last - first + 1, 1, tot, gw);
     if (gl == 0) *c1 = 0;                                   // counter ready for the next step
@@ -276,14 +315,14 @@ __device__ __noinline__ void finish_cut_row(int u, int tile, int d, const float*
                 if (k < d) st_vec<VEC>(sp + w * d + k, tot[w][i]);
             }
         if (gl == 0) sp[NW * d] = gw;
-        __threadfence();
+        fence_gpu(light_fence);
         __syncwarp(gmask);
         int32_t* c2 = arrive + 2 * n_tiles1 + tA;
         const int n_runs = (tB - tA) / kFan + 1;
         if (gl == 0) old = atomicAdd(c2, 1);
         old = __shfl_sync(gmask, old, 0, LPR);
         if (old != n_runs - 1) return;
-        __threadfence();
+        fence_gpu(light_fence);
         sum_slots<VEC, LPR, NV, NW>(gslot, dp, d, gl, tA, true, n_runs, kFan, tot, gw);
         if (gl == 0) *c2 = 0;
     }
