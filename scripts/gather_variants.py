@@ -1,5 +1,5 @@
 """Backward-gather launch knobs side by side (run under an ncu launch list restricted to k_gather):
-for every (workload, gather_dyn, gather_fence, gather_keep) four fused steps, in this order."""
+for every (workload, gather_dyn, gather_wide) four fused steps, in this order."""
 import os
 import sys
 
@@ -10,7 +10,7 @@ import bench                                                   # noqa: E402
 from vae_b200 import synth                                      # noqa: E402
 from vae_b200 import _lib as L                                  # noqa: E402
 
-VARIANTS = [(0, 0, 32), (0, 1, 32), (1, 0, 32), (1, 1, 32), (1, 1, 64), (1, 1, 128), (1, 1, 1)]
+VARIANTS = [(0, 0), (0, 1), (1, 0), (1, 1)]      # (gather_dyn, gather_wide)
 L.check(L.lib().vfmb_set_grid_reserve(1))
 for name, rows in (("sideinfo", 1_000_000), ("ml20m", 2_000_000)):
     w = synth.make_workload(name, n_rows=rows)
@@ -20,12 +20,12 @@ for name, rows in (("sideinfo", 1_000_000), ("ml20m", 2_000_000)):
     y = torch.from_numpy(w.y).cuda()
     nb = w.n_train // B
     i = 0
-    for dyn, fence, keep in VARIANTS:
-        for k, v in (("gather_dyn", dyn), ("gather_fence", fence), ("gather_keep", keep)):
+    for dyn, wide in VARIANTS:
+        for k, v in (("gather_dyn", dyn), ("gather_wide", wide)):
             L.check(L.lib().vfmb_set_tuning(k.encode(), v))
         for _ in range(4):
             j = i % nb
             i += 1
             out = model.fused_step(x[j * B:(j + 1) * B], y[j * B:(j + 1) * B])
         torch.cuda.synchronize()
-        print(name, dyn, fence, keep, "loss", out["loss"].item(), flush=True)
+        print(name, dyn, wide, "loss", out["loss"].item(), flush=True)

@@ -493,7 +493,7 @@ def test_gather_launch_knobs_do_not_change_a_bit(fuse):
         finally:
             L.lib().vfmb_set_tuning(b"gather_dyn", 1)
             L.lib().vfmb_set_tuning(b"gather_fence", 1)
-            L.lib().vfmb_set_tuning(b"fuse_score", -1)
+            L.lib().vfmb_set_tuning(b"fuse_score", 0)
     for r in res[1:]:
         assert r[0] == res[0][0]
         for a, b in zip(res[0][1:], r[1:]):

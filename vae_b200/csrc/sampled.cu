@@ -503,136 +503,209 @@ k_scatter_resid(const float* __restrict__ resid, const int32_t* __restrict__ pos
 }
 
 // ------------------------------------------------------------------------------- k_gather
-// Backward, phase A: deterministic segmented reduction over the SORTED occurrence list, tiled by
-// position so that every lane group does the same amount of work whatever the row popularity
-// (a Zipf head row with thousands of occurrences is just many tiles).  A group walks the kTile
-// positions of its tile in order, accumulating r_n * partner row; when the unique rank changes it
-// flushes.  Rows that lie inside the tile are final (-> grow/gws).  A row cut by a tile boundary
-// leaves a partial in the tile's head slot (row continues from the previous tile) or tail slot
-// (row starts here and continues); k_adam_rows adds a row's partials in tile order.  Fixed
-// summation order, no atomics => bitwise reproducible.
+// Backward, phase A: deterministic segmented reduction over the SORTED occurrence list,
+//   g_u = sum over the occurrences (u, n) of  r_n * (partner row | field sums S_n),   g_w,u = sum r_n.
+// Tiled by POSITION, so every lane group does the same amount of work whatever the row popularity
+// (a Zipf head row with thousands of occurrences is just many tiles), in two levels:
+//   block tile  512 consecutive positions per block and pass, handed out by a counter;
+//   group tile  2 * LPR of them per lane group (two positions per lane: all index loads of a tile are
+//               one round trip, the row gathers UNR at a time).
+// A group walks its positions in order and flushes when the unique rank changes.  Rows inside the
+// group tile are final (-> grow/gws, or the owner's slot over NVLink).  A row cut by a group-tile
+// boundary leaves a partial in SHARED memory; after one __syncthreads the group holding the row's last
+// piece in the block adds the pieces in tile order.  Only a row that crosses a BLOCK-tile boundary goes
+// through global slots and finish_cut_row (fence + arrival counter; <= 2 per block tile -- in round-2
+// profiles the per-tile fences and atomics of a flat 32-position tiling cost as much as the gather).
+// The two groups of a warp run in lockstep (same trip counts, pads carry a zero coefficient), so the
+// shuffles are full-mask and the compiler needs no convergence checks.  Fixed summation order, no
+// floating-point atomics => bitwise reproducible whatever the schedule.
 // Everything read here is L2-resident scratch written by k_stage / k_score.
+#ifdef VFMB_TILE_TIMING                                     // measurement build (scripts/gather_tiles.py), not the product
+__device__ int4 g_tile_dbg[1 << 16];                        // per block tile: main cycles, combine cycles, SM, start (ns)
+__device__ __forceinline__ unsigned dbg_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (unsigned)t; }
+__device__ __forceinline__ int dbg_sm() { int s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+extern "C" int vfmb_debug_tile_times(int32_t* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_tile_dbg, (size_t)n * sizeof(int4));
+}
+#endif
+
 template <int VEC, int LPR, int NV, int UNIT>
 __global__ void __launch_bounds__(256, 2)
 k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
          const int32_t* __restrict__ urec, const float* __restrict__ vs, const float* __restrict__ msg,
          const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
-         int32_t* arrive, int vp, float* const* __restrict__ gptr, const int32_t* __restrict__ own_slot,
-         GatherKnobs kn) {
+         int32_t* arrive, int vp, float* const* __restrict__ gptr, GatherKnobs kn) {
     // F > 2 (pairwise): the sums are over the per-sample field sums S_n; the row's own term (sum r_n) v_u is
     // removed by the row kernel, which holds v_u anyway (DevCfg.pairwise).
     // mode B: vp = pitch of the gathered rows (received slots: d + 4); gptr[u] = where the finished gradient
-    // row of unique rank u goes (its owner's slot over NVLink, bias gradient at [d]); rsorted == NULL (owner
-    // side, UNIT): the coefficient sits at [d] of the row
-    constexpr int GPW = kWarp / LPR;
-    const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
-    const int lane = threadIdx.x & 31, gl = lane % LPR;
-    const unsigned gmask = group_mask<LPR>();
-    const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
-    const int ngroups = gridDim.x * (blockDim.x >> 5) * GPW;
-    const int n_tiles = (N + kTile - 1) / kTile;
-    const float* table = (F == 2) ? vs : msg;
-    const int tpitch = (F == 2 || UNIT) ? vp : d;        // F > 2: the per-sample field sums are local, d wide
+    // row of unique rank u goes (its owner's slot over NVLink, bias gradient at [d]).
+    // UNIT: unit coefficients (acc += row; the collective mode-B owner side), g_w still sums rsorted.
+    constexpr int GPW = kWarp / LPR, G = 8 * GPW;       // lane groups per warp / per block
+    constexpr int TP = 2 * LPR;                         // positions per group tile
+    constexpr int BT = G * TP;                          // positions per block tile (512)
+    constexpr int W = LPR * VEC * NV;                   // row width covered by a group
+    constexpr int SP = W + 4;                           // pitch of a partial in shared memory (sum of r at [W])
+    constexpr int UNR = LPR < 8 ? LPR : (NV == 1 ? 8 : 4);
+    __shared__ __align__(16) float s_part[2][G][2][SP]; // [parity][group][head | tail]
+    __shared__ int s_hu[2][G], s_tu[2][G], s_next[2];
 
-    // tiles: the first one by group index, the following ones from a counter (tile costs vary with the row
-    // lengths and correlate along the sorted list; a fixed stride left SMs idle for half of the kernel)
-    int32_t* tctr = arrive + 3 * (n_tiles + 1);         // [0] tiles handed out, [1] groups done; both end at zero
-    for (int tile = group, next; tile < n_tiles; tile = next) {
+    const int dp = d + 4;                               // global slot pitch (keeps 16 B alignment)
+    const int lane = threadIdx.x & 31, gl = lane % LPR, gbase = lane - gl;
+    const int g = (threadIdx.x >> 5) * GPW + lane / LPR;
+    const unsigned gmask = group_mask<LPR>();
+    const int n_bt = (N + BT - 1) / BT;
+    const float* table = (F == 2) ? vs : msg;
+    const int tpitch = (F == 2 || UNIT) ? vp : d;       // F > 2: the per-sample field sums are local, d wide
+    int32_t* tctr = arrive + 3 * (n_bt + 1);            // [0] block tiles handed out, [1] blocks done; both end at zero
+    int kc[NV]; bool act[NV];                           // column of this lane; lanes past d load column 0 and store nothing
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { const int k = (gl + i * LPR) * VEC; act[i] = k < d; kc[i] = act[i] ? k : 0; }
+    auto row_out = [&](int u) { return gptr ? gptr[u] : grow + (size_t)u * d; };
+
+    int it = 0;
+    for (int bt = blockIdx.x; bt < n_bt; ++it) {
+        const int par = it & 1;
         int fetched = 0;
-        if (kn.dyn && gl == 0) fetched = atomicAdd(tctr, 1);      // in flight during the tile
-        // [t0, t1): the tile's positions, short rows kept whole; head_u / tail_u: the long row that continues
-        // from the previous tile / into the next one
-        const TileSpan ts = tile_span(tile, N, kn.keep, pos_rank, urec);
-        const int t0 = ts.t0, t1 = ts.t1;
-        int cur = ts.head_u;                                // else set from the first position
+        if (kn.dyn && threadIdx.x == 0) fetched = atomicAdd(tctr, 1);   // in flight during the tile
+#ifdef VFMB_TILE_TIMING
+        const long long dbg_c0 = clock64(); const unsigned dbg_t0 = dbg_ns();
+#endif
+        const int t0 = bt * BT + g * TP, t1 = min(N, t0 + TP), cnt = max(0, t1 - t0);
+        const int wt0 = bt * BT + (threadIdx.x >> 5) * GPW * TP;        // first position of the warp
+        // ---- lane-parallel: two positions per lane, plus the ranks just outside the tile
+        int src[2], ur[2]; float rr[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int idx = t0 + h * LPR + gl;
+            const bool ok = idx < t1;
+            src[h] = ok ? __ldg(partner + idx) : 0;
+            rr[h] = ok ? __ldg(rsorted + idx) : 0.f;
+            ur[h] = ok ? __ldg(pos_rank + idx) : -1;
+        }
+        int nb = -1;
+        if (gl == 0 && cnt > 0 && t0 > 0) nb = __ldg(pos_rank + t0 - 1);
+        if (gl == LPR - 1 && cnt > 0 && t1 < N) nb = __ldg(pos_rank + t1);
+        const int prev_u = __shfl_sync(0xffffffffu, nb, gbase), next_u = __shfl_sync(0xffffffffu, nb, gbase + LPR - 1);
+        const int first_u = __shfl_sync(0xffffffffu, ur[0], gbase);
+        const int la = __shfl_sync(0xffffffffu, ur[0], gbase + min(max(cnt, 1), LPR) - 1);
+        const int lb = __shfl_sync(0xffffffffu, ur[1], gbase + min(max(cnt - LPR, 1), LPR) - 1);
+        const int last_u = cnt > LPR ? lb : la;                       // -1 when the tile has no position
+#pragma unroll
+        for (int h = 0; h < 2; ++h) if (ur[h] < 0) ur[h] = last_u;    // pads never open a segment
+        const int head_u = (cnt > 0 && prev_u == first_u) ? first_u : -1;   // the row continues from the previous tile
+        const int tail_u = (cnt > 0 && next_u == last_u) ? last_u : -1;     // ... into the next one
+
+        int cur = first_u;
         Vec<VEC> acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
+            for (int q = 0; q < VEC; ++q) acc[i].v[q] = 0.f;
         float gw = 0.f;
-
-        auto row_out = [&](int u) { return gptr ? gptr[u] : grow + (size_t)u * d; };
         auto flush = [&](int u) {
-            const bool open_h = u == ts.head_u, open_t = u == ts.tail_u;
-            float* dst; float* dstw;
-            if (open_h)      { dst = gslot + ((size_t)tile * 2) * dp;     dstw = dst + d; }
-            else if (open_t) { dst = gslot + ((size_t)tile * 2 + 1) * dp; dstw = dst + d; }
-            else             { dst = row_out(u);                          dstw = gptr ? dst + d : gws + u; }
+            if (u == head_u || u == tail_u) {                         // partial: shared memory
+                float* dst = &s_part[par][g][u == head_u ? 0 : 1][0];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                int k = (gl + i * LPR) * VEC;
-                if (k < d) {
-                    st_vec<VEC>(dst + k, acc[i]);
-                }
+                for (int i = 0; i < NV; ++i) st_vec<VEC>(dst + (gl + i * LPR) * VEC, acc[i]);
+                if (gl == 0) dst[W] = gw;
+            } else {
+                float* dst = row_out(u);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) if (act[i]) st_vec<VEC>(dst + kc[i], acc[i]);
+                if (gl == 0) *(gptr ? dst + d : gws + u) = gw;
             }
-            if (gl == 0) *dstw = gw;
         };
 
-        for (int b0 = t0; b0 < t1; b0 += LPR) {
-            const int idx = b0 + gl;
-            const bool ok = idx < t1;
-            const int src = ok ? __ldg(partner + idx) : 0;
-            const float r = !ok ? 0.f : (rsorted ? __ldg(rsorted + idx) : __ldg(table + (size_t)src * tpitch + d));
-            const int ur = ok ? __ldg(pos_rank + idx) : 0;
-            const int cnt = min(LPR, t1 - b0);
-            const int src0 = __shfl_sync(gmask, src, 0, LPR);
-            if (b0 == t0) cur = __shfl_sync(gmask, ur, 0, LPR);
-            constexpr int UNR = (NV == 1) ? 8 : 4;
-            for (int j = 0; j < cnt; j += UNR) {               // UNR row gathers in flight
-                float rj[UNR]; int uj[UNR]; Vec<VEC> t[UNR][NV];
 #pragma unroll
-                for (int e = 0; e < UNR; ++e) {
-                    rj[e] = __shfl_sync(gmask, r, (j + e) & (LPR - 1), LPR);
-                    uj[e] = __shfl_sync(gmask, ur, (j + e) & (LPR - 1), LPR);
-                    int sj = __shfl_sync(gmask, src, (j + e) & (LPR - 1), LPR);
-                    if (j + e >= cnt) sj = src0;
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+            for (int j0 = 0; j0 < LPR; j0 += UNR) {
+                if (wt0 + h * LPR + j0 >= N) break;                   // warp-uniform: nothing left for either group
+                Vec<VEC> t[UNR][NV]; int uj[UNR]; float cj[UNR];
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        int k = (gl + i * LPR) * VEC;
-                        if (k < d) t[e][i] = ld_vec_nc<VEC>(table + (size_t)sj * tpitch + k);
-                    }
+                for (int e = 0; e < UNR; ++e) {                       // UNR row gathers in flight
+                    const int sj = __shfl_sync(0xffffffffu, src[h], gbase + j0 + e);
+                    uj[e] = __shfl_sync(0xffffffffu, ur[h], gbase + j0 + e);
+                    cj[e] = __shfl_sync(0xffffffffu, rr[h], gbase + j0 + e);
+                    const float* row = table + (size_t)sj * tpitch;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) t[e][i] = ld_vec_nc<VEC>(row + kc[i]);
                 }
 #pragma unroll
                 for (int e = 0; e < UNR; ++e) {
-                    if (j + e < cnt) {                         // group-uniform
-                        if (uj[e] != cur) {
-                            flush(cur);
-                            cur = uj[e];
+                    if (uj[e] != cur) {                               // group-uniform
+                        flush(cur);
+                        cur = uj[e];
 #pragma unroll
-                            for (int i = 0; i < NV; ++i)
+                        for (int i = 0; i < NV; ++i)
 #pragma unroll
-                                for (int q = 0; q < VEC; ++q) acc[i].v[q] = 0.f;
-                            gw = 0.f;
-                        }
-                        gw += rj[e];
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) {
-                            int k = (gl + i * LPR) * VEC;
-                            if (k < d)
-#pragma unroll
-                                for (int q = 0; q < VEC; ++q)
-                                    acc[i].v[q] = UNIT ? acc[i].v[q] + t[e][i].v[q] : fmaf(rj[e], t[e][i].v[q], acc[i].v[q]);
-                        }
+                            for (int q = 0; q < VEC; ++q) acc[i].v[q] = 0.f;
+                        gw = 0.f;
                     }
+                    gw += cj[e];
+                    const float ce = UNIT ? ((t0 + h * LPR + j0 + e < t1) ? 1.f : 0.f) : cj[e];   // pads: zero
+#pragma unroll
+                    for (int i = 0; i < NV; ++i)
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) acc[i].v[q] = fmaf(ce, t[e][i].v[q], acc[i].v[q]);
                 }
             }
         }
-        if (t0 < t1) flush(cur);                           // (a tile can be empty: its rows went to the left)
-        // rows cut by this tile's boundaries (at most two): whoever stores the last partial finishes the row
-        if (ts.head_u >= 0) {
-            float* o = row_out(ts.head_u);
-            finish_cut_row<VEC, LPR, NV, 1>(ts.head_u, tile, d, nullptr, urec, gslot, o,
-                                            gptr ? o + d : gws + ts.head_u, arrive, n_tiles + 1, kn.light_fence);
+        if (cur >= 0) flush(cur);
+        if (gl == 0) { s_hu[par][g] = head_u; s_tu[par][g] = tail_u; }
+        if (threadIdx.x == 0) s_next[par] = kn.dyn ? (int)gridDim.x + fetched : bt + (int)gridDim.x;
+#ifdef VFMB_TILE_TIMING
+        const long long dbg_c1 = clock64();
+#endif
+        __syncthreads();
+        // ---- rows cut by group-tile boundaries inside the block: the group holding the last piece adds them
+        const int g_last = (min(N, bt * BT + BT) - bt * BT - 1) / TP;     // last group with positions
+        if (head_u >= 0 && (tail_u != head_u || g == g_last)) {
+            const int u = head_u;
+            int s0 = g;
+            while (s0 > 0 && s_hu[par][s0] == u) --s0;                    // first piece: group s0
+            const bool open_left = s_hu[par][s0] == u;                    // (s0 == 0) the row comes from the previous block tile
+            const bool open_right = tail_u == u;                          // (g == g_last) ... runs on into the next one
+            const float* p0 = &s_part[par][s0][open_left ? 0 : 1][0];
+            Vec<VEC> tot[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) tot[i] = ld_vec<VEC>(p0 + (gl + i * LPR) * VEC);
+            float gwt = p0[W];
+            for (int k = s0 + 1; k <= g; ++k) {                           // head partials, in tile order
+                const float* pk = &s_part[par][k][0][0];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const Vec<VEC> a = ld_vec<VEC>(pk + (gl + i * LPR) * VEC);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) tot[i].v[q] += a.v[q];
+                }
+                gwt += pk[W];
+            }
+            float* o = row_out(u);
+            float* ow = gptr ? o + d : gws + u;
+            const bool cut = open_left || open_right;
+            float* dst = cut ? gslot + ((size_t)bt * 2 + (open_left ? 0 : 1)) * dp : o;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) if (act[i]) st_vec<VEC>(dst + kc[i], tot[i]);
+            if (gl == 0) *(cut ? dst + d : ow) = gwt;
+            if (cut) finish_cut_row<VEC, LPR, NV, 1>(u, bt, d, nullptr, urec, gslot, o, ow, arrive, n_bt + 1, kn.light_fence, BT);
         }
-        if (ts.tail_u >= 0 && ts.tail_u != ts.head_u) {
-            float* o = row_out(ts.tail_u);
-            finish_cut_row<VEC, LPR, NV, 1>(ts.tail_u, tile, d, nullptr, urec, gslot, o,
-                                            gptr ? o + d : gws + ts.tail_u, arrive, n_tiles + 1, kn.light_fence);
+        if (tail_u >= 0 && tail_u != head_u && g == g_last) {             // a row that starts in the last group tile and runs on
+            const int u = tail_u;
+            const float* p0 = &s_part[par][g][1][0];
+            float* dst = gslot + ((size_t)bt * 2 + 1) * dp;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) if (act[i]) st_vec<VEC>(dst + kc[i], ld_vec<VEC>(p0 + (gl + i * LPR) * VEC));
+            if (gl == 0) dst[d] = p0[W];
+            float* o = row_out(u);
+            finish_cut_row<VEC, LPR, NV, 1>(u, bt, d, nullptr, urec, gslot, o, gptr ? o + d : gws + u, arrive, n_bt + 1, kn.light_fence, BT);
         }
-        next = kn.dyn ? ngroups + __shfl_sync(gmask, fetched, 0, LPR) : tile + ngroups;
+#ifdef VFMB_TILE_TIMING
+        if (threadIdx.x == 0) g_tile_dbg[bt & 0xFFFF] = make_int4((int)(dbg_c1 - dbg_c0), (int)(clock64() - dbg_c1), dbg_sm(), (int)dbg_t0);
+#endif
+        bt = s_next[par];          // (parity buffers: the next tile's partials do not touch what a slow combiner still reads)
     }
-    if (kn.dyn && gl == 0 && atomicAdd(tctr + 1, 1) == ngroups - 1) { tctr[0] = 0; tctr[1] = 0; }   // last group out
+    if (kn.dyn && threadIdx.x == 0 && atomicAdd(tctr + 1, 1) == (int)gridDim.x - 1) { tctr[0] = 0; tctr[1] = 0; }   // last block out
 }
 
 // ------------------------------------------------------------------------------- k_gather_score
@@ -968,7 +1041,7 @@ extern "C" int vfmb_sampled_forward(const vfmb_config* cfg, const vfmb_tables* t
 
 // mode B: rows gathered in place from received slots (pitch vp), finished gradient rows stored through
 // gptr (requester side) / coefficient read from the row itself (owner side)
-struct GatherB { const float* rows; int vp; const int32_t* partner; float* const* gptr; const int32_t* own_slot; bool coef_in_row; };
+struct GatherB { const float* rows; int vp; const int32_t* partner; float* const* gptr; };
 
 static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vfmb_step_io* io_,
                          const float* table, int32_t unit_coef, vfmb_stream stream_, int smp = 0,
@@ -986,7 +1059,7 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
         if (shifted.msg) shifted.msg += (size_t)smp * cfg->B * cfg->d;
     }
     const vfmb_step_io* io = &shifted;
-    if (!io->grow || !io->gws || (!io->rsorted && !(gb && gb->coef_in_row)) || !io->partials)
+    if (!io->grow || !io->gws || !io->rsorted || !io->partials)
         return set_error(VFMB_EINVAL, "vfmb_sampled_gather: scratch required");
     const Layout& L = P.L; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
@@ -1000,19 +1073,31 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
     const int vp = gb ? gb->vp : cfg->d;
     const int32_t* partner = gb && gb->partner ? gb->partner : plan->partner;
     float* const* gptr = gb ? gb->gptr : nullptr;
-    const int32_t* own_slot = gb ? gb->own_slot : nullptr;
-    const float* rs = (gb && gb->coef_in_row) ? nullptr : io->rsorted;
+    const float* rs = io->rsorted;
     const GatherKnobs kn{tuning().gather_keep, tuning().gather_dyn, tuning().gather_fence};
-    VFMB_LAYOUT_SWITCH(L, {
-        if (unit_coef)
-            k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
-                cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive,
-                vp, gptr, own_slot, kn);
-        else
-            k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, cap.n_tiles, 32 / L.lpr), 256, 0, counted(stream)>>>(
-                cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive,
-                vp, gptr, own_slot, kn);
+    // one block per 512-position block tile, at most the resident blocks (further tiles come from the counter)
+    const int64_t n_bt = ((int64_t)N + 511) / 512;
+#define LAUNCH_GATHER(VEC, LPR, NV)                                                                          \
+    do {                                                                                                     \
+        if (unit_coef)                                                                                       \
+            k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, n_bt * 8, 1), 256, 0, counted(stream)>>>( \
+                cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive, \
+                vp, gptr, kn);                                                                               \
+        else                                                                                                 \
+            k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, n_bt * 8, 1), 256, 0, counted(stream)>>>( \
+                cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive, \
+                vp, gptr, kn);                                                                               \
+    } while (0)
+    // The gather has no cross-lane arithmetic (every output element is a sequential sum over positions), so its
+    // lane mapping is free: half as many lanes per row with two vectors each puts twice the positions behind
+    // every warp instruction of the per-position bookkeeping, which is what bounds the kernel.
+    if (L.vec == 4 && L.nv == 1 && L.lpr == 8 && tuning().gather_wide) LAUNCH_GATHER(4, 4, 2);
+    else if (L.vec == 4 && L.nv == 1 && L.lpr == 16 && tuning().gather_wide) LAUNCH_GATHER(4, 8, 2);
+    else if (L.vec == 4 && L.nv == 1 && L.lpr == 32 && tuning().gather_wide) LAUNCH_GATHER(4, 16, 2);
+    else VFMB_LAYOUT_SWITCH(L, {
+        LAUNCH_GATHER(VEC, LPR, NV);
     });
+#undef LAUNCH_GATHER
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1180,7 +1265,7 @@ extern "C" int vfmb_shard_gather_put(const vfmb_config* cfg_l, const vfmb_plan* 
     if (!cfg_l || !recv_rows || !partner_slot || !gptr || !own_slot) return set_error(VFMB_EINVAL, "vfmb_shard_gather_put: bad argument");
     if (cfg_l->S != 1) return set_error(VFMB_ESHAPE, "vfmb_shard_gather_put: S = 1 only");
     GatherB gb{};
-    gb.rows = recv_rows; gb.vp = SP; gb.partner = partner_slot; gb.gptr = gptr; gb.own_slot = own_slot; gb.coef_in_row = false;
+    gb.rows = recv_rows; gb.vp = SP; gb.partner = partner_slot; gb.gptr = gptr;
     return launch_gather(cfg_l, plan_l, io_l, nullptr, 0, stream, 0, &gb);
 }
 

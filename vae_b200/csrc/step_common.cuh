@@ -284,7 +284,7 @@ template <int VEC, int LPR, int NV, int NW>
 __device__ __noinline__ void finish_cut_row(int u, int tile, int d, const float* __restrict__ own_row,
                                             const int32_t* __restrict__ urec, float* gslot, float* __restrict__ out_row,
                                             float* __restrict__ out_w, int32_t* arrive, int n_tiles1,
-                                            bool light_fence) {
+                                            bool light_fence, int tile_size = kTile) {
     // own_row (F > 2, pairwise): the row's own sampled vector, removed from the sum; out_row / out_w:
     // where the finished gradient goes (the per-rank scratch, or the owner's slot over NVLink)
     const int lane = threadIdx.x & 31, gl = lane % LPR;
@@ -293,7 +293,7 @@ __device__ __noinline__ void finish_cut_row(int u, int tile, int d, const float*
     fence_gpu(light_fence);                                        // this group's partial is visible ...
     __syncwarp(gmask);
     const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + u);
-    const int tA = rec.z / kTile, tB = (rec.z + rec.y - 1) / kTile;     // long rows are cut at the nominal boundaries
+    const int tA = rec.z / tile_size, tB = (rec.z + rec.y - 1) / tile_size;     // cut rows are cut at the nominal boundaries
     const int run = (tile - tA) / kFan;
     const int first = tA + run * kFan, last = min(tB, first + kFan - 1);
     int32_t* c1 = arrive + 2 * first + (run == 0 ? 1 : 0);
