@@ -39,6 +39,8 @@ extern "C" int vfmb_set_tuning(const char* key, int value) {
     if (!strcmp(key, "fuse_score")) { if (value < -1 || value > 1) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: fuse_score -1..1"); t.fuse_score = value; return 0; }
     if (!strcmp(key, "adam_reserve")) { t.adam_reserve = value != 0; return 0; }
     if (!strcmp(key, "adam_pipe")) { t.adam_pipe = value != 0; return 0; }
+    if (!strcmp(key, "stage_wide")) { t.stage_wide = value != 0; return 0; }
+    if (!strcmp(key, "score_wide")) { t.score_wide = value != 0; return 0; }
     if (!strcmp(key, "gather_wide")) { t.gather_wide = value != 0; return 0; }
     if (!strcmp(key, "gather_dyn")) { t.gather_dyn = value != 0; return 0; }
     if (!strcmp(key, "gather_fence")) { t.gather_fence = value != 0; return 0; }

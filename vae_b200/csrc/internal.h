@@ -25,11 +25,15 @@ struct Tuning {
     int grid_reserve = 0;    // block slots per SM the persistent step kernels leave free
     int fuse_score = 0;      // F == 2 fused step: 1 = k_gather_score (one pass for score + gather), -1 = that unless a
                              //   slot is reserved, 0 = k_score + k_gather (default: faster since the gather went hierarchical)
-    int adam_reserve = 0;    // 1: k_adam_rows also leaves the reserved slot free
+    int adam_reserve = 1;    // 1: k_adam_rows also leaves the reserved slot free (round 2, pipelined kernel: 104.2 vs
+                             //   108.4 us per ml20m step next to the plan; 0 was better for the register-staged kernel)
     int adam_pipe = 1;       // Adam on the touched rows: cp.async-pipelined kernel (k_adam_rows_pipe) when the row
                              //   layout allows (d % 4 == 0, d <= 128); 0 = the register-staged k_adam_rows
     int gather_dyn = 1;      // backward gather: tiles after a group's first are handed out by an atomic counter
                              //   (0 = static stride); results do not depend on it
+    int stage_wide = 0;      // k_stage: half the lanes per row, two vectors per lane
+    int score_wide = 0;      // k_score: half the lanes per row, two vectors per lane (another summation order of the
+                             //   dot product: last-bit differences, so one setting per process)
     int gather_wide = 1;     // backward gather: half the lanes per row, two vectors per lane (results identical)
     int gather_keep = 32;    // backward gather: rows of up to this many occurrences are never cut by a tile boundary
     int gather_fence = 1;    // finisher of cut rows: 1 = fence.acq_rel.gpu, 0 = __threadfence() (fence.sc)

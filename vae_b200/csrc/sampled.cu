@@ -18,11 +18,6 @@
 // Host side: launch_* (internal) and the extern "C" entry points at the end of the file.
 #include "sampled_common.cuh"
 
-#ifndef VFMB_SCORE_HOIST
-#define VFMB_SCORE_HOIST 0          // k_score, F == 2: 1 = fetch the row pairs of all rounds before the dot products
-                                    // (measured: no gain -- 80 registers cost a resident block per SM)
-#endif
-
 namespace vfmb {
 
 // ------------------------------------------------------------------------------- k_stage
@@ -43,7 +38,8 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
     // this kernel is issue-bound on Philox and the DRAM pipe idles -- k_adam_rows finds them there
     // smp: variational sample this launch draws (S > 1: one launch per sample, outputs [S][u_stride]);
     // the KL and the KL weights do not depend on the sample and are formed by sample 0
-    constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
+    constexpr int GPW = kWarp / LPR, ROUNDS = LPR;      // 32 unique rows per warp and pass, GPW per round
+    constexpr int UR = (NV == 1) ? 4 : 2;               // rounds whose [mean | raw scale] loads are in flight
     const int U = meta[0];
     const int d = c.d;
     if (vs) vs += (size_t)smp * u_stride * d;
@@ -52,16 +48,19 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
     if (ebs) ebs += (size_t)smp * u_stride;
     const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
-    const unsigned gmask = group_mask<LPR>();
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     float facc = 0.f;                                   // sum_u c_u * KL_u over this thread's rows
+    int kc[NV]; bool act[NV];                           // column of this lane; lanes past d load column 0, store nothing
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { const int k = (gl + i * LPR) * VEC; act[i] = k < d; kc[i] = act[i] ? k : 0; }
 
-    for (int base = gwarp * CH; base < U; base += nwarps * CH) {
-        // ---- lane-parallel: one unique row per lane (first CH lanes)
+    for (int base = gwarp * kWarp; base < U; base += nwarps * kWarp) {
+        // ---- lane-parallel: one unique row per lane
         const int ul = base + lane;
-        const bool valid = lane < CH && ul < U;
-        int rowid_l = 0, seg0_l = 0, len_l = 0;
+        const bool valid = ul < U;
+        const int nvalid = min(kWarp, U - base);
+        int rowid_l = 0, seg0_l = 0, len_l = 0;          // (lanes past U gather row 0: harmless)
         float klb = 0.f, cqv = 0.f, w_l = 0.f;
         if (valid) {
             const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
@@ -88,68 +87,77 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         float klrow = 0.f;
         // ---- wide work: GPW rows per round, LPR lanes per row (rows were prefetched into L2 above)
 #pragma unroll 1
-        for (int it = 0; it < kRounds; ++it) {
-            const int sel = it * GPW + gidx;
-            const int rowid = bcast(rowid_l, sel);
-            const int u = base + sel;
-            // requesters of the row (mode B): its sorted occurrences in the owner's plan are request slots
-            int n_req = 0, seg0 = 0;
-            float w_u = 0.f;
-            if (put.pe.n) {
-                n_req = bcast(len_l, sel); seg0 = bcast(seg0_l, sel); w_u = bcast(w_l, sel);
-                if (u >= U || rowid >= put.n_real) n_req = 0;          // padding slots share a sentinel row
+        for (int it0 = 0; it0 < ROUNDS; it0 += UR) {
+            if (it0 * GPW >= nvalid) break;                  // warp-uniform
+            Vec<VEC> mu[UR][NV], rho[UR][NV];
+#pragma unroll
+            for (int q = 0; q < UR; ++q) {
+                const float* erow = entity + (size_t)bcast(rowid_l, (it0 + q) * GPW + gidx) * 2 * d;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) { mu[q][i] = ld_vec<VEC>(erow + kc[i]); rho[q][i] = ld_vec<VEC>(erow + d + kc[i]); }
             }
-            auto put_row = [&](int k, const Vec<VEC>& out) {
-                for (int i = 0; i < n_req; ++i) {
-                    const int sl = __ldg(put.occ + seg0 + i);
-                    const int q = sl / put.CAP, j = sl - q * put.CAP;
-                    float* dst = reinterpret_cast<float*>(put.pe.base[q]) + ((size_t)put.pe.rank * put.CAP + j) * put.SP;
-                    st_vec<VEC>(dst + k, out);
-                    if (k == 0) dst[d] = w_u;
+#pragma unroll
+            for (int q = 0; q < UR; ++q) {
+                const int it = it0 + q;
+                const int sel = it * GPW + gidx;
+                const int rowid = bcast(rowid_l, sel);
+                const int u = base + sel;
+                // requesters of the row (mode B): its sorted occurrences in the owner's plan are request slots
+                int n_req = 0, seg0 = 0;
+                float w_u = 0.f;
+                if (put.pe.n) {
+                    n_req = bcast(len_l, sel); seg0 = bcast(seg0_l, sel); w_u = bcast(w_l, sel);
+                    if (u >= U || rowid >= put.n_real) n_req = 0;          // padding slots share a sentinel row
                 }
-            };
-            float kl = 0.f;
-            if (u < U) {
-                const float* erow = entity + (size_t)rowid * 2 * d;
+                auto put_row = [&](int k, const Vec<VEC>& out) {
+                    for (int i = 0; i < n_req; ++i) {
+                        const int sl = __ldg(put.occ + seg0 + i);
+                        const int pq = sl / put.CAP, j = sl - pq * put.CAP;
+                        float* dst = reinterpret_cast<float*>(put.pe.base[pq]) + ((size_t)put.pe.rank * put.CAP + j) * put.SP;
+                        st_vec<VEC>(dst + k, out);
+                        if (k == 0) dst[d] = w_u;
+                    }
+                };
+                float kl = 0.f;
+                if (u < U) {
 #pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d) {
-                        const Vec<VEC> mu = ld_vec<VEC>(erow + k), rho = ld_vec<VEC>(erow + d + k);
-                        Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step, smp, U), out;
-                        if (!LEAN && !eps_entity) st_vec<VEC>(es + (size_t)u * d + k, e);
-                        if (LEAN) {
+                    for (int i = 0; i < NV; ++i) {
+                        const int k = kc[i];
+                        if (act[i]) {
+                            Vec<VEC> e = entity_eps<VEC>(eps_entity, c, u, rowid * c.row_stride + c.row_offset, k, step, smp, U), out;
+                            if (!LEAN && !eps_entity) st_vec<VEC>(es + (size_t)u * d + k, e);
+                            if (LEAN) {
 #pragma unroll
-                            for (int j = 0; j < VEC; ++j) out.v[j] = fmaf(e.v[j], link_fn<LINK>(rho.v[j]), mu.v[j]);
+                                for (int j = 0; j < VEC; ++j) out.v[j] = fmaf(e.v[j], link_fn<LINK>(rho[q][i].v[j]), mu[q][i].v[j]);
+                                if (vs) st_vec<VEC>(vs + (size_t)u * d + k, out);
+                                put_row(k, out);
+                                continue;
+                            }
+                            // sum_k KL(N(mu,sig)||N(0,1)) = 0.5 (sum sig^2 + mu^2 - 1) - 0.5 log prod sig^2:
+                            // one logarithm per lane instead of one per element
+                            float quad = 0.f, prodv = 1.f;
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) {
+                                const float sig = link_fn<LINK>(rho[q][i].v[j]);
+                                out.v[j] = fmaf(e.v[j], sig, mu[q][i].v[j]);
+                                const float vr = sig * sig;
+                                quad += vr + mu[q][i].v[j] * mu[q][i].v[j] - 1.f;
+                                prodv *= vr;
+                            }
+                            float lg = __logf(prodv);
+                            if (!(prodv > 1e-30f && prodv < 1e30f)) {       // tiny / huge scales: no product trick
+                                lg = 0.f;
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho[q][i].v[j]); lg += logf(sg * sg); }
+                            }
+                            kl += 0.5f * (quad - lg);
                             if (vs) st_vec<VEC>(vs + (size_t)u * d + k, out);
                             put_row(k, out);
-                            continue;
                         }
-                        // sum_k KL(N(mu,sig)||N(0,1)) = 0.5 (sum sig^2 + mu^2 - 1) - 0.5 log prod sig^2:
-                        // one logarithm per lane instead of one per element
-                        float quad = 0.f, prodv = 1.f;
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            const float sig = link_fn<LINK>(rho.v[j]);
-                            out.v[j] = fmaf(e.v[j], sig, mu.v[j]);
-                            const float vr = sig * sig;
-                            quad += vr + mu.v[j] * mu.v[j] - 1.f;
-                            prodv *= vr;
-                        }
-                        float lg = __logf(prodv);
-                        if (!(prodv > 1e-30f && prodv < 1e30f)) {       // tiny / huge scales: no product trick
-                            lg = 0.f;
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) { const float sg = link_fn<LINK>(rho.v[j]); lg += logf(sg * sg); }
-                        }
-                        kl += 0.5f * (quad - lg);
-                        if (vs) st_vec<VEC>(vs + (size_t)u * d + k, out);
-                        put_row(k, out);
                     }
                 }
-                if (!LEAN) kl = group_sum<LPR>(kl, gmask);
+                if (!LEAN) { kl = group_sum<LPR>(kl, 0xffffffffu); hand_back<LPR>(klrow, kl, it, lane); }
             }
-            if (!LEAN) hand_back<LPR>(klrow, kl, it, lane);
         }
         if (valid) facc = fmaf(cqv, klrow + klb, facc);
     }
@@ -167,6 +175,13 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
 }
 
 // ------------------------------------------------------------------------------- k_score
+// Forward, phase B: per sample the logit (global bias + bias sum + FM interaction of the sampled rows),
+// the likelihood terms, the residual r_n = dloss/dpred_n (also scattered into sorted-occurrence order
+// for the backward) and, F > 2, the field sums S_n the backward gathers.
+// A warp takes 32 consecutive samples per pass: the per-sample scalars are lane-parallel (one sample
+// per lane, coalesced), the d-wide interaction runs GPW samples per round with the rows of UR rounds
+// in flight.  The kernel is bound by L2 round trips per warp, so the passes are short (one per warp on
+// the benchmark shapes) and every load of a round is issued before the first is used.
 template <int VEC, int LPR, int NV, int LINK, int LIK>
 __global__ void __launch_bounds__(256)
 k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__ inverse,
@@ -178,11 +193,13 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         int defer_kl, int vp, TailPut tp) {
     // vp: pitch of the sampled rows in floats (d; mode B: the received slots, d + 4, bias sample at [d] and
     // `inverse` holding slot indices; ws == NULL then).  tp: mode B, see TailPut.
-    constexpr int GPW = kWarp / LPR, CH = kRounds * GPW;
+    constexpr int GPW = kWarp / LPR, ROUNDS = LPR;      // 32 samples per warp and pass, GPW per round
+    constexpr int UR = (NV == 1) ? 4 : 2;               // F == 2: rounds in flight (two rows each)
+    constexpr int FU = (NV == 1) ? 4 : 2;               // F > 2: rows of one sample in flight
+    __shared__ int s_idx[8][kWarp * kMaxFields];        // F > 2: row ranks of the warp's 32 samples
     const int d = c.d, F = c.F, B = c.B;
     const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
     const int lane = threadIdx.x & 31, gl = lane % LPR, gidx = lane / LPR;
-    const unsigned gmask = group_mask<LPR>();
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     const float mu0 = scalars[VFMB_S_GB_MEAN];
@@ -192,106 +209,104 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
     const float half_log_alpha = 0.5f * logf(alpha);
     const float scale = c.n_train / ((float)c.S * (float)B);
     double acc[3] = {0.0, 0.0, 0.0};     // nll, resid, squared error
+    int kc[NV]; bool act[NV];            // column of this lane; lanes past d load column 0 and contribute nothing
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { const int k = (gl + i * LPR) * VEC; act[i] = k < d; kc[i] = act[i] ? k : 0; }
 
-    for (int base = gwarp * CH; base < B; base += nwarps * CH) {
+    for (int base = gwarp * kWarp; base < B; base += nwarps * kWarp) {
         // ---- lane-parallel: one sample per lane (ranks, bias sum, target)
         const int nl = base + lane;
-        const bool valid = lane < CH && nl < B;
-        int2 rr = make_int2(0, 0);
+        const bool valid = nl < B;
+        const int nvalid = min(kWarp, B - base);
+        int2 rr = make_int2(0, 0);                                    // (invalid samples gather row 0: harmless)
         float bsum = 0.f, yn = 0.f;
-        if (valid) {
-            if (F == 2) {
+        int* si = s_idx[threadIdx.x >> 5];
+        if (F == 2) {
+            if (valid) {
                 rr = __ldg(reinterpret_cast<const int2*>(inverse) + nl);
                 bsum = ws ? __ldg(ws + rr.x) + __ldg(ws + rr.y)
                           : __ldg(vs + (size_t)rr.x * vp + d) + __ldg(vs + (size_t)rr.y * vp + d);
-            } else {
+            }
+        } else {
+            for (int q = lane; q < nvalid * F; q += kWarp) si[q] = __ldg(inverse + (size_t)base * F + q);   // coalesced
+            __syncwarp();
+            if (valid)
                 for (int f = 0; f < F; ++f) {
-                    const int r = __ldg(inverse + (size_t)nl * F + f);
+                    const int r = si[lane * F + f];
                     bsum += ws ? __ldg(ws + r) : __ldg(vs + (size_t)r * vp + d);
                 }
-            }
-            if (y) yn = __ldg(y + nl);
         }
+        if (valid && y) yn = __ldg(y + nl);
         float inter_l = 0.f;
         // ---- wide work: interaction of GPW samples per round
         if (F == 2) {
-            // the row pairs of all rounds are fetched up front (2 * kRounds * NV independent 128-bit loads
-            // per lane): the kernel is bound by L2 latency, not by registers
-            constexpr int HR = VFMB_SCORE_HOIST ? kRounds : 1;
-            Vec<VEC> ra[HR][NV], rb[HR][NV];
-#if VFMB_SCORE_HOIST
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
-            for (int it = 0; it < kRounds; ++it) {
-                const int sel = it * GPW + gidx;
-                const int r0 = bcast(rr.x, sel), r1 = bcast(rr.y, sel);
+            for (int it0 = 0; it0 < ROUNDS; it0 += UR) {
+                if (it0 * GPW >= nvalid) break;                       // warp-uniform
+                Vec<VEC> ra[UR][NV], rb[UR][NV];
 #pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    int k = (gl + i * LPR) * VEC;
-                    if (k < d && base + sel < B) {
-                        ra[it % HR][i] = ld_vec_nc<VEC>(vs + (size_t)r0 * vp + k);
-                        rb[it % HR][i] = ld_vec_nc<VEC>(vs + (size_t)r1 * vp + k);
-                    }
+                for (int u = 0; u < UR; ++u) {
+                    const int sel = (it0 + u) * GPW + gidx;
+                    const float* p0 = vs + (size_t)bcast(rr.x, sel) * vp;
+                    const float* p1 = vs + (size_t)bcast(rr.y, sel) * vp;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) { ra[u][i] = ld_vec_nc<VEC>(p0 + kc[i]); rb[u][i] = ld_vec_nc<VEC>(p1 + kc[i]); }
                 }
-#if VFMB_SCORE_HOIST
-            }
 #pragma unroll
-            for (int it = 0; it < kRounds; ++it) {
-                const int sel = it * GPW + gidx;
-#endif
-                float part = 0.f;
-                if (base + sel < B) {
+                for (int u = 0; u < UR; ++u) {
+                    float part = 0.f;
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        int k = (gl + i * LPR) * VEC;
-                        if (k < d)
+                    for (int i = 0; i < NV; ++i)
+                        if (act[i])
 #pragma unroll
-                            for (int j = 0; j < VEC; ++j) part = fmaf(ra[it % HR][i].v[j], rb[it % HR][i].v[j], part);
-                    }
+                            for (int j = 0; j < VEC; ++j) part = fmaf(ra[u][i].v[j], rb[u][i].v[j], part);
+                    part = group_sum<LPR>(part, 0xffffffffu);
+                    hand_back<LPR>(inter_l, part, it0 + u, lane);
                 }
-                part = group_sum<LPR>(part, gmask);
-                hand_back<LPR>(inter_l, part, it, lane);
             }
         } else {
 #pragma unroll 1
-            for (int it = 0; it < kRounds; ++it) {
+            for (int it = 0; it < ROUNDS; ++it) {
+                if (it * GPW >= nvalid) break;                        // warp-uniform
                 const int sel = it * GPW + gidx;
                 const int n = base + sel;
-                float part = 0.f;
-                if (n < B) {
-                    Vec<VEC> ssum[NV], sq[NV];
+                const int* sidx = si + min(sel, nvalid - 1) * F;
+                Vec<VEC> ssum[NV], sq[NV];
 #pragma unroll
-                    for (int i = 0; i < NV; ++i)
+                for (int i = 0; i < NV; ++i)
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) { ssum[i].v[j] = 0.f; sq[i].v[j] = 0.f; }
-#pragma unroll 4
-                    for (int f = 0; f < F; ++f) {
-                        const int r = __ldg(inverse + (size_t)n * F + f);
+                    for (int j = 0; j < VEC; ++j) { ssum[i].v[j] = 0.f; sq[i].v[j] = 0.f; }
+                for (int f0 = 0; f0 < F; f0 += FU) {
+                    Vec<VEC> a[FU][NV];
 #pragma unroll
-                        for (int i = 0; i < NV; ++i) {
-                            int k = (gl + i * LPR) * VEC;
-                            if (k < d) {
-                                Vec<VEC> a = ld_vec_nc<VEC>(vs + (size_t)r * vp + k);
+                    for (int e = 0; e < FU; ++e) {
+                        const float* row = vs + (size_t)sidx[min(f0 + e, F - 1)] * vp;
 #pragma unroll
-                                for (int j = 0; j < VEC; ++j) { ssum[i].v[j] += a.v[j]; sq[i].v[j] = fmaf(a.v[j], a.v[j], sq[i].v[j]); }
-                            }
-                        }
+                        for (int i = 0; i < NV; ++i) a[e][i] = ld_vec_nc<VEC>(row + kc[i]);
                     }
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        int k = (gl + i * LPR) * VEC;
-                        if (k < d) {
+                    for (int e = 0; e < FU; ++e)
+                        if (f0 + e < F)
 #pragma unroll
-                            for (int j = 0; j < VEC; ++j) part += 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]);
-                            if (msg) st_vec<VEC>(msg + (size_t)n * d + k, ssum[i]);   // S_n = sum_f v_f (unscaled)
-                        }
-                    }
+                            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) {
+                                    ssum[i].v[j] += a[e][i].v[j];
+                                    sq[i].v[j] = fmaf(a[e][i].v[j], a[e][i].v[j], sq[i].v[j]);
+                                }
                 }
-                part = group_sum<LPR>(part, gmask);
+                float part = 0.f;
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+                    if (act[i]) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) part += 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]);
+                        if (msg && n < B) st_vec<VEC>(msg + (size_t)n * d + kc[i], ssum[i]);   // S_n = sum_f v_f (unscaled)
+                    }
+                part = group_sum<LPR>(part, 0xffffffffu);
                 hand_back<LPR>(inter_l, part, it, lane);
             }
+            __syncwarp();                                             // s_idx is rewritten by the next pass
         }
         // ---- lane-parallel: likelihood, residual, outputs (coalesced)
         if (valid) {
@@ -529,8 +544,15 @@ extern "C" int vfmb_debug_tile_times(int32_t* host, int n) {
 }
 #endif
 
+#ifndef VFMB_GATHER_MAXREG
+#define VFMB_GATHER_MAXREG 0
+#endif
 template <int VEC, int LPR, int NV, int UNIT>
+#if VFMB_GATHER_MAXREG
+__global__ void __maxnreg__(VFMB_GATHER_MAXREG)
+#else
 __global__ void __launch_bounds__(256, 2)
+#endif
 k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t* __restrict__ pos_rank,
          const int32_t* __restrict__ urec, const float* __restrict__ vs, const float* __restrict__ msg,
          const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
@@ -931,19 +953,28 @@ static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vf
         return set_error(VFMB_EINVAL, "vfmb_sampled_stage: scratch required");
     RowPut put{};
     if (put_) put = *put_;
-    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch; const auto& cap = P.cap;
+    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     // fused training step only: the row update follows within the same step
     const float* pf_m = (lean && (tuning().prefetch_mv & 1)) ? tab->entity_m : nullptr;
     const float* pf_v = (lean && (tuning().prefetch_mv & 2)) ? tab->entity_v : nullptr;
 #define LAUNCH_STAGE(LINK, LEAN)                                                                       \
-    k_stage<VEC, LPR, NV, LINK, LEAN><<<grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, ch), 256, 0, counted(stream)>>>( \
+    k_stage<VEC, LPR, NV, LINK, LEAN><<<grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, 32), 256, 0, counted(stream)>>>( \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
         io->eps_bias, io->eps_entity, tab->noise_step, io->vs, io->ws, io->es,                         \
         io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap, pf_m, pf_v, put)
-    VFMB_LAYOUT_SWITCH(L, {
-        if (cfg->link == VFMB_LINK_ABS) { if (lean) LAUNCH_STAGE(0, 1); else LAUNCH_STAGE(0, 0); }
-        else                            { if (lean) LAUNCH_STAGE(1, 1); else LAUNCH_STAGE(1, 0); }
-    });
+#define LAUNCH_STAGE_ALL()                                                                             \
+    do {                                                                                               \
+        if (cfg->link == VFMB_LINK_ABS) { if (lean) LAUNCH_STAGE(0, 1); else LAUNCH_STAGE(0, 0); }     \
+        else                            { if (lean) LAUNCH_STAGE(1, 1); else LAUNCH_STAGE(1, 0); }     \
+    } while (0)
+    // stage_wide: half the lanes per row, two vectors per lane (the draws are keyed by row and column, so
+    // the sampled rows are the same bits; only the KL sum of the non-lean forward changes its last bit)
+    const bool wide = tuning().stage_wide && L.vec == 4 && L.nv == 1 && L.lpr >= 8;
+    if (wide && L.lpr == 8) { constexpr int VEC = 4, LPR = 4, NV = 2; LAUNCH_STAGE_ALL(); }
+    else if (wide && L.lpr == 16) { constexpr int VEC = 4, LPR = 8, NV = 2; LAUNCH_STAGE_ALL(); }
+    else if (wide && L.lpr == 32) { constexpr int VEC = 4, LPR = 16, NV = 2; LAUNCH_STAGE_ALL(); }
+    else VFMB_LAYOUT_SWITCH(L, { LAUNCH_STAGE_ALL(); });
+#undef LAUNCH_STAGE_ALL
 #undef LAUNCH_STAGE
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -960,7 +991,7 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     if (!tab || !plan || !io) return set_error(VFMB_EINVAL, "vfmb_sampled_score: null argument");
     if (!tab->noise_step) return set_error(VFMB_EINVAL, "vfmb_sampled_score: tables.noise_step required");
     if (cfg->F > 2 && io->y && !io->msg) return set_error(VFMB_EINVAL, "vfmb_sampled_score: msg scratch required for F>2");
-    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const int ch = P.ch;
+    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream;
     const float* rows = sb ? sb->rows : io->vs;
     const float* wsp = sb ? nullptr : io->ws;
     const int32_t* inv = sb ? sb->inv_slot : plan->inverse;
@@ -968,17 +999,26 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     TailPut tp{};
     if (sb) tp = sb->tp;
 #define LAUNCH_SCORE(LINK, LIK)                                                                        \
-    k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, counted(stream)>>>( \
+    k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, 32), 256, 0, counted(stream)>>>( \
         dc, tab->scalars, inv, plan->pos_of, rows, wsp, io->y, io->eps_global,                         \
         tab->noise_step, plan->meta, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials, \
         io->counters + 1, io->stats, defer_kl, vp, tp)
-    VFMB_LAYOUT_SWITCH(L, {
-        if (cfg->link == VFMB_LINK_ABS) {
-            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SCORE(0, VFMB_GAUSSIAN); else LAUNCH_SCORE(0, VFMB_BERNOULLI);
-        } else {
-            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SCORE(1, VFMB_GAUSSIAN); else LAUNCH_SCORE(1, VFMB_BERNOULLI);
-        }
-    });
+#define LAUNCH_SCORE_ALL()                                                                              \
+    do {                                                                                                \
+        if (cfg->link == VFMB_LINK_ABS) {                                                               \
+            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SCORE(0, VFMB_GAUSSIAN); else LAUNCH_SCORE(0, VFMB_BERNOULLI); \
+        } else {                                                                                        \
+            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_SCORE(1, VFMB_GAUSSIAN); else LAUNCH_SCORE(1, VFMB_BERNOULLI); \
+        }                                                                                               \
+    } while (0)
+    // score_wide: half the lanes per row, two vectors per lane -- twice the samples per round.  The dot
+    // product is then summed in another (fixed) order: a different last bit, so it is one knob for the process.
+    const bool wide = tuning().score_wide && L.vec == 4 && L.nv == 1 && L.lpr >= 8;
+    if (wide && L.lpr == 8) { constexpr int VEC = 4, LPR = 4, NV = 2; LAUNCH_SCORE_ALL(); }
+    else if (wide && L.lpr == 16) { constexpr int VEC = 4, LPR = 8, NV = 2; LAUNCH_SCORE_ALL(); }
+    else if (wide && L.lpr == 32) { constexpr int VEC = 4, LPR = 16, NV = 2; LAUNCH_SCORE_ALL(); }
+    else VFMB_LAYOUT_SWITCH(L, { LAUNCH_SCORE_ALL(); });
+#undef LAUNCH_SCORE_ALL
 #undef LAUNCH_SCORE
     CUDA_TRY(cudaGetLastError());
     return 0;

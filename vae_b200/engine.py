@@ -170,7 +170,10 @@ class GraphedLoop:
         res = loop.step()                         # last staged batch
     """
 
-    def __init__(self, model, B: int, step_fn, depth: int = 2, reserve: int = 1, side_priority: int = -1):
+    def __init__(self, model, B: int, step_fn, depth: int = 2, reserve: int = 1, side_priority: int = -1,
+                 plan_in_graph: bool = True):
+        # plan_in_graph=False (measurement only, scripts/graph_overheads.py): the graphs hold the step alone and
+        # replay whatever plans the staging slots were left with
         assert depth in (2, 3)
         self.model, self.B, self.device, self.depth = model, int(B), model.device, depth
         F = model.F if hasattr(model, "F") else model.G
@@ -211,11 +214,13 @@ class GraphedLoop:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     cur = torch.cuda.current_stream(self.device)
-                    self.side.wait_stream(cur)                   # fork
-                    with torch.cuda.stream(self.side):
-                        self.plans[nxt].build(self.cfg, self.xs[nxt], model.train_counts)
+                    if plan_in_graph:
+                        self.side.wait_stream(cur)               # fork
+                        with torch.cuda.stream(self.side):
+                            self.plans[nxt].build(self.cfg, self.xs[nxt], model.train_counts)
                     step_fn(self.plans[s], self.ys[s], self.outs[s])   # main branch
-                    cur.wait_stream(self.side)                   # join
+                    if plan_in_graph:
+                        cur.wait_stream(self.side)               # join
                 self.graphs.append(g)
         finally:
             L.lib().vfmb_set_grid_reserve(0)
