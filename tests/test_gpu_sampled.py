@@ -466,34 +466,35 @@ def test_pipelined_and_register_staged_row_updates_agree_bitwise(name):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("fuse", [0, 1])
-def test_gather_launch_knobs_do_not_change_a_bit(fuse):
-    """Tile hand-out (static stride / atomic counter) and the fence flavour of the cut-row finisher are
-    scheduling only: parameters, moments and losses are identical.  The batch has Zipf head rows of
-    hundreds of occurrences (cut rows, two-level finisher) and thousands of short rows (kept whole)."""
+@pytest.mark.parametrize("d", [32, 64, 20])
+def test_gather_launch_knobs_do_not_change_a_bit(d):
+    """Tile hand-out (static stride / counter), the lane mapping of the gather and of k_stage, and the fence
+    flavour of the cut-row finisher are scheduling only: parameters, moments and losses are identical.
+    The batch has Zipf head rows of thousands of occurrences (cut by group and block tiles, global finisher)
+    and thousands of short rows."""
     from vae_b200 import _lib as L
     from vae_b200.vfm_torch import CF
-    fs, d, B = [3000, 400], 32, 16384
+    fs, B = [3000, 400], 16384
     rng = np.random.default_rng(11)
     p1 = 1.0 / np.arange(1, fs[1] + 1); p1 /= p1.sum()
     x = np.stack([rng.integers(0, fs[0], B), fs[0] + rng.choice(fs[1], B, p=p1)], 1).astype(np.int64)
     y = rng.normal(size=B).astype(np.float32)
     xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
     counts = torch.from_numpy(np.bincount(x.reshape(-1), minlength=sum(fs)).astype(np.float32))
+    knobs = ("gather_dyn", "gather_fence", "gather_wide", "stage_wide", "l2_keep")
+    defaults = (1, 1, 1, 0, 1)
     res = []
-    for dyn, fence in ((1, 1), (0, 0), (1, 0)):
-        L.check(L.lib().vfmb_set_tuning(b"gather_dyn", dyn))
-        L.check(L.lib().vfmb_set_tuning(b"gather_fence", fence))
-        L.check(L.lib().vfmb_set_tuning(b"fuse_score", fuse))
+    for setting in (defaults, (0, 0, 0, 1, 0), (1, 0, 0, 0, 1)):
+        for k, v in zip(knobs, setting):
+            L.check(L.lib().vfmb_set_tuning(k.encode(), v))
         try:
             torch.manual_seed(2)
             m = CF(d, output="reg", n_users=fs[0], n_items=fs[1], train_counts=counts, n_train=B, max_batch=B, lr=0.01)
             losses = [m.fused_step(xd, yd)["loss"].item() for _ in range(4)]
             res.append((losses, m.entity_params.weight.clone(), m.entity_m.clone(), m.bias_params.weight.clone()))
         finally:
-            L.lib().vfmb_set_tuning(b"gather_dyn", 1)
-            L.lib().vfmb_set_tuning(b"gather_fence", 1)
-            L.lib().vfmb_set_tuning(b"fuse_score", 0)
+            for k, v in zip(knobs, defaults):
+                L.lib().vfmb_set_tuning(k.encode(), v)
     for r in res[1:]:
         assert r[0] == res[0][0]
         for a, b in zip(res[0][1:], r[1:]):

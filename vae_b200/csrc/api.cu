@@ -36,9 +36,11 @@ extern "C" int vfmb_set_tuning(const char* key, int value) {
     if (!key) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: null key");
     vfmb::Tuning& t = vfmb::g_tuning;
     if (!strcmp(key, "grid_reserve")) return vfmb_set_grid_reserve(value);
-    if (!strcmp(key, "fuse_score")) { if (value < -1 || value > 1) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: fuse_score -1..1"); t.fuse_score = value; return 0; }
+    if (!strcmp(key, "fuse_score")) return 0;               // (the fused score + gather kernel is gone; accepted, ignored)
     if (!strcmp(key, "adam_reserve")) { t.adam_reserve = value != 0; return 0; }
     if (!strcmp(key, "adam_pipe")) { t.adam_pipe = value != 0; return 0; }
+    if (!strcmp(key, "l2_keep")) { if (value < 0 || value > 7) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: l2_keep 0..7"); t.l2_keep = value; return 0; }
+    if (!strcmp(key, "pdl")) { t.pdl = value != 0; return 0; }
     if (!strcmp(key, "stage_wide")) { t.stage_wide = value != 0; return 0; }
     if (!strcmp(key, "score_wide")) { t.score_wide = value != 0; return 0; }
     if (!strcmp(key, "gather_wide")) { t.gather_wide = value != 0; return 0; }

@@ -88,6 +88,13 @@ __device__ __forceinline__ void st_vec(float* p, const Vec<VEC>& r) {
     }
 }
 
+// Kernels launched with launch_chained() (internal.h): wait for the predecessor grid to complete (its writes are
+// visible afterwards), then let the successor be scheduled behind this grid.  No-ops for a plain launch.
+__device__ __forceinline__ void chain_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+}
+
 // mask of the LPR-lane group the calling lane belongs to.  Groups of one warp run
 // independent grid-stride loops (different trip counts), so every shuffle inside such a
 // loop must name only its own group -- a full-warp mask would wait for lanes that left.
@@ -126,6 +133,16 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 // L2 prefetch of the 128-byte line holding p: no register is tied up while it is in flight
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+// L2 residency hints (tuning l2_keep): k_stage pulls the rows k_adam_rows will read ~50 us later into L2 with
+// evict_last priority so that the scratch traffic in between does not displace them; the row update reads
+// them with an evict_first policy, which hands the lines back.
+__device__ __forceinline__ void prefetch_l2_keep(const void* p) {
+    asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(p));
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
 }
 
 // ---------------------------------------------------------------- link functions

@@ -23,8 +23,6 @@ int set_error(int code, const char* fmt, ...);
 // host, never by device code.  Defaults are the measured best for the BASELINE shapes.
 struct Tuning {
     int grid_reserve = 0;    // block slots per SM the persistent step kernels leave free
-    int fuse_score = 0;      // F == 2 fused step: 1 = k_gather_score (one pass for score + gather), -1 = that unless a
-                             //   slot is reserved, 0 = k_score + k_gather (default: faster since the gather went hierarchical)
     int adam_reserve = 1;    // 1: k_adam_rows also leaves the reserved slot free (round 2, pipelined kernel: 104.2 vs
                              //   108.4 us per ml20m step next to the plan; 0 was better for the register-staged kernel)
     int adam_pipe = 1;       // Adam on the touched rows: cp.async-pipelined kernel (k_adam_rows_pipe) when the row
@@ -37,6 +35,14 @@ struct Tuning {
     int gather_wide = 1;     // backward gather: half the lanes per row, two vectors per lane (results identical)
     int gather_keep = 32;    // backward gather: rows of up to this many occurrences are never cut by a tile boundary
     int gather_fence = 1;    // finisher of cut rows: 1 = fence.acq_rel.gpu, 0 = __threadfence() (fence.sc)
+    int pdl = 0;             // programmatic dependent launch along the step's and the plan's kernel chains: the next
+                             //   kernel is scheduled behind its predecessor and waits (griddepcontrol.wait) for it.
+                             //   Measured: 115.5 vs 104.6 us per ml20m step -- the grids are sized to the resident
+                             //   capacity, so the early blocks only take slots; off by default
+    int l2_keep = 1;         // fused step: k_stage parks the rows of entity (bit 0) / m (bit 1) / v (bit 2) in L2 with
+                             //   evict_last priority for the row update, which reads them evict_first.  Measured per ml20m
+                             //   step: 0: 104.9 us (update 49.3), 1: 102.7 (45.6), 3: 107.9 (42.8), 7: 112.2 (41.8) -- the
+                             //   moments do not fit next to the scratch; having k_score prefetch them instead lost too
     int prefetch_mv = 0;     // fused step: earlier phases pull the Adam moments of the touched rows into L2
                              //   (bit 0: k_stage fetches m, bit 1: k_stage fetches v, bit 2: k_gather fetches m,
                              //    bit 3: k_gather fetches v)
@@ -47,6 +53,24 @@ static inline int grid_reserve() { return tuning().grid_reserve; }
 // number of own kernels enqueued (or captured into a CUDA graph) by this process so far
 extern unsigned long long g_launch_count;
 static inline cudaStream_t counted(cudaStream_t s) { ++g_launch_count; return s; }
+// Launch of a kernel in a dependency chain.  With tuning().pdl the launch carries the programmatic-serialization
+// attribute: the grid may be scheduled once every block of its predecessor in the stream has passed its own
+// chain_wait() (or exited); it must therefore call chain_wait() (device side, common.cuh) before touching anything
+// an earlier kernel wrote.  Captured into a CUDA graph this becomes a programmatic edge.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chained(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream,
+                                         Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = counted(stream);
+    cudaLaunchAttribute at[1];
+    if (tuning().pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 // optional events around the dominant kernel (see vfmb_profile_events)
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
 

@@ -39,6 +39,7 @@ k_sort_hist(const int64_t* __restrict__ x, const int32_t* __restrict__ kin,
             const float* __restrict__ train_counts, int N, int F, int R,
             int tile, int n_tiles, int shift, int bins, int32_t* __restrict__ hist, int32_t* __restrict__ gtot,
             int32_t* __restrict__ meta, double* __restrict__ partials, float* __restrict__ z) {
+    chain_wait();                                           // launched with launch_chained()
     __shared__ int s_hist[kMaxBins];
     __shared__ double s_part[kMaxFields][kSortWarps];
     __shared__ bool s_last;
@@ -101,6 +102,7 @@ k_sort_hist(const int64_t* __restrict__ x, const int32_t* __restrict__ kin,
 // ---- S2: hist[bin][tile] -> global offset of the first key of (bin, tile) ----------------------
 __global__ void __launch_bounds__(128)
 k_sort_scan(int32_t* __restrict__ hist, const int32_t* __restrict__ gtot, int n_tiles) {
+    chain_wait();                                           // launched with launch_chained()
     __shared__ int s_w[4];
     __shared__ int s_carry;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(kSortThreads)
 k_sort_scatter(const int64_t* __restrict__ x, int R, const int32_t* __restrict__ kin,
                const int32_t* __restrict__ vin, int32_t* __restrict__ kout, int32_t* __restrict__ vout,
                int N, int tile_shift, int n_tiles, int shift, int bins, const int32_t* __restrict__ base) {
+    chain_wait();                                           // launched with launch_chained()
     __shared__ int s_base[kMaxBins];
     __shared__ int s_cnt[kSortWarps][kMaxBins];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = blockIdx.x;
@@ -192,6 +195,7 @@ k_sort_scatter(const int64_t* __restrict__ x, int R, const int32_t* __restrict__
 // ---- P2: number of segment heads per tile of the sorted keys -----------------------------------
 __global__ void __launch_bounds__(kSortThreads)
 k_plan_heads(const int32_t* __restrict__ keys_s, int N, int tile_shift, int32_t* __restrict__ tile_heads) {
+    chain_wait();                                           // launched with launch_chained()
     __shared__ int s_w[kSortWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = blockIdx.x;
     const int lo = t << tile_shift, hi = min(N, lo + (1 << tile_shift));
@@ -214,6 +218,7 @@ k_plan_scatter(const int32_t* __restrict__ keys_s, const int32_t* __restrict__ v
                const int32_t* __restrict__ tile_heads, int N, int tile_shift, int32_t* __restrict__ uniq,
                int32_t* __restrict__ seg_off, int32_t* __restrict__ inverse, int32_t* __restrict__ occ,
                int32_t* __restrict__ pos_of, int32_t* __restrict__ pos_rank, int32_t* __restrict__ meta) {
+    chain_wait();                                           // launched with launch_chained()
     __shared__ int s_w[kSortWarps];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = blockIdx.x;
@@ -285,6 +290,7 @@ k_plan_finish(const int32_t* __restrict__ uniq, const int32_t* __restrict__ seg_
               const int32_t* __restrict__ occ, const int32_t* __restrict__ inverse, int N, int F,
               ClassBounds cb, int32_t* __restrict__ partner, int32_t* __restrict__ urec,
               int32_t* __restrict__ class_off, int32_t* __restrict__ meta, int32_t* __restrict__ hot, int hot_cap) {
+    chain_wait();                                           // launched with launch_chained()
     const int U = meta[0];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int i = tid; i < N; i += nth) {
@@ -405,37 +411,35 @@ extern "C" int vfmb_plan_build(const vfmb_config* cfg, const int64_t* x, const f
     int32_t* kout = w.kA; int32_t* vout = w.vA;
     for (int p = 0; p < g.npass; ++p) {
         if (p == 0)
-            k_sort_hist<true><<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(x, nullptr, train_counts, N, cfg->F, cfg->R,
-                1 << g.tile_shift, g.n_tiles, 0, g.bins[0], w.hist, gtot[0], plan->meta, w.partials, plan->z);
+            CUDA_TRY(launch_chained(k_sort_hist<true>, g.n_tiles, kSortThreads, 0, stream, x, nullptr, train_counts, N, cfg->F, cfg->R,
+                1 << g.tile_shift, g.n_tiles, 0, g.bins[0], w.hist, gtot[0], plan->meta, w.partials, plan->z));
         else
-            k_sort_hist<false><<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(nullptr, kin, nullptr, N, cfg->F, cfg->R,
-                1 << g.tile_shift, g.n_tiles, g.shift[p], g.bins[p], w.hist, gtot[p], plan->meta, nullptr, nullptr);
-        k_sort_scan<<<g.bins[p], 128, 0, counted(stream)>>>(w.hist, gtot[p], g.n_tiles);
+            CUDA_TRY(launch_chained(k_sort_hist<false>, g.n_tiles, kSortThreads, 0, stream, nullptr, kin, nullptr, N, cfg->F, cfg->R,
+                1 << g.tile_shift, g.n_tiles, g.shift[p], g.bins[p], w.hist, gtot[p], plan->meta, nullptr, nullptr));
+        CUDA_TRY(launch_chained(k_sort_scan, g.bins[p], 128, 0, stream, w.hist, gtot[p], g.n_tiles));
         if (p == 0)
-            k_sort_scatter<true><<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
-                                                                         g.n_tiles, g.shift[p], g.bins[p], w.hist);
+            CUDA_TRY(launch_chained(k_sort_scatter<true>, g.n_tiles, kSortThreads, 0, stream, x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
+                                                                         g.n_tiles, g.shift[p], g.bins[p], w.hist));
         else
-            k_sort_scatter<false><<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
-                                                                          g.n_tiles, g.shift[p], g.bins[p], w.hist);
+            CUDA_TRY(launch_chained(k_sort_scatter<false>, g.n_tiles, kSortThreads, 0, stream, x, cfg->R, kin, vin, kout, vout, N, g.tile_shift,
+                                                                          g.n_tiles, g.shift[p], g.bins[p], w.hist));
         CUDA_TRY(cudaGetLastError());
         kin = kout; vin = vout;
         kout = (kout == w.kA) ? w.kB : w.kA;
         vout = (vout == w.vA) ? w.vB : w.vA;
     }
     const int32_t* keys_s = kin; const int32_t* vals_s = vin;
-    k_plan_heads<<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(keys_s, N, g.tile_shift, w.tile_heads);
-    k_plan_scatter<<<g.n_tiles, kSortThreads, 0, counted(stream)>>>(keys_s, vals_s, w.tile_heads, N, g.tile_shift, plan->uniq,
+    CUDA_TRY(launch_chained(k_plan_heads, g.n_tiles, kSortThreads, 0, stream, keys_s, N, g.tile_shift, w.tile_heads));
+    CUDA_TRY(launch_chained(k_plan_scatter, g.n_tiles, kSortThreads, 0, stream, keys_s, vals_s, w.tile_heads, N, g.tile_shift, plan->uniq,
                                                            plan->seg_off, plan->inverse, plan->occ, plan->pos_of,
-                                                           plan->pos_rank, plan->meta);
-    CUDA_TRY(cudaGetLastError());
+                                                           plan->pos_rank, plan->meta));
     int grid2 = (N + 255) / 256;
     if (grid2 > 4 * kPlanGrid) grid2 = 4 * kPlanGrid;
     ClassBounds cbd{};
     cbd.n = cfg->n_classes;
     for (int i = 0; i < kMaxFields; ++i) cbd.bound[i] = cfg->class_bound[i];
-    k_plan_finish<<<grid2, 256, 0, counted(stream)>>>(plan->uniq, plan->seg_off, plan->occ, plan->inverse, N, cfg->F,
+    CUDA_TRY(launch_chained(k_plan_finish, grid2, 256, 0, stream, plan->uniq, plan->seg_off, plan->occ, plan->inverse, N, cfg->F,
                                              cbd, plan->partner, plan->urec, plan->class_off, plan->meta, plan->hot,
-                                             (int)cut_list_capacity(cap.n_tiles));
-    CUDA_TRY(cudaGetLastError());
+                                             (int)cut_list_capacity(cap.n_tiles)));
     return 0;
 }

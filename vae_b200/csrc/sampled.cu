@@ -9,7 +9,6 @@
 //   k_gather     ordered segmented sum of residual * partner row over the sorted occurrence list,
 //                tiled by position; the group that stores the last partial of a row cut by tile
 //                boundaries adds the row's partials in tile order (finish_cut_row).
-//   k_gather_score  F = 2, step running alone: k_score + k_gather in one pass (3 launches).
 //   k_adam_rows  per unique row: chain rule to (mu, rho) + KL gradient + Adam; FLAVOR 2 also forms
 //                the KL and recomputes the Philox draws; the last block updates the scalar
 //                parameters (alpha, global bias) and the step counter.
@@ -32,7 +31,8 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         const int32_t* __restrict__ noise_step, float* __restrict__ vs, float* __restrict__ ws,
         float* __restrict__ es, float* __restrict__ ebs, float* __restrict__ cq,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
-        int smp, int u_stride, const float* __restrict__ pf_m, const float* __restrict__ pf_v, RowPut put) {
+        int smp, int u_stride, const float* __restrict__ pf_m, const float* __restrict__ pf_v, int keep, RowPut put) {
+    chain_wait();                                           // launched with launch_chained()
     // put (mode B, owner side): the sampled row also goes into the slot of every rank that asked for it
     // pf_m / pf_v (optional): Adam moment tables whose touched rows are pulled into L2 here, while
     // this kernel is issue-bound on Philox and the DRAM pipe idles -- k_adam_rows finds them there
@@ -65,9 +65,9 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         if (valid) {
             const int4 rec = __ldg(reinterpret_cast<const int4*>(urec) + ul);
             rowid_l = rec.x; len_l = rec.y; seg0_l = rec.z;
-            prefetch_row(entity + (size_t)rowid_l * 2 * d, 8 * d);
-            if (pf_m) prefetch_row(pf_m + (size_t)rowid_l * 2 * d, 8 * d);
-            if (pf_v) prefetch_row(pf_v + (size_t)rowid_l * 2 * d, 8 * d);
+            prefetch_row(entity + (size_t)rowid_l * 2 * d, 8 * d, keep & 1);     // keep: see prefetch_l2_keep
+            if (pf_m) prefetch_row(pf_m + (size_t)rowid_l * 2 * d, 8 * d, keep & 2);
+            if (pf_v) prefetch_row(pf_v + (size_t)rowid_l * 2 * d, 8 * d, keep & 4);
             const float2 ab = *reinterpret_cast<const float2*>(bias + (size_t)rowid_l * 2);
             const float tcnt = __ldg(train_counts + rowid_l);
             const int gid_l = rowid_l * c.row_stride + c.row_offset;     // global id (row-sharded tables)
@@ -191,6 +191,7 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         float* __restrict__ resid, float* __restrict__ rsorted, float* __restrict__ msg,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
         int defer_kl, int vp, TailPut tp) {
+    chain_wait();                                           // launched with launch_chained()
     // vp: pitch of the sampled rows in floats (d; mode B: the received slots, d + 4, bias sample at [d] and
     // `inverse` holding slot indices; ws == NULL then).  tp: mode B, see TailPut.
     constexpr int GPW = kWarp / LPR, ROUNDS = LPR;      // 32 samples per warp and pass, GPW per round
@@ -557,6 +558,7 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
          const int32_t* __restrict__ urec, const float* __restrict__ vs, const float* __restrict__ msg,
          const float* __restrict__ rsorted, float* gslot, float* __restrict__ grow, float* __restrict__ gws,
          int32_t* arrive, int vp, float* const* __restrict__ gptr, GatherKnobs kn) {
+    chain_wait();                                           // launched with launch_chained()
     // F > 2 (pairwise): the sums are over the per-sample field sums S_n; the row's own term (sum r_n) v_u is
     // removed by the row kernel, which holds v_u anyway (DevCfg.pairwise).
     // mode B: vp = pitch of the gathered rows (received slots: d + 4); gptr[u] = where the finished gradient
@@ -730,171 +732,6 @@ k_gather(int d, int F, int N, const int32_t* __restrict__ partner, const int32_t
     if (kn.dyn && threadIdx.x == 0 && atomicAdd(tctr + 1, 1) == (int)gridDim.x - 1) { tctr[0] = 0; tctr[1] = 0; }   // last block out
 }
 
-// ------------------------------------------------------------------------------- k_gather_score
-// F == 2 fused step: k_score and k_gather in one pass over the SORTED occurrence list.  An
-// occurrence (row u, sample n) needs the residual r_n = dloss/dpred_n and the partner row; the
-// partner row is being loaded anyway, so the group forms the score <v_u, v_partner> itself --
-// every sample is scored twice, once from each of its rows, with bit-identical results (products
-// and bias sums commute, the lane mapping and the shuffle tree are those of k_score).  The
-// occurrence of field 0 writes the sample's outputs and its likelihood terms.  Saves a launch, the
-// residual round trip through memory and one of the two passes over the sampled rows.
-template <int VEC, int LPR, int NV, int LINK, int LIK>
-__global__ void __launch_bounds__(256, 2)
-k_gather_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__ partner,
-               const int32_t* __restrict__ pos_rank, const int32_t* __restrict__ occ,
-               const int32_t* __restrict__ urec, int32_t* arrive,
-               const float* __restrict__ vs, const float* __restrict__ ws, const float* __restrict__ y,
-               const float* __restrict__ eps_global, int32_t* noise_step, const int32_t* __restrict__ meta,
-               float* __restrict__ pred, float* __restrict__ mean, float* __restrict__ resid,
-               float* gslot, float* __restrict__ grow, float* __restrict__ gws,
-               double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
-               GatherKnobs kn) {
-    constexpr int GPW = kWarp / LPR, UNR = 4;
-    const int d = c.d, B = c.B, N = 2 * c.B;
-    const int dp = d + 4;                               // slot pitch (keeps 16 B alignment)
-    const uint32_t step = noise_step ? (uint32_t)noise_step[0] : 0u;
-    const int lane = threadIdx.x & 31, gl = lane % LPR;
-    const unsigned gmask = group_mask<LPR>();
-    const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR;
-    const int ngroups = gridDim.x * (blockDim.x >> 5) * GPW;
-    const int n_tiles = (N + kTile - 1) / kTile;
-    const float mu0 = scalars[VFMB_S_GB_MEAN];
-    const float sig0 = link_fn<LINK>(scalars[VFMB_S_GB_SCALE]);
-    const float w0 = mu0 + global_eps(eps_global, c, step) * sig0;
-    const float alpha = link_fn<LINK>(scalars[VFMB_S_ALPHA]);
-    const float half_log_alpha = 0.5f * logf(alpha);
-    const float scale = c.n_train / ((float)c.S * (float)B);
-    double acc3[3] = {0.0, 0.0, 0.0};                   // nll, resid, squared error (field-0 occurrences)
-
-    for (int tile = group; tile < n_tiles; tile += ngroups) {
-        const TileSpan ts = tile_span(tile, N, kn.keep, pos_rank, urec);
-        const int t0 = ts.t0, t1 = ts.t1;
-        if (t0 >= t1) continue;
-        int cur = ts.head_u;                                // else set from the first position
-        Vec<VEC> acc[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[i].v[j] = 0.f;
-        float gw = 0.f;
-
-        auto flush = [&](int u) {
-            const bool open_h = u == ts.head_u, open_t = u == ts.tail_u;
-            float* dst; float* dstw;
-            if (open_h)      { dst = gslot + ((size_t)tile * 2) * dp;     dstw = dst + d; }
-            else if (open_t) { dst = gslot + ((size_t)tile * 2 + 1) * dp; dstw = dst + d; }
-            else             { dst = grow + (size_t)u * d;                dstw = gws + u; }
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                int k = (gl + i * LPR) * VEC;
-                if (k < d) st_vec<VEC>(dst + k, acc[i]);
-            }
-            if (gl == 0) *dstw = gw;
-        };
-
-        for (int b0 = t0; b0 < t1; b0 += LPR) {
-            // ---- lane-parallel: one position per lane of the group
-            const int idx = b0 + gl;
-            const bool ok = idx < t1;
-            const int src = ok ? __ldg(partner + idx) : 0;
-            const int ur = ok ? __ldg(pos_rank + idx) : 0;
-            const int o = ok ? __ldg(occ + idx) : 1;
-            // bias sum in field order (as k_score: ws[rank of field 0] + ws[rank of field 1])
-            const float bs = ok ? ((o & 1) ? __ldg(ws + src) + __ldg(ws + ur) : __ldg(ws + ur) + __ldg(ws + src)) : 0.f;
-            const float yl = ok ? __ldg(y + (o >> 1)) : 0.f;
-            const int cnt = min(LPR, t1 - b0);
-            const int src0 = __shfl_sync(gmask, src, 0, LPR), ur0 = __shfl_sync(gmask, ur, 0, LPR);
-            if (b0 == t0) cur = ur0;
-            for (int j = 0; j < cnt; j += UNR) {               // UNR row pairs in flight
-                int uj[UNR], sj[UNR];
-                Vec<VEC> t[UNR][NV], own[UNR][NV];
-#pragma unroll
-                for (int e = 0; e < UNR; ++e) {
-                    uj[e] = __shfl_sync(gmask, ur, (j + e) & (LPR - 1), LPR);
-                    sj[e] = __shfl_sync(gmask, src, (j + e) & (LPR - 1), LPR);
-                    if (j + e >= cnt) { sj[e] = src0; uj[e] = ur0; }
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        int k = (gl + i * LPR) * VEC;
-                        if (k < d) {
-                            t[e][i] = ld_vec_nc<VEC>(vs + (size_t)sj[e] * d + k);
-                            own[e][i] = ld_vec_nc<VEC>(vs + (size_t)uj[e] * d + k);   // L1 hit inside a segment
-                        }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < UNR; ++e) {
-                    if (j + e < cnt) {                         // group-uniform
-                        const int oj = __shfl_sync(gmask, o, (j + e) & (LPR - 1), LPR);
-                        const float bsj = __shfl_sync(gmask, bs, (j + e) & (LPR - 1), LPR);
-                        const float yn = __shfl_sync(gmask, yl, (j + e) & (LPR - 1), LPR);
-                        // field-0 row first, as k_score multiplies them (a * b is commutative; kept for clarity)
-                        float part = 0.f;
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) {
-                            int k = (gl + i * LPR) * VEC;
-                            if (k < d)
-#pragma unroll
-                                for (int q = 0; q < VEC; ++q) part = fmaf(own[e][i].v[q], t[e][i].v[q], part);
-                        }
-                        part = group_sum<LPR>(part, gmask);
-                        const float p = w0 + bsj + part;
-                        float r, mu_out = p;
-                        if (LIK == VFMB_BERNOULLI) { mu_out = 1.f / (1.f + expf(-p)); r = scale * (mu_out - yn); }
-                        else r = scale * alpha * (p - yn);
-                        if (!(oj & 1) && gl == 0) {            // the field-0 occurrence owns the sample's outputs
-                            const int n = oj >> 1;
-                            const float err = yn - p;
-                            float nll;
-                            if (LIK == VFMB_GAUSSIAN) nll = 0.5f * alpha * err * err - half_log_alpha + 0.9189385332046727f;
-                            else nll = fmaxf(p, 0.f) - yn * p + log1pf(expf(-fabsf(p)));
-                            pred[n] = p; mean[n] = mu_out; resid[n] = r;
-                            acc3[0] += (double)nll; acc3[1] += (double)r; acc3[2] += (double)err * (double)err;
-                        }
-                        if (uj[e] != cur) {
-                            flush(cur);
-                            cur = uj[e];
-#pragma unroll
-                            for (int i = 0; i < NV; ++i)
-#pragma unroll
-                                for (int q = 0; q < VEC; ++q) acc[i].v[q] = 0.f;
-                            gw = 0.f;
-                        }
-                        gw += r;
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) {
-                            int k = (gl + i * LPR) * VEC;
-                            if (k < d)
-#pragma unroll
-                                for (int q = 0; q < VEC; ++q) acc[i].v[q] = fmaf(r, t[e][i].v[q], acc[i].v[q]);
-                        }
-                    }
-                }
-            }
-        }
-        flush(cur);
-        if (ts.head_u >= 0)
-            finish_cut_row<VEC, LPR, NV, 1>(ts.head_u, tile, d, nullptr, urec, gslot, grow + (size_t)ts.head_u * d,
-                                            gws + ts.head_u, arrive, n_tiles + 1, kn.light_fence);
-        if (ts.tail_u >= 0 && ts.tail_u != ts.head_u)
-            finish_cut_row<VEC, LPR, NV, 1>(ts.tail_u, tile, d, nullptr, urec, gslot, grow + (size_t)ts.tail_u * d,
-                                            gws + ts.tail_u, arrive, n_tiles + 1, kn.light_fence);
-    }
-    if (block_partials<3>(acc3, partials, counter)) {
-        double tot[3];
-        final_sums<3>(partials, tot);
-        if (threadIdx.x == 0) {     // the KL is added by k_adam_rows<FLAVOR 2> (data term only here)
-            stats[VFMB_ST_NLL_MEAN] = (float)(tot[0] / (double)B);
-            stats[VFMB_ST_SUM_RESID] = (float)tot[1];
-            stats[VFMB_ST_SUM_SQERR] = (float)tot[2];
-            stats[VFMB_ST_LOSS] = (float)((double)c.n_train * tot[0] / (double)B);
-            stats[VFMB_ST_W0] = w0;
-            forward_done(noise_step, step, meta, stats);
-            *counter = 0;
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------- philox export
 template <int VEC>
 __global__ void k_philox_export(DevCfg c, const int32_t* __restrict__ uniq, int U, uint32_t step,
@@ -955,13 +792,14 @@ static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     if (put_) put = *put_;
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     // fused training step only: the row update follows within the same step
-    const float* pf_m = (lean && (tuning().prefetch_mv & 1)) ? tab->entity_m : nullptr;
-    const float* pf_v = (lean && (tuning().prefetch_mv & 2)) ? tab->entity_v : nullptr;
+    const int keep = lean ? tuning().l2_keep : 0;
+    const float* pf_m = (lean && ((tuning().prefetch_mv & 1) || (keep & 2))) ? tab->entity_m : nullptr;
+    const float* pf_v = (lean && ((tuning().prefetch_mv & 2) || (keep & 4))) ? tab->entity_v : nullptr;
 #define LAUNCH_STAGE(LINK, LEAN)                                                                       \
-    k_stage<VEC, LPR, NV, LINK, LEAN><<<grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, 32), 256, 0, counted(stream)>>>( \
+    CUDA_TRY(launch_chained(k_stage<VEC, LPR, NV, LINK, LEAN>, grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, 32), 256, 0, stream, \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
         io->eps_bias, io->eps_entity, tab->noise_step, io->vs, io->ws, io->es,                         \
-        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap, pf_m, pf_v, put)
+        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap, pf_m, pf_v, keep, put))
 #define LAUNCH_STAGE_ALL()                                                                             \
     do {                                                                                               \
         if (cfg->link == VFMB_LINK_ABS) { if (lean) LAUNCH_STAGE(0, 1); else LAUNCH_STAGE(0, 0); }     \
@@ -999,10 +837,10 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     TailPut tp{};
     if (sb) tp = sb->tp;
 #define LAUNCH_SCORE(LINK, LIK)                                                                        \
-    k_score<VEC, LPR, NV, LINK, LIK><<<grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, 32), 256, 0, counted(stream)>>>( \
+    CUDA_TRY(launch_chained(k_score<VEC, LPR, NV, LINK, LIK>, grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, 32), 256, 0, stream, \
         dc, tab->scalars, inv, plan->pos_of, rows, wsp, io->y, io->eps_global,                         \
         tab->noise_step, plan->meta, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials, \
-        io->counters + 1, io->stats, defer_kl, vp, tp)
+        io->counters + 1, io->stats, defer_kl, vp, tp))
 #define LAUNCH_SCORE_ALL()                                                                              \
     do {                                                                                                \
         if (cfg->link == VFMB_LINK_ABS) {                                                               \
@@ -1120,13 +958,13 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
 #define LAUNCH_GATHER(VEC, LPR, NV)                                                                          \
     do {                                                                                                     \
         if (unit_coef)                                                                                       \
-            k_gather<VEC, LPR, NV, 1><<<grid_resident(k_gather<VEC, LPR, NV, 1>, n_bt * 8, 1), 256, 0, counted(stream)>>>( \
+            CUDA_TRY(launch_chained(k_gather<VEC, LPR, NV, 1>, grid_resident(k_gather<VEC, LPR, NV, 1>, n_bt * 8, 1), 256, 0, stream, \
                 cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive, \
-                vp, gptr, kn);                                                                               \
+                vp, gptr, kn));                                                                              \
         else                                                                                                 \
-            k_gather<VEC, LPR, NV, 0><<<grid_resident(k_gather<VEC, LPR, NV, 0>, n_bt * 8, 1), 256, 0, counted(stream)>>>( \
+            CUDA_TRY(launch_chained(k_gather<VEC, LPR, NV, 0>, grid_resident(k_gather<VEC, LPR, NV, 0>, n_bt * 8, 1), 256, 0, stream, \
                 cfg->d, cfg->F, N, partner, plan->pos_rank, plan->urec, vsp, tbl, rs, gslot, io->grow, io->gws, arrive, \
-                vp, gptr, kn);                                                                               \
+                vp, gptr, kn));                                                                              \
     } while (0)
     // The gather has no cross-lane arithmetic (every output element is a sequential sum over positions), so its
     // lane mapping is free: half as many lanes per row with two vectors each puts twice the positions behind
@@ -1138,42 +976,6 @@ static int launch_gather(const vfmb_config* cfg, const vfmb_plan* plan, const vf
         LAUNCH_GATHER(VEC, LPR, NV);
     });
 #undef LAUNCH_GATHER
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-// F == 2 fused step: k_gather_score (score + ordered segmented sum)
-static int launch_gather_score(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan* plan,
-                               const vfmb_step_io* io, vfmb_stream stream_) {
-    Prep P;
-    int rc = prep(cfg, "vfmb_sampled_step", stream_, 2, &P);
-    if (rc) return rc;
-    if (!io->grow || !io->gws || !io->partials || !io->pred || !io->mean || !io->resid || !plan->occ)
-        return set_error(VFMB_EINVAL, "vfmb_sampled_step: scratch required");
-    const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
-    float* gslot = (float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off;
-    // one lane group per tile.  (Smaller blocks were tried for the plan-overlapped step -- 121.9 us with
-    // 128 threads, 125.2 us with 64, against 113.4 us for the unfused pair: the fused kernel does not
-    // lose to the plan through SM slots.)
-    const int gs_block = 256;
-    const int64_t gs_warps = (cap.n_tiles + (32 / L.lpr) - 1) / (32 / L.lpr);
-    int gs_grid = (int)((gs_warps + gs_block / 32 - 1) / (gs_block / 32));
-    if (gs_grid > kGridCap) gs_grid = kGridCap;            // block partials are sized for kGridCap blocks
-    int32_t* arrive = (int32_t*)((float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).arrive_off);
-    const GatherKnobs kn{tuning().gather_keep, 0, tuning().gather_fence};
-#define LAUNCH_GS(LINK, LIK)                                                                             \
-    k_gather_score<VEC, LPR, NV, LINK, LIK><<<gs_grid, gs_block, 0, counted(stream)>>>(                  \
-        dc, tab->scalars, plan->partner, plan->pos_rank, plan->occ, plan->urec, arrive, io->vs, io->ws, io->y, \
-        io->eps_global, tab->noise_step, plan->meta, io->pred, io->mean, io->resid, gslot, io->grow, io->gws, \
-        io->partials, io->counters + 1, io->stats, kn)
-    VFMB_LAYOUT_SWITCH(L, {
-        if (cfg->link == VFMB_LINK_ABS) {
-            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_GS(0, VFMB_GAUSSIAN); else LAUNCH_GS(0, VFMB_BERNOULLI);
-        } else {
-            if (cfg->likelihood == VFMB_GAUSSIAN) LAUNCH_GS(1, VFMB_GAUSSIAN); else LAUNCH_GS(1, VFMB_BERNOULLI);
-        }
-    });
-#undef LAUNCH_GS
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1233,17 +1035,8 @@ extern "C" int vfmb_sampled_step(const vfmb_config* cfg, const vfmb_tables* tab,
     }
     int rc = launch_stage(cfg, tab, plan, io, stream, true);
     if (rc) return rc;
-    // measured (ml20m): alone the fused kernel saves 5 us per step (104 -> 99 us); next to a
-    // concurrently running plan it loses 6 us -- it needs 111 registers per thread, which leaves no
-    // room on an SM for the plan's blocks.  So: fused unless the caller reserved room for the plan.
-    const int fuse_knob = tuning().fuse_score;
-    const bool fuse_gs = fuse_knob >= 0 ? fuse_knob != 0 : grid_reserve() == 0;
-    if (cfg && cfg->F == 2 && plan && plan->occ && fuse_gs) {
-        // F == 2: 3 launches -- k_stage<LEAN>, k_gather_score, k_adam_rows<FLAVOR 2>
-        rc = launch_gather_score(cfg, tab, plan, io, stream);
-        if (rc) return rc;
-        return launch_adam(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, 2, stream);
-    }
+    // (a one-pass k_gather_score existed for F == 2 until the gather went hierarchical: the pair below then won,
+    //  98.9 vs 105.4 us per ml20m step with cached plans, and the fused kernel was removed)
     rc = launch_score(cfg, tab, plan, io, stream, 1);
     if (rc) return rc;
     return backward_impl(cfg, tab, plan, io, adam, VFMB_ADAM_TOUCHED, 1.0f, 2, stream);

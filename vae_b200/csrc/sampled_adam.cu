@@ -288,6 +288,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16_hint(void* smem, const void* gmem, uint64_t pol) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(s), "l"(gmem), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -301,6 +305,7 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
                  const float* __restrict__ eps_bias, const float* __restrict__ eps_entity,
                  const float* __restrict__ cq, const float* __restrict__ grow, const float* __restrict__ gws,
                  AdamDev h, int32_t* __restrict__ adam_step, float kl_scale, FinalArgs fa) {
+    chain_wait();                                           // launched with launch_chained()
     constexpr int VEC = 4, GPW = kWarp / LPR, NS = kPipeStages;
     constexpr bool KLF = FLAVOR == 2;
     constexpr bool DPF = FLAVOR == 3;    // mode B owner: scalar parameters + loss from the ranks' tail slots
@@ -317,6 +322,7 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
     float step_size, inv_bc2;
     adam_coeffs(h, (int)step + 1, &step_size, &inv_bc2);
     float4* my = s_stage + (size_t)warp * (NS * 6 * 32) + lane;
+    const uint64_t pol = policy_evict_first();            // rows k_stage parked in L2 (fa.l2_demote) are handed back
     // FLAVOR >= 1: the last block takes no rows; its first thread updates the scalar parameters right
     // away (they depend on the sums k_score left, not on the row gradients) -- off the critical path
     const bool split = FLAVOR >= 1 && gridDim.x > 1;
@@ -366,9 +372,12 @@ k_adam_rows_pipe(DevCfg c, float* __restrict__ bias, float* __restrict__ bias_m,
             if (cbase + sel < hi && kin) {
                 const size_t eoff = (size_t)rowid * 2 * d + k;
                 float4* dst = my + (r % NS) * (6 * 32);
-                cp_async16(dst + 0 * 32, entity + eoff);     cp_async16(dst + 1 * 32, entity + eoff + d);
-                cp_async16(dst + 2 * 32, entity_m + eoff);   cp_async16(dst + 3 * 32, entity_m + eoff + d);
-                cp_async16(dst + 4 * 32, entity_v + eoff);   cp_async16(dst + 5 * 32, entity_v + eoff + d);
+                if (fa.l2_demote & 1) { cp_async16_hint(dst + 0 * 32, entity + eoff, pol); cp_async16_hint(dst + 1 * 32, entity + eoff + d, pol); }
+                else { cp_async16(dst + 0 * 32, entity + eoff);     cp_async16(dst + 1 * 32, entity + eoff + d); }
+                if (fa.l2_demote & 2) { cp_async16_hint(dst + 2 * 32, entity_m + eoff, pol); cp_async16_hint(dst + 3 * 32, entity_m + eoff + d, pol); }
+                else { cp_async16(dst + 2 * 32, entity_m + eoff);   cp_async16(dst + 3 * 32, entity_m + eoff + d); }
+                if (fa.l2_demote & 4) { cp_async16_hint(dst + 4 * 32, entity_v + eoff, pol); cp_async16_hint(dst + 5 * 32, entity_v + eoff + d, pol); }
+                else { cp_async16(dst + 4 * 32, entity_v + eoff);   cp_async16(dst + 5 * 32, entity_v + eoff + d); }
             }
             cp_async_commit();
         };
@@ -636,6 +645,7 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
     fa.counter = io->counters ? io->counters + 2 : nullptr;
     fa.gslot = io->partials ? (const float*)io->partials + scratch_map(cfg->B, cfg->F, cfg->d, cap.u_cap).gslot_off : nullptr;
     fa.likelihood = cfg->likelihood; fa.noise_step = tab->noise_step;
+    fa.l2_demote = (flavor == 2) ? tuning().l2_keep : 0;    // the fused step's lean k_stage parked the rows
     if (flavor == 3) {
         if (!dp || !dp->tail_slots || !dp->stats_out) return set_error(VFMB_EINVAL, "vfmb_shard_owner_update: tail slots required");
         if (!(mode == VFMB_ADAM_TOUCHED && P.L.vec == 4 && P.L.nv == 1 && tuning().adam_pipe != 0))
@@ -667,9 +677,9 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
             if (adam_reserve && grid_reserve() > 0 && grid / kNumSMs > grid_reserve() + 1) grid -= grid_reserve() * kNumSMs; \
             const int64_t need = (cap.u_cap + 63) / 64;        /* >= 8 rows per warp */                    \
             if (grid > need) grid = (int)(need < 1 ? 1 : need);                                           \
-            kern<<<grid, 256, smem, counted(stream)>>>(dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, \
+            CUDA_TRY(launch_chained(kern, grid, 256, smem, stream, dc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, \
                 tab->entity_m, tab->entity_v, plan->urec, plan->meta, eps_b, eps_e, io->cq, io->grow, io->gws, \
-                h, tab->adam_step, kl_grad_scale, fa);                                                    \
+                h, tab->adam_step, kl_grad_scale, fa));                                                   \
         } while (0)
 #define LAUNCH_PIPE_F(LPR_, LINK)                                                                         \
         do { if (flavor == 0) LAUNCH_PIPE(LPR_, LINK, 0); else if (flavor == 1) LAUNCH_PIPE(LPR_, LINK, 1); \

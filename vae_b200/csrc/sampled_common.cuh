@@ -62,6 +62,7 @@ struct FinalArgs {
     const float* tail_slots; int tail_P, tail_pitch;
     int B_global; float n_train_global;
     const float* recv_grads; const int32_t* occ; int slot_pitch, n_real;   // the requesters' gradient slots
+    int l2_demote;                      // bit 0 / 1 / 2: rows of entity / m / v were parked in L2 by k_stage (tuning l2_keep)
 };
 
 // Mode B / mode A: scalar parameters (replicated on every rank, identical results) and the global-batch

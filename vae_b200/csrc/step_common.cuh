@@ -142,8 +142,9 @@ __device__ __forceinline__ void hand_back(T& mine, T val, int it, int lane) {
     }
 }
 
-__device__ __forceinline__ void prefetch_row(const float* p, int bytes) {
-    for (int off = 0; off < bytes; off += 128) prefetch_l2(reinterpret_cast<const char*>(p) + off);
+__device__ __forceinline__ void prefetch_row(const float* p, int bytes, bool keep = false) {
+    if (keep) for (int off = 0; off < bytes; off += 128) prefetch_l2_keep(reinterpret_cast<const char*>(p) + off);
+    else for (int off = 0; off < bytes; off += 128) prefetch_l2(reinterpret_cast<const char*>(p) + off);
 }
 
 
@@ -183,7 +184,7 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g,
 // the step: parameters and both Adam moments of every touched row are read and written once.
 
 // ------------------------------------------------------------------------------- cut rows
-// The backward's segmented reduction (k_gather / k_gather_score / k_cgather) walks the sorted
+// The backward's segmented reduction (k_gather / k_cgather) walks the sorted
 // occurrence list in tiles of kTile positions (tile_span below: rows of up to kTile occurrences are kept
 // whole).  A longer row is cut by the tile boundaries and leaves one partial per
 // tile it touches: in the tail slot of its first tile, in the head slots of the following ones.
