@@ -55,39 +55,57 @@ def rows_kernel_bytes(B, F, d, U):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML while the timed region runs.
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    The thread is started BEFORE the warm-up (its first NVML calls are slow and, on a timed region of a
+    few milliseconds, landed inside it: 115 vs 103 us per step at --steps 20) and samples every 50 ms; the
+    samples that count are those between ``mark()`` and ``stop()``, plus one taken by the caller with
+    ``sample()`` right after the last step is enqueued, i.e. while the GPU is inside the timed region."""
+
+    def __init__(self, index: int, period_s: float = 0.05):
         super().__init__(daemon=True)
         self.period, self.samples, self.reasons, self.max_mhz = period_s, [], set(), None
         self._stop_evt = threading.Event()
+        self._t_mark = None
+        self._lock = threading.Lock()
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.names = {pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                          pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                          pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                          pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
         except Exception:                                     # pragma: no cover
             self.nv = None
 
-    def run(self):
+    def sample(self):
         if self.nv is None:
             return
-        nv = self.nv
-        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
-                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:                                 # pragma: no cover
-                pass
+        try:
+            mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        except Exception:                                     # pragma: no cover
+            return
+        with self._lock:
+            if self._t_mark is None:
+                return                                        # before the timed region: warms NVML up only
+            self.samples.append(mhz)
+            for bit, name in self.names.items():
+                if mask & bit:
+                    self.reasons.add(name)
+
+    def run(self):
+        while self.nv is not None and not self._stop_evt.is_set():
+            self.sample()
             time.sleep(self.period)
+
+    def mark(self):
+        """Start of the timed region: samples count from here."""
+        with self._lock:
+            self._t_mark = time.time()
 
     def stop(self):
         self._stop_evt.set()
@@ -232,16 +250,18 @@ def run_ours(args):
             j = (i * world + rank) % n_batches
             if j not in static_plans:
                 static_plans[j] = model.static_plan(batch(i)[0])
-    run_steps(0, W)
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    run_steps(0, W)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     n_launch0 = int(L.lib().vfmb_launch_count())
+    sampler.mark()
     ev0.record()
     last = run_steps(W, W + K)
     ev1.record()
+    sampler.sample()                                         # the GPU is still inside the timed region here
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
@@ -485,6 +505,8 @@ def run_sharded(args):
         torch.cuda.synchronize()
 
     W, K = args.warmup, args.steps
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(W):
         out = model.step(*batch(i))
     barrier()
@@ -519,10 +541,9 @@ def run_sharded(args):
             for i in range(W):
                 out = step(*batch(i))
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     ev0.record()
     if pipe is not None:
         for i in range(W, W + K):
@@ -531,6 +552,7 @@ def run_sharded(args):
         for i in range(W, W + K):
             out = step(*batch(i))
     ev1.record()
+    sampler.sample()                                         # the GPU is still inside the timed region here
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()

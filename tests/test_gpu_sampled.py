@@ -468,8 +468,10 @@ def test_pipelined_and_register_staged_row_updates_agree_bitwise(name):
 
 @pytest.mark.parametrize("d", [32, 64, 20])
 def test_gather_launch_knobs_do_not_change_a_bit(d):
-    """Tile hand-out (static stride / counter), the lane mapping of the gather and of k_stage, and the fence
+    """Tile hand-out (static stride / counter), the lane mapping of k_stage, the L2 hints and the fence
     flavour of the cut-row finisher are scheduling only: parameters, moments and losses are identical.
+    The lane mapping of the gather also sets its group-tile size, i.e. where a long row's sum is cut:
+    same result up to the association of that sum (one setting per process).
     The batch has Zipf head rows of thousands of occurrences (cut by group and block tiles, global finisher)
     and thousands of short rows."""
     from vae_b200 import _lib as L
@@ -484,7 +486,7 @@ def test_gather_launch_knobs_do_not_change_a_bit(d):
     knobs = ("gather_dyn", "gather_fence", "gather_wide", "stage_wide", "l2_keep")
     defaults = (1, 1, 1, 0, 1)
     res = []
-    for setting in (defaults, (0, 0, 0, 1, 0), (1, 0, 0, 0, 1)):
+    for setting in (defaults, (0, 0, 1, 1, 0), (1, 0, 1, 0, 1), (1, 1, 0, 0, 1)):
         for k, v in zip(knobs, setting):
             L.check(L.lib().vfmb_set_tuning(k.encode(), v))
         try:
@@ -495,10 +497,13 @@ def test_gather_launch_knobs_do_not_change_a_bit(d):
         finally:
             for k, v in zip(knobs, defaults):
                 L.lib().vfmb_set_tuning(k.encode(), v)
-    for r in res[1:]:
+    for r in res[1:3]:
         assert r[0] == res[0][0]
         for a, b in zip(res[0][1:], r[1:]):
             assert torch.equal(a, b)
+    np.testing.assert_allclose(res[3][0], res[0][0], rtol=1e-6)         # gather_wide = 0: another association
+    for a, b in zip(res[0][1:], res[3][1:]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)                 # (four steps amplify the last bits)
 
 
 @pytest.mark.parametrize("output,F", [("class", 2), ("reg", 2), ("class", 3)])

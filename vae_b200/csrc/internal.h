@@ -32,7 +32,8 @@ struct Tuning {
     int stage_wide = 0;      // k_stage: half the lanes per row, two vectors per lane
     int score_wide = 0;      // k_score: half the lanes per row, two vectors per lane (another summation order of the
                              //   dot product: last-bit differences, so one setting per process)
-    int gather_wide = 1;     // backward gather: half the lanes per row, two vectors per lane (results identical)
+    int gather_wide = 1;     // backward gather: half the lanes per row, two vectors per lane.  This also halves the group
+                             //   tile, i.e. moves the cuts of a long row's sum: last-bit differences, one setting per process
     int gather_keep = 32;    // backward gather: rows of up to this many occurrences are never cut by a tile boundary
     int gather_fence = 1;    // finisher of cut rows: 1 = fence.acq_rel.gpu, 0 = __threadfence() (fence.sc)
     int pdl = 0;             // programmatic dependent launch along the step's and the plan's kernel chains: the next
