@@ -182,6 +182,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     (in-tree, so that it travels to the GPU box).  No-op when up to date."""
     if not force and not _stale():
         return LIB_PATH
+    # one builder at a time: the ranks of a torchrun job all get here when the library is stale (it happened:
+    # eight concurrent builds wrote the same objects and the first ranks loaded a half-linked library)
+    import fcntl
+    os.makedirs(os.path.join(_ROOT, "build"), exist_ok=True)
+    with open(os.path.join(_ROOT, "build", ".lock" + ("_" + _VARIANT if _VARIANT else "")), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():                   # another process built it while this one waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
     # one object per translation unit, compiled concurrently (the template instantiations make
     # each .cu ~20-60 s of ptxas time), then one link step
@@ -202,12 +217,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
             errs.append(out)
     if errs:
         raise RuntimeError("nvcc failed:\n" + "\n".join(errs))
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH] + [obj for obj, _ in jobs]
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp] + [obj for obj, _ in jobs]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)                                # readers never see a partly written library
     with open(LIB_PATH + ".sha256", "w") as fh:
         fh.write(_source_digest())
     return LIB_PATH
