@@ -30,7 +30,7 @@ struct Tuning {
     int gather_dyn = 1;      // backward gather: tiles after a group's first are handed out by an atomic counter
                              //   (0 = static stride); results do not depend on it
     int stage_wide = 0;      // k_stage: half the lanes per row, two vectors per lane
-    int score_wide = 0;      // k_score: half the lanes per row, two vectors per lane (another summation order of the
+    int score_wide = -1;     // k_score: half the lanes per row, two vectors per lane; -1 = when F > 2 (another summation order of the
                              //   dot product: last-bit differences, so one setting per process)
     int gather_wide = 1;     // backward gather: half the lanes per row, two vectors per lane.  This also halves the group
                              //   tile, i.e. moves the cuts of a long row's sum: last-bit differences, one setting per process

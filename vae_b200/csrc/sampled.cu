@@ -851,7 +851,8 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     } while (0)
     // score_wide: half the lanes per row, two vectors per lane -- twice the samples per round.  The dot
     // product is then summed in another (fixed) order: a different last bit, so it is one knob for the process.
-    const bool wide = tuning().score_wide && L.vec == 4 && L.nv == 1 && L.lpr >= 8;
+    const int sw = tuning().score_wide;                        // -1: for F > 2 (sideinfo: 49.8 -> 34.5 us; ml20m: no gain in the step)
+    const bool wide = (sw < 0 ? cfg->F > 2 : sw != 0) && L.vec == 4 && L.nv == 1 && L.lpr >= 8;
     if (wide && L.lpr == 8) { constexpr int VEC = 4, LPR = 4, NV = 2; LAUNCH_SCORE_ALL(); }
     else if (wide && L.lpr == 16) { constexpr int VEC = 4, LPR = 8, NV = 2; LAUNCH_SCORE_ALL(); }
     else if (wide && L.lpr == 32) { constexpr int VEC = 4, LPR = 16, NV = 2; LAUNCH_SCORE_ALL(); }
