@@ -836,7 +836,7 @@ extern "C" int vfmb_closed_backward_weighted(const vfmb_config* cfg, const vfmb_
     });
     cudaEvent_t ev0, ev1;                                   // measurement hook (vfmb_profile_events)
     profile_events(&ev0, &ev1);
-    if (ev0 && ev1) cudaEventRecord(ev0, stream);
+    if (ev0 && ev1) record_profile_event(ev0, stream);
     VFMB_LAYOUT_SWITCH(L, {
         if (mode == VFMB_ADAM_TOUCHED)
             k_cadam<VEC, LPR, NV, VFMB_ADAM_TOUCHED><<<grid_u, 256, 0, counted(stream)>>>(
@@ -847,7 +847,7 @@ extern "C" int vfmb_closed_backward_weighted(const vfmb_config* cfg, const vfmb_
                 cc, tab->bias, tab->bias_m, tab->bias_v, tab->entity, tab->entity_m, tab->entity_v, tab->scalars,
                 plan->urec, plan->meta, io->cq, io->grow, io->gws, h, tab->adam_step, io->grad_bias, io->grad_entity);
     });
-    if (ev0 && ev1) cudaEventRecord(ev1, stream);
+    if (ev0 && ev1) record_profile_event(ev1, stream);
     const int items = cfg->F * (2 * cfg->d + 3);
     const int grid_f = (items + 7) / 8;
     if (mode == VFMB_ADAM_TOUCHED)

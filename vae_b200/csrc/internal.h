@@ -74,6 +74,15 @@ static inline cudaError_t launch_chained(void (*kern)(KArgs...), int grid, int b
 }
 // optional events around the dominant kernel (see vfmb_profile_events)
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
+// record a measurement event; on a capturing stream as an external event-record NODE (a plain record would
+// only mark a dependency inside the capture and never fire at replay)
+static inline void record_profile_event(cudaEvent_t ev, cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive)
+        cudaEventRecordWithFlags(ev, stream, cudaEventRecordExternal);
+    else
+        cudaEventRecord(ev, stream);
+}
 
 #define CUDA_TRY(expr)                                                                  \
     do {                                                                                \

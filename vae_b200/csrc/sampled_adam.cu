@@ -662,7 +662,7 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
         const size_t smem = (size_t)8 * kPipeStages * 6 * 32 * sizeof(float4);
         cudaEvent_t ev0, ev1;
         profile_events(&ev0, &ev1);
-        if (ev0 && ev1) cudaEventRecord(ev0, stream);
+        if (ev0 && ev1) record_profile_event(ev0, stream);
 #define LAUNCH_PIPE(LPR_, LINK, FLAVOR)                                                                   \
         do {                                                                                              \
             auto kern = k_adam_rows_pipe<LPR_, LINK, FLAVOR>;                                             \
@@ -693,7 +693,7 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
 #undef LAUNCH_PIPE_L
 #undef LAUNCH_PIPE_F
 #undef LAUNCH_PIPE
-        if (ev0 && ev1) cudaEventRecord(ev1, stream);
+        if (ev0 && ev1) record_profile_event(ev1, stream);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -708,13 +708,13 @@ int launch_adam(const vfmb_config* cfg, const vfmb_tables* tab, const vfmb_plan*
     VFMB_LAYOUT_SWITCH(L, {
         cudaEvent_t ev0, ev1;
         profile_events(&ev0, &ev1);
-        if (ev0 && ev1) cudaEventRecord(ev0, stream);
+        if (ev0 && ev1) record_profile_event(ev0, stream);
         if (cfg->link == VFMB_LINK_ABS) {
             if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM_F(0, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM_F(0, VFMB_GRAD_ONLY);
         } else {
             if (mode == VFMB_ADAM_TOUCHED) LAUNCH_ADAM_F(1, VFMB_ADAM_TOUCHED); else LAUNCH_ADAM_F(1, VFMB_GRAD_ONLY);
         }
-        if (ev0 && ev1) cudaEventRecord(ev1, stream);
+        if (ev0 && ev1) record_profile_event(ev1, stream);
     });
 #undef LAUNCH_ADAM_F
 #undef LAUNCH_ADAM
