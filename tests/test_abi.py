@@ -80,3 +80,20 @@ def test_capacity_invariants_and_host_side_argument_checks():
     cfg.B, cfg.F, cfg.d, cfg.R, cfg.S, cfg.n_classes = 8, 2, 4, 10, 9, 2                  # S out of range
     assert lib.vfmb_sampled_forward(C.byref(cfg), C.byref(L.Tables()), C.byref(L.Plan()), C.byref(L.StepIO()), None) != 0
     assert b"variational samples" in lib.vfmb_last_error()
+
+
+def test_launch_knobs_accept_known_keys_and_reject_the_rest():
+    """vfmb_set_tuning is host-side state only: every documented key round-trips, bad keys / values are
+    refused with an error text (no GPU needed)."""
+    lib = L.lib()
+    good = {"grid_reserve": (1, 0), "adam_reserve": (0, 1), "adam_pipe": (0, 1), "l2_keep": (0, 7, 1),
+            "gather_dyn": (0, 1), "gather_fence": (0, 1), "gather_wide": (0, 1), "gather_keep": (1, 32),
+            "stage_wide": (1, 0), "score_wide": (1, 0, -1), "stage_chunk": (32, 16), "score_chunk": (16, 32),
+            "pdl": (1, 0), "prefetch_mv": (3, 0), "fuse_score": (1, 0)}
+    for key, values in good.items():
+        for v in values:                                       # the last value of every tuple is the default
+            assert lib.vfmb_set_tuning(key.encode(), v) == 0, (key, v, lib.vfmb_last_error())
+    for key, v in (("no_such_knob", 1), ("l2_keep", 8), ("stage_chunk", 24), ("gather_keep", 0), ("prefetch_mv", 99)):
+        assert lib.vfmb_set_tuning(key.encode(), v) != 0
+        assert key.split("_")[0].encode() in lib.vfmb_last_error() or b"unknown" in lib.vfmb_last_error()
+    assert lib.vfmb_set_tuning(None, 0) != 0

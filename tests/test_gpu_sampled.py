@@ -483,10 +483,10 @@ def test_gather_launch_knobs_do_not_change_a_bit(d):
     y = rng.normal(size=B).astype(np.float32)
     xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
     counts = torch.from_numpy(np.bincount(x.reshape(-1), minlength=sum(fs)).astype(np.float32))
-    knobs = ("gather_dyn", "gather_fence", "gather_wide", "stage_wide", "l2_keep")
-    defaults = (1, 1, 1, 0, 1)
+    knobs = ("gather_dyn", "gather_fence", "gather_wide", "stage_wide", "l2_keep", "stage_chunk", "score_chunk")
+    defaults = (1, 1, 1, 0, 1, 16, 32)
     res = []
-    for setting in (defaults, (0, 0, 1, 1, 0), (1, 0, 1, 0, 1), (1, 1, 0, 0, 1)):
+    for setting in (defaults, (0, 0, 1, 1, 0, 32, 16), (1, 0, 1, 0, 1, 32, 32), (1, 1, 0, 0, 1, 16, 32)):
         for k, v in zip(knobs, setting):
             L.check(L.lib().vfmb_set_tuning(k.encode(), v))
         try:

@@ -41,6 +41,10 @@ extern "C" int vfmb_set_tuning(const char* key, int value) {
     if (!strcmp(key, "adam_pipe")) { t.adam_pipe = value != 0; return 0; }
     if (!strcmp(key, "l2_keep")) { if (value < 0 || value > 7) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: l2_keep 0..7"); t.l2_keep = value; return 0; }
     if (!strcmp(key, "pdl")) { t.pdl = value != 0; return 0; }
+    if (!strcmp(key, "stage_chunk") || !strcmp(key, "score_chunk")) {
+        if (value != 16 && value != 32) return vfmb::set_error(VFMB_EINVAL, "vfmb_set_tuning: %s must be 16 or 32", key);
+        (key[1] == 't' ? t.stage_chunk : t.score_chunk) = value; return 0;
+    }
     if (!strcmp(key, "stage_wide")) { t.stage_wide = value != 0; return 0; }
     if (!strcmp(key, "score_wide")) { t.score_wide = value < 0 ? -1 : (value != 0); return 0; }
     if (!strcmp(key, "gather_wide")) { t.gather_wide = value != 0; return 0; }

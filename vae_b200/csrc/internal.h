@@ -29,6 +29,8 @@ struct Tuning {
                              //   layout allows (d % 4 == 0, d <= 128); 0 = the register-staged k_adam_rows
     int gather_dyn = 1;      // backward gather: tiles after a group's first are handed out by an atomic counter
                              //   (0 = static stride); results do not depend on it
+    int stage_chunk = 16;    // k_stage / k_score: units (unique rows / samples) per warp and pass, 16 or 32 (measured:
+    int score_chunk = 32;    //   k_stage 42 -> 36 us on sideinfo with 16, neutral on ml20m; k_score loses with 16)
     int stage_wide = 0;      // k_stage: half the lanes per row, two vectors per lane
     int score_wide = -1;     // k_score: half the lanes per row, two vectors per lane; -1 = when F > 2 (another summation order of the
                              //   dot product: last-bit differences, so one setting per process)

@@ -31,14 +31,14 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
         const int32_t* __restrict__ noise_step, float* __restrict__ vs, float* __restrict__ ws,
         float* __restrict__ es, float* __restrict__ ebs, float* __restrict__ cq,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
-        int smp, int u_stride, const float* __restrict__ pf_m, const float* __restrict__ pf_v, int keep, RowPut put) {
+        int smp, int u_stride, const float* __restrict__ pf_m, const float* __restrict__ pf_v, int keep, int ch, RowPut put) {
     chain_wait();                                           // launched with launch_chained()
     // put (mode B, owner side): the sampled row also goes into the slot of every rank that asked for it
     // pf_m / pf_v (optional): Adam moment tables whose touched rows are pulled into L2 here, while
     // this kernel is issue-bound on Philox and the DRAM pipe idles -- k_adam_rows finds them there
     // smp: variational sample this launch draws (S > 1: one launch per sample, outputs [S][u_stride]);
     // the KL and the KL weights do not depend on the sample and are formed by sample 0
-    constexpr int GPW = kWarp / LPR, ROUNDS = LPR;      // 32 unique rows per warp and pass, GPW per round
+    constexpr int GPW = kWarp / LPR, ROUNDS = LPR;      // up to 32 unique rows per warp and pass, GPW per round
     constexpr int UR = (NV == 1) ? 4 : 2;               // rounds whose [mean | raw scale] loads are in flight
     const int U = meta[0];
     const int d = c.d;
@@ -55,11 +55,12 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
 #pragma unroll
     for (int i = 0; i < NV; ++i) { const int k = (gl + i * LPR) * VEC; act[i] = k < d; kc[i] = act[i] ? k : 0; }
 
-    for (int base = gwarp * kWarp; base < U; base += nwarps * kWarp) {
+    // ch (16 or 32): unique rows per warp and pass -- fewer rows per warp = more warps in flight and a shorter chain
+    for (int base = gwarp * ch; base < U; base += nwarps * ch) {
         // ---- lane-parallel: one unique row per lane
         const int ul = base + lane;
-        const bool valid = ul < U;
-        const int nvalid = min(kWarp, U - base);
+        const bool valid = lane < ch && ul < U;
+        const int nvalid = min(ch, U - base);
         int rowid_l = 0, seg0_l = 0, len_l = 0;          // (lanes past U gather row 0: harmless)
         float klb = 0.f, cqv = 0.f, w_l = 0.f;
         if (valid) {
@@ -190,11 +191,11 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
         int32_t* noise_step, const int32_t* __restrict__ meta, float* __restrict__ pred, float* __restrict__ mean,
         float* __restrict__ resid, float* __restrict__ rsorted, float* __restrict__ msg,
         double* __restrict__ partials, int32_t* __restrict__ counter, float* __restrict__ stats,
-        int defer_kl, int vp, TailPut tp) {
+        int defer_kl, int vp, int ch, TailPut tp) {
     chain_wait();                                           // launched with launch_chained()
     // vp: pitch of the sampled rows in floats (d; mode B: the received slots, d + 4, bias sample at [d] and
     // `inverse` holding slot indices; ws == NULL then).  tp: mode B, see TailPut.
-    constexpr int GPW = kWarp / LPR, ROUNDS = LPR;      // 32 samples per warp and pass, GPW per round
+    constexpr int GPW = kWarp / LPR, ROUNDS = LPR;      // up to 32 samples per warp and pass, GPW per round
     constexpr int UR = (NV == 1) ? 4 : 2;               // F == 2: rounds in flight (two rows each)
     constexpr int FU = (NV == 1) ? 4 : 2;               // F > 2: rows of one sample in flight
     __shared__ int s_idx[8][kWarp * kMaxFields];        // F > 2: row ranks of the warp's 32 samples
@@ -214,11 +215,12 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
 #pragma unroll
     for (int i = 0; i < NV; ++i) { const int k = (gl + i * LPR) * VEC; act[i] = k < d; kc[i] = act[i] ? k : 0; }
 
-    for (int base = gwarp * kWarp; base < B; base += nwarps * kWarp) {
+    // ch (16 or 32): samples per warp and pass
+    for (int base = gwarp * ch; base < B; base += nwarps * ch) {
         // ---- lane-parallel: one sample per lane (ranks, bias sum, target)
         const int nl = base + lane;
-        const bool valid = nl < B;
-        const int nvalid = min(kWarp, B - base);
+        const bool valid = lane < ch && nl < B;
+        const int nvalid = min(ch, B - base);
         int2 rr = make_int2(0, 0);                                    // (invalid samples gather row 0: harmless)
         float bsum = 0.f, yn = 0.f;
         int* si = s_idx[threadIdx.x >> 5];
@@ -793,13 +795,14 @@ static int launch_stage(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     const Layout& L = P.L; const DevCfg& dc = P.dc; cudaStream_t stream = P.stream; const auto& cap = P.cap;
     // fused training step only: the row update follows within the same step
     const int keep = lean ? tuning().l2_keep : 0;
+    const int ch = tuning().stage_chunk;
     const float* pf_m = (lean && ((tuning().prefetch_mv & 1) || (keep & 2))) ? tab->entity_m : nullptr;
     const float* pf_v = (lean && ((tuning().prefetch_mv & 2) || (keep & 4))) ? tab->entity_v : nullptr;
 #define LAUNCH_STAGE(LINK, LEAN)                                                                       \
-    CUDA_TRY(launch_chained(k_stage<VEC, LPR, NV, LINK, LEAN>, grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, 32), 256, 0, stream, \
+    CUDA_TRY(launch_chained(k_stage<VEC, LPR, NV, LINK, LEAN>, grid_resident(k_stage<VEC, LPR, NV, LINK, LEAN>, cap.u_cap, ch), 256, 0, stream, \
         dc, tab->bias, tab->entity, tab->train_counts, plan->urec, plan->meta, plan->z,                \
         io->eps_bias, io->eps_entity, tab->noise_step, io->vs, io->ws, io->es,                         \
-        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap, pf_m, pf_v, keep, put))
+        io->ebs, io->cq, io->partials, io->counters + 0, io->stats, smp, (int)cap.u_cap, pf_m, pf_v, keep, ch, put))
 #define LAUNCH_STAGE_ALL()                                                                             \
     do {                                                                                               \
         if (cfg->link == VFMB_LINK_ABS) { if (lean) LAUNCH_STAGE(0, 1); else LAUNCH_STAGE(0, 0); }     \
@@ -836,11 +839,12 @@ static int launch_score(const vfmb_config* cfg, const vfmb_tables* tab, const vf
     const int vp = sb ? sb->vp : cfg->d;
     TailPut tp{};
     if (sb) tp = sb->tp;
+    const int ch = tuning().score_chunk;
 #define LAUNCH_SCORE(LINK, LIK)                                                                        \
-    CUDA_TRY(launch_chained(k_score<VEC, LPR, NV, LINK, LIK>, grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, 32), 256, 0, stream, \
+    CUDA_TRY(launch_chained(k_score<VEC, LPR, NV, LINK, LIK>, grid_resident(k_score<VEC, LPR, NV, LINK, LIK>, cfg->B, ch), 256, 0, stream, \
         dc, tab->scalars, inv, plan->pos_of, rows, wsp, io->y, io->eps_global,                         \
         tab->noise_step, plan->meta, io->pred, io->mean, io->resid, io->rsorted, io->msg, io->partials, \
-        io->counters + 1, io->stats, defer_kl, vp, tp))
+        io->counters + 1, io->stats, defer_kl, vp, ch, tp))
 #define LAUNCH_SCORE_ALL()                                                                              \
     do {                                                                                                \
         if (cfg->link == VFMB_LINK_ABS) {                                                               \
