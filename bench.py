@@ -162,6 +162,9 @@ def make_port(w: synth.Workload, train_counts, lr):
     port = vfm_port.SampledPort(w.field_sizes[0], w.field_sizes[1], w.d, tc, output=w.output,
                                 field_sizes=w.field_sizes, kl_weighting=kl,
                                 interaction="prod" if w.n_fields == 2 else "pairwise")
+    with torch.no_grad():                                    # N(0,1) init of 10^7..10^8 values holds a few exact zeros: a
+        for prm in port.parameters():                        # raw scale of 0 is sigma = 0 under the abs link, which torch's
+            prm[prm == 0] = 1e-6                             # Normal rejects (the CUDA path floors sigma, common.cuh)
     opt = torch.optim.Adam(port.parameters(), lr=lr)
     step = lambda x, y, noise=None: vfm_port.sampled_port_step(port, opt, x, y, w.n_train, noise)
     return port, opt, step

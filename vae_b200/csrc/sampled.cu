@@ -108,7 +108,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                 float w_u = 0.f;
                 if (put.pe.n) {
                     n_req = bcast(len_l, sel); seg0 = bcast(seg0_l, sel); w_u = bcast(w_l, sel);
-                    if (u >= U || rowid >= put.n_real) n_req = 0;          // padding slots share a sentinel row
+                    if (sel >= nvalid || rowid >= put.n_real) n_req = 0;   // padding slots share a sentinel row
                 }
                 auto put_row = [&](int k, const Vec<VEC>& out) {
                     for (int i = 0; i < n_req; ++i) {
@@ -120,7 +120,7 @@ k_stage(DevCfg c, const float* __restrict__ bias, const float* __restrict__ enti
                     }
                 };
                 float kl = 0.f;
-                if (u < U) {
+                if (sel < nvalid) {                              // (a round can reach past the warp's chunk)
 #pragma unroll
                     for (int i = 0; i < NV; ++i) {
                         const int k = kc[i];
@@ -304,7 +304,7 @@ k_score(DevCfg c, const float* __restrict__ scalars, const int32_t* __restrict__
                     if (act[i]) {
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) part += 0.5f * (ssum[i].v[j] * ssum[i].v[j] - sq[i].v[j]);
-                        if (msg && n < B) st_vec<VEC>(msg + (size_t)n * d + kc[i], ssum[i]);   // S_n = sum_f v_f (unscaled)
+                        if (msg && sel < nvalid) st_vec<VEC>(msg + (size_t)n * d + kc[i], ssum[i]);   // S_n = sum_f v_f (unscaled)
                     }
                 part = group_sum<LPR>(part, 0xffffffffu);
                 hand_back<LPR>(inter_l, part, it, lane);
