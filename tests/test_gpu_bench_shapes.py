@@ -2,8 +2,11 @@
 3, 4, 5 at full batch size), through the code paths the benchmark takes:
 
 * config 3  ml20m      F = 2, d = 64,  B = 65 536, R = 165 237 -- Zipf head rows with thousands of
-                       occurrences per batch, so the hot-row branch of ``k_combine_cut``
-                       (``combine_hot_row``: rows spanning > 32 backward tiles) provably runs;
+                       occurrences per batch: they cross a dozen 512-position block tiles of ``k_gather``,
+                       so the shared-memory combine AND the global finisher (``finish_cut_row``) run;
+* hot3                 F = 2, d = 64, B = 65 536, an item field of THREE rows (~21 800 occurrences each =
+                       43 block tiles): the second level of the finisher's tree (rows spanning more than
+                       32 block tiles) provably runs;
 * config 5  d = 128    F = 2, B = 65 536, Zipf 1.05, table scaled to 300 000 rows (LPR = 32 lanes/row);
 * config 4  sideinfo   F = 8, d = 64, B = 65 536, R = 10^6, Bernoulli, pairwise interaction.
 
@@ -13,7 +16,7 @@ reference (``oracle/vfm_port.py``) for the F = 2 cases.  Two consecutive steps a
   step 1  injected noise (north_star's protocol): ``gradients`` and ``fused_step(noise=...)``;
   step 2  the benchmarked path -- in-kernel Philox noise, lean stage, KL / scalars / step counter
           folded into ``k_adam_rows``, both with and without a block slot reserved for the plan
-          (``k_score`` + ``k_gather`` vs the fused ``k_gather_score``) -- replayed in the oracle from
+          (grid sizes differ) -- replayed in the oracle from
           the GPU's exact state (p, m, v, t = 1) and the exported Philox draws.
 
 Tolerances (north_star: fp32 within 1e-5 relative): ELBO / KL rtol 1e-5; predictions rtol 1e-5 plus an
@@ -49,6 +52,11 @@ def _case(name):
         w = synth.make_workload("ml20m", n_rows=4 * B)
         fs, d, out, inter, kl = w.field_sizes, w.d, "reg", "prod", "torch"
         x, y = w.x, w.y
+    elif name == "hot3":
+        fs, d, out, inter, kl = [40_000, 3], 64, "reg", "prod", "torch"
+        rng = np.random.default_rng(5)
+        x = np.stack([synth.make_ids([fs[0]], [0.8], 4 * B)[:, 0], fs[0] + rng.integers(0, 3, 4 * B)], 1).astype(np.int64)
+        y = synth._ratings(np.random.default_rng(2), 4 * B)
     elif name == "d128":
         fs, d, out, inter, kl = [210_000, 90_000], 128, "reg", "prod", "torch"
         x = synth.make_ids(fs, [1.05, 1.05], 4 * B)
@@ -116,7 +124,7 @@ def _record(rec):
         fh.write(json.dumps(rec) + "\n")
 
 
-@pytest.mark.parametrize("name", ["ml20m", "d128", "sideinfo"])
+@pytest.mark.parametrize("name", ["ml20m", "d128", "sideinfo", "hot3"])
 def test_two_steps_at_benchmark_shape_match_oracle(name):
     from vae_b200 import _lib as L
     c = _case(name)
@@ -143,7 +151,9 @@ def test_two_steps_at_benchmark_shape_match_oracle(name):
     n_hot, n_cut = int(plan.meta[3].item()), int(plan.meta[5].item())
     rec.update(U0=U0, hot_rows=n_hot, cut_rows=n_cut, max_occurrences=int(ex["plan"]["counts"].max()))
     if name != "sideinfo":
-        assert n_hot > 0, "the hot-row branch (rows spanning > 32 backward tiles) must be exercised"
+        assert n_hot > 0, "rows spanning > 32 nominal tiles (1 024 occurrences) must be present"
+    if name == "hot3":
+        assert rec["max_occurrences"] > 32 * 512, "a row must span more than 32 block tiles (second finisher level)"
     assert np.array_equal(plan.as_unique()[0].cpu().numpy(), ex["plan"]["uniq"])
     np.testing.assert_allclose(gr["loss"].item(), ex["loss"], rtol=1e-5)
     _pred_close(gr["pred"].cpu().numpy(), ex["mean"].squeeze())
@@ -191,7 +201,7 @@ def test_two_steps_at_benchmark_shape_match_oracle(name):
     assert int(m.adam_step.item()) == 1
 
     # ------------------------------------------------------------ step 2: the benchmarked path (Philox)
-    for reserve in (1, 0):          # 1: k_score + k_gather (graphed bench);  0: fused k_gather_score (F = 2)
+    for reserve in (1, 0):          # 1: grids as in the graphed bench (one block slot per SM left to the plan);  0: full
         m2 = _model(c)
         m2.load_state_dict(m.state_dict())
         for dst, src in ((m2.entity_m, m.entity_m), (m2.entity_v, m.entity_v), (m2.bias_m, m.bias_m),
