@@ -215,7 +215,8 @@ int vfmb_sampled_backward(const vfmb_config* cfg, const vfmb_tables* tab, const 
  * runs them on different ranks with all-to-all exchanges in between; F may be 1 here):
  *   stage      k_stage       unique rows -> vs, ws, es, ebs, cq, KL sum       (needs plan->urec, z)
  *   score      k_score       samples -> pred, mean, resid, rsorted, msg       (needs vs, ws)
- *   gather     k_gather + k_combine -> grow, gws.  unit_coef != 0: rows of `table` are added
+ *   gather     k_gather      sorted occurrences -> grow, gws (rows cut by tile boundaries are finished in
+ *              the kernel).  unit_coef != 0: rows of `table` are added
  *              unscaled and gws sums io->rsorted -- the owner-side ordered sum of the
  *              gradient rows received from the other ranks (table [B*F, d])
  *   adam_rows  k_adam_rows   chain rule + KL gradient + Adam / dense gradients
@@ -409,11 +410,17 @@ int64_t vfmb_launch_count(void);
  * affects launches made after the call.  Default 0. */
 int vfmb_set_grid_reserve(int blocks_per_sm);
 
-/* Other process-wide launch knobs (host side only; results never depend on them -- every variant
- * is bitwise identical, tests/test_gpu_sampled.py): key = "grid_reserve" (as above), "fuse_score"
- * (-1 auto / 0 / 1: score the samples inside the backward's segmented reduction when F == 2),
- * "adam_reserve" (0 / 1), "adam_pipe" (1 / 0: cp.async-pipelined or register-staged row update), "prefetch_mv" (bit mask: which earlier phase of the fused step pulls the
- * Adam moments of the touched rows into L2 ahead of the row update). */
+/* Other process-wide launch knobs (host side only).  Bit-identical results whatever the value
+ * (tests/test_gpu_sampled.py): "grid_reserve" (as above), "adam_reserve" (0 / 1: the row update leaves the
+ * reserved slot free too), "adam_pipe" (1 / 0: cp.async-pipelined or register-staged row update), "l2_keep"
+ * (bit mask: rows of entity / m / v parked in L2 between the sampling kernel and the row update),
+ * "prefetch_mv" (bit mask: k_stage prefetches the Adam moments), "gather_dyn" (1 / 0: block tiles handed
+ * out by a counter or a fixed stride), "gather_fence" (1 / 0: fence.acq_rel or fence.sc in the cut-row
+ * finisher), "stage_wide" (0 / 1: lane mapping of k_stage), "stage_chunk" / "score_chunk" (16 / 32 units
+ * per warp pass), "pdl" (0 / 1: programmatic dependent launch along the kernel chains), "gather_keep"
+ * (closed-form gather: rows up to this many occurrences are never cut).  Another fixed association of one
+ * sum each (last-bit differences; set once per process): "gather_wide" (1 / 0), "score_wide" (-1 = when
+ * F > 2 / 0 / 1).  Defaults are the measured best.  Unknown keys are an error. */
 int vfmb_set_tuning(const char* key, int value);
 
 const char* vfmb_last_error(void);
