@@ -706,3 +706,93 @@ def test_training_loop_learns_and_metrics_path():
     assert auc1 > max(0.75, auc0 + 0.1), (auc0, auc1)
     ev = metrics.evaluate(m, xd[:2000], yd[:2000])
     assert set(ev) == {"auc", "map"} and 0.7 < ev["auc"].item() <= 1.0 and 0.5 < ev["map"].item() <= 1.0
+
+
+@pytest.mark.parametrize("output", ["reg", "class"])
+def test_epoch_level_metrics_equal_reference_loop(output):
+    """Two epochs of the script's loop (vfm-torch.py:347-384: model(x) -> loss -> backward -> dense Adam, the
+    epoch's train RMSE / AUC / MAP from the per-batch predictions, save_weights()) and its display block
+    (:402-422: sampled forward on the test set, RMSE / RMSE-all / RMSE of the last and of the epoch-mean
+    posterior, or AUC / MAP), run on the drop-in module with the metrics of vae_b200.metrics on the device,
+    against the same loop on the reference restatement with sklearn's metrics -- same noise injected."""
+    from sklearn.metrics import average_precision_score, mean_squared_error, roc_auc_score
+
+    from oracle import vfm_port
+    from vae_b200 import metrics
+    from vae_b200.vfm_torch import CF
+    N, M, d, B, n_train, n_test, lr = 80, 50, 8, 256, 1024, 300, 0.02
+    rng = np.random.default_rng(21)
+    x = np.stack([rng.integers(0, N, n_train + n_test), N + rng.integers(0, M, n_train + n_test)], 1).astype(np.int64)
+    y = np.clip(np.round(3.5 + rng.standard_normal(len(x))), 1, 5).astype(np.float32)
+    if output == "class":
+        y = (y >= 4).astype(np.float32)
+    xtr, ytr, xte, yte = x[:n_train], y[:n_train], x[n_train:], y[n_train:]
+    tc = np.bincount(xtr.reshape(-1), minlength=N + M)
+    tc[tc == 0] = 1
+    torch.manual_seed(5)
+    port = vfm_port.SampledPort(N, M, d, torch.from_numpy(tc), output=output, faithful_cost=False)
+    m = CF(d, output=output, n_users=N, n_items=M, train_counts=torch.from_numpy(tc), n_train=n_train,
+           max_batch=max(B, n_test), lr=lr, device=DEV)
+    own = m.state_dict()
+    m.load_state_dict({k: v.to(DEV).reshape(own[k].shape) for k, v in port.state_dict().items() if k in own}, strict=False)
+    opt_m, opt_p = torch.optim.Adam(m.parameters(), lr=lr), torch.optim.Adam(port.parameters(), lr=lr)
+    gen = torch.Generator().manual_seed(9)
+
+    def draw(xb):
+        U = len(np.unique(xb))
+        return [torch.randn(1, 1, generator=gen), torch.randn(1, U, generator=gen), torch.randn(1, U, d, generator=gen)]
+
+    saved = []                                               # the port's save_weights() (vfm-torch.py:179-185)
+    all_m, all_p = [], []
+    xte_d, yte_d = torch.from_numpy(xte).to(DEV), torch.from_numpy(yte).to(DEV)
+    for epoch in range(2):
+        pred_m, pred_p = [], []
+        for lo in range(0, n_train, B):
+            xb, yb = xtr[lo:lo + B], ytr[lo:lo + B]
+            noise = draw(xb)
+            lik, _, _, kl = m(torch.from_numpy(xb).to(DEV), noise=[n.to(DEV) for n in noise])
+            loss = -lik.log_prob(torch.from_numpy(yb).to(DEV)).mean() * n_train + kl
+            pred_m.append(lik.mean.squeeze().detach())
+            opt_m.zero_grad()
+            loss.backward()
+            opt_m.step()
+            po = vfm_port.sampled_port_step(port, opt_p, torch.from_numpy(xb), torch.from_numpy(yb), n_train, noise)
+            pred_p.extend(po["pred"].numpy().tolist())
+            np.testing.assert_allclose(loss.item(), po["loss"].item(), rtol=2e-5)
+        pm, truth_d = torch.cat(pred_m), torch.from_numpy(ytr).to(DEV)
+        if output == "reg":
+            m.save_weights()
+            saved.append((port.global_bias_mean.detach().numpy().copy(), port.bias_params.weight[:, 0].detach().numpy().copy(),
+                          port.entity_params.weight[:, :d].detach().numpy().copy()))
+            want = mean_squared_error(ytr, np.clip(pred_p, 1, 5)) ** 0.5
+            np.testing.assert_allclose(metrics.rmse(truth_d, pm, clip=(1, 5)).item(), want, rtol=1e-5)
+        else:
+            np.testing.assert_allclose(metrics.roc_auc(truth_d, pm).item(), roc_auc_score(ytr, pred_p), rtol=1e-5)
+            np.testing.assert_allclose(metrics.average_precision(truth_d, pm).item(), average_precision_score(ytr, pred_p), rtol=1e-5)
+        # display block: a sampled forward on the test set
+        noise = draw(xte)
+        with torch.no_grad():
+            lik_p, _, _ = port(torch.from_numpy(xte), noise)
+            yp = lik_p.mean.squeeze().numpy()
+
+            class _Injected:                                 # evaluate() calls model(x_test): inject the same draws
+                output = m.output
+
+                def __call__(self, xq):
+                    return m(xq, noise=[n.to(DEV) for n in noise])
+            ev = metrics.evaluate(_Injected(), xte_d, yte_d, all_preds=all_m)
+        if output == "reg":
+            all_p.append(np.clip(yp, 1, 5).tolist())
+            gb, bm, em = saved[-1]
+            last = gb + bm[xte].sum(axis=1) + em[xte].prod(axis=1).sum(axis=1)
+            mgb, mbm, mem = (np.mean([s[i] for s in saved], axis=0) for i in range(3))
+            mean_l = mgb + mbm[xte].sum(axis=1) + mem[xte].prod(axis=1).sum(axis=1)
+            want = {"rmse": mean_squared_error(yte, np.clip(yp, 1, 5)) ** 0.5,
+                    "rmse_all": mean_squared_error(yte, np.array(all_p).mean(axis=0)) ** 0.5,
+                    "rmse_of_last": mean_squared_error(yte, last) ** 0.5,
+                    "rmse_of_mean": mean_squared_error(yte, np.clip(mean_l, 1, 5)) ** 0.5}
+        else:
+            want = {"auc": roc_auc_score(yte, yp), "map": average_precision_score(yte, yp)}
+        assert set(ev) == set(want), (sorted(ev), sorted(want))
+        for k, v in want.items():
+            np.testing.assert_allclose(ev[k].item(), v, rtol=2e-5, err_msg=f"epoch {epoch} {k}")

@@ -131,3 +131,46 @@ def test_golden_files_are_current():
     out = ref_slice.sampled_step(ref, opt, torch.from_numpy(x), torch.from_numpy(y), meta["n_train"], noise)
     np.testing.assert_allclose(out["loss"].numpy(), g["step0.loss"], rtol=1e-6)
     np.testing.assert_allclose(out["pred"].numpy(), g["step0.pred"], rtol=1e-6)
+
+
+def test_data_loading_equals_reference_prepare_py(tmp_path, monkeypatch):
+    """vae_b200.data.load_data == the reference's prepare_data + load_data (prepare.py:10-62), executed
+    live on a raw ratings file: ids re-indexed to 0..N-1 / 0..M-1, items shifted by N, fold files
+    honoured, 'outcome' = rating >= 4, libFM export lines."""
+    import importlib.util
+    import os
+    import shutil
+
+    import pandas as pd
+
+    from vae_b200 import data
+    rng = np.random.default_rng(3)
+    n = 400
+    raw = pd.DataFrame({"user": rng.choice([3, 7, 8, 15, 21, 22, 40, 41, 97], n),
+                        "item": rng.choice([100, 101, 105, 230, 231, 999], n),
+                        "rating": rng.integers(1, 6, n)})
+    perm = rng.permutation(n)
+    ours_dir = tmp_path / "ours"
+    ref_dir = tmp_path / "data" / "toybinary"
+    for d in (ours_dir, ref_dir):
+        os.makedirs(d)
+        raw.assign(outcome=(raw["rating"] >= 4).astype(int)).to_csv(d / "data.csv", index=False) if d is ours_dir \
+            else raw.to_csv(d / "data.csv", index=False)
+        pd.DataFrame({"index": np.sort(perm[:320])}).to_csv(d / "trainval.csv", index=False)
+        pd.DataFrame({"index": np.sort(perm[320:])}).to_csv(d / "test.csv", index=False)
+    spec = importlib.util.spec_from_file_location("ref_prepare", os.path.join(ref_slice.REFERENCE_DIR, "prepare.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    monkeypatch.chdir(tmp_path)                              # the reference reads ./data/<name>/
+    ref.prepare_data("toybinary", True)                      # rewrites data.csv, writes the libFM files
+    for output in ("class", "reg"):
+        N, M, X_train, X_test, y_train, y_test, folds = ref.load_data("toybinary", output)
+        got = data.load_data(str(ours_dir), output)
+        assert (got.n_users, got.n_items) == (N, M)
+        assert np.array_equal(got.x_train, X_train) and np.array_equal(got.x_test, X_test)
+        assert np.array_equal(got.y_train, y_train.astype(np.float32)) and np.array_equal(got.y_test, y_test.astype(np.float32))
+        assert np.array_equal(got.folds["trainval"], folds["trainval"]) and np.array_equal(got.folds["test"], folds["test"])
+    got = data.load_data(str(ours_dir), "class")
+    data.write_libfm(str(tmp_path / "ours.libfm"), got.x_test, got.y_test.astype(int))
+    assert (tmp_path / "ours.libfm").read_text() == (ref_dir / "toybinary.test_libfm").read_text()
+    shutil.rmtree(tmp_path / "data")
