@@ -1,14 +1,15 @@
 // Sampled-ELBO VFM step (vfm-torch.py:189-324 forward, :359 loss, :368-370 backward + Adam).
 //
 // Four launches per fused training step (S = 1), all HBM/L2-bound (no dense contraction on this path):
-//   k_stage      one lane group per UNIQUE row: gather [mean|raw scale], draw eps (Philox or
-//                injected), write the sampled row v = mu + eps*|rho| and bias w to an L2-resident
+//   k_stage      one lane group per UNIQUE row (16 / 32 rows per warp pass): gather [mean|raw scale], draw
+//                eps (Philox or injected), write the sampled row v = mu + eps*|rho| and bias w to an L2-resident
 //                scratch (+ the count-rescaled KL when not fused).   (vfm-torch.py:207-241, 290-317)
-//   k_score      one lane group per SAMPLE: FM interaction of the sampled rows, likelihood,
+//   k_score      one lane group per SAMPLE (32 per warp pass): FM interaction of the sampled rows, likelihood,
 //                residual dloss/dpred.                                (vfm-torch.py:244-270, 359)
 //   k_gather     ordered segmented sum of residual * partner row over the sorted occurrence list,
-//                tiled by position; the group that stores the last partial of a row cut by tile
-//                boundaries adds the row's partials in tile order (finish_cut_row).
+//                in 512-position block tiles; rows cut inside a block are combined through shared memory,
+//                rows cut by block-tile boundaries by the group that stores their last partial
+//                (finish_cut_row), in tile order.
 //   k_adam_rows  per unique row: chain rule to (mu, rho) + KL gradient + Adam; FLAVOR 2 also forms
 //                the KL and recomputes the Philox draws; the last block updates the scalar
 //                parameters (alpha, global bias) and the step counter.

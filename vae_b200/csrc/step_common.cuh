@@ -184,9 +184,10 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g,
 // the step: parameters and both Adam moments of every touched row are read and written once.
 
 // ------------------------------------------------------------------------------- cut rows
-// The backward's segmented reduction (k_gather / k_cgather) walks the sorted
-// occurrence list in tiles of kTile positions (tile_span below: rows of up to kTile occurrences are kept
-// whole).  A longer row is cut by the tile boundaries and leaves one partial per
+// The backward's segmented reduction walks the sorted occurrence list in tiles: k_gather in block tiles
+// of 512 positions (rows cut inside a block never get here: shared memory), k_cgather in tiles of kTile
+// positions (tile_span below: rows of up to `keep` occurrences are kept whole).  A row cut by the tile
+// boundaries leaves one partial per
 // tile it touches: in the tail slot of its first tile, in the head slots of the following ones.
 // The lane group that stores the LAST partial adds them -- no separate combine launch (12 us of
 // pure latency on the ml20m step in round 1).  To keep that serial sum short for a Zipf head row
