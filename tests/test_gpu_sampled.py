@@ -796,3 +796,60 @@ def test_epoch_level_metrics_equal_reference_loop(output):
         assert set(ev) == set(want), (sorted(ev), sorted(want))
         for k, v in want.items():
             np.testing.assert_allclose(ev[k].item(), v, rtol=2e-5, err_msg=f"epoch {epoch} {k}")
+
+
+@pytest.mark.parametrize("F,d,B,hot", [
+    (2, 4, 1, 0), (2, 5, 33, 1), (2, 12, 511, 1), (2, 16, 512, 0), (2, 20, 513, 1), (2, 32, 1025, 1),
+    (2, 64, 2049, 1), (2, 100, 777, 1), (2, 128, 1536, 1), (2, 256, 600, 1), (3, 8, 257, 1), (5, 36, 1000, 1),
+    (8, 128, 300, 0)])
+def test_gradients_on_ragged_shapes_match_fp64_maths(F, d, B, hot):
+    """Every lane layout (d = 4 ... 256: 4 / 8 / 16 / 32 lanes per row, one or two vectors per lane, the scalar
+    layout for d % 4 != 0), batch sizes around the gather's group- and block-tile sizes (B * F = 1 ... 4 098
+    positions: empty groups, a last short tile, several block tiles), with and without a row that takes a
+    third of all occurrences (cut by group tiles, block tiles, or both): gradients, loss and predictions of
+    one step against the fp64 maths, and the fused update against torch's Adam recurrence on those gradients."""
+    from vae_b200.vfm_torch import CF
+    fs = [max(3, 40 - 4 * f) for f in range(F)]
+    R = sum(fs)
+    rng = np.random.default_rng(1000 * F + d + B)
+    offs = np.concatenate(([0], np.cumsum(fs)[:-1]))
+    x = np.stack([offs[f] + rng.integers(0, fs[f], B) for f in range(F)], 1).astype(np.int64)
+    if hot:
+        x[rng.random(B) < 0.33, F - 1] = offs[F - 1]          # one row of the last field in a third of the samples
+    out = "reg" if d % 8 else "class"
+    y = rng.normal(3.0, 1.0, B).astype(np.float32) if out == "reg" else (rng.random(B) < 0.5).astype(np.float32)
+    tc = np.bincount(x.reshape(-1), minlength=R)
+    tc[tc == 0] = 1
+    kl = "torch" if F == 2 else "group"
+    inter = "prod" if F == 2 else "pairwise"
+    torch.manual_seed(17)
+    lr = 0.01
+    m = CF(d, output=out, n_users=fs[0], n_items=fs[1], train_counts=torch.from_numpy(tc), field_sizes=fs,
+           kl_weighting=kl, n_train=4 * B, max_batch=B, lr=lr)
+    with torch.no_grad():
+        m.entity_params.weight.mul_(0.5 if F == 2 else 0.25)
+    sd = {k: v.cpu().numpy() for k, v in m.state_dict().items()}
+    uniq = np.unique(x)
+    U = len(uniq)
+    gen = torch.Generator().manual_seed(3)
+    noise = [torch.randn(1, 1, generator=gen), torch.randn(1, U, generator=gen), torch.randn(1, U, d, generator=gen)]
+    ex = vfm_math.sampled_step(gu.sampled_math_params(sd), x, y, [n.numpy() for n in noise], tc, 4 * B, fs,
+                               output=out, interaction=inter, kl_weighting=kl)
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    nd = [n.to(DEV) for n in noise]
+    gr = m.gradients(xd, yd, noise=nd)
+    np.testing.assert_allclose(gr["loss"].item(), ex["loss"], rtol=1e-5)
+    want = ex["mean"].squeeze().reshape(-1)
+    np.testing.assert_allclose(gr["pred"].cpu().numpy().reshape(-1), want, rtol=1e-5,
+                               atol=2e-6 + 1e-6 * float(np.sqrt(np.mean(want ** 2))))
+    assert gu.rel_err(gr["entity_params.weight"].cpu().numpy(), ex["grads"]["entity"]) < 1e-5
+    assert gu.rel_err(gr["bias_params.weight"].cpu().numpy(), ex["grads"]["bias"]) < 1e-5
+    m.fused_step(xd, yd, noise=nd)
+    g64 = ex["grads"]["entity"][uniq]
+    step1 = sd["entity_params.weight"][uniq] - lr * g64 / (np.abs(g64) + 1e-8)      # Adam, t = 1, zero moments
+    got = m.entity_params.weight.detach().cpu().numpy()[uniq]
+    err = np.abs(got - step1)
+    bad = err > 1e-5 * np.abs(step1) + 1e-4 * lr
+    rowmax = np.abs(g64).max(axis=1, keepdims=True)
+    assert bad.mean() <= 1e-3 and (not bad.any() or (np.abs(g64) / np.maximum(rowmax, 1e-300))[bad].max() < 1e-3), \
+        (float(bad.mean()), float(err.max() / lr))
